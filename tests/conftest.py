@@ -1,0 +1,50 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def load_meta(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def golden_state(model_key, meta_file="models.json", calib=True):
+    """State dict for a golden model fixture: name-keyed synthetic weights (+ calibrated BN stats)."""
+    from stereo_toolbox_b200.synth import synth_state_dict, state_checksum
+    meta = load_meta(meta_file)[model_key]
+    template = {k: torch.zeros(s, dtype=torch.int64 if k.endswith("num_batches_tracked") else torch.float32)
+                for k, s in meta["keys"].items()}
+    over = None
+    if calib:
+        z = np.load(os.path.join(GOLDEN, f"bn_calib_{model_key}.npz"))
+        over = {k: z[k] for k in z.files}
+    sd = synth_state_dict(template, 0, over)
+    assert abs(state_checksum(sd) - meta["checksum"]) <= 1e-6 * abs(meta["checksum"]), "synthetic weights drifted"
+    return sd, meta

@@ -1,0 +1,190 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by RUNNING THE REFERENCE ITSELF.
+
+Runs only in the build container (needs /root/reference, read-only).  The reference is
+imported with the stub recipe of SURVEY.md section 8c (its ``models/__init__.py`` pulls in timm /
+opt_einsum, which are absent).  Inputs are seeded; both inputs and reference outputs are
+stored, so the fixtures do not depend on RNG reproducibility.  Model fixtures store only the
+input seed, the weight checksum and the outputs (weights come from
+``stereo_toolbox_b200.synth.synth_state_dict``, keyed by parameter name).
+
+    python tests/golden/make_golden.py
+"""
+import importlib
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+import stereo_toolbox  # noqa: E402  (empty __init__)
+
+_m = types.ModuleType("stereo_toolbox.models")
+_m.__path__ = ["/root/reference/stereo_toolbox/models"]
+sys.modules["stereo_toolbox.models"] = _m
+_oe = types.ModuleType("opt_einsum")
+_oe.contract = None
+sys.modules["opt_einsum"] = _oe
+sys.modules.setdefault("timm_0_5_4", types.ModuleType("timm_0_5_4"))
+
+from stereo_toolbox_b200.synth import synth_state_dict, state_checksum, synth_pair  # noqa: E402
+
+
+def ref(mod):
+    return importlib.import_module("stereo_toolbox.models." + mod)
+
+
+def rnd(seed, *shape):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+@torch.no_grad()
+def ops():
+    gsub = ref("GwcNet.submodule")
+    asub = ref("ACVNet.submodule")
+    psub = ref("PSMNet.submodule")
+    out = {}
+    # --- volumes
+    L, R = rnd(1, 2, 16, 5, 23), rnd(2, 2, 16, 5, 23)
+    out.update(gwc_L=L, gwc_R=R, gwc_out=gsub.build_gwc_volume(L, R, 9, 4))
+    L8, R8 = rnd(3, 1, 24, 4, 12), rnd(4, 1, 24, 4, 12)
+    out.update(gwc8_L=L8, gwc8_R=R8, gwc8_out=ref("IGEVStereo.submodule").build_gwc_volume(L8, R8, 6, 8))
+    cl, cr = rnd(5, 2, 3, 5, 23), rnd(6, 2, 3, 5, 23)
+    out.update(cat_L=cl, cat_R=cr, catA_out=gsub.build_concat_volume(cl, cr, 9),
+               catB_out=asub.build_concat_volume(cl, cr, 9))
+    att = rnd(7, 2, 1, 9, 5, 23)
+    out.update(att=att, acv_out=torch.softmax(att, dim=2) * out["catB_out"])
+    # --- head
+    cost = rnd(8, 2, 1, 6, 5, 7) * 3
+    import torch.nn.functional as F
+    for ac in (False, True):
+        up = F.interpolate(cost, [24, 20, 28], mode="trilinear", align_corners=ac)
+        out[f"up_{int(ac)}"] = up[:, 0]
+        prob = F.softmax(up[:, 0], dim=1)
+        out[f"head_{int(ac)}"] = gsub.disparity_regression(prob, 24)
+    out["head_cost"] = cost
+    out["head_keepdim"] = psub.disparityregression(24)(F.softmax(out["up_0"], dim=1))
+    # IGEV style: no upsampling, keepdim
+    c4 = rnd(9, 2, 12, 5, 7)
+    out.update(sam_cost=c4, sam_out=ref("IGEVStereo.submodule").disparity_regression(F.softmax(c4, dim=1), 12))
+    save("ops_volume_head.npz", **out)
+
+    # --- 1-D correlation (RAFT)
+    out = {}
+    corr_mod = ref("RAFTStereo.corr")
+    f1, f2 = rnd(10, 2, 8, 3, 32), rnd(11, 2, 8, 3, 32)
+    blk = corr_mod.CorrBlock1D(f1, f2, num_levels=4, radius=4)
+    g = torch.Generator().manual_seed(12)
+    coords = torch.arange(32.0).view(1, 1, 1, 32).repeat(2, 2, 3, 1)
+    coords[:, 0] += (torch.rand(2, 3, 32, generator=g) - 0.5) * 48  # includes out-of-range taps
+    out.update(f1=f1, f2=f2, coords=coords, corr=corr_mod.CorrBlock1D.corr(f1, f2)[:, :, :, 0],
+               lookup=blk(coords))
+    for i, p in enumerate(blk.corr_pyramid):
+        out[f"pyr{i}"] = p.reshape(2, 3, 32, -1)
+    # --- IGEV geometry
+    geo_mod = ref("IGEVStereo.geometry")
+    m1, m2, gv = rnd(13, 1, 8, 3, 16), rnd(14, 1, 8, 3, 16), rnd(15, 1, 4, 8, 3, 16)
+    geo = geo_mod.Combined_Geo_Encoding_Volume(m1, m2, gv, num_levels=2, radius=4)
+    disp = torch.rand(1, 1, 3, 16, generator=g) * 10 - 1
+    cx = torch.arange(16.0).view(1, 1, 1, 16).repeat(1, 1, 3, 1)
+    out.update(geo_m1=m1, geo_m2=m2, geo_vol=gv, geo_disp=disp, geo_coords=cx, geo_out=geo(disp, cx))
+    save("ops_corr.npz", **out)
+
+
+def _load_synth(model, seed=0, calib=None, calib_name=None):
+    """Name-keyed synthetic weights; with ``calib`` (a left/right pair) the BatchNorm running
+    statistics are then replaced by the batch statistics of one reference forward in train mode
+    (momentum=None -> exact batch mean / unbiased var), so that every BN really normalises and
+    activations stay O(1) like in a trained network.  The calibrated statistics are saved as
+    ``bn_calib_<name>.npz`` and re-used by tests and bench.py."""
+    sd = synth_state_dict(model.state_dict(), seed)
+    model.load_state_dict(sd, strict=True)
+    if calib is not None:
+        bns = [m for m in model.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+        for m in bns:
+            m.reset_running_stats()
+            m.momentum = None
+        model.train()
+        model(*calib)
+        for m in bns:
+            m.momentum = 0.1
+            m.num_batches_tracked.zero_()
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        save(f"bn_calib_{calib_name}.npz", **{k: v for k, v in sd.items()
+                                               if k.endswith("running_mean") or k.endswith("running_var")})
+    model.eval()
+    return sd
+
+
+def _keys(sd):
+    return {k: list(v.shape) for k, v in sd.items()}
+
+
+@torch.no_grad()
+def blocks():
+    """One hourglass of each flavour: conv / strided conv / transposed conv / BN fold / residual order."""
+    out, meta = {}, {}
+    hg = ref("GwcNet.gwcnet").hourglass(8)
+    sd = _load_synth(hg)
+    x = rnd(20, 1, 8, 8, 12, 16)
+    out.update(gwc_hg_x=x, gwc_hg_y=hg(x))
+    meta["gwc_hg"] = dict(keys=_keys(sd), checksum=state_checksum(sd))
+    ph = ref("PSMNet.stackhourglass").hourglass(8)
+    sd = _load_synth(ph)
+    y, pre, post = ph(x, None, None)
+    y2, pre2, post2 = ph(x, pre, post)
+    out.update(psm_hg_y=y, psm_hg_pre=pre, psm_hg_post=post, psm_hg_y2=y2, psm_hg_pre2=pre2, psm_hg_post2=post2)
+    meta["psm_hg"] = dict(keys=_keys(sd), checksum=state_checksum(sd))
+    save("blocks.npz", **out)
+    json.dump(meta, open(os.path.join(HERE, "blocks.json"), "w"))
+
+
+@torch.no_grad()
+def models():
+    meta = {}
+    # GwcNet_GC, d=32, 64x128 pair  (volume [1,64,8,16,32])
+    calib = synth_pair(2, 64, 128, seed=100, shift=3)
+    net = ref("GwcNet.gwcnet").GwcNet_GC(32)
+    sd = _load_synth(net, calib=calib, calib_name="gwcnet_gc")
+    left, right = synth_pair(1, 64, 128, seed=0, shift=5)
+    cap = {}
+    net.classif3.register_forward_hook(lambda m, i, o: cap.__setitem__("cost3", o))
+    net.dres0.register_forward_hook(lambda m, i, o: cap.__setitem__("dres0", o))
+    disp = net(left, right)
+    save("gwcnet_gc.npz", disp=disp, cost3=cap["cost3"], dres0=cap["dres0"])
+    meta["gwcnet_gc"] = dict(keys=_keys(sd), checksum=state_checksum(sd), maxdisp=32, shape=[1, 64, 128], shift=5)
+    net = ref("GwcNet.gwcnet").GwcNet_G(32)
+    sd = _load_synth(net, calib=calib, calib_name="gwcnet_g")
+    save("gwcnet_g.npz", disp=net(left, right))
+    meta["gwcnet_g"] = dict(keys=_keys(sd), checksum=state_checksum(sd), maxdisp=32, shape=[1, 64, 128], shift=5)
+    # PSMNet, maxdisp=32, 256x256 (SPP needs H/4 >= 64)
+    net = ref("PSMNet.stackhourglass").PSMNet(32)
+    sd = _load_synth(net, calib=synth_pair(2, 256, 256, seed=101, shift=4), calib_name="psmnet")
+    left, right = synth_pair(1, 256, 256, seed=1, shift=7)
+    cap = {}
+    net.classif3.register_forward_hook(lambda m, i, o: cap.__setitem__("c3", o))
+    disp = net(left, right)
+    save("psmnet.npz", disp=disp, classif3=cap["c3"][:, :, :, ::4, ::4])
+    meta["psmnet"] = dict(keys=_keys(sd), checksum=state_checksum(sd), maxdisp=32, shape=[1, 256, 256], shift=7)
+    json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ["ops", "blocks", "models"]
+    for w in which:
+        globals()[w]()
