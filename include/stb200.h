@@ -1,0 +1,126 @@
+/*
+ * stb200.h -- C ABI of libstb200.so: hand-written sm_100a CUDA kernels for the cost-volume hot
+ * path of xxxupeng/stereo_toolbox.
+ *
+ * The reference has no FFI / plugin boundary for this path: it is reached through ordinary
+ * Python calls into torch.  Each entry point below therefore names the reference *function*
+ * (file:line under /root/reference/stereo_toolbox/models/) whose arithmetic it replaces; the
+ * Python binding that the toolbox-side maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless noted
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered and re-entrant,
+ *     allocates nothing and keeps no global state (tensor maps are built per call on the host)
+ *   - return value: 0 = ok; <0 = STB_E_* (the Python wrapper raises RuntimeError with
+ *     stb_error_string()); a CUDA launch error is returned as -(1000 + cudaError_t)
+ *   - fp32 tensors are NCDHW / NCHW contiguous exactly like the reference's; the bf16 fast path
+ *     uses channels-last NDHWC (documented per function)
+ */
+#ifndef STB200_H
+#define STB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STB_OK 0
+#define STB_E_BADARG (-1)
+#define STB_E_UNSUPPORTED (-2)
+#define STB_E_SMEM (-3)
+#define STB_E_DRIVER (-4)
+
+/* activation codes (epilogue of the conv family) */
+#define STB_ACT_NONE 0
+#define STB_ACT_RELU 1
+#define STB_ACT_LEAKY 2   /* LeakyReLU(0.01), IGEVStereo/submodule.py:36 */
+#define STB_ACT_MISH 3    /* x*tanh(softplus(x)), CFNet/submodule.py:99-106 */
+
+const char* stb_error_string(int code);
+int stb_version(void);
+
+/* ---- cost-volume builders (fp32, NCDHW out) ------------------------------------------------
+ * build_gwc_volume: GwcNet/submodule.py:53-63 (+ACVNet:228-238, CFNet:171-181, PCWNet:109-119,
+ * IGEVStereo:161-171) incl. groupwise_correlation :44-50.
+ *   vol[b, c_off+g, d, h, w] = mean_c L[b,g*k+c,h,w] * R[b,g*k+c,h,w-d]   (w>=d), else 0
+ * `vol` has c_total channels; only channels [c_off, c_off+G) are written (lets GwcNet_GC build
+ * gwc+concat into one buffer instead of torch.cat, GwcNet/gwcnet.py:180). */
+int stb_gwc_volume_f32(const float* left, const float* right, float* vol,
+                       int B, int C, int H, int W, int D, int G, int c_total, int c_off, void* stream);
+
+/* build_concat_volume: variant A (mask_left=1) GwcNet/submodule.py:30-41, CFNet:141-152,
+ * PCWNet:86-97, inline PSMNet/stackhourglass.py:111-120; variant B (mask_left=0)
+ * ACVNet/submodule.py:180-191, IGEVStereo/submodule.py:208-219.
+ * Writes channels [c_off, c_off+2C) of a c_total-channel volume.
+ * att_prob (nullable): [B,1,D,H,W] probabilities = softmax_d(att_weights) from stb_softmax_d_f32;
+ * when given every written value is multiplied by it -- ACVNet/acv.py:196 fused into the build. */
+int stb_concat_volume_f32(const float* left, const float* right, const float* att_prob, float* vol,
+                          int B, int C, int H, int W, int D, int mask_left, int c_total, int c_off,
+                          void* stream);
+
+/* F.softmax(x, dim=D axis) of a [B,D,plane] tensor (ACVNet/acv.py:196, plane = H*W). */
+int stb_softmax_d_f32(const float* x, float* y, int B, int D, long long plane, void* stream);
+
+/* ---- head: F.upsample(trilinear) + softmax over D + disparity_regression, fused -------------
+ * GwcNet/gwcnet.py:220-223 + GwcNet/submodule.py:23-27; PSMNet/stackhourglass.py:150-156;
+ * align_corners=1: CFNet/cfnet.py:605-613, PCWNet/pcwnet.py:486.  With out sizes equal to the
+ * input sizes it is the plain softmax+regression of IGEVStereo/igev_stereo.py:212-213.
+ * cost [B,D,H,W] fp32  ->  disp [B,outH,outW] fp32 ; the [B,outD,outH,outW] tensor is never
+ * materialised. */
+int stb_upsample_softargmin_f32(const float* cost, float* disp, int B, int D, int H, int W,
+                                int outD, int outH, int outW, int align_corners, void* stream);
+
+/* disparity_regression on an explicit probability volume: GwcNet/submodule.py:23-27,
+ * PSMNet/submodule.py:46-54.  prob [B,D,plane] -> disp [B,plane], disp = sum_d d*prob[d]. */
+int stb_disparity_regression_f32(const float* prob, float* disp, int B, int D, long long plane, void* stream);
+
+/* ---- 3-D convolution family, exact fp32 path (CUDA cores) ------------------------------------
+ * convbn_3d (+ReLU/Mish/LeakyReLU, + residual before the activation): PSMNet/submodule.py:16-19,
+ * GwcNet/gwcnet.py:72-105; ConvTranspose3d(k3,s2,p1,op1) PSMNet/stackhourglass.py:25-29;
+ * k4 s2 p1 IGEVStereo/igev_stereo.py:43-50.  One call computes
+ *   out[b,co, jd*os+od0, jh*os+oh0, jw*os+ow0] =
+ *       act( sum_t sum_ci wt[t][ci][co] * x[b,ci, jd*is+dd[t], jh*is+dh[t], jw*is+dw[t]]
+ *            + shift[co] + residual[same index] )            for (jd,jh,jw) in [0,nd)x[0,nh)x[0,nw)
+ * with zero padding outside x.  A strided conv is is=2; a transposed conv is one call per output
+ * parity class (os=2).  wt is the tap-major repack [ntaps][Cin][Cout] (BN scale pre-multiplied),
+ * dd/dh/dw are HOST arrays of ntaps offsets (ntaps <= 64).  x [B,Cin,Di,Hi,Wi], out/residual
+ * [B,Cout,Do,Ho,Wo], all fp32 NCDHW. shift/residual may be NULL. */
+int stb_conv3d_taps_f32(const float* x, const float* wt, const float* shift, const float* residual,
+                        float* out, int B, int Cin, int Di, int Hi, int Wi, int Cout, int Do, int Ho,
+                        int Wo, int ntaps, const int* dd, const int* dh, const int* dw, int in_stride,
+                        int out_stride, int od0, int oh0, int ow0, int nd, int nh, int nw, int act,
+                        void* stream);
+
+/* ---- 1-D all-pairs correlation + pyramid + lookup --------------------------------------------
+ * CorrBlock1D.corr (RAFTStereo/corr.py:148-156, scale=1/sqrt(C)) and
+ * Combined_Geo_Encoding_Volume.corr (IGEVStereo/geometry.py:62-70, scale=1).
+ * f1 [B,C,H,W1], f2 [B,C,H,W2] fp32 -> corr [B,H,W1,W2] fp32 (level 0), corr *= scale. */
+int stb_corr1d_f32(const float* f1, const float* f2, float* corr, int B, int C, int H, int W1, int W2,
+                   float scale, void* stream);
+
+/* F.avg_pool2d(x,[1,2],stride=[1,2]) along the last axis (RAFTStereo/corr.py:123-125,
+ * IGEVStereo/geometry.py:24-30): src [rows, Wsrc] -> dst [rows, Wsrc/2]. */
+int stb_avgpool_last_f32(const float* src, float* dst, long long rows, int Wsrc, void* stream);
+
+/* CorrBlock1D.__call__ (RAFTStereo/corr.py:127-146) with bilinear_sampler
+ * (RAFTStereo/utils/utils.py:59-74): all levels x (2r+1) taps in one launch.
+ * pyr[l] (HOST array of device pointers) [B,H,W1,W2>>l]; coords_x [B,H,W1] (channel 0 of the
+ * coords tensor); out [B, levels*(2r+1), H, W1] fp32. Out-of-range taps contribute 0. */
+int stb_corr1d_lookup_f32(const float* const* pyr, const float* coords_x, long long coords_bstride,
+                          float* out, int B, int H, int W1, int W2, int levels, int radius, void* stream);
+
+/* Combined_Geo_Encoding_Volume.__call__ (IGEVStereo/geometry.py:35-59).
+ * geo[l] [B,H,W,C,D>>l], corr[l] [B,H,W,W2>>l] (HOST arrays of device pointers);
+ * disp, coords_x [B,H,W]; out [B, levels*(2r+1)*(C+1), H, W]. */
+int stb_geo_lookup_f32(const float* const* geo, const float* const* corr, const float* disp,
+                       const float* coords_x, float* out, int B, int H, int W, int C, int D, int W2,
+                       int levels, int radius, void* stream);
+
+/* geo volume [B,C,D,H,W] -> [B,H,W,C,D] (IGEVStereo/geometry.py:19). */
+int stb_geo_permute_f32(const float* src, float* dst, int B, int C, int D, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STB200_H */

@@ -1,0 +1,12 @@
+"""stereo_toolbox_b200 -- Blackwell-native (sm_100a) cost-volume hot path behind the model API of
+xxxupeng/stereo_toolbox.  See DESIGN.md for scope, INTEGRATION.md for the drop-in recipe."""
+from .functional import (build_gwc_volume, build_concat_volume, build_concat_volume_unmasked,
+                         groupwise_correlation, disparity_regression, disparityregression,
+                         upsample_softargmin, CorrBlock1D, Combined_Geo_Encoding_Volume)
+from .gwcnet import GwcNet_G, GwcNet_GC
+from .psmnet import PSMNet
+from .checkpoint import load_checkpoint_flexible
+
+__all__ = ["build_gwc_volume", "build_concat_volume", "build_concat_volume_unmasked", "groupwise_correlation",
+           "disparity_regression", "disparityregression", "upsample_softargmin", "CorrBlock1D",
+           "Combined_Geo_Encoding_Volume", "GwcNet_G", "GwcNet_GC", "PSMNet", "load_checkpoint_flexible"]

@@ -1,0 +1,84 @@
+"""ctypes binding of libstb200.so (the C ABI declared in include/stb200.h).
+
+There is no fallback: if the shared library is missing or a kernel reports an error the call
+raises.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` (or
+``stereo_toolbox_b200/csrc/build.sh``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstb200.so")
+
+_lib = None
+
+
+class StbError(RuntimeError):
+    pass
+
+
+_P, _I, _F, _LL = c_void_p, c_int, c_float, c_longlong
+_IP = POINTER(c_int)
+_PP = POINTER(c_void_p)
+
+# name -> argtypes ; every function returns int except the two library-level ones
+SIGNATURES = {
+    "stb_gwc_volume_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "stb_concat_volume_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "stb_softmax_d_f32": [_P, _P, _I, _I, _LL, _P],
+    "stb_upsample_softargmin_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "stb_disparity_regression_f32": [_P, _P, _I, _I, _LL, _P],
+    "stb_conv3d_taps_f32": [_P, _P, _P, _P, _P] + [_I] * 10 + [_IP, _IP, _IP] + [_I] * 9 + [_P],
+    "stb_corr1d_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "stb_avgpool_last_f32": [_P, _P, _LL, _I, _P],
+    "stb_corr1d_lookup_f32": [_PP, _P, _LL, _P, _I, _I, _I, _I, _I, _I, _P],
+    "stb_geo_lookup_f32": [_PP, _PP, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "stb_geo_permute_f32": [_P, _P, _I, _I, _I, _I, _I, _P],
+}
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises StbError if the library is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise StbError(
+                f"{LIB_PATH} not found: the CUDA library is not built and there is no CPU fallback. "
+                "Run stereo_toolbox_b200/csrc/build.sh (or __graft_entry__.build()).")
+        h = ctypes.CDLL(LIB_PATH)
+        h.stb_error_string.restype = c_char_p
+        h.stb_error_string.argtypes = [c_int]
+        h.stb_version.restype = c_int
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(h, name)      # AttributeError here = header/library mismatch
+            fn.restype = c_int
+            fn.argtypes = argtypes
+        _lib = h
+    return _lib
+
+
+def register(name, argtypes):
+    """Late registration used by optional translation units (e.g. the tcgen05 conv path)."""
+    SIGNATURES[name] = argtypes
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.restype = c_int
+        fn.argtypes = argtypes
+
+
+def check(code: int, what: str):
+    if code != 0:
+        raise StbError(f"{what} failed: {lib().stb_error_string(code).decode()} (code {code})")
+
+
+LAUNCH_COUNT = 0   # number of kernel launches issued through this binding (bench.py reports it)
+
+
+def call(name: str, *args):
+    global LAUNCH_COUNT
+    code = getattr(lib(), name)(*args)
+    check(code, name)
+    LAUNCH_COUNT += 1

@@ -1,0 +1,183 @@
+// Exact-fp32 3-D convolution family on CUDA cores ("tap-list" direct convolution, NCDHW).
+//
+// Every conv flavour of the stacked hourglass is expressed as a list of taps
+// (input offset dd/dh/dw, weight slice wt[t][ci][co]) over a class of output positions:
+//   Conv3d k3 s1/s2 p1, k1        PSMNet/submodule.py:16-19, GwcNet/gwcnet.py:72-93
+//   ConvTranspose3d k3 s2 p1 op1  PSMNet/stackhourglass.py:25-29  (8 output-parity classes, 1..8 taps)
+//   ConvTranspose3d k4 s2 p1      IGEVStereo/igev_stereo.py:43-50 (8 classes x 8 taps)
+// Epilogue: + shift (folded eval BatchNorm3d) + residual, then ReLU / LeakyReLU / Mish.
+//
+// CTA = 128 threads = 4 warps.  Tile: 32 output channels x (1 x 4 x 32) positions; warp w owns
+// output channels [8w, 8w+8) (its weight loads are warp-uniform broadcasts), lane = (row, quad):
+// 4 consecutive w positions.  Input channels are staged in chunks of CK through shared memory
+// together with the [tap][ck][32] weight slab.  This is the bit-faithful path (fp32 FMA, same
+// summation structure per output up to ordering); the tensor-core path lives in conv3d_umma.cu.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CT_THREADS = 128;
+constexpr int CO_TILE = 32;
+constexpr int TH = 4, TW = 32;
+constexpr int MAX_TAPS = 64;
+
+struct ConvArgs {
+    const float* x; const float* wt; const float* shift; const float* residual; float* out;
+    int B, Cin, Di, Hi, Wi, Cout, Do, Ho, Wo;
+    int ntaps, is, os, od0, oh0, ow0, nd, nh, nw, act;
+    int min_d, min_h, min_w, ED, EH, EW, EWp, CK;   // staged input extent per channel
+    int tiles_h, tiles_w;
+    signed char dd[MAX_TAPS], dh[MAX_TAPS], dw[MAX_TAPS];
+};
+
+__global__ void __launch_bounds__(CT_THREADS)
+conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int CK = a.CK;
+    float* xs = smem;                                   // [CK][ED][EH][EWp]
+    float* ws = smem + CK * a.ED * a.EH * a.EWp;        // [ntaps][CK][CO_TILE]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = lane >> 3, quad = lane & 7;
+
+    int t = blockIdx.x;
+    const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+    const int th_i = t % a.tiles_h; t /= a.tiles_h;
+    const int jd = t % a.nd;
+    const int b = t / a.nd;
+    const int co0 = blockIdx.y * CO_TILE;
+    const int jh0 = th_i * TH, jw0 = tw_i * TW;
+
+    // input-space origin of the staged tile
+    const int id0 = jd * a.is + a.min_d, ih0 = jh0 * a.is + a.min_h, iw0 = jw0 * a.is + a.min_w;
+    const size_t in_plane = (size_t)a.Hi * a.Wi, in_vol = (size_t)a.Di * in_plane;
+    const int tile_elems = a.ED * a.EH * a.EWp;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int c0 = 0; c0 < a.Cin; c0 += CK) {
+        __syncthreads();
+        // stage input tile (zero padded)
+        for (int i = threadIdx.x; i < CK * tile_elems; i += CT_THREADS) {
+            int ck = i / tile_elems, r = i - ck * tile_elems;
+            int ed = r / (a.EH * a.EWp); r -= ed * a.EH * a.EWp;
+            int eh = r / a.EWp, ew = r - eh * a.EWp;
+            int ci = c0 + ck, id = id0 + ed, ih = ih0 + eh, iw = iw0 + ew;
+            float v = 0.f;
+            if (ci < a.Cin && ew < a.EW && (unsigned)id < (unsigned)a.Di && (unsigned)ih < (unsigned)a.Hi &&
+                (unsigned)iw < (unsigned)a.Wi)
+                v = __ldg(a.x + ((size_t)b * a.Cin + ci) * in_vol + (size_t)id * in_plane + (size_t)ih * a.Wi + iw);
+            xs[i] = v;
+        }
+        // stage weights [tap][ck][co]
+        for (int i = threadIdx.x; i < a.ntaps * CK * CO_TILE; i += CT_THREADS) {
+            int co = i % CO_TILE, r = i / CO_TILE;
+            int ck = r % CK, tp = r / CK;
+            int ci = c0 + ck;
+            float v = 0.f;
+            if (ci < a.Cin && co0 + co < a.Cout) v = __ldg(a.wt + ((size_t)tp * a.Cin + ci) * a.Cout + co0 + co);
+            ws[i] = v;
+        }
+        __syncthreads();
+        for (int tp = 0; tp < a.ntaps; ++tp) {
+            const int off = ((a.dd[tp] - a.min_d) * a.EH + (row * a.is + a.dh[tp] - a.min_h)) * a.EWp +
+                            (quad * 4 * a.is + a.dw[tp] - a.min_w);
+            const float* wrow = ws + (size_t)tp * CK * CO_TILE + warp * 8;
+            const float* xrow = xs + off;
+            for (int ck = 0; ck < CK; ++ck) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wrow + ck * CO_TILE);
+                const float4 w1 = *reinterpret_cast<const float4*>(wrow + ck * CO_TILE + 4);
+                const float* xp = xrow + ck * tile_elems;
+                float xv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xv[j] = xp[j * a.is];
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+            }
+        }
+    }
+
+    // epilogue
+    const int jh = jh0 + row;
+    if (jh >= a.nh) return;
+    const int od = jd * a.os + a.od0, oh = jh * a.os + a.oh0;
+    const size_t out_plane = (size_t)a.Ho * a.Wo, out_vol = (size_t)a.Do * out_plane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int co = co0 + warp * 8 + i;
+        if (co >= a.Cout) break;
+        const float sh = a.shift ? __ldg(a.shift + co) : 0.f;
+        const size_t obase = ((size_t)b * a.Cout + co) * out_vol + (size_t)od * out_plane + (size_t)oh * a.Wo;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int jw = jw0 + quad * 4 + j;
+            if (jw < a.nw) {
+                const size_t o = obase + (size_t)(jw * a.os + a.ow0);
+                float v = acc[i][j] + sh;
+                if (a.residual) v += __ldg(a.residual + o);
+                a.out[o] = stb_act(v, a.act);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int stb_conv3d_taps_f32(const float* x, const float* wt, const float* shift, const float* residual,
+                                   float* out, int B, int Cin, int Di, int Hi, int Wi, int Cout, int Do, int Ho,
+                                   int Wo, int ntaps, const int* dd, const int* dh, const int* dw, int in_stride,
+                                   int out_stride, int od0, int oh0, int ow0, int nd, int nh, int nw, int act,
+                                   void* stream) {
+    if (!x || !wt || !out || !dd || !dh || !dw) return STB_E_BADARG;
+    if (B <= 0 || Cin <= 0 || Cout <= 0 || ntaps <= 0 || ntaps > MAX_TAPS) return STB_E_BADARG;
+    if (in_stride < 1 || in_stride > 2 || out_stride < 1 || out_stride > 2) return STB_E_UNSUPPORTED;
+    if (nd <= 0 || nh <= 0 || nw <= 0) return STB_E_BADARG;
+    if ((nd - 1) * out_stride + od0 >= Do || (nh - 1) * out_stride + oh0 >= Ho || (nw - 1) * out_stride + ow0 >= Wo)
+        return STB_E_BADARG;
+    ConvArgs a;
+    a.x = x; a.wt = wt; a.shift = shift; a.residual = residual; a.out = out;
+    a.B = B; a.Cin = Cin; a.Di = Di; a.Hi = Hi; a.Wi = Wi; a.Cout = Cout; a.Do = Do; a.Ho = Ho; a.Wo = Wo;
+    a.ntaps = ntaps; a.is = in_stride; a.os = out_stride; a.od0 = od0; a.oh0 = oh0; a.ow0 = ow0;
+    a.nd = nd; a.nh = nh; a.nw = nw; a.act = act;
+    int mn[3] = {127, 127, 127}, mx[3] = {-127, -127, -127};
+    for (int t = 0; t < ntaps; ++t) {
+        const int o[3] = {dd[t], dh[t], dw[t]};
+        for (int k = 0; k < 3; ++k) {
+            if (o[k] < -8 || o[k] > 8) return STB_E_UNSUPPORTED;
+            mn[k] = o[k] < mn[k] ? o[k] : mn[k];
+            mx[k] = o[k] > mx[k] ? o[k] : mx[k];
+        }
+        a.dd[t] = (signed char)dd[t]; a.dh[t] = (signed char)dh[t]; a.dw[t] = (signed char)dw[t];
+    }
+    a.min_d = mn[0]; a.min_h = mn[1]; a.min_w = mn[2];
+    a.ED = mx[0] - mn[0] + 1;
+    a.EH = (TH - 1) * in_stride + mx[1] - mn[1] + 1;
+    a.EW = (TW - 1) * in_stride + mx[2] - mn[2] + 1;
+    a.EWp = a.EW | 1;                       // odd pitch: the 4 rows of a warp hit distinct banks
+    if ((a.EWp & 3) == 1 && in_stride == 1) a.EWp += 2;  // prefer pitch = 3 (mod 4)
+    a.tiles_h = stb_ceil_div(nh, TH);
+    a.tiles_w = stb_ceil_div(nw, TW);
+    // channel chunk: as large as fits ~96 KB so that 2 CTAs share an SM
+    int CK = 8;
+    auto smem_for = [&](int ck) {
+        return (size_t)(ck * a.ED * a.EH * a.EWp + ntaps * ck * CO_TILE) * sizeof(float);
+    };
+    while (CK > 1 && smem_for(CK) > 96 * 1024) CK >>= 1;
+    if (CK > Cin) { CK = 1; while (CK * 2 <= Cin && CK < 8) CK <<= 1; }
+    a.CK = CK;
+    size_t smem = smem_for(CK);
+    if (smem > 200 * 1024) return STB_E_SMEM;
+    cudaFuncSetAttribute(conv3d_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long nblk = (long long)B * nd * a.tiles_h * a.tiles_w;
+    if (nblk > 2147483647LL) return STB_E_BADARG;
+    dim3 grid((unsigned)nblk, stb_ceil_div(Cout, CO_TILE), 1);
+    conv3d_taps_kernel<<<grid, CT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    STB_CHECK_LAUNCH();
+    return STB_OK;
+}

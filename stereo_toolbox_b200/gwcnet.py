@@ -1,0 +1,101 @@
+"""GwcNet_G / GwcNet_GC drop-ins (reference: models/GwcNet/gwcnet.py:108-232).
+
+Same constructor, same ``forward(left, right)`` contract, same state-dict names/shapes; the
+region between the 2-D feature extractor and the returned disparity -- volume build, dres0/1,
+three hourglasses, classif3, trilinear upsample + softmax + regression -- runs in libstb200.so.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .aggregation import convbn_3d, deconvbn_3d, make_backend
+from .features2d import GwcFeatures
+
+
+class hourglass(nn.Module):
+    """Parameter container of GwcNet/gwcnet.py:68-93; ``run`` is forward :95-105 on a backend."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Sequential(convbn_3d(c, c * 2, 3, 2, 1), nn.ReLU(inplace=True))
+        self.conv2 = nn.Sequential(convbn_3d(c * 2, c * 2, 3, 1, 1), nn.ReLU(inplace=True))
+        self.conv3 = nn.Sequential(convbn_3d(c * 2, c * 4, 3, 2, 1), nn.ReLU(inplace=True))
+        self.conv4 = nn.Sequential(convbn_3d(c * 4, c * 4, 3, 1, 1), nn.ReLU(inplace=True))
+        self.conv5 = deconvbn_3d(c * 4, c * 2)
+        self.conv6 = deconvbn_3d(c * 2, c)
+        self.redir1 = convbn_3d(c, c, 1, 1, 0)
+        self.redir2 = convbn_3d(c * 2, c * 2, 1, 1, 0)
+
+    def run(self, be, x):
+        c1 = be.conv(self.conv1[0], x, "relu")
+        c2 = be.conv(self.conv2[0], c1, "relu")
+        c3 = be.conv(self.conv3[0], c2, "relu")
+        c4 = be.conv(self.conv4[0], c3, "relu")
+        r2 = be.conv(self.redir2, c2)
+        c5 = be.conv(self.conv5, c4, "relu", residual=r2)      # relu(conv5(conv4) + redir2(conv2))
+        r1 = be.conv(self.redir1, x)
+        return be.conv(self.conv6, c5, "relu", residual=r1)    # relu(conv6(conv5) + redir1(x))
+
+
+def _classif():
+    return nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True),
+                         nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False))
+
+
+class GwcNet(nn.Module):
+    def __init__(self, maxdisp, use_concat_volume=False, precision="fp32"):
+        super().__init__()
+        self.maxdisp = maxdisp
+        self.use_concat_volume = use_concat_volume
+        self.num_groups = 40
+        self.concat_channels = 12 if use_concat_volume else 0
+        self.feature_extraction = GwcFeatures(use_concat_volume, 12)
+        self.dres0 = nn.Sequential(convbn_3d(self.num_groups + self.concat_channels * 2, 32, 3, 1, 1),
+                                   nn.ReLU(inplace=True), convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True))
+        self.dres1 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True), convbn_3d(32, 32, 3, 1, 1))
+        self.dres2 = hourglass(32)
+        self.dres3 = hourglass(32)
+        self.dres4 = hourglass(32)
+        self.classif0, self.classif1, self.classif2, self.classif3 = _classif(), _classif(), _classif(), _classif()
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str):
+        """'fp32' = exact CUDA-core path; 'bf16' = tcgen05 tensor-core path."""
+        self.precision = precision
+        self._be = make_backend(precision)
+        return self
+
+    def aggregate(self, fl, fr, height, width):
+        """The hot path: features -> disparity [B,H,W]."""
+        be = self._be
+        vol = be.volume_gwc_concat(fl["gwc_feature"], fr["gwc_feature"], fl.get("concat_feature"),
+                                   fr.get("concat_feature"), self.maxdisp // 4, self.num_groups)
+        c = be.conv(self.dres0[0], vol, "relu")
+        cost0 = be.conv(self.dres0[2], c, "relu")
+        c = be.conv(self.dres1[0], cost0, "relu")
+        cost0 = be.conv(self.dres1[2], c, "none", residual=cost0)
+        out1 = self.dres2.run(be, cost0)
+        out2 = self.dres3.run(be, out1)
+        out3 = self.dres4.run(be, out2)
+        c = be.conv(self.classif3[0], out3, "relu")
+        cost3 = be.conv(self.classif3[2], c)
+        self._last_cost = cost3
+        return be.head(cost3, self.maxdisp, height, width, align_corners=False)
+
+    def forward(self, left, right):
+        if self.training:
+            raise NotImplementedError(
+                "stereo_toolbox_b200: the training (autograd / batch-stat BatchNorm3d) path is not built yet; "
+                "call model.eval() -- see DESIGN.md 'out of scope this round'")
+        fl = self.feature_extraction(left)
+        fr = self.feature_extraction(right)
+        return self.aggregate(fl, fr, left.shape[2], left.shape[3])
+
+
+def GwcNet_G(d=192, **kw):
+    return GwcNet(d, use_concat_volume=False, **kw)
+
+
+def GwcNet_GC(d=192, **kw):
+    return GwcNet(d, use_concat_volume=True, **kw)

@@ -1,0 +1,321 @@
+"""Tensor-level wrappers over the C ABI (include/stb200.h) + ``torch.ops.stb200.*`` registration.
+
+Every wrapper validates its inputs the way the reference function does (same asserts), then
+passes raw device pointers, sizes and the current CUDA stream to libstb200.so.  Inputs must be
+CUDA tensors: there is deliberately no CPU / eager fallback (the CPU path is the oracle, which
+lives outside the product).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+ACT = {"none": 0, "relu": 1, "leaky": 2, "mish": 3}
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.StbError("stereo_toolbox_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------ volumes
+def gwc_volume(left: torch.Tensor, right: torch.Tensor, maxdisp: int, num_groups: int,
+               out: Optional[torch.Tensor] = None, c_off: int = 0) -> torch.Tensor:
+    """build_gwc_volume (GwcNet/submodule.py:53-63). ``out``/``c_off`` let a caller build into a
+    slice of a wider [B,Ct,D,H,W] volume."""
+    _need_cuda(left, right)
+    B, C, H, W = left.shape
+    assert right.shape == left.shape
+    assert C % num_groups == 0                       # GwcNet/submodule.py:46
+    left, right = _f32c(left), _f32c(right)
+    if out is None:
+        out = torch.empty(B, num_groups, maxdisp, H, W, device=left.device, dtype=torch.float32)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.shape[2:] == (maxdisp, H, W)
+    _lib.call("stb_gwc_volume_f32", _p(left), _p(right), _p(out), B, C, H, W, maxdisp, num_groups,
+              out.shape[1], c_off, _stream())
+    return out
+
+
+def concat_volume(left: torch.Tensor, right: torch.Tensor, maxdisp: int, mask_left: bool = True,
+                  att_prob: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                  c_off: int = 0) -> torch.Tensor:
+    """build_concat_volume, variant A (mask_left) GwcNet/submodule.py:30-41 / variant B
+    ACVNet/submodule.py:180-191; optional fused ACVNet attention multiply (acv.py:196)."""
+    _need_cuda(left, right, att_prob)
+    B, C, H, W = left.shape
+    assert right.shape == left.shape
+    left, right = _f32c(left), _f32c(right)
+    if att_prob is not None:
+        att_prob = _f32c(att_prob)
+        assert att_prob.numel() == B * maxdisp * H * W
+    if out is None:
+        out = torch.empty(B, 2 * C, maxdisp, H, W, device=left.device, dtype=torch.float32)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.shape[2:] == (maxdisp, H, W)
+    _lib.call("stb_concat_volume_f32", _p(left), _p(right), _p(att_prob), _p(out), B, C, H, W, maxdisp,
+              int(mask_left), out.shape[1], c_off, _stream())
+    return out
+
+
+def softmax_d(x: torch.Tensor) -> torch.Tensor:
+    """F.softmax(x, dim=2) of [B,1,D,H,W] (or dim=1 of [B,D,H,W])."""
+    _need_cuda(x)
+    x = _f32c(x)
+    if x.dim() == 5:
+        assert x.shape[1] == 1
+        B, D, plane = x.shape[0], x.shape[2], x.shape[3] * x.shape[4]
+    else:
+        B, D, plane = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    y = torch.empty_like(x)
+    _lib.call("stb_softmax_d_f32", _p(x), _p(y), B, D, plane, _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------ head
+def upsample_softargmin(cost: torch.Tensor, maxdisp: int, out_h: int, out_w: int,
+                        align_corners: bool = False) -> torch.Tensor:
+    """F.upsample(cost,[maxdisp,H,W],'trilinear') + softmax(dim=1) + disparity_regression, fused.
+    cost [B,1,D,h,w] or [B,D,h,w] -> [B,out_h,out_w]."""
+    _need_cuda(cost)
+    if cost.dim() == 5:
+        assert cost.shape[1] == 1
+        cost = cost[:, 0]
+    cost = _f32c(cost)
+    B, D, H, W = cost.shape
+    disp = torch.empty(B, out_h, out_w, device=cost.device, dtype=torch.float32)
+    _lib.call("stb_upsample_softargmin_f32", _p(cost), _p(disp), B, D, H, W, maxdisp, out_h, out_w,
+              int(align_corners), _stream())
+    return disp
+
+
+def disparity_regression(prob: torch.Tensor, maxdisp: int, keepdim: bool = False) -> torch.Tensor:
+    """sum_d d * prob[:, d] (GwcNet/submodule.py:23-27; keepdim=True: PSMNet/submodule.py:46-54)."""
+    _need_cuda(prob)
+    assert len(prob.shape) == 4                      # GwcNet/submodule.py:24
+    assert prob.shape[1] == maxdisp
+    prob = _f32c(prob)
+    B, D, H, W = prob.shape
+    disp = torch.empty(B, H, W, device=prob.device, dtype=torch.float32)
+    _lib.call("stb_disparity_regression_f32", _p(prob), _p(disp), B, D, H * W, _stream())
+    return disp.unsqueeze(1) if keepdim else disp
+
+
+# ------------------------------------------------------------------------------------ conv family (fp32)
+class ConvPlan:
+    """Tap-list form of one Conv3d / ConvTranspose3d (+ folded eval BatchNorm3d) -- see
+    include/stb200.h:stb_conv3d_taps_f32.  Built once per layer and cached on the module."""
+
+    def __init__(self, weight: torch.Tensor, bn: Optional[Tuple[torch.Tensor, ...]], stride: int, padding: int,
+                 transposed: bool, output_padding: int = 0, eps: float = 1e-5):
+        w = weight.detach().float()
+        dev = w.device
+        if transposed:
+            cin, cout = w.shape[0], w.shape[1]
+        else:
+            cout, cin = w.shape[0], w.shape[1]
+        ks = tuple(w.shape[2:])
+        assert ks[0] == ks[1] == ks[2], "cubic kernels only"
+        k = ks[0]
+        if bn is not None:
+            gamma, beta, mean, var = [t.detach().float() for t in bn]
+            scale = gamma / torch.sqrt(var + eps)
+            shift = (beta - mean * scale).contiguous()
+        else:
+            scale = torch.ones(cout, device=dev)
+            shift = None
+        # [kd,kh,kw,Cin,Cout] * scale[co]
+        wt = (w.permute(2, 3, 4, 0, 1) if transposed else w.permute(2, 3, 4, 1, 0)) * scale.view(1, 1, 1, 1, -1)
+        self.cin, self.cout, self.k, self.stride, self.padding = cin, cout, k, stride, padding
+        self.transposed, self.output_padding = transposed, output_padding
+        self.shift = shift
+        self.classes = []   # (wt[T,Cin,Cout], dd, dh, dw (ctypes int arrays), T, in_stride, out_stride, (od0,oh0,ow0))
+        if not transposed:
+            offs = [kk - padding for kk in range(k)]
+            taps = [(a, b, c) for a in range(k) for b in range(k) for c in range(k)]
+            self._add_class(wt, taps, [(offs[a], offs[b], offs[c]) for a, b, c in taps], stride, 1, (0, 0, 0))
+        else:
+            per_dim = []
+            for c in range(stride):
+                per_dim.append([(kk, (c + padding - kk) // stride) for kk in range(k) if (c + padding - kk) % stride == 0])
+            for cd in range(stride):
+                for ch in range(stride):
+                    for cw in range(stride):
+                        taps, offs = [], []
+                        for kd, od in per_dim[cd]:
+                            for kh, oh in per_dim[ch]:
+                                for kw, ow in per_dim[cw]:
+                                    taps.append((kd, kh, kw))
+                                    offs.append((od, oh, ow))
+                        if taps:
+                            self._add_class(wt, taps, offs, 1, stride, (cd, ch, cw))
+
+    def _add_class(self, wt, taps, offs, in_stride, out_stride, origin):
+        T = len(taps)
+        sel = torch.stack([wt[a, b, c] for a, b, c in taps], 0).contiguous()
+        arr = lambda i: (ctypes.c_int * T)(*[o[i] for o in offs])
+        self.classes.append((sel, arr(0), arr(1), arr(2), T, in_stride, out_stride, origin))
+
+    def out_size(self, n: int) -> int:
+        if self.transposed:
+            return (n - 1) * self.stride - 2 * self.padding + self.k + self.output_padding
+        return (n + 2 * self.padding - self.k) // self.stride + 1
+
+
+def conv3d_plan_apply(plan: ConvPlan, x: torch.Tensor, act: str = "none",
+                      residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, residual)
+    x = _f32c(x)
+    B, Cin, Di, Hi, Wi = x.shape
+    assert Cin == plan.cin, f"expected {plan.cin} input channels, got {Cin}"
+    Do, Ho, Wo = plan.out_size(Di), plan.out_size(Hi), plan.out_size(Wi)
+    out = torch.empty(B, plan.cout, Do, Ho, Wo, device=x.device, dtype=torch.float32)
+    if residual is not None:
+        residual = _f32c(residual)
+        assert residual.shape == out.shape
+    for sel, dd, dh, dw, T, in_s, out_s, (od0, oh0, ow0) in plan.classes:
+        nd = (Do - od0 + out_s - 1) // out_s
+        nh = (Ho - oh0 + out_s - 1) // out_s
+        nw = (Wo - ow0 + out_s - 1) // out_s
+        if nd <= 0 or nh <= 0 or nw <= 0:
+            continue
+        _lib.call("stb_conv3d_taps_f32", _p(x), _p(sel), _p(plan.shift), _p(residual), _p(out), B, Cin, Di, Hi, Wi,
+                  plan.cout, Do, Ho, Wo, T, dd, dh, dw, in_s, out_s, od0, oh0, ow0, nd, nh, nw, ACT[act], _stream())
+    return out
+
+
+def conv3d_bn_act(x, weight, bn=None, stride=1, padding=1, act="none", residual=None, transposed=False,
+                  output_padding=0):
+    """Functional one-shot form (plans are normally cached by the model modules)."""
+    plan = ConvPlan(weight, bn, stride, padding, transposed, output_padding)
+    return conv3d_plan_apply(plan, x, act, residual)
+
+
+# ------------------------------------------------------------------------------------ 1-D correlation
+def corr1d(fmap1: torch.Tensor, fmap2: torch.Tensor, scale: bool = True) -> torch.Tensor:
+    """CorrBlock1D.corr (RAFTStereo/corr.py:148-156) -> [B,H,W1,W2] fp32."""
+    _need_cuda(fmap1, fmap2)
+    fmap1, fmap2 = _f32c(fmap1), _f32c(fmap2)
+    B, C, H, W1 = fmap1.shape
+    W2 = fmap2.shape[3]
+    assert fmap2.shape[:3] == (B, C, H)
+    corr = torch.empty(B, H, W1, W2, device=fmap1.device, dtype=torch.float32)
+    s = 1.0 / math.sqrt(C) if scale else 1.0
+    _lib.call("stb_corr1d_f32", _p(fmap1), _p(fmap2), _p(corr), B, C, H, W1, W2, ctypes.c_float(s), _stream())
+    return corr
+
+
+def avgpool_last(x: torch.Tensor) -> torch.Tensor:
+    """F.avg_pool2d(x,[1,2],stride=[1,2]) along the last axis."""
+    _need_cuda(x)
+    x = _f32c(x)
+    W = x.shape[-1]
+    out = torch.empty(*x.shape[:-1], W // 2, device=x.device, dtype=torch.float32)
+    rows = x.numel() // W
+    if W // 2 > 0:
+        _lib.call("stb_avgpool_last_f32", _p(x), _p(out), rows, W, _stream())
+    return out
+
+
+def _ptr_array(ts: Sequence[torch.Tensor]):
+    return (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def corr1d_lookup(pyramid: Sequence[torch.Tensor], coords: torch.Tensor, radius: int, num_levels: int) -> torch.Tensor:
+    """CorrBlock1D.__call__ (RAFTStereo/corr.py:127-146). coords [B,2,H,W] (channel 0 used) or [B,1,H,W]."""
+    _need_cuda(coords)
+    B, _, H, W1 = coords.shape
+    coords = _f32c(coords)
+    W2 = pyramid[0].shape[-1]
+    out = torch.empty(B, num_levels * (2 * radius + 1), H, W1, device=coords.device, dtype=torch.float32)
+    _lib.call("stb_corr1d_lookup_f32", _ptr_array(pyramid[:num_levels]), _p(coords), coords.stride(0), _p(out),
+              B, H, W1, W2, num_levels, radius, _stream())
+    return out
+
+
+def geo_permute(geo_volume: torch.Tensor) -> torch.Tensor:
+    """[B,C,D,H,W] -> [B,H,W,C,D] (IGEVStereo/geometry.py:19)."""
+    _need_cuda(geo_volume)
+    g = _f32c(geo_volume)
+    B, C, D, H, W = g.shape
+    out = torch.empty(B, H, W, C, D, device=g.device, dtype=torch.float32)
+    _lib.call("stb_geo_permute_f32", _p(g), _p(out), B, C, D, H, W, _stream())
+    return out
+
+
+def geo_lookup(geos, corrs, disp: torch.Tensor, coords: torch.Tensor, radius: int) -> torch.Tensor:
+    """Combined_Geo_Encoding_Volume.__call__ (IGEVStereo/geometry.py:35-59)."""
+    _need_cuda(disp, coords)
+    disp, coords = _f32c(disp), _f32c(coords)
+    B, H, W, C, D = geos[0].shape
+    W2 = corrs[0].shape[-1]
+    L = len(geos)
+    out = torch.empty(B, L * (2 * radius + 1) * (C + 1), H, W, device=disp.device, dtype=torch.float32)
+    _lib.call("stb_geo_lookup_f32", _ptr_array(geos), _ptr_array(corrs), _p(disp), _p(coords), _p(out),
+              B, H, W, C, D, W2, L, radius, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------ torch.ops registration
+# torch.ops.stb200.<op>: same kernels behind the dispatcher, with fake (meta) kernels so that
+# tracing / DDP / autocast wrappers around a patched model keep working.
+_REGISTERED = False
+
+
+def register_torch_ops():
+    global _REGISTERED
+    if _REGISTERED:
+        return
+    _REGISTERED = True
+    lib = torch.library.Library("stb200", "DEF")
+    lib.define("gwc_volume(Tensor left, Tensor right, int maxdisp, int num_groups) -> Tensor")
+    lib.define("concat_volume(Tensor left, Tensor right, int maxdisp, bool mask_left) -> Tensor")
+    lib.define("upsample_softargmin(Tensor cost, int maxdisp, int out_h, int out_w, bool align_corners) -> Tensor")
+    lib.define("conv3d_bn_act(Tensor x, Tensor weight, Tensor? gamma, Tensor? beta, Tensor? mean, Tensor? var, "
+               "int stride, int padding, str act, Tensor? residual, bool transposed, int output_padding) -> Tensor")
+    lib.define("corr1d(Tensor fmap1, Tensor fmap2, bool scale) -> Tensor")
+    lib.define("corr1d_lookup(Tensor[] pyramid, Tensor coords, int radius, int num_levels) -> Tensor")
+
+    def _conv(x, weight, gamma, beta, mean, var, stride, padding, act, residual, transposed, output_padding):
+        bn = None if gamma is None else (gamma, beta, mean, var)
+        return conv3d_bn_act(x, weight, bn, stride, padding, act, residual, transposed, output_padding)
+
+    lib.impl("gwc_volume", lambda l, r, d, g: gwc_volume(l, r, d, g), "CUDA")
+    lib.impl("concat_volume", lambda l, r, d, m: concat_volume(l, r, d, m), "CUDA")
+    lib.impl("upsample_softargmin", lambda c, d, h, w, a: upsample_softargmin(c, d, h, w, a), "CUDA")
+    lib.impl("conv3d_bn_act", _conv, "CUDA")
+    lib.impl("corr1d", lambda a, b, s: corr1d(a, b, s), "CUDA")
+    lib.impl("corr1d_lookup", lambda p, c, r, n: corr1d_lookup(p, c, r, n), "CUDA")
+
+    def _conv_meta(x, weight, gamma, beta, mean, var, stride, padding, act, residual, transposed, output_padding):
+        k = weight.shape[2]
+        cout = weight.shape[1] if transposed else weight.shape[0]
+        f = (lambda n: (n - 1) * stride - 2 * padding + k + output_padding) if transposed else \
+            (lambda n: (n + 2 * padding - k) // stride + 1)
+        return x.new_empty(x.shape[0], cout, f(x.shape[2]), f(x.shape[3]), f(x.shape[4]))
+
+    lib.impl("gwc_volume", lambda l, r, d, g: l.new_empty(l.shape[0], g, d, l.shape[2], l.shape[3]), "Meta")
+    lib.impl("concat_volume", lambda l, r, d, m: l.new_empty(l.shape[0], 2 * l.shape[1], d, l.shape[2], l.shape[3]), "Meta")
+    lib.impl("upsample_softargmin", lambda c, d, h, w, a: c.new_empty(c.shape[0], h, w), "Meta")
+    lib.impl("conv3d_bn_act", _conv_meta, "Meta")
+    lib.impl("corr1d", lambda a, b, s: a.new_empty(a.shape[0], a.shape[2], a.shape[3], b.shape[3]), "Meta")
+    lib.impl("corr1d_lookup", lambda p, c, r, n: c.new_empty(c.shape[0], n * (2 * r + 1), c.shape[2], c.shape[3]), "Meta")
+    register_torch_ops._lib = lib   # keep alive

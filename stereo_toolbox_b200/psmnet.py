@@ -1,0 +1,86 @@
+"""PSMNet drop-in (reference: models/PSMNet/stackhourglass.py:53-161).
+
+Same constructor / ``forward(left, right)`` / state-dict names; eval output [B,1,H,W].
+The inline concat-volume loop (:111-120), dres0..4, classif1..3 (cumulative) and the
+trilinear+softmax+regression head run in libstb200.so.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .aggregation import convbn_3d, deconvbn_3d, make_backend
+from .features2d import PsmFeatures
+
+
+class hourglass(nn.Module):
+    """Parameter container of PSMNet/stackhourglass.py:10-29; ``run`` is forward :31-50."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Sequential(convbn_3d(c, c * 2, 3, 2, 1), nn.ReLU(inplace=True))
+        self.conv2 = convbn_3d(c * 2, c * 2, 3, 1, 1)
+        self.conv3 = nn.Sequential(convbn_3d(c * 2, c * 2, 3, 2, 1), nn.ReLU(inplace=True))
+        self.conv4 = nn.Sequential(convbn_3d(c * 2, c * 2, 3, 1, 1), nn.ReLU(inplace=True))
+        self.conv5 = deconvbn_3d(c * 2, c * 2)
+        self.conv6 = deconvbn_3d(c * 2, c)
+
+    def run(self, be, x, presqu, postsqu, skip):
+        """Returns (conv6(...) + skip, pre, post); ``skip`` is the ``+cost0`` of :126-132 fused in."""
+        out = be.conv(self.conv1[0], x, "relu")
+        pre = be.conv(self.conv2, out, "relu", residual=postsqu)          # relu(conv2 + postsqu) / relu(conv2)
+        out = be.conv(self.conv3[0], pre, "relu")
+        out = be.conv(self.conv4[0], out, "relu")
+        post = be.conv(self.conv5, out, "relu", residual=presqu if presqu is not None else pre)
+        out = be.conv(self.conv6, post, "none", residual=skip)
+        return out, pre, post
+
+
+def _classif():
+    return nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True),
+                         nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False))
+
+
+class PSMNet(nn.Module):
+    def __init__(self, maxdisp=192, precision="fp32"):
+        super().__init__()
+        self.maxdisp = maxdisp
+        self.feature_extraction = PsmFeatures()
+        self.dres0 = nn.Sequential(convbn_3d(64, 32, 3, 1, 1), nn.ReLU(inplace=True),
+                                   convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True))
+        self.dres1 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True), convbn_3d(32, 32, 3, 1, 1))
+        self.dres2 = hourglass(32)
+        self.dres3 = hourglass(32)
+        self.dres4 = hourglass(32)
+        self.classif1, self.classif2, self.classif3 = _classif(), _classif(), _classif()
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str):
+        self.precision = precision
+        self._be = make_backend(precision)
+        return self
+
+    def aggregate(self, fl, fr, height, width):
+        be = self._be
+        vol = be.volume_concat(fl, fr, self.maxdisp // 4, mask_left=True)
+        c = be.conv(self.dres0[0], vol, "relu")
+        cost0 = be.conv(self.dres0[2], c, "relu")
+        c = be.conv(self.dres1[0], cost0, "relu")
+        cost0 = be.conv(self.dres1[2], c, "none", residual=cost0)
+        out1, pre1, post1 = self.dres2.run(be, cost0, None, None, cost0)
+        out2, pre2, post2 = self.dres3.run(be, out1, pre1, post1, cost0)
+        out3, pre3, post3 = self.dres4.run(be, out2, pre1, post2, cost0)
+        cost1 = be.conv(self.classif1[2], be.conv(self.classif1[0], out1, "relu"))
+        cost2 = be.conv(self.classif2[2], be.conv(self.classif2[0], out2, "relu"), residual=cost1)
+        cost3 = be.conv(self.classif3[2], be.conv(self.classif3[0], out3, "relu"), residual=cost2)
+        self._last_cost = cost3
+        return be.head(cost3, self.maxdisp, height, width, align_corners=False).unsqueeze(1)
+
+    def forward(self, left, right):
+        if self.training:
+            raise NotImplementedError(
+                "stereo_toolbox_b200: the training (autograd / batch-stat BatchNorm3d) path is not built yet; "
+                "call model.eval() -- see DESIGN.md 'out of scope this round'")
+        fl = self.feature_extraction(left)
+        fr = self.feature_extraction(right)
+        return self.aggregate(fl, fr, left.shape[2], left.shape[3])

@@ -1,0 +1,82 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/stb200.h declares, rejects bad arguments without touching a GPU, and the host mirror keeps
+the reference's state-dict layout."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_meta
+from stereo_toolbox_b200 import _lib
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "stb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(stb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    h = _lib.lib()
+    names = _declared()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(h, n), f"{n} declared in include/stb200.h but not exported by libstb200.so"
+    for n in _lib.SIGNATURES:
+        assert n in names, f"{n} bound in _lib.py but not declared in the header"
+    assert h.stb_version() >= 100
+    assert b"bad argument" in h.stb_error_string(-1)
+
+
+def test_bad_arguments_are_rejected_before_any_launch():
+    h = _lib.lib()
+    null = ctypes.c_void_p(0)
+    assert h.stb_gwc_volume_f32(null, null, null, 1, 8, 4, 4, 2, 4, 4, 0, null) == -1
+    one = ctypes.c_void_p(16)
+    assert h.stb_gwc_volume_f32(one, one, one, 1, 10, 4, 4, 2, 4, 4, 0, null) == -1      # C % G != 0
+    assert h.stb_upsample_softargmin_f32(one, one, 1, 0, 4, 4, 8, 16, 16, 0, null) == -1
+    with pytest.raises(_lib.StbError):
+        _lib.check(-2, "x")
+
+
+def test_ops_refuse_cpu_tensors():
+    from stereo_toolbox_b200 import build_gwc_volume, CorrBlock1D
+    with pytest.raises(_lib.StbError):
+        build_gwc_volume(torch.zeros(1, 8, 4, 4), torch.zeros(1, 8, 4, 4), 2, 4)
+    with pytest.raises(_lib.StbError):
+        CorrBlock1D(torch.zeros(1, 8, 4, 16), torch.zeros(1, 8, 4, 16))
+
+
+def test_state_dict_layout_matches_reference():
+    import stereo_toolbox_b200 as S
+    meta = load_meta("models.json")
+    for key, ctor in (("gwcnet_gc", lambda: S.GwcNet_GC(32)), ("gwcnet_g", lambda: S.GwcNet_G(32)),
+                      ("psmnet", lambda: S.PSMNet(32))):
+        sd = ctor().state_dict()
+        want = meta[key]["keys"]
+        assert set(sd) == set(want)
+        for k, shape in want.items():
+            assert list(sd[k].shape) == shape, k
+
+
+def test_conv_plan_tap_lists():
+    """Tap decomposition of the conv flavours (host logic, no GPU): tap counts and offsets."""
+    from stereo_toolbox_b200.ops import ConvPlan
+    w = torch.randn(4, 3, 3, 3, 3)
+    p = ConvPlan(w, None, 2, 1, False)
+    assert len(p.classes) == 1 and p.classes[0][4] == 27 and p.classes[0][5] == 2 and p.out_size(8) == 4
+    wt = torch.randn(3, 4, 3, 3, 3)
+    p = ConvPlan(wt, None, 2, 1, True, 1)           # ConvTranspose3d k3 s2 p1 op1
+    assert sorted(c[4] for c in p.classes) == [1, 2, 2, 2, 4, 4, 4, 8] and p.out_size(6) == 12
+    assert sum(c[4] for c in p.classes) == 27
+    p = ConvPlan(torch.randn(3, 4, 4, 4, 4), None, 2, 1, True, 0)   # IGEV k4 s2 p1
+    assert [c[4] for c in p.classes] == [8] * 8 and p.out_size(6) == 12
+
+
+def test_training_mode_fails_loudly():
+    import stereo_toolbox_b200 as S
+    net = S.GwcNet_GC(32).train()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 64, 128), torch.zeros(1, 3, 64, 128))

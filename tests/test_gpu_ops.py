@@ -1,0 +1,146 @@
+"""Parity of the CUDA operators (through the C ABI) against the golden fixtures and the oracle."""
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def close(a, b, rtol=1e-5, atol=1e-5):
+    torch.testing.assert_close(a.cpu(), b, rtol=rtol, atol=atol)
+
+
+def rnd(seed, *shape):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def test_volumes_golden():
+    import stereo_toolbox_b200 as S
+    g = load_golden("ops_volume_head.npz")
+    close(S.build_gwc_volume(cu(g["gwc_L"]), cu(g["gwc_R"]), 9, 4), g["gwc_out"])
+    close(S.build_gwc_volume(cu(g["gwc8_L"]), cu(g["gwc8_R"]), 6, 8), g["gwc8_out"])
+    close(S.build_concat_volume(cu(g["cat_L"]), cu(g["cat_R"]), 9), g["catA_out"], 0, 0)       # bit-exact copy
+    close(S.build_concat_volume_unmasked(cu(g["cat_L"]), cu(g["cat_R"]), 9), g["catB_out"], 0, 0)
+    from stereo_toolbox_b200 import ops
+    prob = ops.softmax_d(cu(g["att"]))
+    close(ops.concat_volume(cu(g["cat_L"]), cu(g["cat_R"]), 9, False, att_prob=prob), g["acv_out"])
+    close(S.groupwise_correlation(cu(g["gwc_L"]), cu(g["gwc_R"]), 4), g["gwc_out"][:, :, 0])
+
+
+@pytest.mark.parametrize("B,C,G,H,W,D", [(1, 320, 40, 7, 52, 12), (2, 96, 8, 5, 33, 48), (1, 40, 40, 3, 8, 16),
+                                         (1, 64, 4, 2, 4, 9)])
+def test_gwc_volume_oracle(B, C, G, H, W, D):
+    import stereo_toolbox_b200 as S
+    L, Rr = rnd(1, B, C, H, W), rnd(2, B, C, H, W)
+    close(S.build_gwc_volume(cu(L), cu(Rr), D, G), R.build_gwc_volume(L, Rr, D, G), 1e-5, 2e-5)
+
+
+def test_volume_into_slice():
+    from stereo_toolbox_b200.aggregation import Fp32Backend
+    gl, gr, cl, cr = rnd(1, 2, 80, 6, 20), rnd(2, 2, 80, 6, 20), rnd(3, 2, 12, 6, 20), rnd(4, 2, 12, 6, 20)
+    vol = Fp32Backend().volume_gwc_concat(cu(gl), cu(gr), cu(cl), cu(cr), 8, 40)
+    want = torch.cat((R.build_gwc_volume(gl, gr, 8, 40), R.build_concat_volume(cl, cr, 8, True)), 1)
+    close(vol, want, 1e-5, 2e-5)
+
+
+def test_head_golden():
+    import stereo_toolbox_b200 as S
+    g = load_golden("ops_volume_head.npz")
+    cost = cu(g["head_cost"])
+    close(S.upsample_softargmin(cost, 24, 20, 28, False), g["head_0"], 1e-5, 5e-5)
+    close(S.upsample_softargmin(cost, 24, 20, 28, True), g["head_1"], 1e-5, 5e-5)
+    close(S.upsample_softargmin(cost, 24, 20, 28, False, keepdim=True), g["head_keepdim"], 1e-5, 5e-5)
+    close(S.upsample_softargmin(cu(g["sam_cost"]), 12, 5, 7, keepdim=True), g["sam_out"], 1e-5, 5e-5)
+    prob = torch.softmax(g["up_0"], 1)
+    close(S.disparity_regression(cu(prob), 24), g["head_0"], 1e-5, 5e-5)
+    close(S.disparityregression(24)(cu(prob)), g["head_keepdim"], 1e-5, 5e-5)
+
+
+@pytest.mark.parametrize("align", [False, True])
+def test_head_oracle_x4(align):
+    import stereo_toolbox_b200 as S
+    cost = rnd(5, 2, 1, 48, 12, 39) * 2
+    got = S.upsample_softargmin(cu(cost), 192, 48, 156, align)
+    want = R.upsample_softargmin(cost, 192, 48, 156, align)
+    assert (got.cpu() - want).abs().max().item() < 2e-4
+
+
+CONVS = [
+    # cin, cout, k, stride, pad, transposed, outpad, act, residual
+    (8, 16, 3, 1, 1, False, 0, "relu", False),
+    (16, 8, 3, 2, 1, False, 0, "relu", False),
+    (8, 8, 1, 1, 0, False, 0, "none", False),
+    (16, 8, 3, 2, 1, True, 1, "relu", True),
+    (12, 40, 3, 1, 1, False, 0, "mish", True),
+    (8, 1, 3, 1, 1, False, 0, "none", True),
+    (16, 8, 4, 2, 1, True, 0, "leaky", False),
+    (64, 32, 3, 1, 1, False, 0, "relu", False),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,tr,op,act,res", CONVS)
+def test_conv3d_family_oracle(cin, cout, k, stride, pad, tr, op, act, res):
+    from stereo_toolbox_b200 import ops
+    x = rnd(1, 2, cin, 6, 9, 37)
+    w = rnd(2, *((cin, cout) if tr else (cout, cin)), k, k, k) * (2.0 / (cin * k ** 3)) ** 0.5
+    bn = dict(weight=0.75 + 0.5 * torch.rand(cout), bias=0.1 * rnd(3, cout), running_mean=0.1 * rnd(4, cout),
+              running_var=0.5 + torch.rand(cout))
+    want0 = R.conv3d_bn_act(x, w, bn, stride, pad, "none", None, tr, op)
+    resid = rnd(5, *want0.shape) if res else None
+    want = R.conv3d_bn_act(x, w, bn, stride, pad, act, resid, tr, op)
+    got = ops.conv3d_bn_act(cu(x), cu(w), tuple(cu(bn[k_]) for k_ in ("weight", "bias", "running_mean", "running_var")),
+                            stride, pad, act, None if resid is None else cu(resid), tr, op)
+    assert got.shape == want.shape
+    close(got, want, 1e-4, 1e-4)
+
+
+def test_corr_golden():
+    import stereo_toolbox_b200 as S
+    g = load_golden("ops_corr.npz")
+    blk = S.CorrBlock1D(cu(g["f1"]), cu(g["f2"]), num_levels=4, radius=4)
+    assert len(blk.corr_pyramid) == 5
+    close(S.CorrBlock1D.corr(cu(g["f1"]), cu(g["f2"]))[:, :, :, 0], g["corr"])
+    for i, p in enumerate(blk.corr_pyramid):
+        assert p.shape == (2 * 3 * 32, 1, 1, 32 >> i)
+        close(p.reshape(2, 3, 32, -1), g[f"pyr{i}"])
+    out = blk(cu(g["coords"]))
+    assert out.shape == g["lookup"].shape and out.dtype == torch.float32
+    close(out, g["lookup"], 1e-5, 3e-5)
+
+
+def test_corr_oracle_raft_shape():
+    import stereo_toolbox_b200 as S
+    f1, f2 = rnd(1, 1, 256, 6, 100), rnd(2, 1, 256, 6, 100)
+    blk = S.CorrBlock1D(cu(f1), cu(f2), 4, 4)
+    corr = R.corr1d(f1, f2, True)
+    close(blk._levels[0], corr, 1e-4, 1e-4)
+    coords = torch.arange(100.0).view(1, 1, 1, 100).repeat(1, 2, 6, 1)
+    coords[:, 0] += (torch.rand(1, 6, 100, generator=torch.Generator().manual_seed(3)) - 0.5) * 150
+    want = R.corr_lookup(R.corr_pyramid(corr, 4), coords[:, 0], 4, 4)
+    close(blk(cu(coords)), want, 1e-4, 2e-4)
+
+
+def test_geo_golden():
+    import stereo_toolbox_b200 as S
+    g = load_golden("ops_corr.npz")
+    geo = S.Combined_Geo_Encoding_Volume(cu(g["geo_m1"]), cu(g["geo_m2"]), cu(g["geo_vol"]), num_levels=2, radius=4)
+    out = geo(cu(g["geo_disp"]), cu(g["geo_coords"]))
+    assert out.shape == g["geo_out"].shape
+    close(out, g["geo_out"], 1e-5, 3e-5)
+
+
+def test_torch_ops_registration():
+    from stereo_toolbox_b200 import ops
+    ops.register_torch_ops()
+    L, Rr = rnd(1, 1, 16, 4, 12), rnd(2, 1, 16, 4, 12)
+    v = torch.ops.stb200.gwc_volume(cu(L), cu(Rr), 5, 4)
+    close(v, R.build_gwc_volume(L, Rr, 5, 4), 1e-5, 2e-5)
+    m = torch.ops.stb200.gwc_volume(L.to("meta"), Rr.to("meta"), 5, 4)
+    assert m.shape == v.shape
