@@ -94,13 +94,15 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(sd, batch_pairs, steps, warmup):
-    """The reference's CPU implementation of the path = the oracle port (oracle/ref_models.py) on all host
-    cores; each step is `batch_pairs` pairs of the same workload."""
+def cpu_reference_run(sd, batch_pairs, steps, warmup, pair=None):
+    """The reference's CPU implementation of the path = the oracle port (oracle/ref_models.py) on the host
+    cores; each step is `batch_pairs` pairs of the same workload.  Threads: STB_CPU_THREADS or
+    min(cpu_count, 32) -- torch's CPU conv3d gets SLOWER beyond that on the 128-thread GPU hosts
+    (measured: 82 s/pair with 128 threads)."""
     from oracle import ref_models as M
-    cores = os.cpu_count() or 1
+    cores = int(os.environ.get("STB_CPU_THREADS", min(os.cpu_count() or 1, 32)))
     torch.set_num_threads(cores)
-    left, right = synth_batch(batch_pairs, seed=0)
+    left, right = pair if pair is not None else synth_batch(batch_pairs, seed=0)
     disp = None
     for _ in range(warmup):
         disp = M.gwcnet_forward(sd, left, right, MAXDISP, True)
@@ -213,7 +215,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": prof.roofline(precision),
             "kernels": prof.summary()}
     if not a.no_cpu_baseline:
-        r = cpu_reference_run(sd, a.cpu_sample, 1, 0)
+        r = cpu_reference_run(sd, a.cpu_sample, 1, 0, pair=(left_h[: a.cpu_sample].clone(), right_h[: a.cpu_sample].clone()))
         line["cpu_baseline"] = {"value": r["value"], "unit": "maps/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
         ref = r["disp"]

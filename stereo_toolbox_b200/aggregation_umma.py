@@ -1,0 +1,234 @@
+"""Tensor-core backend of the 3-D aggregation: channels-last bf16 activations, tcgen05 implicit-GEMM
+convolution (csrc/conv3d_umma.cu) with a CUDA-core companion for the layer shapes it does not take yet.
+
+Same interface as aggregation.Fp32Backend, so the model code (gwcnet.py / psmnet.py) is unchanged:
+tensors that flow between backend calls are [B,D,H,W,C] bf16 here.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .aggregation import _NoProf, _split, conv_work
+from .ops import ACT, _p, _stream
+
+# UMMA descriptor base-offset convention for row-shifted operand views, settled by
+# csrc/probe/umma_probe.cu on a B200 (see profiles/umma_probe_r01.txt).
+BO_MODE = int(os.environ.get("STB_UMMA_BO_MODE", "0"))
+FORCE_SIMT = os.environ.get("STB_UMMA_FORCE_SIMT", "0") == "1"
+
+
+def _iarr(vals):
+    return (ctypes.c_int * len(vals))(*vals)
+
+
+class UmmaPlan:
+    """Everything one Conv3d / ConvTranspose3d layer needs on the tensor-core path: bf16 weight tiles
+    [tile][kc][Cpad][KC], the tap / class tables of stb_conv3d_umma_bf16, and the fp32 tap plan for the
+    CUDA-core companion."""
+
+    def __init__(self, conv, bn, cin_tensor: int):
+        w = conv.weight.detach().float()
+        tr = isinstance(conv, nn.ConvTranspose3d)
+        stride, pad, k = conv.stride[0], conv.padding[0], conv.kernel_size[0]
+        assert conv.kernel_size[0] == conv.kernel_size[1] == conv.kernel_size[2]
+        cin, cout = (w.shape[0], w.shape[1]) if tr else (w.shape[1], w.shape[0])
+        self.cin, self.cout, self.k, self.stride, self.pad, self.tr = cin, cout, k, stride, pad, tr
+        self.cin_tensor = cin_tensor
+        bnp = None if bn is None else (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        eps = 1e-5 if bn is None else bn.eps
+        opad = conv.output_padding[0] if tr else 0
+        if cin_tensor != cin:       # zero-padded input channels (e.g. the 40-ch gwc volume padded to 48)
+            wpad = torch.zeros((cin_tensor,) + tuple(w.shape[1:]) if tr else (w.shape[0], cin_tensor) + tuple(w.shape[2:]),
+                               device=w.device)
+            if tr:
+                wpad[:cin] = w
+            else:
+                wpad[:, :cin] = w
+            w = wpad
+        self.simt = ops.ConvPlan(w, bnp, stride, pad, tr, opad, eps)     # fp32 taps (+ shift) for the companion
+        self.shift = self.simt.shift
+        self.umma_ok = (not FORCE_SIMT) and self._build_umma(w, bnp, eps)
+
+    def out_size(self, n):
+        return self.simt.out_size(n)
+
+    def _build_umma(self, w, bnp, eps) -> bool:
+        cin, cout, k, stride, pad, tr = self.cin_tensor, self.cout, self.k, self.stride, self.pad, self.tr
+        if cin % 16 or cin < 16 or (cin > 64 and cin % 64):
+            return False
+        if (not tr and stride != 1) or (tr and stride != 2):
+            return False
+        kc = min(cin, 64)
+        nkc = cin // kc
+        cpad = (cout + 15) // 16 * 16
+        if bnp is not None:
+            gamma, beta, mean, var = [t.detach().float() for t in bnp]
+            scale = gamma / torch.sqrt(var + eps)
+        else:
+            scale = torch.ones(cout, device=w.device)
+        # [kd,kh,kw,co,ci] with the BN scale folded, padded to cpad rows
+        wt = (w.permute(2, 3, 4, 1, 0) if tr else w.permute(2, 3, 4, 0, 1)) * scale.view(1, 1, 1, -1, 1)
+        tiles = torch.zeros(k * k * k, cpad, cin, device=w.device)
+        tiles[:, :cout] = wt.reshape(k * k * k, cout, cin)
+        # -> [tile][kc][cpad][KC]
+        self.wt = tiles.view(k ** 3, cpad, nkc, kc).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16)
+        self.nwtiles = k ** 3
+        # smallest resident-weight footprint (N split to 16) must fit next to >= 3 plane slots
+        if self.nwtiles * nkc * 16 * kc * 2 > 112 * 1024:
+            return False
+        flat = lambda a, b, c: (a * k + b) * k + c
+        dz, dh, dw, widx, tb, te, od0, oh0, ow0 = [], [], [], [], [], [], [], [], []
+        if not tr:
+            offs = [kk - pad for kk in range(k)]
+            mn = min(offs)
+            tb.append(0)
+            for a in range(k):
+                for b in range(k):
+                    for c in range(k):
+                        dz.append(offs[a]); dh.append(offs[b] - mn); dw.append(offs[c] - mn); widx.append(flat(a, b, c))
+            te.append(len(dz)); od0.append(0); oh0.append(0); ow0.append(0)
+            self.in_off = mn
+            self.out_stride = 1
+        else:
+            per_dim = [[(kk, (c + pad - kk) // stride) for kk in range(k) if (c + pad - kk) % stride == 0]
+                       for c in range(stride)]
+            mn = min(o for lst in per_dim for _, o in lst)
+            for cd in range(stride):
+                for ch in range(stride):
+                    for cw in range(stride):
+                        tb.append(len(dz))
+                        for kd, a in per_dim[cd]:
+                            for kh, b in per_dim[ch]:
+                                for kw, c in per_dim[cw]:
+                                    dz.append(a); dh.append(b - mn); dw.append(c - mn); widx.append(flat(kd, kh, kw))
+                        te.append(len(dz)); od0.append(cd); oh0.append(ch); ow0.append(cw)
+            self.in_off = mn
+            self.out_stride = stride
+        if max(dh) > 3 or max(dw) > 3 or len(dz) > 64:
+            return False
+        self.ntaps, self.nclass = len(dz), len(tb)
+        self.c_dz, self.c_dh, self.c_dw, self.c_widx = _iarr(dz), _iarr(dh), _iarr(dw), _iarr(widx)
+        self.c_tb, self.c_te, self.c_od0, self.c_oh0, self.c_ow0 = _iarr(tb), _iarr(te), _iarr(od0), _iarr(oh0), _iarr(ow0)
+        self.cpad = cpad
+        return True
+
+
+class UmmaBackend:
+    name = "bf16"
+
+    def __init__(self):
+        self._plans: Dict[int, tuple] = {}
+        self.prof = _NoProf()
+        self.dchunk = 0
+
+    def _plan(self, layer, cin_tensor) -> UmmaPlan:
+        conv, bn = _split(layer)
+        ver = (conv.weight.data_ptr(), conv.weight._version, cin_tensor) + \
+              (() if bn is None else (bn.weight._version, bn.bias._version, bn.running_mean._version,
+                                      bn.running_var._version, bn.running_mean.data_ptr()))
+        hit = self._plans.get(id(conv))
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        plan = UmmaPlan(conv, bn, cin_tensor)
+        self._plans[id(conv)] = (ver, plan)
+        return plan
+
+    # ---------------------------------------------------------------- volumes (layout entry)
+    def volume_gwc_concat(self, gwc_l, gwc_r, cat_l, cat_r, maxdisp4, groups):
+        B, Cg, H, W = gwc_l.shape
+        cc = 0 if cat_l is None else cat_l.shape[1]
+        ct = groups + 2 * cc
+        ct_pad = (ct + 15) // 16 * 16
+        f = lambda t: None if t is None else ops._f32c(t)
+        gwc_l, gwc_r, cat_l, cat_r = f(gwc_l), f(gwc_r), f(cat_l), f(cat_r)
+        vol = torch.empty(B, maxdisp4, H, W, ct_pad, device=gwc_l.device, dtype=torch.bfloat16)
+        with self.prof.bracket("volume_cl_bf16", 0.0, 4.0 * 2 * (gwc_l.numel() + (0 if cat_l is None else cat_l.numel()))
+                               + 2.0 * vol.numel()):
+            _lib.call("stb_volume_cl_bf16", _p(gwc_l), _p(gwc_r), _p(cat_l), _p(cat_r), _p(vol), B, Cg, groups, cc,
+                      H, W, maxdisp4, ct_pad, 1, _stream())
+        return vol
+
+    def volume_concat(self, l, r, maxdisp4, mask_left=True, att_prob=None):
+        if att_prob is not None:
+            raise NotImplementedError("attention-weighted concat volume is only built on the fp32 path yet")
+        B, C, H, W = l.shape
+        ct_pad = (2 * C + 15) // 16 * 16
+        l, r = ops._f32c(l), ops._f32c(r)
+        vol = torch.empty(B, maxdisp4, H, W, ct_pad, device=l.device, dtype=torch.bfloat16)
+        with self.prof.bracket("volume_cl_bf16", 0.0, 4.0 * 2 * l.numel() + 2.0 * vol.numel()):
+            _lib.call("stb_volume_cl_bf16", _p(None), _p(None), _p(l), _p(r), _p(vol), B, 0, 0, C, H, W, maxdisp4,
+                      ct_pad, int(mask_left), _stream())
+        return vol
+
+    # ---------------------------------------------------------------- conv family
+    def conv(self, layer, x, act="none", residual=None):
+        assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 5
+        B, Di, Hi, Wi, Cin = x.shape
+        plan = self._plan(layer, Cin)
+        Do, Ho, Wo = plan.out_size(Di), plan.out_size(Hi), plan.out_size(Wi)
+        out_fp32 = plan.cout < 8          # the 32->1 classifier feeds the fp32 soft-argmin head directly
+        out = torch.empty(B, Do, Ho, Wo, plan.cout, device=x.device,
+                          dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        if residual is not None:
+            assert residual.shape == out.shape and residual.is_contiguous()
+            if residual.dtype != torch.bfloat16:
+                residual = residual.to(torch.bfloat16)
+        fam = "conv3d_umma_bf16" if plan.umma_ok else "conv3d_taps_cl_bf16"
+        fl, by = 0.0, 0.0
+        if self.prof.enabled:
+            fl, by = conv_work(plan.simt, (B, Cin, Di, Hi, Wi), (B, plan.cout, Do, Ho, Wo), 2, residual is not None)
+        with self.prof.bracket(fam, fl, by):
+            if plan.umma_ok:
+                tr = plan.tr
+                nsteps, nh, nw = (Di, Hi, Wi) if tr else (Do, Ho, Wo)
+                _lib.call("stb_conv3d_umma_bf16", _p(x), _p(plan.wt), _p(plan.shift), _p(residual), _p(out),
+                          B, Cin, Di, Hi, Wi, plan.cout, plan.cout, Do, Ho, Wo, plan.ntaps, plan.c_dz, plan.c_dh,
+                          plan.c_dw, plan.c_widx, plan.nwtiles, plan.nclass, plan.c_tb, plan.c_te, plan.c_od0,
+                          plan.c_oh0, plan.c_ow0, plan.out_stride, nsteps, nh, nw, plan.in_off, plan.in_off,
+                          ACT[act], int(out_fp32), BO_MODE, self.dchunk, _stream())
+            else:
+                sp = plan.simt
+                for sel, dd, dh, dw, T, in_s, out_s, (od0, oh0, ow0) in sp.classes:
+                    nd = (Do - od0 + out_s - 1) // out_s
+                    nh = (Ho - oh0 + out_s - 1) // out_s
+                    nw = (Wo - ow0 + out_s - 1) // out_s
+                    if nd <= 0 or nh <= 0 or nw <= 0:
+                        continue
+                    _lib.call("stb_conv3d_taps_cl_bf16", _p(x), _p(sel), _p(sp.shift), _p(residual), _p(out),
+                              int(out_fp32), B, Cin, Di, Hi, Wi, plan.cout, Do, Ho, Wo, T, dd, dh, dw, in_s, out_s,
+                              od0, oh0, ow0, nd, nh, nw, ACT[act], _stream())
+        return out
+
+    # ---------------------------------------------------------------- head (layout exit)
+    def head(self, cost, maxdisp, H, W, align_corners=False):
+        assert cost.dtype == torch.float32 and cost.shape[-1] == 1
+        B, D, h, w, _ = cost.shape
+        with self.prof.bracket("upsample_softargmin", 0.0, 4.0 * (cost.numel() + B * H * W)):
+            return ops.upsample_softargmin(cost.view(B, D, h, w), maxdisp, H, W, align_corners)
+
+
+# layout helpers for tests / callers holding reference-layout tensors
+def to_channels_last_bf16(x: torch.Tensor, cpad: Optional[int] = None) -> torch.Tensor:
+    x = ops._f32c(x)
+    B, C = x.shape[:2]
+    S = x.numel() // (B * C)
+    cpad = cpad or C
+    out = torch.empty((B,) + tuple(x.shape[2:]) + (cpad,), device=x.device, dtype=torch.bfloat16)
+    _lib.call("stb_ncdhw_to_cl_bf16", _p(x), _p(out), B, C, S, cpad, _stream())
+    return out
+
+
+def from_channels_last_bf16(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    B, cpad = x.shape[0], x.shape[-1]
+    c = c or cpad
+    S = x.numel() // (B * cpad)
+    out = torch.empty((B, c) + tuple(x.shape[1:-1]), device=x.device, dtype=torch.float32)
+    _lib.call("stb_cl_bf16_to_ncdhw", _p(x), _p(out), B, c, S, cpad, _stream())
+    return out

@@ -22,7 +22,8 @@ constexpr int TH = 4, TW = 32;
 constexpr int MAX_TAPS = 64;
 
 struct ConvArgs {
-    const float* x; const float* wt; const float* shift; const float* residual; float* out;
+    const void* x; const float* wt; const float* shift; const void* residual; void* out;
+    int out_fp32;
     int B, Cin, Di, Hi, Wi, Cout, Do, Ho, Wo;
     int ntaps, is, os, od0, oh0, ow0, nd, nh, nw, act;
     int min_d, min_h, min_w, ED, EH, EW, EWp, CK;   // staged input extent per channel
@@ -30,6 +31,9 @@ struct ConvArgs {
     signed char dd[MAX_TAPS], dh[MAX_TAPS], dw[MAX_TAPS];
 };
 
+// CL = false: fp32 NCDHW tensors.  CL = true: bf16 channels-last NDHWC tensors (the layout of the tcgen05
+// path; this kernel is its CUDA-core companion for layer shapes conv3d_umma.cu does not take yet).
+template <bool CL>
 __global__ void __launch_bounds__(CT_THREADS)
 conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -62,15 +66,23 @@ conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
         __syncthreads();
         // stage input tile (zero padded)
         for (int i = threadIdx.x; i < CK * tile_elems; i += CT_THREADS) {
-            int ck = i / tile_elems, r = i - ck * tile_elems;
+            int ck, r;
+            if (CL) { ck = i % CK; r = i / CK; } else { ck = i / tile_elems; r = i - ck * tile_elems; }
+            const int r0 = r;
             int ed = r / (a.EH * a.EWp); r -= ed * a.EH * a.EWp;
             int eh = r / a.EWp, ew = r - eh * a.EWp;
             int ci = c0 + ck, id = id0 + ed, ih = ih0 + eh, iw = iw0 + ew;
             float v = 0.f;
             if (ci < a.Cin && ew < a.EW && (unsigned)id < (unsigned)a.Di && (unsigned)ih < (unsigned)a.Hi &&
-                (unsigned)iw < (unsigned)a.Wi)
-                v = __ldg(a.x + ((size_t)b * a.Cin + ci) * in_vol + (size_t)id * in_plane + (size_t)ih * a.Wi + iw);
-            xs[i] = v;
+                (unsigned)iw < (unsigned)a.Wi) {
+                if (CL)
+                    v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.x)[
+                        ((((size_t)b * a.Di + id) * a.Hi + ih) * a.Wi + iw) * a.Cin + ci]);
+                else
+                    v = __ldg(reinterpret_cast<const float*>(a.x) + ((size_t)b * a.Cin + ci) * in_vol +
+                              (size_t)id * in_plane + (size_t)ih * a.Wi + iw);
+            }
+            xs[ck * tile_elems + r0] = v;
         }
         // stage weights [tap][ck][co]
         for (int i = threadIdx.x; i < a.ntaps * CK * CO_TILE; i += CT_THREADS) {
@@ -108,6 +120,51 @@ conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
     if (jh >= a.nh) return;
     const int od = jd * a.os + a.od0, oh = jh * a.os + a.oh0;
     const size_t out_plane = (size_t)a.Ho * a.Wo, out_vol = (size_t)a.Do * out_plane;
+    if (CL) {
+        const int cob = co0 + warp * 8;
+        if (cob >= a.Cout) return;
+        const int nch = min(8, a.Cout - cob);
+        const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(a.residual);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int jw = jw0 + quad * 4 + j;
+            if (jw >= a.nw) continue;
+            const size_t vox = (((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + (size_t)(jw * a.os + a.ow0);
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float v = acc[i][j];
+                if (i < nch) {
+                    if (a.shift) v += __ldg(a.shift + cob + i);
+                    if (res) v += __bfloat162float(res[vox * a.Cout + cob + i]);
+                }
+                f[i] = stb_act(v, a.act);
+            }
+            if (a.out_fp32) {
+                float* op = reinterpret_cast<float*>(a.out) + vox * a.Cout + cob;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < nch) op[i] = f[i];
+            } else {
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + vox * a.Cout + cob;
+                if (nch == 8 && (a.Cout & 7) == 0) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+                    uint4 o;
+                    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                    *reinterpret_cast<uint4*>(op) = o;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i < nch) op[i] = __float2bfloat16(f[i]);
+                }
+            }
+        }
+        return;
+    }
+    const float* resf = reinterpret_cast<const float*>(a.residual);
+    float* outf = reinterpret_cast<float*>(a.out);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int co = co0 + warp * 8 + i;
@@ -120,8 +177,8 @@ conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
             if (jw < a.nw) {
                 const size_t o = obase + (size_t)(jw * a.os + a.ow0);
                 float v = acc[i][j] + sh;
-                if (a.residual) v += __ldg(a.residual + o);
-                a.out[o] = stb_act(v, a.act);
+                if (resf) v += __ldg(resf + o);
+                outf[o] = stb_act(v, a.act);
             }
         }
     }
@@ -129,11 +186,11 @@ conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
 
 }  // namespace
 
-extern "C" int stb_conv3d_taps_f32(const float* x, const float* wt, const float* shift, const float* residual,
-                                   float* out, int B, int Cin, int Di, int Hi, int Wi, int Cout, int Do, int Ho,
-                                   int Wo, int ntaps, const int* dd, const int* dh, const int* dw, int in_stride,
-                                   int out_stride, int od0, int oh0, int ow0, int nd, int nh, int nw, int act,
-                                   void* stream) {
+static int conv3d_taps_launch(bool cl, int out_fp32, const void* x, const float* wt, const float* shift,
+                              const void* residual, void* out, int B, int Cin, int Di, int Hi, int Wi, int Cout,
+                              int Do, int Ho, int Wo, int ntaps, const int* dd, const int* dh, const int* dw,
+                              int in_stride, int out_stride, int od0, int oh0, int ow0, int nd, int nh, int nw,
+                              int act, void* stream) {
     if (!x || !wt || !out || !dd || !dh || !dw) return STB_E_BADARG;
     if (B <= 0 || Cin <= 0 || Cout <= 0 || ntaps <= 0 || ntaps > MAX_TAPS) return STB_E_BADARG;
     if (in_stride < 1 || in_stride > 2 || out_stride < 1 || out_stride > 2) return STB_E_UNSUPPORTED;
@@ -141,7 +198,7 @@ extern "C" int stb_conv3d_taps_f32(const float* x, const float* wt, const float*
     if ((nd - 1) * out_stride + od0 >= Do || (nh - 1) * out_stride + oh0 >= Ho || (nw - 1) * out_stride + ow0 >= Wo)
         return STB_E_BADARG;
     ConvArgs a;
-    a.x = x; a.wt = wt; a.shift = shift; a.residual = residual; a.out = out;
+    a.x = x; a.wt = wt; a.shift = shift; a.residual = residual; a.out = out; a.out_fp32 = out_fp32;
     a.B = B; a.Cin = Cin; a.Di = Di; a.Hi = Hi; a.Wi = Wi; a.Cout = Cout; a.Do = Do; a.Ho = Ho; a.Wo = Wo;
     a.ntaps = ntaps; a.is = in_stride; a.os = out_stride; a.od0 = od0; a.oh0 = oh0; a.ow0 = ow0;
     a.nd = nd; a.nh = nh; a.nw = nw; a.act = act;
@@ -173,11 +230,34 @@ extern "C" int stb_conv3d_taps_f32(const float* x, const float* wt, const float*
     a.CK = CK;
     size_t smem = smem_for(CK);
     if (smem > 200 * 1024) return STB_E_SMEM;
-    cudaFuncSetAttribute(conv3d_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long nblk = (long long)B * nd * a.tiles_h * a.tiles_w;
     if (nblk > 2147483647LL) return STB_E_BADARG;
     dim3 grid((unsigned)nblk, stb_ceil_div(Cout, CO_TILE), 1);
-    conv3d_taps_kernel<<<grid, CT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    if (cl) {
+        cudaFuncSetAttribute(conv3d_taps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv3d_taps_kernel<true><<<grid, CT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        cudaFuncSetAttribute(conv3d_taps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv3d_taps_kernel<false><<<grid, CT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    }
     STB_CHECK_LAUNCH();
     return STB_OK;
+}
+
+extern "C" int stb_conv3d_taps_f32(const float* x, const float* wt, const float* shift, const float* residual,
+                                   float* out, int B, int Cin, int Di, int Hi, int Wi, int Cout, int Do, int Ho,
+                                   int Wo, int ntaps, const int* dd, const int* dh, const int* dw, int in_stride,
+                                   int out_stride, int od0, int oh0, int ow0, int nd, int nh, int nw, int act,
+                                   void* stream) {
+    return conv3d_taps_launch(false, 1, x, wt, shift, residual, out, B, Cin, Di, Hi, Wi, Cout, Do, Ho, Wo, ntaps, dd,
+                              dh, dw, in_stride, out_stride, od0, oh0, ow0, nd, nh, nw, act, stream);
+}
+
+extern "C" int stb_conv3d_taps_cl_bf16(const void* x, const float* wt, const float* shift, const void* residual,
+                                       void* out, int out_fp32, int B, int Cin, int Di, int Hi, int Wi, int Cout,
+                                       int Do, int Ho, int Wo, int ntaps, const int* dd, const int* dh, const int* dw,
+                                       int in_stride, int out_stride, int od0, int oh0, int ow0, int nd, int nh,
+                                       int nw, int act, void* stream) {
+    return conv3d_taps_launch(true, out_fp32, x, wt, shift, residual, out, B, Cin, Di, Hi, Wi, Cout, Do, Ho, Wo,
+                              ntaps, dd, dh, dw, in_stride, out_stride, od0, oh0, ow0, nd, nh, nw, act, stream);
 }

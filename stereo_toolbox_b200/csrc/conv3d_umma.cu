@@ -1,0 +1,393 @@
+// Tensor-core 3-D convolution family for sm_100a: implicit GEMM on tcgen05 with TMEM accumulators,
+// WITHOUT materialising im2col -- every filter tap is a row-shifted *view* of one TMA-staged,
+// zero-padded activation tile in shared memory.
+//
+//   activations : channels-last NDHWC bf16  x[b][d][h][w][c]
+//   weights     : tap-major, K-major bf16   wt[tap][kchunk][co][KC]  (eval BatchNorm scale folded in)
+//   accumulate  : fp32 in TMEM; epilogue = + shift[co] (+ residual) -> ReLU/LeakyReLU/Mish -> bf16 (or fp32)
+//
+// Work item (one CTA): an (h-tile, w-tile) column of the volume marching along depth.  Each input
+// depth-plane tile  [(TH+span_h) x 32 voxels x Cin]  is loaded ONCE by TMA (5-D box, out-of-bounds
+// = zero = conv padding) into a ring of shared-memory slots.  Rows of the UMMA A operand are the
+// flattened (h, w) positions of the *padded* tile (row pitch 32 voxels), so tap (dz, dh, dw) is the same
+// tile with its descriptor start address advanced by (dh*32 + dw) rows: the 128 rows of an M-tile
+// are 4 padded rows; columns >= TW of each padded row are junk outputs that the epilogue skips.
+// This covers Conv3d k3 s1 p1 (27 taps), k1 (1 tap) and every output-parity class of
+// ConvTranspose3d k3 s2 p1 op1 / k4 s2 p1 (taps with offsets {0,+1}/{-1,0,+1}, strided store);
+// reference layers: PSMNet/submodule.py:16-19, PSMNet/stackhourglass.py:14-29, GwcNet/gwcnet.py:72-93.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane, also owns
+// TMEM alloc/dealloc), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Pipelines:
+// plane ring (full/empty mbarriers, released by tcgen05.commit) and a 2-deep TMEM accumulator ring.
+#include "common.cuh"
+#include "umma.cuh"
+
+using namespace umma;
+
+namespace {
+
+constexpr int TWP = 32;            // padded tile row pitch in voxels (one warp = one padded row in the epilogue)
+constexpr int MAX_UTAPS = 64;
+constexpr int MAX_UCLASS = 8;
+constexpr int MAX_RING = 6;
+constexpr int UMMA_THREADS = 192;
+
+struct UTap { int8_t dz; int8_t pad0; int16_t rowoff; uint16_t widx; uint16_t pad1; };
+struct UClass { uint16_t tap_begin, tap_end; int8_t od0, oh0, ow0, pad; };
+
+struct UArgs {
+    const __nv_bfloat16* residual;   // NDHWC, Cout_total channels (nullable)
+    void* out;                       // bf16 NDHWC (Cout_total) or fp32
+    const float* shift;              // [Cout_total] (nullable)
+    int B, Di, Hi, Wi, Do, Ho, Wo;
+    int Cn, Cn_valid, cout_off, Cout_total, w_rows, nwtiles;
+    int TH, TW, nM, box_h;
+    int sd_in, dzmin, dzmax, R;
+    int out_stride, nclass;
+    int nsteps, dchunk, nchunks, tiles_h, tiles_w;
+    int in_h_off, in_w_off;
+    int act, out_fp32;
+    int KC, NKC, ROWB, layout, bo_mode;
+    int nclass_h, nclass_w;          // class output extents per step in h/w (positions)
+    uint32_t plane_bytes, chunk_bytes, wtile_bytes, w_bytes_total, tmem_cols;
+    UClass cls[MAX_UCLASS];
+    UTap taps[MAX_UTAPS];
+    int ntaps;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(UMMA_THREADS, 1)
+conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                   const __grid_constant__ UArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    // [0,1024): barriers + tmem holder ; then weights ; then plane ring
+    uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* plane_full = bar_w + 1;
+    uint64_t* plane_empty = plane_full + MAX_RING;
+    uint64_t* tmem_full = plane_empty + MAX_RING;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint8_t* sW = smem + 1024;
+    uint8_t* sP = sW + ((a.w_bytes_total + 1023) & ~1023u);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- work item decode
+    int t = blockIdx.x;
+    const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+    const int th_i = t % a.tiles_h; t /= a.tiles_h;
+    const int ch_i = t % a.nchunks;
+    const int b = t / a.nchunks;
+    const int s_lo = ch_i * a.dchunk, s_hi = min(a.nsteps, s_lo + a.dchunk);
+    const int jh0 = th_i * a.TH, jw0 = tw_i * a.TW;          // class-position origin of this tile
+    const int p_first = s_lo * a.sd_in + a.dzmin;
+    const int p_last = (s_hi - 1) * a.sd_in + a.dzmax;
+    const int nplanes = p_last - p_first + 1;
+    const int nouts = (s_hi - s_lo) * a.nclass;               // accumulator rounds
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_w, 1);
+        for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_holder, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            prefetch_tmap(&tm_x);
+            prefetch_tmap(&tm_w);
+            mbar_arrive_expect_tx(bar_w, a.w_bytes_total);
+            const int ntiles = a.nwtiles * a.NKC;
+            for (int i = 0; i < ntiles; ++i)
+                tma_load_2d(sW + (size_t)i * a.wtile_bytes, &tm_w, bar_w, 0, i * a.w_rows + a.cout_off);
+            const int ih0 = jh0 * 1 + a.in_h_off, iw0 = jw0 * 1 + a.in_w_off;
+            for (int n = 0; n < nplanes; ++n) {
+                const int slot = n % a.R;
+                mbar_wait(&plane_empty[slot], ((n / a.R) & 1) ^ 1);
+                mbar_arrive_expect_tx(&plane_full[slot], (uint32_t)a.NKC * a.chunk_bytes);
+                uint8_t* dst = sP + (size_t)slot * a.plane_bytes;
+                for (int kc = 0; kc < a.NKC; ++kc)
+                    tma_load_5d(dst + (size_t)kc * a.chunk_bytes, &tm_x, &plane_full[slot], kc * a.KC, iw0, ih0,
+                                p_first + n, b);
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_f16(128, a.Cn, 1);
+            const uint32_t sbo = 8 * a.ROWB;
+            const uint32_t w0 = smem_u32(sW), p0 = smem_u32(sP);
+            mbar_wait(bar_w, 0);
+            int waited = 0;                       // planes [0, waited) are known to be resident
+            int round = 0;
+            for (int s = s_lo; s < s_hi; ++s) {
+                const int need = (s * a.sd_in + a.dzmax) - p_first + 1;
+                while (waited < need) {
+                    mbar_wait(&plane_full[waited % a.R], (waited / a.R) & 1);
+                    ++waited;
+                }
+                tc_fence_after();
+                for (int c = 0; c < a.nclass; ++c, ++round) {
+                    const int buf = round & 1;
+                    mbar_wait(&tmem_empty[buf], ((round >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const UClass cl = a.cls[c];
+                    for (int m = 0; m < a.nM; ++m) {
+                        const uint32_t dcol = tmem_base + (uint32_t)((buf * a.nM + m) * a.Cn);
+                        uint32_t acc = 0;
+                        for (int tp = cl.tap_begin; tp < cl.tap_end; ++tp) {
+                            const UTap tap = a.taps[tp];
+                            const int n = (s * a.sd_in + tap.dz) - p_first;
+                            const uint32_t abase = p0 + (uint32_t)(n % a.R) * a.plane_bytes +
+                                                   (uint32_t)(128 * m + tap.rowoff) * a.ROWB;
+                            const uint32_t bbase = w0 + (uint32_t)(tap.widx * a.NKC) * a.wtile_bytes;
+                            for (int kc = 0; kc < a.NKC; ++kc) {
+                                for (int ks = 0; ks < a.KC / 16; ++ks) {
+                                    const uint32_t aaddr = abase + kc * a.chunk_bytes + ks * 32;
+                                    const uint32_t baddr = bbase + kc * a.wtile_bytes + ks * 32;
+                                    const uint32_t abo = a.bo_mode ? ((aaddr >> 7) & 7) : 0;
+                                    mma_f16_ss(dcol, smem_desc(aaddr, 16, sbo, a.layout, abo),
+                                               smem_desc(baddr, 16, sbo, a.layout, 0), idesc, acc);
+                                    acc = 1;
+                                }
+                            }
+                        }
+                    }
+                    mma_commit(&tmem_full[buf]);
+                }
+                // planes below the next step's window are dead once this step's MMAs retire
+                const int dead_upto = (s + 1 < s_hi) ? ((s + 1) * a.sd_in + a.dzmin) - p_first : nplanes;
+                for (int n = (s == s_lo ? 0 : (s * a.sd_in + a.dzmin) - p_first); n < dead_upto; ++n)
+                    mma_commit(&plane_empty[n % a.R]);
+            }
+        }
+    } else {
+        // ================================ epilogue warps ================================
+        const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
+        const size_t ostride_w = (size_t)a.Cout_total;
+        for (int round = 0; round < nouts; ++round) {
+            const int buf = round & 1;
+            const int s = s_lo + round / a.nclass;
+            const UClass cl = a.cls[round % a.nclass];
+            mbar_wait(&tmem_full[buf], (round >> 1) & 1);
+            tc_fence_after();
+            const int od = s * a.out_stride + cl.od0;
+            for (int m = 0; m < a.nM; ++m) {
+                const int q = 128 * m + q4 * 32 + lane;
+                const int jh_l = q / TWP, jw_l = q % TWP;
+                const int jh = jh0 + jh_l, jw = jw0 + jw_l;
+                const bool valid = (jh_l < a.TH) && (jw_l < a.TW) && (jh < a.nclass_h) && (jw < a.nclass_w) && (od < a.Do);
+                const int oh = jh * a.out_stride + cl.oh0, ow = jw * a.out_stride + cl.ow0;
+                const bool inb = valid && oh < a.Ho && ow < a.Wo;
+                const size_t vox = (((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow;
+                for (int c0 = 0; c0 < a.Cn; c0 += 32) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * a.nM + m) * a.Cn + c0);
+                    __syncwarp();                      // tcgen05.ld is .sync.aligned: whole warp, converged
+                    tmem_ld_32x32(taddr, v);
+                    tmem_ld_wait();
+                    const int nch = min(32, a.Cn_valid - c0);
+                    if (inb && nch > 0) {
+                        float f[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                        if (a.shift) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nch) f[i] += __ldg(a.shift + a.cout_off + c0 + i);
+                        }
+                        if (a.residual) {
+                            const __nv_bfloat16* rp = a.residual + vox * ostride_w + a.cout_off + c0;
+                            if (nch == 32) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+                                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                                        f[i * 8 + j * 2] += __low2float(h2);
+                                        f[i * 8 + j * 2 + 1] += __high2float(h2);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (i < nch) f[i] += __bfloat162float(rp[i]);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], a.act);
+                        if (a.out_fp32) {
+                            float* op = reinterpret_cast<float*>(a.out) + vox * ostride_w + a.cout_off + c0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nch) op[i] = f[i];
+                        } else {
+                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + vox * ostride_w + a.cout_off + c0;
+                            if (nch == 32) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    uint4 o;
+                                    o.x = pack_bf16(f[i * 8 + 0], f[i * 8 + 1]);
+                                    o.y = pack_bf16(f[i * 8 + 2], f[i * 8 + 3]);
+                                    o.z = pack_bf16(f[i * 8 + 4], f[i * 8 + 5]);
+                                    o.w = pack_bf16(f[i * 8 + 6], f[i * 8 + 7]);
+                                    reinterpret_cast<uint4*>(op)[i] = o;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (i < nch) op[i] = __float2bfloat16(f[i]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+}  // namespace
+
+// Host entry.  x: [B,Di,Hi,Wi,Cin] bf16; wt: [ntaps][NKC][Cout_total][KC] bf16 (KC = min(Cin,64));
+// out/residual: [B,Do,Ho,Wo,Cout_total] (bf16, or fp32 out with out_fp32=1).  One call = one conv layer
+// flavour expressed as `nclass` output classes (1 for a plain conv, 8 for a stride-2 transposed conv):
+// class c owns taps [tap_begin[c], tap_end[c]) and writes outputs (s*os+od0, jh*os+oh0, jw*os+ow0).
+// tap t reads input plane (s + dz[t]) at tile-relative offset (dh[t], dw[t]) >= 0 and uses weight tile
+// widx[t].  in_h_off/in_w_off: tile origin of the staged input relative to the class position origin.
+extern "C" int stb_conv3d_umma_bf16(const void* x, const void* wt, const float* shift, const void* residual, void* out,
+                                    int B, int Cin, int Di, int Hi, int Wi, int Cout_total, int Cout_valid, int Do,
+                                    int Ho, int Wo, int ntaps, const int* dz, const int* dh, const int* dw,
+                                    const int* widx, int nwtiles, int nclass, const int* tap_begin,
+                                    const int* tap_end, const int* od0, const int* oh0, const int* ow0,
+                                    int out_stride, int nsteps, int nclass_h, int nclass_w, int in_h_off,
+                                    int in_w_off, int act, int out_fp32, int bo_mode, int dchunk, void* stream) {
+    if (!x || !wt || !out || !dz || !dh || !dw || !widx || !tap_begin || !tap_end || !od0 || !oh0 || !ow0)
+        return STB_E_BADARG;
+    if (B <= 0 || ntaps <= 0 || ntaps > MAX_UTAPS || nclass <= 0 || nclass > MAX_UCLASS || nsteps <= 0) return STB_E_BADARG;
+    if (Cin % 16 || Cin < 16 || (Cin > 64 && Cin % 64)) return STB_E_UNSUPPORTED;
+    if (out_stride < 1 || out_stride > 2) return STB_E_UNSUPPORTED;
+    UArgs a;
+    memset(&a, 0, sizeof(a));
+    a.KC = Cin < 64 ? Cin : 64;
+    a.NKC = Cin / a.KC;
+    a.ROWB = a.KC * 2;
+    a.layout = a.ROWB == 128 ? SW_128B : a.ROWB == 64 ? SW_64B : SW_32B;
+    const CUtensorMapSwizzle cusw = a.ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                    : a.ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    a.bo_mode = bo_mode;
+    // N per launch: keep all weight tiles resident (<= ~112 KB) -> split Cout across launches if needed
+    int Cpad = (Cout_total + 15) / 16 * 16;     // weights are padded to a multiple of 16 rows per tile by the packer
+    int Cn = Cpad;
+    while ((size_t)nwtiles * a.NKC * Cn * a.ROWB > 112 * 1024 && Cn > 16) Cn = (Cn / 2 + 15) / 16 * 16;
+    if ((size_t)nwtiles * a.NKC * Cn * a.ROWB > 150 * 1024) return STB_E_SMEM;
+    if (Cn > 256) return STB_E_UNSUPPORTED;
+    int maxdh = 0, maxdw = 0, dzmin = 127, dzmax = -127;
+    for (int t = 0; t < ntaps; ++t) {
+        if (dh[t] < 0 || dw[t] < 0 || dh[t] > 3 || dw[t] > 3 || widx[t] < 0 || widx[t] >= nwtiles) return STB_E_BADARG;
+        maxdh = dh[t] > maxdh ? dh[t] : maxdh;
+        maxdw = dw[t] > maxdw ? dw[t] : maxdw;
+        dzmin = dz[t] < dzmin ? dz[t] : dzmin;
+        dzmax = dz[t] > dzmax ? dz[t] : dzmax;
+        a.taps[t].dz = (int8_t)dz[t];
+        a.taps[t].rowoff = (int16_t)(dh[t] * TWP + dw[t]);
+        a.taps[t].widx = (uint16_t)widx[t];
+    }
+    a.ntaps = ntaps;
+    for (int c = 0; c < nclass; ++c) {
+        a.cls[c].tap_begin = (uint16_t)tap_begin[c];
+        a.cls[c].tap_end = (uint16_t)tap_end[c];
+        a.cls[c].od0 = (int8_t)od0[c]; a.cls[c].oh0 = (int8_t)oh0[c]; a.cls[c].ow0 = (int8_t)ow0[c];
+    }
+    a.nclass = nclass;
+    a.TW = TWP - maxdw;
+    a.dzmin = dzmin; a.dzmax = dzmax; a.sd_in = 1;
+    a.R = (dzmax - dzmin + 1) + 1;
+    if (a.R > MAX_RING) return STB_E_UNSUPPORTED;
+    a.residual = (const __nv_bfloat16*)residual; a.out = out; a.shift = shift;
+    a.B = B; a.Di = Di; a.Hi = Hi; a.Wi = Wi; a.Do = Do; a.Ho = Ho; a.Wo = Wo;
+    a.Cout_total = Cout_total;
+    a.out_stride = out_stride; a.nsteps = nsteps; a.nclass_h = nclass_h; a.nclass_w = nclass_w;
+    a.in_h_off = in_h_off; a.in_w_off = in_w_off; a.act = act; a.out_fp32 = out_fp32;
+    // tile height: as tall as TMEM (2 buffers x nM x Cn <= 512 cols) and shared memory allow
+    const size_t smem_cap = 220 * 1024;
+    int TH = 16;
+    for (;; TH -= 4) {
+        if (TH < 4) return STB_E_SMEM;
+        int nM = TH * TWP / 128;
+        if (2 * nM * Cn + 32 > 512) continue;       // +32: the epilogue reads TMEM in 32-column blocks
+        size_t plane = (size_t)a.NKC * (size_t)(TH + maxdh) * TWP * a.ROWB;
+        plane = (plane + 1023) & ~(size_t)1023;
+        size_t need = 2048 + (((size_t)nwtiles * a.NKC * Cn * a.ROWB + 1023) & ~(size_t)1023) + a.R * plane + 1024;
+        if (need <= smem_cap) break;
+    }
+    while (TH > 4 && TH - 4 >= nclass_h) TH -= 4;      // do not stage rows that do not exist
+    a.TH = TH; a.nM = TH * TWP / 128; a.box_h = TH + maxdh;
+    a.chunk_bytes = (uint32_t)(a.box_h * TWP * a.ROWB);
+    a.plane_bytes = (uint32_t)(((size_t)a.NKC * a.chunk_bytes + 1023) & ~(size_t)1023);
+    a.tiles_h = stb_ceil_div(nclass_h, a.TH);
+    a.tiles_w = stb_ceil_div(nclass_w, a.TW);
+    if (dchunk <= 0) {
+        // enough CTAs for >= ~6 waves of 148 SMs, but keep >= 8 steps per CTA to amortise the halo planes
+        long long cols = (long long)B * a.tiles_h * a.tiles_w;
+        dchunk = nsteps;
+        while (dchunk > 8 && cols * stb_ceil_div(nsteps, dchunk) < 148 * 6) dchunk = (dchunk + 1) / 2;
+    }
+    a.dchunk = dchunk;
+    a.nchunks = stb_ceil_div(nsteps, dchunk);
+    int tmem_cols = 32;
+    while (tmem_cols < 2 * a.nM * Cn + 32) tmem_cols <<= 1;
+    a.tmem_cols = (uint32_t)tmem_cols;
+
+    CUtensorMap tm_x, tm_w;
+    {
+        uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)Di, (uint64_t)B};
+        uint64_t str[4] = {(uint64_t)Cin * 2, (uint64_t)Wi * Cin * 2, (uint64_t)Hi * Wi * Cin * 2,
+                           (uint64_t)Di * Hi * Wi * Cin * 2};
+        uint32_t box[5] = {(uint32_t)a.KC, (uint32_t)TWP, (uint32_t)a.box_h, 1, 1};
+        if (!umma_host::make_tmap(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, str, box, cusw))
+            return STB_E_DRIVER;
+    }
+    cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    a.w_rows = Cpad;
+    a.nwtiles = nwtiles;
+    const long long nblk = (long long)B * a.nchunks * a.tiles_h * a.tiles_w;
+    if (nblk > 2147483647LL) return STB_E_BADARG;
+    for (int co = 0; co < Cpad; co += Cn) {
+        const int cn = (Cpad - co) < Cn ? (Cpad - co) : Cn;
+        a.Cn = cn;
+        a.cout_off = co;
+        a.Cn_valid = (Cout_valid - co) < cn ? (Cout_valid - co) : cn;
+        if (a.Cn_valid <= 0) break;
+        a.wtile_bytes = (uint32_t)(cn * a.ROWB);
+        a.w_bytes_total = (uint32_t)((size_t)nwtiles * a.NKC * a.wtile_bytes);
+        uint64_t dims[2] = {(uint64_t)a.KC, (uint64_t)nwtiles * a.NKC * Cpad};
+        uint64_t str[1] = {(uint64_t)a.KC * 2};
+        uint32_t box[2] = {(uint32_t)a.KC, (uint32_t)cn};
+        if (!umma_host::make_tmap(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wt), dims, str, box, cusw))
+            return STB_E_DRIVER;
+        size_t smem = 2048 + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
+        if (smem > smem_cap) return STB_E_SMEM;
+        conv3d_umma_kernel<<<(unsigned)nblk, UMMA_THREADS, smem, (cudaStream_t)stream>>>(tm_x, tm_w, a);
+        STB_CHECK_LAUNCH();
+    }
+    return STB_OK;
+}

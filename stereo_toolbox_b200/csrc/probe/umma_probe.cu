@@ -1,0 +1,209 @@
+// Hardware probe for the facts conv3d_umma.cu depends on (run on a B200; one variant per process):
+//   * K-major UMMA tiles written by TMA with SWIZZLE_128B / 64B / 32B rows (128/64/32-byte channel rows)
+//   * ROW-SHIFTED operand views: start address = tile + j * row_bytes (the im2col-free 3x3x3 tap trick),
+//     with base_offset = 0 and base_offset = (addr >> 7) & 7
+//   * 5-D TMA box loads with out-of-bounds (negative) coordinates -> zero fill (conv padding)
+// usage: umma_probe <swizzle:128|64|32> <shift_rows> <base_offset_mode:0|1> [N=32]
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <cuda_bf16.h>
+#include "../umma.cuh"
+
+using namespace umma;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 2; } } while (0)
+
+constexpr int M = 128;
+constexpr int ROWS_LOADED = 160;   // rows staged in smem (>= M + max shift)
+
+struct Params {
+    int K;            // elements per row (row_bytes = 2K = swizzle span)
+    int N;
+    int shift;        // rows
+    int bo_mode;
+    uint32_t layout;  // umma::Swizzle
+};
+
+__global__ void __launch_bounds__(128)
+probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* out, Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    __shared__ uint64_t bar_tma, bar_mma;
+    __shared__ uint32_t tmem_holder;
+    const int row_bytes = p.K * 2;
+    uint8_t* sA = smem;                                   // ROWS_LOADED rows
+    uint8_t* sB = smem + ((ROWS_LOADED * row_bytes + 1023) / 1024) * 1024;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_tma, 1);
+        mbar_init(&bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_holder, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_holder;
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&bar_tma, (ROWS_LOADED + p.N) * row_bytes);
+        tma_load_2d(sA, &tmA, &bar_tma, 0, 0);
+        tma_load_2d(sB, &tmB, &bar_tma, 0, 0);
+        mbar_wait(&bar_tma, 0);
+        tc_fence_after();
+        const uint32_t idesc = instr_desc_f16(M, p.N, 1);
+        const uint32_t a0 = smem_u32(sA) + p.shift * row_bytes;
+        const uint32_t b0 = smem_u32(sB);
+        const uint32_t sbo = 8 * row_bytes;
+        for (int k = 0; k < p.K / 16; ++k) {
+            const uint32_t aaddr = a0 + k * 32, baddr = b0 + k * 32;
+            const uint32_t abo = p.bo_mode ? ((aaddr >> 7) & 7) : 0;
+            uint64_t ad = smem_desc(aaddr, 16, sbo, p.layout, abo);
+            uint64_t bd = smem_desc(baddr, 16, sbo, p.layout, 0);
+            mma_f16_ss(tmem, ad, bd, idesc, k > 0);
+        }
+        mma_commit(&bar_mma);
+    }
+    __syncthreads();
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    uint32_t v[32];
+    for (int c0 = 0; c0 < p.N; c0 += 32) {
+        tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) out[(size_t)(warp * 32 + (threadIdx.x & 31)) * p.N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+// 5-D halo load check: NDHWC tensor, box with negative origin
+__global__ void halo_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* dump, int nelem, int c0, int w0,
+                            int h0, int d0, int n0) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    __shared__ uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&bar, nelem * 2);
+        tma_load_5d(smem, &tm, &bar, c0, w0, h0, d0, n0);
+    }
+    mbar_wait(&bar, 0);
+    for (int i = threadIdx.x; i < nelem; i += blockDim.x) dump[i] = reinterpret_cast<__nv_bfloat16*>(smem)[i];
+}
+
+static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+int main(int argc, char** argv) {
+    if (argc >= 2 && !strcmp(argv[1], "halo")) {
+        // tensor [N=2][D=4][H=5][W=6][C=32] bf16, box (C=32, W=8, H=4, D=3, N=1) at (0,-1,-1,-1,1), SWIZZLE_64B
+        const int N = 2, D = 4, H = 5, W = 6, C = 32;
+        std::vector<__nv_bfloat16> h((size_t)N * D * H * W * C);
+        for (size_t i = 0; i < h.size(); ++i) h[i] = __float2bfloat16((float)(i % 4093) * 0.25f + 1.f);
+        __nv_bfloat16 *d, *dump;
+        CK(cudaMalloc(&d, h.size() * 2));
+        CK(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+        const int bw = 8, bh = 4, bd = 3, nelem = C * bw * bh * bd;
+        CK(cudaMalloc(&dump, nelem * 2));
+        CUtensorMap tm;
+        uint64_t dims[5] = {C, W, H, D, N};
+        uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)D * H * W * C * 2};
+        uint32_t box[5] = {C, bw, bh, bd, 1};
+        if (!umma_host::make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) {
+            printf("halo: tensor map encode FAILED\n");
+            return 1;
+        }
+        halo_kernel<<<1, 128, nelem * 2 + 1024>>>(tm, dump, nelem, 0, -1, -1, -1, 1);
+        CK(cudaDeviceSynchronize());
+        std::vector<__nv_bfloat16> o(nelem);
+        CK(cudaMemcpy(o.data(), dump, nelem * 2, cudaMemcpyDeviceToHost));
+        // expected: row r = ((dd*bh)+hh)*bw+ww ; 64-byte rows, 16B chunk index ^= (byte_addr>>7)&3
+        int bad = 0;
+        for (int r = 0; r < bw * bh * bd; ++r) {
+            int ww = r % bw, hh = (r / bw) % bh, dd = r / (bw * bh);
+            int gw = ww - 1, gh = hh - 1, gd = dd - 1;
+            bool in = gw >= 0 && gw < W && gh >= 0 && gh < H && gd >= 0 && gd < D;
+            for (int c = 0; c < C; ++c) {
+                float want = in ? __bfloat162float(h[((((size_t)1 * D + gd) * H + gh) * W + gw) * C + c]) : 0.f;
+                int chunk = c / 8, within = c % 8;
+                int byte_row = r * 64;
+                int pchunk = chunk ^ ((byte_row >> 7) & 3);
+                float got = __bfloat162float(o[(size_t)r * 32 + pchunk * 8 + within]);
+                if (got != want) { if (bad < 5) printf("halo mismatch r=%d c=%d want %g got %g\n", r, c, want, got); ++bad; }
+            }
+        }
+        printf("halo 5D OOB zero-fill + SW64 layout: %s (%d mismatches)\n", bad ? "FAIL" : "PASS", bad);
+        return bad ? 1 : 0;
+    }
+    if (argc < 4) { printf("usage\n"); return 1; }
+    const int sw = atoi(argv[1]);
+    Params p;
+    p.shift = atoi(argv[2]);
+    p.bo_mode = atoi(argv[3]);
+    p.N = argc > 4 ? atoi(argv[4]) : 32;
+    p.K = sw / 2;
+    p.layout = sw == 128 ? SW_128B : sw == 64 ? SW_64B : SW_32B;
+    CUtensorMapSwizzle cusw = sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : sw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    const int K = p.K, N = p.N;
+    std::vector<float> A((size_t)ROWS_LOADED * K), B((size_t)N * K);
+    std::vector<__nv_bfloat16> Ab(A.size()), Bb(B.size());
+    srand(1);
+    for (size_t i = 0; i < A.size(); ++i) { A[i] = bf((rand() % 2001 - 1000) / 500.f); Ab[i] = __float2bfloat16(A[i]); }
+    for (size_t i = 0; i < B.size(); ++i) { B[i] = bf((rand() % 2001 - 1000) / 500.f); Bb[i] = __float2bfloat16(B[i]); }
+    __nv_bfloat16 *dA, *dB;
+    float* dO;
+    CK(cudaMalloc(&dA, Ab.size() * 2));
+    CK(cudaMalloc(&dB, Bb.size() * 2));
+    CK(cudaMalloc(&dO, (size_t)M * N * 4));
+    CK(cudaMemcpy(dA, Ab.data(), Ab.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, Bb.data(), Bb.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dO, 0, (size_t)M * N * 4));
+    CUtensorMap tmA, tmB;
+    uint64_t dimsA[2] = {(uint64_t)K, ROWS_LOADED}, dimsB[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t boxA[2] = {(uint32_t)K, ROWS_LOADED}, boxB[2] = {(uint32_t)K, (uint32_t)N};
+    if (!umma_host::make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dA, dimsA, str, boxA, cusw) ||
+        !umma_host::make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dB, dimsB, str, boxB, cusw)) {
+        printf("tensor map encode FAILED\n");
+        return 1;
+    }
+    size_t smem = ((ROWS_LOADED * K * 2 + 1023) / 1024) * 1024 + N * K * 2 + 2048;
+    CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    probe_kernel<<<1, 128, smem>>>(tmA, tmB, dO, p);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> O((size_t)M * N);
+    CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
+    // expected with row shift; also find, for the first rows, which source row each output row actually used
+    double maxerr = 0;
+    for (int r = 0; r < M; ++r)
+        for (int n = 0; n < N; ++n) {
+            float acc = 0;
+            for (int k = 0; k < K; ++k) acc += A[(size_t)(r + p.shift) * K + k] * B[(size_t)n * K + k];
+            maxerr = fmax(maxerr, fabs(acc - O[(size_t)r * N + n]));
+        }
+    printf("sw=%d shift=%d bo_mode=%d N=%d : maxerr %.4g -> %s\n", sw, p.shift, p.bo_mode, N, maxerr, maxerr < 1e-2 ? "PASS" : "FAIL");
+    if (maxerr >= 1e-2) {
+        printf("  row mapping (out row -> best source row, err): ");
+        for (int r = 0; r < 16; ++r) {
+            int best = -1; double be = 1e30;
+            for (int s = 0; s < ROWS_LOADED; ++s) {
+                double e = 0;
+                for (int n = 0; n < N; ++n) {
+                    float acc = 0;
+                    for (int k = 0; k < K; ++k) acc += A[(size_t)s * K + k] * B[(size_t)n * K + k];
+                    e = fmax(e, fabs(acc - O[(size_t)r * N + n]));
+                }
+                if (e < be) { be = e; best = s; }
+            }
+            printf("%d->%d(%.2g) ", r, best, be);
+        }
+        printf("\n");
+    }
+    return maxerr < 1e-2 ? 0 : 1;
+}

@@ -8,7 +8,6 @@
 namespace {
 
 constexpr int GWC_THREADS = 128;
-constexpr int GWC_MAX_CPG = 16;
 
 // grid: (H, G, B); dynamic smem: cpg*(W) + cpg*(W+Dpad) floats
 template <int CPG>
@@ -187,7 +186,9 @@ extern "C" int stb_gwc_volume_f32(const float* left, const float* right, float* 
     switch (C / G) {
         case 1: return launch_gwc<1>(left, right, vol, B, C, H, W, D, G, c_total, c_off, st);
         case 2: return launch_gwc<2>(left, right, vol, B, C, H, W, D, G, c_total, c_off, st);
+        case 3: return launch_gwc<3>(left, right, vol, B, C, H, W, D, G, c_total, c_off, st);
         case 4: return launch_gwc<4>(left, right, vol, B, C, H, W, D, G, c_total, c_off, st);
+        case 6: return launch_gwc<6>(left, right, vol, B, C, H, W, D, G, c_total, c_off, st);
         case 8: return launch_gwc<8>(left, right, vol, B, C, H, W, D, G, c_total, c_off, st);
         case 12: return launch_gwc<12>(left, right, vol, B, C, H, W, D, G, c_total, c_off, st);
         case 16: return launch_gwc<16>(left, right, vol, B, C, H, W, D, G, c_total, c_off, st);

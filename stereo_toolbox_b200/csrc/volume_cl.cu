@@ -1,0 +1,175 @@
+// Cost-volume builder for the tensor-core path: gwc (+ concat) volume written ONCE, channels-last
+// bf16  vol[b][d][h][w][Ct]  (Ct = G + 2*Cc, zero-padded to Ct_pad), i.e. directly in the layout the
+// first 3x3x3 conv TMA-loads.  Replaces build_gwc_volume + build_concat_volume + torch.cat
+// (GwcNet/submodule.py:30-63, GwcNet/gwcnet.py:175-180; inline loop PSMNet/stackhourglass.py:111-120).
+// Products and the group mean are fp32; only the stored value is rounded to bf16.
+#include "common.cuh"
+
+namespace {
+
+constexpr int VT = 256;      // threads
+constexpr int VW = 32;       // w positions per CTA
+
+// grid (tiles_w, H, B). dynamic smem: 64*(VW+1) + 64*(VW+D) floats
+__global__ void __launch_bounds__(VT)
+volume_cl_kernel(const float* __restrict__ gl, const float* __restrict__ gr, const float* __restrict__ cl,
+                 const float* __restrict__ cr, __nv_bfloat16* __restrict__ vol, int Cg, int G, int Cc, int H, int W,
+                 int D, int Ct, int Ct_pad, int mask_left) {
+    extern __shared__ __align__(16) float sm[];
+    const int LP = VW + 1, RP = VW + D;           // row pitches; R window covers w in [w0-D+1, w0+VW)
+    float* Ls = sm;                                // [64][LP]
+    float* Rs = sm + 64 * LP;                      // [64][RP]
+    const int w0 = blockIdx.x * VW, h = blockIdx.y, b = blockIdx.z;
+    const int cpg = G > 0 ? Cg / G : 1;
+    const size_t plane = (size_t)H * W;
+    const int lw = threadIdx.x & 31, dgrp = threadIdx.x >> 5;   // 8 depth groups
+    const int w = w0 + lw;
+    const int nchunk = Ct_pad / 8;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const int oc0 = ch * 8;
+        __syncthreads();
+        // ---- stage the source rows of this chunk
+        const bool gwc_chunk = oc0 + 8 <= G;       // all 8 output channels are correlation groups
+        const int nrow = gwc_chunk ? 8 * cpg : 8;
+        if (gwc_chunk) {
+            if (nrow > 64) return;                 // guarded on the host
+            const float* lsrc = gl + ((size_t)b * Cg + (size_t)oc0 * cpg) * plane + (size_t)h * W;
+            const float* rsrc = gr + ((size_t)b * Cg + (size_t)oc0 * cpg) * plane + (size_t)h * W;
+            for (int i = threadIdx.x; i < nrow * VW; i += VT) {
+                int r = i / VW, x = i - r * VW;
+                Ls[r * LP + x] = (w0 + x < W) ? __ldg(lsrc + (size_t)r * plane + w0 + x) : 0.f;
+            }
+            for (int i = threadIdx.x; i < nrow * (VW + D - 1); i += VT) {
+                int r = i / (VW + D - 1), x = i - r * (VW + D - 1);
+                int ww = w0 - (D - 1) + x;
+                Rs[r * RP + x] = (ww >= 0 && ww < W) ? __ldg(rsrc + (size_t)r * plane + ww) : 0.f;
+            }
+        } else {
+            // mixed chunk: per output channel pick its source row (gwc group rows are not mixed with concat
+            // rows by construction: G % 8 == 0 is required on the host)
+            for (int i = threadIdx.x; i < 8 * (VW + D - 1); i += VT) {
+                int r = i / (VW + D - 1), x = i - r * (VW + D - 1);
+                int ww = w0 - (D - 1) + x;
+                int j = oc0 + r - G;
+                float v = 0.f;
+                if (j >= 0 && j < 2 * Cc && ww >= 0 && ww < W) {
+                    const float* src = j < Cc ? cl + ((size_t)b * Cc + j) * plane : cr + ((size_t)b * Cc + (j - Cc)) * plane;
+                    v = __ldg(src + (size_t)h * W + ww);
+                }
+                Rs[r * RP + x] = v;
+            }
+        }
+        __syncthreads();
+        if (w >= W) continue;
+        for (int d = dgrp; d < D; d += VT / 32) {
+            float o[8];
+            if (gwc_chunk) {
+                const float inv = 1.f / (float)cpg;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    float acc = 0.f;
+                    for (int c = 0; c < cpg; ++c) {
+                        const int r = g * cpg + c;
+                        acc = fmaf(Ls[r * LP + lw], Rs[r * RP + lw + (D - 1) - d], acc);
+                    }
+                    o[g] = acc * inv;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int j = oc0 + r - G;
+                    float v = 0.f;
+                    if (j >= 0 && j < Cc) v = (!mask_left || w >= d) ? Rs[r * RP + lw + (D - 1)] : 0.f;
+                    else if (j >= Cc && j < 2 * Cc) v = Rs[r * RP + lw + (D - 1) - d];   // zero-filled where w-d < 0
+                    o[r] = v;
+                }
+            }
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            __nv_bfloat16* dst = vol + ((((size_t)b * D + d) * H + h) * W + w) * Ct_pad + oc0;
+            *reinterpret_cast<uint4*>(dst) = pk;
+        }
+    }
+}
+
+// NCDHW fp32 -> NDHWC bf16 and back (layout boundary of the tensor-core path; used by tests and by
+// models that enter / leave the path with reference-layout tensors)
+__global__ void ncdhw_to_cl_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, size_t S,
+                                   int Cpad) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const size_t s0 = (size_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i;
+        const size_t sidx = s0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && sidx < S) ? __ldg(src + ((size_t)b * C + c) * S + sidx) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const size_t sidx = s0 + i;
+        const int c = c0 + threadIdx.x;
+        if (sidx < S && c < Cpad) dst[((size_t)b * S + sidx) * Cpad + c] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+}
+
+__global__ void cl_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, size_t S,
+                                   int Cpad) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const size_t s0 = (size_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const size_t sidx = s0 + i;
+        const int c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (sidx < S && c < C) ? __bfloat162float(src[((size_t)b * S + sidx) * Cpad + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i;
+        const size_t sidx = s0 + threadIdx.x;
+        if (c < C && sidx < S) dst[((size_t)b * C + c) * S + sidx] = tile[threadIdx.x][i];
+    }
+}
+
+}  // namespace
+
+extern "C" int stb_volume_cl_bf16(const float* gwc_l, const float* gwc_r, const float* cat_l, const float* cat_r,
+                                  void* vol, int B, int Cg, int G, int Cc, int H, int W, int D, int Ct_pad,
+                                  int mask_left, void* stream) {
+    if (!vol || B <= 0 || H <= 0 || W <= 0 || D <= 0 || G < 0 || Cc < 0) return STB_E_BADARG;
+    if (G > 0 && (!gwc_l || !gwc_r || Cg % G)) return STB_E_BADARG;
+    if (Cc > 0 && (!cat_l || !cat_r)) return STB_E_BADARG;
+    const int Ct = G + 2 * Cc;
+    if (Ct <= 0 || Ct_pad < Ct || Ct_pad % 8 || G % 8) return STB_E_UNSUPPORTED;
+    if (G > 0 && 8 * (Cg / G) > 64) return STB_E_UNSUPPORTED;
+    if (H > 65535 || B > 65535) return STB_E_BADARG;
+    size_t smem = (size_t)(64 * (VW + 1) + 64 * (VW + D)) * sizeof(float);
+    if (smem > 200 * 1024) return STB_E_SMEM;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(volume_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(stb_ceil_div(W, VW), H, B);
+    volume_cl_kernel<<<grid, VT, smem, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r, (__nv_bfloat16*)vol, Cg, G, Cc,
+                                                            H, W, D, Ct, Ct_pad, mask_left);
+    STB_CHECK_LAUNCH();
+    return STB_OK;
+}
+
+extern "C" int stb_ncdhw_to_cl_bf16(const float* src, void* dst, int B, int C, long long S, int Cpad, void* stream) {
+    if (!src || !dst || B <= 0 || C <= 0 || S <= 0 || Cpad < C) return STB_E_BADARG;
+    dim3 grid((unsigned)((S + 31) / 32), stb_ceil_div(Cpad, 32), B);
+    ncdhw_to_cl_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, C, (size_t)S, Cpad);
+    STB_CHECK_LAUNCH();
+    return STB_OK;
+}
+
+extern "C" int stb_cl_bf16_to_ncdhw(const void* src, float* dst, int B, int C, long long S, int Cpad, void* stream) {
+    if (!src || !dst || B <= 0 || C <= 0 || S <= 0 || Cpad < C) return STB_E_BADARG;
+    dim3 grid((unsigned)((S + 31) / 32), stb_ceil_div(C, 32), B);
+    cl_to_ncdhw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, C, (size_t)S, Cpad);
+    STB_CHECK_LAUNCH();
+    return STB_OK;
+}

@@ -81,6 +81,13 @@ class PSMNet(nn.Module):
             raise NotImplementedError(
                 "stereo_toolbox_b200: the training (autograd / batch-stat BatchNorm3d) path is not built yet; "
                 "call model.eval() -- see DESIGN.md 'out of scope this round'")
-        fl = self.feature_extraction(left)
-        fr = self.feature_extraction(right)
+        # 'fp32' promises <=1e-3 px vs the fp32 reference: keep cuDNN from silently using TF32 in the 2-D
+        # extractor (torch's default for convolutions).  'bf16' leaves torch's default alone.
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = prev and self.precision != "fp32"
+        try:
+            fl = self.feature_extraction(left)
+            fr = self.feature_extraction(right)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
         return self.aggregate(fl, fr, left.shape[2], left.shape[3])

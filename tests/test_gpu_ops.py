@@ -69,7 +69,7 @@ def test_head_oracle_x4(align):
     cost = rnd(5, 2, 1, 48, 12, 39) * 2
     got = S.upsample_softargmin(cu(cost), 192, 48, 156, align)
     want = R.upsample_softargmin(cost, 192, 48, 156, align)
-    assert (got.cpu() - want).abs().max().item() < 2e-4
+    assert (got.cpu() - want).abs().max().item() < 1e-3      # values up to 191; fp32 index math vs fp64 oracle
 
 
 CONVS = [
