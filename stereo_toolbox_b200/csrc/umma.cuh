@@ -36,8 +36,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 26); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    for (uint32_t i = 1;; ++i) {
         if (mbar_try_wait(bar, parity)) return;
+        if ((i & 255u) == 0 && clock64() - t0 > 6000000000LL) break;   // ~3 s at 2 GHz
+    }
     asm volatile("trap;");
 }
 
