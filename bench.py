@@ -195,16 +195,13 @@ def main():
         ms_e2e = e0.elapsed_time(e1)
         clocks = sampler.stop()
 
-    t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    from stereo_toolbox_b200.distrib import reduce_stats
+    (ms, ms_e2e), (total_pairs, launches) = reduce_stats([ms, ms_e2e], [a.batch * a.steps, launches], device="cuda")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    total_pairs = a.batch * a.steps * world
     value = total_pairs / (ms / 1e3)
     line = {"metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -1,0 +1,45 @@
+"""N>1 host logic on CPU: two gloo ranks agree on max-over-ranks timing and whole-job unit counts, and
+the batch sharding covers every unit exactly once (no data-path collective)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from stereo_toolbox_b200.distrib import shard_range, reduce_stats
+
+
+def test_shard_range_partitions():
+    for total in (1, 7, 8, 64, 100):
+        for world in (1, 2, 3, 8):
+            seen = [i for r in range(world) for i in shard_range(total, r, world)]
+            assert seen == list(range(total))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    times, counts = reduce_stats([10.0 + 5 * rank, 3.0 - rank], [8.0, float(rank)])
+    dist.barrier()
+    q.put((rank, times, counts))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_reduction():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, times, counts in res:
+        assert times == [15.0, 3.0]        # slowest rank per region
+        assert counts == [16.0, 1.0]       # whole-job units
