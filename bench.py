@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
-    ap.add_argument("--precision", default=None, help="fp32 | bf16 (default: fastest built path)")
+    ap.add_argument("--precision", default=None, help="fp32 | bf16 | fp16 (default: STB_PRECISION or fp16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=1, help="pairs in the cpu_baseline sample")
     return ap.parse_args()
@@ -205,7 +205,7 @@ def main():
     value = total_pairs / (ms / 1e3)
     line = {"metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
+            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[precision], "data": "synthetic",
             "config": workload_config(a.batch, precision),
             "e2e": {"value": total_pairs / (ms_e2e / 1e3), "unit": "maps/s",
                     "h2d_bytes_per_step": int(left_h.numel() * 4 * 2), "d2h_bytes_per_step": int(out_h.numel() * 4)},
@@ -224,11 +224,9 @@ def main():
 
 
 def default_precision():
-    try:
-        from stereo_toolbox_b200 import aggregation_umma  # noqa: F401
-        return "bf16"
-    except ImportError:
-        return "fp32"
+    """fp16 storage on the tcgen05 path: same tensor rate as bf16 and the only 16-bit format that meets the
+    <=1e-2 px parity bar on these networks."""
+    return os.environ.get("STB_PRECISION", "fp16")
 
 
 def workload_config(batch, precision):
@@ -294,7 +292,7 @@ class KernelProfiler:
                     "frac": ach / peak, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                     "note": "fp32 CUDA-core path has no tensor-pipe work; frac is against the bf16 tensor peak"
-                    if precision == "fp32" else "bf16 tcgen05 path",
+                    if precision == "fp32" else f"{precision} tcgen05 path (kind::f16 has one rate for bf16 and fp16)",
                     "launches": v["n"], "avg_us": 1e3 * v["ms"] / v["n"]}
         peak = peaks.get("hbm_gbs", 6650.0)
         ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9

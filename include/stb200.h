@@ -92,45 +92,51 @@ int stb_conv3d_taps_f32(const float* x, const float* wt, const float* shift, con
                         int out_stride, int od0, int oh0, int ow0, int nd, int nh, int nw, int act,
                         void* stream);
 
-/* ---- tensor-core path (tcgen05 / TMEM / TMA), channels-last bf16 -----------------------------------
- * Layout: activations NDHWC bf16 x[b][d][h][w][c].  Same reference layers as stb_conv3d_taps_f32.
+/* ---- tensor-core path (tcgen05 / TMEM / TMA), channels-last 16-bit ---------------------------------
+ * Layout: activations NDHWC x[b][d][h][w][c], 16-bit: f16 = 0 -> bf16, f16 = 1 -> fp16 (same tensor-core
+ * rate, 3 more mantissa bits).  Same reference layers as stb_conv3d_taps_f32.
  *
- * stb_volume_cl_bf16: build_gwc_volume (+ build_concat_volume variant A/B + torch.cat,
+ * stb_volume_cl16: build_gwc_volume (+ build_concat_volume variant A/B + torch.cat,
  * GwcNet/gwcnet.py:175-180; PSMNet/stackhourglass.py:111-120 with G=0) written once as
- * vol[b][d][h][w][Ct_pad] bf16 (channels [0,G) correlation groups, [G,G+Cc) left, [G+Cc,G+2Cc) right,
- * the rest zero).  Inputs fp32 NCHW. Requires G % 8 == 0, Ct_pad % 8 == 0, 8*(Cg/G) <= 64. */
-int stb_volume_cl_bf16(const float* gwc_l, const float* gwc_r, const float* cat_l, const float* cat_r,
-                       void* vol, int B, int Cg, int G, int Cc, int H, int W, int D, int Ct_pad,
-                       int mask_left, void* stream);
+ * vol[b][d][h][w][Ct_pad] (channels [0,G) correlation groups, [G,G+Cc) left, [G+Cc,G+2Cc) right,
+ * the rest zero).  Inputs fp32 NCHW. Requires G % 8 == 0, Ct_pad % 8 == 0. */
+int stb_volume_cl16(const float* gwc_l, const float* gwc_r, const float* cat_l, const float* cat_r,
+                    void* vol, int f16, int B, int Cg, int G, int Cc, int H, int W, int D, int Ct_pad,
+                    int mask_left, void* stream);
 
-/* Layout boundary helpers: [B,C,S] fp32 <-> [B,S,Cpad] bf16 (S = D*H*W). */
-int stb_ncdhw_to_cl_bf16(const float* src, void* dst, int B, int C, long long S, int Cpad, void* stream);
-int stb_cl_bf16_to_ncdhw(const void* src, float* dst, int B, int C, long long S, int Cpad, void* stream);
+/* Layout boundary helpers: [B,C,S] fp32 <-> [B,S,Cpad] 16-bit (S = D*H*W). */
+int stb_ncdhw_to_cl16(const float* src, void* dst, int f16, int B, int C, long long S, int Cpad, void* stream);
+int stb_cl16_to_ncdhw(const void* src, float* dst, int f16, int B, int C, long long S, int Cpad, void* stream);
 
 /* Implicit-GEMM conv on tcgen05: every tap is a row-shifted view of a TMA-staged zero-padded tile
- * (see csrc/conv3d_umma.cu).  x [B,Di,Hi,Wi,Cin] bf16 (Cin % 16 == 0, Cin <= 64 or Cin % 64 == 0);
- * wt [nwtiles][NKC][Cpad][KC] bf16, KC = min(Cin,64), NKC = Cin/KC, Cpad = Cout_total rounded up to 16
- * (BN scale folded); out/residual [B,Do,Ho,Wo,Cout_total] bf16 (out fp32 if out_fp32).
+ * (see csrc/conv3d_umma.cu).  x [B,Di,Hi,Wi,Cin]; KC in {16,32,64} = channels per K-chunk (Cin % KC == 0;
+ * Cin/KC > 1 runs K-split passes chained through the fp32 workspace ws[B,Do,Ho,Wo,Cout_total]);
+ * wt [nwtiles][Cin/KC][Cpad][KC], Cpad = Cout_total rounded up to 16 (BN scale folded);
+ * out/residual [B,Do,Ho,Wo,Cout_total] 16-bit (out fp32 if out_fp32).
  * `nclass` output classes: class c owns taps [tap_begin[c],tap_end[c]) and writes output
- * (s*os+od0[c], jh*os+oh0[c], jw*os+ow0[c]) for s in [0,nsteps), jh in [0,nclass_h), jw in [0,nclass_w);
- * tap t reads input plane s+dz[t] at (jh+in_h_off+dh[t], jw+in_w_off+dw[t]), dh,dw in [0,3], with weight
- * tile widx[t].  All index arrays are HOST arrays.  bo_mode: UMMA descriptor base-offset convention
- * (0 = zero, 1 = (addr>>7)&7), dchunk: depth steps per CTA (0 = auto). Cout_valid = real channels. */
-int stb_conv3d_umma_bf16(const void* x, const void* wt, const float* shift, const void* residual, void* out,
-                         int B, int Cin, int Di, int Hi, int Wi, int Cout_total, int Cout_valid, int Do,
-                         int Ho, int Wo, int ntaps, const int* dz, const int* dh, const int* dw,
-                         const int* widx, int nwtiles, int nclass, const int* tap_begin,
-                         const int* tap_end, const int* od0, const int* oh0, const int* ow0,
-                         int out_stride, int nsteps, int nclass_h, int nclass_w, int in_h_off,
-                         int in_w_off, int act, int out_fp32, int bo_mode, int dchunk, void* stream);
+ * (s*os+od0[c], jh*os+oh0[c], jw*os+ow0[c]) for s in [0,nsteps), jh in [0,nclass_h), jw in [0,nclass_w).
+ * in_stride 1: tap t reads input plane s+dz[t] at (jh+in_h_off+dh[t], jw+in_w_off+dw[t]).
+ * in_stride 2: tap t reads plane 2s+dz[t], parity sub-tile sub[t] = 2*ph+pw, at half-resolution index
+ * (jh+in_h_off+dh[t], jw+in_w_off+dw[t]) i.e. input (2*(..)+ph, 2*(..)+pw).   dh,dw in [0,3]; weight tile
+ * widx[t].  All index arrays are HOST arrays.  flags: bit0 = UMMA base-offset convention, bit1 = TMA
+ * element-stride box convention (both settled by csrc/probe/umma_probe.cu); dchunk: depth steps per CTA
+ * (0 = auto).  Cout_valid = real (unpadded) channels. */
+int stb_conv3d_umma(const void* x, const void* wt, const float* shift, const void* residual, void* out,
+                    float* ws, int f16, int B, int Cin, int KC, int Di, int Hi, int Wi, int Cout_total,
+                    int Cout_valid, int Do, int Ho, int Wo, int ntaps, const int* dz, const int* dh,
+                    const int* dw, const int* sub, const int* widx, int nwtiles, int nclass,
+                    const int* tap_begin, const int* tap_end, const int* od0, const int* oh0,
+                    const int* ow0, int in_stride, int out_stride, int nsteps, int nclass_h, int nclass_w,
+                    int in_h_off, int in_w_off, int act, int out_fp32, int flags, int dchunk,
+                    void* stream);
 
-/* CUDA-core companion on the same channels-last bf16 tensors (fp32 weights wt[ntaps][Cin][Cout], fp32
- * accumulate) for layer shapes the tcgen05 kernel does not take yet; arguments as stb_conv3d_taps_f32. */
-int stb_conv3d_taps_cl_bf16(const void* x, const float* wt, const float* shift, const void* residual,
-                            void* out, int out_fp32, int B, int Cin, int Di, int Hi, int Wi, int Cout,
-                            int Do, int Ho, int Wo, int ntaps, const int* dd, const int* dh, const int* dw,
-                            int in_stride, int out_stride, int od0, int oh0, int ow0, int nd, int nh,
-                            int nw, int act, void* stream);
+/* CUDA-core companion on the same channels-last 16-bit tensors (fp32 weights wt[ntaps][Cin][Cout], fp32
+ * accumulate); arguments as stb_conv3d_taps_f32. */
+int stb_conv3d_taps_cl16(const void* x, const float* wt, const float* shift, const void* residual,
+                         void* out, int out_fp32, int f16, int B, int Cin, int Di, int Hi, int Wi, int Cout,
+                         int Do, int Ho, int Wo, int ntaps, const int* dd, const int* dh, const int* dw,
+                         int in_stride, int out_stride, int od0, int oh0, int ow0, int nd, int nh,
+                         int nw, int act, void* stream);
 
 /* ---- 1-D all-pairs correlation + pyramid + lookup --------------------------------------------
  * CorrBlock1D.corr (RAFTStereo/corr.py:148-156, scale=1/sqrt(C)) and

@@ -32,12 +32,12 @@ SIGNATURES = {
     "stb_upsample_softargmin_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "stb_disparity_regression_f32": [_P, _P, _I, _I, _LL, _P],
     "stb_conv3d_taps_f32": [_P, _P, _P, _P, _P] + [_I] * 10 + [_IP, _IP, _IP] + [_I] * 9 + [_P],
-    "stb_volume_cl_bf16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "stb_ncdhw_to_cl_bf16": [_P, _P, _I, _I, _LL, _I, _P],
-    "stb_cl_bf16_to_ncdhw": [_P, _P, _I, _I, _LL, _I, _P],
-    "stb_conv3d_umma_bf16": [_P, _P, _P, _P, _P] + [_I] * 11 + [_IP, _IP, _IP, _IP, _I, _I, _IP, _IP, _IP, _IP, _IP]
-                            + [_I] * 10 + [_P],
-    "stb_conv3d_taps_cl_bf16": [_P, _P, _P, _P, _P, _I] + [_I] * 10 + [_IP, _IP, _IP] + [_I] * 9 + [_P],
+    "stb_volume_cl16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "stb_ncdhw_to_cl16": [_P, _P, _I, _I, _I, _LL, _I, _P],
+    "stb_cl16_to_ncdhw": [_P, _P, _I, _I, _I, _LL, _I, _P],
+    "stb_conv3d_umma": [_P, _P, _P, _P, _P, _P] + [_I] * 13 + [_IP, _IP, _IP, _IP, _IP, _I, _I, _IP, _IP, _IP, _IP, _IP]
+                       + [_I] * 11 + [_P],
+    "stb_conv3d_taps_cl16": [_P, _P, _P, _P, _P, _I, _I] + [_I] * 10 + [_IP, _IP, _IP] + [_I] * 9 + [_P],
     "stb_corr1d_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "stb_avgpool_last_f32": [_P, _P, _LL, _I, _P],
     "stb_corr1d_lookup_f32": [_PP, _P, _LL, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -128,7 +128,7 @@ class Fp32Backend:
 def make_backend(precision: str):
     if precision == "fp32":
         return Fp32Backend()
-    if precision == "bf16":
+    if precision in ("bf16", "fp16"):
         from .aggregation_umma import UmmaBackend
-        return UmmaBackend()
-    raise ValueError(f"unknown precision {precision!r} (use 'fp32' or 'bf16')")
+        return UmmaBackend(precision)
+    raise ValueError(f"unknown precision {precision!r} (use 'fp32', 'bf16' or 'fp16')")

@@ -19,8 +19,20 @@ from .ops import ACT, _p, _stream
 
 # UMMA descriptor base-offset convention for row-shifted operand views, settled by
 # csrc/probe/umma_probe.cu on a B200 (see profiles/umma_probe_r01.txt).
+# profiles/umma_probe_r01.txt: shifted views work with base_offset = 0 (absolute-address swizzle).
 BO_MODE = int(os.environ.get("STB_UMMA_BO_MODE", "0"))
+ES_VARIANT = int(os.environ.get("STB_TMA_ES_VARIANT", "0"))      # box extent convention under TMA element strides
 FORCE_SIMT = os.environ.get("STB_UMMA_FORCE_SIMT", "0") == "1"
+SIMT_STRIDE2 = os.environ.get("STB_UMMA_SIMT_STRIDE2", "0") == "1"   # keep strided convs on the CUDA-core companion
+TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def pad_channels(c: int) -> int:
+    """Channel count the channels-last tensors are padded to: one swizzle row (16/32/64 ch) or a multiple of 64."""
+    for k in (16, 32, 64):
+        if c <= k:
+            return k
+    return (c + 63) // 64 * 64
 
 
 def _iarr(vals):
@@ -32,7 +44,8 @@ class UmmaPlan:
     [tile][kc][Cpad][KC], the tap / class tables of stb_conv3d_umma_bf16, and the fp32 tap plan for the
     CUDA-core companion."""
 
-    def __init__(self, conv, bn, cin_tensor: int):
+    def __init__(self, conv, bn, cin_tensor: int, dtype=torch.bfloat16):
+        self.dtype = dtype
         w = conv.weight.detach().float()
         tr = isinstance(conv, nn.ConvTranspose3d)
         stride, pad, k = conv.stride[0], conv.padding[0], conv.kernel_size[0]
@@ -60,38 +73,45 @@ class UmmaPlan:
 
     def _build_umma(self, w, bnp, eps) -> bool:
         cin, cout, k, stride, pad, tr = self.cin_tensor, self.cout, self.k, self.stride, self.pad, self.tr
-        if cin % 16 or cin < 16 or (cin > 64 and cin % 64):
+        if cin not in (16, 32, 64) and cin % 64:
             return False
-        if (not tr and stride != 1) or (tr and stride != 2):
+        if tr and stride != 2:
             return False
-        kc = min(cin, 64)
-        nkc = cin // kc
+        if not tr and stride not in (1, 2):
+            return False
+        if not tr and stride == 2 and SIMT_STRIDE2:
+            return False
+        in_stride = 1 if tr else stride
+        kc = min(cin, 32 if in_stride == 2 else 64)      # channels per K-chunk = one swizzled smem row
+        nk = cin // kc
         cpad = (cout + 15) // 16 * 16
         if bnp is not None:
             gamma, beta, mean, var = [t.detach().float() for t in bnp]
             scale = gamma / torch.sqrt(var + eps)
         else:
             scale = torch.ones(cout, device=w.device)
-        # [kd,kh,kw,co,ci] with the BN scale folded, padded to cpad rows
+        # [kd,kh,kw,co,ci] with the BN scale folded, padded to cpad rows -> [tile][nk][cpad][KC]
         wt = (w.permute(2, 3, 4, 1, 0) if tr else w.permute(2, 3, 4, 0, 1)) * scale.view(1, 1, 1, -1, 1)
         tiles = torch.zeros(k * k * k, cpad, cin, device=w.device)
         tiles[:, :cout] = wt.reshape(k * k * k, cout, cin)
-        # -> [tile][kc][cpad][KC]
-        self.wt = tiles.view(k ** 3, cpad, nkc, kc).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16)
-        self.nwtiles = k ** 3
-        # smallest resident-weight footprint (N split to 16) must fit next to >= 3 plane slots
-        if self.nwtiles * nkc * 16 * kc * 2 > 112 * 1024:
+        self.wt = tiles.view(k ** 3, cpad, nk, kc).permute(0, 2, 1, 3).contiguous().to(self.dtype)
+        self.nwtiles, self.kc, self.nk, self.in_stride = k ** 3, kc, nk, in_stride
+        if self.nwtiles * 16 * kc * 2 > 150 * 1024:
             return False
         flat = lambda a, b, c: (a * k + b) * k + c
-        dz, dh, dw, widx, tb, te, od0, oh0, ow0 = [], [], [], [], [], [], [], [], []
+        dz, dh, dw, sub, widx, tb, te, od0, oh0, ow0 = [], [], [], [], [], [], [], [], [], []
         if not tr:
-            offs = [kk - pad for kk in range(k)]
-            mn = min(offs)
+            # input index = stride*o + (kk - pad); for stride 2 split into parity p and half-res offset
+            e = [kk - pad for kk in range(k)]
+            par = [x % in_stride for x in e]
+            off = [(x - p) // in_stride for x, p in zip(e, par)]
+            mn = min(off)
             tb.append(0)
             for a in range(k):
                 for b in range(k):
                     for c in range(k):
-                        dz.append(offs[a]); dh.append(offs[b] - mn); dw.append(offs[c] - mn); widx.append(flat(a, b, c))
+                        dz.append(e[a]); dh.append(off[b] - mn); dw.append(off[c] - mn)
+                        sub.append(par[b] * 2 + par[c] if in_stride == 2 else 0); widx.append(flat(a, b, c))
             te.append(len(dz)); od0.append(0); oh0.append(0); ow0.append(0)
             self.in_off = mn
             self.out_stride = 1
@@ -106,24 +126,29 @@ class UmmaPlan:
                         for kd, a in per_dim[cd]:
                             for kh, b in per_dim[ch]:
                                 for kw, c in per_dim[cw]:
-                                    dz.append(a); dh.append(b - mn); dw.append(c - mn); widx.append(flat(kd, kh, kw))
+                                    dz.append(a); dh.append(b - mn); dw.append(c - mn); sub.append(0)
+                                    widx.append(flat(kd, kh, kw))
                         te.append(len(dz)); od0.append(cd); oh0.append(ch); ow0.append(cw)
             self.in_off = mn
             self.out_stride = stride
         if max(dh) > 3 or max(dw) > 3 or len(dz) > 64:
             return False
         self.ntaps, self.nclass = len(dz), len(tb)
-        self.c_dz, self.c_dh, self.c_dw, self.c_widx = _iarr(dz), _iarr(dh), _iarr(dw), _iarr(widx)
+        self.c_dz, self.c_dh, self.c_dw, self.c_sub, self.c_widx = _iarr(dz), _iarr(dh), _iarr(dw), _iarr(sub), _iarr(widx)
         self.c_tb, self.c_te, self.c_od0, self.c_oh0, self.c_ow0 = _iarr(tb), _iarr(te), _iarr(od0), _iarr(oh0), _iarr(ow0)
         self.cpad = cpad
         return True
 
 
 class UmmaBackend:
-    name = "bf16"
+    """precision 'bf16' or 'fp16': 16-bit channels-last activations, fp32 accumulation in TMEM."""
 
-    def __init__(self):
+    def __init__(self, precision: str = "bf16"):
+        self.name = precision
+        self.dtype = TORCH_DT[precision]
+        self.f16 = int(precision == "fp16")
         self._plans: Dict[int, tuple] = {}
+        self._ws: Dict[tuple, torch.Tensor] = {}
         self.prof = _NoProf()
         self.dchunk = 0
 
@@ -135,63 +160,72 @@ class UmmaBackend:
         hit = self._plans.get(id(conv))
         if hit is not None and hit[0] == ver:
             return hit[1]
-        plan = UmmaPlan(conv, bn, cin_tensor)
+        plan = UmmaPlan(conv, bn, cin_tensor, self.dtype)
         self._plans[id(conv)] = (ver, plan)
         return plan
+
+    def _workspace(self, numel, device):
+        """fp32 partial-sum buffer of the K-split passes (grown on demand, reused across layers: launches on
+        one stream are ordered, and every K-split sequence fully rewrites the region it reads)."""
+        key = (device.index,)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < numel:
+            ws = torch.empty(numel, device=device, dtype=torch.float32)
+            self._ws[key] = ws
+        return ws
 
     # ---------------------------------------------------------------- volumes (layout entry)
     def volume_gwc_concat(self, gwc_l, gwc_r, cat_l, cat_r, maxdisp4, groups):
         B, Cg, H, W = gwc_l.shape
         cc = 0 if cat_l is None else cat_l.shape[1]
-        ct = groups + 2 * cc
-        ct_pad = (ct + 15) // 16 * 16
+        ct_pad = pad_channels(groups + 2 * cc)
         f = lambda t: None if t is None else ops._f32c(t)
         gwc_l, gwc_r, cat_l, cat_r = f(gwc_l), f(gwc_r), f(cat_l), f(cat_r)
-        vol = torch.empty(B, maxdisp4, H, W, ct_pad, device=gwc_l.device, dtype=torch.bfloat16)
-        with self.prof.bracket("volume_cl_bf16", 0.0, 4.0 * 2 * (gwc_l.numel() + (0 if cat_l is None else cat_l.numel()))
+        vol = torch.empty(B, maxdisp4, H, W, ct_pad, device=gwc_l.device, dtype=self.dtype)
+        with self.prof.bracket("volume_cl16", 0.0, 4.0 * 2 * (gwc_l.numel() + (0 if cat_l is None else cat_l.numel()))
                                + 2.0 * vol.numel()):
-            _lib.call("stb_volume_cl_bf16", _p(gwc_l), _p(gwc_r), _p(cat_l), _p(cat_r), _p(vol), B, Cg, groups, cc,
-                      H, W, maxdisp4, ct_pad, 1, _stream())
+            _lib.call("stb_volume_cl16", _p(gwc_l), _p(gwc_r), _p(cat_l), _p(cat_r), _p(vol), self.f16, B, Cg, groups,
+                      cc, H, W, maxdisp4, ct_pad, 1, _stream())
         return vol
 
     def volume_concat(self, l, r, maxdisp4, mask_left=True, att_prob=None):
         if att_prob is not None:
             raise NotImplementedError("attention-weighted concat volume is only built on the fp32 path yet")
         B, C, H, W = l.shape
-        ct_pad = (2 * C + 15) // 16 * 16
+        ct_pad = pad_channels(2 * C)
         l, r = ops._f32c(l), ops._f32c(r)
-        vol = torch.empty(B, maxdisp4, H, W, ct_pad, device=l.device, dtype=torch.bfloat16)
-        with self.prof.bracket("volume_cl_bf16", 0.0, 4.0 * 2 * l.numel() + 2.0 * vol.numel()):
-            _lib.call("stb_volume_cl_bf16", _p(None), _p(None), _p(l), _p(r), _p(vol), B, 0, 0, C, H, W, maxdisp4,
-                      ct_pad, int(mask_left), _stream())
+        vol = torch.empty(B, maxdisp4, H, W, ct_pad, device=l.device, dtype=self.dtype)
+        with self.prof.bracket("volume_cl16", 0.0, 4.0 * 2 * l.numel() + 2.0 * vol.numel()):
+            _lib.call("stb_volume_cl16", _p(None), _p(None), _p(l), _p(r), _p(vol), self.f16, B, 0, 0, C, H, W,
+                      maxdisp4, ct_pad, int(mask_left), _stream())
         return vol
 
     # ---------------------------------------------------------------- conv family
     def conv(self, layer, x, act="none", residual=None):
-        assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 5
+        assert x.dtype == self.dtype and x.is_contiguous() and x.dim() == 5
         B, Di, Hi, Wi, Cin = x.shape
         plan = self._plan(layer, Cin)
         Do, Ho, Wo = plan.out_size(Di), plan.out_size(Hi), plan.out_size(Wi)
         out_fp32 = plan.cout < 8          # the 32->1 classifier feeds the fp32 soft-argmin head directly
-        out = torch.empty(B, Do, Ho, Wo, plan.cout, device=x.device,
-                          dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        out = torch.empty(B, Do, Ho, Wo, plan.cout, device=x.device, dtype=torch.float32 if out_fp32 else self.dtype)
         if residual is not None:
             assert residual.shape == out.shape and residual.is_contiguous()
-            if residual.dtype != torch.bfloat16:
-                residual = residual.to(torch.bfloat16)
-        fam = "conv3d_umma_bf16" if plan.umma_ok else "conv3d_taps_cl_bf16"
+            if residual.dtype != self.dtype:
+                residual = residual.to(self.dtype)
+        fam = "conv3d_umma" if plan.umma_ok else "conv3d_taps_cl16"
         fl, by = 0.0, 0.0
         if self.prof.enabled:
             fl, by = conv_work(plan.simt, (B, Cin, Di, Hi, Wi), (B, plan.cout, Do, Ho, Wo), 2, residual is not None)
         with self.prof.bracket(fam, fl, by):
             if plan.umma_ok:
-                tr = plan.tr
-                nsteps, nh, nw = (Di, Hi, Wi) if tr else (Do, Ho, Wo)
-                _lib.call("stb_conv3d_umma_bf16", _p(x), _p(plan.wt), _p(plan.shift), _p(residual), _p(out),
-                          B, Cin, Di, Hi, Wi, plan.cout, plan.cout, Do, Ho, Wo, plan.ntaps, plan.c_dz, plan.c_dh,
-                          plan.c_dw, plan.c_widx, plan.nwtiles, plan.nclass, plan.c_tb, plan.c_te, plan.c_od0,
-                          plan.c_oh0, plan.c_ow0, plan.out_stride, nsteps, nh, nw, plan.in_off, plan.in_off,
-                          ACT[act], int(out_fp32), BO_MODE, self.dchunk, _stream())
+                nsteps, nh, nw = (Di, Hi, Wi) if plan.tr else (Do, Ho, Wo)
+                ws = self._workspace(out.numel(), x.device) if plan.nk > 1 else None
+                _lib.call("stb_conv3d_umma", _p(x), _p(plan.wt), _p(plan.shift), _p(residual), _p(out), _p(ws),
+                          self.f16, B, Cin, plan.kc, Di, Hi, Wi, plan.cout, plan.cout, Do, Ho, Wo, plan.ntaps,
+                          plan.c_dz, plan.c_dh, plan.c_dw, plan.c_sub, plan.c_widx, plan.nwtiles, plan.nclass,
+                          plan.c_tb, plan.c_te, plan.c_od0, plan.c_oh0, plan.c_ow0, plan.in_stride, plan.out_stride,
+                          nsteps, nh, nw, plan.in_off, plan.in_off, ACT[act], int(out_fp32),
+                          BO_MODE | (ES_VARIANT << 1), self.dchunk, _stream())
             else:
                 sp = plan.simt
                 for sel, dd, dh, dw, T, in_s, out_s, (od0, oh0, ow0) in sp.classes:
@@ -200,9 +234,9 @@ class UmmaBackend:
                     nw = (Wo - ow0 + out_s - 1) // out_s
                     if nd <= 0 or nh <= 0 or nw <= 0:
                         continue
-                    _lib.call("stb_conv3d_taps_cl_bf16", _p(x), _p(sel), _p(sp.shift), _p(residual), _p(out),
-                              int(out_fp32), B, Cin, Di, Hi, Wi, plan.cout, Do, Ho, Wo, T, dd, dh, dw, in_s, out_s,
-                              od0, oh0, ow0, nd, nh, nw, ACT[act], _stream())
+                    _lib.call("stb_conv3d_taps_cl16", _p(x), _p(sel), _p(sp.shift), _p(residual), _p(out),
+                              int(out_fp32), self.f16, B, Cin, Di, Hi, Wi, plan.cout, Do, Ho, Wo, T, dd, dh, dw, in_s,
+                              out_s, od0, oh0, ow0, nd, nh, nw, ACT[act], _stream())
         return out
 
     # ---------------------------------------------------------------- head (layout exit)
@@ -214,21 +248,25 @@ class UmmaBackend:
 
 
 # layout helpers for tests / callers holding reference-layout tensors
-def to_channels_last_bf16(x: torch.Tensor, cpad: Optional[int] = None) -> torch.Tensor:
+def to_channels_last(x: torch.Tensor, cpad: Optional[int] = None, dtype=torch.bfloat16) -> torch.Tensor:
     x = ops._f32c(x)
     B, C = x.shape[:2]
     S = x.numel() // (B * C)
     cpad = cpad or C
-    out = torch.empty((B,) + tuple(x.shape[2:]) + (cpad,), device=x.device, dtype=torch.bfloat16)
-    _lib.call("stb_ncdhw_to_cl_bf16", _p(x), _p(out), B, C, S, cpad, _stream())
+    out = torch.empty((B,) + tuple(x.shape[2:]) + (cpad,), device=x.device, dtype=dtype)
+    _lib.call("stb_ncdhw_to_cl16", _p(x), _p(out), int(dtype == torch.float16), B, C, S, cpad, _stream())
     return out
 
 
-def from_channels_last_bf16(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
-    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+def from_channels_last(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+    assert x.dtype in (torch.bfloat16, torch.float16) and x.is_contiguous()
     B, cpad = x.shape[0], x.shape[-1]
     c = c or cpad
     S = x.numel() // (B * cpad)
     out = torch.empty((B, c) + tuple(x.shape[1:-1]), device=x.device, dtype=torch.float32)
-    _lib.call("stb_cl_bf16_to_ncdhw", _p(x), _p(out), B, c, S, cpad, _stream())
+    _lib.call("stb_cl16_to_ncdhw", _p(x), _p(out), int(x.dtype == torch.float16), B, c, S, cpad, _stream())
     return out
+
+
+to_channels_last_bf16 = to_channels_last
+from_channels_last_bf16 = from_channels_last

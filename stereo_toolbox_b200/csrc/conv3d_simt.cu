@@ -12,9 +12,24 @@
 // 4 consecutive w positions.  Input channels are staged in chunks of CK through shared memory
 // together with the [tap][ck][32] weight slab.  This is the bit-faithful path (fp32 FMA, same
 // summation structure per output up to ordering); the tensor-core path lives in conv3d_umma.cu.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace {
+
+__device__ __forceinline__ float ld16(const void* base, size_t i, int f16) {
+    return f16 ? __half2float(reinterpret_cast<const __half*>(base)[i])
+               : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
+}
+__device__ __forceinline__ uint32_t pk16(float a, float b, int f16) {
+    if (f16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void st16(void* base, size_t i, float v, int f16) {
+    if (f16) reinterpret_cast<__half*>(base)[i] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(base)[i] = __float2bfloat16(v);
+}
 
 constexpr int CT_THREADS = 128;
 constexpr int CO_TILE = 32;
@@ -23,7 +38,7 @@ constexpr int MAX_TAPS = 64;
 
 struct ConvArgs {
     const void* x; const float* wt; const float* shift; const void* residual; void* out;
-    int out_fp32;
+    int out_fp32, f16;
     int B, Cin, Di, Hi, Wi, Cout, Do, Ho, Wo;
     int ntaps, is, os, od0, oh0, ow0, nd, nh, nw, act;
     int min_d, min_h, min_w, ED, EH, EW, EWp, CK;   // staged input extent per channel
@@ -76,8 +91,7 @@ conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
             if (ci < a.Cin && ew < a.EW && (unsigned)id < (unsigned)a.Di && (unsigned)ih < (unsigned)a.Hi &&
                 (unsigned)iw < (unsigned)a.Wi) {
                 if (CL)
-                    v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.x)[
-                        ((((size_t)b * a.Di + id) * a.Hi + ih) * a.Wi + iw) * a.Cin + ci]);
+                    v = ld16(a.x, ((((size_t)b * a.Di + id) * a.Hi + ih) * a.Wi + iw) * a.Cin + ci, a.f16);
                 else
                     v = __ldg(reinterpret_cast<const float*>(a.x) + ((size_t)b * a.Cin + ci) * in_vol +
                               (size_t)id * in_plane + (size_t)ih * a.Wi + iw);
@@ -124,7 +138,7 @@ conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
         const int cob = co0 + warp * 8;
         if (cob >= a.Cout) return;
         const int nch = min(8, a.Cout - cob);
-        const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(a.residual);
+        const void* res = a.residual;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int jw = jw0 + quad * 4 + j;
@@ -136,7 +150,7 @@ conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
                 float v = acc[i][j];
                 if (i < nch) {
                     if (a.shift) v += __ldg(a.shift + cob + i);
-                    if (res) v += __bfloat162float(res[vox * a.Cout + cob + i]);
+                    if (res) v += ld16(res, vox * a.Cout + cob + i, a.f16);
                 }
                 f[i] = stb_act(v, a.act);
             }
@@ -146,18 +160,16 @@ conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
                 for (int i = 0; i < 8; ++i)
                     if (i < nch) op[i] = f[i];
             } else {
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + vox * a.Cout + cob;
+                uint16_t* op = reinterpret_cast<uint16_t*>(a.out) + vox * a.Cout + cob;
                 if (nch == 8 && (a.Cout & 7) == 0) {
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
-                    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
                     uint4 o;
-                    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-                    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                    o.x = pk16(f[0], f[1], a.f16); o.y = pk16(f[2], f[3], a.f16);
+                    o.z = pk16(f[4], f[5], a.f16); o.w = pk16(f[6], f[7], a.f16);
                     *reinterpret_cast<uint4*>(op) = o;
                 } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        if (i < nch) op[i] = __float2bfloat16(f[i]);
+                        if (i < nch) st16(op, i, f[i], a.f16);
                 }
             }
         }
@@ -186,7 +198,7 @@ conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
 
 }  // namespace
 
-static int conv3d_taps_launch(bool cl, int out_fp32, const void* x, const float* wt, const float* shift,
+static int conv3d_taps_launch(bool cl, int out_fp32, int f16, const void* x, const float* wt, const float* shift,
                               const void* residual, void* out, int B, int Cin, int Di, int Hi, int Wi, int Cout,
                               int Do, int Ho, int Wo, int ntaps, const int* dd, const int* dh, const int* dw,
                               int in_stride, int out_stride, int od0, int oh0, int ow0, int nd, int nh, int nw,
@@ -198,7 +210,7 @@ static int conv3d_taps_launch(bool cl, int out_fp32, const void* x, const float*
     if ((nd - 1) * out_stride + od0 >= Do || (nh - 1) * out_stride + oh0 >= Ho || (nw - 1) * out_stride + ow0 >= Wo)
         return STB_E_BADARG;
     ConvArgs a;
-    a.x = x; a.wt = wt; a.shift = shift; a.residual = residual; a.out = out; a.out_fp32 = out_fp32;
+    a.x = x; a.wt = wt; a.shift = shift; a.residual = residual; a.out = out; a.out_fp32 = out_fp32; a.f16 = f16;
     a.B = B; a.Cin = Cin; a.Di = Di; a.Hi = Hi; a.Wi = Wi; a.Cout = Cout; a.Do = Do; a.Ho = Ho; a.Wo = Wo;
     a.ntaps = ntaps; a.is = in_stride; a.os = out_stride; a.od0 = od0; a.oh0 = oh0; a.ow0 = ow0;
     a.nd = nd; a.nh = nh; a.nw = nw; a.act = act;
@@ -249,15 +261,15 @@ extern "C" int stb_conv3d_taps_f32(const float* x, const float* wt, const float*
                                    int Wo, int ntaps, const int* dd, const int* dh, const int* dw, int in_stride,
                                    int out_stride, int od0, int oh0, int ow0, int nd, int nh, int nw, int act,
                                    void* stream) {
-    return conv3d_taps_launch(false, 1, x, wt, shift, residual, out, B, Cin, Di, Hi, Wi, Cout, Do, Ho, Wo, ntaps, dd,
+    return conv3d_taps_launch(false, 1, 0, x, wt, shift, residual, out, B, Cin, Di, Hi, Wi, Cout, Do, Ho, Wo, ntaps, dd,
                               dh, dw, in_stride, out_stride, od0, oh0, ow0, nd, nh, nw, act, stream);
 }
 
-extern "C" int stb_conv3d_taps_cl_bf16(const void* x, const float* wt, const float* shift, const void* residual,
-                                       void* out, int out_fp32, int B, int Cin, int Di, int Hi, int Wi, int Cout,
+extern "C" int stb_conv3d_taps_cl16(const void* x, const float* wt, const float* shift, const void* residual,
+                                    void* out, int out_fp32, int f16, int B, int Cin, int Di, int Hi, int Wi, int Cout,
                                        int Do, int Ho, int Wo, int ntaps, const int* dd, const int* dh, const int* dw,
                                        int in_stride, int out_stride, int od0, int oh0, int ow0, int nd, int nh,
                                        int nw, int act, void* stream) {
-    return conv3d_taps_launch(true, out_fp32, x, wt, shift, residual, out, B, Cin, Di, Hi, Wi, Cout, Do, Ho, Wo,
+    return conv3d_taps_launch(true, out_fp32, f16, x, wt, shift, residual, out, B, Cin, Di, Hi, Wi, Cout, Do, Ho, Wo,
                               ntaps, dd, dh, dw, in_stride, out_stride, od0, oh0, ow0, nd, nh, nw, act, stream);
 }

@@ -2,23 +2,30 @@
 // WITHOUT materialising im2col -- every filter tap is a row-shifted *view* of one TMA-staged,
 // zero-padded activation tile in shared memory.
 //
-//   activations : channels-last NDHWC bf16  x[b][d][h][w][c]
-//   weights     : tap-major, K-major bf16   wt[tap][kchunk][co][KC]  (eval BatchNorm scale folded in)
-//   accumulate  : fp32 in TMEM; epilogue = + shift[co] (+ residual) -> ReLU/LeakyReLU/Mish -> bf16 (or fp32)
+//   activations : channels-last NDHWC, 16-bit (bf16 or fp16)  x[b][d][h][w][c]
+//   weights     : tap-major, K-major 16-bit  wt[tile][kchunk][co][KC]  (eval BatchNorm scale folded in)
+//   accumulate  : fp32 in TMEM; epilogue = (+ fp32 partial) + shift[co] (+ residual) -> act -> 16-bit (or fp32)
 //
 // Work item (one CTA): an (h-tile, w-tile) column of the volume marching along depth.  Each input
-// depth-plane tile  [(TH+span_h) x 32 voxels x Cin]  is loaded ONCE by TMA (5-D box, out-of-bounds
+// depth-plane tile  [(TH+span_h) x 32 voxels x KC]  is loaded ONCE by TMA (5-D box, out-of-bounds
 // = zero = conv padding) into a ring of shared-memory slots.  Rows of the UMMA A operand are the
 // flattened (h, w) positions of the *padded* tile (row pitch 32 voxels), so tap (dz, dh, dw) is the same
-// tile with its descriptor start address advanced by (dh*32 + dw) rows: the 128 rows of an M-tile
-// are 4 padded rows; columns >= TW of each padded row are junk outputs that the epilogue skips.
-// This covers Conv3d k3 s1 p1 (27 taps), k1 (1 tap) and every output-parity class of
-// ConvTranspose3d k3 s2 p1 op1 / k4 s2 p1 (taps with offsets {0,+1}/{-1,0,+1}, strided store);
-// reference layers: PSMNet/submodule.py:16-19, PSMNet/stackhourglass.py:14-29, GwcNet/gwcnet.py:72-93.
+// tile with its descriptor start address advanced by (dh*32 + dw) rows (verified on hardware by
+// probe/umma_probe.cu: the 128B/64B/32B swizzles are functions of the absolute smem address, base_offset
+// stays 0): the 128 rows of an M-tile are 4 padded rows; columns >= TW of each padded row are junk outputs
+// that the epilogue skips.  Flavours, all expressed as tap tables built on the host:
+//   Conv3d k3 s1 p1 (27 taps), k1 (1 tap)                       PSMNet/submodule.py:16-19
+//   Conv3d k3 s2 p1: the input plane is staged as 4 (h,w)-parity sub-tiles (TMA element strides 2), so a
+//     stride-2 tap is again a unit-stride row shift inside one sub-tile; depth advances 2 planes per step
+//   ConvTranspose3d k3 s2 p1 op1 / k4 s2 p1: 8 output-parity classes share the staged tile; each class is
+//     an accumulator round of 1..8 taps stored with stride 2    PSMNet/stackhourglass.py:25-29
+// Input channels beyond one K-chunk (64, or 32 for stride 2) are handled by the host as K-split passes that
+// chain through an fp32 partial buffer; output channels whose weight tiles do not fit in smem as N-split passes.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane, also owns
 // TMEM alloc/dealloc), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Pipelines:
 // plane ring (full/empty mbarriers, released by tcgen05.commit) and a 2-deep TMEM accumulator ring.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -31,33 +38,49 @@ constexpr int MAX_UTAPS = 64;
 constexpr int MAX_UCLASS = 8;
 constexpr int MAX_RING = 6;
 constexpr int UMMA_THREADS = 192;
+constexpr size_t SMEM_CAP = 227 * 1024;
 
-struct UTap { int8_t dz; int8_t pad0; int16_t rowoff; uint16_t widx; uint16_t pad1; };
+struct UTap { int8_t dz; uint8_t sub; int16_t rowoff; uint16_t widx; uint16_t pad1; };
 struct UClass { uint16_t tap_begin, tap_end; int8_t od0, oh0, ow0, pad; };
 
 struct UArgs {
-    const __nv_bfloat16* residual;   // NDHWC, Cout_total channels (nullable)
-    void* out;                       // bf16 NDHWC (Cout_total) or fp32
+    const void* residual;            // NDHWC 16-bit, Cout_total channels (nullable)
+    const float* partial;            // fp32 [.., Cout_total] partial sums of earlier K-split passes (nullable)
+    void* out;                       // 16-bit NDHWC (Cout_total) or fp32
     const float* shift;              // [Cout_total] (nullable)
-    int B, Di, Hi, Wi, Do, Ho, Wo;
-    int Cn, Cn_valid, cout_off, Cout_total, w_rows, nwtiles;
-    int TH, TW, nM, box_h;
-    int sd_in, dzmin, dzmax, R;
+    int B, Do, Ho, Wo;
+    int Cn, Cn_valid, cout_off, Cout_total, w_rows, w_tile_stride, w_kc_off, nwtiles;
+    int TH, TW, nM;
+    int sd_in, dzmin, dzmax, R, in_stride, nsub;
     int out_stride, nclass;
     int nsteps, dchunk, nchunks, tiles_h, tiles_w;
-    int in_h_off, in_w_off;
-    int act, out_fp32;
-    int KC, NKC, ROWB, layout, bo_mode;
+    int in_h_off, in_w_off, cin_off;
+    int act, out_fp32, f16;
+    int ROWB, layout, bo_mode;
     int nclass_h, nclass_w;          // class output extents per step in h/w (positions)
     uint32_t plane_bytes, chunk_bytes, wtile_bytes, w_bytes_total, tmem_cols;
     UClass cls[MAX_UCLASS];
     UTap taps[MAX_UTAPS];
-    int ntaps;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
+    if (f16) {
+        __half2 v = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t w, int f16) {
+    if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+__device__ __forceinline__ float load16(const uint16_t* p, int f16) {
+    return f16 ? __half2float(*reinterpret_cast<const __half*>(p)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
+}
+__device__ __forceinline__ void store16(uint16_t* p, float v, int f16) {
+    if (f16) *reinterpret_cast<__half*>(p) = __float2half_rn(v);
+    else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16(v);
 }
 
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
@@ -108,26 +131,27 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             prefetch_tmap(&tm_x);
             prefetch_tmap(&tm_w);
             mbar_arrive_expect_tx(bar_w, a.w_bytes_total);
-            const int ntiles = a.nwtiles * a.NKC;
-            for (int i = 0; i < ntiles; ++i)
-                tma_load_2d(sW + (size_t)i * a.wtile_bytes, &tm_w, bar_w, 0, i * a.w_rows + a.cout_off);
-            const int ih0 = jh0 * 1 + a.in_h_off, iw0 = jw0 * 1 + a.in_w_off;
+            for (int i = 0; i < a.nwtiles; ++i)
+                tma_load_2d(sW + (size_t)i * a.wtile_bytes, &tm_w, bar_w, 0,
+                            (i * a.w_tile_stride + a.w_kc_off) * a.w_rows + a.cout_off);
+            const int ih0 = (jh0 + a.in_h_off) * a.in_stride, iw0 = (jw0 + a.in_w_off) * a.in_stride;
             for (int n = 0; n < nplanes; ++n) {
                 const int slot = n % a.R;
                 mbar_wait(&plane_empty[slot], ((n / a.R) & 1) ^ 1);
-                mbar_arrive_expect_tx(&plane_full[slot], (uint32_t)a.NKC * a.chunk_bytes);
+                mbar_arrive_expect_tx(&plane_full[slot], (uint32_t)a.nsub * a.chunk_bytes);
                 uint8_t* dst = sP + (size_t)slot * a.plane_bytes;
-                for (int kc = 0; kc < a.NKC; ++kc)
-                    tma_load_5d(dst + (size_t)kc * a.chunk_bytes, &tm_x, &plane_full[slot], kc * a.KC, iw0, ih0,
-                                p_first + n, b);
+                for (int sb = 0; sb < a.nsub; ++sb)       // sub-tile sb = (h parity, w parity) for stride 2
+                    tma_load_5d(dst + (size_t)sb * a.chunk_bytes, &tm_x, &plane_full[slot], a.cin_off,
+                                iw0 + (sb & 1), ih0 + (sb >> 1), p_first + n, b);
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            const uint32_t idesc = instr_desc_f16(128, a.Cn, 1);
+            const uint32_t idesc = instr_desc_f16(128, a.Cn, a.f16 ? 0 : 1);
             const uint32_t sbo = 8 * a.ROWB;
             const uint32_t w0 = smem_u32(sW), p0 = smem_u32(sP);
+            const int ksteps = a.ROWB / 32;
             mbar_wait(bar_w, 0);
             int waited = 0;                       // planes [0, waited) are known to be resident
             int round = 0;
@@ -149,18 +173,15 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         for (int tp = cl.tap_begin; tp < cl.tap_end; ++tp) {
                             const UTap tap = a.taps[tp];
                             const int n = (s * a.sd_in + tap.dz) - p_first;
-                            const uint32_t abase = p0 + (uint32_t)(n % a.R) * a.plane_bytes +
+                            const uint32_t abase = p0 + (uint32_t)(n % a.R) * a.plane_bytes + tap.sub * a.chunk_bytes +
                                                    (uint32_t)(128 * m + tap.rowoff) * a.ROWB;
-                            const uint32_t bbase = w0 + (uint32_t)(tap.widx * a.NKC) * a.wtile_bytes;
-                            for (int kc = 0; kc < a.NKC; ++kc) {
-                                for (int ks = 0; ks < a.KC / 16; ++ks) {
-                                    const uint32_t aaddr = abase + kc * a.chunk_bytes + ks * 32;
-                                    const uint32_t baddr = bbase + kc * a.wtile_bytes + ks * 32;
-                                    const uint32_t abo = a.bo_mode ? ((aaddr >> 7) & 7) : 0;
-                                    mma_f16_ss(dcol, smem_desc(aaddr, 16, sbo, a.layout, abo),
-                                               smem_desc(baddr, 16, sbo, a.layout, 0), idesc, acc);
-                                    acc = 1;
-                                }
+                            const uint32_t bbase = w0 + (uint32_t)tap.widx * a.wtile_bytes;
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                const uint32_t aaddr = abase + ks * 32, baddr = bbase + ks * 32;
+                                const uint32_t abo = a.bo_mode ? ((aaddr >> 7) & 7) : 0;
+                                mma_f16_ss(dcol, smem_desc(aaddr, 16, sbo, a.layout, abo),
+                                           smem_desc(baddr, 16, sbo, a.layout, 0), idesc, acc);
+                                acc = 1;
                             }
                         }
                     }
@@ -176,6 +197,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // ================================ epilogue warps ================================
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
         const size_t ostride_w = (size_t)a.Cout_total;
+        const int f16 = a.f16;
         for (int round = 0; round < nouts; ++round) {
             const int buf = round & 1;
             const int s = s_lo + round / a.nclass;
@@ -202,13 +224,28 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         float f[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                        const size_t eoff = vox * ostride_w + a.cout_off + c0;
+                        if (a.partial) {
+                            const float* pp = a.partial + eoff;
+                            if (nch == 32) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 pv = __ldg(reinterpret_cast<const float4*>(pp) + i);
+                                    f[i * 4] += pv.x; f[i * 4 + 1] += pv.y; f[i * 4 + 2] += pv.z; f[i * 4 + 3] += pv.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (i < nch) f[i] += __ldg(pp + i);
+                            }
+                        }
                         if (a.shift) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
                                 if (i < nch) f[i] += __ldg(a.shift + a.cout_off + c0 + i);
                         }
                         if (a.residual) {
-                            const __nv_bfloat16* rp = a.residual + vox * ostride_w + a.cout_off + c0;
+                            const uint16_t* rp = reinterpret_cast<const uint16_t*>(a.residual) + eoff;
                             if (nch == 32) {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
@@ -216,40 +253,46 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                                     const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                                     for (int j = 0; j < 4; ++j) {
-                                        __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-                                        f[i * 8 + j * 2] += __low2float(h2);
-                                        f[i * 8 + j * 2 + 1] += __high2float(h2);
+                                        const float2 h2 = unpack16(rw[j], f16);
+                                        f[i * 8 + j * 2] += h2.x;
+                                        f[i * 8 + j * 2 + 1] += h2.y;
                                     }
                                 }
                             } else {
 #pragma unroll
                                 for (int i = 0; i < 32; ++i)
-                                    if (i < nch) f[i] += __bfloat162float(rp[i]);
+                                    if (i < nch) f[i] += load16(rp + i, f16);
                             }
                         }
 #pragma unroll
                         for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], a.act);
                         if (a.out_fp32) {
-                            float* op = reinterpret_cast<float*>(a.out) + vox * ostride_w + a.cout_off + c0;
+                            float* op = reinterpret_cast<float*>(a.out) + eoff;
+                            if (nch == 32) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i < nch) op[i] = f[i];
+                                for (int i = 0; i < 8; ++i)
+                                    reinterpret_cast<float4*>(op)[i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (i < nch) op[i] = f[i];
+                            }
                         } else {
-                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + vox * ostride_w + a.cout_off + c0;
+                            uint16_t* op = reinterpret_cast<uint16_t*>(a.out) + eoff;
                             if (nch == 32) {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     uint4 o;
-                                    o.x = pack_bf16(f[i * 8 + 0], f[i * 8 + 1]);
-                                    o.y = pack_bf16(f[i * 8 + 2], f[i * 8 + 3]);
-                                    o.z = pack_bf16(f[i * 8 + 4], f[i * 8 + 5]);
-                                    o.w = pack_bf16(f[i * 8 + 6], f[i * 8 + 7]);
+                                    o.x = pack16(f[i * 8 + 0], f[i * 8 + 1], f16);
+                                    o.y = pack16(f[i * 8 + 2], f[i * 8 + 3], f16);
+                                    o.z = pack16(f[i * 8 + 4], f[i * 8 + 5], f16);
+                                    o.w = pack16(f[i * 8 + 6], f[i * 8 + 7], f16);
                                     reinterpret_cast<uint4*>(op)[i] = o;
                                 }
                             } else {
 #pragma unroll
                                 for (int i = 0; i < 32; ++i)
-                                    if (i < nch) op[i] = __float2bfloat16(f[i]);
+                                    if (i < nch) store16(op + i, f[i], f16);
                             }
                         }
                     }
@@ -267,51 +310,51 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
 }  // namespace
 
-// Host entry.  x: [B,Di,Hi,Wi,Cin] bf16; wt: [ntaps][NKC][Cout_total][KC] bf16 (KC = min(Cin,64));
-// out/residual: [B,Do,Ho,Wo,Cout_total] (bf16, or fp32 out with out_fp32=1).  One call = one conv layer
-// flavour expressed as `nclass` output classes (1 for a plain conv, 8 for a stride-2 transposed conv):
-// class c owns taps [tap_begin[c], tap_end[c]) and writes outputs (s*os+od0, jh*os+oh0, jw*os+ow0).
-// tap t reads input plane (s + dz[t]) at tile-relative offset (dh[t], dw[t]) >= 0 and uses weight tile
-// widx[t].  in_h_off/in_w_off: tile origin of the staged input relative to the class position origin.
-extern "C" int stb_conv3d_umma_bf16(const void* x, const void* wt, const float* shift, const void* residual, void* out,
-                                    int B, int Cin, int Di, int Hi, int Wi, int Cout_total, int Cout_valid, int Do,
-                                    int Ho, int Wo, int ntaps, const int* dz, const int* dh, const int* dw,
-                                    const int* widx, int nwtiles, int nclass, const int* tap_begin,
-                                    const int* tap_end, const int* od0, const int* oh0, const int* ow0,
-                                    int out_stride, int nsteps, int nclass_h, int nclass_w, int in_h_off,
-                                    int in_w_off, int act, int out_fp32, int bo_mode, int dchunk, void* stream) {
-    if (!x || !wt || !out || !dz || !dh || !dw || !widx || !tap_begin || !tap_end || !od0 || !oh0 || !ow0)
+// Host entry -- see include/stb200.h for the argument contract.
+extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift, const void* residual, void* out,
+                               float* ws, int f16, int B, int Cin, int KC, int Di, int Hi, int Wi, int Cout_total,
+                               int Cout_valid, int Do, int Ho, int Wo, int ntaps, const int* dz, const int* dh,
+                               const int* dw, const int* sub, const int* widx, int nwtiles, int nclass,
+                               const int* tap_begin, const int* tap_end, const int* od0, const int* oh0,
+                               const int* ow0, int in_stride, int out_stride, int nsteps, int nclass_h, int nclass_w,
+                               int in_h_off, int in_w_off, int act, int out_fp32, int flags, int dchunk,
+                               void* stream) {
+    if (!x || !wt || !out || !dz || !dh || !dw || !sub || !widx || !tap_begin || !tap_end || !od0 || !oh0 || !ow0)
         return STB_E_BADARG;
     if (B <= 0 || ntaps <= 0 || ntaps > MAX_UTAPS || nclass <= 0 || nclass > MAX_UCLASS || nsteps <= 0) return STB_E_BADARG;
-    if (Cin % 16 || Cin < 16 || (Cin > 64 && Cin % 64)) return STB_E_UNSUPPORTED;
-    if (out_stride < 1 || out_stride > 2) return STB_E_UNSUPPORTED;
+    if (KC != 16 && KC != 32 && KC != 64) return STB_E_UNSUPPORTED;      // one swizzle row = one voxel's K-chunk
+    if (Cin % KC) return STB_E_UNSUPPORTED;
+    if (in_stride < 1 || in_stride > 2 || out_stride < 1 || out_stride > 2) return STB_E_UNSUPPORTED;
+    if (in_stride == 2 && out_stride != 1) return STB_E_UNSUPPORTED;
+    const int nk = Cin / KC;                       // K-split passes
+    if (nk > 1 && !ws) return STB_E_BADARG;        // needs the fp32 partial workspace [B,Do,Ho,Wo,Cout_total]
     UArgs a;
     memset(&a, 0, sizeof(a));
-    a.KC = Cin < 64 ? Cin : 64;
-    a.NKC = Cin / a.KC;
-    a.ROWB = a.KC * 2;
+    a.f16 = f16;
+    a.ROWB = KC * 2;
     a.layout = a.ROWB == 128 ? SW_128B : a.ROWB == 64 ? SW_64B : SW_32B;
     const CUtensorMapSwizzle cusw = a.ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                     : a.ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-    a.bo_mode = bo_mode;
-    // N per launch: keep all weight tiles resident (<= ~112 KB) -> split Cout across launches if needed
-    int Cpad = (Cout_total + 15) / 16 * 16;     // weights are padded to a multiple of 16 rows per tile by the packer
-    int Cn = Cpad;
-    while ((size_t)nwtiles * a.NKC * Cn * a.ROWB > 112 * 1024 && Cn > 16) Cn = (Cn / 2 + 15) / 16 * 16;
-    if ((size_t)nwtiles * a.NKC * Cn * a.ROWB > 150 * 1024) return STB_E_SMEM;
-    if (Cn > 256) return STB_E_UNSUPPORTED;
+    const CUtensorMapDataType cudt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    a.bo_mode = flags & 1;
+    const int es_variant = (flags >> 1) & 1;
+    a.in_stride = in_stride;
+    a.nsub = in_stride == 2 ? 4 : 1;
+    a.sd_in = in_stride;
     int maxdh = 0, maxdw = 0, dzmin = 127, dzmax = -127;
     for (int t = 0; t < ntaps; ++t) {
-        if (dh[t] < 0 || dw[t] < 0 || dh[t] > 3 || dw[t] > 3 || widx[t] < 0 || widx[t] >= nwtiles) return STB_E_BADARG;
+        if (dh[t] < 0 || dw[t] < 0 || dh[t] > 3 || dw[t] > 3 || widx[t] < 0 || widx[t] >= nwtiles || sub[t] < 0 ||
+            sub[t] >= a.nsub)
+            return STB_E_BADARG;
         maxdh = dh[t] > maxdh ? dh[t] : maxdh;
         maxdw = dw[t] > maxdw ? dw[t] : maxdw;
         dzmin = dz[t] < dzmin ? dz[t] : dzmin;
         dzmax = dz[t] > dzmax ? dz[t] : dzmax;
         a.taps[t].dz = (int8_t)dz[t];
+        a.taps[t].sub = (uint8_t)sub[t];
         a.taps[t].rowoff = (int16_t)(dh[t] * TWP + dw[t]);
         a.taps[t].widx = (uint16_t)widx[t];
     }
-    a.ntaps = ntaps;
     for (int c = 0; c < nclass; ++c) {
         a.cls[c].tap_begin = (uint16_t)tap_begin[c];
         a.cls[c].tap_end = (uint16_t)tap_end[c];
@@ -319,30 +362,36 @@ extern "C" int stb_conv3d_umma_bf16(const void* x, const void* wt, const float* 
     }
     a.nclass = nclass;
     a.TW = TWP - maxdw;
-    a.dzmin = dzmin; a.dzmax = dzmax; a.sd_in = 1;
-    a.R = (dzmax - dzmin + 1) + 1;
-    if (a.R > MAX_RING) return STB_E_UNSUPPORTED;
-    a.residual = (const __nv_bfloat16*)residual; a.out = out; a.shift = shift;
-    a.B = B; a.Di = Di; a.Hi = Hi; a.Wi = Wi; a.Do = Do; a.Ho = Ho; a.Wo = Wo;
+    a.dzmin = dzmin; a.dzmax = dzmax;
+    const int window = dzmax - dzmin + 1;
+    a.B = B; a.Do = Do; a.Ho = Ho; a.Wo = Wo;
     a.Cout_total = Cout_total;
     a.out_stride = out_stride; a.nsteps = nsteps; a.nclass_h = nclass_h; a.nclass_w = nclass_w;
-    a.in_h_off = in_h_off; a.in_w_off = in_w_off; a.act = act; a.out_fp32 = out_fp32;
-    // tile height: as tall as TMEM (2 buffers x nM x Cn <= 512 cols) and shared memory allow
-    const size_t smem_cap = 220 * 1024;
-    int TH = 16;
-    for (;; TH -= 4) {
-        if (TH < 4) return STB_E_SMEM;
-        int nM = TH * TWP / 128;
-        if (2 * nM * Cn + 32 > 512) continue;       // +32: the epilogue reads TMEM in 32-column blocks
-        size_t plane = (size_t)a.NKC * (size_t)(TH + maxdh) * TWP * a.ROWB;
-        plane = (plane + 1023) & ~(size_t)1023;
-        size_t need = 2048 + (((size_t)nwtiles * a.NKC * Cn * a.ROWB + 1023) & ~(size_t)1023) + a.R * plane + 1024;
-        if (need <= smem_cap) break;
+    a.in_h_off = in_h_off; a.in_w_off = in_w_off;
+    const int Cpad = (Cout_total + 15) / 16 * 16;     // weight tiles are padded to a multiple of 16 rows by the packer
+    // ---- tiling: pick (Cn, TH, R) that fit shared memory; prefer tall tiles, then wide N
+    int Cn = Cpad > 256 ? 256 : Cpad, TH = 0, R = 0;
+    auto fits = [&](int cn, int th, int r) {
+        const int nM = th * TWP / 128;
+        if (2 * nM * cn + 32 > 512 || r > MAX_RING) return false;   // +32: the epilogue reads TMEM in 32-column blocks
+        const size_t wbytes = (((size_t)nwtiles * cn * a.ROWB) + 1023) & ~(size_t)1023;
+        const size_t plane = (size_t)a.nsub * (th + maxdh) * TWP * a.ROWB;
+        return 2048 + wbytes + (size_t)r * plane + 1024 <= SMEM_CAP;
+    };
+    for (bool found = false; !found;) {
+        for (int th = 16; th >= 4 && !found; th -= 4)
+            for (int r = window + a.sd_in; r >= window + 1 && !found; --r)
+                if (fits(Cn, th, r)) { TH = th; R = r; found = true; }
+        if (found) break;
+        if (Cn <= 16) return STB_E_SMEM;
+        Cn = (Cn / 2 + 15) / 16 * 16;
     }
     while (TH > 4 && TH - 4 >= nclass_h) TH -= 4;      // do not stage rows that do not exist
-    a.TH = TH; a.nM = TH * TWP / 128; a.box_h = TH + maxdh;
-    a.chunk_bytes = (uint32_t)(a.box_h * TWP * a.ROWB);
-    a.plane_bytes = (uint32_t)(((size_t)a.NKC * a.chunk_bytes + 1023) & ~(size_t)1023);
+    a.R = R;
+    a.TH = TH; a.nM = TH * TWP / 128;
+    const int box_h = TH + maxdh;
+    a.chunk_bytes = (uint32_t)(box_h * TWP * a.ROWB);
+    a.plane_bytes = (uint32_t)a.nsub * a.chunk_bytes;
     a.tiles_h = stb_ceil_div(nclass_h, a.TH);
     a.tiles_w = stb_ceil_div(nclass_w, a.TW);
     if (dchunk <= 0) {
@@ -362,32 +411,44 @@ extern "C" int stb_conv3d_umma_bf16(const void* x, const void* wt, const float* 
         uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)Di, (uint64_t)B};
         uint64_t str[4] = {(uint64_t)Cin * 2, (uint64_t)Wi * Cin * 2, (uint64_t)Hi * Wi * Cin * 2,
                            (uint64_t)Di * Hi * Wi * Cin * 2};
-        uint32_t box[5] = {(uint32_t)a.KC, (uint32_t)TWP, (uint32_t)a.box_h, 1, 1};
-        if (!umma_host::make_tmap(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, str, box, cusw))
-            return STB_E_DRIVER;
+        const uint32_t bm = (in_stride == 2 && !es_variant) ? 2u : 1u;     // box extent convention under element strides
+        uint32_t box[5] = {(uint32_t)KC, (uint32_t)TWP * bm, (uint32_t)box_h * bm, 1, 1};
+        uint32_t es[5] = {1, (uint32_t)in_stride, (uint32_t)in_stride, 1, 1};
+        if (!umma_host::make_tmap(&tm_x, cudt, 5, const_cast<void*>(x), dims, str, box, cusw, es)) return STB_E_DRIVER;
     }
-    cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+    cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
     a.w_rows = Cpad;
+    a.w_tile_stride = nk;
     a.nwtiles = nwtiles;
     const long long nblk = (long long)B * a.nchunks * a.tiles_h * a.tiles_w;
     if (nblk > 2147483647LL) return STB_E_BADARG;
-    for (int co = 0; co < Cpad; co += Cn) {
-        const int cn = (Cpad - co) < Cn ? (Cpad - co) : Cn;
-        a.Cn = cn;
-        a.cout_off = co;
-        a.Cn_valid = (Cout_valid - co) < cn ? (Cout_valid - co) : cn;
-        if (a.Cn_valid <= 0) break;
-        a.wtile_bytes = (uint32_t)(cn * a.ROWB);
-        a.w_bytes_total = (uint32_t)((size_t)nwtiles * a.NKC * a.wtile_bytes);
-        uint64_t dims[2] = {(uint64_t)a.KC, (uint64_t)nwtiles * a.NKC * Cpad};
-        uint64_t str[1] = {(uint64_t)a.KC * 2};
-        uint32_t box[2] = {(uint32_t)a.KC, (uint32_t)cn};
-        if (!umma_host::make_tmap(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wt), dims, str, box, cusw))
-            return STB_E_DRIVER;
-        size_t smem = 2048 + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
-        if (smem > smem_cap) return STB_E_SMEM;
-        conv3d_umma_kernel<<<(unsigned)nblk, UMMA_THREADS, smem, (cudaStream_t)stream>>>(tm_x, tm_w, a);
-        STB_CHECK_LAUNCH();
+    for (int kp = 0; kp < nk; ++kp) {
+        const bool last = kp == nk - 1;
+        a.cin_off = kp * KC;
+        a.w_kc_off = kp;
+        a.partial = kp > 0 ? ws : nullptr;
+        a.out = last ? out : (void*)ws;
+        a.out_fp32 = last ? out_fp32 : 1;
+        a.shift = last ? shift : nullptr;
+        a.residual = last ? residual : nullptr;
+        a.act = last ? act : STB_ACT_NONE;
+        for (int co = 0; co < Cpad; co += Cn) {
+            const int cn = (Cpad - co) < Cn ? (Cpad - co) : Cn;
+            a.Cn = cn;
+            a.cout_off = co;
+            a.Cn_valid = (Cout_valid - co) < cn ? (Cout_valid - co) : cn;
+            if (a.Cn_valid <= 0) break;
+            a.wtile_bytes = (uint32_t)(cn * a.ROWB);
+            a.w_bytes_total = (uint32_t)((size_t)nwtiles * a.wtile_bytes);
+            uint64_t dims[2] = {(uint64_t)KC, (uint64_t)nwtiles * nk * Cpad};
+            uint64_t str[1] = {(uint64_t)KC * 2};
+            uint32_t box[2] = {(uint32_t)KC, (uint32_t)cn};
+            if (!umma_host::make_tmap(&tm_w, cudt, 2, const_cast<void*>(wt), dims, str, box, cusw)) return STB_E_DRIVER;
+            size_t smem = 2048 + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
+            if (smem > SMEM_CAP) return STB_E_SMEM;
+            conv3d_umma_kernel<<<(unsigned)nblk, UMMA_THREADS, smem, (cudaStream_t)stream>>>(tm_x, tm_w, a);
+            STB_CHECK_LAUNCH();
+        }
     }
     return STB_OK;
 }

@@ -4,6 +4,8 @@ cd "$(dirname "$0")"
 out=${1:-/dev/stdout}
 {
 timeout 60 ./umma_probe halo
+timeout 60 ./umma_probe halo2 0
+timeout 60 ./umma_probe halo2 1
 for sw in 128 64 32; do
   for bo in 0 1; do
     for sh in 0 1 2 3 5 8 9; do

@@ -141,6 +141,48 @@ int main(int argc, char** argv) {
         printf("halo 5D OOB zero-fill + SW64 layout: %s (%d mismatches)\n", bad ? "FAIL" : "PASS", bad);
         return bad ? 1 : 0;
     }
+    if (argc >= 2 && !strcmp(argv[1], "halo2")) {
+        // stride-2 deinterleave by TMA elementStrides: tensor [N=1][D=2][H=9][W=13][C=32], element strides
+        // (1,2,2,1,1); box extents given in the ORIGINAL index space (2*8, 2*4) -> 8 x 4 voxels; start (-1,-1)
+        const int N = 1, D = 2, H = 9, W = 13, C = 32;
+        std::vector<__nv_bfloat16> h((size_t)N * D * H * W * C);
+        for (size_t i = 0; i < h.size(); ++i) h[i] = __float2bfloat16((float)(i % 4093) * 0.25f + 1.f);
+        __nv_bfloat16 *d, *dump;
+        CK(cudaMalloc(&d, h.size() * 2));
+        CK(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+        const int bw = 8, bh = 4, nelem = C * bw * bh;
+        CK(cudaMalloc(&dump, nelem * 2));
+        CK(cudaMemset(dump, 0xff, nelem * 2));
+        int variant = argc > 2 ? atoi(argv[2]) : 0;       // 0: boxDim = 2*n ; 1: boxDim = n
+        CUtensorMap tm;
+        uint64_t dims[5] = {C, W, H, D, N};
+        uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)D * H * W * C * 2};
+        uint32_t box[5] = {C, (uint32_t)(variant ? bw : 2 * bw), (uint32_t)(variant ? bh : 2 * bh), 1, 1};
+        uint32_t es[5] = {1, 2, 2, 1, 1};
+        if (!umma_host::make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, es)) {
+            printf("halo2 variant %d: tensor map encode FAILED\n", variant);
+            return 1;
+        }
+        halo_kernel<<<1, 128, nelem * 2 + 1024>>>(tm, dump, nelem, 0, -1, -1, 1, 0);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("halo2 variant %d: kernel failed: %s (byte count mismatch -> trap)\n", variant, cudaGetErrorString(e)); return 1; }
+        std::vector<__nv_bfloat16> o(nelem);
+        CK(cudaMemcpy(o.data(), dump, nelem * 2, cudaMemcpyDeviceToHost));
+        int bad = 0;
+        for (int r = 0; r < bw * bh; ++r) {
+            int ww = r % bw, hh = r / bw;
+            int gw = -1 + 2 * ww, gh = -1 + 2 * hh, gd = 1;
+            bool in = gw >= 0 && gw < W && gh >= 0 && gh < H;
+            for (int c = 0; c < C; ++c) {
+                float want = in ? __bfloat162float(h[((((size_t)0 * D + gd) * H + gh) * W + gw) * C + c]) : 0.f;
+                int pchunk = (c / 8) ^ (((r * 64) >> 7) & 3);
+                float got = __bfloat162float(o[(size_t)r * 32 + pchunk * 8 + c % 8]);
+                if (got != want) { if (bad < 5) printf("halo2 mismatch r=%d c=%d want %g got %g\n", r, c, want, got); ++bad; }
+            }
+        }
+        printf("halo2 (elementStrides=2, variant %d: boxDim=%s): %s (%d mismatches)\n", variant, variant ? "n" : "2n", bad ? "FAIL" : "PASS", bad);
+        return bad ? 1 : 0;
+    }
     if (argc < 4) { printf("usage\n"); return 1; }
     const int sw = atoi(argv[1]);
     Params p;

@@ -3,22 +3,38 @@
 // first 3x3x3 conv TMA-loads.  Replaces build_gwc_volume + build_concat_volume + torch.cat
 // (GwcNet/submodule.py:30-63, GwcNet/gwcnet.py:175-180; inline loop PSMNet/stackhourglass.py:111-120).
 // Products and the group mean are fp32; only the stored value is rounded to bf16.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace {
 
+__device__ __forceinline__ uint32_t pk16(float a, float b, int f16) {
+    if (f16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint16_t cv16(float a, int f16) {
+    if (f16) { __half v = __float2half_rn(a); return *reinterpret_cast<uint16_t*>(&v); }
+    __nv_bfloat16 v = __float2bfloat16(a);
+    return *reinterpret_cast<uint16_t*>(&v);
+}
+__device__ __forceinline__ float ld16(uint16_t w, int f16) {
+    if (f16) return __half2float(*reinterpret_cast<const __half*>(&w));
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&w));
+}
+
 constexpr int VT = 256;      // threads
 constexpr int VW = 32;       // w positions per CTA
 
-// grid (tiles_w, H, B). dynamic smem: 64*(VW+1) + 64*(VW+D) floats
+// grid (tiles_w, H, B). dynamic smem: NR*(VW+1) + NR*(VW+D) floats, NR = max(8, 8*cpg) staged rows
 __global__ void __launch_bounds__(VT)
 volume_cl_kernel(const float* __restrict__ gl, const float* __restrict__ gr, const float* __restrict__ cl,
-                 const float* __restrict__ cr, __nv_bfloat16* __restrict__ vol, int Cg, int G, int Cc, int H, int W,
-                 int D, int Ct, int Ct_pad, int mask_left) {
+                 const float* __restrict__ cr, uint16_t* __restrict__ vol, int Cg, int G, int Cc, int H, int W,
+                 int D, int Ct, int Ct_pad, int mask_left, int NR, int f16) {
     extern __shared__ __align__(16) float sm[];
     const int LP = VW + 1, RP = VW + D;           // row pitches; R window covers w in [w0-D+1, w0+VW)
-    float* Ls = sm;                                // [64][LP]
-    float* Rs = sm + 64 * LP;                      // [64][RP]
+    float* Ls = sm;                                // [NR][LP]
+    float* Rs = sm + NR * LP;                      // [NR][RP]
     const int w0 = blockIdx.x * VW, h = blockIdx.y, b = blockIdx.z;
     const int cpg = G > 0 ? Cg / G : 1;
     const size_t plane = (size_t)H * W;
@@ -32,7 +48,7 @@ volume_cl_kernel(const float* __restrict__ gl, const float* __restrict__ gr, con
         const bool gwc_chunk = oc0 + 8 <= G;       // all 8 output channels are correlation groups
         const int nrow = gwc_chunk ? 8 * cpg : 8;
         if (gwc_chunk) {
-            if (nrow > 64) return;                 // guarded on the host
+            if (nrow > NR) return;                 // guarded on the host
             const float* lsrc = gl + ((size_t)b * Cg + (size_t)oc0 * cpg) * plane + (size_t)h * W;
             const float* rsrc = gr + ((size_t)b * Cg + (size_t)oc0 * cpg) * plane + (size_t)h * W;
             for (int i = threadIdx.x; i < nrow * VW; i += VT) {
@@ -84,12 +100,10 @@ volume_cl_kernel(const float* __restrict__ gl, const float* __restrict__ gr, con
                     o[r] = v;
                 }
             }
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
             uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-            __nv_bfloat16* dst = vol + ((((size_t)b * D + d) * H + h) * W + w) * Ct_pad + oc0;
+            pk.x = pk16(o[0], o[1], f16); pk.y = pk16(o[2], o[3], f16);
+            pk.z = pk16(o[4], o[5], f16); pk.w = pk16(o[6], o[7], f16);
+            uint16_t* dst = vol + ((((size_t)b * D + d) * H + h) * W + w) * Ct_pad + oc0;
             *reinterpret_cast<uint4*>(dst) = pk;
         }
     }
@@ -97,8 +111,8 @@ volume_cl_kernel(const float* __restrict__ gl, const float* __restrict__ gr, con
 
 // NCDHW fp32 -> NDHWC bf16 and back (layout boundary of the tensor-core path; used by tests and by
 // models that enter / leave the path with reference-layout tensors)
-__global__ void ncdhw_to_cl_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, size_t S,
-                                   int Cpad) {
+__global__ void ncdhw_to_cl_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C, size_t S,
+                                   int Cpad, int f16) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const size_t s0 = (size_t)blockIdx.x * 32;
@@ -112,12 +126,12 @@ __global__ void ncdhw_to_cl_kernel(const float* __restrict__ src, __nv_bfloat16*
     for (int i = threadIdx.y; i < 32; i += 8) {
         const size_t sidx = s0 + i;
         const int c = c0 + threadIdx.x;
-        if (sidx < S && c < Cpad) dst[((size_t)b * S + sidx) * Cpad + c] = __float2bfloat16(tile[threadIdx.x][i]);
+        if (sidx < S && c < Cpad) dst[((size_t)b * S + sidx) * Cpad + c] = cv16(tile[threadIdx.x][i], f16);
     }
 }
 
-__global__ void cl_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, size_t S,
-                                   int Cpad) {
+__global__ void cl_to_ncdhw_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, int C, size_t S,
+                                   int Cpad, int f16) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const size_t s0 = (size_t)blockIdx.x * 32;
@@ -125,7 +139,7 @@ __global__ void cl_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float*
     for (int i = threadIdx.y; i < 32; i += 8) {
         const size_t sidx = s0 + i;
         const int c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (sidx < S && c < C) ? __bfloat162float(src[((size_t)b * S + sidx) * Cpad + c]) : 0.f;
+        tile[i][threadIdx.x] = (sidx < S && c < C) ? ld16(src[((size_t)b * S + sidx) * Cpad + c], f16) : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += 8) {
@@ -137,39 +151,40 @@ __global__ void cl_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float*
 
 }  // namespace
 
-extern "C" int stb_volume_cl_bf16(const float* gwc_l, const float* gwc_r, const float* cat_l, const float* cat_r,
-                                  void* vol, int B, int Cg, int G, int Cc, int H, int W, int D, int Ct_pad,
-                                  int mask_left, void* stream) {
+extern "C" int stb_volume_cl16(const float* gwc_l, const float* gwc_r, const float* cat_l, const float* cat_r,
+                               void* vol, int f16, int B, int Cg, int G, int Cc, int H, int W, int D, int Ct_pad,
+                               int mask_left, void* stream) {
     if (!vol || B <= 0 || H <= 0 || W <= 0 || D <= 0 || G < 0 || Cc < 0) return STB_E_BADARG;
     if (G > 0 && (!gwc_l || !gwc_r || Cg % G)) return STB_E_BADARG;
     if (Cc > 0 && (!cat_l || !cat_r)) return STB_E_BADARG;
     const int Ct = G + 2 * Cc;
     if (Ct <= 0 || Ct_pad < Ct || Ct_pad % 8 || G % 8) return STB_E_UNSUPPORTED;
-    if (G > 0 && 8 * (Cg / G) > 64) return STB_E_UNSUPPORTED;
+    const int NR = G > 0 ? (8 * (Cg / G) > 8 ? 8 * (Cg / G) : 8) : 8;
+    if (NR > 256) return STB_E_UNSUPPORTED;
     if (H > 65535 || B > 65535) return STB_E_BADARG;
-    size_t smem = (size_t)(64 * (VW + 1) + 64 * (VW + D)) * sizeof(float);
+    size_t smem = (size_t)(NR * (VW + 1) + NR * (VW + D)) * sizeof(float);
     if (smem > 200 * 1024) return STB_E_SMEM;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(volume_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(stb_ceil_div(W, VW), H, B);
-    volume_cl_kernel<<<grid, VT, smem, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r, (__nv_bfloat16*)vol, Cg, G, Cc,
-                                                            H, W, D, Ct, Ct_pad, mask_left);
+    volume_cl_kernel<<<grid, VT, smem, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r, (uint16_t*)vol, Cg, G, Cc, H, W, D,
+                                                            Ct, Ct_pad, mask_left, NR, f16);
     STB_CHECK_LAUNCH();
     return STB_OK;
 }
 
-extern "C" int stb_ncdhw_to_cl_bf16(const float* src, void* dst, int B, int C, long long S, int Cpad, void* stream) {
+extern "C" int stb_ncdhw_to_cl16(const float* src, void* dst, int f16, int B, int C, long long S, int Cpad, void* stream) {
     if (!src || !dst || B <= 0 || C <= 0 || S <= 0 || Cpad < C) return STB_E_BADARG;
     dim3 grid((unsigned)((S + 31) / 32), stb_ceil_div(Cpad, 32), B);
-    ncdhw_to_cl_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, C, (size_t)S, Cpad);
+    ncdhw_to_cl_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, C, (size_t)S, Cpad, f16);
     STB_CHECK_LAUNCH();
     return STB_OK;
 }
 
-extern "C" int stb_cl_bf16_to_ncdhw(const void* src, float* dst, int B, int C, long long S, int Cpad, void* stream) {
+extern "C" int stb_cl16_to_ncdhw(const void* src, float* dst, int f16, int B, int C, long long S, int Cpad, void* stream) {
     if (!src || !dst || B <= 0 || C <= 0 || S <= 0 || Cpad < C) return STB_E_BADARG;
     dim3 grid((unsigned)((S + 31) / 32), stb_ceil_div(C, 32), B);
-    cl_to_ncdhw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, C, (size_t)S, Cpad);
+    cl_to_ncdhw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const uint16_t*)src, dst, C, (size_t)S, Cpad, f16);
     STB_CHECK_LAUNCH();
     return STB_OK;
 }
