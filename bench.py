@@ -210,14 +210,20 @@ def main():
             "e2e": {"value": total_pairs / (ms_e2e / 1e3), "unit": "maps/s",
                     "h2d_bytes_per_step": int(left_h.numel() * 4 * 2), "d2h_bytes_per_step": int(out_h.numel() * 4)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": prof.roofline(precision),
-            "kernels": prof.summary()}
+            "kernels": prof.summary(), "layers": prof.layer_table()}
     if not a.no_cpu_baseline:
         r = cpu_reference_run(sd, a.cpu_sample, 1, 0, pair=(left_h[: a.cpu_sample].clone(), right_h[: a.cpu_sample].clone()))
         line["cpu_baseline"] = {"value": r["value"], "unit": "maps/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
         ref = r["disp"]
-        got = out_h[: a.cpu_sample] if rank == 0 else None
-        line["epe_vs_cpu_reference_px"] = float((got - ref).abs().mean())
+        # EPE vs the CPU fp32 reference on the same pair(s): (i) as benchmarked (torch-default TF32 2-D extractor,
+        # like the reference itself on a GPU), (ii) hot path alone (exact fp32 features fed to our kernels)
+        with torch.no_grad():
+            ls, rs = left[: a.cpu_sample], right[: a.cpu_sample]
+            line["epe_e2e_px"] = float((net(ls, rs).cpu() - ref).abs().mean())
+            net.feature_tf32 = False
+            line["epe_hot_path_px"] = float((net(ls, rs).cpu() - ref).abs().mean())
+            net.feature_tf32 = None
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -243,8 +249,10 @@ class KernelProfiler:
     def __init__(self):
         self.enabled = False
         self.records = []      # (family, flops, bytes, ev0, ev1)
+        self.details = {}      # layer signature -> [n, ms, flops]
+        self._detail_evs = []
 
-    def bracket(self, family, flops, nbytes):
+    def bracket(self, family, flops, nbytes, detail=""):
         prof = self
 
         class _Ctx:
@@ -258,6 +266,8 @@ class KernelProfiler:
                 if prof.enabled:
                     self_.e1.record()
                     prof.records.append((family, flops, nbytes, self_.e0, self_.e1))
+                    if detail:
+                        prof._detail_evs.append((detail, flops, self_.e0, self_.e1))
         return _Ctx()
 
     def _agg(self):
@@ -269,6 +279,14 @@ class KernelProfiler:
             d["flops"] += fl
             d["bytes"] += by
         return agg
+
+    def layer_table(self):
+        agg = {}
+        for d, fl, e0, e1 in self._detail_evs:
+            v = agg.setdefault(d, [0, 0.0, 0.0])
+            v[0] += 1; v[1] += e0.elapsed_time(e1); v[2] += fl
+        return {k: {"n": v[0], "avg_us": round(1e3 * v[1] / v[0], 1), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)}
+                for k, v in agg.items()}
 
     def summary(self):
         return {k: {"launches": v["n"], "ms_total": round(v["ms"], 3), "avg_us": round(1e3 * v["ms"] / max(1, v["n"]), 2),

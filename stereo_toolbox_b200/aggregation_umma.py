@@ -23,6 +23,7 @@ from .ops import ACT, _p, _stream
 BO_MODE = int(os.environ.get("STB_UMMA_BO_MODE", "0"))
 ES_VARIANT = int(os.environ.get("STB_TMA_ES_VARIANT", "0"))      # box extent convention under TMA element strides
 FORCE_SIMT = os.environ.get("STB_UMMA_FORCE_SIMT", "0") == "1"
+KWMERGE = os.environ.get("STB_UMMA_KWMERGE", "1") == "1"          # merge the 3 kw taps along N (N = 3*Cout) for k3 s1 convs
 SIMT_STRIDE2 = os.environ.get("STB_UMMA_SIMT_STRIDE2", "0") == "1"   # keep strided convs on the CUDA-core companion
 TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
 
@@ -107,8 +108,14 @@ class UmmaPlan:
             off = [(x - p) // in_stride for x, p in zip(e, par)]
             mn = min(off)
             tb.append(0)
+            self.merge = KWMERGE and in_stride == 1 and k == 3 and pad == 1
             for a in range(k):
                 for b in range(k):
+                    if self.merge:
+                        # one MMA per (kd,kh) against the 3 contiguous weight tiles (kd,kh,0..2): N = 3*Cout;
+                        # the epilogue realigns the three column blocks by 0/1/2 lanes (see conv3d_umma.cu)
+                        dz.append(e[a]); dh.append(off[b] - mn); dw.append(0); sub.append(0); widx.append(flat(a, b, 0))
+                        continue
                     for c in range(k):
                         dz.append(e[a]); dh.append(off[b] - mn); dw.append(off[c] - mn)
                         sub.append(par[b] * 2 + par[c] if in_stride == 2 else 0); widx.append(flat(a, b, c))
@@ -116,6 +123,7 @@ class UmmaPlan:
             self.in_off = mn
             self.out_stride = 1
         else:
+            self.merge = False
             per_dim = [[(kk, (c + pad - kk) // stride) for kk in range(k) if (c + pad - kk) % stride == 0]
                        for c in range(stride)]
             mn = min(o for lst in per_dim for _, o in lst)
@@ -216,7 +224,10 @@ class UmmaBackend:
         fl, by = 0.0, 0.0
         if self.prof.enabled:
             fl, by = conv_work(plan.simt, (B, Cin, Di, Hi, Wi), (B, plan.cout, Do, Ho, Wo), 2, residual is not None)
-        with self.prof.bracket(fam, fl, by):
+        detail = ""
+        if self.prof.enabled:
+            detail = f"{Cin}->{plan.cout} k{plan.k} s{plan.stride}{'T' if plan.tr else ''} @{Di}x{Hi}x{Wi}"
+        with self.prof.bracket(fam, fl, by, detail=detail):
             if plan.umma_ok:
                 nsteps, nh, nw = (Di, Hi, Wi) if plan.tr else (Do, Ho, Wo)
                 ws = self._workspace(out.numel(), x.device) if plan.nk > 1 else None
@@ -225,7 +236,7 @@ class UmmaBackend:
                           plan.c_dz, plan.c_dh, plan.c_dw, plan.c_sub, plan.c_widx, plan.nwtiles, plan.nclass,
                           plan.c_tb, plan.c_te, plan.c_od0, plan.c_oh0, plan.c_ow0, plan.in_stride, plan.out_stride,
                           nsteps, nh, nw, plan.in_off, plan.in_off, ACT[act], int(out_fp32),
-                          BO_MODE | (ES_VARIANT << 1), self.dchunk, _stream())
+                          BO_MODE | (ES_VARIANT << 1) | (4 if plan.merge else 0), self.dchunk, _stream())
             else:
                 sp = plan.simt
                 for sel, dd, dh, dw, T, in_s, out_s, (od0, oh0, ow0) in sp.classes:

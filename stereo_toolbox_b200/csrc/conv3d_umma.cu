@@ -56,7 +56,7 @@ struct UArgs {
     int nsteps, dchunk, nchunks, tiles_h, tiles_w;
     int in_h_off, in_w_off, cin_off;
     int act, out_fp32, f16;
-    int ROWB, layout, bo_mode;
+    int ROWB, layout, bo_mode, merge, ntaps_total;
     int nclass_h, nclass_w;          // class output extents per step in h/w (positions)
     uint32_t plane_bytes, chunk_bytes, wtile_bytes, w_bytes_total, tmem_cols;
     UClass cls[MAX_UCLASS];
@@ -95,6 +95,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     uint64_t* tmem_full = plane_empty + MAX_RING;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint32_t* tapA = tmem_holder + 2;            // [MAX_UTAPS] A byte offset of the tap inside a plane slot
+    uint32_t* tapB = tapA + MAX_UTAPS;           // [MAX_UTAPS] low word of the tap's B (weight tile) descriptor
+    uint32_t* tapZ = tapB + MAX_UTAPS;           // [MAX_UTAPS] plane index of the tap relative to dzmin
     uint8_t* sW = smem + 1024;
     uint8_t* sP = sW + ((a.w_bytes_total + 1023) & ~1023u);
 
@@ -147,40 +150,61 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
+        // The issuing lane must sustain one tcgen05.mma per 16..48 clocks, so everything that does not change
+        // per instruction is hoisted: per-tap A offsets / B descriptor words live in smem tables, the
+        // descriptor high word is constant, and the K-slice advance is a +2 on the encoded start address.
+        for (int tp = lane; tp < a.ntaps_total; tp += 32) {
+            tapA[tp] = (uint32_t)a.taps[tp].sub * a.chunk_bytes + (uint32_t)a.taps[tp].rowoff * a.ROWB;
+            tapB[tp] = (((smem_u32(sW) + (uint32_t)a.taps[tp].widx * a.wtile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+            tapZ[tp] = (uint32_t)(a.taps[tp].dz - a.dzmin);
+        }
+        __syncwarp();
         if (lane == 0) {
-            const uint32_t idesc = instr_desc_f16(128, a.Cn, a.f16 ? 0 : 1);
-            const uint32_t sbo = 8 * a.ROWB;
-            const uint32_t w0 = smem_u32(sW), p0 = smem_u32(sP);
+            const uint32_t idesc = instr_desc_f16(128, a.Cn * a.merge, a.f16 ? 0 : 1);
+            const uint64_t desc_hi = (uint64_t)((((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29)) << 32;
+            const uint32_t p0 = smem_u32(sP);
             const int ksteps = a.ROWB / 32;
+            const uint32_t mtile_bytes = 128u * a.ROWB;
+            const int nM = a.nM, R = a.R, sd = a.sd_in, nclass = a.nclass;
+            const uint32_t ncol = (uint32_t)(a.Cn * a.merge);
             mbar_wait(bar_w, 0);
             int waited = 0;                       // planes [0, waited) are known to be resident
             int round = 0;
             for (int s = s_lo; s < s_hi; ++s) {
-                const int need = (s * a.sd_in + a.dzmax) - p_first + 1;
+                const int need = (s * sd + a.dzmax) - p_first + 1;
                 while (waited < need) {
-                    mbar_wait(&plane_full[waited % a.R], (waited / a.R) & 1);
+                    mbar_wait(&plane_full[waited % R], (waited / R) & 1);
                     ++waited;
                 }
                 tc_fence_after();
-                for (int c = 0; c < a.nclass; ++c, ++round) {
+                uint32_t slot_lo[MAX_RING];       // encoded (addr>>4) of the slot holding plane (s*sd + dzmin + i)
+#pragma unroll
+                for (int i = 0; i < MAX_RING; ++i)
+                    slot_lo[i] = (p0 + (uint32_t)(((s * sd + a.dzmin + i) - p_first) % R) * a.plane_bytes) >> 4;
+                for (int c = 0; c < nclass; ++c, ++round) {
                     const int buf = round & 1;
                     mbar_wait(&tmem_empty[buf], ((round >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const UClass cl = a.cls[c];
-                    for (int m = 0; m < a.nM; ++m) {
-                        const uint32_t dcol = tmem_base + (uint32_t)((buf * a.nM + m) * a.Cn);
+                    const int t0 = a.cls[c].tap_begin, t1 = a.cls[c].tap_end;
+                    for (int m = 0; m < nM; ++m) {
+                        const uint32_t dcol = tmem_base + (uint32_t)(buf * nM + m) * ncol;
+                        const uint32_t moff = ((uint32_t)m * mtile_bytes) >> 4;
                         uint32_t acc = 0;
-                        for (int tp = cl.tap_begin; tp < cl.tap_end; ++tp) {
-                            const UTap tap = a.taps[tp];
-                            const int n = (s * a.sd_in + tap.dz) - p_first;
-                            const uint32_t abase = p0 + (uint32_t)(n % a.R) * a.plane_bytes + tap.sub * a.chunk_bytes +
-                                                   (uint32_t)(128 * m + tap.rowoff) * a.ROWB;
-                            const uint32_t bbase = w0 + (uint32_t)tap.widx * a.wtile_bytes;
+                        for (int tp = t0; tp < t1; ++tp) {
+                            uint32_t sl;
+                            switch (tapZ[tp]) {      // avoids dynamic indexing of a register array
+                                case 0: sl = slot_lo[0]; break;
+                                case 1: sl = slot_lo[1]; break;
+                                case 2: sl = slot_lo[2]; break;
+                                case 3: sl = slot_lo[3]; break;
+                                case 4: sl = slot_lo[4]; break;
+                                default: sl = slot_lo[5]; break;
+                            }
+                            const uint32_t alo = ((sl + moff + (tapA[tp] >> 4)) & 0x3FFFu) | (1u << 16);
+                            const uint32_t blo = tapB[tp];
+#pragma unroll 4
                             for (int ks = 0; ks < ksteps; ++ks) {
-                                const uint32_t aaddr = abase + ks * 32, baddr = bbase + ks * 32;
-                                const uint32_t abo = a.bo_mode ? ((aaddr >> 7) & 7) : 0;
-                                mma_f16_ss(dcol, smem_desc(aaddr, 16, sbo, a.layout, abo),
-                                           smem_desc(baddr, 16, sbo, a.layout, 0), idesc, acc);
+                                mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 2u * ks), desc_hi | (uint64_t)(blo + 2u * ks), idesc, acc);
                                 acc = 1;
                             }
                         }
@@ -188,9 +212,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     mma_commit(&tmem_full[buf]);
                 }
                 // planes below the next step's window are dead once this step's MMAs retire
-                const int dead_upto = (s + 1 < s_hi) ? ((s + 1) * a.sd_in + a.dzmin) - p_first : nplanes;
-                for (int n = (s == s_lo ? 0 : (s * a.sd_in + a.dzmin) - p_first); n < dead_upto; ++n)
-                    mma_commit(&plane_empty[n % a.R]);
+                const int dead_upto = (s + 1 < s_hi) ? ((s + 1) * sd + a.dzmin) - p_first : nplanes;
+                for (int n = (s == s_lo ? 0 : (s * sd + a.dzmin) - p_first); n < dead_upto; ++n)
+                    mma_commit(&plane_empty[n % R]);
             }
         }
     } else {
@@ -198,6 +222,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
         const size_t ostride_w = (size_t)a.Cout_total;
         const int f16 = a.f16;
+        float sh0[32];                              // folded-BN shift of the first 32 output channels, kept in registers
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + a.cout_off + i) : 0.f;
         for (int round = 0; round < nouts; ++round) {
             const int buf = round & 1;
             const int s = s_lo + round / a.nclass;
@@ -215,15 +242,26 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const size_t vox = (((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow;
                 for (int c0 = 0; c0 < a.Cn; c0 += 32) {
                     uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * a.nM + m) * a.Cn + c0);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) +
+                                           (uint32_t)((buf * a.nM + m) * a.Cn * a.merge + c0);
                     __syncwarp();                      // tcgen05.ld is .sync.aligned: whole warp, converged
                     tmem_ld_32x32(taddr, v);
                     tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    // kw-merged accumulators: column block k holds P_k[q] = sum over (kd,kh,ci) for filter column
+                    // kw = k evaluated WITHOUT the w shift; out[q] = P_0[q] + P_1[q+1] + P_2[q+2], and q+k is
+                    // lane+k of the same warp (one warp = one padded tile row).
+                    for (int k = 1; k < a.merge; ++k) {
+                        __syncwarp();
+                        tmem_ld_32x32(taddr + (uint32_t)(k * a.Cn), v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[i]), k);
+                    }
                     const int nch = min(32, a.Cn_valid - c0);
                     if (inb && nch > 0) {
-                        float f[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                         const size_t eoff = vox * ostride_w + a.cout_off + c0;
                         if (a.partial) {
                             const float* pp = a.partial + eoff;
@@ -239,7 +277,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                                     if (i < nch) f[i] += __ldg(pp + i);
                             }
                         }
-                        if (a.shift) {
+                        if (c0 == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) f[i] += sh0[i];
+                        } else if (a.shift) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
                                 if (i < nch) f[i] += __ldg(a.shift + a.cout_off + c0 + i);
@@ -338,6 +379,8 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     const CUtensorMapDataType cudt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     a.bo_mode = flags & 1;
     const int es_variant = (flags >> 1) & 1;
+    a.merge = (flags & 4) ? 3 : 1;            // kw-merged taps: N = 3*Cn, weight tiles (kd,kh,0..2) are contiguous
+    if (a.merge == 3 && (in_stride != 1 || out_stride != 1 || nclass != 1)) return STB_E_UNSUPPORTED;
     a.in_stride = in_stride;
     a.nsub = in_stride == 2 ? 4 : 1;
     a.sd_in = in_stride;
@@ -355,13 +398,14 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         a.taps[t].rowoff = (int16_t)(dh[t] * TWP + dw[t]);
         a.taps[t].widx = (uint16_t)widx[t];
     }
+    a.ntaps_total = ntaps;
     for (int c = 0; c < nclass; ++c) {
         a.cls[c].tap_begin = (uint16_t)tap_begin[c];
         a.cls[c].tap_end = (uint16_t)tap_end[c];
         a.cls[c].od0 = (int8_t)od0[c]; a.cls[c].oh0 = (int8_t)oh0[c]; a.cls[c].ow0 = (int8_t)ow0[c];
     }
     a.nclass = nclass;
-    a.TW = TWP - maxdw;
+    a.TW = TWP - (a.merge == 3 ? 2 : maxdw);
     a.dzmin = dzmin; a.dzmax = dzmax;
     const int window = dzmax - dzmin + 1;
     a.B = B; a.Do = Do; a.Ho = Ho; a.Wo = Wo;
@@ -373,7 +417,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     int Cn = Cpad > 256 ? 256 : Cpad, TH = 0, R = 0;
     auto fits = [&](int cn, int th, int r) {
         const int nM = th * TWP / 128;
-        if (2 * nM * cn + 32 > 512 || r > MAX_RING) return false;   // +32: the epilogue reads TMEM in 32-column blocks
+        if (2 * nM * cn * a.merge + 32 > 512 || cn * a.merge > 256 || r > MAX_RING) return false;   // +32: the epilogue reads TMEM in 32-column blocks
         const size_t wbytes = (((size_t)nwtiles * cn * a.ROWB) + 1023) & ~(size_t)1023;
         const size_t plane = (size_t)a.nsub * (th + maxdh) * TWP * a.ROWB;
         return 2048 + wbytes + (size_t)r * plane + 1024 <= SMEM_CAP;
@@ -403,7 +447,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.dchunk = dchunk;
     a.nchunks = stb_ceil_div(nsteps, dchunk);
     int tmem_cols = 32;
-    while (tmem_cols < 2 * a.nM * Cn + 32) tmem_cols <<= 1;
+    while (tmem_cols < 2 * a.nM * Cn * a.merge + 32) tmem_cols <<= 1;
     a.tmem_cols = (uint32_t)tmem_cols;
 
     CUtensorMap tm_x, tm_w;

@@ -53,6 +53,7 @@ class PSMNet(nn.Module):
         self.dres3 = hourglass(32)
         self.dres4 = hourglass(32)
         self.classif1, self.classif2, self.classif3 = _classif(), _classif(), _classif()
+        self.feature_tf32 = None
         self.set_precision(precision)
 
     def set_precision(self, precision: str):
@@ -81,10 +82,12 @@ class PSMNet(nn.Module):
             raise NotImplementedError(
                 "stereo_toolbox_b200: the training (autograd / batch-stat BatchNorm3d) path is not built yet; "
                 "call model.eval() -- see DESIGN.md 'out of scope this round'")
-        # 'fp32' promises <=1e-3 px vs the fp32 reference: keep cuDNN from silently using TF32 in the 2-D
-        # extractor (torch's default for convolutions).  'bf16' leaves torch's default alone.
+        # The 2-D extractor is outside the hot path and runs through torch/cuDNN, whose default lets convs use
+        # TF32 (that alone costs ~1e-2 px vs the fp32 reference).  feature_tf32=False forces exact fp32
+        # features; None = exact for precision 'fp32' (which promises <=1e-3 px), torch's default otherwise.
         prev = torch.backends.cudnn.allow_tf32
-        torch.backends.cudnn.allow_tf32 = prev and self.precision != "fp32"
+        want = self.feature_tf32 if self.feature_tf32 is not None else self.precision != "fp32"
+        torch.backends.cudnn.allow_tf32 = prev and want
         try:
             fl = self.feature_extraction(left)
             fr = self.feature_extraction(right)
