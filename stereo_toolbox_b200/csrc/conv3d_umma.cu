@@ -36,7 +36,7 @@ namespace {
 constexpr int TWP = 32;            // padded tile row pitch in voxels (one warp = one padded row in the epilogue)
 constexpr int MAX_UTAPS = 64;
 constexpr int MAX_UCLASS = 8;
-constexpr int MAX_RING = 6;
+constexpr int MAX_RING = 12;
 constexpr int UMMA_THREADS = 192;
 constexpr size_t SMEM_CAP = 227 * 1024;
 
@@ -177,9 +177,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     ++waited;
                 }
                 tc_fence_after();
-                uint32_t slot_lo[MAX_RING];       // encoded (addr>>4) of the slot holding plane (s*sd + dzmin + i)
+                uint32_t slot_lo[6];              // encoded (addr>>4) of the slot holding plane (s*sd + dzmin + i)
 #pragma unroll
-                for (int i = 0; i < MAX_RING; ++i)
+                for (int i = 0; i < 6; ++i)
                     slot_lo[i] = (p0 + (uint32_t)(((s * sd + a.dzmin + i) - p_first) % R) * a.plane_bytes) >> 4;
                 for (int c = 0; c < nclass; ++c, ++round) {
                     const int buf = round & 1;
@@ -415,18 +415,31 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     const int Cpad = (Cout_total + 15) / 16 * 16;     // weight tiles are padded to a multiple of 16 rows by the packer
     // ---- tiling: pick (Cn, TH, R) that fit shared memory; prefer tall tiles, then wide N
     int Cn = Cpad > 256 ? 256 : Cpad, TH = 0, R = 0;
-    auto fits = [&](int cn, int th, int r) {
+    // A single in-flight TMA box sustains only a few GB/s per SM (measured: 20-32 KB per ~7-13 us), so the plane
+    // ring must keep many planes in flight: choose the tile height whose ring holds the most prefetched bytes
+    // (capped at 128 KB), ties to the taller tile.
+    auto ring_for = [&](int cn, int th) {
         const int nM = th * TWP / 128;
-        if (2 * nM * cn * a.merge + 32 > 512 || cn * a.merge > 256 || r > MAX_RING) return false;   // +32: the epilogue reads TMEM in 32-column blocks
+        if (2 * nM * cn * a.merge + 32 > 512 || cn * a.merge > 256) return 0;   // +32: epilogue reads 32-col blocks
         const size_t wbytes = (((size_t)nwtiles * cn * a.ROWB) + 1023) & ~(size_t)1023;
         const size_t plane = (size_t)a.nsub * (th + maxdh) * TWP * a.ROWB;
-        return 2048 + wbytes + (size_t)r * plane + 1024 <= SMEM_CAP;
+        if (2048 + wbytes + 1024 >= SMEM_CAP) return 0;
+        int r = (int)((SMEM_CAP - 2048 - wbytes - 1024) / plane);
+        if (r > MAX_RING) r = MAX_RING;
+        return r >= window + 1 ? r : 0;
     };
-    for (bool found = false; !found;) {
-        for (int th = 16; th >= 4 && !found; th -= 4)
-            for (int r = window + a.sd_in; r >= window + 1 && !found; --r)
-                if (fits(Cn, th, r)) { TH = th; R = r; found = true; }
-        if (found) break;
+    if (window > 6) return STB_E_UNSUPPORTED;
+    for (;;) {
+        size_t best_score = 0;
+        for (int th = 16; th >= 4; th -= 4) {
+            const int r = ring_for(Cn, th);
+            if (!r) continue;
+            const size_t plane = (size_t)a.nsub * (th + maxdh) * TWP * a.ROWB;
+            size_t inflight = (size_t)(r - window) * plane;
+            if (inflight > 128 * 1024) inflight = 128 * 1024;
+            if (inflight > best_score) { best_score = inflight; TH = th; R = r; }
+        }
+        if (best_score) break;
         if (Cn <= 16) return STB_E_SMEM;
         Cn = (Cn / 2 + 15) / 16 * 16;
     }
@@ -439,10 +452,24 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.tiles_h = stb_ceil_div(nclass_h, a.TH);
     a.tiles_w = stb_ceil_div(nclass_w, a.TW);
     if (dchunk <= 0) {
-        // enough CTAs for >= ~6 waves of 148 SMs, but keep >= 8 steps per CTA to amortise the halo planes
-        long long cols = (long long)B * a.tiles_h * a.tiles_w;
-        dchunk = nsteps;
-        while (dchunk > 8 && cols * stb_ceil_div(nsteps, dchunk) < 148 * 6) dchunk = (dchunk + 1) / 2;
+        // Depth chunking: CTAs = columns x chunks, one CTA per SM at a time.  Pick the chunk count that best
+        // fills whole waves of SMs while keeping the redundant halo planes (window-1 per chunk) small.
+        static int num_sms = 0;
+        if (!num_sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+        }
+        const long long cols = (long long)B * a.tiles_h * a.tiles_w;
+        double best = -1.0;
+        for (int nch = 1; nch <= nsteps; ++nch) {
+            const int dch = stb_ceil_div(nsteps, nch);
+            if (dch < 4 && nch > 1) break;
+            const long long ctas = cols * stb_ceil_div(nsteps, dch);
+            const long long waves = (ctas + num_sms - 1) / num_sms;
+            const double eff = (double)ctas / (double)(waves * num_sms) * (double)dch / (double)(dch + window - 1);
+            if (eff > best + 1e-3) { best = eff; dchunk = dch; }
+        }
     }
     a.dchunk = dchunk;
     a.nchunks = stb_ceil_div(nsteps, dchunk);

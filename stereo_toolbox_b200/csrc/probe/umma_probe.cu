@@ -98,6 +98,34 @@ __global__ void halo_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat1
     for (int i = threadIdx.x; i < nelem; i += blockDim.x) dump[i] = reinterpret_cast<__nv_bfloat16*>(smem)[i];
 }
 
+// TMA box-load throughput: every CTA streams `nbox` boxes [rows x 32 voxels x C ch] of an NDHWC tensor through
+// a ring of `R` smem slots (re-issuing a slot as soon as its box has landed); no compute.
+__global__ void __launch_bounds__(64)
+tmabw_kernel(const __grid_constant__ CUtensorMap tm, int R, int nbox, uint32_t box_bytes, int D, int tiles_w, int tiles_h) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    __shared__ uint64_t full[16];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < R; ++i) mbar_init(&full[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = blockIdx.x;
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th = t % tiles_h; t /= tiles_h;
+        const int b = t;
+        for (int n = 0; n < nbox + R; ++n) {
+            const int slot = n % R;
+            if (n >= R) mbar_wait(&full[slot], ((n / R) - 1) & 1);      // box n-R has landed -> slot reusable
+            if (n < nbox) {
+                mbar_arrive_expect_tx(&full[slot], box_bytes);
+                tma_load_5d(smem + (size_t)slot * box_bytes, &tm, &full[slot], 0, tw * 30 - 1, th * 8 - 1, (n % D), b);
+            }
+        }
+    }
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 int main(int argc, char** argv) {
@@ -140,6 +168,40 @@ int main(int argc, char** argv) {
         }
         printf("halo 5D OOB zero-fill + SW64 layout: %s (%d mismatches)\n", bad ? "FAIL" : "PASS", bad);
         return bad ? 1 : 0;
+    }
+    if (argc >= 2 && !strcmp(argv[1], "tmabw")) {
+        // usage: tmabw <C:32|64> <rows> <R>
+        const int C = atoi(argv[2]), rows = atoi(argv[3]), R = atoi(argv[4]);
+        const int B = 8, D = 48, H = 96, W = 312;
+        size_t n = (size_t)B * D * H * W * C;
+        __nv_bfloat16* d;
+        CK(cudaMalloc(&d, n * 2));
+        CK(cudaMemset(d, 0, n * 2));
+        CUtensorMap tm;
+        uint64_t dims[5] = {(uint64_t)C, W, H, D, B};
+        uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)D * H * W * C * 2};
+        uint32_t box[5] = {(uint32_t)C, 32, (uint32_t)rows, 1, 1};
+        if (!umma_host::make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d, dims, str, box,
+                                  C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) { printf("tmap fail\n"); return 1; }
+        const uint32_t box_bytes = (uint32_t)C * 2 * 32 * rows;
+        const int tiles_w = 11, tiles_h = 12, nbox = 96;
+        size_t smem = (size_t)R * box_bytes + 2048;
+        CK(cudaFuncSetAttribute(tmabw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        const int grid = B * tiles_w * tiles_h;
+        tmabw_kernel<<<grid, 64, smem>>>(tm, R, nbox, box_bytes, D, tiles_w, tiles_h);
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        tmabw_kernel<<<grid, 64, smem>>>(tm, R, nbox, box_bytes, D, tiles_w, tiles_h);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double gb = (double)grid * nbox * box_bytes / 1e9;
+        printf("tmabw C=%d rows=%d (box %u B) ring=%d smem=%zu KB: %.3f ms, %.1f GB/s (%d CTAs x %d boxes)\n", C, rows, box_bytes, R,
+               smem / 1024, ms, gb / (ms * 1e-3), grid, nbox);
+        return 0;
     }
     if (argc >= 2 && !strcmp(argv[1], "halo2")) {
         // stride-2 deinterleave by TMA elementStrides: tensor [N=1][D=2][H=9][W=13][C=32], element strides

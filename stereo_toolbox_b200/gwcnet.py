@@ -96,8 +96,9 @@ class GwcNet(nn.Module):
         want = self.feature_tf32 if self.feature_tf32 is not None else self.precision != "fp32"
         torch.backends.cudnn.allow_tf32 = prev and want
         try:
-            fl = self.feature_extraction(left)
-            fr = self.feature_extraction(right)
+            with self._be.prof.bracket("torch_features2d", 0.0, 0.0):
+                fl = self.feature_extraction(left)
+                fr = self.feature_extraction(right)
         finally:
             torch.backends.cudnn.allow_tf32 = prev
         return self.aggregate(fl, fr, left.shape[2], left.shape[3])
