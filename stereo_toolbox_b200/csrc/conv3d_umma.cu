@@ -83,6 +83,10 @@ __device__ __forceinline__ void store16(uint16_t* p, float v, int f16) {
     else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16(v);
 }
 
+// ACT / F16 are compile-time so the epilogue stays a few hundred instructions: with a runtime activation switch
+// unrolled over 32 channels the kernel was 83 KB of SASS and the epilogue warps stalled on instruction fetch
+// (ncu: stall_no_inst on every epilogue line, profiles/ncu_umma_r01_*.txt).
+template <int ACT, bool F16>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ UArgs a) {
@@ -160,7 +164,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         }
         __syncwarp();
         if (lane == 0) {
-            const uint32_t idesc = instr_desc_f16(128, a.Cn * a.merge, a.f16 ? 0 : 1);
+            const uint32_t idesc = instr_desc_f16(128, a.Cn * a.merge, F16 ? 0 : 1);
             const uint64_t desc_hi = (uint64_t)((((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29)) << 32;
             const uint32_t p0 = smem_u32(sP);
             const int ksteps = a.ROWB / 32;
@@ -221,10 +225,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // ================================ epilogue warps ================================
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
         const size_t ostride_w = (size_t)a.Cout_total;
-        const int f16 = a.f16;
-        float sh0[32];                              // folded-BN shift of the first 32 output channels, kept in registers
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + a.cout_off + i) : 0.f;
+        constexpr int f16 = F16 ? 1 : 0;
+        const bool full32 = (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
+        const int merge = a.merge, Cn = a.Cn, nM = a.nM;
         for (int round = 0; round < nouts; ++round) {
             const int buf = round & 1;
             const int s = s_lo + round / a.nclass;
@@ -232,7 +235,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             mbar_wait(&tmem_full[buf], (round >> 1) & 1);
             tc_fence_after();
             const int od = s * a.out_stride + cl.od0;
-            for (int m = 0; m < a.nM; ++m) {
+            for (int m = 0; m < nM; ++m) {
                 const int q = 128 * m + q4 * 32 + lane;
                 const int jh_l = q / TWP, jw_l = q % TWP;
                 const int jh = jh0 + jh_l, jw = jw0 + jw_l;
@@ -240,10 +243,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const int oh = jh * a.out_stride + cl.oh0, ow = jw * a.out_stride + cl.ow0;
                 const bool inb = valid && oh < a.Ho && ow < a.Wo;
                 const size_t vox = (((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow;
-                for (int c0 = 0; c0 < a.Cn; c0 += 32) {
+                for (int c0 = 0; c0 < Cn; c0 += 32) {
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) +
-                                           (uint32_t)((buf * a.nM + m) * a.Cn * a.merge + c0);
+                                           (uint32_t)((buf * nM + m) * Cn * merge + c0);
                     __syncwarp();                      // tcgen05.ld is .sync.aligned: whole warp, converged
                     tmem_ld_32x32(taddr, v);
                     tmem_ld_wait();
@@ -253,87 +256,77 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     // kw-merged accumulators: column block k holds P_k[q] = sum over (kd,kh,ci) for filter column
                     // kw = k evaluated WITHOUT the w shift; out[q] = P_0[q] + P_1[q+1] + P_2[q+2], and q+k is
                     // lane+k of the same warp (one warp = one padded tile row).
-                    for (int k = 1; k < a.merge; ++k) {
+                    for (int k = 1; k < merge; ++k) {
                         __syncwarp();
-                        tmem_ld_32x32(taddr + (uint32_t)(k * a.Cn), v);
+                        tmem_ld_32x32(taddr + (uint32_t)(k * Cn), v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) f[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[i]), k);
                     }
-                    const int nch = min(32, a.Cn_valid - c0);
-                    if (inb && nch > 0) {
-                        const size_t eoff = vox * ostride_w + a.cout_off + c0;
+                    const size_t eoff = vox * ostride_w + a.cout_off + c0;
+                    if (inb && full32) {
+                        // ---------------- vector path: 32 complete channels
                         if (a.partial) {
-                            const float* pp = a.partial + eoff;
-                            if (nch == 32) {
+                            const float4* pp = reinterpret_cast<const float4*>(a.partial + eoff);
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 pv = __ldg(reinterpret_cast<const float4*>(pp) + i);
-                                    f[i * 4] += pv.x; f[i * 4 + 1] += pv.y; f[i * 4 + 2] += pv.z; f[i * 4 + 3] += pv.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (i < nch) f[i] += __ldg(pp + i);
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 pv = __ldg(pp + i);
+                                f[i * 4] += pv.x; f[i * 4 + 1] += pv.y; f[i * 4 + 2] += pv.z; f[i * 4 + 3] += pv.w;
                             }
                         }
-                        if (c0 == 0) {
+                        if (a.shift) {
+                            const float4* sp = reinterpret_cast<const float4*>(a.shift + a.cout_off + c0);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) f[i] += sh0[i];
-                        } else if (a.shift) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i < nch) f[i] += __ldg(a.shift + a.cout_off + c0 + i);
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 sv = __ldg(sp + i);
+                                f[i * 4] += sv.x; f[i * 4 + 1] += sv.y; f[i * 4 + 2] += sv.z; f[i * 4 + 3] += sv.w;
+                            }
                         }
                         if (a.residual) {
-                            const uint16_t* rp = reinterpret_cast<const uint16_t*>(a.residual) + eoff;
-                            if (nch == 32) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.residual) + eoff);
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp) + i);
-                                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+                            for (int i = 0; i < 4; ++i) {
+                                const uint4 rv = __ldg(rp + i);
+                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        const float2 h2 = unpack16(rw[j], f16);
-                                        f[i * 8 + j * 2] += h2.x;
-                                        f[i * 8 + j * 2 + 1] += h2.y;
-                                    }
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 h2 = unpack16(rw[j], f16);
+                                    f[i * 8 + j * 2] += h2.x;
+                                    f[i * 8 + j * 2 + 1] += h2.y;
                                 }
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (i < nch) f[i] += load16(rp + i, f16);
                             }
                         }
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], a.act);
+                        for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], ACT);
                         if (a.out_fp32) {
-                            float* op = reinterpret_cast<float*>(a.out) + eoff;
-                            if (nch == 32) {
+                            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + eoff);
 #pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    reinterpret_cast<float4*>(op)[i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (i < nch) op[i] = f[i];
-                            }
+                            for (int i = 0; i < 8; ++i) op[i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
                         } else {
-                            uint16_t* op = reinterpret_cast<uint16_t*>(a.out) + eoff;
-                            if (nch == 32) {
+                            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + eoff);
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    uint4 o;
-                                    o.x = pack16(f[i * 8 + 0], f[i * 8 + 1], f16);
-                                    o.y = pack16(f[i * 8 + 2], f[i * 8 + 3], f16);
-                                    o.z = pack16(f[i * 8 + 4], f[i * 8 + 5], f16);
-                                    o.w = pack16(f[i * 8 + 6], f[i * 8 + 7], f16);
-                                    reinterpret_cast<uint4*>(op)[i] = o;
-                                }
-                            } else {
+                            for (int i = 0; i < 4; ++i) {
+                                uint4 o;
+                                o.x = pack16(f[i * 8 + 0], f[i * 8 + 1], f16);
+                                o.y = pack16(f[i * 8 + 2], f[i * 8 + 3], f16);
+                                o.z = pack16(f[i * 8 + 4], f[i * 8 + 5], f16);
+                                o.w = pack16(f[i * 8 + 6], f[i * 8 + 7], f16);
+                                op[i] = o;
+                            }
+                        }
+                    } else if (inb) {
+                        // ---------------- ragged path (Cout not a multiple of 32: the 32->1 classifier, IGEV widths)
+                        const int nch = min(32, a.Cn_valid - c0);
 #pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (i < nch) store16(op + i, f[i], f16);
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < nch) {
+                                float x = f[i];
+                                if (a.partial) x += __ldg(a.partial + eoff + i);
+                                if (a.shift) x += __ldg(a.shift + a.cout_off + c0 + i);
+                                if (a.residual) x += load16(reinterpret_cast<const uint16_t*>(a.residual) + eoff + i, f16);
+                                x = stb_act(x, ACT);
+                                if (a.out_fp32) reinterpret_cast<float*>(a.out)[eoff + i] = x;
+                                else store16(reinterpret_cast<uint16_t*>(a.out) + eoff + i, x, f16);
                             }
                         }
                     }
@@ -347,6 +340,32 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+template <int ACT, bool F16>
+int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, const UArgs& a) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv3d_umma_kernel<ACT, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
+        attr_set = true;
+    }
+    conv3d_umma_kernel<ACT, F16><<<grid, UMMA_THREADS, smem, st>>>(tx, tw, a);
+    STB_CHECK_LAUNCH();
+    return STB_OK;
+}
+
+int launch_umma(int act, int f16, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx,
+                const CUtensorMap& tw, const UArgs& a) {
+#define STB_LAUNCH_ACT(A)                                                         \
+    case A: return f16 ? launch_one<A, true>(grid, smem, st, tx, tw, a) : launch_one<A, false>(grid, smem, st, tx, tw, a);
+    switch (act) {
+        STB_LAUNCH_ACT(STB_ACT_NONE)
+        STB_LAUNCH_ACT(STB_ACT_RELU)
+        STB_LAUNCH_ACT(STB_ACT_LEAKY)
+        STB_LAUNCH_ACT(STB_ACT_MISH)
+        default: return STB_E_BADARG;
+    }
+#undef STB_LAUNCH_ACT
 }
 
 }  // namespace
@@ -487,7 +506,6 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         uint32_t es[5] = {1, (uint32_t)in_stride, (uint32_t)in_stride, 1, 1};
         if (!umma_host::make_tmap(&tm_x, cudt, 5, const_cast<void*>(x), dims, str, box, cusw, es)) return STB_E_DRIVER;
     }
-    cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
     a.w_rows = Cpad;
     a.w_tile_stride = nk;
     a.nwtiles = nwtiles;
@@ -517,8 +535,8 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             if (!umma_host::make_tmap(&tm_w, cudt, 2, const_cast<void*>(wt), dims, str, box, cusw)) return STB_E_DRIVER;
             size_t smem = 2048 + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
             if (smem > SMEM_CAP) return STB_E_SMEM;
-            conv3d_umma_kernel<<<(unsigned)nblk, UMMA_THREADS, smem, (cudaStream_t)stream>>>(tm_x, tm_w, a);
-            STB_CHECK_LAUNCH();
+            const int rc = launch_umma(a.act, f16, (unsigned)nblk, smem, (cudaStream_t)stream, tm_x, tm_w, a);
+            if (rc != STB_OK) return rc;
         }
     }
     return STB_OK;

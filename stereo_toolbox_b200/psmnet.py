@@ -54,6 +54,7 @@ class PSMNet(nn.Module):
         self.dres4 = hourglass(32)
         self.classif1, self.classif2, self.classif3 = _classif(), _classif(), _classif()
         self.feature_tf32 = None
+        self.feature_mode = None
         self.set_precision(precision)
 
     def set_precision(self, precision: str):
@@ -77,21 +78,39 @@ class PSMNet(nn.Module):
         self._last_cost = cost3
         return be.head(cost3, self.maxdisp, height, width, align_corners=False).unsqueeze(1)
 
+    def _features(self, left, right):
+        """2-D extractor: outside the hot path, runs through torch/cuDNN.  feature_mode:
+          'fp32' exact fp32 convs (what the CPU reference computes; default for precision='fp32', which promises
+                 <=1e-3 px), 'tf32' torch's default for convs (what the reference itself does on a GPU),
+          'fp16' channels-last fp16 autocast (fastest).  None = 'fp32' for precision fp32, else 'tf32'.
+        feature_tf32 (legacy knob): False forces 'fp32'."""
+        mode = self.feature_mode
+        if self.feature_tf32 is False:
+            mode = "fp32"
+        if mode is None:
+            mode = "fp32" if self.precision == "fp32" else "tf32"
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = prev and mode != "fp32"
+        try:
+            with self._be.prof.bracket("torch_features2d", 0.0, 0.0):
+                if mode == "fp16":
+                    with torch.autocast("cuda", dtype=torch.float16):
+                        fl = self.feature_extraction(left.contiguous(memory_format=torch.channels_last))
+                        fr = self.feature_extraction(right.contiguous(memory_format=torch.channels_last))
+                    cvt = lambda t: t.float().contiguous()
+                    fl = {k: cvt(v) for k, v in fl.items()} if isinstance(fl, dict) else cvt(fl)
+                    fr = {k: cvt(v) for k, v in fr.items()} if isinstance(fr, dict) else cvt(fr)
+                else:
+                    fl = self.feature_extraction(left)
+                    fr = self.feature_extraction(right)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        return fl, fr
+
     def forward(self, left, right):
         if self.training:
             raise NotImplementedError(
                 "stereo_toolbox_b200: the training (autograd / batch-stat BatchNorm3d) path is not built yet; "
                 "call model.eval() -- see DESIGN.md 'out of scope this round'")
-        # The 2-D extractor is outside the hot path and runs through torch/cuDNN, whose default lets convs use
-        # TF32 (that alone costs ~1e-2 px vs the fp32 reference).  feature_tf32=False forces exact fp32
-        # features; None = exact for precision 'fp32' (which promises <=1e-3 px), torch's default otherwise.
-        prev = torch.backends.cudnn.allow_tf32
-        want = self.feature_tf32 if self.feature_tf32 is not None else self.precision != "fp32"
-        torch.backends.cudnn.allow_tf32 = prev and want
-        try:
-            with self._be.prof.bracket("torch_features2d", 0.0, 0.0):
-                fl = self.feature_extraction(left)
-                fr = self.feature_extraction(right)
-        finally:
-            torch.backends.cudnn.allow_tf32 = prev
+        fl, fr = self._features(left, right)
         return self.aggregate(fl, fr, left.shape[2], left.shape[3])
