@@ -92,7 +92,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                    const __grid_constant__ UArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-    // [0,1024): barriers + tmem holder ; then weights ; then plane ring
+    // [0,2048): barriers + tmem holder + issue tables ; then weights ; then plane ring
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem);
     uint64_t* plane_full = bar_w + 1;
     uint64_t* plane_empty = plane_full + MAX_RING;
@@ -102,7 +102,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     uint32_t* tapA = tmem_holder + 2;            // [MAX_UTAPS] A byte offset of the tap inside a plane slot
     uint32_t* tapB = tapA + MAX_UTAPS;           // [MAX_UTAPS] low word of the tap's B (weight tile) descriptor
     uint32_t* tapZ = tapB + MAX_UTAPS;           // [MAX_UTAPS] plane index of the tap relative to dzmin
-    uint8_t* sW = smem + 1024;
+    uint32_t* slotTab = tapZ + MAX_UTAPS;        // [MAX_RING] encoded (addr >> 4) of every ring slot
+    uint8_t* sW = smem + 2048;
     uint8_t* sP = sW + ((a.w_bytes_total + 1023) & ~1023u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,7 +135,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        if (elect_one()) {
             prefetch_tmap(&tm_x);
             prefetch_tmap(&tm_w);
             mbar_arrive_expect_tx(bar_w, a.w_bytes_total);
@@ -154,26 +155,28 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        // The issuing lane must sustain one tcgen05.mma per 16..48 clocks, so everything that does not change
-        // per instruction is hoisted: per-tap A offsets / B descriptor words live in smem tables, the
-        // descriptor high word is constant, and the K-slice advance is a +2 on the encoded start address.
+        // One lane must sustain a tcgen05.mma every few tens of clocks with nobody to hide its latencies, so the
+        // loop carries no division, no descriptor construction and no constant-bank traffic: per tap one 64-bit
+        // A-offset/B-descriptor pair comes from a smem table, the ring slot base from a second table, and the
+        // K-slice advance is a +2 on the encoded start address.
         for (int tp = lane; tp < a.ntaps_total; tp += 32) {
-            tapA[tp] = (uint32_t)a.taps[tp].sub * a.chunk_bytes + (uint32_t)a.taps[tp].rowoff * a.ROWB;
+            tapA[tp] = ((uint32_t)a.taps[tp].sub * a.chunk_bytes + (uint32_t)a.taps[tp].rowoff * a.ROWB) >> 4;
             tapB[tp] = (((smem_u32(sW) + (uint32_t)a.taps[tp].widx * a.wtile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
             tapZ[tp] = (uint32_t)(a.taps[tp].dz - a.dzmin);
         }
+        for (int i = lane; i < a.R; i += 32) slotTab[i] = (smem_u32(sP) + (uint32_t)i * a.plane_bytes) >> 4;
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = instr_desc_f16(128, a.Cn * a.merge, F16 ? 0 : 1);
             const uint64_t desc_hi = (uint64_t)((((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29)) << 32;
-            const uint32_t p0 = smem_u32(sP);
             const int ksteps = a.ROWB / 32;
-            const uint32_t mtile_bytes = 128u * a.ROWB;
+            const uint32_t mtile16 = (128u * a.ROWB) >> 4;
             const int nM = a.nM, R = a.R, sd = a.sd_in, nclass = a.nclass;
             const uint32_t ncol = (uint32_t)(a.Cn * a.merge);
             mbar_wait(bar_w, 0);
             int waited = 0;                       // planes [0, waited) are known to be resident
             int round = 0;
+            int base_slot = 0;                    // ring slot of plane (s*sd + dzmin); advanced by sd per step
             for (int s = s_lo; s < s_hi; ++s) {
                 const int need = (s * sd + a.dzmax) - p_first + 1;
                 while (waited < need) {
@@ -181,10 +184,6 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     ++waited;
                 }
                 tc_fence_after();
-                uint32_t slot_lo[6];              // encoded (addr>>4) of the slot holding plane (s*sd + dzmin + i)
-#pragma unroll
-                for (int i = 0; i < 6; ++i)
-                    slot_lo[i] = (p0 + (uint32_t)(((s * sd + a.dzmin + i) - p_first) % R) * a.plane_bytes) >> 4;
                 for (int c = 0; c < nclass; ++c, ++round) {
                     const int buf = round & 1;
                     mbar_wait(&tmem_empty[buf], ((round >> 1) & 1) ^ 1);
@@ -192,25 +191,20 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     const int t0 = a.cls[c].tap_begin, t1 = a.cls[c].tap_end;
                     for (int m = 0; m < nM; ++m) {
                         const uint32_t dcol = tmem_base + (uint32_t)(buf * nM + m) * ncol;
-                        const uint32_t moff = ((uint32_t)m * mtile_bytes) >> 4;
+                        const uint32_t moff = (uint32_t)m * mtile16;
                         uint32_t acc = 0;
                         for (int tp = t0; tp < t1; ++tp) {
-                            uint32_t sl;
-                            switch (tapZ[tp]) {      // avoids dynamic indexing of a register array
-                                case 0: sl = slot_lo[0]; break;
-                                case 1: sl = slot_lo[1]; break;
-                                case 2: sl = slot_lo[2]; break;
-                                case 3: sl = slot_lo[3]; break;
-                                case 4: sl = slot_lo[4]; break;
-                                default: sl = slot_lo[5]; break;
-                            }
-                            const uint32_t alo = ((sl + moff + (tapA[tp] >> 4)) & 0x3FFFu) | (1u << 16);
+                            int sl = base_slot + (int)tapZ[tp];
+                            sl -= (sl >= R) ? R : 0;
+                            const uint32_t alo = ((slotTab[sl] + moff + tapA[tp]) & 0x3FFFu) | (1u << 16);
                             const uint32_t blo = tapB[tp];
-#pragma unroll 4
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 2u * ks), desc_hi | (uint64_t)(blo + 2u * ks), idesc, acc);
-                                acc = 1;
+                            mma_f16_ss(dcol, desc_hi | (uint64_t)alo, desc_hi | (uint64_t)blo, idesc, acc);
+                            mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 2u), desc_hi | (uint64_t)(blo + 2u), idesc, 1u);
+                            if (ksteps == 4) {
+                                mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 4u), desc_hi | (uint64_t)(blo + 4u), idesc, 1u);
+                                mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 6u), desc_hi | (uint64_t)(blo + 6u), idesc, 1u);
                             }
+                            acc = 1;
                         }
                     }
                     mma_commit(&tmem_full[buf]);
@@ -219,6 +213,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const int dead_upto = (s + 1 < s_hi) ? ((s + 1) * sd + a.dzmin) - p_first : nplanes;
                 for (int n = (s == s_lo ? 0 : (s * sd + a.dzmin) - p_first); n < dead_upto; ++n)
                     mma_commit(&plane_empty[n % R]);
+                base_slot += sd;
+                base_slot -= (base_slot >= R) ? R : 0;
             }
         }
     } else {
@@ -442,8 +438,8 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         if (2 * nM * cn * a.merge + 32 > 512 || cn * a.merge > 256) return 0;   // +32: epilogue reads 32-col blocks
         const size_t wbytes = (((size_t)nwtiles * cn * a.ROWB) + 1023) & ~(size_t)1023;
         const size_t plane = (size_t)a.nsub * (th + maxdh) * TWP * a.ROWB;
-        if (2048 + wbytes + 1024 >= SMEM_CAP) return 0;
-        int r = (int)((SMEM_CAP - 2048 - wbytes - 1024) / plane);
+        if (3072 + wbytes + 1024 >= SMEM_CAP) return 0;
+        int r = (int)((SMEM_CAP - 3072 - wbytes - 1024) / plane);
         if (r > MAX_RING) r = MAX_RING;
         return r >= window + 1 ? r : 0;
     };
@@ -533,7 +529,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             uint64_t str[1] = {(uint64_t)KC * 2};
             uint32_t box[2] = {(uint32_t)KC, (uint32_t)cn};
             if (!umma_host::make_tmap(&tm_w, cudt, 2, const_cast<void*>(wt), dims, str, box, cusw)) return STB_E_DRIVER;
-            size_t smem = 2048 + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
+            size_t smem = 3072 + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
             if (smem > SMEM_CAP) return STB_E_SMEM;
             const int rc = launch_umma(a.act, f16, (unsigned)nblk, smem, (cudaStream_t)stream, tm_x, tm_w, a);
             if (rc != STB_OK) return rc;

@@ -72,6 +72,19 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// One lane of a converged warp: the compiler treats an elect.sync predicate as single-thread, so uniform-
+// datapath instructions (UTCHMMA, UTMALDG) issue without the ELECT/BRA.U.ANY serialisation loop that a plain
+// `if (lane == 0)` produces.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* holder_smem, uint32_t ncols) {   // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder_smem)),

@@ -27,6 +27,9 @@ constexpr int VT = 256;      // threads
 constexpr int VW = 32;       // w positions per CTA
 
 // grid (tiles_w, H, B). dynamic smem: NR*(VW+1) + NR*(VW+D) floats, NR = max(8, 8*cpg) staged rows
+// CPG > 0: channels per correlation group known at compile time -> the left features of a chunk live in
+// registers and every (d, w) costs one shared-memory load per MAC instead of two.
+template <int CPG>
 __global__ void __launch_bounds__(VT)
 volume_cl_kernel(const float* __restrict__ gl, const float* __restrict__ gr, const float* __restrict__ cl,
                  const float* __restrict__ cr, uint16_t* __restrict__ vol, int Cg, int G, int Cc, int H, int W,
@@ -77,6 +80,29 @@ volume_cl_kernel(const float* __restrict__ gl, const float* __restrict__ gr, con
         }
         __syncthreads();
         if (w >= W) continue;
+        if (CPG > 0 && gwc_chunk) {
+            float lreg[8 * (CPG > 0 ? CPG : 1)];
+#pragma unroll
+            for (int r = 0; r < 8 * CPG; ++r) lreg[r] = Ls[r * LP + lw];
+            const float inv = 1.f / (float)CPG;
+            for (int d = dgrp; d < D; d += VT / 32) {
+                const float* rrow = Rs + lw + (D - 1) - d;
+                float o[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < CPG; ++c) acc = fmaf(lreg[g * CPG + c], rrow[(g * CPG + c) * RP], acc);
+                    o[g] = acc * inv;
+                }
+                uint4 pk;
+                pk.x = pk16(o[0], o[1], f16); pk.y = pk16(o[2], o[3], f16);
+                pk.z = pk16(o[4], o[5], f16); pk.w = pk16(o[6], o[7], f16);
+                uint16_t* dst = vol + ((((size_t)b * D + d) * H + h) * W + w) * Ct_pad + oc0;
+                *reinterpret_cast<uint4*>(dst) = pk;
+            }
+            continue;
+        }
         for (int d = dgrp; d < D; d += VT / 32) {
             float o[8];
             if (gwc_chunk) {
@@ -164,11 +190,19 @@ extern "C" int stb_volume_cl16(const float* gwc_l, const float* gwc_r, const flo
     if (H > 65535 || B > 65535) return STB_E_BADARG;
     size_t smem = (size_t)(NR * (VW + 1) + NR * (VW + D)) * sizeof(float);
     if (smem > 200 * 1024) return STB_E_SMEM;
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(volume_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(stb_ceil_div(W, VW), H, B);
-    volume_cl_kernel<<<grid, VT, smem, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r, (uint16_t*)vol, Cg, G, Cc, H, W, D,
-                                                            Ct, Ct_pad, mask_left, NR, f16);
+    const int cpg = G > 0 ? Cg / G : 0;
+#define STB_VOL_LAUNCH(K)                                                                                          \
+    do {                                                                                                           \
+        if (smem > 48 * 1024)                                                                                      \
+            cudaFuncSetAttribute(volume_cl_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        volume_cl_kernel<K><<<grid, VT, smem, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r, (uint16_t*)vol, Cg, G, \
+                                                                   Cc, H, W, D, Ct, Ct_pad, mask_left, NR, f16);   \
+    } while (0)
+    if (cpg == 8) STB_VOL_LAUNCH(8);
+    else if (cpg == 4) STB_VOL_LAUNCH(4);
+    else STB_VOL_LAUNCH(0);
+#undef STB_VOL_LAUNCH
     STB_CHECK_LAUNCH();
     return STB_OK;
 }
