@@ -199,7 +199,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                             const uint32_t alo = ((slotTab[sl] + moff + tapA[tp]) & 0x3FFFu) | (1u << 16);
                             const uint32_t blo = tapB[tp];
                             mma_f16_ss(dcol, desc_hi | (uint64_t)alo, desc_hi | (uint64_t)blo, idesc, acc);
-                            mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 2u), desc_hi | (uint64_t)(blo + 2u), idesc, 1u);
+                            if (ksteps >= 2)
+                                mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 2u), desc_hi | (uint64_t)(blo + 2u), idesc, 1u);
                             if (ksteps == 4) {
                                 mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 4u), desc_hi | (uint64_t)(blo + 4u), idesc, 1u);
                                 mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 6u), desc_hi | (uint64_t)(blo + 6u), idesc, 1u);

@@ -199,9 +199,10 @@ extern "C" int stb_volume_cl16(const float* gwc_l, const float* gwc_r, const flo
         volume_cl_kernel<K><<<grid, VT, smem, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r, (uint16_t*)vol, Cg, G, \
                                                                    Cc, H, W, D, Ct, Ct_pad, mask_left, NR, f16);   \
     } while (0)
-    if (cpg == 8) STB_VOL_LAUNCH(8);
-    else if (cpg == 4) STB_VOL_LAUNCH(4);
-    else STB_VOL_LAUNCH(0);
+    // (register-blocked CPG variants measured SLOWER on B200 -- 2.43 vs 1.86 ms at B=8 K-shape: occupancy drops
+    //  to 2 CTAs/SM and the kernel is bound by staging latency + 16-byte strided stores, not by LDS)
+    (void)cpg;
+    STB_VOL_LAUNCH(0);
 #undef STB_VOL_LAUNCH
     STB_CHECK_LAUNCH();
     return STB_OK;
