@@ -37,7 +37,7 @@ constexpr int TWP = 32;            // padded tile row pitch in voxels (one warp 
 constexpr int MAX_UTAPS = 64;
 constexpr int MAX_UCLASS = 8;
 constexpr int MAX_RING = 12;
-constexpr int UMMA_THREADS = 192;
+constexpr int UMMA_THREADS = 352;      // warp 0 TMA, warps 1-2 MMA issuers, warps 3-10 epilogue (two groups of 4)
 constexpr size_t SMEM_CAP = 227 * 1024;
 
 struct UTap { int8_t dz; uint8_t sub; int16_t rowoff; uint16_t widx; uint16_t pad1; };
@@ -123,11 +123,20 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
-        for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        const int nlanes = a.nM >= 2 ? 2 : 1;    // active MMA issuers = active epilogue groups (M-tiles m = i, i+2, ...)
+        for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], nlanes); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], nlanes); mbar_init(&tmem_empty[i], 4 * nlanes); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_holder, a.tmem_cols);
+    // issue tables (see the MMA issuer): per tap the A offset inside a ring slot, the B descriptor low word and the
+    // plane index relative to dzmin; per ring slot its encoded base address
+    for (int tp = threadIdx.x; tp < a.ntaps_total; tp += UMMA_THREADS) {
+        tapA[tp] = ((uint32_t)a.taps[tp].sub * a.chunk_bytes + (uint32_t)a.taps[tp].rowoff * a.ROWB) >> 4;
+        tapB[tp] = (((smem_u32(sW) + (uint32_t)a.taps[tp].widx * a.wtile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+        tapZ[tp] = (uint32_t)(a.taps[tp].dz - a.dzmin);
+    }
+    for (int i = threadIdx.x; i < a.R; i += UMMA_THREADS) slotTab[i] = (smem_u32(sP) + (uint32_t)i * a.plane_bytes) >> 4;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -153,19 +162,15 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                                 iw0 + (sb & 1), ih0 + (sb >> 1), p_first + n, b);
             }
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
+    } else if (warp <= 2) {
+        // ================================ MMA issuers (2) ================================
         // One lane must sustain a tcgen05.mma every few tens of clocks with nobody to hide its latencies, so the
-        // loop carries no division, no descriptor construction and no constant-bank traffic: per tap one 64-bit
-        // A-offset/B-descriptor pair comes from a smem table, the ring slot base from a second table, and the
-        // K-slice advance is a +2 on the encoded start address.
-        for (int tp = lane; tp < a.ntaps_total; tp += 32) {
-            tapA[tp] = ((uint32_t)a.taps[tp].sub * a.chunk_bytes + (uint32_t)a.taps[tp].rowoff * a.ROWB) >> 4;
-            tapB[tp] = (((smem_u32(sW) + (uint32_t)a.taps[tp].widx * a.wtile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
-            tapZ[tp] = (uint32_t)(a.taps[tp].dz - a.dzmin);
-        }
-        for (int i = lane; i < a.R; i += 32) slotTab[i] = (smem_u32(sP) + (uint32_t)i * a.plane_bytes) >> 4;
-        __syncwarp();
+        // loop carries no division, no descriptor construction and no constant-bank traffic (smem tables above),
+        // and the M-tiles of a round are split between two issuing warps (m = issuer, issuer+2, ...).
+        const int issuer = warp - 1;
+        if (issuer >= (a.nM >= 2 ? 2 : 1)) {
+            // idle issuer (single M-tile rounds)
+        } else
         if (elect_one()) {
             const uint32_t idesc = instr_desc_f16(128, a.Cn * a.merge, F16 ? 0 : 1);
             const uint64_t desc_hi = (uint64_t)((((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29)) << 32;
@@ -189,7 +194,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     mbar_wait(&tmem_empty[buf], ((round >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const int t0 = a.cls[c].tap_begin, t1 = a.cls[c].tap_end;
-                    for (int m = 0; m < nM; ++m) {
+                    for (int m = issuer; m < nM; m += 2) {
                         const uint32_t dcol = tmem_base + (uint32_t)(buf * nM + m) * ncol;
                         const uint32_t moff = (uint32_t)m * mtile16;
                         uint32_t acc = 0;
@@ -221,18 +226,20 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     } else {
         // ================================ epilogue warps ================================
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
+        const int egroup = (warp - 3) >> 2;         // epilogue group 0/1 drains M-tiles m = egroup, egroup+2, ...
+        const int my_rounds = egroup < (a.nM >= 2 ? 2 : 1) ? nouts : 0;   // idle group when rounds have one M-tile
         const size_t ostride_w = (size_t)a.Cout_total;
         constexpr int f16 = F16 ? 1 : 0;
         const bool full32 = (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
         const int merge = a.merge, Cn = a.Cn, nM = a.nM;
-        for (int round = 0; round < nouts; ++round) {
+        for (int round = 0; round < my_rounds; ++round) {
             const int buf = round & 1;
             const int s = s_lo + round / a.nclass;
             const UClass cl = a.cls[round % a.nclass];
             mbar_wait(&tmem_full[buf], (round >> 1) & 1);
             tc_fence_after();
             const int od = s * a.out_stride + cl.od0;
-            for (int m = 0; m < nM; ++m) {
+            for (int m = egroup; m < nM; m += 2) {
                 const int q = 128 * m + q4 * 32 + lane;
                 const int jh_l = q / TWP, jw_l = q % TWP;
                 const int jh = jh0 + jh_l, jw = jw0 + jw_l;
