@@ -126,6 +126,45 @@ tmabw_kernel(const __grid_constant__ CUtensorMap tm, int R, int nbox, uint32_t b
     }
 }
 
+// Raw tcgen05.mma issue/execute rate: `nissue` warps each issue `iters` x `per_iter` MMAs (M=128, N, K=16) on
+// garbage smem operands (no TMA, no epilogue), operands K-major with the given swizzle / row shift.
+__global__ void __launch_bounds__(128)
+mmarate_kernel(int N, uint32_t layout, int rowb, int shift, int iters, int per_iter, int nissue, long long* cycles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t holder;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = holder;
+    long long t0 = 0, t1 = 0;
+    if (warp < nissue && elect_one()) {
+        const uint32_t idesc = instr_desc_f16(128, N, 1);
+        const uint64_t hi = (uint64_t)((((8u * rowb) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29)) << 32;
+        const uint32_t a0 = ((smem_u32(smem) + warp * 32768 + shift * rowb) >> 4 & 0x3FFFu) | (1u << 16);
+        const uint32_t b0 = ((smem_u32(smem) + 65536 + warp * 32768) >> 4 & 0x3FFFu) | (1u << 16);
+        const uint32_t d = tmem + warp * 256;
+        t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            for (int j = 0; j < per_iter; ++j) {
+                const uint32_t off = (uint32_t)((j & 15) * (rowb * 8 / 16));   // walk over row groups like taps do
+                mma_f16_ss(d, hi | (uint64_t)(a0 + off), hi | (uint64_t)(b0 + (j & 1) * 2), idesc, 1u);
+            }
+        }
+        mma_commit(&bar[warp]);
+        mbar_wait(&bar[warp], 0);
+        t1 = clock64();
+        if (blockIdx.x == 0) cycles[warp] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 int main(int argc, char** argv) {
@@ -168,6 +207,27 @@ int main(int argc, char** argv) {
         }
         printf("halo 5D OOB zero-fill + SW64 layout: %s (%d mismatches)\n", bad ? "FAIL" : "PASS", bad);
         return bad ? 1 : 0;
+    }
+    if (argc >= 2 && !strcmp(argv[1], "mmarate")) {
+        // usage: mmarate <N> <rowb:64|128> <shift_rows> <nissue:1|2>
+        const int N = atoi(argv[2]), rowb = atoi(argv[3]), shift = atoi(argv[4]), nissue = atoi(argv[5]);
+        const uint32_t layout = rowb == 128 ? SW_128B : SW_64B;
+        long long* dc;
+        CK(cudaMalloc(&dc, 16));
+        CK(cudaMemset(dc, 0, 16));
+        const int iters = 200, per_iter = 36;
+        size_t smem = 140 * 1024;
+        CK(cudaFuncSetAttribute(mmarate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mmarate_kernel<<<148, 128, smem>>>(N, layout, rowb, shift, iters, per_iter, nissue, dc);
+        CK(cudaDeviceSynchronize());
+        mmarate_kernel<<<148, 128, smem>>>(N, layout, rowb, shift, iters, per_iter, nissue, dc);
+        CK(cudaDeviceSynchronize());
+        long long hc[2];
+        CK(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
+        const double per = (double)hc[0] / (iters * per_iter);
+        printf("mmarate N=%d rowb=%d shift=%d issuers=%d : %.1f clk per MMA per issuer (%.1f clk per MMA overall), ideal math %.1f\n",
+               N, rowb, shift, nissue, per, per / nissue, 128.0 * N / 256.0);
+        return 0;
     }
     if (argc >= 2 && !strcmp(argv[1], "tmabw")) {
         // usage: tmabw <C:32|64> <rows> <R>
