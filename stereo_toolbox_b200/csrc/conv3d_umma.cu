@@ -231,6 +231,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const size_t ostride_w = (size_t)a.Cout_total;
         constexpr int f16 = F16 ? 1 : 0;
         const bool full32 = (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
+        float sh0[32];                              // folded-BN shift of the first 32 channels stays in registers
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + a.cout_off + i) : 0.f;
         const int merge = a.merge, Cn = a.Cn, nM = a.nM;
         for (int round = 0; round < my_rounds; ++round) {
             const int buf = round & 1;
@@ -278,7 +281,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                                 f[i * 4] += pv.x; f[i * 4 + 1] += pv.y; f[i * 4 + 2] += pv.z; f[i * 4 + 3] += pv.w;
                             }
                         }
-                        if (a.shift) {
+                        if (c0 == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) f[i] += sh0[i];
+                        } else if (a.shift) {
                             const float4* sp = reinterpret_cast<const float4*>(a.shift + a.cout_off + c0);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
@@ -440,7 +446,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     int Cn = Cpad > 256 ? 256 : Cpad, TH = 0, R = 0;
     // A single in-flight TMA box sustains only a few GB/s per SM (measured: 20-32 KB per ~7-13 us), so the plane
     // ring must keep many planes in flight: choose the tile height whose ring holds the most prefetched bytes
-    // (capped at 128 KB), ties to the taller tile.
+    // (capped at 64 KB), ties to the taller tile.
     auto ring_for = [&](int cn, int th) {
         const int nM = th * TWP / 128;
         if (2 * nM * cn * a.merge + 32 > 512 || cn * a.merge > 256) return 0;   // +32: epilogue reads 32-col blocks
@@ -459,7 +465,8 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             if (!r) continue;
             const size_t plane = (size_t)a.nsub * (th + maxdh) * TWP * a.ROWB;
             size_t inflight = (size_t)(r - window) * plane;
-            if (inflight > 128 * 1024) inflight = 128 * 1024;
+            if (inflight > 64 * 1024) inflight = 64 * 1024;   // enough to cover TMA latency; beyond that prefer tall tiles
+                                                              // (>= 2 M-tiles per round keep both issuers / epilogue groups busy)
             if (inflight > best_score) { best_score = inflight; TH = th; R = r; }
         }
         if (best_score) break;
