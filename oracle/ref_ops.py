@@ -253,3 +253,15 @@ def geo_lookup(geos, corrs, disp: torch.Tensor, coords_x: torch.Tensor, radius: 
         outs.append(sample_1d_zero(corr, xc))
     out = torch.cat(outs, dim=-1)
     return out.permute(0, 3, 1, 2).contiguous().float()
+
+
+class CorrBlock1D:
+    """CPU stand-in with the interface of RAFTStereo/corr.py:110-156, built from the restatements above; tests swap
+    it into the drop-in RAFTStereo to obtain an oracle for the whole iterative model."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        self.num_levels, self.radius = num_levels, radius
+        self.pyramid = corr_pyramid(corr1d(fmap1, fmap2, True), num_levels)
+
+    def __call__(self, coords):
+        return corr_lookup(self.pyramid, coords[:, 0], self.radius, self.num_levels)

@@ -1,0 +1,301 @@
+"""RAFT-Stereo drop-in (reference: models/RAFTStereo/raft_stereo.py:26-188, extractor.py, update.py).
+
+Same constructor (``RAFTStereo(args=None, imagenet_norm=False)``, ``args`` a Namespace merged via ``vars()``),
+same ``forward(image1, image2, iters=None, flow_init=None, test_mode=False)`` and state-dict names.  The hot
+path of the iterative model -- all-pairs 1-D correlation, its 1x2 average pyramid and the 4-level x 9-tap
+lookup executed every GRU iteration (``CorrBlock1D``, RAFTStereo/corr.py:110-156) -- runs in libstb200.so;
+encoders, ConvGRUs and convex upsampling stay in torch ("next").
+"""
+from __future__ import annotations
+
+import argparse
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .functional import CorrBlock1D
+
+
+def _norm(kind: str, ch: int):
+    if kind == "batch":
+        return nn.BatchNorm2d(ch)
+    if kind == "instance":
+        return nn.InstanceNorm2d(ch)
+    if kind == "group":
+        return nn.GroupNorm(ch // 8, ch)
+    return nn.Sequential()
+
+
+class ResidualBlock(nn.Module):
+    """extractor.py:5-58: two 3x3 convs with norm + ReLU, 1x1-conv shortcut when the shape changes."""
+
+    def __init__(self, in_planes, planes, norm_fn="group", stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_planes, planes, 3, stride, 1)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1)
+        self.relu = nn.ReLU(inplace=True)
+        self.norm1, self.norm2 = _norm(norm_fn, planes), _norm(norm_fn, planes)
+        self.downsample = None
+        if stride != 1 or in_planes != planes:
+            self.norm3 = _norm(norm_fn, planes)
+            self.downsample = nn.Sequential(nn.Conv2d(in_planes, planes, 1, stride), self.norm3)
+
+    def forward(self, x):
+        y = self.relu(self.norm1(self.conv1(x)))
+        y = self.relu(self.norm2(self.conv2(y)))
+        return self.relu((x if self.downsample is None else self.downsample(x)) + y)
+
+
+class _Trunk(nn.Module):
+    """conv1 (7x7) + layer1..3 shared by BasicEncoder and MultiBasicEncoder (extractor.py:122-160, 198-230)."""
+
+    def __init__(self, norm_fn, downsample):
+        super().__init__()
+        self.norm_fn = norm_fn
+        self.norm1 = nn.GroupNorm(8, 64) if norm_fn == "group" else _norm(norm_fn, 64)
+        self.conv1 = nn.Conv2d(3, 64, 7, 1 + (downsample > 2), 3)
+        self.relu1 = nn.ReLU(inplace=True)
+        self.in_planes = 64
+        self.layer1 = self._make_layer(64, 1)
+        self.layer2 = self._make_layer(96, 1 + (downsample > 1))
+        self.layer3 = self._make_layer(128, 1 + (downsample > 0))
+
+    def _make_layer(self, dim, stride):
+        seq = nn.Sequential(ResidualBlock(self.in_planes, dim, self.norm_fn, stride),
+                            ResidualBlock(dim, dim, self.norm_fn, 1))
+        self.in_planes = dim
+        return seq
+
+    def _init(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, (nn.BatchNorm2d, nn.InstanceNorm2d, nn.GroupNorm)):
+                if m.weight is not None:
+                    nn.init.constant_(m.weight, 1)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def trunk(self, x):
+        x = self.relu1(self.norm1(self.conv1(x)))
+        return self.layer3(self.layer2(self.layer1(x)))
+
+
+class BasicEncoder(_Trunk):
+    def __init__(self, output_dim=128, norm_fn="batch", dropout=0.0, downsample=3):
+        super().__init__(norm_fn, downsample)
+        self.conv2 = nn.Conv2d(128, output_dim, 1)
+        self.dropout = nn.Dropout2d(dropout) if dropout > 0 else None
+        self._init()
+
+    def forward(self, x, dual_inp=False):
+        is_list = isinstance(x, (tuple, list))
+        if is_list:
+            n = x[0].shape[0]
+            x = torch.cat(x, dim=0)
+        x = self.conv2(self.trunk(x))
+        if self.training and self.dropout is not None:
+            x = self.dropout(x)
+        return x.split(n, dim=0) if is_list else x
+
+
+class MultiBasicEncoder(_Trunk):
+    def __init__(self, output_dim=[128], norm_fn="batch", dropout=0.0, downsample=3):
+        super().__init__(norm_fn, downsample)
+        self.layer4 = self._make_layer(128, 2)
+        self.layer5 = self._make_layer(128, 2)
+        self.outputs08 = nn.ModuleList([nn.Sequential(ResidualBlock(128, 128, norm_fn, 1), nn.Conv2d(128, d[2], 3, padding=1))
+                                        for d in output_dim])
+        self.outputs16 = nn.ModuleList([nn.Sequential(ResidualBlock(128, 128, norm_fn, 1), nn.Conv2d(128, d[1], 3, padding=1))
+                                        for d in output_dim])
+        self.outputs32 = nn.ModuleList([nn.Conv2d(128, d[0], 3, padding=1) for d in output_dim])
+        self.dropout = nn.Dropout2d(dropout) if dropout > 0 else None
+        self._init()
+
+    def forward(self, x, dual_inp=False, num_layers=3):
+        x = self.trunk(x)
+        v = x
+        if dual_inp:
+            x = x[: x.shape[0] // 2]
+        outs = [[f(x) for f in self.outputs08]]
+        if num_layers >= 2:
+            y = self.layer4(x)
+            outs.append([f(y) for f in self.outputs16])
+        if num_layers >= 3:
+            outs.append([f(self.layer5(y)) for f in self.outputs32])
+        return tuple(outs) + ((v,) if dual_inp else ())
+
+
+# ------------------------------------------------------------------------------------------ update block
+class FlowHead(nn.Module):
+    def __init__(self, input_dim=128, hidden_dim=256, output_dim=2):
+        super().__init__()
+        self.conv1 = nn.Conv2d(input_dim, hidden_dim, 3, padding=1)
+        self.conv2 = nn.Conv2d(hidden_dim, output_dim, 3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.conv2(self.relu(self.conv1(x)))
+
+
+class ConvGRU(nn.Module):
+    def __init__(self, hidden_dim, input_dim, kernel_size=3):
+        super().__init__()
+        p = kernel_size // 2
+        self.convz = nn.Conv2d(hidden_dim + input_dim, hidden_dim, kernel_size, padding=p)
+        self.convr = nn.Conv2d(hidden_dim + input_dim, hidden_dim, kernel_size, padding=p)
+        self.convq = nn.Conv2d(hidden_dim + input_dim, hidden_dim, kernel_size, padding=p)
+
+    def forward(self, h, cz, cr, cq, *x_list):
+        x = torch.cat(x_list, dim=1)
+        hx = torch.cat([h, x], dim=1)
+        z = torch.sigmoid(self.convz(hx) + cz)
+        r = torch.sigmoid(self.convr(hx) + cr)
+        q = torch.tanh(self.convq(torch.cat([r * h, x], dim=1)) + cq)
+        return (1 - z) * h + z * q
+
+
+class BasicMotionEncoder(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        cor_planes = args.corr_levels * (2 * args.corr_radius + 1)
+        self.convc1 = nn.Conv2d(cor_planes, 64, 1)
+        self.convc2 = nn.Conv2d(64, 64, 3, padding=1)
+        self.convf1 = nn.Conv2d(2, 64, 7, padding=3)
+        self.convf2 = nn.Conv2d(64, 64, 3, padding=1)
+        self.conv = nn.Conv2d(128, 128 - 2, 3, padding=1)
+
+    def forward(self, flow, corr):
+        cor = F.relu(self.convc2(F.relu(self.convc1(corr))))
+        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
+        out = F.relu(self.conv(torch.cat([cor, flo], dim=1)))
+        return torch.cat([out, flow], dim=1)
+
+
+def _pool2x(x):
+    return F.avg_pool2d(x, 3, stride=2, padding=1)
+
+
+def _interp(x, dest):
+    return F.interpolate(x, dest.shape[2:], mode="bilinear", align_corners=True)
+
+
+class BasicMultiUpdateBlock(nn.Module):
+    def __init__(self, args, hidden_dims=[]):
+        super().__init__()
+        self.args = args
+        self.encoder = BasicMotionEncoder(args)
+        self.gru08 = ConvGRU(hidden_dims[2], 128 + hidden_dims[1] * (args.n_gru_layers > 1))
+        self.gru16 = ConvGRU(hidden_dims[1], hidden_dims[0] * (args.n_gru_layers == 3) + hidden_dims[2])
+        self.gru32 = ConvGRU(hidden_dims[0], hidden_dims[1])
+        self.flow_head = FlowHead(hidden_dims[2], hidden_dim=256, output_dim=2)
+        factor = 2 ** args.n_downsample
+        self.mask = nn.Sequential(nn.Conv2d(hidden_dims[2], 256, 3, padding=1), nn.ReLU(inplace=True),
+                                  nn.Conv2d(256, (factor ** 2) * 9, 1))
+
+    def forward(self, net, inp, corr=None, flow=None, iter08=True, iter16=True, iter32=True, update=True):
+        if iter32:
+            net[2] = self.gru32(net[2], *(inp[2]), _pool2x(net[1]))
+        if iter16:
+            extra = (_interp(net[2], net[1]),) if self.args.n_gru_layers > 2 else ()
+            net[1] = self.gru16(net[1], *(inp[1]), _pool2x(net[0]), *extra)
+        if iter08:
+            motion = self.encoder(flow, corr)
+            extra = (_interp(net[1], net[0]),) if self.args.n_gru_layers > 1 else ()
+            net[0] = self.gru08(net[0], *(inp[0]), motion, *extra)
+        if not update:
+            return net
+        return net, 0.25 * self.mask(net[0]), self.flow_head(net[0])
+
+
+def coords_grid(batch, ht, wd, device):
+    ys, xs = torch.meshgrid(torch.arange(ht, device=device), torch.arange(wd, device=device), indexing="ij")
+    return torch.stack([xs, ys], dim=0).float()[None].repeat(batch, 1, 1, 1)
+
+
+class RAFTStereo(nn.Module):
+    def __init__(self, args=None, imagenet_norm=False):
+        super().__init__()
+        self.args = argparse.Namespace(hidden_dims=[128] * 3, corr_implementation="reg", shared_backbone=False,
+                                       corr_levels=4, corr_radius=4, n_downsample=2, context_norm="batch",
+                                       slow_fast_gru=False, n_gru_layers=3, train_iters=22, valid_iters=32,
+                                       mixed_precision=False)
+        if args is not None:
+            for key, value in vars(args).items():
+                setattr(self.args, key, value)
+        self.imagenet_norm = imagenet_norm
+        a = self.args
+        ctx = a.hidden_dims
+        self.cnet = MultiBasicEncoder(output_dim=[a.hidden_dims, ctx], norm_fn=a.context_norm, downsample=a.n_downsample)
+        self.update_block = BasicMultiUpdateBlock(a, hidden_dims=a.hidden_dims)
+        self.context_zqr_convs = nn.ModuleList([nn.Conv2d(ctx[i], a.hidden_dims[i] * 3, 3, padding=1)
+                                                for i in range(a.n_gru_layers)])
+        if a.shared_backbone:
+            self.conv2 = nn.Sequential(ResidualBlock(128, 128, "instance", stride=1), nn.Conv2d(128, 256, 3, padding=1))
+        else:
+            self.fnet = BasicEncoder(output_dim=256, norm_fn="instance", downsample=a.n_downsample)
+        self.freeze_bn()
+
+    def freeze_bn(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    def upsample_flow(self, flow, mask):
+        """Convex 9-tap upsampling (raft_stereo.py:81-93)."""
+        N, D, H, W = flow.shape
+        f = 2 ** self.args.n_downsample
+        mask = torch.softmax(mask.view(N, 1, 9, f, f, H, W), dim=2)
+        up = F.unfold(f * flow, [3, 3], padding=1).view(N, D, 9, 1, 1, H, W)
+        up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
+        return up.reshape(N, D, f * H, f * W)
+
+    def forward(self, image1, image2, iters=None, flow_init=None, test_mode=False):
+        if self.training:
+            raise NotImplementedError("stereo_toolbox_b200: the training path is not built yet; call model.eval()")
+        a = self.args
+        iters = a.valid_iters if iters is None else iters
+        if not self.imagenet_norm:
+            mean = torch.tensor([0.485, 0.456, 0.406], device=image1.device).view(1, 3, 1, 1)
+            std = torch.tensor([0.229, 0.224, 0.225], device=image1.device).view(1, 3, 1, 1)
+            image1 = 2 * (image1 * std + mean) - 1.0
+            image2 = 2 * (image2 * std + mean) - 1.0
+        if a.shared_backbone:
+            *cnet_list, x = self.cnet(torch.cat((image1, image2), dim=0), dual_inp=True, num_layers=a.n_gru_layers)
+            fmap1, fmap2 = self.conv2(x).split(x.shape[0] // 2, dim=0)
+        else:
+            cnet_list = self.cnet(image1, num_layers=a.n_gru_layers)
+            fmap1, fmap2 = self.fnet([image1, image2])
+        net_list = [torch.tanh(x[0]) for x in cnet_list]
+        inp_list = [torch.relu(x[1]) for x in cnet_list]
+        inp_list = [list(conv(i).split(conv.out_channels // 3, dim=1)) for i, conv in zip(inp_list, self.context_zqr_convs)]
+
+        if a.corr_implementation not in ("reg", "reg_cuda"):
+            raise NotImplementedError("only the regular all-pairs CorrBlock1D ('reg') is built on the CUDA path")
+        # ---- hot path: all-pairs correlation + pyramid (once), lookup (every iteration)
+        corr_fn = CorrBlock1D(fmap1.float(), fmap2.float(), radius=a.corr_radius, num_levels=a.corr_levels)
+
+        n, _, h, w = net_list[0].shape
+        coords0 = coords_grid(n, h, w, image1.device)
+        coords1 = coords0.clone()
+        if flow_init is not None:
+            coords1 = coords1 + flow_init
+        flow_up = None
+        for itr in range(iters):
+            coords1 = coords1.detach()
+            corr = corr_fn(coords1)
+            flow = coords1 - coords0
+            if a.n_gru_layers == 3 and a.slow_fast_gru:
+                net_list = self.update_block(net_list, inp_list, iter32=True, iter16=False, iter08=False, update=False)
+            if a.n_gru_layers >= 2 and a.slow_fast_gru:
+                net_list = self.update_block(net_list, inp_list, iter32=a.n_gru_layers == 3, iter16=True, iter08=False,
+                                             update=False)
+            net_list, up_mask, delta_flow = self.update_block(net_list, inp_list, corr, flow,
+                                                              iter32=a.n_gru_layers == 3, iter16=a.n_gru_layers >= 2)
+            delta_flow[:, 1] = 0.0                    # stereo: project the update onto the epipolar line
+            coords1 = coords1 + delta_flow
+            if itr < iters - 1:
+                continue
+            flow_up = self.upsample_flow(coords1 - coords0, up_mask)[:, :1]
+        return -flow_up

@@ -183,8 +183,21 @@ def models():
     json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
 
 
+@torch.no_grad()
+def raft():
+    """RAFT-Stereo (config 4 family): 1x3x64x128, 6 iterations, default args (3 GRU levels, corr 4 levels r=4)."""
+    net = ref("RAFTStereo.raft_stereo").RAFTStereo()
+    sd = _load_synth(net)
+    left, right = synth_pair(1, 64, 128, seed=2, shift=3)
+    out = net(left, right, iters=6)
+    save("raft_stereo.npz", disp=out)
+    meta = json.load(open(os.path.join(HERE, "models.json")))
+    meta["raft_stereo"] = dict(keys=_keys(sd), checksum=state_checksum(sd), shape=[1, 64, 128], shift=3, iters=6)
+    json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["ops", "blocks", "models"]
+    which = sys.argv[1:] or ["ops", "blocks", "models", "raft"]
     for w in which:
         globals()[w]()

@@ -63,3 +63,58 @@ def test_gwcnet_oracle_fp32_wider():
         disp = net(left.cuda(), right.cuda()).cpu()
     torch.testing.assert_close(net._last_cost.cpu(), aux["cost3"], rtol=2e-3, atol=2e-3)
     assert (disp - want).abs().mean().item() < 1e-3
+
+
+def test_raft_stereo_golden():
+    """BASELINE config 4 family: RAFT-Stereo with CorrBlock1D (all-pairs corr + pyramid + per-iteration lookup) on the
+    CUDA path vs the reference's own output."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    g = load_golden("raft_stereo.npz")
+    sd, meta = golden_state("raft_stereo", calib=False)
+    net = S.RAFTStereo()
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    left, right = synth_pair(1, 64, 128, seed=2, shift=meta["shift"])
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False       # the 2-D encoders/GRUs are torch; keep them fp32 for the comparison
+    try:
+        with torch.no_grad():
+            out = net(left.cuda(), right.cuda(), iters=meta["iters"]).cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert out.shape == g["disp"].shape == (1, 1, 64, 128)
+    epe = (out - g["disp"]).abs().mean().item()
+    assert epe < 1e-3, f"EPE vs reference {epe}"
+
+
+def test_raft_stereo_oracle_512x1024_shape_slice():
+    """A wider pair (W/4 = 96 > one lookup tile, 8 iterations) against the same model run on CPU with the oracle
+    CorrBlock1D."""
+    import stereo_toolbox_b200 as S
+    import stereo_toolbox_b200.raft_stereo as rs
+    from oracle import ref_ops as R
+    from stereo_toolbox_b200.synth import synth_pair
+    sd, meta = golden_state("raft_stereo", calib=False)
+    left, right = synth_pair(1, 96, 384, seed=4, shift=11)
+    cpu = rs.RAFTStereo()
+    cpu.load_state_dict(sd)
+    cpu.eval()
+    old = rs.CorrBlock1D
+    rs.CorrBlock1D = R.CorrBlock1D
+    try:
+        with torch.no_grad():
+            want = cpu(left, right, iters=8)
+    finally:
+        rs.CorrBlock1D = old
+    net = S.RAFTStereo()
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            got = net(left.cuda(), right.cuda(), iters=8).cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert (got - want).abs().mean().item() < 1e-3
