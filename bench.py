@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
     ap.add_argument("--precision", default=None, help="fp32 | bf16 | fp16 (default: STB_PRECISION or fp16)")
-    ap.add_argument("--features", default=None, help="2-D extractor mode: fp32 | tf32 | fp16 (default: model default)")
+    ap.add_argument("--features", default=None, help="2-D extractor mode: fp32 | tf32 | tf32_cl | fp16 (default: model default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=1, help="pairs in the cpu_baseline sample")
     return ap.parse_args()
@@ -174,6 +174,8 @@ def main():
         sampler.start()
         time.sleep(0.25)
         prof.enabled = True
+        if os.environ.get("STB_CUDA_PROFILER"):       # ncu --profile-from-start off: capture the timed region only
+            torch.cuda.profiler.start()
         launches0 = _lib.LAUNCH_COUNT
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -182,6 +184,8 @@ def main():
         ev1.record()
         barrier()
         launches = _lib.LAUNCH_COUNT - launches0
+        if os.environ.get("STB_CUDA_PROFILER"):
+            torch.cuda.profiler.stop()
         prof.enabled = False
         ms = ev0.elapsed_time(ev1)
         # ---- end-to-end region: pinned host -> device -> model -> host, EVERY step, through the public

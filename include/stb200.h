@@ -118,13 +118,17 @@ int stb_cl16_to_ncdhw(const void* src, float* dst, int f16, int B, int C, long l
  * in_stride 1: tap t reads input plane s+dz[t] at (jh+in_h_off+dh[t], jw+in_w_off+dw[t]).
  * in_stride 2: tap t reads plane 2s+dz[t], parity sub-tile sub[t] = 2*ph+pw, at half-resolution index
  * (jh+in_h_off+dh[t], jw+in_w_off+dw[t]) i.e. input (2*(..)+ph, 2*(..)+pw).   dh,dw in [0,3]; weight tile
- * widx[t].  All index arrays are HOST arrays.  flags: bit0 = UMMA base-offset convention, bit1 = TMA
- * element-stride box convention (both settled by csrc/probe/umma_probe.cu); dchunk: depth steps per CTA
+ * widx[t].  nblk[t]/cls0[t] (nullable): the tap's MMA spans nblk consecutive weight tiles (N = nblk*Cn) and
+ * accumulates into column blocks [cls0, cls0+nblk) -- kw-merge uses 3 blocks, the merged transposed conv
+ * (flags bit3) 8 parity-class blocks drained in one round.  All index arrays are HOST arrays.
+ * flags: bit0 UMMA base-offset convention, bit1 TMA element-stride box convention (both settled by
+ * csrc/probe/umma_probe.cu), bit2 kw-merge, bit3 merged transposed conv; dchunk: depth steps per CTA
  * (0 = auto).  Cout_valid = real (unpadded) channels. */
 int stb_conv3d_umma(const void* x, const void* wt, const float* shift, const void* residual, void* out,
                     float* ws, int f16, int B, int Cin, int KC, int Di, int Hi, int Wi, int Cout_total,
                     int Cout_valid, int Do, int Ho, int Wo, int ntaps, const int* dz, const int* dh,
-                    const int* dw, const int* sub, const int* widx, int nwtiles, int nclass,
+                    const int* dw, const int* sub, const int* widx, const int* nblk, const int* cls0,
+                    int nwtiles, int nclass,
                     const int* tap_begin, const int* tap_end, const int* od0, const int* oh0,
                     const int* ow0, int in_stride, int out_stride, int nsteps, int nclass_h, int nclass_w,
                     int in_h_off, int in_w_off, int act, int out_fp32, int flags, int dchunk,

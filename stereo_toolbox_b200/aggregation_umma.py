@@ -24,6 +24,7 @@ BO_MODE = int(os.environ.get("STB_UMMA_BO_MODE", "0"))
 ES_VARIANT = int(os.environ.get("STB_TMA_ES_VARIANT", "0"))      # box extent convention under TMA element strides
 FORCE_SIMT = os.environ.get("STB_UMMA_FORCE_SIMT", "0") == "1"
 KWMERGE = os.environ.get("STB_UMMA_KWMERGE", "1") == "1"          # merge the 3 kw taps along N (N = 3*Cout) for k3 s1 convs
+DECONV_MERGE = os.environ.get("STB_UMMA_DECONV_MERGE", "1") == "1"  # transposed conv: 8 parity classes in one accumulator round
 SIMT_STRIDE2 = os.environ.get("STB_UMMA_SIMT_STRIDE2", "0") == "1"   # keep strided convs on the CUDA-core companion
 TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
 
@@ -93,15 +94,53 @@ class UmmaPlan:
             scale = torch.ones(cout, device=w.device)
         # [kd,kh,kw,co,ci] with the BN scale folded, padded to cpad rows -> [tile][nk][cpad][KC]
         wt = (w.permute(2, 3, 4, 1, 0) if tr else w.permute(2, 3, 4, 0, 1)) * scale.view(1, 1, 1, -1, 1)
-        tiles = torch.zeros(k * k * k, cpad, cin, device=w.device)
-        tiles[:, :cout] = wt.reshape(k * k * k, cout, cin)
-        self.wt = tiles.view(k ** 3, cpad, nk, kc).permute(0, 2, 1, 3).contiguous().to(self.dtype)
-        self.nwtiles, self.kc, self.nk, self.in_stride = k ** 3, kc, nk, in_stride
-        if self.nwtiles * 16 * kc * 2 > 150 * 1024:
-            return False
         flat = lambda a, b, c: (a * k + b) * k + c
         dz, dh, dw, sub, widx, tb, te, od0, oh0, ow0 = [], [], [], [], [], [], [], [], [], []
-        if not tr:
+        nblk, cls0 = None, None
+        tile_src = list(range(k ** 3))          # which (kd,kh,kw) weight matrix each staged tile holds
+        self.deconv_merge = False
+        if tr and DECONV_MERGE and stride == 2:
+            # ---- merged transposed conv: one accumulator round holds all 8 output-parity classes (column block
+            # c = cd*4+ch*2+cw).  A shift (a,b,c) of the input tile feeds every class whose per-dim tap set contains it;
+            # each maximal run of consecutive class indices is ONE MMA (N = run*Cn) against consecutively staged tiles.
+            per_dim = [[(kk, (c + pad - kk) // stride) for kk in range(k) if (c + pad - kk) % stride == 0]
+                       for c in range(stride)]
+            offs = sorted({o for lst in per_dim for _, o in lst})
+            mn = min(offs)
+            kof = [{o: kk for kk, o in per_dim[c]} for c in range(stride)]       # class bit -> {offset: k}
+            shifts = [(a, b, c) for a in offs for b in offs for c in offs]
+            def classes_of(sh):
+                return [cd * 4 + ch * 2 + cw for cd in range(2) for ch in range(2) for cw in range(2)
+                        if sh[0] in kof[cd] and sh[1] in kof[ch] and sh[2] in kof[cw]]
+            shifts.sort(key=lambda sh: -len(classes_of(sh)))                      # the all-classes shift first
+            if len(classes_of(shifts[0])) == 8:
+                tile_src, nblk, cls0 = [], [], []
+                tb.append(0)
+                for sh in shifts:
+                    cl = classes_of(sh)
+                    i = 0
+                    while i < len(cl):
+                        j = i
+                        while j + 1 < len(cl) and cl[j + 1] == cl[j] + 1:
+                            j += 1
+                        dz.append(sh[0]); dh.append(sh[1] - mn); dw.append(sh[2] - mn); sub.append(0)
+                        widx.append(len(tile_src)); nblk.append(j - i + 1); cls0.append(cl[i])
+                        for c in cl[i:j + 1]:
+                            cd, ch, cw = c >> 2, (c >> 1) & 1, c & 1
+                            tile_src.append(flat(kof[cd][sh[0]], kof[ch][sh[1]], kof[cw][sh[2]]))
+                        i = j + 1
+                te.append(len(dz)); od0.append(0); oh0.append(0); ow0.append(0)
+                self.in_off, self.out_stride, self.merge, self.deconv_merge = mn, stride, False, True
+        full = torch.zeros(k * k * k, cpad, cin, device=w.device)
+        full[:, :cout] = wt.reshape(k * k * k, cout, cin)
+        tiles = full[torch.tensor(tile_src, device=w.device)]
+        self.wt = tiles.view(len(tile_src), cpad, nk, kc).permute(0, 2, 1, 3).contiguous().to(self.dtype)
+        self.nwtiles, self.kc, self.nk, self.in_stride = len(tile_src), kc, nk, in_stride
+        if self.nwtiles * 16 * kc * 2 > 150 * 1024 or len(dz) > 64:
+            return False
+        if self.deconv_merge:
+            pass
+        elif not tr:
             # input index = stride*o + (kk - pad); for stride 2 split into parity p and half-res offset
             e = [kk - pad for kk in range(k)]
             par = [x % in_stride for x in e]
@@ -143,6 +182,8 @@ class UmmaPlan:
             return False
         self.ntaps, self.nclass = len(dz), len(tb)
         self.c_dz, self.c_dh, self.c_dw, self.c_sub, self.c_widx = _iarr(dz), _iarr(dh), _iarr(dw), _iarr(sub), _iarr(widx)
+        self.c_nblk = _iarr(nblk) if nblk is not None else None
+        self.c_cls0 = _iarr(cls0) if cls0 is not None else None
         self.c_tb, self.c_te, self.c_od0, self.c_oh0, self.c_ow0 = _iarr(tb), _iarr(te), _iarr(od0), _iarr(oh0), _iarr(ow0)
         self.cpad = cpad
         return True
@@ -233,10 +274,12 @@ class UmmaBackend:
                 ws = self._workspace(out.numel(), x.device) if plan.nk > 1 else None
                 _lib.call("stb_conv3d_umma", _p(x), _p(plan.wt), _p(plan.shift), _p(residual), _p(out), _p(ws),
                           self.f16, B, Cin, plan.kc, Di, Hi, Wi, plan.cout, plan.cout, Do, Ho, Wo, plan.ntaps,
-                          plan.c_dz, plan.c_dh, plan.c_dw, plan.c_sub, plan.c_widx, plan.nwtiles, plan.nclass,
+                          plan.c_dz, plan.c_dh, plan.c_dw, plan.c_sub, plan.c_widx, plan.c_nblk, plan.c_cls0,
+                          plan.nwtiles, plan.nclass,
                           plan.c_tb, plan.c_te, plan.c_od0, plan.c_oh0, plan.c_ow0, plan.in_stride, plan.out_stride,
                           nsteps, nh, nw, plan.in_off, plan.in_off, ACT[act], int(out_fp32),
-                          BO_MODE | (ES_VARIANT << 1) | (4 if plan.merge else 0), self.dchunk, _stream())
+                          BO_MODE | (ES_VARIANT << 1) | (4 if plan.merge else 0) | (8 if plan.deconv_merge else 0),
+                          self.dchunk, _stream())
             else:
                 sp = plan.simt
                 for sel, dd, dh, dw, T, in_s, out_s, (od0, oh0, ow0) in sp.classes:

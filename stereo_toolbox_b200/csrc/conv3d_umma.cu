@@ -40,7 +40,7 @@ constexpr int MAX_RING = 12;
 constexpr int UMMA_THREADS = 352;      // warp 0 TMA, warps 1-2 MMA issuers, warps 3-10 epilogue (two groups of 4)
 constexpr size_t SMEM_CAP = 227 * 1024;
 
-struct UTap { int8_t dz; uint8_t sub; int16_t rowoff; uint16_t widx; uint16_t pad1; };
+struct UTap { int8_t dz; uint8_t sub; int16_t rowoff; uint16_t widx; uint8_t nblk; uint8_t cls0; };
 struct UClass { uint16_t tap_begin, tap_end; int8_t od0, oh0, ow0, pad; };
 
 struct UArgs {
@@ -57,6 +57,7 @@ struct UArgs {
     int in_h_off, in_w_off, cin_off;
     int act, out_fp32, f16;
     int ROWB, layout, bo_mode, merge, ntaps_total;
+    int cblocks;                     // accumulator column blocks (of Cn) per M-tile: 1, 3 (kw-merge) or 8 (merged transposed conv)
     int nclass_h, nclass_w;          // class output extents per step in h/w (positions)
     uint32_t plane_bytes, chunk_bytes, wtile_bytes, w_bytes_total, tmem_cols;
     UClass cls[MAX_UCLASS];
@@ -102,7 +103,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     uint32_t* tapA = tmem_holder + 2;            // [MAX_UTAPS] A byte offset of the tap inside a plane slot
     uint32_t* tapB = tapA + MAX_UTAPS;           // [MAX_UTAPS] low word of the tap's B (weight tile) descriptor
     uint32_t* tapZ = tapB + MAX_UTAPS;           // [MAX_UTAPS] plane index of the tap relative to dzmin
-    uint32_t* slotTab = tapZ + MAX_UTAPS;        // [MAX_RING] encoded (addr >> 4) of every ring slot
+    uint32_t* tapI = tapZ + MAX_UTAPS;           // [MAX_UTAPS] instruction descriptor (N = nblk*Cn differs per tap)
+    uint32_t* tapD = tapI + MAX_UTAPS;           // [MAX_UTAPS] accumulator column offset (cls0*Cn)
+    uint32_t* slotTab = tapD + MAX_UTAPS;        // [MAX_RING] encoded (addr >> 4) of every ring slot
     uint8_t* sW = smem + 2048;
     uint8_t* sP = sW + ((a.w_bytes_total + 1023) & ~1023u);
 
@@ -123,9 +126,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
-        const int nlanes = a.nM >= 2 ? 2 : 1;    // active MMA issuers = active epilogue groups (M-tiles m = i, i+2, ...)
-        for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], nlanes); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], nlanes); mbar_init(&tmem_empty[i], 4 * nlanes); }
+        const int n_iss = a.nM >= 2 ? 2 : 1;                                     // active MMA issuers (M-tiles m, m+2, ..)
+        const int n_grp = a.nM * (a.cblocks == 8 ? 8 : 1) >= 2 ? 2 : 1;           // active epilogue groups
+        for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], n_iss); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], n_iss); mbar_init(&tmem_empty[i], 4 * n_grp); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_holder, a.tmem_cols);
@@ -135,6 +139,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         tapA[tp] = ((uint32_t)a.taps[tp].sub * a.chunk_bytes + (uint32_t)a.taps[tp].rowoff * a.ROWB) >> 4;
         tapB[tp] = (((smem_u32(sW) + (uint32_t)a.taps[tp].widx * a.wtile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
         tapZ[tp] = (uint32_t)(a.taps[tp].dz - a.dzmin);
+        tapI[tp] = instr_desc_f16(128, (uint32_t)a.taps[tp].nblk * a.Cn, F16 ? 0 : 1);
+        tapD[tp] = (uint32_t)a.taps[tp].cls0 * a.Cn;
     }
     for (int i = threadIdx.x; i < a.R; i += UMMA_THREADS) slotTab[i] = (smem_u32(sP) + (uint32_t)i * a.plane_bytes) >> 4;
     tc_fence_before();
@@ -172,12 +178,11 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             // idle issuer (single M-tile rounds)
         } else
         if (elect_one()) {
-            const uint32_t idesc = instr_desc_f16(128, a.Cn * a.merge, F16 ? 0 : 1);
             const uint64_t desc_hi = (uint64_t)((((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29)) << 32;
             const int ksteps = a.ROWB / 32;
             const uint32_t mtile16 = (128u * a.ROWB) >> 4;
             const int nM = a.nM, R = a.R, sd = a.sd_in, nclass = a.nclass;
-            const uint32_t ncol = (uint32_t)(a.Cn * a.merge);
+            const uint32_t ncol = (uint32_t)(a.Cn * a.cblocks);
             mbar_wait(bar_w, 0);
             int waited = 0;                       // planes [0, waited) are known to be resident
             int round = 0;
@@ -203,12 +208,14 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                             sl -= (sl >= R) ? R : 0;
                             const uint32_t alo = ((slotTab[sl] + moff + tapA[tp]) & 0x3FFFu) | (1u << 16);
                             const uint32_t blo = tapB[tp];
-                            mma_f16_ss(dcol, desc_hi | (uint64_t)alo, desc_hi | (uint64_t)blo, idesc, acc);
+                            const uint32_t idesc = tapI[tp];
+                            const uint32_t dcol_t = dcol + tapD[tp];
+                            mma_f16_ss(dcol_t, desc_hi | (uint64_t)alo, desc_hi | (uint64_t)blo, idesc, acc);
                             if (ksteps >= 2)
-                                mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 2u), desc_hi | (uint64_t)(blo + 2u), idesc, 1u);
+                                mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 2u), desc_hi | (uint64_t)(blo + 2u), idesc, 1u);
                             if (ksteps == 4) {
-                                mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 4u), desc_hi | (uint64_t)(blo + 4u), idesc, 1u);
-                                mma_f16_ss(dcol, desc_hi | (uint64_t)(alo + 6u), desc_hi | (uint64_t)(blo + 6u), idesc, 1u);
+                                mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 4u), desc_hi | (uint64_t)(blo + 4u), idesc, 1u);
+                                mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 6u), desc_hi | (uint64_t)(blo + 6u), idesc, 1u);
                             }
                             acc = 1;
                         }
@@ -227,7 +234,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // ================================ epilogue warps ================================
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
         const int egroup = (warp - 3) >> 2;         // epilogue group 0/1 drains M-tiles m = egroup, egroup+2, ...
-        const int my_rounds = egroup < (a.nM >= 2 ? 2 : 1) ? nouts : 0;   // idle group when rounds have one M-tile
+        const int nblk_e = a.cblocks == 8 ? 8 : 1;     // merged transposed conv: all 8 parity classes in one round
+        const int items = a.nM * nblk_e;               // (M-tile, class block) work items per round, dealt to 2 groups
+        const int my_rounds = egroup < (items >= 2 ? 2 : 1) ? nouts : 0;
         const size_t ostride_w = (size_t)a.Cout_total;
         constexpr int f16 = F16 ? 1 : 0;
         const bool full32 = (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
@@ -241,19 +250,23 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const UClass cl = a.cls[round % a.nclass];
             mbar_wait(&tmem_full[buf], (round >> 1) & 1);
             tc_fence_after();
-            const int od = s * a.out_stride + cl.od0;
-            for (int m = egroup; m < nM; m += 2) {
+            for (int item = egroup; item < items; item += 2) {
+              {
+                const int m = item / nblk_e, blk = item - m * nblk_e;
+                const int cd = nblk_e == 8 ? (blk >> 2) : cl.od0, chh = nblk_e == 8 ? ((blk >> 1) & 1) : cl.oh0,
+                          cww = nblk_e == 8 ? (blk & 1) : cl.ow0;
+                const int od = s * a.out_stride + cd;
                 const int q = 128 * m + q4 * 32 + lane;
                 const int jh_l = q / TWP, jw_l = q % TWP;
                 const int jh = jh0 + jh_l, jw = jw0 + jw_l;
                 const bool valid = (jh_l < a.TH) && (jw_l < a.TW) && (jh < a.nclass_h) && (jw < a.nclass_w) && (od < a.Do);
-                const int oh = jh * a.out_stride + cl.oh0, ow = jw * a.out_stride + cl.ow0;
+                const int oh = jh * a.out_stride + chh, ow = jw * a.out_stride + cww;
                 const bool inb = valid && oh < a.Ho && ow < a.Wo;
                 const size_t vox = (((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow;
                 for (int c0 = 0; c0 < Cn; c0 += 32) {
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) +
-                                           (uint32_t)((buf * nM + m) * Cn * merge + c0);
+                                           (uint32_t)((buf * nM + m) * Cn * a.cblocks + (nblk_e == 8 ? blk * Cn : 0) + c0);
                     __syncwarp();                      // tcgen05.ld is .sync.aligned: whole warp, converged
                     tmem_ld_32x32(taddr, v);
                     tmem_ld_wait();
@@ -341,6 +354,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         }
                     }
                 }
+              }
             }
             tc_fence_before();
             __syncwarp();
@@ -384,7 +398,8 @@ int launch_umma(int act, int f16, unsigned grid, size_t smem, cudaStream_t st, c
 extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift, const void* residual, void* out,
                                float* ws, int f16, int B, int Cin, int KC, int Di, int Hi, int Wi, int Cout_total,
                                int Cout_valid, int Do, int Ho, int Wo, int ntaps, const int* dz, const int* dh,
-                               const int* dw, const int* sub, const int* widx, int nwtiles, int nclass,
+                               const int* dw, const int* sub, const int* widx, const int* nblk, const int* cls0,
+                               int nwtiles, int nclass,
                                const int* tap_begin, const int* tap_end, const int* od0, const int* oh0,
                                const int* ow0, int in_stride, int out_stride, int nsteps, int nclass_h, int nclass_w,
                                int in_h_off, int in_w_off, int act, int out_fp32, int flags, int dchunk,
@@ -426,7 +441,16 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         a.taps[t].sub = (uint8_t)sub[t];
         a.taps[t].rowoff = (int16_t)(dh[t] * TWP + dw[t]);
         a.taps[t].widx = (uint16_t)widx[t];
+        a.taps[t].nblk = (uint8_t)(nblk ? nblk[t] : a.merge);
+        a.taps[t].cls0 = (uint8_t)(cls0 ? cls0[t] : 0);
+        if (a.taps[t].nblk < 1 || a.taps[t].nblk + a.taps[t].cls0 > 8) return STB_E_BADARG;
     }
+    // accumulator column blocks per M-tile: 8 when taps address parity-class blocks (merged transposed conv),
+    // 3 for kw-merge, else 1.  The first tap of every class must cover all blocks (it zero-initialises them).
+    a.cblocks = (flags & 8) ? 8 : a.merge;
+    for (int c = 0; c < nclass; ++c)
+        if (a.taps[tap_begin[c]].nblk != a.cblocks || a.taps[tap_begin[c]].cls0 != 0) return STB_E_BADARG;
+    if (a.cblocks == 8 && (nclass != 1 || out_stride != 2 || in_stride != 1)) return STB_E_UNSUPPORTED;
     a.ntaps_total = ntaps;
     for (int c = 0; c < nclass; ++c) {
         a.cls[c].tap_begin = (uint16_t)tap_begin[c];
@@ -449,7 +473,8 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     // (capped at 64 KB), ties to the taller tile.
     auto ring_for = [&](int cn, int th) {
         const int nM = th * TWP / 128;
-        if (2 * nM * cn * a.merge + 32 > 512 || cn * a.merge > 256) return 0;   // +32: epilogue reads 32-col blocks
+        const int slack = (cn & 31) ? 32 : 0;                                     // epilogue reads 32-column blocks
+        if (2 * nM * cn * a.cblocks + slack > 512 || cn * a.cblocks > 256) return 0;
         const size_t wbytes = (((size_t)nwtiles * cn * a.ROWB) + 1023) & ~(size_t)1023;
         const size_t plane = (size_t)a.nsub * (th + maxdh) * TWP * a.ROWB;
         if (3072 + wbytes + 1024 >= SMEM_CAP) return 0;
@@ -504,7 +529,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.dchunk = dchunk;
     a.nchunks = stb_ceil_div(nsteps, dchunk);
     int tmem_cols = 32;
-    while (tmem_cols < 2 * a.nM * Cn * a.merge + 32) tmem_cols <<= 1;
+    while (tmem_cols < 2 * a.nM * Cn * a.cblocks + ((Cn & 31) ? 32 : 0)) tmem_cols <<= 1;
     a.tmem_cols = (uint32_t)tmem_cols;
 
     CUtensorMap tm_x, tm_w;
@@ -520,8 +545,8 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.w_rows = Cpad;
     a.w_tile_stride = nk;
     a.nwtiles = nwtiles;
-    const long long nblk = (long long)B * a.nchunks * a.tiles_h * a.tiles_w;
-    if (nblk > 2147483647LL) return STB_E_BADARG;
+    const long long ncta = (long long)B * a.nchunks * a.tiles_h * a.tiles_w;
+    if (ncta > 2147483647LL) return STB_E_BADARG;
     for (int kp = 0; kp < nk; ++kp) {
         const bool last = kp == nk - 1;
         a.cin_off = kp * KC;
@@ -546,7 +571,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             if (!umma_host::make_tmap(&tm_w, cudt, 2, const_cast<void*>(wt), dims, str, box, cusw)) return STB_E_DRIVER;
             size_t smem = 3072 + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
             if (smem > SMEM_CAP) return STB_E_SMEM;
-            const int rc = launch_umma(a.act, f16, (unsigned)nblk, smem, (cudaStream_t)stream, tm_x, tm_w, a);
+            const int rc = launch_umma(a.act, f16, (unsigned)ncta, smem, (cudaStream_t)stream, tm_x, tm_w, a);
             if (rc != STB_OK) return rc;
         }
     }

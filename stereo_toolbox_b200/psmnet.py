@@ -82,13 +82,15 @@ class PSMNet(nn.Module):
         """2-D extractor: outside the hot path, runs through torch/cuDNN.  feature_mode:
           'fp32' exact fp32 convs (what the CPU reference computes; default for precision='fp32', which promises
                  <=1e-3 px), 'tf32' torch's default for convs (what the reference itself does on a GPU),
-          'fp16' channels-last fp16 autocast (fastest).  None = 'fp32' for precision fp32, else 'tf32'.
+          'tf32_cl' same arithmetic as 'tf32' but channels-last activations: cuDNN's TF32 kernels are NHWC, and with
+                 NCHW tensors ~46% of the extractor's GPU time is nchwToNhwc/nhwcToNchw transposes (profiles/ncu_launches_r01.txt),
+          'fp16' channels-last fp16 autocast.  None = 'fp32' for precision fp32, else 'tf32_cl'.
         feature_tf32 (legacy knob): False forces 'fp32'."""
         mode = self.feature_mode
         if self.feature_tf32 is False:
             mode = "fp32"
         if mode is None:
-            mode = "fp32" if self.precision == "fp32" else "tf32"
+            mode = "fp32" if self.precision == "fp32" else "tf32_cl"
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = prev and mode != "fp32"
         try:
@@ -100,6 +102,12 @@ class PSMNet(nn.Module):
                     cvt = lambda t: t.float().contiguous()
                     fl = {k: cvt(v) for k, v in fl.items()} if isinstance(fl, dict) else cvt(fl)
                     fr = {k: cvt(v) for k, v in fr.items()} if isinstance(fr, dict) else cvt(fr)
+                elif mode == "tf32_cl":
+                    if not getattr(self, "_fe_channels_last", False):
+                        self.feature_extraction.to(memory_format=torch.channels_last)
+                        self._fe_channels_last = True
+                    fl = self.feature_extraction(left.contiguous(memory_format=torch.channels_last))
+                    fr = self.feature_extraction(right.contiguous(memory_format=torch.channels_last))
                 else:
                     fl = self.feature_extraction(left)
                     fr = self.feature_extraction(right)
