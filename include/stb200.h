@@ -134,6 +134,11 @@ int stb_conv3d_umma(const void* x, const void* wt, const float* shift, const voi
                     int in_h_off, int in_w_off, int act, int out_fp32, int flags, int dchunk,
                     void* stream);
 
+/* Debug aid: arm (dev_buf = [rounds][4] int64 device buffer) or disarm (NULL) the in-kernel timeline of CTA 0 of
+ * subsequent stb_conv3d_umma launches: per accumulator round clock64() at issue start / commit / epilogue wake /
+ * buffer release.  Not used by the product path. */
+int stb_conv3d_umma_set_trace(long long* dev_buf, int rounds);
+
 /* CUDA-core companion on the same channels-last 16-bit tensors (fp32 weights wt[ntaps][Cin][Cout], fp32
  * accumulate); arguments as stb_conv3d_taps_f32. */
 int stb_conv3d_taps_cl16(const void* x, const float* wt, const float* shift, const void* residual,

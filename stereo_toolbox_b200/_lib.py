@@ -37,6 +37,7 @@ SIGNATURES = {
     "stb_cl16_to_ncdhw": [_P, _P, _I, _I, _I, _LL, _I, _P],
     "stb_conv3d_umma": [_P, _P, _P, _P, _P, _P] + [_I] * 13 + [_IP, _IP, _IP, _IP, _IP, _IP, _IP, _I, _I, _IP, _IP, _IP, _IP, _IP]
                        + [_I] * 11 + [_P],
+    "stb_conv3d_umma_set_trace": [_P, _I],
     "stb_conv3d_taps_cl16": [_P, _P, _P, _P, _P, _I, _I] + [_I] * 10 + [_IP, _IP, _IP] + [_I] * 9 + [_P],
     "stb_corr1d_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "stb_avgpool_last_f32": [_P, _P, _LL, _I, _P],

@@ -64,6 +64,12 @@ struct UArgs {
     UTap taps[MAX_UTAPS];
 };
 
+// Optional in-kernel timeline (debug aid, see tools/umma_trace.py): when armed through stb_conv3d_umma_set_trace,
+// CTA 0 records globaltimer-free clock64() stamps per accumulator round: [0] issuer-0 start of issue, [1] issuer-0
+// after commit, [2] epilogue group 0 woke (accumulator ready), [3] epilogue group 0 released the buffer.
+__device__ long long* g_umma_trace = nullptr;
+__device__ int g_umma_trace_rounds = 0;
+
 __device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
     if (f16) {
         __half2 v = __floats2half2_rn(a, b);
@@ -198,6 +204,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     const int buf = round & 1;
                     mbar_wait(&tmem_empty[buf], ((round >> 1) & 1) ^ 1);
                     tc_fence_after();
+                    const bool trace = g_umma_trace && blockIdx.x == 0 && issuer == 0 && round < g_umma_trace_rounds;
+                    if (trace) g_umma_trace[round * 4 + 0] = clock64();
                     const int t0 = a.cls[c].tap_begin, t1 = a.cls[c].tap_end;
                     for (int m = issuer; m < nM; m += 2) {
                         const uint32_t dcol = tmem_base + (uint32_t)(buf * nM + m) * ncol;
@@ -221,6 +229,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         }
                     }
                     mma_commit(&tmem_full[buf]);
+                    if (trace) g_umma_trace[round * 4 + 1] = clock64();
                 }
                 // planes below the next step's window are dead once this step's MMAs retire
                 const int dead_upto = (s + 1 < s_hi) ? ((s + 1) * sd + a.dzmin) - p_first : nplanes;
@@ -250,6 +259,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const UClass cl = a.cls[round % a.nclass];
             mbar_wait(&tmem_full[buf], (round >> 1) & 1);
             tc_fence_after();
+            const bool trace = g_umma_trace && blockIdx.x == 0 && warp == 3 && lane == 0 && round < g_umma_trace_rounds;
+            if (trace) g_umma_trace[round * 4 + 2] = clock64();
             for (int item = egroup; item < items; item += 2) {
               {
                 const int m = item / nblk_e, blk = item - m * nblk_e;
@@ -359,6 +370,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            if (trace) g_umma_trace[round * 4 + 3] = clock64();
         }
     }
     tc_fence_before();
@@ -393,6 +405,12 @@ int launch_umma(int act, int f16, unsigned grid, size_t smem, cudaStream_t st, c
 }
 
 }  // namespace
+
+extern "C" int stb_conv3d_umma_set_trace(long long* dev_buf, int rounds) {
+    if (cudaMemcpyToSymbol(g_umma_trace, &dev_buf, sizeof(dev_buf)) != cudaSuccess) return STB_E_BADARG;
+    if (cudaMemcpyToSymbol(g_umma_trace_rounds, &rounds, sizeof(rounds)) != cudaSuccess) return STB_E_BADARG;
+    return STB_OK;
+}
 
 // Host entry -- see include/stb200.h for the argument contract.
 extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift, const void* residual, void* out,
