@@ -66,7 +66,8 @@ struct UArgs {
 
 // Optional in-kernel timeline (debug aid, see tools/umma_trace.py): when armed through stb_conv3d_umma_set_trace,
 // CTA 0 records globaltimer-free clock64() stamps per accumulator round: [0] issuer-0 start of issue, [1] issuer-0
-// after commit, [2] epilogue group 0 woke (accumulator ready), [3] epilogue group 0 released the buffer.
+// after commit, [2] epilogue group 0 woke (accumulator ready), [3] epilogue group 0 released the buffer
+// (8 int64 slots per round: step top, planes resident, issue start, commit, epilogue wake, epilogue end).
 __device__ long long* g_umma_trace = nullptr;
 __device__ int g_umma_trace_rounds = 0;
 
@@ -132,10 +133,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
-        const int n_iss = a.nM >= 2 ? 2 : 1;                                     // active MMA issuers (M-tiles m, m+2, ..)
+        const int n_iss = nouts >= 2 ? 2 : 1;                                    // MMA issuers take alternate rounds
         const int n_grp = a.nM * (a.cblocks == 8 ? 8 : 1) >= 2 ? 2 : 1;           // active epilogue groups
         for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], n_iss); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], n_iss); mbar_init(&tmem_empty[i], 4 * n_grp); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * n_grp); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_holder, a.tmem_cols);
@@ -176,67 +177,73 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         }
     } else if (warp <= 2) {
         // ================================ MMA issuers (2) ================================
-        // One lane must sustain a tcgen05.mma every few tens of clocks with nobody to hide its latencies, so the
-        // loop carries no division, no descriptor construction and no constant-bank traffic (smem tables above),
-        // and the M-tiles of a round are split between two issuing warps (m = issuer, issuer+2, ...).
+        // The two issuing warps take ALTERNATE accumulator rounds: while one is blocked on a full MMA queue, the
+        // other performs the waits / bookkeeping of the next round, so the tensor pipe sees back-to-back work
+        // (in-kernel timeline, profiles/umma_trace_r01.txt: with a single issuing sequence ~1.6K of every 4.2K
+        // clocks were barrier waits with the pipe idle).  The issue loop itself carries no division, no descriptor
+        // construction and no constant-bank traffic (smem tables above).
         const int issuer = warp - 1;
-        if (issuer >= (a.nM >= 2 ? 2 : 1)) {
-            // idle issuer (single M-tile rounds)
-        } else
-        if (elect_one()) {
+        const int n_iss = nouts >= 2 ? 2 : 1;
+        if (issuer < n_iss && elect_one()) {
             const uint64_t desc_hi = (uint64_t)((((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29)) << 32;
             const int ksteps = a.ROWB / 32;
             const uint32_t mtile16 = (128u * a.ROWB) >> 4;
             const int nM = a.nM, R = a.R, sd = a.sd_in, nclass = a.nclass;
             const uint32_t ncol = (uint32_t)(a.Cn * a.cblocks);
             mbar_wait(bar_w, 0);
-            int waited = 0;                       // planes [0, waited) are known to be resident
-            int round = 0;
-            int base_slot = 0;                    // ring slot of plane (s*sd + dzmin); advanced by sd per step
-            for (int s = s_lo; s < s_hi; ++s) {
+            int waited = 0;                       // planes [0, waited) are known to be resident (this issuer's view)
+            int released = 0;                     // planes [0, released) have been handed back by this issuer
+            int wslot = 0, wphase = 0;            // ring slot / phase of plane `waited`
+            int rslot = 0;                        // ring slot of plane `released`
+            for (int round = issuer; round < nouts; round += n_iss) {
+                const int si = round / nclass, c = round - si * nclass;      // step index within the chunk, class
+                const int s = s_lo + si;
                 const int need = (s * sd + a.dzmax) - p_first + 1;
+                const bool trace = g_umma_trace && blockIdx.x == 0 && round < g_umma_trace_rounds;
+                if (trace) g_umma_trace[round * 8 + 0] = clock64();
                 while (waited < need) {
-                    mbar_wait(&plane_full[waited % R], (waited / R) & 1);
+                    mbar_wait(&plane_full[wslot], wphase);
                     ++waited;
+                    if (++wslot == R) { wslot = 0; wphase ^= 1; }
                 }
+                if (trace) g_umma_trace[round * 8 + 1] = clock64();
+                const int buf = round & 1;
+                mbar_wait(&tmem_empty[buf], ((round >> 1) & 1) ^ 1);
                 tc_fence_after();
-                for (int c = 0; c < nclass; ++c, ++round) {
-                    const int buf = round & 1;
-                    mbar_wait(&tmem_empty[buf], ((round >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const bool trace = g_umma_trace && blockIdx.x == 0 && issuer == 0 && round < g_umma_trace_rounds;
-                    if (trace) g_umma_trace[round * 4 + 0] = clock64();
-                    const int t0 = a.cls[c].tap_begin, t1 = a.cls[c].tap_end;
-                    for (int m = issuer; m < nM; m += 2) {
-                        const uint32_t dcol = tmem_base + (uint32_t)(buf * nM + m) * ncol;
-                        const uint32_t moff = (uint32_t)m * mtile16;
-                        uint32_t acc = 0;
-                        for (int tp = t0; tp < t1; ++tp) {
-                            int sl = base_slot + (int)tapZ[tp];
-                            sl -= (sl >= R) ? R : 0;
-                            const uint32_t alo = ((slotTab[sl] + moff + tapA[tp]) & 0x3FFFu) | (1u << 16);
-                            const uint32_t blo = tapB[tp];
-                            const uint32_t idesc = tapI[tp];
-                            const uint32_t dcol_t = dcol + tapD[tp];
-                            mma_f16_ss(dcol_t, desc_hi | (uint64_t)alo, desc_hi | (uint64_t)blo, idesc, acc);
-                            if (ksteps >= 2)
-                                mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 2u), desc_hi | (uint64_t)(blo + 2u), idesc, 1u);
-                            if (ksteps == 4) {
-                                mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 4u), desc_hi | (uint64_t)(blo + 4u), idesc, 1u);
-                                mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 6u), desc_hi | (uint64_t)(blo + 6u), idesc, 1u);
-                            }
-                            acc = 1;
+                if (trace) g_umma_trace[round * 8 + 2] = clock64();
+                int base_slot = ((s * sd + a.dzmin) - p_first) % R;          // one division per round
+                const int t0 = a.cls[c].tap_begin, t1 = a.cls[c].tap_end;
+                for (int m = 0; m < nM; ++m) {
+                    const uint32_t dcol = tmem_base + (uint32_t)(buf * nM + m) * ncol;
+                    const uint32_t moff = (uint32_t)m * mtile16;
+                    uint32_t acc = 0;
+                    for (int tp = t0; tp < t1; ++tp) {
+                        int sl = base_slot + (int)tapZ[tp];
+                        sl -= (sl >= R) ? R : 0;
+                        const uint32_t alo = ((slotTab[sl] + moff + tapA[tp]) & 0x3FFFu) | (1u << 16);
+                        const uint32_t blo = tapB[tp];
+                        const uint32_t idesc = tapI[tp];
+                        const uint32_t dcol_t = dcol + tapD[tp];
+                        mma_f16_ss(dcol_t, desc_hi | (uint64_t)alo, desc_hi | (uint64_t)blo, idesc, acc);
+                        if (ksteps >= 2)
+                            mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 2u), desc_hi | (uint64_t)(blo + 2u), idesc, 1u);
+                        if (ksteps == 4) {
+                            mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 4u), desc_hi | (uint64_t)(blo + 4u), idesc, 1u);
+                            mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 6u), desc_hi | (uint64_t)(blo + 6u), idesc, 1u);
                         }
+                        acc = 1;
                     }
-                    mma_commit(&tmem_full[buf]);
-                    if (trace) g_umma_trace[round * 4 + 1] = clock64();
                 }
-                // planes below the next step's window are dead once this step's MMAs retire
-                const int dead_upto = (s + 1 < s_hi) ? ((s + 1) * sd + a.dzmin) - p_first : nplanes;
-                for (int n = (s == s_lo ? 0 : (s * sd + a.dzmin) - p_first); n < dead_upto; ++n)
-                    mma_commit(&plane_empty[n % R]);
-                base_slot += sd;
-                base_slot -= (base_slot >= R) ? R : 0;
+                mma_commit(&tmem_full[buf]);
+                if (trace) g_umma_trace[round * 8 + 3] = clock64();
+                // hand back every plane this issuer will not read again: its next round is `round + n_iss`
+                const int nxt = round + n_iss;
+                const int dead_upto = nxt < nouts ? ((s_lo + nxt / nclass) * sd + a.dzmin) - p_first : nplanes;
+                while (released < dead_upto) {
+                    mma_commit(&plane_empty[rslot]);
+                    ++released;
+                    if (++rslot == R) rslot = 0;
+                }
             }
         }
     } else {
@@ -260,7 +267,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             mbar_wait(&tmem_full[buf], (round >> 1) & 1);
             tc_fence_after();
             const bool trace = g_umma_trace && blockIdx.x == 0 && warp == 3 && lane == 0 && round < g_umma_trace_rounds;
-            if (trace) g_umma_trace[round * 4 + 2] = clock64();
+            if (trace) g_umma_trace[round * 8 + 4] = clock64();
             for (int item = egroup; item < items; item += 2) {
               {
                 const int m = item / nblk_e, blk = item - m * nblk_e;
@@ -370,7 +377,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-            if (trace) g_umma_trace[round * 4 + 3] = clock64();
+            if (trace) g_umma_trace[round * 8 + 5] = clock64();
         }
     }
     tc_fence_before();

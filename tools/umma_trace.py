@@ -19,7 +19,7 @@ layer = nn.Sequential(nn.Conv3d(cin, cout, k, 1, k // 2, bias=False), nn.BatchNo
 be = UmmaBackend("fp16")
 be.conv(layer, x, "relu")
 R = 24
-buf = torch.zeros(R, 4, dtype=torch.int64, device="cuda")
+buf = torch.zeros(R, 8, dtype=torch.int64, device="cuda")
 _lib.check(_lib.lib().stb_conv3d_umma_set_trace(ctypes.c_void_p(buf.data_ptr()), R), "set_trace")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
@@ -29,10 +29,10 @@ torch.cuda.synchronize()
 _lib.check(_lib.lib().stb_conv3d_umma_set_trace(ctypes.c_void_p(0), 0), "set_trace")
 t = buf.cpu()
 print(f"layer {cin}->{cout} k{k} on [{B},{D},{H},{W}]: {e0.elapsed_time(e1) * 1e3:.1f} us")
-print("round  issue_start  issue_len  commit->epi_wake  epi_len   (clocks; issue_start relative to round 0)")
+print("round   step_top  wait_planes  wait_tmem  issue_len  commit->epi_wake  epi_len   (clocks; step_top relative to round 0)")
 t0 = int(t[0, 0])
 for r in range(R):
-    a, b, c, d = (int(v) for v in t[r])
-    if a == 0:
+    top, planes, start, commit, wake, end = (int(v) for v in t[r][:6])
+    if top == 0:
         break
-    print(f"{r:5d} {a - t0:12d} {b - a:10d} {c - b:16d} {d - c:9d}")
+    print(f"{r:5d} {top - t0:10d} {planes - top:12d} {start - planes:10d} {commit - start:10d} {wake - commit:17d} {end - wake:8d}")
