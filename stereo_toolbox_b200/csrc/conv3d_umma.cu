@@ -201,6 +201,14 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const int need = (s * sd + a.dzmax) - p_first + 1;
                 const bool trace = g_umma_trace && blockIdx.x == 0 && round < g_umma_trace_rounds;
                 if (trace) g_umma_trace[round * 8 + 0] = clock64();
+                // planes below this round's window are never read by this issuer again (some never were: the other
+                // issuer's rounds cover them) -- hand them back BEFORE blocking on new planes, or the ring deadlocks
+                const int dead_now = (s * sd + a.dzmin) - p_first;
+                while (released < dead_now) {
+                    mma_commit(&plane_empty[rslot]);
+                    ++released;
+                    if (++rslot == R) rslot = 0;
+                }
                 while (waited < need) {
                     mbar_wait(&plane_full[wslot], wphase);
                     ++waited;
