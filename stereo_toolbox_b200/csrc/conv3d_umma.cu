@@ -57,6 +57,7 @@ struct UArgs {
     int in_h_off, in_w_off, cin_off;
     int act, out_fp32, f16;
     int ROWB, layout, bo_mode, merge, ntaps_total;
+    uint32_t tab_bytes;              // issue table bytes (multiple of 1024)
     int cblocks;                     // accumulator column blocks (of Cn) per M-tile: 1, 3 (kw-merge) or 8 (merged transposed conv)
     int nclass_h, nclass_w;          // class output extents per step in h/w (positions)
     uint32_t plane_bytes, chunk_bytes, wtile_bytes, w_bytes_total, tmem_cols;
@@ -113,7 +114,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     uint32_t* tapI = tapZ + MAX_UTAPS;           // [MAX_UTAPS] instruction descriptor (N = nblk*Cn differs per tap)
     uint32_t* tapD = tapI + MAX_UTAPS;           // [MAX_UTAPS] accumulator column offset (cls0*Cn)
     uint32_t* slotTab = tapD + MAX_UTAPS;        // [MAX_RING] encoded (addr >> 4) of every ring slot
-    uint8_t* sW = smem + 2048;
+    uint4* issueTab = reinterpret_cast<uint4*>(smem + 2048);      // [R][ntaps] {A desc lo, B desc lo, idesc, D column offset}
+    uint8_t* sW = smem + 2048 + a.tab_bytes;
     uint8_t* sP = sW + ((a.w_bytes_total + 1023) & ~1023u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,6 +152,20 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         tapD[tp] = (uint32_t)a.taps[tp].cls0 * a.Cn;
     }
     for (int i = threadIdx.x; i < a.R; i += UMMA_THREADS) slotTab[i] = (smem_u32(sP) + (uint32_t)i * a.plane_bytes) >> 4;
+    // one 16-byte record per (ring phase, tap): everything the issuer needs for the tap's first MMA of M-tile 0
+    for (int i = threadIdx.x; i < a.R * a.ntaps_total; i += UMMA_THREADS) {
+        const int ph = i / a.ntaps_total, tp = i - ph * a.ntaps_total;
+        int sl = ph + (int)(a.taps[tp].dz - a.dzmin);
+        sl -= (sl >= a.R) ? a.R : 0;
+        const uint32_t a16 = ((smem_u32(sP) + (uint32_t)sl * a.plane_bytes) >> 4) +
+                             (((uint32_t)a.taps[tp].sub * a.chunk_bytes + (uint32_t)a.taps[tp].rowoff * a.ROWB) >> 4);
+        uint4 e;
+        e.x = a16 & 0x3FFFu;                                                    // (masked + flagged at issue, after + M-tile offset)
+        e.y = (((smem_u32(sW) + (uint32_t)a.taps[tp].widx * a.wtile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
+        e.z = instr_desc_f16(128, (uint32_t)a.taps[tp].nblk * a.Cn, F16 ? 0 : 1);
+        e.w = (uint32_t)a.taps[tp].cls0 * a.Cn;
+        issueTab[i] = e;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -219,19 +235,20 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 mbar_wait(&tmem_empty[buf], ((round >> 1) & 1) ^ 1);
                 tc_fence_after();
                 if (trace) g_umma_trace[round * 8 + 2] = clock64();
-                int base_slot = ((s * sd + a.dzmin) - p_first) % R;          // one division per round
+                const int phase = ((s * sd + a.dzmin) - p_first) % R;         // one division per round
+                const uint4* tab = issueTab + phase * a.ntaps_total;
                 const int t0 = a.cls[c].tap_begin, t1 = a.cls[c].tap_end;
                 for (int m = 0; m < nM; ++m) {
                     const uint32_t dcol = tmem_base + (uint32_t)(buf * nM + m) * ncol;
                     const uint32_t moff = (uint32_t)m * mtile16;
                     uint32_t acc = 0;
+#pragma unroll 3
                     for (int tp = t0; tp < t1; ++tp) {
-                        int sl = base_slot + (int)tapZ[tp];
-                        sl -= (sl >= R) ? R : 0;
-                        const uint32_t alo = ((slotTab[sl] + moff + tapA[tp]) & 0x3FFFu) | (1u << 16);
-                        const uint32_t blo = tapB[tp];
-                        const uint32_t idesc = tapI[tp];
-                        const uint32_t dcol_t = dcol + tapD[tp];
+                        const uint4 e = tab[tp];                                   // one LDS.128 per tap
+                        const uint32_t alo = ((e.x + moff) & 0x3FFFu) | (1u << 16);
+                        const uint32_t blo = e.y;
+                        const uint32_t idesc = e.z;
+                        const uint32_t dcol_t = dcol + e.w;
                         mma_f16_ss(dcol_t, desc_hi | (uint64_t)alo, desc_hi | (uint64_t)blo, idesc, acc);
                         if (ksteps >= 2)
                             mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 2u), desc_hi | (uint64_t)(blo + 2u), idesc, 1u);
@@ -510,8 +527,9 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         if (2 * nM * cn * a.cblocks + slack > 512 || cn * a.cblocks > 256) return 0;
         const size_t wbytes = (((size_t)nwtiles * cn * a.ROWB) + 1023) & ~(size_t)1023;
         const size_t plane = (size_t)a.nsub * (th + maxdh) * TWP * a.ROWB;
-        if (3072 + wbytes + 1024 >= SMEM_CAP) return 0;
-        int r = (int)((SMEM_CAP - 3072 - wbytes - 1024) / plane);
+        if (3072 + wbytes + 2048 >= SMEM_CAP) return 0;
+        // the per-(phase, tap) issue table grows with the ring: r*(plane + 16*ntaps) + 1 KB rounding slack
+        int r = (int)((SMEM_CAP - 3072 - wbytes - 2048) / (plane + (size_t)16 * ntaps));
         if (r > MAX_RING) r = MAX_RING;
         return r >= window + 1 ? r : 0;
     };
@@ -533,6 +551,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     }
     while (TH > 4 && TH - 4 >= nclass_h) TH -= 4;      // do not stage rows that do not exist
     a.R = R;
+    a.tab_bytes = (uint32_t)((((size_t)R * ntaps * 16) + 1023) & ~(size_t)1023);
     a.TH = TH; a.nM = TH * TWP / 128;
     const int box_h = TH + maxdh;
     a.chunk_bytes = (uint32_t)(box_h * TWP * a.ROWB);
@@ -602,7 +621,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             uint64_t str[1] = {(uint64_t)KC * 2};
             uint32_t box[2] = {(uint32_t)KC, (uint32_t)cn};
             if (!umma_host::make_tmap(&tm_w, cudt, 2, const_cast<void*>(wt), dims, str, box, cusw)) return STB_E_DRIVER;
-            size_t smem = 3072 + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
+            size_t smem = 3072 + a.tab_bytes + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
             if (smem > SMEM_CAP) return STB_E_SMEM;
             const int rc = launch_umma(a.act, f16, (unsigned)ncta, smem, (cudaStream_t)stream, tm_x, tm_w, a);
             if (rc != STB_OK) return rc;
