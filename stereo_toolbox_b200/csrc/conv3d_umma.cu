@@ -58,6 +58,7 @@ struct UArgs {
     int act, out_fp32, f16;
     int ROWB, layout, bo_mode, merge, ntaps_total;
     uint32_t tab_bytes;              // issue table bytes (multiple of 1024)
+    int merge_step;                  // lane distance between kw-merged column blocks (= dilation along w)
     int cblocks;                     // accumulator column blocks (of Cn) per M-tile: 1, 3 (kw-merge) or 8 (merged transposed conv)
     int nclass_h, nclass_w;          // class output extents per step in h/w (positions)
     uint32_t plane_bytes, chunk_bytes, wtile_bytes, w_bytes_total, tmem_cols;
@@ -324,7 +325,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         tmem_ld_32x32(taddr + (uint32_t)(k * Cn), v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[i]), k);
+                        for (int i = 0; i < 32; ++i) f[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[i]), k * a.merge_step);
                     }
                     const size_t eoff = vox * ostride_w + a.cout_off + c0;
                     if (inb && full32) {
@@ -474,13 +475,14 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.bo_mode = flags & 1;
     const int es_variant = (flags >> 1) & 1;
     a.merge = (flags & 4) ? 3 : 1;            // kw-merged taps: N = 3*Cn, weight tiles (kd,kh,0..2) are contiguous
+    a.merge_step = ((flags >> 8) & 7) ? ((flags >> 8) & 7) : 1;   // flags bits 8..10: dilation along w of the merged taps
     if (a.merge == 3 && (in_stride != 1 || out_stride != 1 || nclass != 1)) return STB_E_UNSUPPORTED;
     a.in_stride = in_stride;
     a.nsub = in_stride == 2 ? 4 : 1;
     a.sd_in = in_stride;
     int maxdh = 0, maxdw = 0, dzmin = 127, dzmax = -127;
     for (int t = 0; t < ntaps; ++t) {
-        if (dh[t] < 0 || dw[t] < 0 || dh[t] > 3 || dw[t] > 3 || widx[t] < 0 || widx[t] >= nwtiles || sub[t] < 0 ||
+        if (dh[t] < 0 || dw[t] < 0 || dh[t] > 6 || dw[t] > 6 || widx[t] < 0 || widx[t] >= nwtiles || sub[t] < 0 ||
             sub[t] >= a.nsub)
             return STB_E_BADARG;
         maxdh = dh[t] > maxdh ? dh[t] : maxdh;
@@ -508,7 +510,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         a.cls[c].od0 = (int8_t)od0[c]; a.cls[c].oh0 = (int8_t)oh0[c]; a.cls[c].ow0 = (int8_t)ow0[c];
     }
     a.nclass = nclass;
-    a.TW = TWP - (a.merge == 3 ? 2 : maxdw);
+    a.TW = TWP - (a.merge == 3 ? 2 * a.merge_step : maxdw);
     a.dzmin = dzmin; a.dzmax = dzmax;
     const int window = dzmax - dzmin + 1;
     a.B = B; a.Do = Do; a.Ho = Ho; a.Wo = Wo;

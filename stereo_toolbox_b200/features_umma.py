@@ -1,0 +1,155 @@
+"""2-D feature extractor of GwcNet on the tcgen05 convolution kernel ("next").
+
+The extractor's Conv2d+BatchNorm2d(+ReLU, +residual) layers run through the SAME kernel as the 3-D aggregation
+(csrc/conv3d_umma.cu): a 2-D convolution is a tap list with dz = 0 in which the image index of the (left ‖ right)
+batch plays the role of depth, so one CTA keeps its weight tiles in shared memory while it marches over all images.
+Activations stay channels-last fp16 from the RGB input (zero-padded to 16 channels) to the 320-channel
+gwc_feature / 12-channel concat_feature; parameters are read from the reference-named torch modules
+(features2d.GwcFeatures), nothing is duplicated.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .aggregation_umma import (BO_MODE, ES_VARIANT, KWMERGE, TORCH_DT, _iarr, from_channels_last, pad_channels,
+                               to_channels_last)
+from .ops import ACT, _p, _stream
+
+
+class Conv2dPlan:
+    """Tap tables + weight tiles of one Conv2d(+BN) for stb_conv3d_umma (dz = 0 everywhere)."""
+
+    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], cin_tensor: int, dtype):
+        w = conv.weight.detach().float()
+        cout, cin, kh_, kw_ = w.shape
+        assert kh_ == kw_ and conv.groups == 1 and conv.bias is None
+        k, stride, pad, dil = kh_, conv.stride[0], conv.padding[0], conv.dilation[0]
+        assert stride in (1, 2) and (stride == 1 or dil == 1)
+        if cin_tensor != cin:
+            wp = torch.zeros(cout, cin_tensor, k, k, device=w.device)
+            wp[:, :cin] = w
+            w, cin = wp, cin_tensor
+        if bn is not None:
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+            self.shift = (bn.bias.detach().float() - bn.running_mean.float() * scale).contiguous()
+        else:
+            scale, self.shift = torch.ones(cout, device=w.device), None
+        self.cin, self.cout, self.k, self.stride, self.pad, self.dil = cin, cout, k, stride, pad, dil
+        self.in_stride = stride
+        kc = min(cin, 32 if stride == 2 else 64)
+        assert cin % kc == 0 and kc in (16, 32, 64)
+        self.kc, self.nk = kc, cin // kc
+        cpad = (cout + 15) // 16 * 16
+        wt = w.permute(2, 3, 0, 1) * scale.view(1, 1, -1, 1)                # [kh,kw,co,ci]
+        tiles = torch.zeros(k * k, cpad, cin, device=w.device)
+        tiles[:, :cout] = wt.reshape(k * k, cout, cin)
+        self.wt = tiles.view(k * k, cpad, self.nk, kc).permute(0, 2, 1, 3).contiguous().to(dtype)
+        self.nwtiles = k * k
+        e = [kk * dil - pad for kk in range(k)]
+        par = [x % stride for x in e]
+        off = [(x - p) // stride for x, p in zip(e, par)]
+        mn = min(off)
+        self.in_off = mn
+        self.merge = bool(KWMERGE and stride == 1 and k == 3 and cout <= 64)   # N >= 128 is math-bound without merging
+        dz, dh, dw, sub, widx = [], [], [], [], []
+        for a in range(k):
+            if self.merge:
+                dz.append(0); dh.append(off[a] - mn); dw.append(0); sub.append(0); widx.append(a * k)
+                continue
+            for b in range(k):
+                dz.append(0); dh.append(off[a] - mn); dw.append(off[b] - mn)
+                sub.append(par[a] * 2 + par[b] if stride == 2 else 0); widx.append(a * k + b)
+        self.ntaps = len(dz)
+        self.c = [_iarr(v) for v in (dz, dh, dw, sub, widx)]
+        self.c_tb, self.c_te, self.c_z = _iarr([0]), _iarr([self.ntaps]), _iarr([0])
+        self.flags = BO_MODE | (ES_VARIANT << 1) | (4 if self.merge else 0) | ((dil & 7) << 8)
+
+    def out_size(self, n):
+        return (n + 2 * self.pad - self.dil * (self.k - 1) - 1) // self.stride + 1
+
+
+class UmmaGwcFeatures:
+    """Runs features2d.GwcFeatures (GwcNet/gwcnet.py:12-65) on the tensor-core conv kernel."""
+
+    def __init__(self, precision: str = "fp16"):
+        self.dtype = TORCH_DT[precision]
+        self.f16 = int(precision == "fp16")
+        self._plans: Dict[int, tuple] = {}
+        self._ws = None
+
+    def _plan(self, conv, bn, cin_tensor):
+        ver = (conv.weight.data_ptr(), conv.weight._version, cin_tensor) + \
+              (() if bn is None else (bn.weight._version, bn.bias._version, bn.running_mean._version,
+                                      bn.running_var._version, bn.running_mean.data_ptr()))
+        hit = self._plans.get(id(conv))
+        if hit is None or hit[0] != ver:
+            hit = (ver, Conv2dPlan(conv, bn, cin_tensor, self.dtype))
+            self._plans[id(conv)] = hit
+        return hit[1]
+
+    def conv(self, conv, bn, x, act="none", residual=None):
+        """x [1, N, H, W, C] channels-last 16-bit (N images as depth) -> [1, N, Ho, Wo, Cout]."""
+        _, N, H, W, C = x.shape
+        p = self._plan(conv, bn, C)
+        Ho, Wo = p.out_size(H), p.out_size(W)
+        out = torch.empty(1, N, Ho, Wo, p.cout, device=x.device, dtype=self.dtype)
+        ws = None
+        if p.nk > 1:
+            if self._ws is None or self._ws.numel() < out.numel():
+                self._ws = torch.empty(out.numel(), device=x.device, dtype=torch.float32)
+            ws = self._ws
+        if residual is not None:
+            assert residual.shape == out.shape and residual.dtype == self.dtype and residual.is_contiguous()
+        _lib.call("stb_conv3d_umma", _p(x), _p(p.wt), _p(p.shift), _p(residual), _p(out), _p(ws), self.f16,
+                  1, C, p.kc, N, H, W, p.cout, p.cout, N, Ho, Wo, p.ntaps, p.c[0], p.c[1], p.c[2], p.c[3], p.c[4],
+                  None, None, p.nwtiles, 1, p.c_tb, p.c_te, p.c_z, p.c_z, p.c_z, p.in_stride, 1, N, Ho, Wo,
+                  p.in_off, p.in_off, ACT[act], 0, p.flags, 0, _stream())
+        return out
+
+    def _convbn(self, seq, x, act="none", residual=None):
+        return self.conv(seq[0], seq[1], x, act, residual)
+
+    def _block(self, blk, x):
+        """BasicBlock (GwcNet/submodule.py:66-91): conv1+BN+ReLU, conv2+BN, + shortcut (no ReLU after the add)."""
+        y = self._convbn(blk.conv1[0], x, "relu")
+        short = x if blk.downsample is None else self.conv(blk.downsample[0], blk.downsample[1], x)
+        return self._convbn(blk.conv2, y, "none", residual=short)
+
+    @torch.no_grad()
+    def __call__(self, fe, left, right):
+        """fe: features2d.GwcFeatures; left/right [B,3,H,W] fp32.  Returns (feat_left, feat_right) dicts of NCHW fp32
+        tensors like the reference feature_extraction (the layout the volume builder reads)."""
+        B = left.shape[0]
+        x = torch.cat((left, right), 0)                                   # [2B,3,H,W]
+        H, W = x.shape[2:]
+        x = to_channels_last(x.view(2 * B, 3, H, W), 16, self.dtype).view(1, 2 * B, H, W, 16)
+        fc = fe.firstconv
+        x = self._convbn(fc[0], x, "relu")
+        x = self._convbn(fc[2], x, "relu")
+        x = self._convbn(fc[4], x, "relu")
+        for blk in fe.layer1:
+            x = self._block(blk, x)
+        l2 = x
+        for blk in fe.layer2:
+            l2 = self._block(blk, l2)
+        l3 = l2
+        for blk in fe.layer3:
+            l3 = self._block(blk, l3)
+        l4 = l3
+        for blk in fe.layer4:
+            l4 = self._block(blk, l4)
+        gwc = torch.cat((l2, l3, l4), dim=-1)                             # [1,2B,h,w,320]
+        _, N, h, w, _ = gwc.shape
+        gwc_f = from_channels_last(gwc.view(N, h, w, 320))                # [2B,320,h,w] fp32
+        outs = ({"gwc_feature": gwc_f[:B]}, {"gwc_feature": gwc_f[B:]})
+        if fe.concat_feature:
+            y = self._convbn(fe.lastconv[0], gwc, "relu")
+            y = self.conv(fe.lastconv[2], None, y)
+            cat_f = from_channels_last(y.view(N, h, w, y.shape[-1]))
+            outs[0]["concat_feature"], outs[1]["concat_feature"] = cat_f[:B], cat_f[B:]
+        return outs

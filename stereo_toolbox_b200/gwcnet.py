@@ -91,7 +91,9 @@ class GwcNet(nn.Module):
                  <=1e-3 px), 'tf32' torch's default for convs (what the reference itself does on a GPU),
           'tf32_cl' same arithmetic as 'tf32' but channels-last activations: cuDNN's TF32 kernels are NHWC, and with
                  NCHW tensors ~46% of the extractor's GPU time is nchwToNhwc/nhwcToNchw transposes (profiles/ncu_launches_r01.txt),
-          'fp16' channels-last fp16 autocast.  None = 'fp32' for precision fp32, else 'tf32_cl'.
+          'fp16' channels-last fp16 autocast,
+          'umma' the extractor's Conv2d+BN(+ReLU,+residual) layers on the tcgen05 conv kernel in fp16/bf16
+                 (features_umma.py).  None = 'fp32' for precision fp32, else 'tf32_cl'.
         feature_tf32 (legacy knob): False forces 'fp32'."""
         mode = self.feature_mode
         if self.feature_tf32 is False:
@@ -101,6 +103,12 @@ class GwcNet(nn.Module):
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = prev and mode != "fp32"
         try:
+            if mode == "umma":
+                from .features_umma import UmmaGwcFeatures
+                if getattr(self, "_fe_umma", None) is None or self._fe_umma.dtype != self._be.dtype:
+                    self._fe_umma = UmmaGwcFeatures(self._be.name)
+                with self._be.prof.bracket("features2d_umma", 0.0, 0.0):
+                    return self._fe_umma(self.feature_extraction, left, right)
             with self._be.prof.bracket("torch_features2d", 0.0, 0.0):
                 if mode == "fp16":
                     with torch.autocast("cuda", dtype=torch.float16):

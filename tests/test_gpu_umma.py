@@ -178,3 +178,33 @@ def test_psmnet_golden_16bit(prec):
     print(f"psmnet {prec} EPE vs reference: {epe:.4e} px, max {(disp - g['disp']).abs().max().item():.3e}")
     assert disp.shape == g["disp"].shape
     assert epe < EPE_TOL[prec], f"EPE vs reference {epe}"
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_gwc_features_on_umma(prec):
+    """The 2-D extractor on the tensor-core conv kernel (stride-2 stem, residual blocks, 1x1 strided shortcuts,
+    dilation-2 layer4, 320->128 K-split, 128->12 1x1) against the same torch modules in exact fp32."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.features_umma import UmmaGwcFeatures
+    from stereo_toolbox_b200.synth import synth_pair
+    sd, meta = golden_state("gwcnet_gc")
+    net = S.GwcNet_GC(32)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    left, right = synth_pair(2, 64, 160, seed=7, shift=6)
+    left, right = left.cuda(), right.cuda()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want_l, want_r = net.feature_extraction(left), net.feature_extraction(right)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    got_l, got_r = UmmaGwcFeatures(prec)(net.feature_extraction, left, right)
+    for got, want in ((got_l, want_l), (got_r, want_r)):
+        for key in ("gwc_feature", "concat_feature"):
+            g, w = got[key].float().cpu(), want[key].cpu()
+            assert g.shape == w.shape
+            rel = (g - w).abs().mean().item() / (w.abs().mean().item() + 1e-6)
+            print(f"[{prec}] {key}: mean rel err {rel:.3e}, max abs {(g - w).abs().max().item():.3e} (|w| mean {w.abs().mean().item():.3f})")
+            assert rel < (2e-3 if prec == "fp16" else 1.6e-2)
