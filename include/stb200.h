@@ -122,8 +122,8 @@ int stb_cl16_to_ncdhw(const void* src, float* dst, int f16, int B, int C, long l
  * accumulates into column blocks [cls0, cls0+nblk) -- kw-merge uses 3 blocks, the merged transposed conv
  * (flags bit3) 8 parity-class blocks drained in one round.  All index arrays are HOST arrays.
  * flags: bit0 UMMA base-offset convention, bit1 TMA element-stride box convention (both settled by
- * csrc/probe/umma_probe.cu), bit2 kw-merge, bit3 merged transposed conv, bits 8-10 dilation of the
- * kw-merged taps (0 = 1); a 2-D convolution is the same call with dz = 0 and the image index as depth;
+ * csrc/probe/umma_probe.cu), bit2 kw-merge, bit3 merged transposed conv, bit4 2-D convolution (dz = 0,
+ * the image index is the depth axis and is never strided), bits 8-10 dilation of the kw-merged taps (0 = 1);
  * dchunk: depth steps per CTA
  * (0 = auto).  Cout_valid = real (unpadded) channels. */
 int stb_conv3d_umma(const void* x, const void* wt, const float* shift, const void* residual, void* out,

@@ -479,7 +479,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     if (a.merge == 3 && (in_stride != 1 || out_stride != 1 || nclass != 1)) return STB_E_UNSUPPORTED;
     a.in_stride = in_stride;
     a.nsub = in_stride == 2 ? 4 : 1;
-    a.sd_in = in_stride;
+    a.sd_in = (flags & 16) ? 1 : in_stride;     // flags bit4: 2-D convolution, the depth axis (image index) is never strided
     int maxdh = 0, maxdw = 0, dzmin = 127, dzmax = -127;
     for (int t = 0; t < ntaps; ++t) {
         if (dh[t] < 0 || dw[t] < 0 || dh[t] > 6 || dw[t] > 6 || widx[t] < 0 || widx[t] >= nwtiles || sub[t] < 0 ||

@@ -67,7 +67,7 @@ class Conv2dPlan:
         self.ntaps = len(dz)
         self.c = [_iarr(v) for v in (dz, dh, dw, sub, widx)]
         self.c_tb, self.c_te, self.c_z = _iarr([0]), _iarr([self.ntaps]), _iarr([0])
-        self.flags = BO_MODE | (ES_VARIANT << 1) | (4 if self.merge else 0) | ((dil & 7) << 8)
+        self.flags = BO_MODE | (ES_VARIANT << 1) | (4 if self.merge else 0) | 16 | ((dil & 7) << 8)
 
     def out_size(self, n):
         return (n + 2 * self.pad - self.dil * (self.k - 1) - 1) // self.stride + 1
