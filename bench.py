@@ -173,7 +173,7 @@ def main():
         sampler = ClockSampler(local)
         sampler.start()
         time.sleep(0.25)
-        prof.enabled = True
+        prof.enabled = not os.environ.get("STB_BENCH_NOPROF")
         if os.environ.get("STB_CUDA_PROFILER"):       # ncu --profile-from-start off: capture the timed region only
             torch.cuda.profiler.start()
         launches0 = _lib.LAUNCH_COUNT

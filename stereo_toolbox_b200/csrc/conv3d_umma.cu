@@ -218,18 +218,25 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const int need = (s * sd + a.dzmax) - p_first + 1;
                 const bool trace = g_umma_trace && blockIdx.x == 0 && round < g_umma_trace_rounds;
                 if (trace) g_umma_trace[round * 8 + 0] = clock64();
-                // planes below this round's window are never read by this issuer again (some never were: the other
-                // issuer's rounds cover them) -- hand them back BEFORE blocking on new planes, or the ring deadlocks
+                // Ring bookkeeping.  Both issuers observe (wait for) EVERY plane in order and hand back every plane
+                // below their current window, also planes only the other issuer read: a plane slot is recycled when both
+                // have released it.  An issuer releases a plane only after it has seen that plane land, so its arrival can
+                // never fall into the slot's previous phase (that race corrupted the ring once -- flaky deadlock/trap).
                 const int dead_now = (s * sd + a.dzmin) - p_first;
+                while (waited < need) {
+                    while (released < dead_now && released < waited) {
+                        mma_commit(&plane_empty[rslot]);
+                        ++released;
+                        if (++rslot == R) rslot = 0;
+                    }
+                    mbar_wait(&plane_full[wslot], wphase);
+                    ++waited;
+                    if (++wslot == R) { wslot = 0; wphase ^= 1; }
+                }
                 while (released < dead_now) {
                     mma_commit(&plane_empty[rslot]);
                     ++released;
                     if (++rslot == R) rslot = 0;
-                }
-                while (waited < need) {
-                    mbar_wait(&plane_full[wslot], wphase);
-                    ++waited;
-                    if (++wslot == R) { wslot = 0; wphase ^= 1; }
                 }
                 if (trace) g_umma_trace[round * 8 + 1] = clock64();
                 const int buf = round & 1;
@@ -264,7 +271,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 if (trace) g_umma_trace[round * 8 + 3] = clock64();
                 // hand back every plane this issuer will not read again: its next round is `round + n_iss`
                 const int nxt = round + n_iss;
-                const int dead_upto = nxt < nouts ? ((s_lo + nxt / nclass) * sd + a.dzmin) - p_first : nplanes;
+                int dead_upto = nxt < nouts ? ((s_lo + nxt / nclass) * sd + a.dzmin) - p_first : nplanes;
+                if (dead_upto > waited) dead_upto = waited;          // only planes this issuer has seen land
                 while (released < dead_upto) {
                     mma_commit(&plane_empty[rslot]);
                     ++released;
