@@ -93,13 +93,13 @@ class GwcNet(nn.Module):
                  NCHW tensors ~46% of the extractor's GPU time is nchwToNhwc/nhwcToNchw transposes (profiles/ncu_launches_r01.txt),
           'fp16' channels-last fp16 autocast,
           'umma' the extractor's Conv2d+BN(+ReLU,+residual) layers on the tcgen05 conv kernel in fp16/bf16
-                 (features_umma.py).  None = 'fp32' for precision fp32, else 'tf32_cl'.
+                 (features_umma.py).  None = 'fp32' for precision fp32, else 'umma'.
         feature_tf32 (legacy knob): False forces 'fp32'."""
         mode = self.feature_mode
         if self.feature_tf32 is False:
             mode = "fp32"
         if mode is None:
-            mode = "fp32" if self.precision == "fp32" else "tf32_cl"
+            mode = "fp32" if self.precision == "fp32" else "umma"
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = prev and mode != "fp32"
         try:
