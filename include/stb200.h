@@ -177,6 +177,26 @@ int stb_geo_lookup_f32(const float* const* geo, const float* const* corr, const 
 /* geo volume [B,C,D,H,W] -> [B,H,W,C,D] (IGEVStereo/geometry.py:19). */
 int stb_geo_permute_f32(const float* src, float* dst, int B, int C, int D, int H, int W, void* stream);
 
+/* ---- ACVNet pieces -----------------------------------------------------------------------------
+ * Depthwise (1,3,3) dilated "patch" convolution, ACVNet/acv.py:109-112 (nn.Conv3d(C, C, (1,3,3), groups=C,
+ * dilation=d, padding=(0,d,d), bias=False)) as used at :169-173.  x, out [B,c_total,D,H,W] fp32 (out != x);
+ * channels [c_off, c_off+C) are processed with weight [C,1,1,3,3]; the other channels of `out` are untouched, so
+ * patch_l1/l2/l3 write their slices of one buffer (replaces the torch.cat of :173). */
+int stb_patch_dw_f32(const float* x, const float* weight, float* out, int B, int c_total, int c_off, int C,
+                     int D, int H, int W, int dilation, void* stream);
+
+/* Block self-attention core of attention_block.forward, ACVNet/submodule.py:381-428, between the qkv Linear and
+ * final1x1: softmax(q k^T * head_dim^-0.5 + mask) v inside non-overlapping (b0,b1,b2) blocks, `heads` heads.
+ * qkv holds the Linear's output over the UN-padded volume, logical shape [B,3C,D,H0,W0] with the element strides
+ * qkv_strides[5] = (b,c,d,h,w) (so NCDHW fp32 and NDHWC 16-bit tensors both bind); channel = which*C + head*hd + e.
+ * H0/W0 are padded up to multiples of b1/b2 implicitly: padded tokens take q,k,v = qkv_bias [3C] (the reference
+ * pads with zeros BEFORE the Linear), and the pad mask follows :403-409 including its "-0:" slice behaviour.
+ * out: logical [B,C,D,H0,W0] with out_strides[5]; dtype 0 = fp32, 1 = fp16, 2 = bf16 (both tensors).
+ * D must be a multiple of b0 (the reference's view() requires it). */
+int stb_block_attention(const void* qkv, const float* qkv_bias, void* out, int dtype, int B, int C, int heads,
+                        int D, int H0, int W0, int b0, int b1, int b2, const long long* qkv_strides,
+                        const long long* out_strides, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

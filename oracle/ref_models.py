@@ -7,6 +7,7 @@ proves the CUDA-backed models keep the reference's state-dict layout (SURVEY.md 
 
   gwcnet_forward : GwcNet/gwcnet.py:171-224 (+ feature_extraction :12-65, hourglass :68-105)
   psmnet_forward : PSMNet/stackhourglass.py:103-161 (+ feature_extraction PSMNet/submodule.py:57-132)
+  acvnet_forward : ACVNet/acv.py:159-250 eval branch (+ hourglass-with-attention :54-93, attention_block submodule.py:366-430)
 """
 from __future__ import annotations
 
@@ -167,4 +168,54 @@ def psmnet_forward(sd: SD, left, right, maxdisp: int, return_aux: bool = False):
     disp = R.upsample_softargmin(cost3, maxdisp, left.shape[2], left.shape[3], False, True)
     if return_aux:
         return disp, dict(cost3=cost3, volume=vol, features=(fl, fr))
+    return disp
+
+
+# --------------------------------------------------------------------------- ACVNet
+def acv_hourglass(sd: SD, p: str, x):
+    """hourglass.forward (ACVNet/acv.py:84-93): GwcNet's hourglass with the block attention after conv4."""
+    c1 = cbn3(sd, f"{p}.conv1.0", x, 2, 1, "relu")
+    c2 = cbn3(sd, f"{p}.conv2.0", c1, 1, 1, "relu")
+    c3 = cbn3(sd, f"{p}.conv3.0", c2, 2, 1, "relu")
+    c4 = cbn3(sd, f"{p}.conv4.0", c3, 1, 1, "relu")
+    a = f"{p}.attention_block"
+    c4 = R.block_attention(c4, sd[f"{a}.qkv_3d.weight"], sd[f"{a}.qkv_3d.bias"], sd[f"{a}.final1x1.weight"],
+                           sd[f"{a}.final1x1.bias"], 16, (4, 4, 4))
+    r2 = cbn3(sd, f"{p}.redir2", c2, 1, 0)
+    c5 = dbn3(sd, f"{p}.conv5", c4, "relu", r2)
+    r1 = cbn3(sd, f"{p}.redir1", x, 1, 0)
+    return dbn3(sd, f"{p}.conv6", c5, "relu", r1)
+
+
+@torch.no_grad()
+def acvnet_forward(sd: SD, left, right, maxdisp: int, attn_weights_only: bool = False, return_aux: bool = False):
+    """ACVNet.forward, eval mode (ACVNet/acv.py:159-250)."""
+    p = "feature_extraction"
+    gl = torch.cat(backbone(sd, p, left), 1)
+    gr = torch.cat(backbone(sd, p, right), 1)
+    vol = R.build_gwc_volume(gl, gr, maxdisp // 4, 40)
+    vol = R.depthwise_patch(vol, sd["patch.weight"], 1)
+    pv = torch.cat((R.depthwise_patch(vol[:, :8], sd["patch_l1.weight"], 1),
+                    R.depthwise_patch(vol[:, 8:24], sd["patch_l2.weight"], 2),
+                    R.depthwise_patch(vol[:, 24:40], sd["patch_l3.weight"], 3)), 1)
+    c = cbn3(sd, "dres1_att_.0", pv, 1, 1, "relu")
+    c = cbn3(sd, "dres1_att_.2", c, 1, 1)
+    c = acv_hourglass(sd, "dres2_att_", c)
+    att = classif(sd, "classif_att_", c)                                      # [B,1,D/4,H/4,W/4]
+    H, W = left.shape[2:]
+    if attn_weights_only:
+        return R.upsample_softargmin(att, maxdisp, H, W, False, False)
+    cat = lambda g: F.conv2d(torch.relu(convbn2d(sd, "concatconv.0", g, 1)), sd["concatconv.2.weight"])
+    cv = R.build_concat_volume(cat(gl), cat(gr), maxdisp // 4, mask_left=False)   # ACVNet/submodule.py:179-191: left unmasked
+    ac = R.attention_weighted_volume(att, cv)
+    c = cbn3(sd, "dres0.0", ac, 1, 1, "relu")
+    cost0 = cbn3(sd, "dres0.2", c, 1, 1, "relu")
+    c = cbn3(sd, "dres1.0", cost0, 1, 1, "relu")
+    cost0 = cbn3(sd, "dres1.2", c, 1, 1, "none", cost0)
+    out1 = acv_hourglass(sd, "dres2", cost0)
+    out2 = acv_hourglass(sd, "dres3", out1)
+    cost2 = classif(sd, "classif2", out2)
+    disp = R.upsample_softargmin(cost2, maxdisp, H, W, False, False)
+    if return_aux:
+        return disp, dict(cost2=cost2, att=att, patch_volume=pv, features=(gl, gr))
     return disp

@@ -164,6 +164,58 @@ def conv3d_bn_act(x, weight, bn=None, stride=1, padding=1, act="none", residual=
     return activation(y, act)
 
 
+# --------------------------------------------------------------------------- ACVNet pieces
+def depthwise_patch(vol: torch.Tensor, weight: torch.Tensor, dilation: int) -> torch.Tensor:
+    """Depthwise (1,3,3) 'patch' convolution of ACVNet (ACVNet/acv.py:109-112: Conv3d(C, C, (1,3,3), groups=C,
+    dilation=d, padding=(0,d,d), bias=False)); written as 9 shifted multiply-adds.  vol [B,C,D,H,W], weight [C,1,1,3,3]."""
+    B, C, D, H, W = vol.shape
+    d = dilation
+    xp = F.pad(vol, (d, d, d, d))
+    out = torch.zeros_like(vol)
+    for a in range(3):
+        for b in range(3):
+            out = out + weight[:, 0, 0, a, b].view(1, C, 1, 1, 1) * xp[:, :, :, a * d:a * d + H, b * d:b * d + W]
+    return out
+
+
+def block_attention(x: torch.Tensor, qkv_w: torch.Tensor, qkv_b: torch.Tensor, fin_w: torch.Tensor,
+                    fin_b: torch.Tensor, num_heads: int, block=(4, 4, 4)) -> torch.Tensor:
+    """attention_block.forward (ACVNet/submodule.py:381-430): multi-head self-attention inside non-overlapping
+    (b0,b1,b2) blocks of the volume, then a 1x1x1 conv with bias.  x [B,C,D,H0,W0].
+
+    H and W are zero-padded on the bottom/right up to a multiple of the block BEFORE the qkv Linear, so padded
+    tokens carry qkv = bias.  The mask marks padded rows/columns; the reference writes ``mask[:, -pad_b:, :]`` /
+    ``mask[:, :, -pad_r:]`` (:405-406), and a slice ``-0:`` selects EVERYTHING, so when exactly one of pad_b / pad_r
+    is zero the whole mask is 1 and nothing is masked -- kept here on purpose."""
+    B, C, D, H0, W0 = x.shape
+    b0, b1, b2 = block
+    pad_r = (b2 - W0 % b2) % b2
+    pad_b = (b1 - H0 % b1) % b1
+    x = F.pad(x, (0, pad_r, 0, pad_b))
+    H, W = H0 + pad_b, W0 + pad_r
+    d, h, w = D // b0, H // b1, W // b2
+    hd = C // num_heads
+    nt = b0 * b1 * b2
+    tok = x.view(B, C, d, b0, h, b1, w, b2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, d * h * w, nt, C)
+    qkv = tok @ qkv_w.t() + qkv_b                                            # [B,nb,nt,3C]
+    qkv = qkv.view(B, d * h * w, nt, 3, num_heads, hd)
+    q, k, v = (qkv[:, :, :, i].permute(0, 1, 3, 2, 4) for i in range(3))      # [B,nb,heads,nt,hd]
+    attn = torch.einsum("bnhie,bnhje->bnhij", q, k) * (hd ** -0.5)
+    if pad_r > 0 or pad_b > 0:
+        m = torch.zeros(H, W)
+        m[(H - pad_b) if pad_b > 0 else 0:, :] = 1                           # '-0:' == whole axis
+        m[:, (W - pad_r) if pad_r > 0 else 0:] = 1
+        m = m.view(h, b1, w, b2).permute(0, 2, 1, 3).reshape(h * w, b1 * b2)  # per (h,w) block, per in-plane token
+        diff = (m[:, :, None] != m[:, None, :]).float() * -1000.0             # [h*w, b1b2, b1b2]
+        diff = diff.repeat(d, b0, b0)                                        # token order (b0,b1,b2); block order (d,h,w)
+        attn = attn + diff.view(1, d * h * w, 1, nt, nt)
+    attn = torch.softmax(attn, dim=-1)
+    o = torch.einsum("bnhij,bnhje->bnhie", attn, v)                          # [B,nb,heads,nt,hd]
+    o = o.view(B, d, h, w, num_heads, b0, b1, b2, hd).permute(0, 4, 8, 1, 5, 2, 6, 3, 7).reshape(B, C, D, H, W)
+    o = o[:, :, :, :H0, :W0]
+    return torch.einsum("oc,bcdhw->bodhw", fin_w.view(C, C), o) + fin_b.view(1, C, 1, 1, 1)
+
+
 # --------------------------------------------------------------------------- 1-D all-pairs correlation
 def corr1d(fmap1: torch.Tensor, fmap2: torch.Tensor, scale: bool = True) -> torch.Tensor:
     """RAFTStereo/corr.py:148-156 (scale=True: divide by sqrt(C)); IGEVStereo/geometry.py:62-70

@@ -44,6 +44,8 @@ SIGNATURES = {
     "stb_corr1d_lookup_f32": [_PP, _P, _LL, _P, _I, _I, _I, _I, _I, _I, _P],
     "stb_geo_lookup_f32": [_PP, _PP, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "stb_geo_permute_f32": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "stb_patch_dw_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "stb_block_attention": [_P, _P, _P] + [_I] * 10 + [POINTER(c_longlong), POINTER(c_longlong), _P],
 }
 
 

@@ -34,6 +34,11 @@ def _split(layer) -> Tuple[nn.Module, Optional[nn.Module]]:
     return layer, None
 
 
+def _bias_ver(conv):
+    b = getattr(conv, "bias", None)
+    return () if b is None else (b.data_ptr(), b._version)
+
+
 class _NoProf:
     enabled = False
 
@@ -77,7 +82,7 @@ class Fp32Backend:
 
     def _plan(self, layer) -> ops.ConvPlan:
         conv, bn = _split(layer)
-        ver = (conv.weight.data_ptr(), conv.weight._version) + \
+        ver = (conv.weight.data_ptr(), conv.weight._version) + _bias_ver(conv) + \
               (() if bn is None else (bn.weight._version, bn.bias._version, bn.running_mean._version,
                                       bn.running_var._version, bn.running_mean.data_ptr()))
         hit = self._plans.get(id(conv))
@@ -87,7 +92,7 @@ class Fp32Backend:
         bnp = None if bn is None else (bn.weight, bn.bias, bn.running_mean, bn.running_var)
         eps = 1e-5 if bn is None else bn.eps
         plan = ops.ConvPlan(conv.weight, bnp, conv.stride[0], conv.padding[0], tr,
-                            conv.output_padding[0] if tr else 0, eps)
+                            conv.output_padding[0] if tr else 0, eps, bias=conv.bias)
         self._plans[id(conv)] = (ver, plan)
         return plan
 
@@ -118,6 +123,23 @@ class Fp32Backend:
         fl, by = conv_work(plan, tuple(x.shape), oshape, 4, residual is not None)
         with self.prof.bracket("conv3d_taps_f32", fl, by):
             return ops.conv3d_plan_apply(plan, x, act, residual)
+
+    # --- ACVNet helpers (layout boundary + the block attention core)
+    def from_ncdhw(self, x):
+        return ops._f32c(x)
+
+    def cost_ncdhw(self, cost):
+        """classifier output -> [B,1,D,H,W] fp32."""
+        return cost
+
+    def cost_native(self, cost):
+        return cost
+
+    def block_attention(self, qkv, bias, heads, block):
+        B, C3, D, H, W = qkv.shape
+        with self.prof.bracket("block_attention", 4.0 * B * D * H * W * (C3 // 3) * block[0] * block[1] * block[2],
+                               4.0 * (qkv.numel() + qkv.numel() // 3)):
+            return ops.block_attention(qkv, bias, heads, block, channels_last=False)
 
     def head(self, cost, maxdisp, H, W, align_corners=False):
         B = cost.shape[0]

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .aggregation import _NoProf, _split, conv_work
+from .aggregation import _NoProf, _bias_ver, _split, conv_work
 from .ops import ACT, _p, _stream
 
 # UMMA descriptor base-offset convention for row-shifted operand views, settled by
@@ -66,7 +66,7 @@ class UmmaPlan:
             else:
                 wpad[:, :cin] = w
             w = wpad
-        self.simt = ops.ConvPlan(w, bnp, stride, pad, tr, opad, eps)     # fp32 taps (+ shift) for the companion
+        self.simt = ops.ConvPlan(w, bnp, stride, pad, tr, opad, eps, bias=conv.bias)   # fp32 taps (+ shift) for the companion
         self.shift = self.simt.shift
         self.umma_ok = (not FORCE_SIMT) and self._build_umma(w, bnp, eps)
 
@@ -203,7 +203,7 @@ class UmmaBackend:
 
     def _plan(self, layer, cin_tensor) -> UmmaPlan:
         conv, bn = _split(layer)
-        ver = (conv.weight.data_ptr(), conv.weight._version, cin_tensor) + \
+        ver = (conv.weight.data_ptr(), conv.weight._version, cin_tensor) + _bias_ver(conv) + \
               (() if bn is None else (bn.weight._version, bn.bias._version, bn.running_mean._version,
                                       bn.running_var._version, bn.running_mean.data_ptr()))
         hit = self._plans.get(id(conv))
@@ -292,6 +292,26 @@ class UmmaBackend:
                               int(out_fp32), self.f16, B, Cin, Di, Hi, Wi, plan.cout, Do, Ho, Wo, T, dd, dh, dw, in_s,
                               out_s, od0, oh0, ow0, nd, nh, nw, ACT[act], _stream())
         return out
+
+    # ---------------------------------------------------------------- ACVNet helpers
+    def from_ncdhw(self, x):
+        """fp32 [B,C,D,H,W] -> channels-last 16-bit with the channel count padded to a swizzle row."""
+        return to_channels_last(x, pad_channels(x.shape[1]), self.dtype)
+
+    def cost_ncdhw(self, cost):
+        B, D, H, W, C = cost.shape
+        assert C == 1 and cost.dtype == torch.float32
+        return cost.view(B, 1, D, H, W)
+
+    def cost_native(self, cost):
+        B, _, D, H, W = cost.shape
+        return cost.view(B, D, H, W, 1)
+
+    def block_attention(self, qkv, bias, heads, block):
+        B, D, H, W, C3 = qkv.shape
+        with self.prof.bracket("block_attention", 4.0 * B * D * H * W * (C3 // 3) * block[0] * block[1] * block[2],
+                               2.0 * (qkv.numel() + qkv.numel() // 3)):
+            return ops.block_attention(qkv, bias, heads, block, channels_last=True)
 
     # ---------------------------------------------------------------- head (layout exit)
     def head(self, cost, maxdisp, H, W, align_corners=False):

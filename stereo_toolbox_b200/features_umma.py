@@ -121,9 +121,11 @@ class UmmaGwcFeatures:
         return self._convbn(blk.conv2, y, "none", residual=short)
 
     @torch.no_grad()
-    def __call__(self, fe, left, right):
+    def __call__(self, fe, left, right, concat_head=None):
         """fe: features2d.GwcFeatures; left/right [B,3,H,W] fp32.  Returns (feat_left, feat_right) dicts of NCHW fp32
-        tensors like the reference feature_extraction (the layout the volume builder reads)."""
+        tensors like the reference feature_extraction (the layout the volume builder reads).  ``concat_head``:
+        (convbn Sequential, 1x1 Conv2d) applied to the gwc feature -- GwcNet's own lastconv by default, ACVNet's
+        model-level concatconv (ACVNet/acv.py:104-107) when given."""
         B = left.shape[0]
         x = torch.cat((left, right), 0)                                   # [2B,3,H,W]
         H, W = x.shape[2:]
@@ -147,9 +149,11 @@ class UmmaGwcFeatures:
         _, N, h, w, _ = gwc.shape
         gwc_f = from_channels_last(gwc.view(N, h, w, 320))                # [2B,320,h,w] fp32
         outs = ({"gwc_feature": gwc_f[:B]}, {"gwc_feature": gwc_f[B:]})
-        if fe.concat_feature:
-            y = self._convbn(fe.lastconv[0], gwc, "relu")
-            y = self.conv(fe.lastconv[2], None, y)
+        if concat_head is None and fe.concat_feature:
+            concat_head = (fe.lastconv[0], fe.lastconv[2])
+        if concat_head is not None:
+            y = self._convbn(concat_head[0], gwc, "relu")
+            y = self.conv(concat_head[1], None, y)
             cat_f = from_channels_last(y.view(N, h, w, y.shape[-1]))
             outs[0]["concat_feature"], outs[1]["concat_feature"] = cat_f[:B], cat_f[B:]
         return outs

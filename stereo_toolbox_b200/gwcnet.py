@@ -108,7 +108,8 @@ class GwcNet(nn.Module):
                 if getattr(self, "_fe_umma", None) is None or self._fe_umma.dtype != self._be.dtype:
                     self._fe_umma = UmmaGwcFeatures(self._be.name)
                 with self._be.prof.bracket("features2d_umma", 0.0, 0.0):
-                    return self._fe_umma(self.feature_extraction, left, right)
+                    head = (self.concatconv[0], self.concatconv[2]) if hasattr(self, "concatconv") else None
+                    return self._fe_umma(self.feature_extraction, left, right, concat_head=head)
             with self._be.prof.bracket("torch_features2d", 0.0, 0.0):
                 if mode == "fp16":
                     with torch.autocast("cuda", dtype=torch.float16):

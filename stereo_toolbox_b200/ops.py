@@ -119,13 +119,63 @@ def disparity_regression(prob: torch.Tensor, maxdisp: int, keepdim: bool = False
     return disp.unsqueeze(1) if keepdim else disp
 
 
+# ------------------------------------------------------------------------------------ ACVNet pieces
+def patch_dw(x: torch.Tensor, weight: torch.Tensor, dilation: int, out: Optional[torch.Tensor] = None,
+             c_off: int = 0) -> torch.Tensor:
+    """Depthwise (1,3,3) dilated conv, nn.Conv3d(C, C, (1,3,3), groups=C, dilation=d, padding=(0,d,d), bias=False)
+    of ACVNet/acv.py:109-112.  x [B,Ct,D,H,W]; processes channels [c_off, c_off+C) (C = weight.shape[0]) and
+    writes the same channels of ``out`` (default: a new [B,Ct,D,H,W] tensor whose other channels are undefined
+    unless C == Ct)."""
+    _need_cuda(x, weight)
+    x = _f32c(x)
+    w = _f32c(weight)
+    B, Ct, D, H, W = x.shape
+    C = w.shape[0]
+    assert tuple(w.shape[1:]) == (1, 1, 3, 3) and c_off + C <= Ct
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.shape == x.shape and out.is_contiguous() and out.dtype == torch.float32
+    _lib.call("stb_patch_dw_f32", _p(x), _p(w), _p(out), B, Ct, c_off, C, D, H, W, int(dilation), _stream())
+    return out
+
+
+_ATT_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def block_attention(qkv: torch.Tensor, qkv_bias: torch.Tensor, num_heads: int, block=(4, 4, 4),
+                    channels_last: bool = False) -> torch.Tensor:
+    """softmax(q k^T / sqrt(hd) + pad mask) v inside (b0,b1,b2) blocks (ACVNet/submodule.py:381-428 between the qkv
+    Linear and final1x1).  qkv: [B,3C,D,H,W] (channels_last=False) or [B,D,H,W,3C]; returns the same layout with C
+    channels.  Padded tokens take q,k,v = qkv_bias."""
+    _need_cuda(qkv, qkv_bias)
+    assert qkv.is_contiguous() and qkv.dtype in _ATT_DT
+    if channels_last:
+        B, D, H, W, C3 = qkv.shape
+        C = C3 // 3
+        out = torch.empty(B, D, H, W, C, device=qkv.device, dtype=qkv.dtype)
+        qs = (D * H * W * C3, 1, H * W * C3, W * C3, C3)
+        os_ = (D * H * W * C, 1, H * W * C, W * C, C)
+    else:
+        B, C3, D, H, W = qkv.shape
+        C = C3 // 3
+        out = torch.empty(B, C, D, H, W, device=qkv.device, dtype=qkv.dtype)
+        qs = (C3 * D * H * W, D * H * W, H * W, W, 1)
+        os_ = (C * D * H * W, D * H * W, H * W, W, 1)
+    assert C3 == 3 * C and C % num_heads == 0 and qkv_bias.numel() == C3
+    arr = lambda v: (ctypes.c_longlong * 5)(*v)
+    _lib.call("stb_block_attention", _p(qkv), _p(_f32c(qkv_bias)), _p(out), _ATT_DT[qkv.dtype], B, C, num_heads,
+              D, H, W, block[0], block[1], block[2], arr(qs), arr(os_), _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------ conv family (fp32)
 class ConvPlan:
     """Tap-list form of one Conv3d / ConvTranspose3d (+ folded eval BatchNorm3d) -- see
     include/stb200.h:stb_conv3d_taps_f32.  Built once per layer and cached on the module."""
 
     def __init__(self, weight: torch.Tensor, bn: Optional[Tuple[torch.Tensor, ...]], stride: int, padding: int,
-                 transposed: bool, output_padding: int = 0, eps: float = 1e-5):
+                 transposed: bool, output_padding: int = 0, eps: float = 1e-5,
+                 bias: Optional[torch.Tensor] = None):
         w = weight.detach().float()
         dev = w.device
         if transposed:
@@ -142,6 +192,9 @@ class ConvPlan:
         else:
             scale = torch.ones(cout, device=dev)
             shift = None
+        if bias is not None:        # conv bias (ACVNet attention_block.final1x1 / qkv Linear): BN(y + b) = scale*y + (shift + scale*b)
+            sb = (scale * bias.detach().float()).contiguous()
+            shift = sb if shift is None else (shift + sb).contiguous()
         # [kd,kh,kw,Cin,Cout] * scale[co]
         wt = (w.permute(2, 3, 4, 0, 1) if transposed else w.permute(2, 3, 4, 1, 0)) * scale.view(1, 1, 1, 1, -1)
         self.cin, self.cout, self.k, self.stride, self.padding = cin, cout, k, stride, padding

@@ -196,8 +196,42 @@ def raft():
     json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
 
 
+@torch.no_grad()
+def acv():
+    """ACVNet (config 5): op-level fixtures for the block attention (three padding cases, including the reference's
+    '-0:' mask quirk) and the depthwise patch convs, plus the whole model at maxdisp 64 on a 64x144 pair
+    (1/16-scale volume 4x4x9 -> W padded to 12 inside the attention)."""
+    sub = ref("ACVNet.submodule")
+    out = {}
+    for tag, (D, H, W) in (("nopad", (4, 4, 8)), ("padr", (4, 4, 6)), ("padrb", (8, 6, 7))):
+        ab = sub.attention_block(channels_3d=32, num_heads=4, block=(4, 4, 4))
+        sd = _load_synth(ab, seed=7)
+        x = rnd(30, 2, 32, D, H, W)
+        out.update({f"att_{tag}_x": x, f"att_{tag}_y": ab(x)})
+        for k, v in sd.items():
+            out[f"att_{tag}_{k}"] = v
+    vol = rnd(31, 1, 6, 3, 9, 11)
+    for dil in (1, 2, 3):
+        conv = torch.nn.Conv3d(6, 6, kernel_size=(1, 3, 3), stride=1, dilation=dil, groups=6, padding=(0, dil, dil), bias=False)
+        conv.weight.copy_(rnd(32 + dil, 6, 1, 1, 3, 3))
+        out.update({f"patch_w{dil}": conv.weight, f"patch_y{dil}": conv(vol)})
+    out["patch_x"] = vol
+    save("ops_acv.npz", **out)
+    net = ref("ACVNet.acv").ACVNet(64)
+    sd = _load_synth(net, calib=synth_pair(2, 64, 144, seed=102, shift=3), calib_name="acvnet")
+    left, right = synth_pair(1, 64, 144, seed=3, shift=5)
+    cap = {}
+    net.classif2.register_forward_hook(lambda m, i, o: cap.__setitem__("cost2", o))
+    net.classif_att_.register_forward_hook(lambda m, i, o: cap.__setitem__("att", o))
+    disp = net(left, right)
+    save("acvnet.npz", disp=disp, cost2=cap["cost2"], att=cap["att"])
+    meta = json.load(open(os.path.join(HERE, "models.json")))
+    meta["acvnet"] = dict(keys=_keys(sd), checksum=state_checksum(sd), maxdisp=64, shape=[1, 64, 144], shift=5)
+    json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["ops", "blocks", "models", "raft"]
+    which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv"]
     for w in which:
         globals()[w]()

@@ -53,7 +53,8 @@ def test_state_dict_layout_matches_reference():
     import stereo_toolbox_b200 as S
     meta = load_meta("models.json")
     for key, ctor in (("gwcnet_gc", lambda: S.GwcNet_GC(32)), ("gwcnet_g", lambda: S.GwcNet_G(32)),
-                      ("psmnet", lambda: S.PSMNet(32)), ("raft_stereo", lambda: S.RAFTStereo())):
+                      ("psmnet", lambda: S.PSMNet(32)), ("raft_stereo", lambda: S.RAFTStereo()),
+                      ("acvnet", lambda: S.ACVNet(64))):
         sd = ctor().state_dict()
         want = meta[key]["keys"]
         assert set(sd) == set(want)

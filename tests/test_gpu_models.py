@@ -118,3 +118,42 @@ def test_raft_stereo_oracle_512x1024_shape_slice():
     finally:
         torch.backends.cudnn.allow_tf32 = prev
     assert (got - want).abs().mean().item() < 1e-3
+
+
+def test_acvnet_golden_fp32():
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    g = load_golden("acvnet.npz")
+    sd, meta = golden_state("acvnet")
+    net = S.ACVNet(meta["maxdisp"])
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    left, right = synth_pair(1, 64, 144, seed=3, shift=meta["shift"])
+    with torch.no_grad():
+        disp = net(left.cuda(), right.cuda()).cpu()
+    assert disp.shape == g["disp"].shape
+    torch.testing.assert_close(net._last_att.cpu(), g["att"], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(net._last_cost.cpu(), g["cost2"], rtol=2e-3, atol=2e-3)
+    epe = (disp - g["disp"]).abs().mean().item()
+    assert epe < 1e-3, f"EPE vs reference {epe}"
+    net.attn_weights_only = True
+    with torch.no_grad():
+        att_disp = net(left.cuda(), right.cuda()).cpu()
+    want = M.acvnet_forward(sd, left, right, meta["maxdisp"], attn_weights_only=True)
+    assert (att_disp - want).abs().mean().item() < 1e-3
+
+
+def test_acvnet_oracle_fp32_padded_shape():
+    """H/16 and W/16 both ragged against the 4x4x4 attention blocks (pad_b > 0 and pad_r > 0: the masked case)."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    sd, _ = golden_state("acvnet")
+    left, right = synth_pair(1, 96, 112, seed=6, shift=4)          # 1/16 scale: 6 x 7
+    want = M.acvnet_forward(sd, left, right, 64)
+    net = S.ACVNet(64)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        disp = net(left.cuda(), right.cuda()).cpu()
+    epe = (disp - want).abs().mean().item()
+    assert epe < 1e-3, f"EPE vs oracle {epe}"

@@ -144,3 +144,48 @@ def test_torch_ops_registration():
     close(v, R.build_gwc_volume(L, Rr, 5, 4), 1e-5, 2e-5)
     m = torch.ops.stb200.gwc_volume(L.to("meta"), Rr.to("meta"), 5, 4)
     assert m.shape == v.shape
+
+
+@pytest.mark.parametrize("tag", ["nopad", "padr", "padrb"])
+def test_block_attention_golden(tag):
+    """stb_block_attention against the reference attention_block outputs (fixture), fp32 NCDHW; the qkv Linear and
+    final1x1 go through the conv family as 1x1x1 convolutions with bias."""
+    from stereo_toolbox_b200.acvnet import attention_block
+    from stereo_toolbox_b200.aggregation import Fp32Backend
+    g = load_golden("ops_acv.npz")
+    ab = attention_block(32, num_heads=4, block=(4, 4, 4))
+    ab.load_state_dict({k: g[f"att_{tag}_{k}"] for k in ("qkv_3d.weight", "qkv_3d.bias", "final1x1.weight", "final1x1.bias")})
+    ab = ab.cuda()
+    with torch.no_grad():
+        y = ab.run(Fp32Backend(), cu(g[f"att_{tag}_x"]))
+    close(y, g[f"att_{tag}_y"], 1e-4, 1e-5)
+
+
+@pytest.mark.parametrize("D,H,W,heads,C", [(12, 24, 78, 16, 128), (4, 5, 3, 2, 32), (8, 9, 13, 8, 64)])
+def test_block_attention_oracle(D, H, W, heads, C):
+    """KITTI 1/16-scale shape (pad_r = 2, pad_b = 0) and ragged small shapes, kernel alone vs the oracle core."""
+    from stereo_toolbox_b200 import ops
+    qw, qb = rnd(1, 3 * C, C) * C ** -0.5, rnd(2, 3 * C) * 0.1
+    x = rnd(3, 2, C, D, H, W)
+    eye = torch.eye(C)
+    want = R.block_attention(x, qw, qb, eye.view(C, C, 1, 1, 1), torch.zeros(C), heads)
+    qkv = torch.einsum("oc,bcdhw->bodhw", qw, x) + qb.view(1, -1, 1, 1, 1)
+    got = ops.block_attention(cu(qkv.contiguous()), cu(qb), heads, (4, 4, 4))
+    close(got, want, 1e-4, 1e-5)
+    got_cl = ops.block_attention(cu(qkv.permute(0, 2, 3, 4, 1).contiguous()), cu(qb), heads, (4, 4, 4), channels_last=True)
+    close(got_cl.permute(0, 4, 1, 2, 3), want, 1e-4, 1e-5)
+
+
+def test_patch_dw_golden_and_slices():
+    from stereo_toolbox_b200 import ops
+    g = load_golden("ops_acv.npz")
+    x = cu(g["patch_x"])
+    for dil in (1, 2, 3):
+        close(ops.patch_dw(x, cu(g[f"patch_w{dil}"]), dil), g[f"patch_y{dil}"])
+    # channel slices with different dilations into one buffer (ACVNet/acv.py:170-173)
+    out = torch.full_like(x, float("nan"))
+    ops.patch_dw(x, cu(g["patch_w1"][:2]), 1, out=out, c_off=0)
+    ops.patch_dw(x, cu(g["patch_w2"][2:4]), 2, out=out, c_off=2)
+    ops.patch_dw(x, cu(g["patch_w3"][4:]), 3, out=out, c_off=4)
+    want = torch.cat((g["patch_y1"][:, :2], g["patch_y2"][:, 2:4], g["patch_y3"][:, 4:]), 1)
+    close(out, want)

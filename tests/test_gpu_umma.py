@@ -208,3 +208,29 @@ def test_gwc_features_on_umma(prec):
             rel = (g - w).abs().mean().item() / (w.abs().mean().item() + 1e-6)
             print(f"[{prec}] {key}: mean rel err {rel:.3e}, max abs {(g - w).abs().max().item():.3e} (|w| mean {w.abs().mean().item():.3f})")
             assert rel < (2e-3 if prec == "fp16" else 1.6e-2)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_acvnet_golden_16bit(prec):
+    """ACVNet on the tensor-core backend: 1x1x1 qkv / final convs with bias on tcgen05 (Cout 384 -> N-split),
+    the block attention kernel on channels-last 16-bit tensors."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    g = load_golden("acvnet.npz")
+    sd, meta = golden_state("acvnet")
+    net = S.ACVNet(meta["maxdisp"], precision=prec)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    net.feature_tf32 = False
+    left, right = synth_pair(1, 64, 144, seed=3, shift=meta["shift"])
+    with torch.no_grad():
+        disp = net(left.cuda(), right.cuda()).cpu()
+    epe = (disp - g["disp"]).abs().mean().item()
+    e = (net._last_cost.cpu().permute(0, 4, 1, 2, 3) - g["cost2"]).abs()
+    print(f"acvnet {prec} EPE vs reference: {epe:.4e} px; cost2 err mean {e.mean().item():.3e} max {e.max().item():.3e}")
+    assert epe < {"bf16": 0.2, "fp16": 2e-2}[prec], f"EPE vs reference {epe}"
+    net.feature_tf32, net.feature_mode = None, "umma"
+    with torch.no_grad():
+        disp2 = net(left.cuda(), right.cuda()).cpu()
+    print(f"  with the tensor-core extractor + concatconv: EPE {(disp2 - g['disp']).abs().mean().item():.4e} px")
+    assert torch.isfinite(disp2).all()
