@@ -4,6 +4,7 @@
 // (GwcNet/submodule.py:30-63, GwcNet/gwcnet.py:175-180; inline loop PSMNet/stackhourglass.py:111-120).
 // Products and the group mean are fp32; only the stored value is rounded to bf16.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -135,6 +136,181 @@ volume_cl_kernel(const float* __restrict__ gl, const float* __restrict__ gr, con
     }
 }
 
+
+// ---- v2 builder: full-sector stores + LDS.128 register tiles -------------------------------------------------
+// The v1 kernel above stores 16 B per voxel per pass (half a 32-B sector, 128 B apart between lanes) and issues one
+// scalar LDS per MAC; ncu (profiles/ncu_launches_r01.txt) had it at 1.87 ms for 2.1 GB of compulsory traffic.
+// v2: CTA = (32-wide w tile, h, b).  Output channels are produced 16 at a time (32 B per voxel = one full sector);
+// their source rows (16*CPG left rows of 32 floats, 16*CPG right rows covering w0-D4 .. w0+31) are staged in smem.
+// A thread owns a 4(w) x 4(d) register tile of TWO adjacent output channels: per source row it needs 7 consecutive
+// right values (two aligned LDS.128) for 16 FMAs, because R[w-d] is constant along the (w,d) diagonal.  Results are
+// packed to 16-bit pairs into a padded smem tile and written out as 32-B runs per voxel.
+constexpr int V2_TW = 32;      // w per CTA
+constexpr int V2_DP = 16;      // depths per pass (4 e-blocks of 4)
+
+__device__ __forceinline__ void vcl_cp16(float* dst_smem, const float* src, bool valid) {
+    const int sz = valid ? 16 : 0;                   // src-size 0 -> 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src), "r"(sz)
+                 : "memory");
+}
+
+template <int CPG, bool CACHE_L>
+__global__ void __launch_bounds__(256, 2)
+volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, const float* __restrict__ cl,
+                  const float* __restrict__ cr, uint16_t* __restrict__ vol, int Cg, int G, int Cc, int H, int W,
+                  int D, int Ct_pad, int mask_left, int f16) {
+    extern __shared__ __align__(16) float sm[];
+    const int E = (D + 3) >> 2, D4 = E * 4, RP = D4 + V2_TW;
+    constexpr int NR = 16 * CPG;
+    float* Ls = sm;                                   // [NR][32]
+    float* Rs = sm + NR * V2_TW;                      // [NR][RP]   x <-> ww = w0 - D4 + x
+    uint32_t* Os = reinterpret_cast<uint32_t*>(Rs + (size_t)NR * RP);   // [V2_DP][32][9] packed channel pairs
+    const int w0 = blockIdx.x * V2_TW, h = blockIdx.y, b = blockIdx.z;
+    const size_t plane = (size_t)H * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane & 7;                           // w block: w = w0 + 4j + ww
+    const int gp = (warp & 1) * 4 + (lane >> 3);      // channel pair inside the 16-channel group
+    const int el = warp >> 1;                         // e block inside a pass
+    const float inv = 1.f / (float)CPG;
+
+    for (int oc0 = 0; oc0 < Ct_pad; oc0 += 16) {
+        __syncthreads();
+        // ---- stage source rows: one warp per row.  W % 4 == 0: 16-byte cp.async (zero-fill outside the image), all
+        // rows of the group in flight at once -- the scalar LDG->STS loop of the first v2 draft exposed one global
+        // latency per row (ncu: 47 % of the stall samples on the staging STS, long scoreboard).
+        const bool vec = (W & 3) == 0;
+        for (int r = warp; r < NR; r += 8) {
+            const int ol = r / CPG, c = r - ol * CPG, o = oc0 + ol;
+            const float* lsrc = nullptr;
+            const float* rsrc = nullptr;
+            if (o < G) {
+                lsrc = gl + ((size_t)b * Cg + (size_t)o * CPG + c) * plane + (size_t)h * W;
+                rsrc = gr + ((size_t)b * Cg + (size_t)o * CPG + c) * plane + (size_t)h * W;
+            } else if (c == 0 && o < G + Cc) {
+                lsrc = cl + ((size_t)b * Cc + (o - G)) * plane + (size_t)h * W;
+            } else if (c == 0 && o < G + 2 * Cc) {
+                rsrc = cr + ((size_t)b * Cc + (o - G - Cc)) * plane + (size_t)h * W;
+            }
+            if (vec) {
+                if (lsrc && lane < 8) {
+                    const int ww = w0 + 4 * lane;
+                    vcl_cp16(Ls + r * V2_TW + 4 * lane, lsrc + (ww < W ? ww : 0), ww < W);
+                }
+                if (rsrc)
+                    for (int x4 = lane; x4 < (RP >> 2); x4 += 32) {
+                        const int ww = w0 - D4 + 4 * x4;
+                        const bool ok = ww >= 0 && ww < W;
+                        vcl_cp16(Rs + (size_t)r * RP + 4 * x4, rsrc + (ok ? ww : 0), ok);
+                    }
+            } else {
+                if (lsrc) Ls[r * V2_TW + lane] = (w0 + lane < W) ? __ldg(lsrc + w0 + lane) : 0.f;
+                if (rsrc)
+                    for (int x = lane; x < RP; x += 32) {
+                        const int ww = w0 - D4 + x;
+                        Rs[(size_t)r * RP + x] = (ww >= 0 && ww < W) ? __ldg(rsrc + ww) : 0.f;
+                    }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        int kind[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int o = oc0 + 2 * gp + q;
+            kind[q] = o < G ? 0 : (o < G + Cc ? 1 : (o < G + 2 * Cc ? 2 : 3));
+        }
+        float4 Lc[2][CACHE_L ? CPG : 1];
+        if (CACHE_L) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int c = 0; c < CPG; ++c)
+                    if (kind[q] == 0)
+                        Lc[q][CACHE_L ? c : 0] = *reinterpret_cast<const float4*>(Ls + ((2 * gp + q) * CPG + c) * V2_TW + 4 * j);
+        }
+        for (int d0 = 0; d0 < D; d0 += V2_DP) {
+            const int e = (d0 >> 2) + el;
+            uint32_t pk[4][4];
+            if (e < E) {
+                float acc[2][4][4];
+                const int x0 = D4 + 4 * (j - e) - 4;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                    for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+                        for (int ww = 0; ww < 4; ++ww) acc[q][dd][ww] = 0.f;
+                    const int rbase = (2 * gp + q) * CPG;
+                    if (kind[q] == 0) {
+#pragma unroll
+                        for (int c = 0; c < CPG; ++c) {
+                            const float4 l4 = CACHE_L ? Lc[q][CACHE_L ? c : 0]
+                                                      : *reinterpret_cast<const float4*>(Ls + (rbase + c) * V2_TW + 4 * j);
+                            const float* rr = Rs + (size_t)(rbase + c) * RP + x0;
+                            const float4 ra = *reinterpret_cast<const float4*>(rr);
+                            const float4 rb = *reinterpret_cast<const float4*>(rr + 4);
+                            const float v[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                            const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                            for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+                                for (int ww = 0; ww < 4; ++ww) acc[q][dd][ww] = fmaf(l[ww], v[4 + ww - dd], acc[q][dd][ww]);
+                        }
+#pragma unroll
+                        for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+                            for (int ww = 0; ww < 4; ++ww) acc[q][dd][ww] *= inv;
+                    } else if (kind[q] == 1) {
+                        const float4 l4 = *reinterpret_cast<const float4*>(Ls + rbase * V2_TW + 4 * j);
+                        const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                        for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+                            for (int ww = 0; ww < 4; ++ww)
+                                acc[q][dd][ww] = (mask_left && (w0 + 4 * j + ww) < (4 * e + dd)) ? 0.f : l[ww];
+                    } else if (kind[q] == 2) {
+                        const float* rr = Rs + (size_t)rbase * RP + x0;
+                        const float4 ra = *reinterpret_cast<const float4*>(rr);
+                        const float4 rb = *reinterpret_cast<const float4*>(rr + 4);
+                        const float v[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                        for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+                            for (int ww = 0; ww < 4; ++ww) acc[q][dd][ww] = v[4 + ww - dd];
+                    }
+                }
+#pragma unroll
+                for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+                    for (int ww = 0; ww < 4; ++ww) pk[dd][ww] = pk16(acc[0][dd][ww], acc[1][dd][ww], f16);
+            }
+            __syncthreads();          // previous pass's write-out has finished reading Os
+            if (e < E) {
+#pragma unroll
+                for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+                    for (int ww = 0; ww < 4; ++ww) Os[((4 * el + dd) * V2_TW + 4 * j + ww) * 9 + gp] = pk[dd][ww];
+            }
+            __syncthreads();
+            // ---- write-out: 8 words (32 B) per voxel, consecutive lanes -> consecutive words; a thread keeps its
+            // (w, word) and walks the 16 depths of the pass with pointer increments
+            {
+                const int k = threadIdx.x & 7, wl = threadIdx.x >> 3;
+                if (w0 + wl < W) {
+                    const size_t dstride = (size_t)H * W * Ct_pad / 2;       // words per depth plane
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(vol + ((((size_t)b * D + d0) * H + h) * W + w0 + wl) * Ct_pad + oc0) + k;
+                    const uint32_t* src = Os + wl * 9 + k;
+                    const int nd = min(V2_DP, D - d0);
+#pragma unroll 4
+                    for (int dl = 0; dl < nd; ++dl) dst[dl * dstride] = src[dl * V2_TW * 9];
+                }
+            }
+        }
+    }
+}
+
 // NCDHW fp32 -> NDHWC bf16 and back (layout boundary of the tensor-core path; used by tests and by
 // models that enter / leave the path with reference-layout tensors)
 __global__ void ncdhw_to_cl_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C, size_t S,
@@ -202,6 +378,28 @@ extern "C" int stb_volume_cl16(const float* gwc_l, const float* gwc_r, const flo
     // (register-blocked CPG variants measured SLOWER on B200 -- 2.43 vs 1.86 ms at B=8 K-shape: occupancy drops
     //  to 2 CTAs/SM and the kernel is bound by staging latency + 16-byte strided stores, not by LDS)
     (void)cpg;
+    if (Ct_pad % 16 == 0 && W <= 0x7fffffff - 64 && !getenv("STB_VOLUME_V1")) {
+        const int E = (D + 3) / 4, RP = 4 * E + V2_TW;
+        const int cpg2 = G > 0 ? Cg / G : 1;
+        size_t smem2 = (size_t)16 * cpg2 * (V2_TW + RP) * sizeof(float) + (size_t)V2_DP * V2_TW * 9 * sizeof(uint32_t);
+        dim3 grid2(stb_ceil_div(W, V2_TW), H, B);
+#define STB_VOL2_LAUNCH(K, CL)                                                                                      \
+    do {                                                                                                           \
+        cudaFuncSetAttribute(volume_cl2_kernel<K, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);    \
+        volume_cl2_kernel<K, CL><<<grid2, 256, smem2, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r,           \
+                                                                            (uint16_t*)vol, Cg, G, Cc, H, W, D,   \
+                                                                            Ct_pad, mask_left, f16);              \
+        STB_CHECK_LAUNCH();                                                                                        \
+        return STB_OK;                                                                                             \
+    } while (0)
+        if (smem2 <= 200 * 1024) {
+            if (cpg2 == 1) STB_VOL2_LAUNCH(1, true);
+            if (cpg2 == 4) STB_VOL2_LAUNCH(4, true);
+            if (cpg2 == 8) STB_VOL2_LAUNCH(8, true);
+            if (cpg2 == 12) STB_VOL2_LAUNCH(12, false);
+        }
+#undef STB_VOL2_LAUNCH
+    }
     STB_VOL_LAUNCH(0);
 #undef STB_VOL_LAUNCH
     STB_CHECK_LAUNCH();
