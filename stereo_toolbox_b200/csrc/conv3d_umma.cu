@@ -26,6 +26,8 @@
 // TMEM alloc/dealloc), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Pipelines:
 // plane ring (full/empty mbarriers, released by tcgen05.commit) and a 2-deep TMEM accumulator ring.
 #include <cuda_fp16.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -41,7 +43,16 @@ constexpr int UMMA_THREADS = 352;      // warp 0 TMA, warps 1-2 MMA issuers, war
 constexpr size_t SMEM_CAP = 227 * 1024;
 
 struct UTap { int8_t dz; uint8_t sub; int16_t rowoff; uint16_t widx; uint8_t nblk; uint8_t cls0; };
-struct UClass { uint16_t tap_begin, tap_end; int8_t od0, oh0, ow0, pad; };
+// (32-bit fields throughout: sub-word constant loads have no uniform-datapath form and drag the issue loop's
+//  counters into vector registers)
+struct UClass { uint32_t tap_begin, tap_end, grp_begin, grp_end; int32_t od0, oh0, ow0, pad; };
+// A run of taps of one class that read the same plane (z = dz - dzmin); rel = 1 when no later group of the class
+// reads that plane, i.e. the plane may be handed back after this group if no later STEP needs it either.
+struct UGroup { uint32_t tap_begin, tap_end, z, rel; };
+// Per-tap issue record, read by the issuer straight from the kernel-parameter constant bank into UNIFORM registers
+// (LDCU): A start offset inside a plane slot, B start offset inside the weight block (both >> 4), instruction
+// descriptor (N = nblk*Cn differs per tap) and accumulator column offset (cls0*Cn).
+struct UIss { uint32_t a16, b16, idesc, dcol; };
 
 struct UArgs {
     const void* residual;            // NDHWC 16-bit, Cout_total channels (nullable)
@@ -62,9 +73,34 @@ struct UArgs {
     int cblocks;                     // accumulator column blocks (of Cn) per M-tile: 1, 3 (kw-merge) or 8 (merged transposed conv)
     int nclass_h, nclass_w;          // class output extents per step in h/w (positions)
     uint32_t plane_bytes, chunk_bytes, wtile_bytes, w_bytes_total, tmem_cols;
+    uint32_t desc_hi;                // high word of every smem descriptor (SBO = 8 rows, version, swizzle mode)
+    uint32_t smem_base;              // shared-window address of the 1024-aligned dynamic smem base (queried once per kernel instance)
+    int debug;                       // timing experiments only (STB_UMMA_DEBUG): 1 = no TMA plane traffic, 2 = epilogue skips its work
+    int ntiles;                      // work items (b, depth chunk, h tile, w tile); CTAs are persistent and stride over them
+    int ngroups;
     UClass cls[MAX_UCLASS];
     UTap taps[MAX_UTAPS];
+    UGroup grp[MAX_UTAPS];
+    UIss iss[MAX_UTAPS];
 };
+
+// One work item: an (h-tile, w-tile) column of the volume over a chunk of depth steps.
+struct UTile { int b, s_lo, nst, jh0, jw0, p_first, nplanes, nouts; };
+__device__ __forceinline__ UTile decode_tile(const UArgs& a, int t) {
+    UTile u;
+    const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+    const int th_i = t % a.tiles_h; t /= a.tiles_h;
+    const int ch_i = t % a.nchunks;
+    u.b = t / a.nchunks;
+    u.s_lo = ch_i * a.dchunk;
+    const int s_hi = min(a.nsteps, u.s_lo + a.dchunk);
+    u.nst = s_hi - u.s_lo;
+    u.jh0 = th_i * a.TH; u.jw0 = tw_i * a.TW;          // class-position origin of this tile
+    u.p_first = u.s_lo * a.sd_in + a.dzmin;
+    u.nplanes = (s_hi - 1) * a.sd_in + a.dzmax - u.p_first + 1;
+    u.nouts = u.nst * a.nclass;                        // accumulator rounds
+    return u;
+}
 
 // Optional in-kernel timeline (debug aid, see tools/umma_trace.py): when armed through stb_conv3d_umma_set_trace,
 // CTA 0 records globaltimer-free clock64() stamps per accumulator round: [0] issuer-0 start of issue, [1] issuer-0
@@ -93,6 +129,43 @@ __device__ __forceinline__ void store16(uint16_t* p, float v, int f16) {
     else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16(v);
 }
 
+// ---- MMA issue, straight-line.  A branch controlled by a vector register between two UTCHMMAs costs about as much as
+// an MMA (probe mmarate3 variant 2: 99 vs 56 clk per N=96 MMA), and every counter of the issuer lives in a vector
+// register because it is live across mbarrier spin loops.  So the unit of issue is a chunk of NT taps whose
+// NT x NM x KS MMAs are fully unrolled; per-tap records come from the constant bank (LDCU -> uniform registers).
+template <int NT, int NM, int KS>
+__device__ __forceinline__ void issue_taps(const UArgs& a, int tq, uint32_t abase, uint32_t dbase) {
+    const uint32_t mt16 = (128u * (uint32_t)a.ROWB) >> 4, dhi = a.desc_hi, ncol = (uint32_t)(a.Cn * a.cblocks);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const UIss e = a.iss[tq + j];
+        const uint32_t acc = (e.dcol >> 31) ^ 1u;                  // bit 31: first tap of its class (overwrite)
+        const uint32_t dc = dbase + (e.dcol & 0xffffu);
+        const uint32_t a0 = abase + e.a16;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            const uint32_t dcol_t = dc + (uint32_t)m * ncol;
+            const uint32_t alo = a0 + (uint32_t)m * mt16;
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+                mma_f16_ss2(dcol_t, alo + 2u * k, e.b16 + 2u * k, dhi, e.idesc, k ? 1u : acc);
+        }
+    }
+}
+template <int NT, int KS>
+__device__ __forceinline__ void issue_dispatch_m(const UArgs& a, int tq, uint32_t abase, uint32_t dbase, int nM) {
+    if (nM == 2) issue_taps<NT, 2, KS>(a, tq, abase, dbase);
+    else if (nM == 1) issue_taps<NT, 1, KS>(a, tq, abase, dbase);
+    else if (nM == 4) issue_taps<NT, 4, KS>(a, tq, abase, dbase);
+    else issue_taps<NT, 3, KS>(a, tq, abase, dbase);
+}
+template <int NT>
+__device__ __forceinline__ void issue_dispatch(const UArgs& a, int tq, uint32_t abase, uint32_t dbase, int nM, int ks) {
+    if (ks == 2) issue_dispatch_m<NT, 2>(a, tq, abase, dbase, nM);
+    else if (ks == 4) issue_dispatch_m<NT, 4>(a, tq, abase, dbase, nM);
+    else issue_dispatch_m<NT, 1>(a, tq, abase, dbase, nM);
+}
+
 // ACT / F16 are compile-time so the epilogue stays a few hundred instructions: with a runtime activation switch
 // unrolled over 32 channels the kernel was 83 KB of SASS and the epilogue warps stalled on instruction fetch
 // (ncu: stall_no_inst on every epilogue line, profiles/ncu_umma_r01_*.txt).
@@ -109,64 +182,29 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     uint64_t* tmem_full = plane_empty + MAX_RING;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    uint32_t* tapA = tmem_holder + 2;            // [MAX_UTAPS] A byte offset of the tap inside a plane slot
-    uint32_t* tapB = tapA + MAX_UTAPS;           // [MAX_UTAPS] low word of the tap's B (weight tile) descriptor
-    uint32_t* tapZ = tapB + MAX_UTAPS;           // [MAX_UTAPS] plane index of the tap relative to dzmin
-    uint32_t* tapI = tapZ + MAX_UTAPS;           // [MAX_UTAPS] instruction descriptor (N = nblk*Cn differs per tap)
-    uint32_t* tapD = tapI + MAX_UTAPS;           // [MAX_UTAPS] accumulator column offset (cls0*Cn)
-    uint32_t* slotTab = tapD + MAX_UTAPS;        // [MAX_RING] encoded (addr >> 4) of every ring slot
-    uint4* issueTab = reinterpret_cast<uint4*>(smem + 2048);      // [R][ntaps] {A desc lo, B desc lo, idesc, D column offset}
-    uint8_t* sW = smem + 2048 + a.tab_bytes;
+    uint8_t* sW = smem + 2048;
     uint8_t* sP = sW + ((a.w_bytes_total + 1023) & ~1023u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (a.ntiles < 0) {                            // base-address query launch (host: smem_base_of)
+        if (threadIdx.x == 0) *reinterpret_cast<uint32_t*>(a.out) = smem_u32(smem);
+        return;
+    }
 
-    // ---- work item decode
-    int t = blockIdx.x;
-    const int tw_i = t % a.tiles_w; t /= a.tiles_w;
-    const int th_i = t % a.tiles_h; t /= a.tiles_h;
-    const int ch_i = t % a.nchunks;
-    const int b = t / a.nchunks;
-    const int s_lo = ch_i * a.dchunk, s_hi = min(a.nsteps, s_lo + a.dchunk);
-    const int jh0 = th_i * a.TH, jw0 = tw_i * a.TW;          // class-position origin of this tile
-    const int p_first = s_lo * a.sd_in + a.dzmin;
-    const int p_last = (s_hi - 1) * a.sd_in + a.dzmax;
-    const int nplanes = p_last - p_first + 1;
-    const int nouts = (s_hi - s_lo) * a.nclass;               // accumulator rounds
+    // ---- persistent CTA: work items blockIdx.x, blockIdx.x + gridDim.x, ... ; every role walks the same list and
+    // carries its pipeline state (ring slot / phase, accumulator round) across items, so the producer is already
+    // filling the ring for the next item while the tensor pipe and the epilogue finish the current one.
+    long long* const trace_buf = g_umma_trace;                // read ONCE: a global load per round sat on the issuer's critical path
+    const int trace_rounds = (trace_buf && blockIdx.x == 0) ? g_umma_trace_rounds : 0;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
-        const int n_iss = nouts >= 2 ? 2 : 1;                                    // MMA issuers take alternate rounds
         const int n_grp = a.nM * (a.cblocks == 8 ? 8 : 1) >= 2 ? 2 : 1;           // active epilogue groups
-        for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], n_iss); }
+        for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 2); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * n_grp); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_holder, a.tmem_cols);
-    // issue tables (see the MMA issuer): per tap the A offset inside a ring slot, the B descriptor low word and the
-    // plane index relative to dzmin; per ring slot its encoded base address
-    for (int tp = threadIdx.x; tp < a.ntaps_total; tp += UMMA_THREADS) {
-        tapA[tp] = ((uint32_t)a.taps[tp].sub * a.chunk_bytes + (uint32_t)a.taps[tp].rowoff * a.ROWB) >> 4;
-        tapB[tp] = (((smem_u32(sW) + (uint32_t)a.taps[tp].widx * a.wtile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
-        tapZ[tp] = (uint32_t)(a.taps[tp].dz - a.dzmin);
-        tapI[tp] = instr_desc_f16(128, (uint32_t)a.taps[tp].nblk * a.Cn, F16 ? 0 : 1);
-        tapD[tp] = (uint32_t)a.taps[tp].cls0 * a.Cn;
-    }
-    for (int i = threadIdx.x; i < a.R; i += UMMA_THREADS) slotTab[i] = (smem_u32(sP) + (uint32_t)i * a.plane_bytes) >> 4;
-    // one 16-byte record per (ring phase, tap): everything the issuer needs for the tap's first MMA of M-tile 0
-    for (int i = threadIdx.x; i < a.R * a.ntaps_total; i += UMMA_THREADS) {
-        const int ph = i / a.ntaps_total, tp = i - ph * a.ntaps_total;
-        int sl = ph + (int)(a.taps[tp].dz - a.dzmin);
-        sl -= (sl >= a.R) ? a.R : 0;
-        const uint32_t a16 = ((smem_u32(sP) + (uint32_t)sl * a.plane_bytes) >> 4) +
-                             (((uint32_t)a.taps[tp].sub * a.chunk_bytes + (uint32_t)a.taps[tp].rowoff * a.ROWB) >> 4);
-        uint4 e;
-        e.x = a16 & 0x3FFFu;                                                    // (masked + flagged at issue, after + M-tile offset)
-        e.y = (((smem_u32(sW) + (uint32_t)a.taps[tp].widx * a.wtile_bytes) >> 4) & 0x3FFFu) | (1u << 16);
-        e.z = instr_desc_f16(128, (uint32_t)a.taps[tp].nblk * a.Cn, F16 ? 0 : 1);
-        e.w = (uint32_t)a.taps[tp].cls0 * a.Cn;
-        issueTab[i] = e;
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -181,112 +219,117 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             for (int i = 0; i < a.nwtiles; ++i)
                 tma_load_2d(sW + (size_t)i * a.wtile_bytes, &tm_w, bar_w, 0,
                             (i * a.w_tile_stride + a.w_kc_off) * a.w_rows + a.cout_off);
-            const int ih0 = (jh0 + a.in_h_off) * a.in_stride, iw0 = (jw0 + a.in_w_off) * a.in_stride;
-            for (int n = 0; n < nplanes; ++n) {
-                const int slot = n % a.R;
-                mbar_wait(&plane_empty[slot], ((n / a.R) & 1) ^ 1);
-                mbar_arrive_expect_tx(&plane_full[slot], (uint32_t)a.nsub * a.chunk_bytes);
-                uint8_t* dst = sP + (size_t)slot * a.plane_bytes;
-                for (int sb = 0; sb < a.nsub; ++sb)       // sub-tile sb = (h parity, w parity) for stride 2
-                    tma_load_5d(dst + (size_t)sb * a.chunk_bytes, &tm_x, &plane_full[slot], a.cin_off,
-                                iw0 + (sb & 1), ih0 + (sb >> 1), p_first + n, b);
+            int slot = 0;
+            uint32_t eph = 1;                      // parity to wait for on plane_empty[slot] (fresh barrier: passes)
+            for (int tile = blockIdx.x; tile < a.ntiles && !(a.debug & 1); tile += gridDim.x) {
+                const UTile u = decode_tile(a, tile);
+                const int ih0 = (u.jh0 + a.in_h_off) * a.in_stride, iw0 = (u.jw0 + a.in_w_off) * a.in_stride;
+                for (int n = 0; n < u.nplanes; ++n) {
+                    mbar_wait_backoff(&plane_empty[slot], eph, 64);
+                    mbar_arrive_expect_tx(&plane_full[slot], (uint32_t)a.nsub * a.chunk_bytes);
+                    uint8_t* dst = sP + (size_t)slot * a.plane_bytes;
+                    for (int sb = 0; sb < a.nsub; ++sb)       // sub-tile sb = (h parity, w parity) for stride 2
+                        tma_load_5d(dst + (size_t)sb * a.chunk_bytes, &tm_x, &plane_full[slot], a.cin_off,
+                                    iw0 + (sb & 1), ih0 + (sb >> 1), u.p_first + n, u.b);
+                    if (++slot == a.R) { slot = 0; eph ^= 1; }
+                }
             }
         }
     } else if (warp <= 2) {
         // ================================ MMA issuers (2) ================================
-        // The two issuing warps take ALTERNATE accumulator rounds: while one is blocked on a full MMA queue, the
-        // other performs the waits / bookkeeping of the next round, so the tensor pipe sees back-to-back work
-        // (in-kernel timeline, profiles/umma_trace_r01.txt: with a single issuing sequence ~1.6K of every 4.2K
-        // clocks were barrier waits with the pipe idle).  The issue loop itself carries no division, no descriptor
-        // construction and no constant-bank traffic (smem tables above).
+        // One elected thread per warp; the two issuers take ALTERNATE accumulator rounds (issuer i owns TMEM buffer i).
+        // What bounds the tensor pipe here is not the UTCHMMA stream itself but the scalar bookkeeping between the
+        // streams (waits, ring arithmetic, record loads: ~600 clk per group of latency-bound single-thread code, while
+        // the MMA queue is only a few entries deep -- in-kernel timeline, profiles/umma_issue_r01.md): with two issuers
+        // one does its bookkeeping while the other's MMAs run.  The MMAs of a group are issued as straight-line blocks
+        // (issue_taps).  Taps are sorted by the plane they read, so an issuer consumes planes in increasing order: it
+        // waits for a plane right before its first tap and hands it back (tcgen05.commit -> plane_empty, count 2: a slot
+        // is recycled once BOTH issuers released it) right after its last use, i.e. when its next round no longer needs it.
         const int issuer = warp - 1;
-        const int n_iss = nouts >= 2 ? 2 : 1;
-        if (issuer < n_iss && elect_one()) {
-            const uint64_t desc_hi = (uint64_t)((((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29)) << 32;
+        if (elect_one()) {
+            const uint32_t plane16 = a.plane_bytes >> 4;
             const int ksteps = a.ROWB / 32;
-            const uint32_t mtile16 = (128u * a.ROWB) >> 4;
+            // The per-tap records hold ABSOLUTE encoded addresses (the host knows this kernel's dynamic-smem base, see
+            // launch_one): everything the issue blocks need is an LDCU away, never an R2UR.
+            if (smem_u32(smem) != a.smem_base) asm volatile("trap;");
             const int nM = a.nM, R = a.R, sd = a.sd_in, nclass = a.nclass;
             const uint32_t ncol = (uint32_t)(a.Cn * a.cblocks);
             mbar_wait(bar_w, 0);
-            int waited = 0;                       // planes [0, waited) are known to be resident (this issuer's view)
-            int released = 0;                     // planes [0, released) have been handed back by this issuer
-            int wslot = 0, wphase = 0;            // ring slot / phase of plane `waited`
-            int rslot = 0;                        // ring slot of plane `released`
-            for (int round = issuer; round < nouts; round += n_iss) {
-                const int si = round / nclass, c = round - si * nclass;      // step index within the chunk, class
-                const int s = s_lo + si;
-                const int need = (s * sd + a.dzmax) - p_first + 1;
-                const bool trace = g_umma_trace && blockIdx.x == 0 && round < g_umma_trace_rounds;
-                if (trace) g_umma_trace[round * 8 + 0] = clock64();
-                // Ring bookkeeping.  Both issuers observe (wait for) EVERY plane in order and hand back every plane
-                // below their current window, also planes only the other issuer read: a plane slot is recycled when both
-                // have released it.  An issuer releases a plane only after it has seen that plane land, so its arrival can
-                // never fall into the slot's previous phase (that race corrupted the ring once -- flaky deadlock/trap).
-                const int dead_now = (s * sd + a.dzmin) - p_first;
-                while (waited < need) {
-                    while (released < dead_now && released < waited) {
-                        mma_commit(&plane_empty[rslot]);
-                        ++released;
-                        if (++rslot == R) rslot = 0;
-                    }
-                    mbar_wait(&plane_full[wslot], wphase);
+            int waited = 0, released = 0;         // planes of the CURRENT item known resident / handed back (this issuer)
+            int wslot = 0, rslot = 0;             // ring slots of plane `waited` / `released`
+            uint32_t wphase = 0;
+            int base_slot = 0;                    // ring slot of the current item's plane 0
+            uint32_t ground = 0;                  // accumulator round counter over all items
+            const bool no_planes = a.debug & 1;
+            auto wait_upto = [&](int n) {
+                while (waited < n) {
+                    if (!no_planes) mbar_wait(&plane_full[wslot], wphase);
                     ++waited;
                     if (++wslot == R) { wslot = 0; wphase ^= 1; }
                 }
-                while (released < dead_now) {
+            };
+            auto release_upto = [&](int n) {      // each arrival fires when every MMA this thread issued so far has completed
+                while (released < n) {
+                    wait_upto(released + 1);      // never hand back a plane that has not landed (phase safety)
                     mma_commit(&plane_empty[rslot]);
                     ++released;
                     if (++rslot == R) rslot = 0;
                 }
-                if (trace) g_umma_trace[round * 8 + 1] = clock64();
-                const int buf = round & 1;
-                mbar_wait(&tmem_empty[buf], ((round >> 1) & 1) ^ 1);
-                tc_fence_after();
-                if (trace) g_umma_trace[round * 8 + 2] = clock64();
-                const int phase = ((s * sd + a.dzmin) - p_first) % R;         // one division per round
-                const uint4* tab = issueTab + phase * a.ntaps_total;
-                const int t0 = a.cls[c].tap_begin, t1 = a.cls[c].tap_end;
-                for (int m = 0; m < nM; ++m) {
-                    const uint32_t dcol = tmem_base + (uint32_t)(buf * nM + m) * ncol;
-                    const uint32_t moff = (uint32_t)m * mtile16;
-                    uint32_t acc = 0;
-#pragma unroll 3
-                    for (int tp = t0; tp < t1; ++tp) {
-                        const uint4 e = tab[tp];                                   // one LDS.128 per tap
-                        const uint32_t alo = ((e.x + moff) & 0x3FFFu) | (1u << 16);
-                        const uint32_t blo = e.y;
-                        const uint32_t idesc = e.z;
-                        const uint32_t dcol_t = dcol + e.w;
-                        mma_f16_ss(dcol_t, desc_hi | (uint64_t)alo, desc_hi | (uint64_t)blo, idesc, acc);
-                        if (ksteps >= 2)
-                            mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 2u), desc_hi | (uint64_t)(blo + 2u), idesc, 1u);
-                        if (ksteps == 4) {
-                            mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 4u), desc_hi | (uint64_t)(blo + 4u), idesc, 1u);
-                            mma_f16_ss(dcol_t, desc_hi | (uint64_t)(alo + 6u), desc_hi | (uint64_t)(blo + 6u), idesc, 1u);
+            };
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                const UTile u = decode_tile(a, tile);
+                int step_slot = base_slot;        // ring slot of plane (s*sd + dzmin) for the current step
+                for (int si = 0; si < u.nst; ++si) {
+                    const int dead_now = si * sd;                 // item-relative index of the step's first plane
+                    for (int c = 0; c < nclass; ++c, ++ground) {
+                        if ((int)(ground & 1u) != issuer) continue;
+                        const bool trace = (int)ground < trace_rounds;
+                        if (trace) trace_buf[ground * 8 + 0] = clock64();
+                        // first plane this issuer still needs in ITS next round (ground + 2)
+                        int nsi = si, nc = c + 2;
+                        while (nc >= nclass) { nc -= nclass; ++nsi; }
+                        const int next_dead = nsi >= u.nst ? u.nplanes : nsi * sd;
+                        release_upto(dead_now);                   // planes between my previous window and this one
+                        const int buf = issuer;
+                        if (!(a.debug & 4)) {
+                            mbar_wait(&tmem_empty[buf], ((ground >> 1) & 1) ^ 1);
+                            tc_fence_after();
                         }
-                        acc = 1;
+                        if (trace) trace_buf[ground * 8 + 1] = clock64();
+                        const uint32_t dbase = tmem_base + (uint32_t)(buf * nM) * ncol;
+                        const int gb = (int)a.cls[c].grp_begin, ge = (int)a.cls[c].grp_end;
+                        for (int g = gb; g < ge; ++g) {
+                            const UGroup gr = a.grp[g];
+                            const int z = (int)gr.z, g0 = (int)gr.tap_begin, g1 = (int)gr.tap_end;
+                            int sl = step_slot + z;
+                            sl -= sl >= R ? R : 0;
+                            const uint32_t abase = (uint32_t)sl * plane16;
+                            wait_upto(dead_now + z + 1);
+                            if (trace && g == gb) trace_buf[ground * 8 + 2] = clock64();
+                            int tq = g0;
+                            for (; tq + 3 <= g1; tq += 3) issue_dispatch<3>(a, tq, abase, dbase, nM, ksteps);
+                            for (; tq < g1; ++tq) issue_dispatch<1>(a, tq, abase, dbase, nM, ksteps);
+                            if (gr.rel && dead_now + z < next_dead) release_upto(dead_now + z + 1);
+                        }
+                        if (!(a.debug & 4)) mma_commit(&tmem_full[buf]);
+                        if (trace) trace_buf[ground * 8 + 3] = clock64();
                     }
+                    step_slot += sd;
+                    if (step_slot >= R) step_slot -= R;
                 }
-                mma_commit(&tmem_full[buf]);
-                if (trace) g_umma_trace[round * 8 + 3] = clock64();
-                // hand back every plane this issuer will not read again: its next round is `round + n_iss`
-                const int nxt = round + n_iss;
-                int dead_upto = nxt < nouts ? ((s_lo + nxt / nclass) * sd + a.dzmin) - p_first : nplanes;
-                if (dead_upto > waited) dead_upto = waited;          // only planes this issuer has seen land
-                while (released < dead_upto) {
-                    mma_commit(&plane_empty[rslot]);
-                    ++released;
-                    if (++rslot == R) rslot = 0;
-                }
+                release_upto(u.nplanes);          // everything of this item (also planes only the other issuer read)
+                base_slot = (base_slot + u.nplanes) % R;
+                waited -= u.nplanes;              // item-relative counters restart; wslot / rslot / wphase carry on
+                released -= u.nplanes;
             }
         }
-    } else {
+    } else if (warp >= 3) {
         // ================================ epilogue warps ================================
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
         const int egroup = (warp - 3) >> 2;         // epilogue group 0/1 drains M-tiles m = egroup, egroup+2, ...
         const int nblk_e = a.cblocks == 8 ? 8 : 1;     // merged transposed conv: all 8 parity classes in one round
         const int items = a.nM * nblk_e;               // (M-tile, class block) work items per round, dealt to 2 groups
-        const int my_rounds = egroup < (items >= 2 ? 2 : 1) ? nouts : 0;
+        const bool active = egroup < (items >= 2 ? 2 : 1);
         const size_t ostride_w = (size_t)a.Cout_total;
         constexpr int f16 = F16 ? 1 : 0;
         const bool full32 = (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
@@ -294,17 +337,23 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + a.cout_off + i) : 0.f;
         const int merge = a.merge, Cn = a.Cn, nM = a.nM;
-        for (int round = 0; round < my_rounds; ++round) {
-            const int buf = round & 1;
-            const int s = s_lo + round / a.nclass;
-            const UClass cl = a.cls[round % a.nclass];
-            mbar_wait(&tmem_full[buf], (round >> 1) & 1);
+        uint32_t ground = 0;                        // accumulator round counter over all items (same order as the issuer)
+        for (int tile = blockIdx.x; active && tile < a.ntiles && !(a.debug & 4); tile += gridDim.x) {
+          const UTile u = decode_tile(a, tile);
+          const int b = u.b, jh0 = u.jh0, jw0 = u.jw0;
+          int e_si = 0, e_c = 0;                      // (step, class) of the round, kept incrementally (no division)
+          for (int round = 0; round < u.nouts; ++round, ++ground) {
+            const int buf = ground & 1;
+            const int s = u.s_lo + e_si;
+            const UClass cl = a.cls[e_c];
+            if (++e_c == a.nclass) { e_c = 0; ++e_si; }
+            mbar_wait_warp(&tmem_full[buf], (ground >> 1) & 1);
             tc_fence_after();
-            const bool trace = g_umma_trace && blockIdx.x == 0 && warp == 3 && lane == 0 && round < g_umma_trace_rounds;
-            if (trace) g_umma_trace[round * 8 + 4] = clock64();
-            for (int item = egroup; item < items; item += 2) {
+            const bool trace = (int)ground < trace_rounds && warp == 3 && lane == 0;
+            if (trace) trace_buf[ground * 8 + 4] = clock64();
+            for (int item = egroup; item < items && !(a.debug & 2); item += 2) {
               {
-                const int m = item / nblk_e, blk = item - m * nblk_e;
+                const int m = nblk_e == 8 ? (item >> 3) : item, blk = nblk_e == 8 ? (item & 7) : 0;
                 const int cd = nblk_e == 8 ? (blk >> 2) : cl.od0, chh = nblk_e == 8 ? ((blk >> 1) & 1) : cl.oh0,
                           cww = nblk_e == 8 ? (blk & 1) : cl.ow0;
                 const int od = s * a.out_stride + cd;
@@ -316,24 +365,44 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const bool inb = valid && oh < a.Ho && ow < a.Wo;
                 const size_t vox = (((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow;
                 for (int c0 = 0; c0 < Cn; c0 += 32) {
-                    uint32_t v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) +
                                            (uint32_t)((buf * nM + m) * Cn * a.cblocks + (nblk_e == 8 ? blk * Cn : 0) + c0);
-                    __syncwarp();                      // tcgen05.ld is .sync.aligned: whole warp, converged
-                    tmem_ld_32x32(taddr, v);
-                    tmem_ld_wait();
+                    // All TMEM reads of the block are issued back to back and waited for once; after the LAST block of
+                    // the round the accumulator buffer is handed back to its issuer BEFORE the arithmetic and the
+                    // stores (the data is in registers): the buffer is busy ~0.3K instead of ~2.5K clocks per round,
+                    // which was what the issuers were waiting for (profiles/umma_issue_r01.md).
                     float f[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    // kw-merged accumulators: column block k holds P_k[q] = sum over (kd,kh,ci) for filter column
-                    // kw = k evaluated WITHOUT the w shift; out[q] = P_0[q] + P_1[q+1] + P_2[q+2], and q+k is
-                    // lane+k of the same warp (one warp = one padded tile row).
-                    for (int k = 1; k < merge; ++k) {
-                        __syncwarp();
-                        tmem_ld_32x32(taddr + (uint32_t)(k * Cn), v);
+                    __syncwarp();                      // tcgen05.ld is .sync.aligned: whole warp, converged
+                    if (merge == 3) {
+                        // kw-merged accumulators: column block k holds P_k[q] = sum over (kd,kh,ci) for filter column
+                        // kw = k evaluated WITHOUT the w shift; out[q] = P_0[q] + P_1[q+1] + P_2[q+2], and q+k is
+                        // lane+k of the same warp (one warp = one padded tile row).
+                        uint32_t v0[32], v1[32], v2[32];
+                        tmem_ld_32x32(taddr, v0);
+                        tmem_ld_32x32(taddr + (uint32_t)Cn, v1);
+                        tmem_ld_32x32(taddr + (uint32_t)(2 * Cn), v2);
                         tmem_ld_wait();
+                        if (item + 2 >= items && c0 + 32 >= Cn) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                        }
+                        const int ms = a.merge_step;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[i]), k * a.merge_step);
+                        for (int i = 0; i < 32; ++i)
+                            f[i] = __uint_as_float(v0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), ms) +
+                                   __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2 * ms);
+                    } else {
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr, v);
+                        tmem_ld_wait();
+                        if (item + 2 >= items && c0 + 32 >= Cn) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                     }
                     const size_t eoff = vox * ostride_w + a.cout_off + c0;
                     if (inb && full32) {
@@ -408,10 +477,13 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 }
               }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-            if (trace) g_umma_trace[round * 8 + 5] = clock64();
+            if (a.debug & 2) {                   // (timing experiment: no epilogue work, just hand the buffer back)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            }
+            if (trace) trace_buf[ground * 8 + 5] = clock64();
+          }
         }
     }
     tc_fence_before();
@@ -420,19 +492,44 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 }
 
 template <int ACT, bool F16>
-int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, const UArgs& a) {
+int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, UArgs& a) {
     static bool attr_set = false;
+    static uint32_t smem_base = 0;      // per kernel instance: address of the aligned dynamic-smem base in the shared window
     if (!attr_set) {
         cudaFuncSetAttribute(conv3d_umma_kernel<ACT, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
+        // one-off query launch (same kernel, same dynamic-smem attribute; the base does not depend on the size)
+        uint32_t* dev = nullptr;
+        if (cudaMalloc(&dev, sizeof(uint32_t)) != cudaSuccess) return STB_E_DRIVER;
+        UArgs q;
+        memset(&q, 0, sizeof(q));
+        q.ntiles = -1;
+        q.out = dev;
+        conv3d_umma_kernel<ACT, F16><<<1, UMMA_THREADS, 4096, st>>>(tx, tw, q);
+        cudaError_t e = cudaMemcpyAsync(&smem_base, dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(dev);
+        if (e != cudaSuccess || smem_base == 0) return STB_E_DRIVER;
         attr_set = true;
     }
+    // absolute encoded operand addresses: weights at base + 2048, plane ring after the (1 KB-rounded) weight block
+    const uint32_t w0 = smem_base + 2048;
+    const uint32_t p0 = w0 + ((a.w_bytes_total + 1023) & ~1023u);
+    a.smem_base = smem_base;
+    for (int t = 0; t < a.ntaps_total; ++t) {
+        a.iss[t].a16 = ((p0 + (uint32_t)a.taps[t].sub * a.chunk_bytes + (uint32_t)a.taps[t].rowoff * a.ROWB) >> 4) | (1u << 16);
+        a.iss[t].b16 = ((w0 + (uint32_t)a.taps[t].widx * a.wtile_bytes) >> 4) | (1u << 16);
+        a.iss[t].idesc = instr_desc_f16(128, (uint32_t)a.taps[t].nblk * a.Cn, F16 ? 0 : 1);
+        a.iss[t].dcol = (uint32_t)a.taps[t].cls0 * a.Cn;
+    }
+    for (int c = 0; c < a.nclass; ++c) a.iss[a.cls[c].tap_begin].dcol |= 1u << 31;      // overwrite instead of accumulate
+    a.desc_hi = (((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29);
     conv3d_umma_kernel<ACT, F16><<<grid, UMMA_THREADS, smem, st>>>(tx, tw, a);
     STB_CHECK_LAUNCH();
     return STB_OK;
 }
 
 int launch_umma(int act, int f16, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx,
-                const CUtensorMap& tw, const UArgs& a) {
+                const CUtensorMap& tw, UArgs& a) {
 #define STB_LAUNCH_ACT(A)                                                         \
     case A: return f16 ? launch_one<A, true>(grid, smem, st, tx, tw, a) : launch_one<A, false>(grid, smem, st, tx, tw, a);
     switch (act) {
@@ -489,7 +586,23 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.nsub = in_stride == 2 ? 4 : 1;
     a.sd_in = (flags & 16) ? 1 : in_stride;     // flags bit4: 2-D convolution, the depth axis (image index) is never strided
     int maxdh = 0, maxdw = 0, dzmin = 127, dzmax = -127;
-    for (int t = 0; t < ntaps; ++t) {
+    // Taps of a class are issued in the order of the plane they read (stable sort by dz): the issuer then consumes
+    // planes monotonically and can wait for / hand back each plane individually.
+    int order[MAX_UTAPS];
+    {
+        int n = 0;
+        for (int c = 0; c < nclass; ++c) {
+            if (tap_begin[c] < 0 || tap_end[c] > ntaps || tap_begin[c] >= tap_end[c] || tap_begin[c] != n) return STB_E_BADARG;
+            order[n++] = tap_begin[c];          // the caller's first tap initialises the accumulator blocks: keep it first
+            for (int z = -127; z <= 127; ++z)
+                for (int t = tap_begin[c] + 1; t < tap_end[c]; ++t)
+                    if (dz[t] == z) order[n++] = t;
+            if (n != tap_end[c]) return STB_E_BADARG;       // a dz outside [-127, 127]
+        }
+        if (n != ntaps) return STB_E_BADARG;
+    }
+    for (int i = 0; i < ntaps; ++i) {
+        const int t = order[i];
         if (dh[t] < 0 || dw[t] < 0 || dh[t] > 6 || dw[t] > 6 || widx[t] < 0 || widx[t] >= nwtiles || sub[t] < 0 ||
             sub[t] >= a.nsub)
             return STB_E_BADARG;
@@ -497,13 +610,31 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         maxdw = dw[t] > maxdw ? dw[t] : maxdw;
         dzmin = dz[t] < dzmin ? dz[t] : dzmin;
         dzmax = dz[t] > dzmax ? dz[t] : dzmax;
-        a.taps[t].dz = (int8_t)dz[t];
-        a.taps[t].sub = (uint8_t)sub[t];
-        a.taps[t].rowoff = (int16_t)(dh[t] * TWP + dw[t]);
-        a.taps[t].widx = (uint16_t)widx[t];
-        a.taps[t].nblk = (uint8_t)(nblk ? nblk[t] : a.merge);
-        a.taps[t].cls0 = (uint8_t)(cls0 ? cls0[t] : 0);
-        if (a.taps[t].nblk < 1 || a.taps[t].nblk + a.taps[t].cls0 > 8) return STB_E_BADARG;
+        a.taps[i].dz = (int8_t)dz[t];
+        a.taps[i].sub = (uint8_t)sub[t];
+        a.taps[i].rowoff = (int16_t)(dh[t] * TWP + dw[t]);
+        a.taps[i].widx = (uint16_t)widx[t];
+        a.taps[i].nblk = (uint8_t)(nblk ? nblk[t] : a.merge);
+        a.taps[i].cls0 = (uint8_t)(cls0 ? cls0[t] : 0);
+        if (a.taps[i].nblk < 1 || a.taps[i].nblk + a.taps[i].cls0 > 8) return STB_E_BADARG;
+    }
+    // plane groups: maximal runs of taps of one class with the same dz
+    a.ngroups = 0;
+    for (int c = 0; c < nclass; ++c) {
+        a.cls[c].grp_begin = (uint32_t)a.ngroups;
+        for (int t = tap_begin[c]; t < tap_end[c];) {
+            int e = t;
+            while (e < tap_end[c] && a.taps[e].dz == a.taps[t].dz) ++e;
+            a.grp[a.ngroups].tap_begin = (uint32_t)t;
+            a.grp[a.ngroups].tap_end = (uint32_t)e;
+            a.grp[a.ngroups].z = (uint32_t)(a.taps[t].dz - dzmin);
+            a.grp[a.ngroups].rel = 1;
+            for (int l = e; l < tap_end[c]; ++l)
+                if (a.taps[l].dz == a.taps[t].dz) a.grp[a.ngroups].rel = 0;
+            ++a.ngroups;
+            t = e;
+        }
+        a.cls[c].grp_end = (uint32_t)a.ngroups;
     }
     // accumulator column blocks per M-tile: 8 when taps address parity-class blocks (merged transposed conv),
     // 3 for kw-merge, else 1.  The first tap of every class must cover all blocks (it zero-initialises them).
@@ -513,9 +644,9 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     if (a.cblocks == 8 && (nclass != 1 || out_stride != 2 || in_stride != 1)) return STB_E_UNSUPPORTED;
     a.ntaps_total = ntaps;
     for (int c = 0; c < nclass; ++c) {
-        a.cls[c].tap_begin = (uint16_t)tap_begin[c];
-        a.cls[c].tap_end = (uint16_t)tap_end[c];
-        a.cls[c].od0 = (int8_t)od0[c]; a.cls[c].oh0 = (int8_t)oh0[c]; a.cls[c].ow0 = (int8_t)ow0[c];
+        a.cls[c].tap_begin = (uint32_t)tap_begin[c];
+        a.cls[c].tap_end = (uint32_t)tap_end[c];
+        a.cls[c].od0 = od0[c]; a.cls[c].oh0 = oh0[c]; a.cls[c].ow0 = ow0[c];
     }
     a.nclass = nclass;
     a.TW = TWP - (a.merge == 3 ? 2 * a.merge_step : maxdw);
@@ -538,8 +669,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         const size_t wbytes = (((size_t)nwtiles * cn * a.ROWB) + 1023) & ~(size_t)1023;
         const size_t plane = (size_t)a.nsub * (th + maxdh) * TWP * a.ROWB;
         if (3072 + wbytes + 2048 >= SMEM_CAP) return 0;
-        // the per-(phase, tap) issue table grows with the ring: r*(plane + 16*ntaps) + 1 KB rounding slack
-        int r = (int)((SMEM_CAP - 3072 - wbytes - 2048) / (plane + (size_t)16 * ntaps));
+        int r = (int)((SMEM_CAP - 3072 - wbytes - 1024) / plane);
         if (r > MAX_RING) r = MAX_RING;
         return r >= window + 1 ? r : 0;
     };
@@ -561,7 +691,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     }
     while (TH > 4 && TH - 4 >= nclass_h) TH -= 4;      // do not stage rows that do not exist
     a.R = R;
-    a.tab_bytes = (uint32_t)((((size_t)R * ntaps * 16) + 1023) & ~(size_t)1023);
+    a.tab_bytes = 0;
     a.TH = TH; a.nM = TH * TWP / 128;
     const int box_h = TH + maxdh;
     a.chunk_bytes = (uint32_t)(box_h * TWP * a.ROWB);
@@ -609,6 +739,17 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.nwtiles = nwtiles;
     const long long ncta = (long long)B * a.nchunks * a.tiles_h * a.tiles_w;
     if (ncta > 2147483647LL) return STB_E_BADARG;
+    a.ntiles = (int)ncta;
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+    }
+    const unsigned grid = (unsigned)(ncta < sm_count ? ncta : sm_count);     // persistent: one CTA per SM
+    static const bool verbose = getenv("STB_UMMA_VERBOSE") != nullptr;
+    static const int debug = getenv("STB_UMMA_DEBUG") ? atoi(getenv("STB_UMMA_DEBUG")) : 0;
+    a.debug = debug;
     for (int kp = 0; kp < nk; ++kp) {
         const bool last = kp == nk - 1;
         a.cin_off = kp * KC;
@@ -633,7 +774,12 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             if (!umma_host::make_tmap(&tm_w, cudt, 2, const_cast<void*>(wt), dims, str, box, cusw)) return STB_E_DRIVER;
             size_t smem = 3072 + a.tab_bytes + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
             if (smem > SMEM_CAP) return STB_E_SMEM;
-            const int rc = launch_umma(a.act, f16, (unsigned)ncta, smem, (cudaStream_t)stream, tm_x, tm_w, a);
+            if (verbose)
+                fprintf(stderr, "[stb_conv3d_umma] Cin=%d KC=%d kpass=%d/%d Cn=%d/%d taps=%d groups=%d cblocks=%d in_stride=%d out_stride=%d "
+                        "TH=%d TW=%d nM=%d R=%d window=%d plane=%uB weights=%uB smem=%zuB dchunk=%d items=%d grid=%u\n",
+                        Cin, KC, kp, nk, cn, Cpad, ntaps, a.ngroups, a.cblocks, in_stride, out_stride, a.TH, a.TW, a.nM, a.R,
+                        window, a.plane_bytes, a.w_bytes_total, smem, a.dchunk, a.ntiles, grid);
+            const int rc = launch_umma(a.act, f16, grid, smem, (cudaStream_t)stream, tm_x, tm_w, a);
             if (rc != STB_OK) return rc;
         }
     }

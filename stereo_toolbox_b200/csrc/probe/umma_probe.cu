@@ -165,6 +165,146 @@ mmarate_kernel(int N, uint32_t layout, int rowb, int shift, int iters, int per_i
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// mmarate2: as mmarate with more knobs -- operand format (0 fp16 / 1 bf16), smem filled with zeros or random
+// normal-range values (data-dependent power throttling), `nacc` accumulators used round-robin (dependent chains),
+// and `ldwarps` extra warps that keep reading TMEM with tcgen05.ld like the conv epilogue does.
+__global__ void __launch_bounds__(256)
+mmarate2_kernel(int N, uint32_t layout, int rowb, int fmt, int fill, int nacc, int ldwarps, int iters, int per_iter,
+                long long* cycles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t holder;
+    __shared__ volatile int done;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); done = 0; fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&holder, 512);
+    uint16_t* s16 = reinterpret_cast<uint16_t*>(smem);
+    for (int i = threadIdx.x; i < 130 * 1024 / 2; i += blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        const float v = fill ? ((float)(h & 0xffff) / 32768.f - 1.f) : 0.f;
+        if (fmt) { __nv_bfloat16 b = __float2bfloat16(v); s16[i] = *reinterpret_cast<uint16_t*>(&b); }
+        else { __half b = __float2half(v); s16[i] = *reinterpret_cast<uint16_t*>(&b); }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = holder;
+    if (warp == 0 && elect_one()) {
+        const uint32_t idesc = instr_desc_f16(128, N, fmt);
+        const uint64_t hi = (uint64_t)((((8u * rowb) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29)) << 32;
+        const uint32_t a0 = ((smem_u32(smem)) >> 4 & 0x3FFFu) | (1u << 16);
+        const uint32_t b0 = ((smem_u32(smem) + 65536) >> 4 & 0x3FFFu) | (1u << 16);
+        long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            for (int j = 0; j < per_iter; ++j) {
+                const uint32_t off = (uint32_t)((j & 15) * (rowb * 8 / 16));
+                const uint32_t d = tmem + (uint32_t)((j & (nacc - 1)) * N);
+                mma_f16_ss(d, hi | (uint64_t)(a0 + off), hi | (uint64_t)(b0 + (j & 1) * 2), idesc, 1u);
+            }
+        }
+        mma_commit(&bar[0]);
+        mbar_wait(&bar[0], 0);
+        long long t1 = clock64();
+        if (blockIdx.x == 0) cycles[0] = t1 - t0;
+        done = 1;
+    } else if (warp >= 4 && warp < 4 + ldwarps) {
+        uint32_t v[32];
+        uint32_t acc = 0;
+        while (!done) {
+            __syncwarp();
+            tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16), v);
+            tmem_ld_wait();
+            acc += v[0];
+        }
+        if (acc == 0x12345678u) cycles[1] = acc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// mmarate3: the exact MMA address sequence of one accumulator round of the 32->32 k3 kw-merged layer (TH=8: 2 M-tiles,
+// 3 planes x 3 kh taps x 2 K-steps, N=96, SW64): variant 0 = addresses as compile-time immediates (fully unrolled),
+// variant 1 = per-tap records read from the kernel-parameter constant bank like conv3d_umma does.
+struct Iss3 { uint32_t a16, b16, idesc, dcol; };
+struct Tab3 { Iss3 e[9]; };
+template <int VARIANT>
+__global__ void __launch_bounds__(352)
+mmarate3_kernel(const __grid_constant__ Tab3 tab, int iters, long long* cycles, int commit_groups, int iwarp, int nz, int nm) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t holder;
+    __shared__ volatile int vbound;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); vbound = 3; fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&holder, 512);
+    uint16_t* s16 = reinterpret_cast<uint16_t*>(smem);
+    for (int i = threadIdx.x; i < 200 * 1024 / 2; i += blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        __half b = __float2half((float)(h & 0xffff) / 32768.f - 1.f);
+        s16[i] = *reinterpret_cast<uint16_t*>(&b);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = holder;
+    if (warp == iwarp && elect_one()) {
+        const uint32_t idesc = instr_desc_f16(128, 96, 0);
+        const uint32_t hi32 = (((8u * 64) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)SW_64B << 29);
+        const uint64_t hi = (uint64_t)hi32 << 32;
+        const uint32_t sW16 = (smem_u32(smem) >> 4) | (1u << 16);                 // weights: 9 tiles x 6144 B
+        const uint32_t sP16 = ((smem_u32(smem) + 56 * 1024) >> 4) | (1u << 16);   // 3 plane slots x 20480 B
+        long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            if (VARIANT == 0) {
+#pragma unroll
+                for (int z = 0; z < 3; ++z)
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const uint32_t alo = sP16 + (uint32_t)((z * 20480 + m * 8192 + kh * 2048) >> 4) + 2 * k;
+                                const uint32_t blo = sW16 + (uint32_t)(((z * 3 + kh) * 6144) >> 4) + 2 * k;
+                                mma_f16_ss(tmem + m * 96, hi | alo, hi | blo, idesc, (z | kh | k) ? 1u : 0u);
+                                if (m == 1 && kh == 2 && k == 1 && z < commit_groups) mma_commit(&bar[1]);
+                            }
+            } else {
+                for (int z = 0; z < nz; ++z) {
+                    const uint32_t abase = sP16 + (uint32_t)z * (20480 >> 4);
+                    for (int m = 0; m < nm; ++m) {
+                        const uint32_t am = abase + (uint32_t)m * (8192 >> 4);
+                        const uint32_t dcol = tmem + m * 96;
+#pragma unroll 1
+                        const int tend = z * 3 + (VARIANT == 2 ? vbound : 3);     // variant 2: bound in a VECTOR register
+                        for (int tp = z * 3; tp < tend; ++tp) {
+                            const Iss3 e = tab.e[tp];
+                            const uint32_t alo = am + e.a16, blo = sW16 + e.b16;
+                            mma_f16_ss2(dcol + e.dcol, alo, blo, hi32, e.idesc, tp != 0);
+                            mma_f16_ss2(dcol + e.dcol, alo + 2u, blo + 2u, hi32, e.idesc, 1u);
+                        }
+                    }
+                }
+            }
+        }
+        mma_commit(&bar[0]);
+        mbar_wait(&bar[0], 0);
+        long long t1 = clock64();
+        if (blockIdx.x == 0) cycles[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 int main(int argc, char** argv) {
@@ -227,6 +367,68 @@ int main(int argc, char** argv) {
         const double per = (double)hc[0] / (iters * per_iter);
         printf("mmarate N=%d rowb=%d shift=%d issuers=%d : %.1f clk per MMA per issuer (%.1f clk per MMA overall), ideal math %.1f\n",
                N, rowb, shift, nissue, per, per / nissue, 128.0 * N / 256.0);
+        return 0;
+    }
+    if (argc >= 2 && !strcmp(argv[1], "mmarate2")) {
+        // usage: mmarate2 <N> <rowb:64|128> <fmt:0 fp16|1 bf16> <fill:0|1> <nacc> <ldwarps>
+        const int N = atoi(argv[2]), rowb = atoi(argv[3]), fmt = atoi(argv[4]), fill = atoi(argv[5]), nacc = atoi(argv[6]),
+                  ldw = atoi(argv[7]);
+        const uint32_t layout = rowb == 128 ? SW_128B : SW_64B;
+        long long* dc;
+        CK(cudaMalloc(&dc, 16));
+        CK(cudaMemset(dc, 0, 16));
+        const int iters = 200, per_iter = 36;
+        size_t smem = 140 * 1024;
+        CK(cudaFuncSetAttribute(mmarate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int rep = 0; rep < 2; ++rep) {
+            mmarate2_kernel<<<148, 256, smem>>>(N, layout, rowb, fmt, fill, nacc, ldw, iters, per_iter, dc);
+            CK(cudaDeviceSynchronize());
+        }
+        long long hc[2];
+        CK(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
+        printf("mmarate2 N=%d rowb=%d fmt=%s fill=%s nacc=%d ldwarps=%d : %.1f clk per MMA (ideal math %.1f, smem operand bytes/128 = %.1f)\n",
+               N, rowb, fmt ? "bf16" : "fp16", fill ? "random" : "zeros", nacc, ldw, (double)hc[0] / (iters * per_iter),
+               128.0 * N / 256.0, (128.0 * 32 + N * 32.0) / 128.0);
+        return 0;
+    }
+    if (argc >= 2 && !strcmp(argv[1], "mmarate3")) {
+        const int variant = atoi(argv[2]);
+        long long* dc;
+        CK(cudaMalloc(&dc, 16));
+        CK(cudaMemset(dc, 0, 16));
+        Tab3 tab;
+        for (int z = 0; z < 3; ++z)
+            for (int kh = 0; kh < 3; ++kh) {
+                Iss3& e = tab.e[z * 3 + kh];
+                e.a16 = (kh * 2048) >> 4;
+                e.b16 = ((z * 3 + kh) * 6144) >> 4;
+                e.idesc = instr_desc_f16(128, 96, 0);
+                e.dcol = 0;
+            }
+        const int iters = argc > 7 ? atoi(argv[7]) : 400;
+        const int nthr = argc > 4 ? atoi(argv[4]) : 128, iwarp = argc > 5 ? atoi(argv[5]) : 0;
+        size_t smem = (argc > 6 ? atoi(argv[6]) : 210) * 1024;
+        CK(cudaFuncSetAttribute(mmarate3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(mmarate3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(mmarate3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaEvent_t ev0, ev1;
+        cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(ev0);
+            if (variant == 0) mmarate3_kernel<0><<<148, nthr, smem>>>(tab, iters, dc, argc > 3 ? atoi(argv[3]) : 0, iwarp, 3, 2);
+            else if (variant == 1) mmarate3_kernel<1><<<148, nthr, smem>>>(tab, iters, dc, 0, iwarp, 3, 2);
+            else mmarate3_kernel<2><<<148, nthr, smem>>>(tab, iters, dc, 0, iwarp, 3, 2);
+            cudaEventRecord(ev1);
+            CK(cudaDeviceSynchronize());
+        }
+        float wall_ms = 0.f;
+        cudaEventElapsedTime(&wall_ms, ev0, ev1);
+        printf("  wall %.1f us for %d MMAs per SM = %.2f ns per MMA (x1.965 GHz = %.1f clk)\n", wall_ms * 1e3, iters * 36,
+               wall_ms * 1e6 / (iters * 36.0), wall_ms * 1e6 / (iters * 36.0) * 1.965);
+        long long hc[2];
+        CK(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
+        printf("mmarate3 threads=%d issuer_warp=%d smem=%zuKB variant=%d commits/36=%d (%s): %.1f clk per MMA (N=96 K=16; smem-operand bound 56)\n", nthr, iwarp, smem / 1024, variant, argc > 3 ? atoi(argv[3]) : 0,
+               variant ? "constant-bank records" : "immediates", (double)hc[0] / (iters * 36.0));
         return 0;
     }
     if (argc >= 2 && !strcmp(argv[1], "tmabw")) {

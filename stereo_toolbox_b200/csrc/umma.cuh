@@ -45,6 +45,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("trap;");
 }
 
+// Waiting without hammering shared memory: a spinning mbarrier.try_wait from every lane of several warps competes with
+// the tensor core's operand fetch for the shared-memory pipeline (measured on B200: 8 polling epilogue warps halved the
+// tcgen05.mma rate of the conv kernel, 120 vs 56 clk per N=96 MMA).  One lane polls with a short sleep between
+// attempts, the rest of the warp parks on __syncwarp.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    for (uint32_t i = 1;; ++i) {
+        __nanosleep(ns);
+        if (mbar_try_wait(bar, parity)) return;
+        if ((i & 255u) == 0 && clock64() - t0 > 6000000000LL) break;
+    }
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, uint32_t ns = 32) {
+    if ((threadIdx.x & 31) == 0) mbar_wait_backoff(bar, parity, ns);
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -108,6 +127,47 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, descriptors passed as (low word, shared high word) pairs so the 64-bit values are assembled in PTX.
+__device__ __forceinline__ void mma_f16_ss2(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(alo), "r"(blo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Predicated form (always accumulates): the MMA is skipped when `enable` is 0 -- a uniform predicate on the
+// instruction instead of a branch around it.
+__device__ __forceinline__ void mma_f16_ss2p(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t desc_hi, uint32_t idesc,
+                                             bool enable) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n\t}" ::"r"(tmem_d),
+        "r"(alo), "r"(blo), "r"(desc_hi), "r"(idesc), "r"((uint32_t)enable)
+        : "memory");
+}
+// Fully predicated form: issued only when `enable` is set; accumulates when `accumulate` is set.
+__device__ __forceinline__ void mma_f16_ss3(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t accumulate, bool enable) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(alo), "r"(blo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"((uint32_t)enable)
+        : "memory");
+}
+// A value held by ONE active thread (mask = that thread's lane bit), returned through REDUX: ptxas keeps the result in
+// a uniform register, which is what the UTCHMMA operands and uniform branches want.
+__device__ __forceinline__ uint32_t uni(uint32_t self_mask, uint32_t v) { return __reduce_or_sync(self_mask, v); }
 // mbarrier arrives once all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
