@@ -197,6 +197,19 @@ int stb_block_attention(const void* qkv, const float* qkv_bias, void* out, int d
                         int D, int H0, int W0, int b0, int b1, int b2, const long long* qkv_strides,
                         const long long* out_strides, void* stream);
 
+/* ---- IGEV / CFNet elementwise pieces ---------------------------------------------------------------
+ * FeatureAtt gate, IGEVStereo/submodule.py:228-241 (used at igev_stereo.py:71-88,208): out = x * sigmoid(gate)
+ * with the 2-D gate logits [B,C,H,W] (fp32) broadcast over D.  x/out [B,C,D,H,W] fp32, or channels-last 16-bit
+ * [B,D,H,W,Cpad] (channels >= C are padding and pass through). out may alias x. */
+int stb_feature_gate_f32(const float* x, const float* gate, float* out, int B, int C, int D, int H, int W, void* stream);
+int stb_feature_gate_cl16(const void* x, const float* gate, void* out, int f16, int B, int C, int Cpad, int D, int H,
+                          int W, void* stream);
+
+/* disparity_variance, CFNet/submodule.py:127-133: prob [B,D,plane], disp [B,plane] -> var [B,plane]
+ * var = sum_d prob[d] * (d - disp)^2. */
+int stb_disparity_variance_f32(const float* prob, const float* disp, float* var, int B, int D, long long plane,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,8 @@ proves the CUDA-backed models keep the reference's state-dict layout (SURVEY.md 
   gwcnet_forward : GwcNet/gwcnet.py:171-224 (+ feature_extraction :12-65, hourglass :68-105)
   psmnet_forward : PSMNet/stackhourglass.py:103-161 (+ feature_extraction PSMNet/submodule.py:57-132)
   acvnet_forward : ACVNet/acv.py:159-250 eval branch (+ hourglass-with-attention :54-93, attention_block submodule.py:366-430)
+  igev_cost_volume : IGEVStereo/igev_stereo.py:205-213 (+ hourglass :23-90, BasicConv / FeatureAtt submodule.py:9-37,228-241)
+  mish_hourglass / mish_hourglassup : CFNet/cfnet.py:178-271, PCWNet/pcwnet.py:133-251
 """
 from __future__ import annotations
 
@@ -219,3 +221,80 @@ def acvnet_forward(sd: SD, left, right, maxdisp: int, attn_weights_only: bool = 
     if return_aux:
         return disp, dict(cost2=cost2, att=att, patch_volume=pv, features=(gl, gr))
     return disp
+
+
+# ------------------------------------------------------------------ IGEV cost-volume stage (hot path)
+def igev_basic3d(sd: SD, p: str, x, stride=1, pad=1, act="leaky", transposed=False, bn=True):
+    """BasicConv(is_3d=True): IGEVStereo/submodule.py:9-37 (conv -> bn -> LeakyReLU(0.01))."""
+    return R.conv3d_bn_act(x, sd[f"{p}.conv.weight"], _bn(sd, f"{p}.bn") if bn else None, stride, pad, act, None,
+                           transposed=transposed)
+
+
+def igev_feature_att(sd: SD, p: str, cv, feat):
+    """FeatureAtt.forward: IGEVStereo/submodule.py:236-241."""
+    y = F.conv2d(feat, sd[f"{p}.feat_att.0.conv.weight"])
+    b = _bn(sd, f"{p}.feat_att.0.bn")
+    y = F.batch_norm(y, b["running_mean"], b["running_var"], b["weight"], b["bias"], False, 0.0, 1e-5)
+    y = F.leaky_relu(y, 0.01)
+    y = F.conv2d(y, sd[f"{p}.feat_att.1.weight"], sd[f"{p}.feat_att.1.bias"])
+    return torch.sigmoid(y).unsqueeze(2) * cv
+
+
+def igev_hourglass(sd: SD, p: str, x, features):
+    """hourglass.forward: IGEVStereo/igev_stereo.py:66-90."""
+    c1 = igev_basic3d(sd, f"{p}.conv1.1", igev_basic3d(sd, f"{p}.conv1.0", x, 2))
+    c1 = igev_feature_att(sd, f"{p}.feature_att_8", c1, features[1])
+    c2 = igev_basic3d(sd, f"{p}.conv2.1", igev_basic3d(sd, f"{p}.conv2.0", c1, 2))
+    c2 = igev_feature_att(sd, f"{p}.feature_att_16", c2, features[2])
+    c3 = igev_basic3d(sd, f"{p}.conv3.1", igev_basic3d(sd, f"{p}.conv3.0", c2, 2))
+    c3 = igev_feature_att(sd, f"{p}.feature_att_32", c3, features[3])
+    c3u = igev_basic3d(sd, f"{p}.conv3_up", c3, 2, 1, transposed=True)
+    c2 = torch.cat((c3u, c2), 1)
+    c2 = igev_basic3d(sd, f"{p}.agg_0.0", c2, 1, 0)
+    c2 = igev_basic3d(sd, f"{p}.agg_0.2", igev_basic3d(sd, f"{p}.agg_0.1", c2))
+    c2 = igev_feature_att(sd, f"{p}.feature_att_up_16", c2, features[2])
+    c2u = igev_basic3d(sd, f"{p}.conv2_up", c2, 2, 1, transposed=True)
+    c1 = torch.cat((c2u, c1), 1)
+    c1 = igev_basic3d(sd, f"{p}.agg_1.0", c1, 1, 0)
+    c1 = igev_basic3d(sd, f"{p}.agg_1.2", igev_basic3d(sd, f"{p}.agg_1.1", c1))
+    c1 = igev_feature_att(sd, f"{p}.feature_att_up_8", c1, features[1])
+    return igev_basic3d(sd, f"{p}.conv1_up", c1, 2, 1, act="none", transposed=True, bn=False)
+
+
+def igev_cost_volume(sd: SD, match_left, match_right, features_left, max_disp: int):
+    """IGEVStereo.forward lines 205-213: gwc volume (8 groups) -> corr_stem -> corr_feature_att -> cost_agg ->
+    classifier -> softmax regression at 1/4 resolution (keepdim).  Returns (init_disp, geo_encoding_volume)."""
+    vol = R.build_gwc_volume(match_left, match_right, max_disp // 4, 8)
+    x = igev_basic3d(sd, "corr_stem", vol)
+    x = igev_feature_att(sd, "corr_feature_att", x, features_left[0])
+    geo = igev_hourglass(sd, "cost_agg", x, features_left)
+    cost = F.conv3d(geo, sd["classifier.weight"], padding=1)
+    return R.softargmin(cost[:, 0], keepdim=True), geo
+
+
+# ------------------------------------------------------------------ CFNet / PCWNet aggregation blocks (hot path)
+def mish_hourglass(sd: SD, p: str, x):
+    """hourglass.forward: CFNet/cfnet.py:257-271 == PCWNet/pcwnet.py:237-251."""
+    c1 = cbn3(sd, f"{p}.conv1.0", x, 2, 1, "mish")
+    c2 = cbn3(sd, f"{p}.conv2.0", c1, 1, 1, "mish")
+    c3 = cbn3(sd, f"{p}.conv3.0", c2, 2, 1, "mish")
+    c4 = cbn3(sd, f"{p}.conv4.0", c3, 1, 1, "mish")
+    c5 = dbn3(sd, f"{p}.conv5", c4, "mish", cbn3(sd, f"{p}.redir2", c2, 1, 0))
+    return dbn3(sd, f"{p}.conv6", c5, "mish", cbn3(sd, f"{p}.redir1", x, 1, 0))
+
+
+def mish_hourglassup(sd: SD, p: str, x, feature4, feature5, feature6=None):
+    """hourglassup.forward: CFNet/cfnet.py:213-229 (two levels) / PCWNet/pcwnet.py:183-209 (three levels)."""
+    c1 = torch.cat((F.conv3d(x, sd[f"{p}.conv1.weight"], stride=2, padding=1), feature4), 1)
+    c1 = cbn3(sd, f"{p}.combine1.0", c1, 1, 1, "mish")
+    c2 = cbn3(sd, f"{p}.conv2.0", c1, 1, 1, "mish")
+    c3 = torch.cat((F.conv3d(c2, sd[f"{p}.conv3.weight"], stride=2, padding=1), feature5), 1)
+    c3 = cbn3(sd, f"{p}.combine2.0", c3, 1, 1, "mish")
+    c4 = cbn3(sd, f"{p}.conv4.0", c3, 1, 1, "mish")
+    if feature6 is not None:
+        c5 = torch.cat((F.conv3d(c4, sd[f"{p}.conv5.weight"], stride=2, padding=1), feature6), 1)
+        c5 = cbn3(sd, f"{p}.combine3.0", c5, 1, 1, "mish")
+        c6 = cbn3(sd, f"{p}.conv6.0", c5, 1, 1, "mish")
+        c4 = dbn3(sd, f"{p}.conv7", c6, "mish", cbn3(sd, f"{p}.redir3", c4, 1, 0))
+    c8 = dbn3(sd, f"{p}.conv8", c4, "mish", cbn3(sd, f"{p}.redir2", c2, 1, 0))
+    return dbn3(sd, f"{p}.conv9", c8, "mish", cbn3(sd, f"{p}.redir1", x, 1, 0))

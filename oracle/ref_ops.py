@@ -117,6 +117,13 @@ def upsample_softargmin(cost: torch.Tensor, maxdisp: int, out_h: int, out_w: int
     return disparity_regression(prob, maxdisp, keepdim)
 
 
+def disparity_variance(prob: torch.Tensor, maxdisp: int, disparity: torch.Tensor) -> torch.Tensor:
+    """CFNet/submodule.py:127-133: sum_d prob[:, d] * (d - disparity)^2, keepdim.  prob [B,D,H,W], disparity [B,1,H,W]."""
+    assert len(prob.shape) == 4
+    d = torch.arange(0, maxdisp, dtype=prob.dtype).view(1, maxdisp, 1, 1)
+    return torch.sum(prob * (d - disparity) ** 2, 1, keepdim=True)
+
+
 def softargmin(cost: torch.Tensor, keepdim: bool = True) -> torch.Tensor:
     """IGEVStereo/igev_stereo.py:212-213 -- softmax over D and regression at the volume's own
     resolution (no upsampling). ``cost`` [B,D,H,W]."""

@@ -46,6 +46,9 @@ SIGNATURES = {
     "stb_geo_permute_f32": [_P, _P, _I, _I, _I, _I, _I, _P],
     "stb_patch_dw_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "stb_block_attention": [_P, _P, _P] + [_I] * 10 + [POINTER(c_longlong), POINTER(c_longlong), _P],
+    "stb_feature_gate_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "stb_feature_gate_cl16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "stb_disparity_variance_f32": [_P, _P, _P, _I, _I, _LL, _P],
 }
 
 

@@ -141,6 +141,18 @@ class Fp32Backend:
                                4.0 * (qkv.numel() + qkv.numel() // 3)):
             return ops.block_attention(qkv, bias, heads, block, channels_last=False)
 
+    # --- IGEV / CFNet helpers
+    def gate(self, x, gate_logits):
+        """FeatureAtt gate: x * sigmoid(logits)[:, :, None]."""
+        return ops.feature_gate(x, gate_logits, channels_last=False)
+
+    def cat(self, xs):
+        """channel concatenation (torch.cat(dim=1) of the reference)."""
+        return torch.cat(list(xs), dim=1)
+
+    def to_ncdhw(self, x, channels=None):
+        return x
+
     def head(self, cost, maxdisp, H, W, align_corners=False):
         B = cost.shape[0]
         with self.prof.bracket("upsample_softargmin", 0.0, 4.0 * (cost.numel() + B * H * W)):

@@ -313,6 +313,24 @@ class UmmaBackend:
                                2.0 * (qkv.numel() + qkv.numel() // 3)):
             return ops.block_attention(qkv, bias, heads, block, channels_last=True)
 
+    # ---------------------------------------------------------------- IGEV / CFNet helpers
+    def gate(self, x, gate_logits):
+        return ops.feature_gate(x, gate_logits, channels_last=True, channels=gate_logits.shape[1])
+
+    def cat(self, xs):
+        """channel concatenation of channels-last tensors, re-padded to a legal K width."""
+        xs = list(xs)
+        c = sum(t.shape[-1] for t in xs)
+        cp = pad_channels(c)
+        if cp != c:
+            xs.append(torch.zeros(xs[0].shape[:-1] + (cp - c,), device=xs[0].device, dtype=xs[0].dtype))
+        return torch.cat(xs, dim=-1)
+
+    def to_ncdhw(self, x, channels=None):
+        if x.dtype == torch.float32:            # [B,D,H,W,C] fp32 (classifier-style outputs)
+            return x.permute(0, 4, 1, 2, 3).contiguous()
+        return from_channels_last(x, channels)
+
     # ---------------------------------------------------------------- head (layout exit)
     def head(self, cost, maxdisp, H, W, align_corners=False):
         assert cost.dtype == torch.float32 and cost.shape[-1] == 1

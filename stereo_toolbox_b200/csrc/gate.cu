@@ -1,0 +1,102 @@
+// Elementwise companions of the conv family (HBM-bound, one pass):
+//   * FeatureAtt gate of IGEV (IGEVStereo/submodule.py:228-241): cv * sigmoid(feat_att)[:, :, None] -- the 2-D gate
+//     logits [B,C,H,W] are broadcast over the disparity axis of the cost volume
+//   * disparity_variance of CFNet (CFNet/submodule.py:127-133): sum_d p_d * (d - disp)^2
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+
+// x, out [B,C,D,H,W] fp32; gate [B,C,H,W] fp32 logits.  One thread per 4 consecutive w (scalar tail).
+__global__ void gate_f32_kernel(const float* __restrict__ x, const float* __restrict__ gate, float* __restrict__ out,
+                                int C, int D, int H, int W, long long total) {
+    const long long hw = (long long)H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i % hw;              // (h, w)
+        const long long bcd = i / hw;            // (b*C + c)*D + d
+        const long long bc = bcd / D;
+        out[i] = x[i] * sigmoidf_(__ldg(gate + bc * hw + p));
+    }
+}
+
+// x, out [B,D,H,W,Cpad] 16-bit; gate [B,C,H,W] fp32 logits; channels >= C are copied (they are zero padding).
+__global__ void gate_cl16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gate, uint16_t* __restrict__ out,
+                                 int C, int Cpad, int D, int H, int W, long long nvox, int f16) {
+    const int chunks = Cpad >> 3;
+    const long long total = nvox * chunks;
+    const long long hw = (long long)H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long vox = i / chunks;
+        const int c0 = (int)(i - vox * chunks) * 8;
+        const long long p = vox % hw;
+        const long long b = vox / (hw * D);
+        const uint4 v = *reinterpret_cast<const uint4*>(x + vox * Cpad + c0);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f;
+            if (f16) f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+            const int c = c0 + 2 * j;
+            if (c < C) f.x *= sigmoidf_(__ldg(gate + (b * C + c) * hw + p));
+            if (c + 1 < C) f.y *= sigmoidf_(__ldg(gate + (b * C + c + 1) * hw + p));
+            if (f16) { __half2 h = __floats2half2_rn(f.x, f.y); w[j] = *reinterpret_cast<uint32_t*>(&h); }
+            else { __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y); w[j] = *reinterpret_cast<uint32_t*>(&h); }
+        }
+        *reinterpret_cast<uint4*>(out + vox * Cpad + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// prob [B,D,plane], disp [B,plane] -> var [B,plane]
+__global__ void variance_kernel(const float* __restrict__ prob, const float* __restrict__ disp, float* __restrict__ var,
+                                int D, long long plane, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / plane, p = i - b * plane;
+        const float m = disp[i];
+        const float* src = prob + b * D * plane + p;
+        float acc = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float t = (float)d - m;
+            acc = fmaf(__ldg(src + (long long)d * plane), t * t, acc);
+        }
+        var[i] = acc;
+    }
+}
+
+inline unsigned grid_for(long long total, int threads) {
+    long long g = (total + threads - 1) / threads;
+    const long long cap = 148LL * 32;          // a few waves of resident CTAs; the kernels are grid-stride
+    return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int stb_feature_gate_f32(const float* x, const float* gate, float* out, int B, int C, int D, int H, int W,
+                                    void* stream) {
+    if (!x || !gate || !out || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return STB_E_BADARG;
+    const long long total = (long long)B * C * D * H * W;
+    gate_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, gate, out, C, D, H, W, total);
+    STB_CHECK_LAUNCH();
+    return STB_OK;
+}
+
+extern "C" int stb_feature_gate_cl16(const void* x, const float* gate, void* out, int f16, int B, int C, int Cpad, int D,
+                                     int H, int W, void* stream) {
+    if (!x || !gate || !out || B <= 0 || C <= 0 || Cpad < C || (Cpad & 7) || D <= 0 || H <= 0 || W <= 0) return STB_E_BADARG;
+    const long long nvox = (long long)B * D * H * W;
+    gate_cl16_kernel<<<grid_for(nvox * (Cpad >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)x, gate, (uint16_t*)out, C, Cpad, D, H, W, nvox, f16);
+    STB_CHECK_LAUNCH();
+    return STB_OK;
+}
+
+extern "C" int stb_disparity_variance_f32(const float* prob, const float* disp, float* var, int B, int D, long long plane,
+                                          void* stream) {
+    if (!prob || !disp || !var || B <= 0 || D <= 0 || plane <= 0) return STB_E_BADARG;
+    const long long total = (long long)B * plane;
+    variance_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(prob, disp, var, D, plane, total);
+    STB_CHECK_LAUNCH();
+    return STB_OK;
+}

@@ -119,6 +119,40 @@ def disparity_regression(prob: torch.Tensor, maxdisp: int, keepdim: bool = False
     return disp.unsqueeze(1) if keepdim else disp
 
 
+def disparity_variance(prob: torch.Tensor, maxdisp: int, disparity: torch.Tensor) -> torch.Tensor:
+    """sum_d prob[:, d] * (d - disparity)^2, CFNet/submodule.py:127-133.  prob [B,D,H,W], disparity [B,1,H,W]
+    (or [B,H,W]) -> [B,1,H,W]."""
+    _need_cuda(prob, disparity)
+    assert len(prob.shape) == 4 and prob.shape[1] == maxdisp
+    prob, disparity = _f32c(prob), _f32c(disparity)
+    B, D, H, W = prob.shape
+    assert disparity.numel() == B * H * W
+    var = torch.empty(B, 1, H, W, device=prob.device, dtype=torch.float32)
+    _lib.call("stb_disparity_variance_f32", _p(prob), _p(disparity), _p(var), B, D, H * W, _stream())
+    return var
+
+
+def feature_gate(x: torch.Tensor, gate_logits: torch.Tensor, channels_last: bool = False, channels: Optional[int] = None):
+    """FeatureAtt gate (IGEVStereo/submodule.py:236-241): x * sigmoid(gate_logits)[:, :, None].
+    x [B,C,D,H,W] fp32, or channels-last 16-bit [B,D,H,W,Cpad] with ``channels`` real channels; gate_logits [B,C,H,W]."""
+    _need_cuda(x, gate_logits)
+    g = _f32c(gate_logits)
+    if not channels_last:
+        x = _f32c(x)
+        B, C, D, H, W = x.shape
+        assert tuple(g.shape) == (B, C, H, W)
+        out = torch.empty_like(x)
+        _lib.call("stb_feature_gate_f32", _p(x), _p(g), _p(out), B, C, D, H, W, _stream())
+        return out
+    assert x.is_contiguous() and x.dtype in (torch.float16, torch.bfloat16)
+    B, D, H, W, cpad = x.shape
+    C = channels or cpad
+    assert tuple(g.shape) == (B, C, H, W)
+    out = torch.empty_like(x)
+    _lib.call("stb_feature_gate_cl16", _p(x), _p(g), _p(out), int(x.dtype == torch.float16), B, C, cpad, D, H, W, _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------ ACVNet pieces
 def patch_dw(x: torch.Tensor, weight: torch.Tensor, dilation: int, out: Optional[torch.Tensor] = None,
              c_off: int = 0) -> torch.Tensor:

@@ -45,6 +45,6 @@ def golden_state(model_key, meta_file="models.json", calib=True):
     if calib:
         z = np.load(os.path.join(GOLDEN, f"bn_calib_{model_key}.npz"))
         over = {k: z[k] for k in z.files}
-    sd = synth_state_dict(template, 0, over)
+    sd = synth_state_dict(template, meta.get("seed", 0), over)
     assert abs(state_checksum(sd) - meta["checksum"]) <= 1e-6 * abs(meta["checksum"]), "synthetic weights drifted"
     return sd, meta

@@ -230,8 +230,79 @@ def acv():
     json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
 
 
+@torch.no_grad()
+def igev():
+    """IGEV cost-volume stage (config 5 component level; IGEVStereo() itself needs timm weights): the reference's
+    corr_stem / corr_feature_att / cost_agg (hourglass(8)) / classifier run exactly as igev_stereo.py:205-213, plus one
+    geometry-encoding lookup at the initial disparity (geometry.py)."""
+    ig, sub, geo_mod = ref("IGEVStereo.igev_stereo"), ref("IGEVStereo.submodule"), ref("IGEVStereo.geometry")
+
+    class Stage(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.corr_stem = sub.BasicConv(8, 8, is_3d=True, kernel_size=3, stride=1, padding=1)
+            self.corr_feature_att = sub.FeatureAtt(8, 96)
+            self.cost_agg = ig.hourglass(8)
+            self.classifier = torch.nn.Conv3d(8, 1, 3, 1, 1, bias=False)
+
+        def forward(self, ml, mr, feats, max_disp):
+            vol = sub.build_gwc_volume(ml, mr, max_disp // 4, 8)
+            vol = self.corr_feature_att(self.corr_stem(vol), feats[0])
+            geo = self.cost_agg(vol, feats)
+            prob = torch.softmax(self.classifier(geo).squeeze(1), dim=1)
+            return sub.disparity_regression(prob, max_disp // 4), geo
+
+    net = Stage()
+    sd = _load_synth(net, seed=11)
+    h, w, max_disp = 16, 32, 64
+    ml, mr = rnd(40, 1, 96, h, w) * 0.3, rnd(41, 1, 96, h, w) * 0.3
+    feats = [rnd(42, 1, 96, h, w), rnd(43, 1, 64, h // 2, w // 2), rnd(44, 1, 192, h // 4, w // 4), rnd(45, 1, 160, h // 8, w // 8)]
+    init_disp, geo = net(ml, mr, feats, max_disp)
+    fn = geo_mod.Combined_Geo_Encoding_Volume(ml.float(), mr.float(), geo.float(), radius=4, num_levels=2)
+    coords = torch.arange(w).float().reshape(1, 1, w, 1).repeat(1, h, 1, 1)
+    geo_feat = fn(init_disp, coords)
+    save("igev_stage.npz", ml=ml, mr=mr, f0=feats[0], f1=feats[1], f2=feats[2], f3=feats[3], init_disp=init_disp, geo=geo,
+         geo_feat=geo_feat)
+    meta = json.load(open(os.path.join(HERE, "blocks.json")))
+    meta["igev_stage"] = dict(keys=_keys(sd), checksum=state_checksum(sd), max_disp=max_disp, seed=11)
+    json.dump(meta, open(os.path.join(HERE, "blocks.json"), "w"))
+
+
+@torch.no_grad()
+def cascade():
+    """CFNet / PCWNet aggregation blocks: Mish hourglass, hourglassup (2 and 3 levels), align_corners=True head,
+    disparity_variance."""
+    import torch.nn.functional as F
+    cf, pc, cfsub = ref("CFNet.cfnet"), ref("PCWNet.pcwnet"), ref("CFNet.submodule")
+    out = {}
+    meta = json.load(open(os.path.join(HERE, "blocks.json")))
+    x = rnd(50, 1, 8, 8, 16, 16) * 0.5
+    f4, f5, f6 = rnd(51, 1, 16, 4, 8, 8) * 0.5, rnd(52, 1, 16, 2, 4, 4) * 0.5, rnd(53, 1, 16, 1, 2, 2) * 0.5
+    out.update(x=x, f4=f4, f5=f5, f6=f6)
+    hg = cf.hourglass(8)
+    sd = _load_synth(hg, seed=21)
+    out["cf_hg_y"] = hg(x)
+    meta["cf_hg"] = dict(keys=_keys(sd), checksum=state_checksum(sd), seed=21)
+    up2 = cf.hourglassup(8)
+    sd = _load_synth(up2, seed=22)
+    out["cf_up_y"] = up2(x, f4, f5)
+    meta["cf_up"] = dict(keys=_keys(sd), checksum=state_checksum(sd), seed=22)
+    up3 = pc.hourglassup(8)
+    sd = _load_synth(up3, seed=23)
+    out["pc_up_y"] = up3(x, f4, f5, f6)
+    meta["pc_up"] = dict(keys=_keys(sd), checksum=state_checksum(sd), seed=23)
+    # head with align_corners=True (cfnet.py:605-613) + variance (CFNet/submodule.py:127-133)
+    cost = rnd(54, 2, 1, 6, 5, 7) * 3
+    up = F.interpolate(cost, [24, 20, 28], mode="trilinear", align_corners=True)[:, 0]
+    prob = F.softmax(up, dim=1)
+    disp = cfsub.disparity_regression(prob, 24)
+    out.update(head_cost=cost, head_disp=disp, head_prob=prob, head_var=cfsub.disparity_variance(prob, 24, disp.unsqueeze(1)))
+    save("blocks_cascade.npz", **out)
+    json.dump(meta, open(os.path.join(HERE, "blocks.json"), "w"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv"]
+    which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]
     for w in which:
         globals()[w]()
