@@ -210,6 +210,33 @@ int stb_feature_gate_cl16(const void* x, const float* gate, void* out, int f16, 
 int stb_disparity_variance_f32(const float* prob, const float* disp, float* var, int B, int D, long long plane,
                                void* stream);
 
+/* ---- backward kernels (training path, exact fp32, reference layouts) --------------------------------------
+ * The DATA gradient of the conv family needs no entry point of its own: the adjoint of Conv3d(k,s,p) is
+ * ConvTranspose3d(k,s,p,op) with the same weight tensor and vice versa, i.e. another stb_conv3d_taps_f32 call.
+ *
+ * Weight gradient of Conv3d / ConvTranspose3d (PSMNet/submodule.py:16-19, PSMNet/stackhourglass.py:25-29):
+ *   dW[kd][kh][kw][cp][cq] += sum_{b,q} P[b][cp][stride*q + k - pad] * Q[b][cq][q]        (dW must be zeroed by the caller)
+ * Conv3d: P = layer input, Q = grad of the output (weight.grad[co,ci,k] = dW[k][ci][co]);
+ * ConvTranspose3d: P = grad of the output, Q = layer input (weight.grad[ci,co,k] = dW[k][co][ci]).
+ * P [B,Cp,Dp,Hp,Wp], Q [B,Cq,Dq,Hq,Wq] fp32; (K,stride) in {(1,1),(3,1),(3,2),(4,2)}. */
+int stb_conv3d_wgrad_f32(const float* P, const float* Q, float* dW, int B, int Cp, int Dp, int Hp, int Wp, int Cq,
+                         int Dq, int Hq, int Wq, int K, int pad, int stride, void* stream);
+
+/* Adjoint of build_concat_volume (variant A mask_left=1 / B mask_left=0): dvol [B,c_total,D,H,W] channels
+ * [c_off, c_off+2C) -> dleft, dright [B,C,H,W]. */
+int stb_concat_volume_bwd_f32(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W, int D,
+                              int mask_left, int c_total, int c_off, void* stream);
+
+/* Adjoint of build_gwc_volume: dvol channels [c_off, c_off+G) of [B,c_total,D,H,W]; left/right [B,C,H,W] are the
+ * forward inputs -> dleft, dright [B,C,H,W]. */
+int stb_gwc_volume_bwd_f32(const float* dvol, const float* left, const float* right, float* dleft, float* dright,
+                           int B, int C, int H, int W, int D, int G, int c_total, int c_off, void* stream);
+
+/* Adjoint of stb_upsample_softargmin_f32: cost [B,D,H,W] (the forward input), gdisp [B,outH,outW] -> dcost [B,D,H,W]
+ * is ACCUMULATED into (zero it first). */
+int stb_upsample_softargmin_bwd_f32(const float* cost, const float* gdisp, float* dcost, int B, int D, int H, int W,
+                                    int outD, int outH, int outW, int align_corners, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

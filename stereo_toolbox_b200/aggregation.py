@@ -159,6 +159,70 @@ class Fp32Backend:
             return ops.upsample_softargmin(cost, maxdisp, H, W, align_corners)
 
 
+class TrainBackend:
+    """Training path (model.train()): same interface as Fp32Backend, every call differentiable.
+
+    Convolutions, volume builders and the head run forward AND backward in libstb200.so (autograd.py: the data gradient
+    is the adjoint convolution through the same tap-list kernel, the weight gradient stb_conv3d_wgrad_f32, the volume
+    and head adjoints their own kernels).  BatchNorm3d uses batch statistics and updates its running statistics exactly
+    like the reference -- it is the layer's own torch module applied to the raw convolution output -- and the residual
+    add / activation are torch elementwise ops, so their autograd is torch's.  fp32, reference layouts (NCDHW)."""
+    name = "fp32-train"
+
+    def __init__(self):
+        self.prof = _NoProf()
+
+    def volume_gwc_concat(self, gwc_l, gwc_r, cat_l, cat_r, maxdisp4, groups):
+        from . import autograd as A
+        vol = A.gwc_volume(gwc_l, gwc_r, maxdisp4, groups)
+        if cat_l is None:
+            return vol
+        return torch.cat((vol, A.concat_volume(cat_l, cat_r, maxdisp4, True)), 1)       # GwcNet/gwcnet.py:175-180
+
+    def volume_concat(self, l, r, maxdisp4, mask_left=True, att_prob=None):
+        from . import autograd as A
+        vol = A.concat_volume(l, r, maxdisp4, mask_left)
+        return vol if att_prob is None else vol * att_prob
+
+    def conv(self, layer, x, act="none", residual=None):
+        from . import autograd as A
+        conv, bn = _split(layer)
+        y = A.conv3d(x, conv)
+        if bn is not None:
+            y = bn(y)
+        if residual is not None:
+            y = y + residual
+        if act == "relu":
+            return torch.relu(y)
+        if act == "leaky":
+            return torch.nn.functional.leaky_relu(y, 0.01)
+        if act == "mish":
+            return y * torch.tanh(torch.nn.functional.softplus(y))
+        return y
+
+    def from_ncdhw(self, x):
+        return x
+
+    def to_ncdhw(self, x, channels=None):
+        return x
+
+    def cost_ncdhw(self, cost):
+        return cost
+
+    def cost_native(self, cost):
+        return cost
+
+    def cat(self, xs):
+        return torch.cat(list(xs), dim=1)
+
+    def gate(self, x, gate_logits):
+        return x * torch.sigmoid(gate_logits).unsqueeze(2)
+
+    def head(self, cost, maxdisp, H, W, align_corners=False):
+        from . import autograd as A
+        return A.upsample_softargmin(cost, maxdisp, H, W, align_corners)
+
+
 def make_backend(precision: str):
     if precision == "fp32":
         return Fp32Backend()

@@ -1,0 +1,147 @@
+"""Differentiable forms of the hot-path operators (training path, exact fp32): ``torch.autograd.Function`` wrappers whose
+forward AND backward run in libstb200.so.
+
+  conv3d / conv_transpose3d : forward stb_conv3d_taps_f32; data gradient = the adjoint convolution of the same family
+                              (Conv3d <-> ConvTranspose3d with the same weight tensor) through the same kernel; weight
+                              gradient stb_conv3d_wgrad_f32            (PSMNet/submodule.py:16-19, stackhourglass.py:25-29)
+  concat_volume / gwc_volume: stb_*_volume_f32 / stb_*_volume_bwd_f32  (GwcNet/submodule.py:30-63)
+  upsample_softargmin       : fused head and its adjoint               (PSMNet/stackhourglass.py:139-156)
+
+BatchNorm3d (batch statistics in train mode) and the activations are applied by the caller with ordinary torch modules,
+so their autograd is torch's; what the reference trains through cuDNN conv kernels and ~6 materialised [B,192,H,W]
+tensors per head goes through the kernels above.  Gradients are checked against torch autograd of the oracle
+restatement in tests/test_gpu_train.py.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+from .ops import _f32c, _p, _stream
+
+
+def _same(vals, what):
+    v = set(vals)
+    if len(v) != 1:
+        raise ValueError(f"{what} must be equal along D, H and W (got {tuple(vals)})")
+    return vals[0]
+
+
+class _Conv3dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, transposed, output_padding):
+        plan = ops.ConvPlan(weight, None, stride, padding, transposed, output_padding, bias=bias)
+        y = ops.conv3d_plan_apply(plan, x)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, padding, transposed, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, padding, transposed, has_bias = ctx.cfg
+        gy = _f32c(gy)
+        k = w.shape[2]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            if not transposed:
+                # adjoint of Conv3d(k,s,p) = ConvTranspose3d(k,s,p,op) with the SAME weight tensor [Cout,Cin,k,k,k]
+                op = _same([x.shape[i] - ((gy.shape[i] - 1) * stride - 2 * padding + k) for i in (2, 3, 4)], "output_padding")
+                plan = ops.ConvPlan(w, None, stride, padding, True, op)
+            else:
+                # adjoint of ConvTranspose3d = Conv3d with the same weight tensor [Cin,Cout,k,k,k] read as [out,in,...]
+                plan = ops.ConvPlan(w, None, stride, padding, False)
+            gx = ops.conv3d_plan_apply(plan, gy)
+            assert gx.shape == x.shape
+        if ctx.needs_input_grad[1]:
+            P, Q = (gy, _f32c(x)) if transposed else (_f32c(x), gy)
+            dw = torch.zeros(k, k, k, P.shape[1], Q.shape[1], device=x.device, dtype=torch.float32)
+            _lib.call("stb_conv3d_wgrad_f32", _p(P), _p(Q), _p(dw), P.shape[0], P.shape[1], P.shape[2], P.shape[3],
+                      P.shape[4], Q.shape[1], Q.shape[2], Q.shape[3], Q.shape[4], k, padding, stride, _stream())
+            gw = dw.permute(4, 3, 0, 1, 2).contiguous()       # both layouts: weight[cq, cp, kd, kh, kw]
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum((0, 2, 3, 4))
+        return gx, gw, gb, None, None, None, None
+
+
+def conv3d(x, conv: torch.nn.Module):
+    """``conv`` is an nn.Conv3d or nn.ConvTranspose3d (cubic kernel, equal strides / paddings); returns conv(x)."""
+    tr = isinstance(conv, torch.nn.ConvTranspose3d)
+    return _Conv3dFn.apply(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], tr,
+                           conv.output_padding[0] if tr else 0)
+
+
+class _ConcatVolumeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, left, right, maxdisp, mask_left):
+        ctx.cfg = (maxdisp, mask_left, tuple(left.shape))
+        return ops.concat_volume(left, right, maxdisp, mask_left)
+
+    @staticmethod
+    def backward(ctx, gvol):
+        maxdisp, mask_left, (B, C, H, W) = ctx.cfg
+        gvol = _f32c(gvol)
+        gl = torch.empty(B, C, H, W, device=gvol.device, dtype=torch.float32)
+        gr = torch.empty_like(gl)
+        _lib.call("stb_concat_volume_bwd_f32", _p(gvol), _p(gl), _p(gr), B, C, H, W, maxdisp, int(mask_left), 2 * C, 0, _stream())
+        return gl, gr, None, None
+
+
+def concat_volume(left, right, maxdisp, mask_left=True):
+    return _ConcatVolumeFn.apply(left, right, maxdisp, mask_left)
+
+
+class _GwcVolumeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, left, right, maxdisp, groups):
+        left, right = _f32c(left), _f32c(right)
+        ctx.save_for_backward(left, right)
+        ctx.cfg = (maxdisp, groups)
+        return ops.gwc_volume(left, right, maxdisp, groups)
+
+    @staticmethod
+    def backward(ctx, gvol):
+        left, right = ctx.saved_tensors
+        maxdisp, groups = ctx.cfg
+        B, C, H, W = left.shape
+        gvol = _f32c(gvol)
+        gl, gr = torch.empty_like(left), torch.empty_like(right)
+        _lib.call("stb_gwc_volume_bwd_f32", _p(gvol), _p(left), _p(right), _p(gl), _p(gr), B, C, H, W, maxdisp, groups,
+                  groups, 0, _stream())
+        return gl, gr, None, None
+
+
+def gwc_volume(left, right, maxdisp, groups):
+    return _GwcVolumeFn.apply(left, right, maxdisp, groups)
+
+
+class _HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cost, maxdisp, out_h, out_w, align_corners):
+        if cost.dim() == 5:
+            assert cost.shape[1] == 1
+            ctx.squeeze = True
+            cost4 = cost[:, 0]
+        else:
+            ctx.squeeze = False
+            cost4 = cost
+        cost4 = _f32c(cost4)
+        ctx.save_for_backward(cost4)
+        ctx.cfg = (maxdisp, out_h, out_w, align_corners)
+        return ops.upsample_softargmin(cost4, maxdisp, out_h, out_w, align_corners)
+
+    @staticmethod
+    def backward(ctx, gdisp):
+        (cost4,) = ctx.saved_tensors
+        maxdisp, out_h, out_w, align = ctx.cfg
+        B, D, H, W = cost4.shape
+        gdisp = _f32c(gdisp)
+        gcost = torch.zeros_like(cost4)
+        _lib.call("stb_upsample_softargmin_bwd_f32", _p(cost4), _p(gdisp), _p(gcost), B, D, H, W, maxdisp, out_h, out_w,
+                  int(align), _stream())
+        return (gcost.unsqueeze(1) if ctx.squeeze else gcost), None, None, None, None
+
+
+def upsample_softargmin(cost, maxdisp, out_h, out_w, align_corners=False):
+    """[B,1,D,h,w] or [B,D,h,w] -> [B,out_h,out_w]; differentiable w.r.t. cost."""
+    return _HeadFn.apply(cost, maxdisp, out_h, out_w, align_corners)

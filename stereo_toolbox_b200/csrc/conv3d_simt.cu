@@ -54,7 +54,7 @@ conv3d_taps_kernel(const __grid_constant__ ConvArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int CK = a.CK;
     float* xs = smem;                                   // [CK][ED][EH][EWp]
-    float* ws = smem + CK * a.ED * a.EH * a.EWp;        // [ntaps][CK][CO_TILE]
+    float* ws = smem + ((CK * a.ED * a.EH * a.EWp + 3) & ~3);   // [ntaps][CK][CO_TILE], 16-byte aligned (read as float4)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = lane >> 3, quad = lane & 7;
 
@@ -235,7 +235,7 @@ static int conv3d_taps_launch(bool cl, int out_fp32, int f16, const void* x, con
     // channel chunk: as large as fits ~96 KB so that 2 CTAs share an SM
     int CK = 8;
     auto smem_for = [&](int ck) {
-        return (size_t)(ck * a.ED * a.EH * a.EWp + ntaps * ck * CO_TILE) * sizeof(float);
+        return (size_t)(((ck * a.ED * a.EH * a.EWp + 3) & ~3) + ntaps * ck * CO_TILE) * sizeof(float);
     };
     while (CK > 1 && smem_for(CK) > 96 * 1024) CK >>= 1;
     if (CK > Cin) { CK = 1; while (CK * 2 <= Cin && CK < 8) CK <<= 1; }

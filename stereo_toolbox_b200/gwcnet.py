@@ -68,9 +68,9 @@ class GwcNet(nn.Module):
         self._be = make_backend(precision)
         return self
 
-    def aggregate(self, fl, fr, height, width):
-        """The hot path: features -> disparity [B,H,W]."""
-        be = self._be
+    def aggregate(self, fl, fr, height, width, be=None, all_heads=False):
+        """The hot path: features -> disparity [B,H,W] (training: the reference's list of four)."""
+        be = be or self._be
         vol = be.volume_gwc_concat(fl["gwc_feature"], fr["gwc_feature"], fl.get("concat_feature"),
                                    fr.get("concat_feature"), self.maxdisp // 4, self.num_groups)
         c = be.conv(self.dres0[0], vol, "relu")
@@ -80,6 +80,12 @@ class GwcNet(nn.Module):
         out1 = self.dres2.run(be, cost0)
         out2 = self.dres3.run(be, out1)
         out3 = self.dres4.run(be, out2)
+        if all_heads:       # training: [pred0..pred3] from classif0(cost0), classif1(out1), ... (gwcnet.py:191-216)
+            preds = []
+            for cls, t in ((self.classif0, cost0), (self.classif1, out1), (self.classif2, out2), (self.classif3, out3)):
+                c = be.conv(cls[2], be.conv(cls[0], t, "relu"))
+                preds.append(be.head(c, self.maxdisp, height, width, align_corners=False))
+            return preds
         c = be.conv(self.classif3[0], out3, "relu")
         cost3 = be.conv(self.classif3[2], c)
         self._last_cost = cost3
@@ -133,11 +139,22 @@ class GwcNet(nn.Module):
 
     def forward(self, left, right):
         if self.training:
-            raise NotImplementedError(
-                "stereo_toolbox_b200: the training (autograd / batch-stat BatchNorm3d) path is not built yet; "
-                "call model.eval() -- see DESIGN.md 'out of scope this round'")
+            return self._forward_train(left, right)
         fl, fr = self._features(left, right)
         return self.aggregate(fl, fr, left.shape[2], left.shape[3])
+
+    def _forward_train(self, left, right):
+        """Training step forward (exact fp32): torch 2-D extractor (+concatconv) with autograd, cost-volume path on
+        TrainBackend (forward and backward in libstb200.so).  Returns [pred0, pred1, pred2, pred3] (gwcnet.py:216)."""
+        from .aggregation import TrainBackend
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            fl = self.feature_extraction(left)
+            fr = self.feature_extraction(right)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=TrainBackend(), all_heads=True)
 
 
 def GwcNet_G(d=192, **kw):

@@ -62,8 +62,8 @@ class PSMNet(nn.Module):
         self._be = make_backend(precision)
         return self
 
-    def aggregate(self, fl, fr, height, width):
-        be = self._be
+    def aggregate(self, fl, fr, height, width, be=None, all_heads=False):
+        be = be or self._be
         vol = be.volume_concat(fl, fr, self.maxdisp // 4, mask_left=True)
         c = be.conv(self.dres0[0], vol, "relu")
         cost0 = be.conv(self.dres0[2], c, "relu")
@@ -76,6 +76,8 @@ class PSMNet(nn.Module):
         cost2 = be.conv(self.classif2[2], be.conv(self.classif2[0], out2, "relu"), residual=cost1)
         cost3 = be.conv(self.classif3[2], be.conv(self.classif3[0], out3, "relu"), residual=cost2)
         self._last_cost = cost3
+        if all_heads:       # training: [pred1, pred2, pred3], each [B,1,H,W] (stackhourglass.py:139-159)
+            return [be.head(c, self.maxdisp, height, width, align_corners=False).unsqueeze(1) for c in (cost1, cost2, cost3)]
         return be.head(cost3, self.maxdisp, height, width, align_corners=False).unsqueeze(1)
 
     def _features(self, left, right):
@@ -117,8 +119,20 @@ class PSMNet(nn.Module):
 
     def forward(self, left, right):
         if self.training:
-            raise NotImplementedError(
-                "stereo_toolbox_b200: the training (autograd / batch-stat BatchNorm3d) path is not built yet; "
-                "call model.eval() -- see DESIGN.md 'out of scope this round'")
+            return self._forward_train(left, right)
         fl, fr = self._features(left, right)
         return self.aggregate(fl, fr, left.shape[2], left.shape[3])
+
+    def _forward_train(self, left, right):
+        """Training step forward (exact fp32): the 2-D extractor is ordinary torch (train-mode BatchNorm2d, autograd),
+        the cost-volume path runs on TrainBackend -- forward and backward in libstb200.so.  Returns the reference's
+        list [pred1, pred2, pred3] (stackhourglass.py:159)."""
+        from .aggregation import TrainBackend
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = prev and self.feature_mode not in (None, "fp32") and self.feature_tf32 is not False
+        try:
+            fl = self.feature_extraction(left)
+            fr = self.feature_extraction(right)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=TrainBackend(), all_heads=True)

@@ -72,3 +72,11 @@ def synth_pair(batch: int, height: int, width: int, seed: int = 0, shift: int | 
     else:
         right = torch.roll(left, -shift, dims=3) + 0.1 * torch.randn(batch, 3, height, width, generator=g)
     return left, right
+
+
+def synth_gt(batch: int, height: int, width: int) -> torch.Tensor:
+    """Deterministic synthetic ground-truth disparity in [1, 31): an RNG-free pattern so that fixtures and tests agree."""
+    b = torch.arange(batch).view(-1, 1, 1)
+    y = torch.arange(height).view(1, -1, 1)
+    x = torch.arange(width).view(1, 1, -1)
+    return 1.0 + ((x * 7 + y * 13 + b * 5) % 300).float() / 10.0

@@ -301,6 +301,37 @@ def cascade():
     json.dump(meta, open(os.path.join(HERE, "blocks.json"), "w"))
 
 
+def train():
+    """One PSMNet training step of the reference on CPU (config 3 family, small): train-mode forward (batch-statistic
+    BatchNorm), the trainer's loss (smooth-L1 on the three outputs, weights 0.5/0.7/1.0, mask 0 < gt < maxdisp:
+    trainer/trainer_torchrun.py:272-278), backward.  Stores the three predictions, the loss and the gradients of a few
+    parameters that cover conv / strided conv / transposed conv / classifier / BatchNorm3d / the 2-D extractor (i.e. the
+    volume adjoint)."""
+    import torch.nn.functional as F
+    net = ref("PSMNet.stackhourglass").PSMNet(32)
+    z = np.load(os.path.join(HERE, "bn_calib_psmnet.npz"))
+    sd = synth_state_dict(net.state_dict(), 0, {k: z[k] for k in z.files})
+    net.load_state_dict(sd, strict=True)
+    net.train()
+    left, right = synth_pair(2, 256, 256, seed=1, shift=7)     # batch 2: the 64x64 SPP branch leaves one value per channel and image
+    from stereo_toolbox_b200.synth import synth_gt
+    gt = synth_gt(2, 256, 256)
+    preds = net(left, right)
+    mask = (gt > 0) & (gt < 32)
+    loss = sum(w * F.smooth_l1_loss(p.squeeze(1)[mask], gt[mask], reduction="mean") for w, p in zip((0.5, 0.7, 1.0), preds))
+    loss.backward()
+    names = ["dres0.0.0.weight", "dres0.0.1.weight", "dres0.0.1.bias", "dres1.2.0.weight", "dres2.conv1.0.0.weight",
+             "dres2.conv5.0.weight", "dres3.conv6.0.weight", "dres4.conv2.0.weight", "classif1.2.weight", "classif3.0.0.weight",
+             "classif3.2.weight", "feature_extraction.lastconv.2.weight", "feature_extraction.firstconv.0.0.weight"]
+    params = dict(net.named_parameters())
+    sub = lambda p: p.detach()[:, :, ::2, ::2]
+    out = {"loss": loss.detach(), "pred1": sub(preds[0]), "pred2": sub(preds[1]), "pred3": sub(preds[2]),
+           "rm_dres0": net.dres0[0][1].running_mean.detach().clone(), "rv_dres0": net.dres0[0][1].running_var.detach().clone()}
+    for n in names:
+        out["grad:" + n] = params[n].grad.detach()
+    save("psmnet_train.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]

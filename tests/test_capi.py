@@ -77,7 +77,12 @@ def test_conv_plan_tap_lists():
 
 
 def test_training_mode_fails_loudly():
+    """PSMNet / GwcNet train on the CUDA path only (no CPU fallback: CPU tensors are refused); models whose training path
+    is not built raise NotImplementedError instead of silently running something else."""
     import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200._lib import StbError
     net = S.GwcNet_GC(32).train()
+    with pytest.raises(StbError):
+        net(torch.zeros(2, 3, 64, 128), torch.zeros(2, 3, 64, 128))
     with pytest.raises(NotImplementedError):
-        net(torch.zeros(1, 3, 64, 128), torch.zeros(1, 3, 64, 128))
+        S.ACVNet(32).train()(torch.zeros(1, 3, 64, 128), torch.zeros(1, 3, 64, 128))
