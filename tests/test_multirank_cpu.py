@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from stereo_toolbox_b200.distrib import shard_range, reduce_stats
+from stereo_toolbox_b200.distrib import shard_range, reduce_stats, FlatGradAllReduce
 
 
 def test_shard_range_partitions():
@@ -43,3 +43,47 @@ def test_two_rank_gloo_reduction():
     for _, times, counts in res:
         assert times == [15.0, 3.0]        # slowest rank per region
         assert counts == [16.0, 1.0]       # whole-job units
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                   # identical replicas
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    bucket = FlatGradAllReduce(net.parameters())
+    g = torch.Generator().manual_seed(100 + rank)          # each rank has its own shard of the batch
+    x = torch.randn(4, 6, generator=g)
+    for _ in range(2):                                     # second step: zero_() + in-place accumulation keep the views alive
+        bucket.zero_()
+        net(x).square().mean().backward()
+        local = [p.grad.clone() for p in net.parameters()]
+        bucket.allreduce_()
+    views_ok = all(p.grad.data_ptr() >= bucket.flat.data_ptr() and
+                   p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.nbytes for p in net.parameters())
+    q.put((rank, [t.tolist() for t in local], [p.grad.tolist() for p in net.parameters()], views_ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce():
+    """The training exchange step: after FlatGradAllReduce every rank holds the MEAN of the per-rank gradients
+    (DistributedDataParallel semantics), and the parameters' .grad are still views of the flat buffer."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, r0, v0), (_, l1, r1, v1) = res
+    assert v0 and v1
+    for a, b, m0, m1 in zip(l0, l1, r0, r1):
+        want = (torch.tensor(a) + torch.tensor(b)) / 2
+        torch.testing.assert_close(torch.tensor(m0), want)
+        torch.testing.assert_close(torch.tensor(m1), want)
