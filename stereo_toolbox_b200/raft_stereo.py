@@ -251,6 +251,63 @@ class RAFTStereo(nn.Module):
         up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
         return up.reshape(N, D, f * H, f * W)
 
+    def _iteration(self, net_list, inp_list, corr_fn, coords0, coords1):
+        """One GRU iteration of raft_stereo.py:153-182: pyramid lookup (one CUDA kernel) + update block (torch)."""
+        a = self.args
+        coords1 = coords1.detach()
+        corr = corr_fn(coords1)
+        flow = coords1 - coords0
+        if a.n_gru_layers == 3 and a.slow_fast_gru:
+            net_list = self.update_block(net_list, inp_list, iter32=True, iter16=False, iter08=False, update=False)
+        if a.n_gru_layers >= 2 and a.slow_fast_gru:
+            net_list = self.update_block(net_list, inp_list, iter32=a.n_gru_layers == 3, iter16=True, iter08=False,
+                                         update=False)
+        net_list, up_mask, delta_flow = self.update_block(net_list, inp_list, corr, flow,
+                                                          iter32=a.n_gru_layers == 3, iter16=a.n_gru_layers >= 2)
+        delta_flow[:, 1] = 0.0                    # stereo: project the update onto the epipolar line
+        return net_list, up_mask, coords1 + delta_flow
+
+    def _iterate_graphed(self, net_list, inp_list, corr_fn, coords0, coords1, iters):
+        """The 32-iteration loop is launch-bound in eager mode (~60 small kernels per iteration at 1/4 resolution): ONE
+        iteration -- lookup kernel + update block + the write-back of its outputs into its own inputs -- is captured
+        into a CUDA graph once per input shape and replayed ``iters`` times per call.
+        Per call only the graph's static inputs (hidden states, context features, correlation pyramid, coordinates) are
+        refreshed.  Same kernels, same order, so the result is bit-identical to the eager loop.
+        Opt-in: ``model.cuda_graph = True``."""
+        key = (tuple(coords1.shape), tuple(tuple(t.shape) for t in net_list), str(coords1.device))
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            st = dict(net=[t.clone() for t in net_list], inp=[[t.clone() for t in lvl] for lvl in inp_list],
+                      coords=coords1.clone(), coords0=coords0.clone(), levels=[t.clone() for t in corr_fn._levels])
+            corr_fn._levels = st["levels"]                # the captured lookup reads the static pyramid buffers
+            st["corr_fn"] = corr_fn
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                 # warm-up outside capture (cuDNN plans, lazy kernel loading);
+                self._iteration(list(st["net"]), st["inp"], corr_fn, st["coords0"], st["coords"])   # update_block mutates the list
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                n2, m2, c2 = self._iteration(list(st["net"]), st["inp"], corr_fn, st["coords0"], st["coords"])
+                for dst, src in zip(st["net"], n2):
+                    dst.copy_(src)
+                st["coords"].copy_(c2)
+            st["graph"], st["mask"] = graph, m2
+            cache[key] = hit = st
+        else:
+            for dst, src in zip(hit["net"], net_list):
+                dst.copy_(src)
+            for dl, sl in zip(hit["inp"], inp_list):
+                for dst, src in zip(dl, sl):
+                    dst.copy_(src)
+            for dst, src in zip(hit["levels"], corr_fn._levels):
+                dst.copy_(src)
+            hit["coords"].copy_(coords1)
+        for _ in range(iters):
+            hit["graph"].replay()
+        return hit["coords"].clone(), hit["mask"]
+
     def forward(self, image1, image2, iters=None, flow_init=None, test_mode=False):
         if self.training:
             raise NotImplementedError("stereo_toolbox_b200: the training path is not built yet; call model.eval()")
@@ -282,19 +339,12 @@ class RAFTStereo(nn.Module):
         if flow_init is not None:
             coords1 = coords1 + flow_init
         flow_up = None
+        if getattr(self, "cuda_graph", False) and flow_init is None and iters > 1:
+            coords1, up_mask = self._iterate_graphed(net_list, inp_list, corr_fn, coords0, coords1, iters)
+            flow_up = self.upsample_flow(coords1 - coords0, up_mask)[:, :1]
+            return -flow_up
         for itr in range(iters):
-            coords1 = coords1.detach()
-            corr = corr_fn(coords1)
-            flow = coords1 - coords0
-            if a.n_gru_layers == 3 and a.slow_fast_gru:
-                net_list = self.update_block(net_list, inp_list, iter32=True, iter16=False, iter08=False, update=False)
-            if a.n_gru_layers >= 2 and a.slow_fast_gru:
-                net_list = self.update_block(net_list, inp_list, iter32=a.n_gru_layers == 3, iter16=True, iter08=False,
-                                             update=False)
-            net_list, up_mask, delta_flow = self.update_block(net_list, inp_list, corr, flow,
-                                                              iter32=a.n_gru_layers == 3, iter16=a.n_gru_layers >= 2)
-            delta_flow[:, 1] = 0.0                    # stereo: project the update onto the epipolar line
-            coords1 = coords1 + delta_flow
+            net_list, up_mask, coords1 = self._iteration(net_list, inp_list, corr_fn, coords0, coords1)
             if itr < iters - 1:
                 continue
             flow_up = self.upsample_flow(coords1 - coords0, up_mask)[:, :1]

@@ -88,6 +88,30 @@ def test_raft_stereo_golden():
     assert epe < 1e-3, f"EPE vs reference {epe}"
 
 
+def test_raft_stereo_cuda_graph_iteration_is_bit_identical():
+    """model.cuda_graph = True replays one captured GRU iteration (lookup kernel + update block) instead of launching it
+    eagerly: same kernels in the same order, so the output must be bit-identical, and still match the reference."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    g = load_golden("raft_stereo.npz")
+    sd, meta = golden_state("raft_stereo", calib=False)
+    net = S.RAFTStereo()
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    left, right = synth_pair(1, 64, 128, seed=2, shift=meta["shift"])
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            eager = net(left.cuda(), right.cuda(), iters=meta["iters"])
+            net.cuda_graph = True
+            graphed = net(left.cuda(), right.cuda(), iters=meta["iters"])
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert torch.equal(eager, graphed)
+    assert (graphed.cpu() - g["disp"]).abs().mean().item() < 1e-3
+
+
 def test_raft_stereo_oracle_512x1024_shape_slice():
     """A wider pair (W/4 = 96 > one lookup tile, 8 iterations) against the same model run on CPU with the oracle
     CorrBlock1D."""
