@@ -22,9 +22,11 @@
 // Input channels beyond one K-chunk (64, or 32 for stride 2) are handled by the host as K-split passes that
 // chain through an fp32 partial buffer; output channels whose weight tiles do not fit in smem as N-split passes.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane, also owns
-// TMEM alloc/dealloc), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Pipelines:
-// plane ring (full/empty mbarriers, released by tcgen05.commit) and a 2-deep TMEM accumulator ring.
+// Persistent CTAs (one per SM) stride over the work items.  Warp roles (352 threads): warp 0 = TMA producer, warps 1-2 =
+// MMA issuers (one elected lane each, alternate accumulator rounds, issuer i owns TMEM buffer i; warp 1 also owns TMEM
+// alloc/dealloc), warps 3..10 = epilogue in two groups (TMEM lane quarter = warp_id % 4).  Pipelines: plane ring with
+// per-plane full/empty mbarriers (released by tcgen05.commit right after a plane's last use) and the 2-deep TMEM
+// accumulator ring.  What shaped the issue path is measured in profiles/umma_issue_r01.md.
 #include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>

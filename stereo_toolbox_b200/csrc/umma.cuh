@@ -45,10 +45,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("trap;");
 }
 
-// Waiting without hammering shared memory: a spinning mbarrier.try_wait from every lane of several warps competes with
-// the tensor core's operand fetch for the shared-memory pipeline (measured on B200: 8 polling epilogue warps halved the
-// tcgen05.mma rate of the conv kernel, 120 vs 56 clk per N=96 MMA).  One lane polls with a short sleep between
-// attempts, the rest of the warp parks on __syncwarp.
+// Waits used by warps that do not sit on the MMA critical path.  (A sleeping back-off was tried for the epilogue: it does
+// not change the tcgen05.mma rate -- the issue rate is bounded elsewhere, see profiles/umma_issue_r01.md -- but
+// __nanosleep's granularity added 0.3-2K clk to every accumulator hand-over, so the epilogue spins; only the TMA
+// producer, which runs many planes ahead, sleeps between polls.)
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -59,8 +59,9 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     }
     asm volatile("trap;");
 }
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, uint32_t ns = 32) {
-    if ((threadIdx.x & 31) == 0) mbar_wait_backoff(bar, parity, ns);
+// One lane polls, the rest of the warp parks on __syncwarp.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
     __syncwarp();
 }
 
