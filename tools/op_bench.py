@@ -146,6 +146,43 @@ def main():
             return ops.concat_volume(l, r, Dm, False, att_prob=p)
         bn.run("acv_softmax_concat_unmasked", acv, 4.0 * (2 * l.numel() + 3 * att.numel() + 64 * Dm * Hm * Wm),
                note="M: softmax_D(att) * concat variant B, C=32, fp32 NCDHW")
+    # ---- IGEV / CFNet elementwise pieces (M shape) and the training adjoints (S-crop shape 384x512 -> 96x128, D/4=48)
+    if want("gate"):
+        Hm, Wm, Dm = 288, 480, 64
+        vol = rn(1, 16, Dm, Hm, Wm)
+        gl = rn(1, 16, Hm, Wm)
+        bn.run("feature_gate_f32", lambda: ops.feature_gate(vol, gl), 4.0 * (2 * vol.numel() + gl.numel()),
+               note="M: IGEV FeatureAtt gate, 16 ch at 1/4 res")
+        prob = torch.softmax(rn(2, 192, 384, 512), 1)
+        dsp = ops.disparity_regression(prob, 192).unsqueeze(1)
+        bn.run("disparity_variance", lambda: ops.disparity_variance(prob, 192, dsp), 4.0 * (prob.numel() + 2 * dsp.numel()),
+               note="CFNet variance over a full-res probability volume, B=2 384x512")
+        del vol, gl, prob, dsp
+    if want("train"):
+        from stereo_toolbox_b200 import _lib
+        from stereo_toolbox_b200.ops import _p, _stream
+        Bt, Ht, Wt, Dt = 2, 96, 128, 48
+        x, gy = rn(Bt, 32, Dt, Ht, Wt), rn(Bt, 32, Dt, Ht, Wt)
+        dw = torch.zeros(3, 3, 3, 32, 32, device="cuda")
+
+        def wgrad():
+            dw.zero_()
+            _lib.call("stb_conv3d_wgrad_f32", _p(x), _p(gy), _p(dw), Bt, 32, Dt, Ht, Wt, 32, Dt, Ht, Wt, 3, 1, 1, _stream())
+        bn.run("conv3d_wgrad_f32_32x32_k3", wgrad, 4.0 * (x.numel() + gy.numel()), flops=2.0 * 27 * 32 * 32 * Bt * Dt * Ht * Wt,
+               note="weight gradient of a 32->32 k3 s1 layer, B=2 crop shape (fp32 FMA bound)")
+        gvol = rn(Bt, 64, Dt, Ht, Wt)
+        gl_, gr_ = torch.empty(Bt, 32, Ht, Wt, device="cuda"), torch.empty(Bt, 32, Ht, Wt, device="cuda")
+        bn.run("concat_volume_bwd", lambda: _lib.call("stb_concat_volume_bwd_f32", _p(gvol), _p(gl_), _p(gr_), Bt, 32, Ht, Wt, Dt,
+                                                      1, 64, 0, _stream()),
+               4.0 * (gvol.numel() + 2 * gl_.numel()), note="adjoint of the PSMNet concat volume, B=2 crop shape")
+        cost, gd = rn(Bt, Dt, Ht, Wt), rn(Bt, 384, 512)
+        gc = torch.zeros_like(cost)
+
+        def head_bwd():
+            gc.zero_()
+            _lib.call("stb_upsample_softargmin_bwd_f32", _p(cost), _p(gd), _p(gc), Bt, Dt, Ht, Wt, 192, 384, 512, 0, _stream())
+        bn.run("upsample_softargmin_bwd", head_bwd, 4.0 * (2 * cost.numel() + gd.numel()),
+               note="adjoint of the fused head, B=2 384x512 (MUFU + atomics bound)")
     if a.json and not bn.ncu:
         os.makedirs(os.path.dirname(a.json) or ".", exist_ok=True)
         json.dump({"peaks": peaks(), "rows": bn.rows}, open(a.json, "w"), indent=1)
