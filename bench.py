@@ -339,8 +339,16 @@ class KernelProfiler:
         if fam.startswith("conv"):
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            # DRAM traffic per bracketed layer call, from the committed ncu pass over one timed step of this command
+            # (profiles/ncu_launches_r01.txt, session-3 table: 87 conv3d_umma launches of the 30 aggregation layers moved
+            # 25.60 GB read + 10.32 GB written; algorithmic bytes of the same layers: see `kernels.conv3d_umma.gbs`).
+            # Only valid for the default workload (batch 8, 16-bit path); null otherwise.
+            traffic = None
+            if fam == "conv3d_umma" and v["n"] % 30 == 0 and abs(v["bytes"] / v["n"] - 873e6) < 0.05 * 873e6:
+                traffic = (25.60e9 + 10.32e9) / 30.0
             return {"kernel": fam, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None,
+                    "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per layer call (dram read+write, ncu)",
+                    "algorithmic_bytes_per_call": v["bytes"] / v["n"],
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                     "note": "fp32 CUDA-core path has no tensor-pipe work; frac is against the bf16 tensor peak"
                     if precision == "fp32" else f"{precision} tcgen05 path (kind::f16 has one rate for bf16 and fp16)",
