@@ -384,6 +384,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         tmem_ld_32x32(taddr + (uint32_t)Cn, v1);
                         tmem_ld_32x32(taddr + (uint32_t)(2 * Cn), v2);
                         tmem_ld_wait();
+                        if (trace && item == egroup && c0 == 0) trace_buf[ground * 8 + 6] = clock64();     // TMEM data in registers
                         if (item + 2 >= items && c0 + 32 >= Cn) {
                             tc_fence_before();
                             __syncwarp();
@@ -444,6 +445,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         }
 #pragma unroll
                         for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], ACT);
+                        if (trace && item == egroup && c0 == 0) trace_buf[ground * 8 + 7] = clock64();     // arithmetic done, stores next
                         if (a.out_fp32) {
                             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + eoff);
 #pragma unroll

@@ -9,15 +9,26 @@ namespace {
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 
-// x, out [B,C,D,H,W] fp32; gate [B,C,H,W] fp32 logits.  One thread per 4 consecutive w (scalar tail).
+// x, out [B,C,D,H,W] fp32; gate [B,C,H,W] fp32 logits.  blockIdx.x = (b*C + c)*D + d (one volume plane), blockIdx.y strides
+// over the plane: no per-element index decode, float4 accesses when the plane size allows.
 __global__ void gate_f32_kernel(const float* __restrict__ x, const float* __restrict__ gate, float* __restrict__ out,
-                                int C, int D, int H, int W, long long total) {
-    const long long hw = (long long)H * W;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i % hw;              // (h, w)
-        const long long bcd = i / hw;            // (b*C + c)*D + d
-        const long long bc = bcd / D;
-        out[i] = x[i] * sigmoidf_(__ldg(gate + bc * hw + p));
+                                int D, long long hw) {
+    const long long plane = blockIdx.x;
+    const long long bc = plane / D;
+    const float* xp = x + plane * hw;
+    float* op = out + plane * hw;
+    const float* gp = gate + bc * hw;
+    if ((hw & 3) == 0) {
+        const long long n4 = hw >> 2;
+        for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.y * blockDim.x) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xp) + i);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gp) + i);
+            reinterpret_cast<float4*>(op)[i] = make_float4(v.x * sigmoidf_(g.x), v.y * sigmoidf_(g.y), v.z * sigmoidf_(g.z),
+                                                           v.w * sigmoidf_(g.w));
+        }
+    } else {
+        for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.y * blockDim.x)
+            op[i] = xp[i] * sigmoidf_(__ldg(gp + i));
     }
 }
 
@@ -76,8 +87,11 @@ inline unsigned grid_for(long long total, int threads) {
 extern "C" int stb_feature_gate_f32(const float* x, const float* gate, float* out, int B, int C, int D, int H, int W,
                                     void* stream) {
     if (!x || !gate || !out || B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return STB_E_BADARG;
-    const long long total = (long long)B * C * D * H * W;
-    gate_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, gate, out, C, D, H, W, total);
+    const long long planes = (long long)B * C * D, hw = (long long)H * W;
+    if (planes > 2147483647LL) return STB_E_BADARG;
+    long long gy = (hw / 4 + 255) / 256;
+    gy = gy < 1 ? 1 : (gy > 64 ? 64 : gy);
+    gate_f32_kernel<<<dim3((unsigned)planes, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(x, gate, out, D, hw);
     STB_CHECK_LAUNCH();
     return STB_OK;
 }

@@ -29,10 +29,11 @@ torch.cuda.synchronize()
 _lib.check(_lib.lib().stb_conv3d_umma_set_trace(ctypes.c_void_p(0), 0), "set_trace")
 t = buf.cpu()
 print(f"layer {cin}->{cout} k{k} on [{B},{D},{H},{W}]: {e0.elapsed_time(e1) * 1e3:.1f} us")
-print("round   step_top  wait_tmem  wait_plane0  issue_len  (in MMA blocks)  commit->epi_wake  epi_len   (clocks; step_top relative to round 0)")
+print("round   step_top  wait_tmem  wait_plane0  issue_len  commit->epi_wake  epi: tmem_ld  math  stores+rest   (clocks; step_top relative to round 0)")
 t0 = int(t[0, 0])
 for r in range(R):
     top, tmem, start, commit, wake, end = (int(v) for v in t[r][:6])
     if top == 0:
         break
-    print(f"{r:5d} {top - t0:10d} {tmem - top:10d} {start - tmem:12d} {commit - start:10d} {int(t[r][6]):14d} {wake - commit:17d} {end - wake:8d}")
+    ld, mt = int(t[r][6]), int(t[r][7])
+    print(f"{r:5d} {top - t0:10d} {tmem - top:10d} {start - tmem:12d} {commit - start:10d} {wake - commit:17d} {ld - wake:12d} {mt - ld:6d} {end - mt:10d}")
