@@ -17,9 +17,14 @@ gwc_volume_kernel(const float* __restrict__ left, const float* __restrict__ righ
     extern __shared__ __align__(16) float smem[];
     const int h = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
     const int Wp = (W + 3) & ~3;            // padded row pitch for L
-    const int Rp = Wp + D;                  // R rows carry D leading zeros (the w<d region)
+    const int Rl = Wp + D;                  // logical R row: D leading zeros (the w<d region) + the feature row
+    // R rows are stored SKEWED: logical index x lives at x + (x >> 5).  A lane owns 4 consecutive w, so the lanes of a
+    // warp read logical indices 16 bytes apart: unskewed that is a 4-way bank conflict on every sliding-window load
+    // (8 per depth step -- the shared-memory pipe, not HBM, bounded the kernel at 0.37 of the roofline).
+    const int Rp = Rl + (Rl >> 5) + 1;
     float* Ls = smem;                       // [CPG][Wp]
-    float* Rs = smem + CPG * Wp;            // [CPG][Rp]
+    float* Rs = smem + CPG * Wp;            // [CPG][Rp] skewed
+#define RSK(x) ((x) + ((x) >> 5))
     const size_t plane = (size_t)H * W;
     const float* lsrc = left + ((size_t)b * C + (size_t)g * CPG) * plane + (size_t)h * W;
     const float* rsrc = right + ((size_t)b * C + (size_t)g * CPG) * plane + (size_t)h * W;
@@ -27,9 +32,9 @@ gwc_volume_kernel(const float* __restrict__ left, const float* __restrict__ righ
         int c = i / Wp, w = i - c * Wp;
         Ls[i] = (w < W) ? __ldg(lsrc + (size_t)c * plane + w) : 0.f;
     }
-    for (int i = threadIdx.x; i < CPG * Rp; i += GWC_THREADS) {
-        int c = i / Rp, w = i - c * Rp - D;
-        Rs[i] = (w >= 0 && w < W) ? __ldg(rsrc + (size_t)c * plane + w) : 0.f;
+    for (int i = threadIdx.x; i < CPG * Rl; i += GWC_THREADS) {
+        int c = i / Rl, x = i - c * Rl, w = x - D;
+        Rs[c * Rp + RSK(x)] = (w >= 0 && w < W) ? __ldg(rsrc + (size_t)c * plane + w) : 0.f;
     }
     __syncthreads();
 
@@ -53,7 +58,7 @@ gwc_volume_kernel(const float* __restrict__ left, const float* __restrict__ righ
 #pragma unroll
             for (int c = 0; c < CPG; ++c)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) r[c][j] = Rs[c * Rp + D + w0 + j - d_lo];
+                for (int j = 0; j < 4; ++j) r[c][j] = Rs[c * Rp + RSK(D + w0 + j - d_lo)];
         }
         for (int d = d_lo; d < d_hi; ++d) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -74,12 +79,14 @@ gwc_volume_kernel(const float* __restrict__ left, const float* __restrict__ righ
 #pragma unroll
                 for (int c = 0; c < CPG; ++c) {
                     r[c][3] = r[c][2]; r[c][2] = r[c][1]; r[c][1] = r[c][0];
-                    r[c][0] = Rs[c * Rp + D + w0 - (d + 1)];
+                    r[c][0] = Rs[c * Rp + RSK(D + w0 - (d + 1))];
                 }
             }
         }
     }
 }
+
+#undef RSK
 
 // concat volume: grid (H, C, B); each CTA copies one left row and one (shifted) right row into D planes.
 __global__ void __launch_bounds__(128)
@@ -142,7 +149,8 @@ template <int CPG>
 int launch_gwc(const float* l, const float* r, float* v, int B, int C, int H, int W, int D, int G,
                int c_total, int c_off, cudaStream_t st) {
     const int Wp = (W + 3) & ~3;
-    size_t smem = (size_t)(CPG * Wp + CPG * (Wp + D)) * sizeof(float);
+    const int Rl = Wp + D;
+    size_t smem = (size_t)(CPG * Wp + CPG * (Rl + (Rl >> 5) + 1)) * sizeof(float);       // skewed R rows, see the kernel
     if (smem > 200 * 1024) return STB_E_SMEM;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(gwc_volume_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
