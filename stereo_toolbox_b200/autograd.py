@@ -71,6 +71,33 @@ def conv3d(x, conv: torch.nn.Module):
                            conv.output_padding[0] if tr else 0)
 
 
+def concat_volume_backward(gvol, shape, maxdisp, mask_left):
+    B, C, H, W = shape
+    gvol = _f32c(gvol)
+    gl = torch.empty(B, C, H, W, device=gvol.device, dtype=torch.float32)
+    gr = torch.empty_like(gl)
+    _lib.call("stb_concat_volume_bwd_f32", _p(gvol), _p(gl), _p(gr), B, C, H, W, maxdisp, int(mask_left), 2 * C, 0, _stream())
+    return gl, gr
+
+
+def gwc_volume_backward(gvol, left, right, maxdisp, groups):
+    B, C, H, W = left.shape
+    gvol, left, right = _f32c(gvol), _f32c(left), _f32c(right)
+    gl, gr = torch.empty_like(left), torch.empty_like(right)
+    _lib.call("stb_gwc_volume_bwd_f32", _p(gvol), _p(left), _p(right), _p(gl), _p(gr), B, C, H, W, maxdisp, groups,
+              groups, 0, _stream())
+    return gl, gr
+
+
+def upsample_softargmin_backward(gdisp, cost4, maxdisp, out_h, out_w, align_corners):
+    B, D, H, W = cost4.shape
+    gdisp, cost4 = _f32c(gdisp), _f32c(cost4)
+    gcost = torch.zeros_like(cost4)
+    _lib.call("stb_upsample_softargmin_bwd_f32", _p(cost4), _p(gdisp), _p(gcost), B, D, H, W, maxdisp, out_h, out_w,
+              int(align_corners), _stream())
+    return gcost
+
+
 class _ConcatVolumeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, left, right, maxdisp, mask_left):
@@ -79,11 +106,8 @@ class _ConcatVolumeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gvol):
-        maxdisp, mask_left, (B, C, H, W) = ctx.cfg
-        gvol = _f32c(gvol)
-        gl = torch.empty(B, C, H, W, device=gvol.device, dtype=torch.float32)
-        gr = torch.empty_like(gl)
-        _lib.call("stb_concat_volume_bwd_f32", _p(gvol), _p(gl), _p(gr), B, C, H, W, maxdisp, int(mask_left), 2 * C, 0, _stream())
+        maxdisp, mask_left, shape = ctx.cfg
+        gl, gr = concat_volume_backward(gvol, shape, maxdisp, mask_left)
         return gl, gr, None, None
 
 
@@ -103,11 +127,7 @@ class _GwcVolumeFn(torch.autograd.Function):
     def backward(ctx, gvol):
         left, right = ctx.saved_tensors
         maxdisp, groups = ctx.cfg
-        B, C, H, W = left.shape
-        gvol = _f32c(gvol)
-        gl, gr = torch.empty_like(left), torch.empty_like(right)
-        _lib.call("stb_gwc_volume_bwd_f32", _p(gvol), _p(left), _p(right), _p(gl), _p(gr), B, C, H, W, maxdisp, groups,
-                  groups, 0, _stream())
+        gl, gr = gwc_volume_backward(gvol, left, right, maxdisp, groups)
         return gl, gr, None, None
 
 
@@ -134,11 +154,7 @@ class _HeadFn(torch.autograd.Function):
     def backward(ctx, gdisp):
         (cost4,) = ctx.saved_tensors
         maxdisp, out_h, out_w, align = ctx.cfg
-        B, D, H, W = cost4.shape
-        gdisp = _f32c(gdisp)
-        gcost = torch.zeros_like(cost4)
-        _lib.call("stb_upsample_softargmin_bwd_f32", _p(cost4), _p(gdisp), _p(gcost), B, D, H, W, maxdisp, out_h, out_w,
-                  int(align), _stream())
+        gcost = upsample_softargmin_backward(gdisp, cost4, maxdisp, out_h, out_w, align)
         return (gcost.unsqueeze(1) if ctx.squeeze else gcost), None, None, None, None
 
 

@@ -405,4 +405,41 @@ def register_torch_ops():
     lib.impl("conv3d_bn_act", _conv_meta, "Meta")
     lib.impl("corr1d", lambda a, b, s: a.new_empty(a.shape[0], a.shape[2], a.shape[3], b.shape[3]), "Meta")
     lib.impl("corr1d_lookup", lambda p, c, r, n: c.new_empty(c.shape[0], n * (2 * r + 1), c.shape[2], c.shape[3]), "Meta")
+    # autograd formulas (torch.library.register_autograd): the dispatcher ops are differentiable like the reference's
+    # functions; the adjoints are the kernels of csrc/train.cu (see autograd.py)
+    from . import autograd as A
+
+    def _gwc_setup(ctx, inputs, output):
+        l, r, d, g = inputs
+        ctx.save_for_backward(l, r)
+        ctx.cfg = (d, g)
+
+    def _gwc_bwd(ctx, gv):
+        l, r = ctx.saved_tensors
+        gl, gr = A.gwc_volume_backward(gv, l, r, *ctx.cfg)
+        return gl, gr, None, None
+
+    def _cat_setup(ctx, inputs, output):
+        l, r, d, m = inputs
+        ctx.cfg = (tuple(l.shape), d, m)
+
+    def _cat_bwd(ctx, gv):
+        shape, d, m = ctx.cfg
+        gl, gr = A.concat_volume_backward(gv, shape, d, m)
+        return gl, gr, None, None
+
+    def _head_setup(ctx, inputs, output):
+        c, d, h, w, a = inputs
+        ctx.save_for_backward(c)
+        ctx.cfg = (d, h, w, a)
+
+    def _head_bwd(ctx, gd):
+        (c,) = ctx.saved_tensors
+        c4 = c[:, 0] if c.dim() == 5 else c
+        g = A.upsample_softargmin_backward(gd, c4, *ctx.cfg)
+        return (g.unsqueeze(1) if c.dim() == 5 else g), None, None, None, None
+
+    torch.library.register_autograd("stb200::gwc_volume", _gwc_bwd, setup_context=_gwc_setup, lib=lib)
+    torch.library.register_autograd("stb200::concat_volume", _cat_bwd, setup_context=_cat_setup, lib=lib)
+    torch.library.register_autograd("stb200::upsample_softargmin", _head_bwd, setup_context=_head_setup, lib=lib)
     register_torch_ops._lib = lib   # keep alive
