@@ -104,6 +104,14 @@ int stb_volume_cl16(const float* gwc_l, const float* gwc_r, const float* cat_l, 
                     void* vol, int f16, int B, int Cg, int G, int Cc, int H, int W, int D, int Ct_pad,
                     int mask_left, void* stream);
 
+/* Same volume from CHANNELS-LAST 16-bit features, as the tensor-core extractor produces them: feats[i] is
+ * [2B][H][W][feat_ch[i]] (left = image b, right = image B+b; the channels of the nfeat <= 4 tensors concatenate to the
+ * 8*G correlation channels -- GwcNet's layer2/3/4 outputs, no torch.cat), cat [2B][H][W][cat_c] holds the Cc concat
+ * channels (nullable when Cc = 0).  feats / feat_ch are HOST arrays.  Saves the NCHW fp32 copies of the features. */
+int stb_volume_cl16_from_cl16(const void* const* feats, const int* feat_ch, int nfeat, const void* cat, int cat_c,
+                              void* vol, int f16, int B, int G, int Cc, int H, int W, int D, int Ct_pad,
+                              int mask_left, void* stream);
+
 /* Layout boundary helpers: [B,C,S] fp32 <-> [B,S,Cpad] 16-bit (S = D*H*W). */
 int stb_ncdhw_to_cl16(const float* src, void* dst, int f16, int B, int C, long long S, int Cpad, void* stream);
 int stb_cl16_to_ncdhw(const void* src, float* dst, int f16, int B, int C, long long S, int Cpad, void* stream);

@@ -33,6 +33,7 @@ SIGNATURES = {
     "stb_disparity_regression_f32": [_P, _P, _I, _I, _LL, _P],
     "stb_conv3d_taps_f32": [_P, _P, _P, _P, _P] + [_I] * 10 + [_IP, _IP, _IP] + [_I] * 9 + [_P],
     "stb_volume_cl16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "stb_volume_cl16_from_cl16": [_PP, _IP, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "stb_ncdhw_to_cl16": [_P, _P, _I, _I, _I, _LL, _I, _P],
     "stb_cl16_to_ncdhw": [_P, _P, _I, _I, _I, _LL, _I, _P],
     "stb_conv3d_umma": [_P, _P, _P, _P, _P, _P] + [_I] * 13 + [_IP, _IP, _IP, _IP, _IP, _IP, _IP, _I, _I, _IP, _IP, _IP, _IP, _IP]

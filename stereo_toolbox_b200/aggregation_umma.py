@@ -237,6 +237,23 @@ class UmmaBackend:
                       cc, H, W, maxdisp4, ct_pad, 1, _stream())
         return vol
 
+    def volume_from_cl(self, cl, maxdisp4, groups):
+        """gwc (+ concat) volume straight from the tensor-core extractor's channels-last 16-bit outputs
+        (features_umma.UmmaGwcFeatures, ``cl`` = {feats: [[1,2B,h,w,C_i], ...], cat: [1,2B,h,w,Cc_pad] or None, B, cc}):
+        no NCHW fp32 copy of the 320-channel feature and no torch.cat of layer2/3/4."""
+        feats, cat, B, cc = cl["feats"], cl["cat"], cl["B"], cl["cc"]
+        _, N, H, W, _ = feats[0].shape
+        assert N == 2 * B and all(f.dtype == self.dtype and f.is_contiguous() for f in feats)
+        ct_pad = pad_channels(groups + 2 * cc)
+        vol = torch.empty(B, maxdisp4, H, W, ct_pad, device=feats[0].device, dtype=self.dtype)
+        ptrs = (ctypes.c_void_p * len(feats))(*[f.data_ptr() for f in feats])
+        chs = _iarr([f.shape[-1] for f in feats])
+        nbytes = 2.0 * (sum(f.numel() for f in feats) + (0 if cat is None else cat.numel()) + vol.numel())
+        with self.prof.bracket("volume_cl16", 0.0, nbytes):
+            _lib.call("stb_volume_cl16_from_cl16", ptrs, chs, len(feats), _p(cat), 0 if cat is None else cat.shape[-1],
+                      _p(vol), self.f16, B, groups, cc, H, W, maxdisp4, ct_pad, 1, _stream())
+        return vol
+
     def volume_concat(self, l, r, maxdisp4, mask_left=True, att_prob=None):
         if att_prob is not None:
             raise NotImplementedError("attention-weighted concat volume is only built on the fp32 path yet")

@@ -5,6 +5,7 @@
 // Products and the group mean are fp32; only the stored value is rounded to bf16.
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace {
@@ -155,11 +156,32 @@ __device__ __forceinline__ void vcl_cp16(float* dst_smem, const float* src, bool
                  : "memory");
 }
 
-template <int CPG, bool CACHE_L>
+// Channels-last 16-bit feature sources (CLSRC): the tensor-core extractor's own outputs [2B][H][W][C_i] (left = image b,
+// right = image B + b) are read directly -- no NCHW fp32 copy of the 320-channel feature, no torch.cat of layer2/3/4.
+struct ClSrc {
+    const uint16_t* f[4];     // up to 4 source tensors whose channels concatenate to the Cg correlation channels
+    int c[4], c0[4];          // channels of tensor i, first concatenated channel it holds (multiples of 8)
+    int n;
+    const uint16_t* cat;      // concat feature [2B][H][W][cat_c] (Cc real channels), nullable
+    int cat_c, Bn;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& q, int f16, float (&v)[8]) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t;
+        if (f16) t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        else t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        v[2 * i] = t.x; v[2 * i + 1] = t.y;
+    }
+}
+
+template <int CPG, bool CACHE_L, bool CLSRC>
 __global__ void __launch_bounds__(256, 2)
 volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, const float* __restrict__ cl,
                   const float* __restrict__ cr, uint16_t* __restrict__ vol, int Cg, int G, int Cc, int H, int W,
-                  int D, int Ct_pad, int mask_left, int f16) {
+                  int D, int Ct_pad, int mask_left, int f16, const ClSrc cs) {
     extern __shared__ __align__(16) float sm[];
     const int E = (D + 3) >> 2, D4 = E * 4, RP = D4 + V2_TW;
     constexpr int NR = 16 * CPG;
@@ -180,7 +202,59 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
         // rows of the group in flight at once -- the scalar LDG->STS loop of the first v2 draft exposed one global
         // latency per row (ncu: 47 % of the stall samples on the staging STS, long scoreboard).
         const bool vec = (W & 3) == 0;
-        for (int r = warp; r < NR; r += 8) {
+        if (CLSRC) {
+            // one 16-byte load = the 8 channels of one correlation group at one voxel; scattered (as fp32) to the 8 source
+            // rows of that group.  Loads of a batch are issued before the first store.
+            static_assert(!CLSRC || CPG == 8, "channels-last sources: 8 channels per group");
+            const int span = V2_TW + RP, total = 16 * span;
+            for (int i0 = threadIdx.x; i0 < total; i0 += 256 * 4) {
+                uint4 q[4];
+                int kind_[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 256;
+                    q[u] = make_uint4(0, 0, 0, 0);
+                    kind_[u] = -1;
+                    if (i >= total) continue;
+                    const int ol = i / span, x = i - ol * span, o = oc0 + ol;
+                    const bool isL = x < V2_TW;
+                    const int ww = isL ? w0 + x : w0 - D4 + (x - V2_TW);
+                    const bool ok = ww >= 0 && ww < W;
+                    const size_t vox = ((size_t)(isL ? b : cs.Bn + b) * H + h) * W + (ok ? ww : 0);
+                    if (o < G) {
+                        kind_[u] = 0;
+                        if (ok) {
+                            const int ch0 = o * 8;
+                            int t = 0;
+#pragma unroll
+                            for (int k = 1; k < 4; ++k) t = (k < cs.n && ch0 >= cs.c0[k]) ? k : t;
+                            q[u] = __ldg(reinterpret_cast<const uint4*>(cs.f[t] + vox * cs.c[t] + (ch0 - cs.c0[t])));
+                        }
+                    } else if (o < G + Cc ? isL : (o < G + 2 * Cc && !isL)) {
+                        kind_[u] = 1;
+                        if (ok) q[u].x = __ldg(cs.cat + vox * cs.cat_c + (o < G + Cc ? o - G : o - G - Cc));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 256;
+                    if (kind_[u] < 0) continue;
+                    const int ol = i / span, x = i - ol * span;
+                    const bool isL = x < V2_TW;
+                    float* dst = isL ? Ls + (size_t)(ol * CPG) * V2_TW + x : Rs + (size_t)(ol * CPG) * RP + (x - V2_TW);
+                    const int pitch = isL ? V2_TW : RP;
+                    if (kind_[u] == 0) {
+                        float v[8];
+                        unpack8(q[u], f16, v);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) dst[c * pitch] = v[c];
+                    } else {
+                        dst[0] = ld16((uint16_t)q[u].x, f16);
+                    }
+                }
+            }
+        }
+        for (int r = warp; r < NR && !CLSRC; r += 8) {
             const int ol = r / CPG, c = r - ol * CPG, o = oc0 + ol;
             const float* lsrc = nullptr;
             const float* rsrc = nullptr;
@@ -332,6 +406,23 @@ __global__ void ncdhw_to_cl_kernel(const float* __restrict__ src, uint16_t* __re
     }
 }
 
+// Few input channels (the RGB image padded to 16): one thread per position gathers its C planes (coalesced along S)
+// and writes one Cpad-channel row; the 32x32 tile transpose above would move 32 channel rows to use 3 of them.
+template <int CPAD>
+__global__ void ncdhw_to_cl_small_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C, size_t S, int f16) {
+    const int b = blockIdx.y;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (size_t)gridDim.x * blockDim.x) {
+        float v[CPAD];
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) v[c] = c < C ? __ldg(src + ((size_t)b * C + c) * S + s) : 0.f;
+        uint4* o = reinterpret_cast<uint4*>(dst + ((size_t)b * S + s) * CPAD);
+#pragma unroll
+        for (int i = 0; i < CPAD / 8; ++i)
+            o[i] = make_uint4(pk16(v[8 * i], v[8 * i + 1], f16), pk16(v[8 * i + 2], v[8 * i + 3], f16),
+                              pk16(v[8 * i + 4], v[8 * i + 5], f16), pk16(v[8 * i + 6], v[8 * i + 7], f16));
+    }
+}
+
 __global__ void cl_to_ncdhw_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, int C, size_t S,
                                    int Cpad, int f16) {
     __shared__ float tile[32][33];
@@ -385,10 +476,10 @@ extern "C" int stb_volume_cl16(const float* gwc_l, const float* gwc_r, const flo
         dim3 grid2(stb_ceil_div(W, V2_TW), H, B);
 #define STB_VOL2_LAUNCH(K, CL)                                                                                      \
     do {                                                                                                           \
-        cudaFuncSetAttribute(volume_cl2_kernel<K, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);    \
-        volume_cl2_kernel<K, CL><<<grid2, 256, smem2, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r,           \
+        cudaFuncSetAttribute(volume_cl2_kernel<K, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+        volume_cl2_kernel<K, CL, false><<<grid2, 256, smem2, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r,    \
                                                                             (uint16_t*)vol, Cg, G, Cc, H, W, D,   \
-                                                                            Ct_pad, mask_left, f16);              \
+                                                                            Ct_pad, mask_left, f16, ClSrc());     \
         STB_CHECK_LAUNCH();                                                                                        \
         return STB_OK;                                                                                             \
     } while (0)
@@ -406,8 +497,50 @@ extern "C" int stb_volume_cl16(const float* gwc_l, const float* gwc_r, const flo
     return STB_OK;
 }
 
+extern "C" int stb_volume_cl16_from_cl16(const void* const* feats, const int* feat_ch, int nfeat, const void* cat, int cat_c,
+                                         void* vol, int f16, int B, int G, int Cc, int H, int W, int D, int Ct_pad,
+                                         int mask_left, void* stream) {
+    if (!feats || !feat_ch || nfeat < 1 || nfeat > 4 || !vol || B <= 0 || H <= 0 || W <= 0 || D <= 0 || G <= 0 || Cc < 0)
+        return STB_E_BADARG;
+    if (Cc > 0 && (!cat || cat_c < Cc)) return STB_E_BADARG;
+    ClSrc cs;
+    memset(&cs, 0, sizeof(cs));
+    int ctot = 0;
+    for (int i = 0; i < nfeat; ++i) {
+        if (!feats[i] || feat_ch[i] <= 0 || feat_ch[i] % 8) return STB_E_UNSUPPORTED;
+        cs.f[i] = (const uint16_t*)feats[i];
+        cs.c[i] = feat_ch[i];
+        cs.c0[i] = ctot;
+        ctot += feat_ch[i];
+    }
+    cs.n = nfeat;
+    cs.cat = (const uint16_t*)cat;
+    cs.cat_c = cat_c;
+    cs.Bn = B;
+    if (ctot != 8 * G) return STB_E_UNSUPPORTED;              // 8 channels per correlation group (GwcNet / ACVNet / PCWNet)
+    const int Ct = G + 2 * Cc;
+    if (Ct_pad < Ct || Ct_pad % 16 || G % 8) return STB_E_UNSUPPORTED;
+    if (H > 65535 || B > 65535) return STB_E_BADARG;
+    const int E = (D + 3) / 4, RP = 4 * E + V2_TW;
+    const size_t smem2 = (size_t)16 * 8 * (V2_TW + RP) * sizeof(float) + (size_t)V2_DP * V2_TW * 9 * sizeof(uint32_t);
+    if (smem2 > 200 * 1024) return STB_E_SMEM;
+    cudaFuncSetAttribute(volume_cl2_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    dim3 grid2(stb_ceil_div(W, V2_TW), H, B);
+    volume_cl2_kernel<8, true, true><<<grid2, 256, smem2, (cudaStream_t)stream>>>(nullptr, nullptr, nullptr, nullptr, (uint16_t*)vol,
+                                                                                8 * G, G, Cc, H, W, D, Ct_pad, mask_left, f16, cs);
+    STB_CHECK_LAUNCH();
+    return STB_OK;
+}
+
 extern "C" int stb_ncdhw_to_cl16(const float* src, void* dst, int f16, int B, int C, long long S, int Cpad, void* stream) {
     if (!src || !dst || B <= 0 || C <= 0 || S <= 0 || Cpad < C) return STB_E_BADARG;
+    if (C <= 8 && Cpad == 16 && B <= 65535) {
+        long long gx = (S + 255) / 256;
+        if (gx > 148 * 8) gx = 148 * 8;
+        ncdhw_to_cl_small_kernel<16><<<dim3((unsigned)gx, B), 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, C, (size_t)S, f16);
+        STB_CHECK_LAUNCH();
+        return STB_OK;
+    }
     dim3 grid((unsigned)((S + 31) / 32), stb_ceil_div(Cpad, 32), B);
     ncdhw_to_cl_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, C, (size_t)S, Cpad, f16);
     STB_CHECK_LAUNCH();

@@ -114,6 +114,11 @@ class UmmaGwcFeatures:
     def _convbn(self, seq, x, act="none", residual=None):
         return self.conv(seq[0], seq[1], x, act, residual)
 
+    def _convbn_multi(self, seq, xs, act="none"):
+        """convbn on the channel concatenation of ``xs`` (the 320-channel lastconv input).  The conv kernel takes one
+        input tensor, so the pieces are concatenated here (a 16-bit copy; the fp32 NCHW copy is what is saved)."""
+        return self.conv(seq[0], seq[1], torch.cat(xs, dim=-1), act)
+
     def _block(self, blk, x):
         """BasicBlock (GwcNet/submodule.py:66-91): conv1+BN+ReLU, conv2+BN, + shortcut (no ReLU after the add)."""
         y = self._convbn(blk.conv1[0], x, "relu")
@@ -121,7 +126,7 @@ class UmmaGwcFeatures:
         return self._convbn(blk.conv2, y, "none", residual=short)
 
     @torch.no_grad()
-    def __call__(self, fe, left, right, concat_head=None):
+    def __call__(self, fe, left, right, concat_head=None, channels_last_out=False):
         """fe: features2d.GwcFeatures; left/right [B,3,H,W] fp32.  Returns (feat_left, feat_right) dicts of NCHW fp32
         tensors like the reference feature_extraction (the layout the volume builder reads).  ``concat_head``:
         (convbn Sequential, 1x1 Conv2d) applied to the gwc feature -- GwcNet's own lastconv by default, ACVNet's
@@ -145,6 +150,21 @@ class UmmaGwcFeatures:
         l4 = l3
         for blk in fe.layer4:
             l4 = self._block(blk, l4)
+        if channels_last_out:
+            # hand the layer2/3/4 outputs (and the concat head's output) to the volume builder as they are
+            # (aggregation_umma.UmmaBackend.volume_from_cl): no torch.cat, no NCHW fp32 copy
+            cat, cc = None, 0
+            if concat_head is None and fe.concat_feature:
+                concat_head = (fe.lastconv[0], fe.lastconv[2])
+            if concat_head is not None:
+                y = self._convbn_multi(concat_head[0], (l2, l3, l4), "relu")
+                cat = self.conv(concat_head[1], None, y)
+                cc = cat.shape[-1]
+                if cc % 8:                                                     # the builder reads whole 16-bit elements
+                    pad = torch.zeros(cat.shape[:-1] + (8 - cc % 8,), device=cat.device, dtype=cat.dtype)
+                    cat = torch.cat((cat, pad), dim=-1)
+            cl = {"feats": [l2, l3, l4], "cat": cat, "B": B, "cc": cc}
+            return {"_cl": cl}, {"_cl": cl}
         gwc = torch.cat((l2, l3, l4), dim=-1)                             # [1,2B,h,w,320]
         _, N, h, w, _ = gwc.shape
         gwc_f = from_channels_last(gwc.view(N, h, w, 320))                # [2B,320,h,w] fp32

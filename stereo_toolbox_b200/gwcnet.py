@@ -6,6 +6,8 @@ three hourglasses, classif3, trilinear upsample + softmax + regression -- runs i
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -71,8 +73,11 @@ class GwcNet(nn.Module):
     def aggregate(self, fl, fr, height, width, be=None, all_heads=False):
         """The hot path: features -> disparity [B,H,W] (training: the reference's list of four)."""
         be = be or self._be
-        vol = be.volume_gwc_concat(fl["gwc_feature"], fr["gwc_feature"], fl.get("concat_feature"),
-                                   fr.get("concat_feature"), self.maxdisp // 4, self.num_groups)
+        if "_cl" in fl:        # tensor-core extractor handed over its channels-last outputs
+            vol = be.volume_from_cl(fl["_cl"], self.maxdisp // 4, self.num_groups)
+        else:
+            vol = be.volume_gwc_concat(fl["gwc_feature"], fr["gwc_feature"], fl.get("concat_feature"),
+                                       fr.get("concat_feature"), self.maxdisp // 4, self.num_groups)
         c = be.conv(self.dres0[0], vol, "relu")
         cost0 = be.conv(self.dres0[2], c, "relu")
         c = be.conv(self.dres1[0], cost0, "relu")
@@ -115,7 +120,8 @@ class GwcNet(nn.Module):
                     self._fe_umma = UmmaGwcFeatures(self._be.name)
                 with self._be.prof.bracket("features2d_umma", 0.0, 0.0):
                     head = (self.concatconv[0], self.concatconv[2]) if hasattr(self, "concatconv") else None
-                    return self._fe_umma(self.feature_extraction, left, right, concat_head=head)
+                    direct = type(self) is GwcNet and os.environ.get("STB_VOLUME_FROM_NCHW", "0") != "1"
+                    return self._fe_umma(self.feature_extraction, left, right, concat_head=head, channels_last_out=direct)
             with self._be.prof.bracket("torch_features2d", 0.0, 0.0):
                 if mode == "fp16":
                     with torch.autocast("cuda", dtype=torch.float16):
