@@ -75,6 +75,7 @@ struct UArgs {
     int cblocks;                     // accumulator column blocks (of Cn) per M-tile: 1, 3 (kw-merge) or 8 (merged transposed conv)
     int nclass_h, nclass_w;          // class output extents per step in h/w (positions)
     uint32_t plane_bytes, chunk_bytes, wtile_bytes, w_bytes_total, tmem_cols;
+    int kdepth;                      // > 0: the K-chunks of the input lie along a PSEUDO-depth axis (plane P = image*kdepth + chunk), 2-D convs
     uint32_t desc_hi;                // high word of every smem descriptor (SBO = 8 rows, version, swizzle mode)
     uint32_t smem_base;              // shared-window address of the 1024-aligned dynamic smem base (queried once per kernel instance)
     int debug;                       // timing experiments only (STB_UMMA_DEBUG): 1 = no TMA plane traffic, 2 = epilogue skips its work
@@ -230,9 +231,16 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     mbar_wait_backoff(&plane_empty[slot], eph, 64);
                     mbar_arrive_expect_tx(&plane_full[slot], (uint32_t)a.nsub * a.chunk_bytes);
                     uint8_t* dst = sP + (size_t)slot * a.plane_bytes;
-                    for (int sb = 0; sb < a.nsub; ++sb)       // sub-tile sb = (h parity, w parity) for stride 2
-                        tma_load_5d(dst + (size_t)sb * a.chunk_bytes, &tm_x, &plane_full[slot], a.cin_off,
-                                    iw0 + (sb & 1), ih0 + (sb >> 1), u.p_first + n, u.b);
+                    if (a.kdepth > 0) {
+                        // 2-D conv with Cin = kdepth K-chunks: pseudo-plane P = image*kdepth + chunk; the taps of chunk c
+                        // carry dz = c, so all chunks accumulate in TMEM inside one launch (no fp32 workspace round trip)
+                        const int P = u.p_first + n, img = P / a.kdepth, chunk = P - img * a.kdepth;
+                        tma_load_5d(dst, &tm_x, &plane_full[slot], chunk * (a.ROWB >> 1), iw0, ih0, img, u.b);
+                    } else {
+                        for (int sb = 0; sb < a.nsub; ++sb)       // sub-tile sb = (h parity, w parity) for stride 2
+                            tma_load_5d(dst + (size_t)sb * a.chunk_bytes, &tm_x, &plane_full[slot], a.cin_off,
+                                        iw0 + (sb & 1), ih0 + (sb >> 1), u.p_first + n, u.b);
+                    }
                     if (++slot == a.R) { slot = 0; eph ^= 1; }
                 }
             }
@@ -571,7 +579,9 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     if (Cin % KC) return STB_E_UNSUPPORTED;
     if (in_stride < 1 || in_stride > 2 || out_stride < 1 || out_stride > 2) return STB_E_UNSUPPORTED;
     if (in_stride == 2 && out_stride != 1) return STB_E_UNSUPPORTED;
-    const int nk = Cin / KC;                       // K-split passes
+    const int kdepth = (flags & 32) ? Cin / KC : 0; // flags bit5: K-chunks along a pseudo-depth axis, accumulated in TMEM (2-D convs)
+    if (kdepth && (!(flags & 16) || in_stride != 1 || out_stride != 1)) return STB_E_UNSUPPORTED;
+    const int nk = kdepth ? 1 : Cin / KC;          // K-split passes
     if (nk > 1 && !ws) return STB_E_BADARG;        // needs the fp32 partial workspace [B,Do,Ho,Wo,Cout_total]
     UArgs a;
     memset(&a, 0, sizeof(a));
@@ -588,7 +598,8 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     if (a.merge == 3 && (in_stride != 1 || out_stride != 1 || nclass != 1)) return STB_E_UNSUPPORTED;
     a.in_stride = in_stride;
     a.nsub = in_stride == 2 ? 4 : 1;
-    a.sd_in = (flags & 16) ? 1 : in_stride;     // flags bit4: 2-D convolution, the depth axis (image index) is never strided
+    a.sd_in = kdepth ? kdepth : ((flags & 16) ? 1 : in_stride);     // flags bit4: 2-D convolution, the depth axis (image index) is never strided
+    a.kdepth = kdepth;
     int maxdh = 0, maxdw = 0, dzmin = 127, dzmax = -127;
     // Taps of a class are issued in the order of the plane they read (stable sort by dz): the issuer then consumes
     // planes monotonically and can wait for / hand back each plane individually.

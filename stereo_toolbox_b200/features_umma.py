@@ -10,6 +10,7 @@ gwc_feature / 12-channel concat_feature; parameters are read from the reference-
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional
 
 import torch
@@ -19,6 +20,8 @@ from . import _lib, ops
 from .aggregation_umma import (BO_MODE, ES_VARIANT, KWMERGE, TORCH_DT, _iarr, from_channels_last, pad_channels,
                                to_channels_last)
 from .ops import ACT, _p, _stream
+
+KDEPTH = os.environ.get("STB_UMMA_KDEPTH", "1") == "1"     # K-chunks accumulated in TMEM (one launch) instead of K-split passes
 
 
 class Conv2dPlan:
@@ -56,18 +59,26 @@ class Conv2dPlan:
         mn = min(off)
         self.in_off = mn
         self.merge = bool(KWMERGE and stride == 1 and k == 3 and cout <= 64)   # N >= 128 is math-bound without merging
+        # Cin beyond one K-chunk: instead of K-split passes chained through an fp32 workspace, lay the K-chunks along a
+        # pseudo-depth axis (plane = image*nk + chunk, taps of chunk c carry dz = c) so they accumulate in TMEM inside
+        # one launch (conv3d_umma flags bit5).  Needs all nk*k*k weight tiles resident: taken for the 128-channel layers.
+        self.kdepth = bool(KDEPTH and self.nk > 1 and stride == 1 and not self.merge and self.nk * k * k <= 64 and self.nk <= 2)
         dz, dh, dw, sub, widx = [], [], [], [], []
-        for a in range(k):
-            if self.merge:
-                dz.append(0); dh.append(off[a] - mn); dw.append(0); sub.append(0); widx.append(a * k)
-                continue
-            for b in range(k):
-                dz.append(0); dh.append(off[a] - mn); dw.append(off[b] - mn)
-                sub.append(par[a] * 2 + par[b] if stride == 2 else 0); widx.append(a * k + b)
+        for c in range(self.nk if self.kdepth else 1):
+            for a in range(k):
+                if self.merge:
+                    dz.append(0); dh.append(off[a] - mn); dw.append(0); sub.append(0); widx.append(a * k)
+                    continue
+                for b in range(k):
+                    dz.append(c); dh.append(off[a] - mn); dw.append(off[b] - mn)
+                    sub.append(par[a] * 2 + par[b] if stride == 2 else 0)
+                    widx.append((a * k + b) * self.nk + c if self.kdepth else a * k + b)
+        if self.kdepth:
+            self.nwtiles = k * k * self.nk           # weight tiles are [tap][chunk][Cpad][KC]: tile index = tap*nk + chunk
         self.ntaps = len(dz)
         self.c = [_iarr(v) for v in (dz, dh, dw, sub, widx)]
         self.c_tb, self.c_te, self.c_z = _iarr([0]), _iarr([self.ntaps]), _iarr([0])
-        self.flags = BO_MODE | (ES_VARIANT << 1) | (4 if self.merge else 0) | 16 | ((dil & 7) << 8)
+        self.flags = BO_MODE | (ES_VARIANT << 1) | (4 if self.merge else 0) | 16 | ((dil & 7) << 8) | (32 if self.kdepth else 0)
 
     def out_size(self, n):
         return (n + 2 * self.pad - self.dil * (self.k - 1) - 1) // self.stride + 1
@@ -99,7 +110,7 @@ class UmmaGwcFeatures:
         Ho, Wo = p.out_size(H), p.out_size(W)
         out = torch.empty(1, N, Ho, Wo, p.cout, device=x.device, dtype=self.dtype)
         ws = None
-        if p.nk > 1:
+        if p.nk > 1 and not p.kdepth:
             if self._ws is None or self._ws.numel() < out.numel():
                 self._ws = torch.empty(out.numel(), device=x.device, dtype=torch.float32)
             ws = self._ws
