@@ -21,6 +21,7 @@ from .aggregation_umma import (BO_MODE, ES_VARIANT, KWMERGE, TORCH_DT, _iarr, fr
                                to_channels_last)
 from .ops import ACT, _p, _stream
 
+KWMERGE_2D = os.environ.get("STB_UMMA_KWMERGE2D", "0")
 KDEPTH = os.environ.get("STB_UMMA_KDEPTH", "1") == "1"     # K-chunks accumulated in TMEM (one launch) instead of K-split passes
 
 
@@ -58,7 +59,12 @@ class Conv2dPlan:
         off = [(x - p) // stride for x, p in zip(e, par)]
         mn = min(off)
         self.in_off = mn
-        self.merge = bool(KWMERGE and stride == 1 and k == 3 and cout <= 64)   # N >= 128 is math-bound without merging
+        # kw-merge trades MMA work (3x fewer A-operand reads) for epilogue work (3 TMEM loads + 64 shuffles per 32 channels).
+        # A 2-D conv has 3x fewer taps per output than a 3-D one, so its epilogue already bounds it: merging is off for
+        # 2-D convs by default (extractor 9.0 -> 8.0 ms at the benchmark shape); STB_UMMA_KWMERGE2D = 1 | 32 | 64 re-enables
+        # it for all / only Cout = 32 / only Cout = 64 layers.
+        m2d = KWMERGE_2D == "1" or KWMERGE_2D == str(cout)
+        self.merge = bool(KWMERGE and m2d and stride == 1 and k == 3 and cout <= 64)   # N >= 128 is math-bound without merging
         # Cin beyond one K-chunk: instead of K-split passes chained through an fp32 workspace, lay the K-chunks along a
         # pseudo-depth axis (plane = image*nk + chunk, taps of chunk c carry dz = c) so they accumulate in TMEM inside
         # one launch (conv3d_umma flags bit5).  Needs all nk*k*k weight tiles resident: taken for the 128-channel layers.
