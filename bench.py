@@ -25,6 +25,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at NCCL_DEBUG=VERSION) off it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 H_PAD, W_PAD, MAXDISP = 384, 1248, 192
 METRIC = "disparity maps/sec @ 1242x375 D=192 (GwcNet_GC inference)"
