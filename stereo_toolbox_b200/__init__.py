@@ -7,8 +7,9 @@ from .gwcnet import GwcNet_G, GwcNet_GC
 from .psmnet import PSMNet
 from .raft_stereo import RAFTStereo
 from .acvnet import ACVNet
+from .cfnet import CFNet
 from .checkpoint import load_checkpoint_flexible
 
 __all__ = ["build_gwc_volume", "build_concat_volume", "build_concat_volume_unmasked", "groupwise_correlation",
            "disparity_regression", "disparityregression", "upsample_softargmin", "CorrBlock1D",
-           "Combined_Geo_Encoding_Volume", "GwcNet_G", "GwcNet_GC", "PSMNet", "RAFTStereo", "ACVNet", "load_checkpoint_flexible"]
+           "Combined_Geo_Encoding_Volume", "GwcNet_G", "GwcNet_GC", "PSMNet", "RAFTStereo", "ACVNet", "CFNet", "load_checkpoint_flexible"]

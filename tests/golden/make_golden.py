@@ -332,6 +332,26 @@ def train():
     save("psmnet_train.npz", **out)
 
 
+@torch.no_grad()
+def cfnet():
+    """CFNet whole model (eval) on CPU.  The reference's UniformSampler / SpatialTransformer pass ``tensor.get_device()``
+    (-1 on CPU) as a device index; for the duration of this run ``Tensor.get_device`` is patched to return the tensor's
+    ``torch.device`` instead -- the reference sources are not touched.  maxdisp 64, 64x128 pair."""
+    orig = torch.Tensor.get_device
+    torch.Tensor.get_device = lambda self: self.device
+    try:
+        net = ref("CFNet.cfnet").CFNet(64)
+        sd = _load_synth(net, calib=synth_pair(2, 64, 128, seed=103, shift=3), calib_name="cfnet")
+        left, right = synth_pair(1, 64, 128, seed=6, shift=5)
+        disp = net(left, right)
+    finally:
+        torch.Tensor.get_device = orig
+    save("cfnet.npz", disp=disp)
+    meta = json.load(open(os.path.join(HERE, "models.json")))
+    meta["cfnet"] = dict(keys=_keys(sd), checksum=state_checksum(sd), maxdisp=64, shape=[1, 64, 128], shift=5)
+    json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]

@@ -181,3 +181,37 @@ def test_acvnet_oracle_fp32_padded_shape():
         disp = net(left.cuda(), right.cuda()).cpu()
     epe = (disp - want).abs().mean().item()
     assert epe < 1e-3, f"EPE vs oracle {epe}"
+
+
+def test_cfnet_golden():
+    """CFNet whole model (fused 1/8-1/16-1/32 volumes + two cascade stages) vs the reference's own output (generated on CPU,
+    tests/golden/make_golden.py cfnet).  The cascade rounds its search ranges to integers (floor / ceil / .long() samples),
+    so a last-bit difference upstream can move one sample of one pixel: the fp32 bar is the median / mean error plus a
+    bound on the fraction of such pixels.  The 16-bit path is compared where the model is still continuous -- the
+    first-stage disparity before any integer sampling -- against the fp32 path; downstream of the integer samplers an
+    untrained (flat-distribution) network turns 1e-2 px of upstream difference into whole-sample jumps."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    g = load_golden("cfnet.npz")
+    sd, meta = golden_state("cfnet")
+    left, right = synth_pair(1, 64, 128, seed=6, shift=meta["shift"])
+    stage1 = {}
+    for precision in ("fp32", "fp16"):
+        net = S.CFNet(meta["maxdisp"], precision=precision)
+        net.load_state_dict(sd, strict=True)
+        net = net.cuda().eval()
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False          # identical fp32 2-D features: the comparison is about the hot path
+        try:
+            with torch.no_grad():
+                disp = net(left.cuda(), right.cuda()).cpu()
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        assert disp.shape == g["disp"].shape == (1, 64, 128) and torch.isfinite(disp).all()
+        stage1[precision] = net._last["pred2_s4"].cpu()
+        if precision == "fp32":
+            err = (disp - g["disp"]).abs()
+            assert err.median().item() < 1e-3 and err.mean().item() < 5e-3, (err.median().item(), err.mean().item())
+            assert (err > 0.1).float().mean().item() < 0.01
+    d = (stage1["fp16"] - stage1["fp32"]).abs().mean().item()
+    assert d < 1e-2, f"first-stage disparity (1/8 scale) fp16 vs fp32 path: {d} px"
