@@ -352,6 +352,26 @@ def cfnet():
     json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
 
 
+@torch.no_grad()
+def pcwnet():
+    """PCWNet_GC whole model (eval) on CPU; same ``Tensor.get_device`` patch as cfnet() (PCWNet/submodule.py:130)."""
+    orig = torch.Tensor.get_device
+    torch.Tensor.get_device = lambda self: self.device
+    try:
+        net = ref("PCWNet.pcwnet").PCWNet_GC(64)
+        sd = _load_synth(net, calib=synth_pair(2, 64, 128, seed=104, shift=3), calib_name="pcwnet_gc")
+        left, right = synth_pair(1, 64, 128, seed=7, shift=5)
+        cap = {}
+        net.classif3.register_forward_hook(lambda m, i, o: cap.__setitem__("cost3", o))
+        disp = net(left, right)
+    finally:
+        torch.Tensor.get_device = orig
+    save("pcwnet_gc.npz", disp=disp, cost3=cap["cost3"])
+    meta = json.load(open(os.path.join(HERE, "models.json")))
+    meta["pcwnet_gc"] = dict(keys=_keys(sd), checksum=state_checksum(sd), maxdisp=64, shape=[1, 64, 128], shift=5)
+    json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]

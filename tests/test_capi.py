@@ -54,7 +54,8 @@ def test_state_dict_layout_matches_reference():
     meta = load_meta("models.json")
     for key, ctor in (("gwcnet_gc", lambda: S.GwcNet_GC(32)), ("gwcnet_g", lambda: S.GwcNet_G(32)),
                       ("psmnet", lambda: S.PSMNet(32)), ("raft_stereo", lambda: S.RAFTStereo()),
-                      ("acvnet", lambda: S.ACVNet(64)), ("cfnet", lambda: S.CFNet(64))):
+                      ("acvnet", lambda: S.ACVNet(64)), ("cfnet", lambda: S.CFNet(64)),
+                      ("pcwnet_gc", lambda: S.PCWNet_GC(64))):
         sd = ctor().state_dict()
         want = meta[key]["keys"]
         assert set(sd) == set(want)

@@ -215,3 +215,34 @@ def test_cfnet_golden():
             assert (err > 0.1).float().mean().item() < 0.01
     d = (stage1["fp16"] - stage1["fp32"]).abs().mean().item()
     assert d < 1e-2, f"first-stage disparity (1/8 scale) fp16 vs fp32 path: {d} px"
+
+
+def test_pcwnet_gc_golden():
+    """PCWNet_GC whole model (4-scale volumes fused by the 3-level hourglassup, align_corners=True head, full-resolution
+    2-D refinement) vs the reference's own CPU output: pre-softmax cost of classif3 and the final disparity (fp32 path);
+    the 16-bit path is compared on the cost-volume stage's disparity (before the 2-D refinement net)."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    g = load_golden("pcwnet_gc.npz")
+    sd, meta = golden_state("pcwnet_gc")
+    left, right = synth_pair(1, 64, 128, seed=7, shift=meta["shift"])
+    stage = {}
+    for precision in ("fp32", "fp16"):
+        net = S.PCWNet_GC(meta["maxdisp"], precision=precision)
+        net.load_state_dict(sd, strict=True)
+        net = net.cuda().eval()
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                disp = net(left.cuda(), right.cuda()).cpu()
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        assert disp.shape == g["disp"].shape == (1, 64, 128) and torch.isfinite(disp).all()
+        stage[precision] = net._last["pred3"].cpu()
+        if precision == "fp32":
+            torch.testing.assert_close(net._last_cost.cpu(), g["cost3"], rtol=2e-3, atol=2e-3)
+            epe = (disp - g["disp"]).abs().mean().item()
+            assert epe < 1e-3, f"EPE vs reference {epe}"
+    d = (stage["fp16"] - stage["fp32"]).abs().mean().item()
+    assert d < 1e-2, f"cost-volume stage disparity fp16 vs fp32 path: {d} px"
