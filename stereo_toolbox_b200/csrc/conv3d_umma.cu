@@ -172,7 +172,11 @@ __device__ __forceinline__ void issue_dispatch(const UArgs& a, int tq, uint32_t 
 // ACT / F16 are compile-time so the epilogue stays a few hundred instructions: with a runtime activation switch
 // unrolled over 32 channels the kernel was 83 KB of SASS and the epilogue warps stalled on instruction fetch
 // (ncu: stall_no_inst on every epilogue line, profiles/ncu_umma_r01_*.txt).
-template <int ACT, bool F16>
+// LEAN instantiation: compiled WITHOUT the rarely used paths (ragged channel counts, fp32 output, K-split partial sums,
+// timeline trace, timing-experiment switches).  The kernel sits at its 168-register cap with spills, and every line added
+// to the epilogue was measured to cost ALL layers (profiles/umma_issue_r01.md section 4), so the common layers get a
+// kernel that does not carry code they never execute.
+template <int ACT, bool F16, bool LEAN>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ UArgs a) {
@@ -197,8 +201,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // ---- persistent CTA: work items blockIdx.x, blockIdx.x + gridDim.x, ... ; every role walks the same list and
     // carries its pipeline state (ring slot / phase, accumulator round) across items, so the producer is already
     // filling the ring for the next item while the tensor pipe and the epilogue finish the current one.
-    long long* const trace_buf = g_umma_trace;                // read ONCE: a global load per round sat on the issuer's critical path
-    const int trace_rounds = (trace_buf && blockIdx.x == 0) ? g_umma_trace_rounds : 0;
+    long long* const trace_buf = LEAN ? nullptr : g_umma_trace;   // read ONCE: a global load per round sat on the issuer's critical path
+    const int trace_rounds = (!LEAN && trace_buf && blockIdx.x == 0) ? g_umma_trace_rounds : 0;
+    const int dbg = LEAN ? 0 : a.debug;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
@@ -224,7 +229,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                             (i * a.w_tile_stride + a.w_kc_off) * a.w_rows + a.cout_off);
             int slot = 0;
             uint32_t eph = 1;                      // parity to wait for on plane_empty[slot] (fresh barrier: passes)
-            for (int tile = blockIdx.x; tile < a.ntiles && !(a.debug & 1); tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < a.ntiles && !(dbg & 1); tile += gridDim.x) {
                 const UTile u = decode_tile(a, tile);
                 const int ih0 = (u.jh0 + a.in_h_off) * a.in_stride, iw0 = (u.jw0 + a.in_w_off) * a.in_stride;
                 for (int n = 0; n < u.nplanes; ++n) {
@@ -270,7 +275,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             uint32_t wphase = 0;
             int base_slot = 0;                    // ring slot of the current item's plane 0
             uint32_t ground = 0;                  // accumulator round counter over all items
-            const bool no_planes = a.debug & 1;
+            const bool no_planes = dbg & 1;
             auto wait_upto = [&](int n) {
                 while (waited < n) {
                     if (!no_planes) mbar_wait(&plane_full[wslot], wphase);
@@ -293,7 +298,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     const int dead_now = si * sd;                 // item-relative index of the step's first plane
                     for (int c = 0; c < nclass; ++c, ++ground) {
                         if ((int)(ground & 1u) != issuer) continue;
-                        const bool trace = (int)ground < trace_rounds;
+                        const bool trace = !LEAN && (int)ground < trace_rounds;
                         if (trace) trace_buf[ground * 8 + 0] = clock64();
                         // first plane this issuer still needs in ITS next round (ground + 2)
                         int nsi = si, nc = c + 2;
@@ -301,7 +306,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         const int next_dead = nsi >= u.nst ? u.nplanes : nsi * sd;
                         release_upto(dead_now);                   // planes between my previous window and this one
                         const int buf = issuer;
-                        if (!(a.debug & 4)) {
+                        if (!(dbg & 4)) {
                             mbar_wait(&tmem_empty[buf], ((ground >> 1) & 1) ^ 1);
                             tc_fence_after();
                         }
@@ -321,7 +326,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                             for (; tq < g1; ++tq) issue_dispatch<1>(a, tq, abase, dbase, nM, ksteps);
                             if (gr.rel && dead_now + z < next_dead) release_upto(dead_now + z + 1);
                         }
-                        if (!(a.debug & 4)) mma_commit(&tmem_full[buf]);
+                        if (!(dbg & 4)) mma_commit(&tmem_full[buf]);
                         if (trace) trace_buf[ground * 8 + 3] = clock64();
                     }
                     step_slot += sd;
@@ -342,13 +347,15 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const bool active = egroup < (items >= 2 ? 2 : 1);
         const size_t ostride_w = (size_t)a.Cout_total;
         constexpr int f16 = F16 ? 1 : 0;
-        const bool full32 = (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
+        const bool full32 = LEAN || (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
+        const float* const partial = LEAN ? nullptr : a.partial;
+        const bool out_fp32 = !LEAN && a.out_fp32;
         float sh0[32];                              // folded-BN shift of the first 32 channels stays in registers
 #pragma unroll
         for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + a.cout_off + i) : 0.f;
         const int merge = a.merge, Cn = a.Cn, nM = a.nM;
         uint32_t ground = 0;                        // accumulator round counter over all items (same order as the issuer)
-        for (int tile = blockIdx.x; active && tile < a.ntiles && !(a.debug & 4); tile += gridDim.x) {
+        for (int tile = blockIdx.x; active && tile < a.ntiles && !(dbg & 4); tile += gridDim.x) {
           const UTile u = decode_tile(a, tile);
           const int b = u.b, jh0 = u.jh0, jw0 = u.jw0;
           int e_si = 0, e_c = 0;                      // (step, class) of the round, kept incrementally (no division)
@@ -359,9 +366,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             if (++e_c == a.nclass) { e_c = 0; ++e_si; }
             mbar_wait_warp(&tmem_full[buf], (ground >> 1) & 1);
             tc_fence_after();
-            const bool trace = (int)ground < trace_rounds && warp == 3 && lane == 0;
+            const bool trace = !LEAN && (int)ground < trace_rounds && warp == 3 && lane == 0;
             if (trace) trace_buf[ground * 8 + 4] = clock64();
-            for (int item = egroup; item < items && !(a.debug & 2); item += 2) {
+            for (int item = egroup; item < items && !(dbg & 2); item += 2) {
               {
                 const int m = nblk_e == 8 ? (item >> 3) : item, blk = nblk_e == 8 ? (item & 7) : 0;
                 const int cd = nblk_e == 8 ? (blk >> 2) : cl.od0, chh = nblk_e == 8 ? ((blk >> 1) & 1) : cl.oh0,
@@ -418,8 +425,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     const size_t eoff = vox * ostride_w + a.cout_off + c0;
                     if (inb && full32) {
                         // ---------------- vector path: 32 complete channels
-                        if (a.partial) {
-                            const float4* pp = reinterpret_cast<const float4*>(a.partial + eoff);
+                        if (partial) {
+                            const float4* pp = reinterpret_cast<const float4*>(partial + eoff);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 pv = __ldg(pp + i);
@@ -454,7 +461,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], ACT);
                         if (trace && item == egroup && c0 == 0) trace_buf[ground * 8 + 7] = clock64();     // arithmetic done, stores next
-                        if (a.out_fp32) {
+                        if (out_fp32) {
                             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + eoff);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) op[i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
@@ -477,11 +484,11 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         for (int i = 0; i < 32; ++i) {
                             if (i < nch) {
                                 float x = f[i];
-                                if (a.partial) x += __ldg(a.partial + eoff + i);
+                                if (partial) x += __ldg(partial + eoff + i);
                                 if (a.shift) x += __ldg(a.shift + a.cout_off + c0 + i);
                                 if (a.residual) x += load16(reinterpret_cast<const uint16_t*>(a.residual) + eoff + i, f16);
                                 x = stb_act(x, ACT);
-                                if (a.out_fp32) reinterpret_cast<float*>(a.out)[eoff + i] = x;
+                                if (out_fp32) reinterpret_cast<float*>(a.out)[eoff + i] = x;
                                 else store16(reinterpret_cast<uint16_t*>(a.out) + eoff + i, x, f16);
                             }
                         }
@@ -489,7 +496,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 }
               }
             }
-            if (a.debug & 2) {                   // (timing experiment: no epilogue work, just hand the buffer back)
+            if (dbg & 2) {                   // (timing experiment: no epilogue work, just hand the buffer back)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -503,12 +510,12 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
-template <int ACT, bool F16>
-int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, UArgs& a) {
+template <int ACT, bool F16, bool LEAN>
+int launch_one_impl(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, UArgs& a) {
     static bool attr_set = false;
     static uint32_t smem_base = 0;      // per kernel instance: address of the aligned dynamic-smem base in the shared window
     if (!attr_set) {
-        cudaFuncSetAttribute(conv3d_umma_kernel<ACT, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
+        cudaFuncSetAttribute(conv3d_umma_kernel<ACT, F16, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
         // one-off query launch (same kernel, same dynamic-smem attribute; the base does not depend on the size)
         uint32_t* dev = nullptr;
         if (cudaMalloc(&dev, sizeof(uint32_t)) != cudaSuccess) return STB_E_DRIVER;
@@ -516,7 +523,7 @@ int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& t
         memset(&q, 0, sizeof(q));
         q.ntiles = -1;
         q.out = dev;
-        conv3d_umma_kernel<ACT, F16><<<1, UMMA_THREADS, 4096, st>>>(tx, tw, q);
+        conv3d_umma_kernel<ACT, F16, LEAN><<<1, UMMA_THREADS, 4096, st>>>(tx, tw, q);
         cudaError_t e = cudaMemcpyAsync(&smem_base, dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         cudaFree(dev);
@@ -535,9 +542,17 @@ int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& t
     }
     for (int c = 0; c < a.nclass; ++c) a.iss[a.cls[c].tap_begin].dcol |= 1u << 31;      // overwrite instead of accumulate
     a.desc_hi = (((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29);
-    conv3d_umma_kernel<ACT, F16><<<grid, UMMA_THREADS, smem, st>>>(tx, tw, a);
+    conv3d_umma_kernel<ACT, F16, LEAN><<<grid, UMMA_THREADS, smem, st>>>(tx, tw, a);
     STB_CHECK_LAUNCH();
     return STB_OK;
+}
+
+bool g_trace_armed = false;      // host mirror of g_umma_trace != nullptr (stb_conv3d_umma_set_trace)
+
+template <int ACT, bool F16>
+int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, UArgs& a) {
+    const bool lean = !a.debug && !g_trace_armed && !a.partial && !a.out_fp32 && (a.Cn_valid & 31) == 0;
+    return lean ? launch_one_impl<ACT, F16, true>(grid, smem, st, tx, tw, a) : launch_one_impl<ACT, F16, false>(grid, smem, st, tx, tw, a);
 }
 
 int launch_umma(int act, int f16, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx,
@@ -559,6 +574,7 @@ int launch_umma(int act, int f16, unsigned grid, size_t smem, cudaStream_t st, c
 extern "C" int stb_conv3d_umma_set_trace(long long* dev_buf, int rounds) {
     if (cudaMemcpyToSymbol(g_umma_trace, &dev_buf, sizeof(dev_buf)) != cudaSuccess) return STB_E_BADARG;
     if (cudaMemcpyToSymbol(g_umma_trace_rounds, &rounds, sizeof(rounds)) != cudaSuccess) return STB_E_BADARG;
+    g_trace_armed = dev_buf != nullptr;
     return STB_OK;
 }
 
