@@ -176,7 +176,9 @@ __device__ __forceinline__ void issue_dispatch(const UArgs& a, int tq, uint32_t 
 // timeline trace, timing-experiment switches).  The kernel sits at its 168-register cap with spills, and every line added
 // to the epilogue was measured to cost ALL layers (profiles/umma_issue_r01.md section 4), so the common layers get a
 // kernel that does not carry code they never execute.
-template <int ACT, bool F16, bool LEAN>
+// LEAN: 0 = generic, 1 = lean / plain taps (one column block), 2 = lean / kw-merged (3 column blocks + lane realignment),
+// 3 = lean / merged transposed conv (8 parity-class blocks).
+template <int ACT, bool F16, int LEAN>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ UArgs a) {
@@ -342,7 +344,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // ================================ epilogue warps ================================
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
         const int egroup = (warp - 3) >> 2;         // epilogue group 0/1 drains M-tiles m = egroup, egroup+2, ...
-        const int nblk_e = a.cblocks == 8 ? 8 : 1;     // merged transposed conv: all 8 parity classes in one round
+        const int nblk_e = LEAN == 3 ? 8 : (LEAN ? 1 : (a.cblocks == 8 ? 8 : 1));     // merged transposed conv: all 8 parity classes in one round
         const int items = a.nM * nblk_e;               // (M-tile, class block) work items per round, dealt to 2 groups
         const bool active = egroup < (items >= 2 ? 2 : 1);
         const size_t ostride_w = (size_t)a.Cout_total;
@@ -353,7 +355,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         float sh0[32];                              // folded-BN shift of the first 32 channels stays in registers
 #pragma unroll
         for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + a.cout_off + i) : 0.f;
-        const int merge = a.merge, Cn = a.Cn, nM = a.nM;
+        const int merge = LEAN == 2 ? 3 : (LEAN ? 1 : a.merge), Cn = a.Cn, nM = a.nM;
         uint32_t ground = 0;                        // accumulator round counter over all items (same order as the issuer)
         for (int tile = blockIdx.x; active && tile < a.ntiles && !(dbg & 4); tile += gridDim.x) {
           const UTile u = decode_tile(a, tile);
@@ -510,7 +512,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
-template <int ACT, bool F16, bool LEAN>
+template <int ACT, bool F16, int LEAN>
 int launch_one_impl(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, UArgs& a) {
     static bool attr_set = false;
     static uint32_t smem_base = 0;      // per kernel instance: address of the aligned dynamic-smem base in the shared window
@@ -552,7 +554,10 @@ bool g_trace_armed = false;      // host mirror of g_umma_trace != nullptr (stb_
 template <int ACT, bool F16>
 int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, UArgs& a) {
     const bool lean = !a.debug && !g_trace_armed && !a.partial && !a.out_fp32 && (a.Cn_valid & 31) == 0;
-    return lean ? launch_one_impl<ACT, F16, true>(grid, smem, st, tx, tw, a) : launch_one_impl<ACT, F16, false>(grid, smem, st, tx, tw, a);
+    if (lean && a.cblocks == 8 && a.merge == 1) return launch_one_impl<ACT, F16, 3>(grid, smem, st, tx, tw, a);
+    if (lean && a.cblocks == 3 && a.merge == 3) return launch_one_impl<ACT, F16, 2>(grid, smem, st, tx, tw, a);
+    if (lean && a.cblocks == 1 && a.merge == 1) return launch_one_impl<ACT, F16, 1>(grid, smem, st, tx, tw, a);
+    return launch_one_impl<ACT, F16, 0>(grid, smem, st, tx, tw, a);
 }
 
 int launch_umma(int act, int f16, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx,
