@@ -129,6 +129,10 @@ class IGEVCostVolume(nn.Module):
         self._be = make_backend(precision)
 
     def forward(self, match_left, match_right, features_left: List[torch.Tensor]):
+        return self.stage(match_left, match_right, features_left)
+
+    def stage(self, match_left, match_right, features_left: List[torch.Tensor]):
+        """The whole hot path of one IGEV forward up to the GRU loop; ``IGEVStereo`` (igev_stereo.py) inherits it."""
         if self.training:
             raise NotImplementedError("stereo_toolbox_b200: inference path only (model.eval()); see DESIGN.md")
         be = self._be

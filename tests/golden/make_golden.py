@@ -372,6 +372,35 @@ def pcwnet():
     json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
 
 
+@torch.no_grad()
+def igev_model():
+    """IGEVStereo whole model (config 5 family).  The reference's constructor asks ``timm_0_5_4`` for a pretrained
+    MobileNetV2 (extractor.py:331); timm is absent and there is no network, so for this run the stub module's
+    ``create_model`` hands it ``stereo_toolbox_b200.mobilenetv2.MobileNetV2Trunk`` (same stage table and module names
+    as timm's mobilenetv2_100).  Everything else -- Feature decoder, stems, context network, cost-volume stage, geometry
+    lookup, GRU loop, convex upsampling -- is the reference's own code.  max_disp 64, 64x128 pair, 4 iterations."""
+    from stereo_toolbox_b200.mobilenetv2 import MobileNetV2Trunk
+    sys.modules["timm_0_5_4"].create_model = lambda *a, **k: MobileNetV2Trunk()
+    net = ref("IGEVStereo.igev_stereo").IGEVStereo({"max_disp": 64})
+    sd = _load_synth(net, calib=synth_pair(2, 64, 128, seed=105, shift=3), calib_name="igev_stereo")
+    # ResidualBlock registers its shortcut norm twice (norm3 and downsample.1 are ONE module, extractor.py:27,49): the
+    # name-keyed generator draws two values, load_state_dict keeps the later name's.  The fingerprint is therefore taken
+    # over the name-keyed dict the tests rebuild, not over the de-duplicated state_dict() of the loaded model.
+    sd = synth_state_dict(net.state_dict(), 0, {k: v for k, v in sd.items() if k.endswith(("running_mean", "running_var"))})
+    left, right = synth_pair(1, 64, 128, seed=8, shift=5)
+    cap = {}
+    net.classifier.register_forward_hook(lambda m, i, o: cap.__setitem__("cost", o))
+    def first_delta(m, i, o):          # a hook that returns a value would replace the module's output
+        cap.setdefault("delta0", o[2])
+    net.update_block.register_forward_hook(first_delta)
+    disp = net(left, right, iters=4)
+    init_disp, preds = net(left, right, iters=2, test_mode=False)
+    save("igev_stereo.npz", disp=disp, cost=cap["cost"], delta0=cap["delta0"], init_disp_up=init_disp, pred_last=preds[-1])
+    meta = json.load(open(os.path.join(HERE, "models.json")))
+    meta["igev_stereo"] = dict(keys=_keys(sd), checksum=state_checksum(sd), max_disp=64, shape=[1, 64, 128], shift=5, iters=4)
+    json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]

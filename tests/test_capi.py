@@ -55,7 +55,7 @@ def test_state_dict_layout_matches_reference():
     for key, ctor in (("gwcnet_gc", lambda: S.GwcNet_GC(32)), ("gwcnet_g", lambda: S.GwcNet_G(32)),
                       ("psmnet", lambda: S.PSMNet(32)), ("raft_stereo", lambda: S.RAFTStereo()),
                       ("acvnet", lambda: S.ACVNet(64)), ("cfnet", lambda: S.CFNet(64)),
-                      ("pcwnet_gc", lambda: S.PCWNet_GC(64))):
+                      ("pcwnet_gc", lambda: S.PCWNet_GC(64)), ("igev_stereo", lambda: S.IGEVStereo({"max_disp": 64}))):
         sd = ctor().state_dict()
         want = meta[key]["keys"]
         assert set(sd) == set(want)
