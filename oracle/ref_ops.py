@@ -185,28 +185,29 @@ def depthwise_patch(vol: torch.Tensor, weight: torch.Tensor, dilation: int) -> t
     return out
 
 
-def block_attention(x: torch.Tensor, qkv_w: torch.Tensor, qkv_b: torch.Tensor, fin_w: torch.Tensor,
-                    fin_b: torch.Tensor, num_heads: int, block=(4, 4, 4)) -> torch.Tensor:
-    """attention_block.forward (ACVNet/submodule.py:381-430): multi-head self-attention inside non-overlapping
-    (b0,b1,b2) blocks of the volume, then a 1x1x1 conv with bias.  x [B,C,D,H0,W0].
+def block_attention_core(qkv: torch.Tensor, qkv_b: torch.Tensor, num_heads: int, block=(4, 4, 4)) -> torch.Tensor:
+    """The part of attention_block.forward between the qkv Linear and final1x1 (ACVNet/submodule.py:392-428).
+    qkv [B,3C,D,H0,W0] (channel order (3, heads, head_dim), i.e. the Linear's output order) -> [B,C,D,H0,W0].
 
-    H and W are zero-padded on the bottom/right up to a multiple of the block BEFORE the qkv Linear, so padded
-    tokens carry qkv = bias.  The mask marks padded rows/columns; the reference writes ``mask[:, -pad_b:, :]`` /
-    ``mask[:, :, -pad_r:]`` (:405-406), and a slice ``-0:`` selects EVERYTHING, so when exactly one of pad_b / pad_r
-    is zero the whole mask is 1 and nothing is masked -- kept here on purpose."""
-    B, C, D, H0, W0 = x.shape
+    The reference zero-pads H and W on the bottom/right up to a multiple of the block BEFORE the qkv Linear, so padded
+    tokens carry qkv = bias; here the qkv volume is padded with the bias instead.  The mask marks padded rows/columns;
+    the reference writes ``mask[:, -pad_b:, :]`` / ``mask[:, :, -pad_r:]`` (:405-406), and a slice ``-0:`` selects
+    EVERYTHING, so when exactly one of pad_b / pad_r is zero the whole mask is 1 and nothing is masked -- kept here on
+    purpose."""
+    B, C3, D, H0, W0 = qkv.shape
+    C = C3 // 3
     b0, b1, b2 = block
     pad_r = (b2 - W0 % b2) % b2
     pad_b = (b1 - H0 % b1) % b1
-    x = F.pad(x, (0, pad_r, 0, pad_b))
     H, W = H0 + pad_b, W0 + pad_r
+    full = qkv_b.view(1, C3, 1, 1, 1).expand(B, C3, D, H, W).clone()
+    full[:, :, :, :H0, :W0] = qkv
     d, h, w = D // b0, H // b1, W // b2
     hd = C // num_heads
     nt = b0 * b1 * b2
-    tok = x.view(B, C, d, b0, h, b1, w, b2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, d * h * w, nt, C)
-    qkv = tok @ qkv_w.t() + qkv_b                                            # [B,nb,nt,3C]
-    qkv = qkv.view(B, d * h * w, nt, 3, num_heads, hd)
-    q, k, v = (qkv[:, :, :, i].permute(0, 1, 3, 2, 4) for i in range(3))      # [B,nb,heads,nt,hd]
+    tok = full.view(B, C3, d, b0, h, b1, w, b2).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, d * h * w, nt, C3)
+    tok = tok.view(B, d * h * w, nt, 3, num_heads, hd)
+    q, k, v = (tok[:, :, :, i].permute(0, 1, 3, 2, 4) for i in range(3))      # [B,nb,heads,nt,hd]
     attn = torch.einsum("bnhie,bnhje->bnhij", q, k) * (hd ** -0.5)
     if pad_r > 0 or pad_b > 0:
         m = torch.zeros(H, W)
@@ -219,7 +220,17 @@ def block_attention(x: torch.Tensor, qkv_w: torch.Tensor, qkv_b: torch.Tensor, f
     attn = torch.softmax(attn, dim=-1)
     o = torch.einsum("bnhij,bnhje->bnhie", attn, v)                          # [B,nb,heads,nt,hd]
     o = o.view(B, d, h, w, num_heads, b0, b1, b2, hd).permute(0, 4, 8, 1, 5, 2, 6, 3, 7).reshape(B, C, D, H, W)
-    o = o[:, :, :, :H0, :W0]
+    return o[:, :, :, :H0, :W0]
+
+
+def block_attention(x: torch.Tensor, qkv_w: torch.Tensor, qkv_b: torch.Tensor, fin_w: torch.Tensor,
+                    fin_b: torch.Tensor, num_heads: int, block=(4, 4, 4)) -> torch.Tensor:
+    """attention_block.forward (ACVNet/submodule.py:381-430): multi-head self-attention inside non-overlapping
+    (b0,b1,b2) blocks of the volume, then a 1x1x1 conv with bias.  x [B,C,D,H0,W0].  The qkv Linear acts on the channel
+    axis of every voxel (:392-400)."""
+    C = x.shape[1]
+    qkv = torch.einsum("oc,bcdhw->bodhw", qkv_w, x) + qkv_b.view(1, -1, 1, 1, 1)
+    o = block_attention_core(qkv, qkv_b, num_heads, block)
     return torch.einsum("oc,bcdhw->bodhw", fin_w.view(C, C), o) + fin_b.view(1, C, 1, 1, 1)
 
 

@@ -1,0 +1,116 @@
+"""Host-side mirrors of the reference models on CPU: every drop-in model runs with its hot path answered by the oracle
+(tests/oracle_backend.py) and is compared with the output the REFERENCE itself produced for the same seeded input and
+name-keyed weights (tests/golden/*.npz, tests/golden/make_golden.py).  What this pins without a GPU: constructor
+signatures, state-dict layout (strict load of the reference's own keys), the torch glue around the hot path (2-D
+extractors, CFNet's uniform sampler + warps, PCWNet's refinement, ACVNet's attention plumbing), layer order, residual
+wiring and return conventions.  The CUDA kernels behind the same calls are pinned by the ``-m gpu`` tests."""
+import pytest
+import torch
+
+from conftest import load_golden, golden_state
+from oracle_backend import oracle_hot_path
+
+
+def _pair(meta, seed):
+    from stereo_toolbox_b200.synth import synth_pair
+    b, h, w = meta["shape"]
+    return synth_pair(b, h, w, seed=seed, shift=meta["shift"])
+
+
+def _run(ctor, key, seed, **fwd):
+    sd, meta = golden_state(key)
+    with oracle_hot_path():
+        import stereo_toolbox_b200 as S
+        net = ctor(S, meta)
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        left, right = _pair(meta, seed)
+        with torch.no_grad():
+            return net(left, right, **fwd), net
+
+
+@pytest.mark.parametrize("key", ["gwcnet_gc", "gwcnet_g"])
+def test_gwcnet_mirror(key):
+    g = load_golden(f"{key}.npz")
+    disp, net = _run(lambda S, m: (S.GwcNet_GC if key == "gwcnet_gc" else S.GwcNet_G)(m["maxdisp"]), key, 0)
+    assert disp.shape == g["disp"].shape                       # [B,H,W]  (gwcnet.py:224)
+    if "cost3" in g:
+        torch.testing.assert_close(net._last_cost, g["cost3"], rtol=1e-3, atol=1e-3)
+    assert (disp - g["disp"]).abs().mean().item() < 1e-3
+
+
+def test_psmnet_mirror():
+    g = load_golden("psmnet.npz")
+    disp, _ = _run(lambda S, m: S.PSMNet(m["maxdisp"]), "psmnet", 1)
+    assert disp.shape == g["disp"].shape == (1, 1, 256, 256)   # keepdim regression (PSMNet/submodule.py:53)
+    assert (disp - g["disp"]).abs().mean().item() < 1e-3
+
+
+def test_acvnet_mirror():
+    g = load_golden("acvnet.npz")
+    disp, _ = _run(lambda S, m: S.ACVNet(m["maxdisp"]), "acvnet", 3)
+    assert disp.shape == g["disp"].shape
+    assert (disp - g["disp"]).abs().mean().item() < 1e-3
+
+
+def test_cfnet_mirror():
+    """Includes the torch glue the GPU build keeps outside the kernels: uniform sampler, gather warps, sampled volumes."""
+    g = load_golden("cfnet.npz")
+    disp, _ = _run(lambda S, m: S.CFNet(m["maxdisp"]), "cfnet", 6)
+    assert disp.shape == g["disp"].shape
+    assert (disp - g["disp"]).abs().mean().item() < 1e-3
+
+
+def test_pcwnet_gc_mirror():
+    g = load_golden("pcwnet_gc.npz")
+    disp, _ = _run(lambda S, m: S.PCWNet_GC(m["maxdisp"]), "pcwnet_gc", 7)
+    assert disp.shape == g["disp"].shape
+    assert (disp - g["disp"]).abs().mean().item() < 1e-3
+
+
+def test_raft_stereo_mirror():
+    """RAFTStereo through the package's own ``functional.CorrBlock1D`` host code (pyramid bookkeeping, level count)."""
+    from stereo_toolbox_b200.synth import synth_pair
+    g = load_golden("raft_stereo.npz")
+    sd, meta = golden_state("raft_stereo", calib=False)
+    with oracle_hot_path():
+        import stereo_toolbox_b200 as S
+        net = S.RAFTStereo()
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        left, right = synth_pair(1, 64, 128, seed=2, shift=meta["shift"])
+        with torch.no_grad():
+            out = net(left, right, iters=meta["iters"])
+    assert out.shape == g["disp"].shape == (1, 1, 64, 128)
+    assert (out - g["disp"]).abs().mean().item() < 1e-3
+
+
+def test_igev_stereo_mirror():
+    """IGEVStereo through ``igev.IGEVCostVolume.stage`` (hourglass wiring, feature gates, layout calls) and
+    ``functional.Combined_Geo_Encoding_Volume`` -- the host code the GPU build runs, unlike the coarser stage swap of
+    tests/test_oracle_golden.py::test_igev_stereo_mirror_with_oracle_stage."""
+    from stereo_toolbox_b200.synth import synth_pair
+    g = load_golden("igev_stereo.npz")
+    sd, meta = golden_state("igev_stereo")
+    with oracle_hot_path():
+        import stereo_toolbox_b200 as S
+        net = S.IGEVStereo({"max_disp": meta["max_disp"]})
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        left, right = synth_pair(1, 64, 128, seed=8, shift=meta["shift"])
+        with torch.no_grad():
+            out = net(left, right, iters=meta["iters"])
+    assert out.shape == g["disp"].shape == (1, 1, 64, 128)
+    assert (out - g["disp"]).abs().mean().item() < 1e-3
+
+
+def test_swap_is_scoped():
+    """Outside ``oracle_hot_path`` the product refuses CPU tensors again (no CPU fallback is left behind)."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200._lib import StbError
+    with oracle_hot_path():
+        pass
+    with pytest.raises(StbError):
+        S.build_gwc_volume(torch.zeros(1, 8, 4, 4), torch.zeros(1, 8, 4, 4), 2, 4)
+    with pytest.raises(StbError):
+        S.GwcNet_G(32).eval()(torch.zeros(1, 3, 64, 128), torch.zeros(1, 3, 64, 128))
