@@ -1,0 +1,19 @@
+#!/bin/bash
+# First GPU trip of the next round (run under gpurun from the repo root): confirm what was written after the
+# round-1 GPU budget ran out (IGEVStereo whole model), then measure the configs bench.py does not carry.
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/r2_pytest.log
+timeout 300 python -m pytest tests/test_igev_stereo_gpu.py -m gpu -q -s > gpurun_out/r2_igev.log 2>&1; echo "igev rc=$?"
+grep -i "EPE\|passed\|failed" gpurun_out/r2_igev.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; echo "bench rc=$?"
+cut -c1-400 gpurun_out/r2_bench.json
+{
+  timeout 300 python tools/model_bench.py --model igev   --height 1152 --width 1920 --maxdisp 256 --iters 32 --precision fp16
+  timeout 300 python tools/model_bench.py --model igev   --height 1152 --width 1920 --maxdisp 256 --iters 32 --precision fp32
+  timeout 300 python tools/model_bench.py --model acvnet --height 1152 --width 1920 --maxdisp 256 --precision fp16
+  timeout 300 python tools/model_bench.py --model raft   --height 512  --width 1024 --iters 32 --cuda-graph
+  timeout 300 python tools/model_bench.py --model psmnet --height 576  --width 960  --batch 4 --precision fp16
+  timeout 300 python tools/model_bench.py --model gwcnet_gc --height 576 --width 960 --batch 4 --precision fp16
+} > gpurun_out/r2_models.jsonl 2> gpurun_out/r2_models.err
+cat gpurun_out/r2_models.jsonl | cut -c1-300
