@@ -401,6 +401,37 @@ def igev_model():
     json.dump(meta, open(os.path.join(HERE, "models.json"), "w"))
 
 
+VARIANTS = {   # constructor-argument variants of the iterative models (host-side wiring; hot-path ops unchanged)
+    "raft_gru2_slowfast": ("raft", dict(n_gru_layers=2, slow_fast_gru=True)),
+    "raft_gru1": ("raft", dict(n_gru_layers=1)),
+    "raft_down3_lvl2_r3": ("raft", dict(n_downsample=3, corr_levels=2, corr_radius=3)),
+    "raft_instance_ctx": ("raft", dict(context_norm="instance")),
+    "igev_gru2_r3": ("igev", dict(max_disp=64, n_gru_layers=2, corr_radius=3)),
+    "igev_gru1_d96": ("igev", dict(max_disp=96, n_gru_layers=1)),
+}
+
+
+@torch.no_grad()
+def variants():
+    """RAFTStereo (args Namespace) / IGEVStereo (args dict) with non-default arguments, 64x128 pair, 3 iterations,
+    un-calibrated name-keyed weights.  Stored: the output and the parameter-name -> shape table of every variant."""
+    import argparse
+    from stereo_toolbox_b200.mobilenetv2 import MobileNetV2Trunk
+    sys.modules["timm_0_5_4"].create_model = lambda *a, **k: MobileNetV2Trunk()
+    left, right = synth_pair(1, 64, 128, seed=2, shift=3)
+    out, meta = {}, {}
+    for tag, (family, kw) in VARIANTS.items():
+        if family == "raft":
+            net = ref("RAFTStereo.raft_stereo").RAFTStereo(argparse.Namespace(**kw))
+        else:
+            net = ref("IGEVStereo.igev_stereo").IGEVStereo(dict(kw))
+        sd = _load_synth(net)
+        out[tag] = net(left, right, iters=3)
+        meta[tag] = dict(family=family, args=kw, keys=_keys(sd), checksum=state_checksum(sd))
+    save("variants.npz", **out)
+    json.dump(meta, open(os.path.join(HERE, "variants.json"), "w"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]

@@ -104,6 +104,40 @@ def test_igev_stereo_mirror():
     assert (out - g["disp"]).abs().mean().item() < 1e-3
 
 
+def _variant_tags():
+    from conftest import load_meta
+    return sorted(load_meta("variants.json"))
+
+
+@pytest.mark.parametrize("tag", _variant_tags())
+def test_iterative_model_argument_variants(tag):
+    """Non-default constructor arguments of RAFTStereo (Namespace) / IGEVStereo (dict): GRU level count, slow-fast
+    schedule, 1/8 resolution, correlation levels / radius, context norm, max_disp -- state-dict layout (strict load of
+    the reference's keys) and output vs the reference run with the same arguments."""
+    import argparse
+    from conftest import load_meta
+    from stereo_toolbox_b200.synth import synth_pair, synth_state_dict, state_checksum
+    meta = load_meta("variants.json")[tag]
+    want = load_golden("variants.npz")[tag]
+    template = {k: torch.zeros(s, dtype=torch.int64 if k.endswith("num_batches_tracked") else torch.float32)
+                for k, s in meta["keys"].items()}
+    sd = synth_state_dict(template, 0)
+    assert abs(state_checksum(sd) - meta["checksum"]) <= 1e-6 * abs(meta["checksum"])
+    with oracle_hot_path():
+        import stereo_toolbox_b200 as S
+        if meta["family"] == "raft":
+            net = S.RAFTStereo(argparse.Namespace(**meta["args"]))
+        else:
+            net = S.IGEVStereo(dict(meta["args"]))
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        left, right = synth_pair(1, 64, 128, seed=2, shift=3)
+        with torch.no_grad():
+            out = net(left, right, iters=3)
+    assert out.shape == want.shape == (1, 1, 64, 128)
+    assert (out - want).abs().mean().item() < 1e-3
+
+
 def test_swap_is_scoped():
     """Outside ``oracle_hot_path`` the product refuses CPU tensors again (no CPU fallback is left behind)."""
     import stereo_toolbox_b200 as S
