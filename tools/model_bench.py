@@ -8,14 +8,12 @@
   SceneFlow  python tools/model_bench.py --model psmnet --height 576 --width 960 --batch 4 --precision fp16
 
 Random-init name-keyed weights (synth.synth_state_dict), synthetic pair, eval + no_grad, CUDA events, median of --reps.
-Prints one JSON line: maps/s, ms per forward, peak memory, and -- with --cpu-reference -- the oracle's CPU time for the
-same input (models whose oracle restatement exists: gwcnet_gc / gwcnet_g / psmnet / acvnet) and the EPE against it.
+Prints one JSON line: maps/s, ms per forward, peak memory.  (Parity is the tests' job; the oracle is not imported here.)
 """
 import argparse
 import json
 import os
 import sys
-import time
 
 import torch
 
@@ -57,7 +55,6 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cuda-graph", action="store_true", help="raft: replay one captured GRU iteration")
-    ap.add_argument("--cpu-reference", action="store_true")
     args = ap.parse_args()
 
     import stereo_toolbox_b200 as S
@@ -90,23 +87,6 @@ def main():
                iters=fwd.get("iters"), ms_per_forward=ms, maps_per_s=args.batch / (ms * 1e-3),
                peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, out_shape=list(out.shape),
                finite=bool(torch.isfinite(out.float()).all().item()))
-    if args.cpu_reference:
-        from oracle import ref_models as M       # CPU leg only: the checker, timed beside the product
-        sd = {k: v.cpu() for k, v in net.state_dict().items()}
-        fn = {"gwcnet_gc": lambda: M.gwcnet_forward(sd, left, right, args.maxdisp, True),
-              "gwcnet_g": lambda: M.gwcnet_forward(sd, left, right, args.maxdisp, False),
-              "psmnet": lambda: M.psmnet_forward(sd, left, right, args.maxdisp),
-              "acvnet": lambda: M.acvnet_forward(sd, left, right, args.maxdisp)}.get(args.model)
-        if fn is None:
-            res["cpu_reference"] = "no whole-model oracle restatement for this model"
-        else:
-            torch.set_num_threads(os.cpu_count() or 1)
-            with torch.no_grad():
-                t0 = time.perf_counter()
-                want = fn()
-                dt = time.perf_counter() - t0
-            res.update(cpu_s=dt, cpu_maps_per_s=args.batch / dt, cpu_threads=torch.get_num_threads(),
-                       epe_vs_cpu_px=(out.float().cpu().reshape(want.shape) - want).abs().mean().item())
     print(json.dumps(res))
 
 
