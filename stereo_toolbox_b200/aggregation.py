@@ -2,8 +2,9 @@
 the backends that run them through libstb200.so.
 
 A *backend* owns the activation layout between kernels so model code never touches it:
-  Fp32Backend : NCDHW fp32, CUDA-core tap-list convolution (bit-faithful path, <=1e-3 px EPE)
-  (the tcgen05 bf16 NDHWC backend plugs in here; see conv3d_umma.cu / DESIGN.md)
+  Fp32Backend  : NCDHW fp32, CUDA-core tap-list convolution (bit-faithful path, <=1e-3 px EPE)
+  TrainBackend : the same, differentiable (autograd.py), batch-statistic BatchNorm
+  UmmaBackend  : NDHWC fp16/bf16, tcgen05 implicit-GEMM convolution (aggregation_umma.py, conv3d_umma.cu)
 """
 from __future__ import annotations
 
