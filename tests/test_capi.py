@@ -87,3 +87,28 @@ def test_training_mode_fails_loudly():
         net(torch.zeros(2, 3, 64, 128), torch.zeros(2, 3, 64, 128))
     with pytest.raises(NotImplementedError):
         S.ACVNet(32).train()(torch.zeros(1, 3, 64, 128), torch.zeros(1, 3, 64, 128))
+
+
+def test_load_checkpoint_flexible(tmp_path):
+    """models/__init__.py:20-51: DDP-prefixed ('module.') checkpoints under a state-dict key, plain checkpoints, extra
+    keys ignored, keys absent from the checkpoint keep the model's current values."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_state_dict
+    src = S.GwcNet_G(32)
+    sd = synth_state_dict(src.state_dict(), 3)
+    held_out = "classif3.2.weight"
+    ddp = {"module." + k: v for k, v in sd.items() if k != held_out}
+    ddp["module.not_in_model.weight"] = torch.zeros(3)
+    path = tmp_path / "ckpt.pth"
+    torch.save({"model": ddp, "epoch": 7}, path)
+    net = S.GwcNet_G(32)
+    before = net.state_dict()[held_out].clone()
+    out = S.load_checkpoint_flexible(net, str(path), "model")
+    assert out is net
+    got = net.state_dict()
+    for k, v in sd.items():
+        assert torch.equal(got[k], before if k == held_out else v), k
+    plain = tmp_path / "plain.pth"
+    torch.save(sd, plain)
+    net2 = S.load_checkpoint_flexible(S.GwcNet_G(32), str(plain))
+    assert all(torch.equal(net2.state_dict()[k], v) for k, v in sd.items())
