@@ -32,3 +32,28 @@ def test_gwcnet_gc_16bit_sits_on_the_storage_model(prec, dtype):
     to_model = (disp - model).abs().mean().item()
     print(f"GwcNet_GC {prec}: EPE vs fp32 reference {to_ref:.3e} px, vs 16-bit storage model {to_model:.3e} px")
     assert to_model < 0.5 * to_ref, (to_model, to_ref)
+
+
+def test_head_x4_fast_path_matches_generic(tmp_path):
+    """STB_HEAD_X4=1 selects ``upsample_softargmin_x4_kernel`` (outD == 4*D, align_corners=False: compile-time bin
+    weights, no per-bin index arithmetic).  It evaluates the generic kernel's expressions in the generic kernel's order,
+    so the two must agree to float rounding; the switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    import stereo_toolbox_b200 as S
+    from oracle import ref_ops as R
+    g = torch.Generator().manual_seed(11)
+    cost = torch.randn(2, 1, 12, 9, 21, generator=g) * 3
+    torch.save(cost, tmp_path / "cost.pt")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, torch; sys.path.insert(0, %r); import stereo_toolbox_b200 as S; "
+            "c = torch.load(%r); torch.save(S.upsample_softargmin(c.cuda(), 48, 36, 84).cpu(), %r)"
+            % (root, str(tmp_path / "cost.pt"), str(tmp_path / "x4.pt")))
+    env = dict(os.environ, STB_HEAD_X4="1")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    fast = torch.load(tmp_path / "x4.pt")
+    generic = S.upsample_softargmin(cost.cuda(), 48, 36, 84).cpu()
+    want = R.upsample_softargmin(cost, 48, 36, 84, False, False)
+    torch.testing.assert_close(fast, want, rtol=1e-4, atol=1e-4)          # the oracle, like the generic kernel's test
+    torch.testing.assert_close(fast, generic, rtol=0, atol=1e-5)
