@@ -17,3 +17,5 @@ cut -c1-400 gpurun_out/r2_bench.json
   timeout 300 python tools/model_bench.py --model gwcnet_gc --height 576 --width 960 --batch 4 --precision fp16
 } > gpurun_out/r2_models.jsonl 2> gpurun_out/r2_models.err
 cat gpurun_out/r2_models.jsonl | cut -c1-300
+# sanitizers last (slow)
+timeout 2400 bash tools/sanitize.sh > gpurun_out/r2_sanitize.log 2>&1; tail -12 gpurun_out/r2_sanitize.log
