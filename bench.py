@@ -29,8 +29,18 @@ sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
 
-H_PAD, W_PAD, MAXDISP = 384, 1248, 192
+MAXDISP = 192
+# content size -> zero-padded size (reference pad_to_2x: top / right); "kitti" is BASELINE.json's metric (configs[1])
+WORKLOADS = {"kitti": (375, 1242, 384, 1248), "sceneflow": (540, 960, 576, 960)}
+H_IN, W_IN, H_PAD, W_PAD = WORKLOADS["kitti"]
 METRIC = "disparity maps/sec @ 1242x375 D=192 (GwcNet_GC inference)"
+
+
+def select_workload(name):
+    """--workload sceneflow: the north_star's second shape (960x540 padded to 960x576), same model and protocol."""
+    global H_IN, W_IN, H_PAD, W_PAD, METRIC
+    H_IN, W_IN, H_PAD, W_PAD = WORKLOADS[name]
+    METRIC = f"disparity maps/sec @ {W_IN}x{H_IN} D={MAXDISP} (GwcNet_GC inference)"
 
 
 def parse():
@@ -42,6 +52,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
     ap.add_argument("--precision", default=None, help="fp32 | bf16 | fp16 (default: STB_PRECISION or fp16)")
     ap.add_argument("--features", default=None, help="2-D extractor mode: fp32 | tf32 | tf32_cl | fp16 (default: model default)")
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS),
+                    help="kitti = BASELINE.json's metric (default); sceneflow = the north_star's second shape")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=1, help="pairs in the cpu_baseline sample")
     return ap.parse_args()
@@ -57,10 +69,11 @@ def synth_weights():
 
 
 def synth_batch(batch, seed):
-    """KITTI-shape pairs: 375x1242 content, zero padded top/right to 384x1248 (reference pad_to_2x)."""
+    """KITTI-shape pairs: 375x1242 content, zero padded top/right to 384x1248 (reference pad_to_2x); --workload
+    sceneflow: 540x960 -> 576x960."""
     from stereo_toolbox_b200.synth import synth_pair
-    l, r = synth_pair(batch, 375, 1242, seed=seed, shift=37)
-    pad = lambda t: torch.nn.functional.pad(t, (0, W_PAD - 1242, H_PAD - 375, 0))
+    l, r = synth_pair(batch, H_IN, W_IN, seed=seed, shift=37)
+    pad = lambda t: torch.nn.functional.pad(t, (0, W_PAD - W_IN, H_PAD - H_IN, 0))
     return pad(l), pad(r)
 
 
@@ -115,11 +128,12 @@ def cpu_reference_run(sd, batch_pairs, steps, warmup, pair=None):
         disp = M.gwcnet_forward(sd, left, right, MAXDISP, True)
     dt = time.perf_counter() - t0
     return dict(value=batch_pairs * steps / dt, seconds=dt, cores=cores, disp=disp,
-                sample=f"{batch_pairs} pair(s)/step x {steps} step(s) of GwcNet_GC 384x1248 D=192, torch CPU fp32, {cores} threads")
+                sample=f"{batch_pairs} pair(s)/step x {steps} step(s) of GwcNet_GC {H_PAD}x{W_PAD} D=192, torch CPU fp32, {cores} threads")
 
 
 def main():
     a = parse()
+    select_workload(a.workload)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -270,7 +284,8 @@ def default_precision():
 
 
 def workload_config(batch, precision):
-    return {"workload": "GwcNet_GC inference, KITTI 1242x375 zero-padded to 1248x384 (pad_to_2x), maxdisp 192",
+    name = "KITTI" if (H_IN, W_IN) == WORKLOADS["kitti"][:2] else "SceneFlow"
+    return {"workload": f"GwcNet_GC inference, {name} {W_IN}x{H_IN} zero-padded to {W_PAD}x{H_PAD} (pad_to_2x), maxdisp 192",
             "batch_per_gpu": batch, "precision": precision, "parallelism": "batch-sharded, no collective",
             "l2": "per-step working set (1.8 GB fp32 volume + 32-ch activations) >> 126 MB L2; no explicit flush",
             "feature_extractor": "precision fp16/bf16: 2-D extractor on the same tcgen05 conv kernel (features_umma.py); "
