@@ -17,10 +17,10 @@ cut -c1-400 gpurun_out/r2_bench.json
   timeout 300 python tools/model_bench.py --model gwcnet_gc --height 576 --width 960 --batch 4 --precision fp16
 } > gpurun_out/r2_models.jsonl 2> gpurun_out/r2_models.err
 cat gpurun_out/r2_models.jsonl | cut -c1-300
-# sanitizers last (slow; SURVEY section 5)
-timeout 2400 bash tools/sanitize.sh > gpurun_out/r2_sanitize.log 2>&1; tail -12 gpurun_out/r2_sanitize.log
 # second north_star shape through the full bench contract
 timeout 600 python bench.py --workload sceneflow --steps 10 --warmup 3 > gpurun_out/r2_bench_sceneflow.json 2> gpurun_out/r2_bench_sceneflow.err; echo "bench sceneflow rc=$?"
 cut -c1-300 gpurun_out/r2_bench_sceneflow.json
 STB_HEAD_X4=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_headx4.json 2> gpurun_out/r2_bench_headx4.err; echo "bench head-x4 rc=$?"
 cut -c1-300 gpurun_out/r2_bench_headx4.json
+# sanitizers last (slow; SURVEY section 5)
+timeout 2400 bash tools/sanitize.sh > gpurun_out/r2_sanitize.log 2>&1; tail -12 gpurun_out/r2_sanitize.log
