@@ -177,6 +177,7 @@ __device__ __forceinline__ void issue_dispatch(const UArgs& a, int tq, uint32_t 
 // to the epilogue was measured to cost ALL layers (profiles/umma_issue_r01.md section 4), so the common layers get a
 // kernel that does not carry code they never execute.
 // LEAN: 0 = generic, 1 = lean / plain taps (one column block), 2 = lean / kw-merged (3 column blocks + lane realignment),
+// 4 = kw-merged single-channel classifier with fp32 output (opt-in, STB_UMMA_CLS1),
 // 3 = lean / merged transposed conv (8 parity-class blocks).
 template <int ACT, bool F16, int LEAN>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
@@ -355,7 +356,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         float sh0[32];                              // folded-BN shift of the first 32 channels stays in registers
 #pragma unroll
         for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + a.cout_off + i) : 0.f;
-        const int merge = LEAN == 2 ? 3 : (LEAN ? 1 : a.merge), Cn = a.Cn, nM = a.nM;
+        const int merge = (LEAN == 2 || LEAN == 4) ? 3 : (LEAN ? 1 : a.merge), Cn = a.Cn, nM = a.nM;
         uint32_t ground = 0;                        // accumulator round counter over all items (same order as the issuer)
         for (int tile = blockIdx.x; active && tile < a.ntiles && !(dbg & 4); tile += gridDim.x) {
           const UTile u = decode_tile(a, tile);
@@ -390,6 +391,27 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     // the round the accumulator buffer is handed back to its issuer BEFORE the arithmetic and the
                     // stores (the data is in registers): the buffer is busy ~0.3K instead of ~2.5K clocks per round,
                     // which was what the issuers were waiting for (profiles/umma_issue_r01.md).
+                    if (LEAN == 4) {
+                        // 32->1 classifier (kw-merged, fp32 out, no residual): ONE accumulator column per kw block is
+                        // live, so read three single columns instead of three 32-column blocks and realign with two
+                        // shuffles instead of 64.  Same additions in the same order as the generic path below.
+                        uint32_t v0, v1, v2;
+                        __syncwarp();
+                        tmem_ld_32x32_x1(taddr, v0);
+                        tmem_ld_32x32_x1(taddr + (uint32_t)Cn, v1);
+                        tmem_ld_32x32_x1(taddr + (uint32_t)(2 * Cn), v2);
+                        tmem_ld_wait();
+                        if (item + 2 >= items) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                        }
+                        const int ms1 = a.merge_step;
+                        const float r = __uint_as_float(v0) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1), ms1) +
+                                        __shfl_down_sync(0xffffffffu, __uint_as_float(v2), 2 * ms1);
+                        if (inb) reinterpret_cast<float*>(a.out)[vox * ostride_w + a.cout_off] = stb_act(r + sh0[0], ACT);
+                        break;                         // Cn = 16: a single column block per item
+                    }
                     float f[32];
                     __syncwarp();                      // tcgen05.ld is .sync.aligned: whole warp, converged
                     if (merge == 3) {
@@ -553,6 +575,13 @@ bool g_trace_armed = false;      // host mirror of g_umma_trace != nullptr (stb_
 
 template <int ACT, bool F16>
 int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, UArgs& a) {
+    // opt-in (STB_UMMA_CLS1=1) until confirmed on hardware: own instantiation for the single-channel classifiers
+    static const bool cls1 = getenv("STB_UMMA_CLS1") != nullptr && atoi(getenv("STB_UMMA_CLS1")) != 0;
+    if constexpr (ACT == STB_ACT_NONE) {
+        if (cls1 && !a.debug && !g_trace_armed && !a.partial && a.out_fp32 && a.Cn_valid == 1 && !a.residual &&
+            a.cblocks == 3 && a.merge == 3 && a.Cn <= 32)
+            return launch_one_impl<ACT, F16, 4>(grid, smem, st, tx, tw, a);
+    }
     const bool lean = !a.debug && !g_trace_armed && !a.partial && !a.out_fp32 && (a.Cn_valid & 31) == 0;
     if (lean && a.cblocks == 8 && a.merge == 1) return launch_one_impl<ACT, F16, 3>(grid, smem, st, tx, tw, a);
     if (lean && a.cblocks == 3 && a.merge == 3) return launch_one_impl<ACT, F16, 2>(grid, smem, st, tx, tw, a);

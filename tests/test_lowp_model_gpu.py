@@ -58,3 +58,37 @@ def test_head_x4_fast_path_matches_generic(tmp_path):
     want = R.upsample_softargmin(cost, 48, 36, 84, False, False)
     torch.testing.assert_close(fast, want, rtol=1e-4, atol=1e-4)          # the oracle, like the generic kernel's test
     torch.testing.assert_close(fast, generic, rtol=0, atol=1e-4)
+
+
+def test_classifier_instantiation_is_bit_identical(tmp_path):
+    """STB_UMMA_CLS1=1 routes the 32->1 classifiers (kw-merged, fp32 out, no residual) to their own instantiation of
+    the tcgen05 conv kernel (three single-column TMEM reads + 2 shuffles instead of three 32-column reads + 64): same
+    accumulators, same additions in the same order, so the pre-softmax cost must be bit-identical.  The switch is read
+    once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r); "
+            "from conftest import golden_state; import stereo_toolbox_b200 as S; "
+            "from stereo_toolbox_b200.synth import synth_pair; "
+            "sd, meta = golden_state('gwcnet_gc'); net = S.GwcNet_GC(meta['maxdisp'], precision='fp16'); "
+            "net.load_state_dict(sd); net = net.cuda().eval(); net.feature_tf32 = False; "
+            "l, r = synth_pair(1, 64, 128, seed=0, shift=meta['shift']); "
+            "d = net(l.cuda(), r.cuda()); torch.save((net._last_cost.cpu(), d.cpu()), %r)"
+            % (root, os.path.join(root, "tests"), str(tmp_path / "cls1.pt")))
+    subprocess.run([sys.executable, "-c", "import torch\nwith torch.no_grad():\n    exec(%r)" % code], check=True,
+                   env=dict(os.environ, STB_UMMA_CLS1="1"), timeout=300)
+    cost1, disp1 = torch.load(tmp_path / "cls1.pt")
+    sd, meta = golden_state("gwcnet_gc")
+    net = S.GwcNet_GC(meta["maxdisp"], precision="fp16")
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    net.feature_tf32 = False
+    left, right = synth_pair(1, 64, 128, seed=0, shift=meta["shift"])
+    with torch.no_grad():
+        disp0 = net(left.cuda(), right.cuda()).cpu()
+    assert torch.equal(net._last_cost.cpu(), cost1)
+    assert torch.equal(disp0, disp1)

@@ -22,5 +22,7 @@ timeout 600 python bench.py --workload sceneflow --steps 10 --warmup 3 > gpurun_
 cut -c1-300 gpurun_out/r2_bench_sceneflow.json
 STB_HEAD_X4=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_headx4.json 2> gpurun_out/r2_bench_headx4.err; echo "bench head-x4 rc=$?"
 cut -c1-300 gpurun_out/r2_bench_headx4.json
+STB_HEAD_X4=1 STB_UMMA_CLS1=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_headx4_cls1.json 2> gpurun_out/r2_bench_headx4_cls1.err; echo "bench head-x4 + cls1 rc=$?"
+cut -c1-300 gpurun_out/r2_bench_headx4_cls1.json
 # sanitizers last (slow)
 timeout 2400 bash tools/sanitize.sh > gpurun_out/r2_sanitize.log 2>&1; tail -12 gpurun_out/r2_sanitize.log
