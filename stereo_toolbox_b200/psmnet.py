@@ -135,4 +135,18 @@ class PSMNet(nn.Module):
             fr = self.feature_extraction(right)
         finally:
             torch.backends.cudnn.allow_tf32 = prev
-        return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=TrainBackend(), all_heads=True)
+        return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=self._train_backend(TrainBackend), all_heads=True)
+
+    def _train_backend(self, exact_cls):
+        """``model.train_precision``: "fp32" (default) = the exact path; "bf16" / "fp16" = train16.Umma16TrainBackend
+        (forward and data gradient of the 3-D convs on the tcgen05 kernel; kept on the model so that its per-layer adjoint
+        modules and kernel plans survive across steps)."""
+        prec = getattr(self, "train_precision", "fp32")
+        if prec == "fp32":
+            return exact_cls()
+        hit = self.__dict__.get("_train16")
+        if hit is None or hit.precision != prec:
+            from .train16 import Umma16TrainBackend
+            hit = Umma16TrainBackend(prec)
+            self.__dict__["_train16"] = hit
+        return hit

@@ -1,0 +1,74 @@
+"""Mixed-precision training backend (train16.Umma16TrainBackend) on the GPU: forward and data gradient of the 3-D convs
+on the tcgen05 kernel, weight gradient on the fp32 kernel.  The same checks as tests/test_train16_cpu.py, with the real
+kernel-backed primitives."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from conftest import GOLDEN, load_golden, load_meta
+
+UNCONFIRMED = ("written after the round-1 GPU budget was spent: the host logic is pinned on CPU (tests/test_train16_cpu.py) "
+               "and both primitives are kernels the inference / fp32 training paths already exercise, but this composition "
+               "has not run on hardware yet -- remove this mark after the first GPU trip of the next round")
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900), pytest.mark.xfail(strict=False, reason=UNCONFIRMED)]
+
+
+@pytest.mark.parametrize("k,s,p,tr,op,dims", [(3, 1, 1, False, 0, (8, 16, 32)), (1, 1, 0, False, 0, (8, 16, 32)),
+                                               (3, 2, 1, False, 0, (8, 16, 32)), (3, 2, 1, True, 1, (4, 8, 16))])
+def test_raw_conv_gradients_match_torch(k, s, p, tr, op, dims):
+    from stereo_toolbox_b200.train16 import Umma16TrainBackend, _RawConvFn
+    be = Umma16TrainBackend("bf16")
+    torch.manual_seed(0)
+    cin, cout = 32, 64
+    conv = (nn.ConvTranspose3d(cin, cout, k, s, p, output_padding=op, bias=False) if tr
+            else nn.Conv3d(cin, cout, k, s, p, bias=False)).cuda()
+    x = torch.randn(2, *dims, cin, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    y = _RawConvFn.apply(x, conv.weight, be, conv)
+    gy = torch.randn_like(y.float()).to(y.dtype)
+    y.backward(gy)
+    x2 = x.detach().float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    w2 = conv.weight.detach().to(torch.bfloat16).float().requires_grad_(True)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y2 = (F.conv_transpose3d(x2, w2, stride=s, padding=p, output_padding=op) if tr
+              else F.conv3d(x2, w2, stride=s, padding=p))
+        y2.backward(gy.float().permute(0, 4, 1, 2, 3))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    torch.testing.assert_close(y.float(), y2.permute(0, 2, 3, 4, 1), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(x.grad.float(), x2.grad.permute(0, 2, 3, 4, 1), rtol=2e-2, atol=5e-2)
+    torch.testing.assert_close(conv.weight.grad, w2.grad, rtol=1e-3, atol=1e-2)
+
+
+def test_psmnet_bf16_training_step_vs_reference():
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_state_dict, synth_pair, synth_gt
+    g = load_golden("psmnet_train.npz")
+    meta = load_meta("models.json")["psmnet"]
+    tmpl = {k: torch.zeros(s, dtype=torch.int64 if k.endswith("num_batches_tracked") else torch.float32)
+            for k, s in meta["keys"].items()}
+    z = np.load(f"{GOLDEN}/bn_calib_psmnet.npz")
+    net = S.PSMNet(32)
+    net.load_state_dict(synth_state_dict(tmpl, 0, {k: z[k] for k in z.files}), strict=True)
+    net = net.cuda().train()
+    net.train_precision = "bf16"
+    left, right = synth_pair(2, 256, 256, seed=1, shift=7)
+    gt = synth_gt(2, 256, 256).cuda()
+    preds = net(left.cuda(), right.cuda())
+    assert len(preds) == 3 and all(p.shape == (2, 1, 256, 256) for p in preds)
+    mask = (gt > 0) & (gt < 32)
+    loss = sum(w * F.smooth_l1_loss(p.squeeze(1)[mask], gt[mask], reduction="mean") for w, p in zip((0.5, 0.7, 1.0), preds))
+    loss.backward()
+    for i, p in enumerate(preds):
+        assert (p.detach().cpu()[:, :, ::2, ::2] - g[f"pred{i + 1}"]).abs().mean().item() < 0.15
+    assert abs(loss.item() - g["loss"].item()) < 0.01 * abs(g["loss"].item())
+    params = dict(net.named_parameters())
+    for name in [k[5:] for k in g if k.startswith("grad:")]:
+        got, want = params[name].grad.flatten().cpu(), g["grad:" + name].flatten()
+        cos = F.cosine_similarity(got, want, dim=0).item()
+        print(f"{name}: cos {cos:.4f} norm ratio {(got.norm() / want.norm()).item():.3f}")
+        assert cos > 0.93, (name, cos)
+        assert 0.9 < (got.norm() / want.norm()).item() < 1.1, name

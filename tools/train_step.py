@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--width", type=int, default=512)
     ap.add_argument("--maxdisp", type=int, default=192)
     ap.add_argument("--lr", type=float, default=1e-4)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp16"],
+                    help="fp32 = exact training path; bf16 / fp16 = train16.Umma16TrainBackend (tcgen05 forward + dgrad)")
     args = ap.parse_args()
     import torch.distributed as dist
     import stereo_toolbox_b200 as S
@@ -50,6 +52,7 @@ def main():
     net = S.PSMNet(args.maxdisp)
     net.load_state_dict(synth_state_dict(tmpl, 0, {k: z[k] for k in z.files}))
     net = net.cuda().train()
+    net.train_precision = args.precision
     bucket = FlatGradAllReduce(net.parameters())
     left, right = synth_pair(args.batch, args.height, args.width, seed=1000 + rank, shift=11)
     left, right = left.cuda(), right.cuda()
@@ -93,7 +96,8 @@ def main():
             "value": pairs / (step_ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "allreduce_ms": ar_ms, "allreduce_bytes": bucket.nbytes, "allreduce_busbw_gbs": bus,
             "grad_disagreement_after_allreduce": disagree, "loss": loss.item(), "scaling": "weak", "dtype": "f32",
-            "config": {"workload": f"PSMNet train step {args.height}x{args.width} D={args.maxdisp}", "batch_per_gpu": args.batch},
+            "config": {"workload": f"PSMNet train step {args.height}x{args.width} D={args.maxdisp}", "batch_per_gpu": args.batch,
+                       "precision": args.precision},
             "gpu_launches": __import__("stereo_toolbox_b200._lib", fromlist=["x"]).LAUNCH_COUNT}))
     if world > 1:
         dist.destroy_process_group()

@@ -27,5 +27,9 @@ cut -c1-300 gpurun_out/r2_bench_headx4_cls1.json
 # BASELINE config 3 shape (exact fp32 training path; the 16-bit training path is not built)
 timeout 600 python tools/train_step.py --height 576 --width 960 --batch 1 --steps 3 --warmup 1 > gpurun_out/r2_train_sceneflow.json 2> gpurun_out/r2_train_sceneflow.err; echo "train rc=$?"
 cut -c1-300 gpurun_out/r2_train_sceneflow.json
+timeout 600 python -m pytest tests/test_train16_gpu.py -m gpu -q -s --runxfail > gpurun_out/r2_train16.log 2>&1; echo "train16 rc=$?"
+grep -i "cos\|passed\|failed\|error" gpurun_out/r2_train16.log | tail -20
+timeout 600 python tools/train_step.py --height 576 --width 960 --batch 1 --steps 3 --warmup 1 --precision bf16 > gpurun_out/r2_train_sceneflow_bf16.json 2> gpurun_out/r2_train_sceneflow_bf16.err; echo "train bf16 rc=$?"
+cut -c1-300 gpurun_out/r2_train_sceneflow_bf16.json
 # sanitizers last (slow)
 timeout 2400 bash tools/sanitize.sh > gpurun_out/r2_sanitize.log 2>&1; tail -12 gpurun_out/r2_sanitize.log
