@@ -224,6 +224,21 @@ class TrainBackend:
         return A.upsample_softargmin(cost, maxdisp, H, W, align_corners)
 
 
+def train_backend_for(model):
+    """Backend of ``model.train()``: ``model.train_precision`` = "fp32" (default) -> TrainBackend, the exact path;
+    "bf16" / "fp16" -> train16.Umma16TrainBackend (forward and data gradient of the 3-D convs on the tcgen05 kernel), kept
+    on the model so that its per-layer adjoint modules and kernel plans survive across steps."""
+    prec = getattr(model, "train_precision", "fp32")
+    if prec == "fp32":
+        return TrainBackend()
+    hit = model.__dict__.get("_train16")
+    if hit is None or hit.precision != prec:
+        from .train16 import Umma16TrainBackend
+        hit = Umma16TrainBackend(prec)
+        model.__dict__["_train16"] = hit
+    return hit
+
+
 def make_backend(precision: str):
     if precision == "fp32":
         return Fp32Backend()

@@ -152,7 +152,7 @@ class GwcNet(nn.Module):
     def _forward_train(self, left, right):
         """Training step forward (exact fp32): torch 2-D extractor (+concatconv) with autograd, cost-volume path on
         TrainBackend (forward and backward in libstb200.so).  Returns [pred0, pred1, pred2, pred3] (gwcnet.py:216)."""
-        from .aggregation import TrainBackend
+        from .aggregation import train_backend_for
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = False
         try:
@@ -160,7 +160,7 @@ class GwcNet(nn.Module):
             fr = self.feature_extraction(right)
         finally:
             torch.backends.cudnn.allow_tf32 = prev
-        return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=TrainBackend(), all_heads=True)
+        return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=train_backend_for(self), all_heads=True)
 
 
 def GwcNet_G(d=192, **kw):

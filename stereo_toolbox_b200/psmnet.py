@@ -127,7 +127,7 @@ class PSMNet(nn.Module):
         """Training step forward (exact fp32): the 2-D extractor is ordinary torch (train-mode BatchNorm2d, autograd),
         the cost-volume path runs on TrainBackend -- forward and backward in libstb200.so.  Returns the reference's
         list [pred1, pred2, pred3] (stackhourglass.py:159)."""
-        from .aggregation import TrainBackend
+        from .aggregation import train_backend_for
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = prev and self.feature_mode not in (None, "fp32") and self.feature_tf32 is not False
         try:
@@ -135,18 +135,4 @@ class PSMNet(nn.Module):
             fr = self.feature_extraction(right)
         finally:
             torch.backends.cudnn.allow_tf32 = prev
-        return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=self._train_backend(TrainBackend), all_heads=True)
-
-    def _train_backend(self, exact_cls):
-        """``model.train_precision``: "fp32" (default) = the exact path; "bf16" / "fp16" = train16.Umma16TrainBackend
-        (forward and data gradient of the 3-D convs on the tcgen05 kernel; kept on the model so that its per-layer adjoint
-        modules and kernel plans survive across steps)."""
-        prec = getattr(self, "train_precision", "fp32")
-        if prec == "fp32":
-            return exact_cls()
-        hit = self.__dict__.get("_train16")
-        if hit is None or hit.precision != prec:
-            from .train16 import Umma16TrainBackend
-            hit = Umma16TrainBackend(prec)
-            self.__dict__["_train16"] = hit
-        return hit
+        return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=train_backend_for(self), all_heads=True)

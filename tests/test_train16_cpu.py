@@ -88,6 +88,32 @@ def test_raw_conv_gradients_match_torch(k, s, p, tr, op, dims):
     torch.testing.assert_close(conv.weight.grad, w2.grad, rtol=1e-4, atol=1e-4)
 
 
+def test_padded_input_channels_and_classifier_shapes():
+    """(i) an input whose channel count was zero-padded to a legal K width (GwcNet_G's 40-group volume -> 64): the data
+    gradient comes back in the padded shape with zeros in the padding; (ii) the 1-channel classifier: fp32 output, fp32
+    output gradient re-entering the kernel as a 16-channel 16-bit operand."""
+    from stereo_toolbox_b200.train16 import _RawConvFn
+    be = _make_backend("bf16")
+    torch.manual_seed(1)
+    conv = nn.Conv3d(40, 32, 3, 1, 1, bias=False)
+    vol = torch.randn(1, 40, 4, 6, 8)
+    x = be._to_cl(vol).requires_grad_(True)
+    assert x.shape == (1, 4, 6, 8, 64) and not x[..., 40:].any()
+    y = _RawConvFn.apply(x, conv.weight, be, conv)
+    y.float().sum().backward()
+    assert x.grad.shape == x.shape and not x.grad[..., 40:].any() and x.grad[..., :40].abs().sum() > 0
+    cls = nn.Conv3d(32, 1, 3, 1, 1, bias=False)
+    h = torch.randn(1, 4, 6, 8, 32).to(torch.bfloat16).requires_grad_(True)
+    c = _RawConvFn.apply(h, cls.weight, be, cls)
+    assert c.dtype == torch.float32 and c.shape == (1, 4, 6, 8, 1)
+    c.square().sum().backward()
+    h2 = h.detach().float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    w2 = cls.weight.detach().to(torch.bfloat16).float().requires_grad_(True)
+    F.conv3d(h2, w2, padding=1).square().sum().backward()
+    torch.testing.assert_close(h.grad.float(), h2.grad.permute(0, 2, 3, 4, 1), rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(cls.weight.grad, w2.grad, rtol=1e-4, atol=1e-4)
+
+
 def test_adjoint_modules_are_cached_and_follow_weight_updates():
     be = _make_backend("bf16")
     conv = nn.Conv3d(16, 32, 3, 1, 1, bias=False)
