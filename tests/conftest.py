@@ -25,6 +25,13 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+# Tests that launch kernel code / kernel configurations which have never run on hardware (written after the round-1 GPU
+# budget was spent) are opt-in: a deadlocked kernel would take the whole GPU run with it.  tools/trip_r2.sh sets the switch.
+import os as _os
+unconfirmed_kernels = pytest.mark.skipif(_os.environ.get("STB200_RUN_UNCONFIRMED") != "1",
+                                         reason="launches kernels not yet confirmed on hardware; set STB200_RUN_UNCONFIRMED=1")
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name))
     return {k: torch.from_numpy(z[k]) for k in z.files}

@@ -6,7 +6,7 @@ motivated it were measured separately (model on CPU 0.1159 px, CUDA path in benc
 import pytest
 import torch
 
-from conftest import golden_state
+from conftest import golden_state, unconfirmed_kernels
 from oracle import ref_lowp, ref_models as M
 
 UNCONFIRMED = ("written after the round-1 GPU budget was spent: composes kernels that are green at these shapes, host code pinned on CPU, but not yet run on hardware -- remove this mark after the first GPU trip of the next round (tools/trip_r2.sh)")
@@ -35,6 +35,7 @@ def test_gwcnet_gc_16bit_sits_on_the_storage_model(prec, dtype):
     assert to_model < 0.5 * to_ref, (to_model, to_ref)
 
 
+@unconfirmed_kernels
 def test_head_x4_fast_path_matches_generic(tmp_path):
     """STB_HEAD_X4=1 selects ``upsample_softargmin_x4_kernel`` (outD == 4*D, align_corners=False: compile-time bin
     weights, no per-bin index arithmetic).  It evaluates the generic kernel's expressions in the generic kernel's order,
@@ -60,6 +61,7 @@ def test_head_x4_fast_path_matches_generic(tmp_path):
     torch.testing.assert_close(fast, generic, rtol=0, atol=1e-4)
 
 
+@unconfirmed_kernels
 def test_classifier_instantiation_is_bit_identical(tmp_path):
     """STB_UMMA_CLS1=1 routes the 32->1 classifiers (kw-merged, fp32 out, no residual) to their own instantiation of
     the tcgen05 conv kernel (three single-column TMEM reads + 2 shuffles instead of three 32-column reads + 64): same
