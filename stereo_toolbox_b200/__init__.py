@@ -11,8 +11,9 @@ from .cfnet import CFNet
 from .pcwnet import PCWNet_G, PCWNet_GC
 from .igev_stereo import IGEVStereo
 from .checkpoint import load_checkpoint_flexible
+from .evaluation import speed_and_memory_test
 
 __all__ = ["build_gwc_volume", "build_concat_volume", "build_concat_volume_unmasked", "groupwise_correlation",
            "disparity_regression", "disparityregression", "upsample_softargmin", "CorrBlock1D",
            "Combined_Geo_Encoding_Volume", "GwcNet_G", "GwcNet_GC", "PSMNet", "RAFTStereo", "ACVNet", "CFNet", "PCWNet_G", "PCWNet_GC", "IGEVStereo",
-           "load_checkpoint_flexible"]
+           "load_checkpoint_flexible", "speed_and_memory_test"]

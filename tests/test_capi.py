@@ -112,3 +112,15 @@ def test_load_checkpoint_flexible(tmp_path):
     torch.save(sd, plain)
     net2 = S.load_checkpoint_flexible(S.GwcNet_G(32), str(plain))
     assert all(torch.equal(net2.state_dict()[k], v) for k, v in sd.items())
+
+
+def test_speed_and_memory_test_keeps_the_reference_signature():
+    """evaluation/speed_and_memory_test.py:11: (model, resolution=None, batch_size=1, num_iterations=100, device='cuda:0')."""
+    import inspect
+    import stereo_toolbox_b200 as S
+    params = inspect.signature(S.speed_and_memory_test).parameters
+    assert list(params)[:5] == ["model", "resolution", "batch_size", "num_iterations", "device"]
+    assert params["resolution"].default is None and params["batch_size"].default == 1
+    assert params["num_iterations"].default == 100 and params["device"].default == "cuda:0"
+    with pytest.raises(ValueError):
+        S.speed_and_memory_test(torch.nn.Identity(), device="cpu")

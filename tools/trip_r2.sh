@@ -32,5 +32,8 @@ timeout 600 python -m pytest tests/test_train16_gpu.py -m gpu -q -s --runxfail >
 grep -i "cos\|passed\|failed\|error" gpurun_out/r2_train16.log | tail -20
 timeout 600 python tools/train_step.py --height 576 --width 960 --batch 1 --steps 3 --warmup 1 --precision bf16 > gpurun_out/r2_train_sceneflow_bf16.json 2> gpurun_out/r2_train_sceneflow_bf16.err; echo "train bf16 rc=$?"
 cut -c1-300 gpurun_out/r2_train_sceneflow_bf16.json
+# the reference's published Table 3 protocol (RTX 4090 numbers in BASELINE.md) on the drop-in models
+timeout 1500 python tools/table3.py --iters 10 > gpurun_out/r2_table3.md 2> gpurun_out/r2_table3.err; echo "table3 rc=$?"
+cat gpurun_out/r2_table3.md | cut -c1-260
 # sanitizers last (slow)
 timeout 2400 bash tools/sanitize.sh > gpurun_out/r2_sanitize.log 2>&1; tail -12 gpurun_out/r2_sanitize.log
