@@ -27,7 +27,7 @@ import torch.nn.functional as F
 
 from .igev import BasicConv, IGEVCostVolume
 from .mobilenetv2 import MobileNetV2Trunk
-from .raft_stereo import ConvGRU, ResidualBlock, _Trunk, _interp, _pool2x
+from .raft_stereo import ConvGRU, ResidualBlock, _Trunk, _interp, _pool2x, glue_channels_last
 
 
 # ------------------------------------------------------------------------------------------ 2-D building blocks
@@ -254,6 +254,9 @@ class IGEVStereo(IGEVCostVolume):
             std = torch.tensor([0.229, 0.224, 0.225], device=image1.device).view(1, 3, 1, 1)
             image1 = 2 * (image1 * std + mean) - 1.0
             image2 = 2 * (image2 * std + mean) - 1.0
+
+        if getattr(self, "channels_last", False):                   # opt-in: NHWC torch glue (raft_stereo.glue_channels_last)
+            image1, image2 = glue_channels_last(self, image1, image2)
 
         # ---- torch glue: 2-D features (igev_stereo.py:195-204)
         features_left = self.feature(image1)

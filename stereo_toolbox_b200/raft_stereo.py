@@ -17,6 +17,21 @@ import torch.nn.functional as F
 from .functional import CorrBlock1D
 
 
+def glue_channels_last(model: nn.Module, *images):
+    """Opt-in (``model.channels_last = True``): run the torch glue (2-D encoders, ConvGRUs, heads) on channels-last
+    tensors.  cuDNN's tensor-core convolution kernels are NHWC; fed NCHW tensors torch brackets every conv with
+    nchw<->nhwc transposes (measured on the GwcNet extractor: ~46 % of its GPU time, profiles/ncu_launches_r01.txt).
+    Same arithmetic, so results agree to summation order.  Only the 4-D weights of 2-D convs are re-laid (``Module.to(
+    memory_format=channels_last)`` would also touch the 5-D Conv3d weights of the hot path and raise); the hot-path ops
+    make their inputs contiguous themselves (ops._f32c).  Returns the images in channels-last layout."""
+    if not model.__dict__.get("_glue_cl_done"):
+        for m in model.modules():
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+        model.__dict__["_glue_cl_done"] = True
+    return tuple(t.contiguous(memory_format=torch.channels_last) for t in images)
+
+
 def _norm(kind: str, ch: int):
     if kind == "batch":
         return nn.BatchNorm2d(ch)
@@ -246,7 +261,7 @@ class RAFTStereo(nn.Module):
         """Convex 9-tap upsampling (raft_stereo.py:81-93)."""
         N, D, H, W = flow.shape
         f = 2 ** self.args.n_downsample
-        mask = torch.softmax(mask.view(N, 1, 9, f, f, H, W), dim=2)
+        mask = torch.softmax(mask.contiguous().view(N, 1, 9, f, f, H, W), dim=2)      # (channels-last glue: NCHW order first)
         up = F.unfold(f * flow, [3, 3], padding=1).view(N, D, 9, 1, 1, H, W)
         up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
         return up.reshape(N, D, f * H, f * W)
@@ -318,6 +333,8 @@ class RAFTStereo(nn.Module):
             std = torch.tensor([0.229, 0.224, 0.225], device=image1.device).view(1, 3, 1, 1)
             image1 = 2 * (image1 * std + mean) - 1.0
             image2 = 2 * (image2 * std + mean) - 1.0
+        if getattr(self, "channels_last", False):
+            image1, image2 = glue_channels_last(self, image1, image2)
         if a.shared_backbone:
             *cnet_list, x = self.cnet(torch.cat((image1, image2), dim=0), dual_inp=True, num_layers=a.n_gru_layers)
             fmap1, fmap2 = self.conv2(x).split(x.shape[0] // 2, dim=0)

@@ -148,3 +148,27 @@ def test_swap_is_scoped():
         S.build_gwc_volume(torch.zeros(1, 8, 4, 4), torch.zeros(1, 8, 4, 4), 2, 4)
     with pytest.raises(StbError):
         S.GwcNet_G(32).eval()(torch.zeros(1, 3, 64, 128), torch.zeros(1, 3, 64, 128))
+
+
+@pytest.mark.parametrize("family", ["raft", "igev"])
+def test_channels_last_glue_is_numerically_equivalent(family):
+    """``model.channels_last = True`` re-lays the torch glue (2-D convs) as NHWC: same arithmetic, same result (to summation
+    order) as the default NCHW run, against the reference's output."""
+    from stereo_toolbox_b200.synth import synth_pair
+    if family == "raft":
+        g, (sd, meta), seed = load_golden("raft_stereo.npz"), golden_state("raft_stereo", calib=False), 2
+    else:
+        g, (sd, meta), seed = load_golden("igev_stereo.npz"), golden_state("igev_stereo"), 8
+    with oracle_hot_path():
+        import stereo_toolbox_b200 as S
+        net = S.RAFTStereo() if family == "raft" else S.IGEVStereo({"max_disp": meta["max_disp"]})
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        net.channels_last = True
+        left, right = synth_pair(1, 64, 128, seed=seed, shift=meta["shift"])
+        with torch.no_grad():
+            out = net(left, right, iters=meta["iters"])
+        assert any(m.weight.is_contiguous(memory_format=torch.channels_last) and not m.weight.is_contiguous()
+                   for m in net.modules() if isinstance(m, torch.nn.Conv2d) and m.weight.shape[1] > 1 and m.weight.shape[2] > 1)
+        assert all(m.weight.is_contiguous() for m in net.modules() if isinstance(m, torch.nn.Conv3d))
+    assert (out - g["disp"]).abs().mean().item() < 1e-3

@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cuda-graph", action="store_true", help="raft: replay one captured GRU iteration")
+    ap.add_argument("--channels-last", action="store_true", help="raft / igev: NHWC torch glue (model.channels_last)")
     args = ap.parse_args()
 
     import stereo_toolbox_b200 as S
@@ -64,6 +65,8 @@ def main():
     net = net.cuda().eval()
     if args.cuda_graph:
         net.cuda_graph = True
+    if args.channels_last:
+        net.channels_last = True
     left, right = synth_pair(args.batch, args.height, args.width, seed=4, shift=9)
     gl, gr = left.cuda(), right.cuda()
     fwd = dict(iters=args.iters) if args.model in ("raft", "igev") else {}
@@ -84,7 +87,7 @@ def main():
     ms = ts[len(ts) // 2]
     res = dict(model=args.model, precision=args.precision if args.model != "raft" else "fp32",
                shape=[args.batch, args.height, args.width], maxdisp=args.maxdisp,
-               iters=fwd.get("iters"), ms_per_forward=ms, maps_per_s=args.batch / (ms * 1e-3),
+               iters=fwd.get("iters"), cuda_graph=args.cuda_graph, channels_last=args.channels_last, ms_per_forward=ms, maps_per_s=args.batch / (ms * 1e-3),
                peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, out_shape=list(out.shape),
                finite=bool(torch.isfinite(out.float()).all().item()))
     print(json.dumps(res))
