@@ -405,6 +405,33 @@ def register_torch_ops():
     lib.impl("conv3d_bn_act", _conv_meta, "Meta")
     lib.impl("corr1d", lambda a, b, s: a.new_empty(a.shape[0], a.shape[2], a.shape[3], b.shape[3]), "Meta")
     lib.impl("corr1d_lookup", lambda p, c, r, n: c.new_empty(c.shape[0], n * (2 * r + 1), c.shape[2], c.shape[3]), "Meta")
+    # ---- the remaining entry points of the path (IGEV geometry lookup / gates, ACVNet pieces, explicit-probability heads)
+    lib.define("avgpool_last(Tensor x) -> Tensor")
+    lib.define("geo_lookup(Tensor[] geos, Tensor[] corrs, Tensor disp, Tensor coords, int radius) -> Tensor")
+    lib.define("feature_gate(Tensor x, Tensor gate_logits) -> Tensor")
+    lib.define("softmax_d(Tensor x) -> Tensor")
+    lib.define("disparity_regression(Tensor prob, int maxdisp, bool keepdim) -> Tensor")
+    lib.define("disparity_variance(Tensor prob, int maxdisp, Tensor disparity) -> Tensor")
+    lib.define("patch_dw(Tensor x, Tensor weight, int dilation) -> Tensor")
+    lib.define("block_attention(Tensor qkv, Tensor qkv_bias, int num_heads, int[] block) -> Tensor")
+    lib.impl("avgpool_last", lambda x: avgpool_last(x), "CUDA")
+    lib.impl("geo_lookup", lambda g, c, d, x, r: geo_lookup(list(g), list(c), d, x, r), "CUDA")
+    lib.impl("feature_gate", lambda x, g: feature_gate(x, g), "CUDA")
+    lib.impl("softmax_d", lambda x: softmax_d(x), "CUDA")
+    lib.impl("disparity_regression", lambda p, d, k: disparity_regression(p, d, k), "CUDA")
+    lib.impl("disparity_variance", lambda p, d, disp: disparity_variance(p, d, disp), "CUDA")
+    lib.impl("patch_dw", lambda x, w, d: patch_dw(x, w, d), "CUDA")
+    lib.impl("block_attention", lambda q, b, h, blk: block_attention(q, b, h, tuple(blk)), "CUDA")
+    lib.impl("avgpool_last", lambda x: x.new_empty(tuple(x.shape[:-1]) + (x.shape[-1] // 2,)), "Meta")
+    lib.impl("geo_lookup", lambda g, c, d, x, r: d.new_empty(g[0].shape[0], len(g) * (2 * r + 1) * (g[0].shape[3] + 1),
+                                                             g[0].shape[1], g[0].shape[2]), "Meta")
+    lib.impl("feature_gate", lambda x, g: torch.empty_like(x), "Meta")
+    lib.impl("softmax_d", lambda x: torch.empty_like(x), "Meta")
+    lib.impl("disparity_regression", lambda p, d, k: p.new_empty((p.shape[0], 1) + tuple(p.shape[2:]) if k
+                                                                 else (p.shape[0],) + tuple(p.shape[2:])), "Meta")
+    lib.impl("disparity_variance", lambda p, d, disp: p.new_empty((p.shape[0], 1) + tuple(p.shape[2:])), "Meta")
+    lib.impl("patch_dw", lambda x, w, d: torch.empty_like(x), "Meta")
+    lib.impl("block_attention", lambda q, b, h, blk: q.new_empty((q.shape[0], q.shape[1] // 3) + tuple(q.shape[2:])), "Meta")
     # autograd formulas (torch.library.register_autograd): the dispatcher ops are differentiable like the reference's
     # functions; the adjoints are the kernels of csrc/train.cu (see autograd.py)
     from . import autograd as A

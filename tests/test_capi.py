@@ -124,3 +124,31 @@ def test_speed_and_memory_test_keeps_the_reference_signature():
     assert params["num_iterations"].default == 100 and params["device"].default == "cuda:0"
     with pytest.raises(ValueError):
         S.speed_and_memory_test(torch.nn.Identity(), device="cpu")
+
+
+def test_torch_ops_fake_kernels_give_reference_shapes():
+    """torch.ops.stb200.*: every op has a fake (Meta) kernel, so tracing / shape propagation around a patched model works
+    without a device; shapes follow the reference functions."""
+    from stereo_toolbox_b200 import ops
+    ops.register_torch_ops()
+    T = torch.ops.stb200
+    m = lambda *s: torch.empty(*s, device="meta")
+    assert T.gwc_volume(m(2, 320, 6, 20), m(2, 320, 6, 20), 12, 40).shape == (2, 40, 12, 6, 20)
+    assert T.concat_volume(m(2, 12, 6, 20), m(2, 12, 6, 20), 12, True).shape == (2, 24, 12, 6, 20)
+    assert T.upsample_softargmin(m(2, 1, 12, 6, 20), 48, 24, 80, False).shape == (2, 24, 80)
+    assert T.conv3d_bn_act(m(1, 32, 8, 8, 8), m(64, 32, 3, 3, 3), None, None, None, None, 2, 1, "relu", None, False, 0).shape \
+        == (1, 64, 4, 4, 4)
+    assert T.conv3d_bn_act(m(1, 64, 4, 4, 4), m(64, 32, 3, 3, 3), None, None, None, None, 2, 1, "none", None, True, 1).shape \
+        == (1, 32, 8, 8, 8)
+    assert T.corr1d(m(1, 256, 8, 16), m(1, 256, 8, 16), True).shape == (1, 8, 16, 16)
+    assert T.corr1d_lookup([m(1, 8, 16, 16), m(1, 8, 16, 8)], m(1, 2, 8, 16), 4, 2).shape == (1, 18, 8, 16)
+    assert T.avgpool_last(m(1, 8, 16, 16)).shape == (1, 8, 16, 8)
+    geos, corrs = [m(1, 8, 16, 8, 12), m(1, 8, 16, 8, 6)], [m(1, 8, 16, 16), m(1, 8, 16, 8)]
+    assert T.geo_lookup(geos, corrs, m(1, 1, 8, 16), m(1, 8, 16, 1), 4).shape == (1, 162, 8, 16)     # IGEVStereo/update.py:76
+    assert T.feature_gate(m(1, 8, 12, 8, 16), m(1, 8, 8, 16)).shape == (1, 8, 12, 8, 16)
+    assert T.softmax_d(m(1, 1, 12, 8, 16)).shape == (1, 1, 12, 8, 16)
+    assert T.disparity_regression(m(2, 12, 8, 16), 12, False).shape == (2, 8, 16)
+    assert T.disparity_regression(m(2, 12, 8, 16), 12, True).shape == (2, 1, 8, 16)
+    assert T.disparity_variance(m(2, 12, 8, 16), 12, m(2, 1, 8, 16)).shape == (2, 1, 8, 16)
+    assert T.patch_dw(m(1, 40, 12, 8, 16), m(40, 1, 1, 3, 3), 2).shape == (1, 40, 12, 8, 16)
+    assert T.block_attention(m(1, 96, 4, 8, 8), m(96), 4, [4, 4, 4]).shape == (1, 32, 4, 8, 8)
