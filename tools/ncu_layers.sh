@@ -3,20 +3,10 @@
 # Launch order inside one layer_bench run of ONE layer: #0 the kernel instance's one-off smem-base query (grid 1),
 # #1 the warm-up conv, #2.. the timed convs  ->  skip 2, capture 1.   Run under gpurun (1 GPU); reports land in gpurun_out/.
 mkdir -p gpurun_out
-METRICS_GREP='gpu__time_duration.sum|dram__bytes_read.sum |dram__bytes_write.sum |sm__pipe_tensor_cycles_active.avg.pct|sm__throughput.avg.pct|l1tex__data_pipe_lsu_wavefronts_mem_shared.sum |smsp__warp_issue_stalled.*_per_warp_active.pct|launch__registers_per_thread|launch__occupancy_limit'
 for L in "64->32 k3 s2T" "128->64 k3 s2T" "32->64 k3 s2" "64->128 k3 s2" "32->32 k3 s1" "32->1 k3 s1"; do
   tag=$(echo "$L" | tr -c 'A-Za-z0-9' '_')
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3d_umma_kernel --launch-skip 2 --launch-count 1 \
     -f -o gpurun_out/ncu_layer_$tag python tools/layer_bench.py --only "$L" --reps 1 > gpurun_out/ncu_layer_$tag.log 2>&1
   echo "== $L rc=$?"
-  ncu -i gpurun_out/ncu_layer_$tag.ncu-rep --page raw --csv 2>/dev/null | python - "$METRICS_GREP" <<'PY'
-import csv, re, sys
-pat = re.compile(sys.argv[1])
-rows = list(csv.reader(sys.stdin))
-if len(rows) >= 3:
-    names, units, vals = rows[0], rows[1], rows[-1]
-    for n, u, v in zip(names, units, vals):
-        if pat.search(n + " "):
-            print(f"  {n} = {v} {u}")
-PY
+  python tools/ncu_summary.py gpurun_out/ncu_layer_$tag.ncu-rep --md 2>/dev/null | tail -2
 done
