@@ -161,3 +161,87 @@ class _HeadFn(torch.autograd.Function):
 def upsample_softargmin(cost, maxdisp, out_h, out_w, align_corners=False):
     """[B,1,D,h,w] or [B,D,h,w] -> [B,out_h,out_w]; differentiable w.r.t. cost."""
     return _HeadFn.apply(cost, maxdisp, out_h, out_w, align_corners)
+
+
+# ------------------------------------------------------------------------------------------ CorrBlock1D (RAFT-Stereo training)
+# Forward = the CUDA kernels of csrc/corr1d.cu.  The adjoints are composed from library calls for now (cuBLAS einsum for the
+# all-pairs correlation, scatter-add for the lookup): they are plain dense / gather adjoints, run once per iteration, and
+# are not on the inference path.  Checked against torch autograd of the oracle restatement (tests/test_raft_train_cpu.py).
+class _Corr1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, scale):
+        ctx.save_for_backward(fmap1, fmap2)
+        ctx.s = (fmap1.shape[1] ** -0.5) if scale else 1.0
+        return ops.corr1d(fmap1, fmap2, scale)
+
+    @staticmethod
+    def backward(ctx, g):                         # g [B,H,W1,W2]
+        f1, f2 = ctx.saved_tensors
+        g = g * ctx.s
+        g1 = torch.einsum("bhij,bchj->bchi", g, f2.float()) if ctx.needs_input_grad[0] else None
+        g2 = torch.einsum("bhij,bchi->bchj", g, f1.float()) if ctx.needs_input_grad[1] else None
+        return g1, g2, None
+
+
+def corr1d(fmap1, fmap2, scale=True):
+    return _Corr1dFn.apply(fmap1, fmap2, scale)
+
+
+class _AvgPoolLastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.w = x.shape[-1]
+        return ops.avgpool_last(x)
+
+    @staticmethod
+    def backward(ctx, g):                         # y[..., j] = (x[..., 2j] + x[..., 2j+1]) / 2; an odd last column is dropped
+        gx = (0.5 * g).repeat_interleave(2, dim=-1)
+        if gx.shape[-1] != ctx.w:
+            gx = torch.nn.functional.pad(gx, (0, ctx.w - gx.shape[-1]))
+        return gx
+
+
+def avgpool_last(x):
+    return _AvgPoolLastFn.apply(x)
+
+
+class _Corr1dLookupFn(torch.autograd.Function):
+    """out[b, l*(2r+1)+k, h, w] = linear interpolation of level l at x = coords[b,0,h,w] / 2^l + (k - r), taps outside the
+    row contribute zero (RAFTStereo/corr.py:127-146).  Differentiable w.r.t. the pyramid levels only: the reference detaches
+    the coordinates before every lookup (raft_stereo.py:154)."""
+
+    @staticmethod
+    def forward(ctx, coords, radius, num_levels, *levels):
+        ctx.save_for_backward(coords)
+        ctx.cfg = (radius, num_levels, [tuple(l.shape) for l in levels])
+        return ops.corr1d_lookup(list(levels), coords, radius, num_levels)
+
+    @staticmethod
+    def backward(ctx, g):                         # g [B, L*(2r+1), H, W1]
+        (coords,) = ctx.saved_tensors
+        radius, num_levels, shapes = ctx.cfg
+        K = 2 * radius + 1
+        B, _, H, W1 = g.shape
+        g = g.view(B, num_levels, K, H, W1).permute(0, 1, 3, 4, 2)            # [B,L,H,W1,K]
+        dx = torch.arange(-radius, radius + 1, device=g.device, dtype=torch.float32)
+        x0c = coords[:, 0].float()
+        grads = []
+        for l, shape in enumerate(shapes):
+            if l >= num_levels or not ctx.needs_input_grad[3 + l]:
+                grads.append(None)
+                continue
+            W2 = shape[-1]
+            x = x0c[..., None] / (2 ** l) + dx                                # [B,H,W1,K]
+            i0 = torch.floor(x)
+            f = x - i0
+            i0 = i0.long()
+            gl = torch.zeros(shape, device=g.device, dtype=torch.float32)
+            for idx, wgt in ((i0, 1.0 - f), (i0 + 1, f)):
+                ok = (idx >= 0) & (idx < W2)
+                gl.scatter_add_(3, idx.clamp(0, W2 - 1), torch.where(ok, wgt * g[:, l], torch.zeros_like(f)))
+            grads.append(gl)
+        return (None, None, None) + tuple(grads)
+
+
+def corr1d_lookup(levels, coords, radius, num_levels):
+    return _Corr1dLookupFn.apply(coords, radius, num_levels, *levels)

@@ -64,15 +64,25 @@ class CorrBlock1D:
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
         self.num_levels = num_levels
         self.radius = radius
-        corr = ops.corr1d(fmap1, fmap2, scale=True)          # [B,H,W1,W2]
+        # training (gradients reach the feature maps): the differentiable forms of autograd.py -- same forward kernels
+        self._diff = torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad)
+        if self._diff:
+            from . import autograd as A
+            corr1d_, pool_ = A.corr1d, A.avgpool_last
+        else:
+            corr1d_, pool_ = ops.corr1d, ops.avgpool_last
+        corr = corr1d_(fmap1, fmap2, True)                    # [B,H,W1,W2]
         self._levels = [corr]
         for _ in range(self.num_levels):                      # reference stores num_levels+1 entries (:122-125)
-            corr = ops.avgpool_last(corr)
+            corr = pool_(corr)
             self._levels.append(corr)
         b, h, w1, _ = self._levels[0].shape
         self.corr_pyramid = [c.view(b * h * w1, 1, 1, c.shape[-1]) for c in self._levels]
 
     def __call__(self, coords):
+        if self._diff:
+            from . import autograd as A
+            return A.corr1d_lookup(self._levels, coords, self.radius, self.num_levels)
         return ops.corr1d_lookup(self._levels, coords, self.radius, self.num_levels)
 
     @staticmethod

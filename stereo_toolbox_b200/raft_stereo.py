@@ -324,10 +324,9 @@ class RAFTStereo(nn.Module):
         return hit["coords"].clone(), hit["mask"]
 
     def forward(self, image1, image2, iters=None, flow_init=None, test_mode=False):
-        if self.training:
-            raise NotImplementedError("stereo_toolbox_b200: the training path is not built yet; call model.eval()")
         a = self.args
-        iters = a.valid_iters if iters is None else iters
+        if iters is None:
+            iters = a.train_iters if self.training else a.valid_iters       # raft_stereo.py:99-103
         if not self.imagenet_norm:
             mean = torch.tensor([0.485, 0.456, 0.406], device=image1.device).view(1, 3, 1, 1)
             std = torch.tensor([0.229, 0.224, 0.225], device=image1.device).view(1, 3, 1, 1)
@@ -356,6 +355,15 @@ class RAFTStereo(nn.Module):
         if flow_init is not None:
             coords1 = coords1 + flow_init
         flow_up = None
+        if self.training:
+            # raft_stereo.py:105-107,152-188: every iterate is upsampled and returned.  Gradients reach the feature maps
+            # through the differentiable CorrBlock1D (autograd.py: forward kernels of csrc/corr1d.cu, composed adjoints);
+            # the update block is torch.  fp32 throughout (the reference's autocast is an optimisation, not semantics).
+            preds = []
+            for _ in range(iters):
+                net_list, up_mask, coords1 = self._iteration(net_list, inp_list, corr_fn, coords0, coords1)
+                preds.append(-self.upsample_flow(coords1 - coords0, up_mask)[:, :1])
+            return preds
         if getattr(self, "cuda_graph", False) and flow_init is None and iters > 1:
             coords1, up_mask = self._iterate_graphed(net_list, inp_list, corr_fn, coords0, coords1, iters)
             flow_up = self.upsample_flow(coords1 - coords0, up_mask)[:, :1]

@@ -432,6 +432,34 @@ def variants():
     json.dump(meta, open(os.path.join(HERE, "variants.json"), "w"))
 
 
+def raft_train():
+    """One RAFT-Stereo training step of the reference on CPU (train mode, BatchNorm frozen as its constructor does,
+    3 iterations, default args): the per-iteration predictions, a sequence loss (L1 to a synthetic ground truth,
+    gamma = 0.9) and the gradients of parameters on both sides of CorrBlock1D -- the feature network only receives
+    gradient through the all-pairs correlation + pyramid + lookup."""
+    from stereo_toolbox_b200.synth import synth_gt
+    net = ref("RAFTStereo.raft_stereo").RAFTStereo()
+    _load_synth(net)
+    net.train()
+    net.freeze_bn()
+    left, right = synth_pair(1, 64, 128, seed=2, shift=3)
+    gt = synth_gt(1, 64, 128)[:, None] * 0.25
+    preds = net(left, right, iters=3)
+    loss = sum(0.9 ** (len(preds) - i - 1) * (p - gt).abs().mean() for i, p in enumerate(preds))
+    loss.backward()
+    names = ["fnet.conv1.weight", "fnet.layer2.0.conv1.weight", "fnet.conv2.weight", "cnet.conv1.weight",
+             "update_block.encoder.convc1.weight", "update_block.gru08.convz.weight", "update_block.flow_head.conv2.weight",
+             "update_block.mask.2.weight", "context_zqr_convs.0.weight"]
+    params = dict(net.named_parameters())
+    out = {"loss": loss.detach()}
+    for i, p in enumerate(preds):
+        out[f"pred{i}"] = p.detach()[:, :, ::2, ::2]
+    for n in names:          # large tensors: every k-th element, k = numel // 20000 (tests apply the same rule)
+        flat = params[n].grad.detach().flatten()
+        out["grad:" + n] = flat[::max(1, flat.numel() // 20000)]
+    save("raft_train.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]
