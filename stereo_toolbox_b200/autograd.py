@@ -245,3 +245,58 @@ class _Corr1dLookupFn(torch.autograd.Function):
 
 def corr1d_lookup(levels, coords, radius, num_levels):
     return _Corr1dLookupFn.apply(coords, radius, num_levels, *levels)
+
+
+# ------------------------------------------------------------------------------------------ geometry encoding (IGEV training)
+class _GeoLookupFn(torch.autograd.Function):
+    """Combined_Geo_Encoding_Volume.__call__ (IGEVStereo/geometry.py:35-59): forward = stb_geo_lookup_f32.  Differentiable
+    w.r.t. the geometry-volume and correlation pyramids; the disparity is detached before every lookup by the reference
+    (igev_stereo.py:238).  Output channel order per level: C*(2r+1) geometry taps (channel-major), then 2r+1 correlation taps."""
+
+    @staticmethod
+    def forward(ctx, disp, coords, radius, n_levels, *pyr):
+        geos, corrs = list(pyr[:n_levels]), list(pyr[n_levels:])
+        ctx.save_for_backward(disp, coords)
+        ctx.cfg = (radius, n_levels, [tuple(t.shape) for t in geos], [tuple(t.shape) for t in corrs])
+        return ops.geo_lookup(geos, corrs, disp, coords, radius)
+
+    @staticmethod
+    def backward(ctx, g):
+        disp, coords = ctx.saved_tensors
+        radius, L, gshapes, cshapes = ctx.cfg
+        K = 2 * radius + 1
+        B, _, H, W = g.shape
+        C = gshapes[0][3]
+        g = g.permute(0, 2, 3, 1).reshape(B, H, W, L, (C + 1) * K)
+        d = disp.reshape(B, H, W).float()
+        xc0 = coords.reshape(B, H, W).float()
+        dx = torch.arange(-radius, radius + 1, device=g.device, dtype=torch.float32)
+
+        def scatter(shape, x, grad):                  # x, grad: [..., K] taps along the last axis of `shape`
+            n = shape[-1]
+            i0 = torch.floor(x)
+            f = x - i0
+            i0 = i0.long()
+            out = torch.zeros(shape, device=grad.device, dtype=torch.float32)
+            for idx, wgt in ((i0, 1.0 - f), (i0 + 1, f)):
+                ok = (idx >= 0) & (idx < n)
+                out.scatter_add_(out.dim() - 1, idx.clamp(0, n - 1), torch.where(ok, wgt * grad, torch.zeros_like(grad)))
+            return out
+
+        ggeo, gcorr = [], []
+        for l in range(L):
+            gl = g[:, :, :, l]
+            x = d[..., None] / (2 ** l) + dx                                                   # [B,H,W,K]
+            if ctx.needs_input_grad[4 + l]:
+                ggeo.append(scatter(gshapes[l], x[..., None, :].expand(B, H, W, C, K), gl[..., :C * K].reshape(B, H, W, C, K)))
+            else:
+                ggeo.append(None)
+            if ctx.needs_input_grad[4 + L + l]:
+                gcorr.append(scatter(cshapes[l], xc0[..., None] / (2 ** l) - d[..., None] / (2 ** l) + dx, gl[..., C * K:]))
+            else:
+                gcorr.append(None)
+        return (None, None, None, None) + tuple(ggeo) + tuple(gcorr)
+
+
+def geo_lookup(geos, corrs, disp, coords, radius):
+    return _GeoLookupFn.apply(disp, coords, radius, len(geos), *geos, *corrs)

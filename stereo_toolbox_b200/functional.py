@@ -98,20 +98,32 @@ class Combined_Geo_Encoding_Volume:
     def __init__(self, init_fmap1, init_fmap2, geo_volume, num_levels=2, radius=4):
         self.num_levels = num_levels
         self.radius = radius
-        corr = ops.corr1d(init_fmap1, init_fmap2, scale=False)
-        geo = ops.geo_permute(geo_volume)                     # [B,H,W,C,D]
+        # training: differentiable forms (autograd.py) -- same forward kernels, the layout permute as a torch op
+        self._diff = torch.is_grad_enabled() and any(t.requires_grad for t in (init_fmap1, init_fmap2, geo_volume))
+        if self._diff:
+            from . import autograd as A
+            corr = A.corr1d(init_fmap1, init_fmap2, False)
+            geo = geo_volume.float().permute(0, 3, 4, 1, 2).contiguous()
+            pool_ = A.avgpool_last
+        else:
+            corr = ops.corr1d(init_fmap1, init_fmap2, scale=False)
+            geo = ops.geo_permute(geo_volume)                 # [B,H,W,C,D]
+            pool_ = ops.avgpool_last
         self._geos, self._corrs = [geo], [corr]
         for _ in range(self.num_levels - 1):
-            geo = ops.avgpool_last(geo)
+            geo = pool_(geo)
             self._geos.append(geo)
         for _ in range(self.num_levels - 1):
-            corr = ops.avgpool_last(corr)
+            corr = pool_(corr)
             self._corrs.append(corr)
         b, h, w, c, _ = self._geos[0].shape
         self.geo_volume_pyramid = [g.view(b * h * w, c, 1, g.shape[-1]) for g in self._geos]
         self.init_corr_pyramid = [x.view(b * h * w, 1, 1, x.shape[-1]) for x in self._corrs]
 
     def __call__(self, disp, coords):
+        if self._diff:
+            from . import autograd as A
+            return A.geo_lookup(self._geos, self._corrs, disp, coords, self.radius)
         return ops.geo_lookup(self._geos, self._corrs, disp, coords, self.radius)
 
     @staticmethod

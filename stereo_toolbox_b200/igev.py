@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .aggregation import make_backend
+from .aggregation import TrainBackend, make_backend
 from .functional import Combined_Geo_Encoding_Volume
 
 
@@ -133,16 +133,22 @@ class IGEVCostVolume(nn.Module):
 
     def stage(self, match_left, match_right, features_left: List[torch.Tensor]):
         """The whole hot path of one IGEV forward up to the GRU loop; ``IGEVStereo`` (igev_stereo.py) inherits it."""
-        if self.training:
-            raise NotImplementedError("stereo_toolbox_b200: inference path only (model.eval()); see DESIGN.md")
-        be = self._be
+        training = self.training
+        be = TrainBackend() if training else self._be          # train(): exact fp32, forward + backward in libstb200.so
         D4 = self.max_disp // 4
-        vol = ops.gwc_volume(match_left, match_right, D4, 8)                       # build_gwc_volume(..., 8)  :206
+        if training:
+            vol = be.volume_gwc_concat(match_left, match_right, None, None, D4, 8)
+        else:
+            vol = ops.gwc_volume(match_left, match_right, D4, 8)                   # build_gwc_volume(..., 8)  :206
         x = self.corr_stem.run(be, be.from_ncdhw(vol))                             # :207
         x = self.corr_feature_att.run(be, x, features_left[0])                     # :208
         geo = self.cost_agg.run(be, x, features_left)                              # :209
         cost = be.cost_ncdhw(be.conv(self.classifier, geo))                        # :212  [B,1,D/4,H/4,W/4]
-        init_disp = ops.upsample_softargmin(cost, D4, cost.shape[3], cost.shape[4]).unsqueeze(1)   # :212-213 (keepdim)
+        if training:      # a [B,D/4,H/4,W/4] tensor: torch softmax + expectation (their autograd), :212-213
+            prob = torch.softmax(cost[:, 0], dim=1)
+            init_disp = (prob * torch.arange(D4, device=cost.device, dtype=prob.dtype).view(1, D4, 1, 1)).sum(1, keepdim=True)
+        else:
+            init_disp = ops.upsample_softargmin(cost, D4, cost.shape[3], cost.shape[4]).unsqueeze(1)   # :212-213 (keepdim)
         geo_ncdhw = be.to_ncdhw(geo, 8)
         geo_fn = Combined_Geo_Encoding_Volume(match_left.float(), match_right.float(), geo_ncdhw,
                                               num_levels=self.corr_levels, radius=self.corr_radius)   # :229-230

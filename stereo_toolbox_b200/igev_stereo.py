@@ -243,12 +243,12 @@ class IGEVStereo(IGEVCostVolume):
         return context_upsample(disp * 4.0, spx_pred).unsqueeze(1)
 
     def forward(self, image1, image2, iters=None, flow_init=None, test_mode=None):
-        if self.training:
-            raise NotImplementedError("stereo_toolbox_b200: IGEVStereo is built for inference (model.eval()); the "
-                                      "geometry-lookup adjoint is not built, see DESIGN.md")
         a = self.args
-        iters = a.valid_iters if iters is None else iters
-        a.mixed_precision = False                                    # igev_stereo.py:182-184 (eval)
+        if iters is None:
+            iters = a.train_iters if self.training else a.valid_iters      # igev_stereo.py:172-176
+        if test_mode is None:
+            test_mode = not self.training                                  # :177-184
+        a.mixed_precision = False      # the reference's training autocast is an optimisation, not semantics: fp32 here
         if not self.imagenet_norm:
             mean = torch.tensor([0.485, 0.456, 0.406], device=image1.device).view(1, 3, 1, 1)
             std = torch.tensor([0.229, 0.224, 0.225], device=image1.device).view(1, 3, 1, 1)
@@ -272,7 +272,6 @@ class IGEVStereo(IGEVCostVolume):
         # ---- hot path: volume + 3-D aggregation + soft-argmin + geometry-encoding pyramids (:205-213, :229-230)
         init_disp, geo_fn, _ = self.stage(match_left, match_right, features_left)
 
-        test_mode = True if test_mode is None else test_mode         # :185-187 (eval default)
         if not test_mode:                                            # :217-221
             spx_pred = F.softmax(self.spx(self.spx_2(self.spx_4(features_left[0]), stem_2x)), 1)
 

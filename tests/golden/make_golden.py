@@ -460,6 +460,36 @@ def raft_train():
     save("raft_train.npz", **out)
 
 
+def igev_train():
+    """One IGEV-Stereo training step of the reference on CPU (train mode: batch-statistic BatchNorm, test_mode False,
+    2 iterations, max_disp 64; timm stub as in igev_model): upsampled initial disparity, per-iteration predictions, an L1
+    loss, and gradients of parameters that only receive gradient through hot-path pieces (volume, 3-D stage incl. the k4
+    transposed convs and feature gates, soft-argmin, all-pairs correlation + geometry lookup)."""
+    from stereo_toolbox_b200.mobilenetv2 import MobileNetV2Trunk
+    from stereo_toolbox_b200.synth import synth_gt
+    sys.modules["timm_0_5_4"].create_model = lambda *a, **k: MobileNetV2Trunk()
+    net = ref("IGEVStereo.igev_stereo").IGEVStereo({"max_disp": 64})
+    z = np.load(os.path.join(HERE, "bn_calib_igev_stereo.npz"))
+    net.load_state_dict(synth_state_dict(net.state_dict(), 0, {k: z[k] for k in z.files}), strict=True)
+    net.train()
+    left, right = synth_pair(2, 64, 128, seed=8, shift=5)
+    gt = synth_gt(2, 64, 128)[:, None] * 0.25
+    init_disp, preds = net(left, right, iters=2)
+    loss = (init_disp - gt).abs().mean() + sum(0.9 ** (len(preds) - i - 1) * (p - gt).abs().mean() for i, p in enumerate(preds))
+    loss.backward()
+    names = ["corr_stem.conv.weight", "cost_agg.conv1.0.conv.weight", "cost_agg.conv3_up.conv.weight",
+             "cost_agg.conv1_up.conv.weight", "cost_agg.feature_att_8.feat_att.1.weight", "classifier.weight", "desc.weight",
+             "conv.conv.weight", "feature.conv_stem.weight", "update_block.encoder.convc1.weight", "spx.0.weight"]
+    params = dict(net.named_parameters())
+    out = {"loss": loss.detach(), "init_disp": init_disp.detach()[:, :, ::2, ::2]}
+    for i, p in enumerate(preds):
+        out[f"pred{i}"] = p.detach()[:, :, ::2, ::2]
+    for n in names:
+        flat = params[n].grad.detach().flatten()
+        out["grad:" + n] = flat[::max(1, flat.numel() // 20000)]
+    save("igev_train.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]

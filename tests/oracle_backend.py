@@ -91,6 +91,19 @@ class OracleBackend:
         return R.upsample_softargmin(cost, maxdisp, H, W, align_corners, False)
 
 
+class OracleTrainBackend(OracleBackend):
+    """aggregation.TrainBackend's semantics (raw conv -> the layer's own BatchNorm3d module, i.e. batch statistics in
+    train mode -> residual -> activation) with torch's convolution instead of the CUDA kernels."""
+    name = "oracle-train"
+
+    def conv(self, layer, x, act="none", residual=None):
+        conv, bn = _split(layer)
+        y = conv(x)
+        if bn is not None:
+            y = bn(y)
+        return R.activation(y if residual is None else y + residual, act)
+
+
 def _patch_dw(x, weight, dilation, out=None, c_off=0):
     C = weight.shape[0]
     y = R.depthwise_patch(x[:, c_off:c_off + C], weight, dilation)
@@ -141,6 +154,9 @@ def oracle_hot_path():
         if hasattr(mod, "make_backend"):
             undo.append((mod, "make_backend", mod.make_backend))
             mod.make_backend = lambda precision: OracleBackend()
+        if hasattr(mod, "TrainBackend"):
+            undo.append((mod, "TrainBackend", mod.TrainBackend))
+            mod.TrainBackend = OracleTrainBackend
     for name, fn in _OPS.items():
         undo.append((ops, name, getattr(ops, name)))
         setattr(ops, name, fn)
