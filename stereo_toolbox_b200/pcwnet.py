@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .aggregation import convbn_3d, make_backend
+from .aggregation import TrainBackend, convbn_3d, make_backend
 from .cascade import hourglass, hourglassup
 from .cfnet import BasicBlock, Mish, _classif, _dres, _dres1, _head2d, convbn
 
@@ -143,14 +143,13 @@ class PCWNet(nn.Module):
         return self
 
     def forward(self, left, right):
-        if self.training:
-            raise NotImplementedError("stereo_toolbox_b200: PCWNet runs in eval mode only (model.eval()); see DESIGN.md")
         if not self.use_concat_volume:
             raise NotImplementedError("PCWNet_G: the reference's refinement reads features_left['finetune_feature'], which its "
                                       "feature_extraction only returns with concat_feature=True (pcwnet.py:127-131, 493)")
-        be = self._be
+        # train(): exact fp32 -- TrainBackend (forward + backward of the 3-D path in libstb200.so, batch-statistic BatchNorm)
+        be = TrainBackend() if self.training else self._be
         prev = torch.backends.cudnn.allow_tf32
-        torch.backends.cudnn.allow_tf32 = prev and self.precision != "fp32"       # exact 2-D nets on the exact path
+        torch.backends.cudnn.allow_tf32 = prev and self.precision != "fp32" and not self.training    # exact 2-D nets on the exact path
         try:
             fl, fr = self.feature_extraction(left), self.feature_extraction(right)
             H, W = left.shape[2:]
@@ -159,10 +158,16 @@ class PCWNet(nn.Module):
             c = be.conv(self.dres0[2], be.conv(self.dres0[0], vols[0], "mish"), "mish")
             cost0 = be.conv(self.dres1[2], be.conv(self.dres1[0], c, "mish"), "none", residual=c)
             combine = self.combine1.run(be, cost0, vols[1], vols[2], vols[3])
-            out3 = self.dres4.run(be, self.dres3.run(be, self.dres2.run(be, combine)))
+            out1 = self.dres2.run(be, combine)
+            out2 = self.dres3.run(be, out1)
+            out3 = self.dres4.run(be, out2)
             cost3 = be.conv(self.classif3[2], be.conv(self.classif3[0], out3, "mish"))
             self._last_cost = cost3
             pred3 = be.head(cost3, self.maxdisp, H, W, align_corners=True).unsqueeze(1)          # pcwnet.py:486-489
+            if self.training:                                                                    # pcwnet.py:430-458
+                head = lambda cls, t: be.head(be.conv(cls[2], be.conv(cls[0], t, "mish")), self.maxdisp, H, W, align_corners=True)
+                pred0, pred1, pred2 = head(self.classif0, cost0), head(self.classif1, out1), head(self.classif2, out2)
+                pred_combine = head(self.classif4, combine)
             # ---- 2-D refinement at full resolution (pcwnet.py:491-506)
             up = lambda t: F.interpolate(t, [H, W], mode="bilinear", align_corners=True)
             rl, rr = up(fl["finetune_feature"]), up(fr["finetune_feature"])
@@ -170,7 +175,10 @@ class PCWNet(nn.Module):
             corr = build_correlation_volume(rl, rr_warp, 24)
             x = torch.cat((rl - rr_warp, rl, self.dispupsample(pred3), pred3, corr), dim=1)
             self._last = dict(pred3=pred3.squeeze(1))
-            return self.refinenet3(x, pred3).squeeze(1)
+            disp_finetune = self.refinenet3(x, pred3).squeeze(1)
+            if self.training:                                                                    # pcwnet.py:480
+                return [pred0, pred_combine, pred1, pred2, pred3.squeeze(1), disp_finetune]
+            return disp_finetune
         finally:
             torch.backends.cudnn.allow_tf32 = prev
 

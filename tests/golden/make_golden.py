@@ -490,6 +490,47 @@ def igev_train():
     save("igev_train.npz", **out)
 
 
+def _grad_sample(params, prefixes):
+    """First conv-like weight under each prefix; large tensors sampled every k-th element (k = numel // 20000)."""
+    out = {}
+    for pre in prefixes:
+        name = next(n for n, p in params.items() if n.startswith(pre) and n.endswith("weight") and p.dim() >= 4 and p.grad is not None)
+        flat = params[name].grad.detach().flatten()
+        out["grad:" + name] = flat[::max(1, flat.numel() // 20000)]
+    return out
+
+
+def pcwnet_train():
+    """One PCWNet_GC training step of the reference on CPU (train mode, batch 2, maxdisp 64; the ``Tensor.get_device``
+    patch of pcwnet()): the six predictions (pcwnet.py:480), a smooth-L1 loss over them, gradients of one weight per
+    sub-network."""
+    import torch.nn.functional as F
+    from stereo_toolbox_b200.synth import synth_gt
+    orig = torch.Tensor.get_device
+    torch.Tensor.get_device = lambda self: self.device
+    try:
+        net = ref("PCWNet.pcwnet").PCWNet_GC(64)
+        z = np.load(os.path.join(HERE, "bn_calib_pcwnet_gc.npz"))
+        net.load_state_dict(synth_state_dict(net.state_dict(), 0, {k: z[k] for k in z.files}), strict=True)
+        net.train()
+        left, right = synth_pair(2, 64, 128, seed=7, shift=5)
+        gt = synth_gt(2, 64, 128)
+        preds = net(left, right)
+        mask = (gt > 0) & (gt < 64)
+        loss = sum(F.smooth_l1_loss(p[mask], gt[mask], reduction="mean") for p in preds)
+        loss.backward()
+    finally:
+        torch.Tensor.get_device = orig
+    out = {"loss": loss.detach()}
+    for i, p in enumerate(preds):
+        out[f"pred{i}"] = p.detach()[:, ::2, ::2]
+    out.update(_grad_sample(dict(net.named_parameters()),
+                            ["dres0.0.0.", "dres1.", "combine1.conv1.", "combine1.conv9.", "dres3.conv5.", "classif0.",
+                             "classif4.", "refinenet3.", "dispupsample.", "feature_extraction.firstconv.",
+                             "feature_extraction.layer4."]))
+    save("pcwnet_train.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]
