@@ -15,7 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .aggregation import convbn_3d, make_backend
+from .aggregation import TrainBackend, convbn_3d, make_backend
 from .cascade import hourglass, hourglassup
 
 
@@ -224,22 +224,32 @@ class cfnet(nn.Module):
         gwc = (lf * wr).view(B, groups, C // groups, S, H, W).mean(dim=2)
         return torch.cat((gwc, concat, samples.unsqueeze(1).float()), dim=1)
 
-    def _stage(self, be, vol, c0, c1, hg2, hg3, classif1, samples):
-        """confidence0/1 + two hourglasses + classifier + softmax over the samples -> expectation over the samples."""
+    def _stage(self, be, vol, c0, c1, hg2, hg3, classif1, samples, softmax):
+        """confidence0/1 + two hourglasses + classifier + softmax over the samples -> expectation over the samples.
+        Also returns the two intermediate volumes the training-only classifiers read (cfnet.py:615-628)."""
         x = be.from_ncdhw(vol)
         c = be.conv(c0[2], be.conv(c0[0], x, "mish"), "mish")
         c = be.conv(c1[2], be.conv(c1[0], c, "mish"), "none", residual=c)
-        out2 = hg3.run(be, hg2.run(be, c))
+        out1 = hg2.run(be, c)
+        out2 = hg3.run(be, out1)
         cost = be.cost_ncdhw(be.conv(classif1[2], be.conv(classif1[0], out2, "mish")))[:, 0]       # [B,S,H,W]
-        prob = ops.softmax_d(cost)
-        return prob, torch.sum(prob * samples, dim=1, keepdim=True)
+        prob = softmax(cost)
+        return prob, torch.sum(prob * samples, dim=1, keepdim=True), c, out1
 
     def forward(self, left, right):
-        if self.training:
-            raise NotImplementedError("stereo_toolbox_b200: CFNet runs in eval mode only (model.eval()); see DESIGN.md")
-        be = self._be
+        tr = self.training
+        # train(): exact fp32 -- TrainBackend (forward + backward of the 3-D path in libstb200.so, batch-statistic BatchNorm);
+        # the explicit-probability ops on [B,S,H,W] tensors are torch there (their autograd)
+        be = TrainBackend() if tr else self._be
+        if tr:
+            softmax = lambda c: torch.softmax(c, dim=1)
+            regression = lambda p, D: torch.sum(p * torch.arange(D, device=p.device, dtype=p.dtype).view(1, D, 1, 1), 1)
+            variance = lambda p, D, d: torch.sum(p * (torch.arange(D, device=p.device, dtype=p.dtype).view(1, D, 1, 1) - d) ** 2,
+                                                 1, keepdim=True)
+        else:
+            softmax, regression, variance = ops.softmax_d, ops.disparity_regression, ops.disparity_variance
         prev = torch.backends.cudnn.allow_tf32
-        torch.backends.cudnn.allow_tf32 = prev and self.precision != "fp32"       # exact 2-D features on the exact path
+        torch.backends.cudnn.allow_tf32 = prev and self.precision != "fp32" and not tr       # exact 2-D features on the exact path
         try:
             fl, fr = self.feature_extraction(left), self.feature_extraction(right)
         finally:
@@ -257,27 +267,40 @@ class cfnet(nn.Module):
         out2_4 = self.dres3.run(be, out1_4)
         cost2 = be.cost_ncdhw(be.conv(self.classif2[2], be.conv(self.classif2[0], out2_4, "mish")))[:, 0]
         D8 = self.maxdisp // 8
-        prob = ops.softmax_d(cost2)
-        pred2_s4 = ops.disparity_regression(prob, D8).unsqueeze(1)
-        var = ops.disparity_variance(prob, D8, pred2_s4).sqrt()
-        mn = pred2_s4 - (self.gamma_s3 + 1) * var - self.beta_s3
-        mx = pred2_s4 + (self.gamma_s3 + 1) * var + self.beta_s3
+        prob = softmax(cost2)
+        pred2_s4 = regression(prob, D8).unsqueeze(1)
+        cur = pred2_s4.detach()                                                                 # cfnet.py:541
+        var = variance(prob, D8, cur).sqrt()
+        mn = cur - (self.gamma_s3 + 1) * var - self.beta_s3
+        mx = cur + (self.gamma_s3 + 1) * var + self.beta_s3
         up = lambda t, s: F.interpolate(t * 2, [H // s, W // s], mode="bilinear", align_corners=True)
         mn, mx = self.generate_search_range(self.sample_count_s3 + 1, up(mn, 4), up(mx, 4), scale=2)
-        samples = self.generate_disparity_samples(mn, mx, self.sample_count_s3).float()
-        vol3 = self._sampled_volume(fl, fr, "gw3", "concat_feature3", samples, self.num_groups)
-        prob3, pred1_s3 = self._stage(be, vol3, self.confidence0_s3, self.confidence1_s3, self.confidence2_s3,
-                                      self.confidence3_s3, self.confidence_classif1_s3, samples)
-        var3 = torch.sum(prob3 * (pred1_s3 - samples) ** 2, 1, keepdim=True).sqrt()            # disparity_variance_confidence
-        mn = pred1_s3 - (self.gamma_s2 + 1) * var3 - self.beta_s2
-        mx = pred1_s3 + (self.gamma_s2 + 1) * var3 + self.beta_s2
+        samples_s3 = self.generate_disparity_samples(mn, mx, self.sample_count_s3).float()
+        vol3 = self._sampled_volume(fl, fr, "gw3", "concat_feature3", samples_s3, self.num_groups)
+        prob3, pred1_s3, cost0_s3, out1_s3 = self._stage(be, vol3, self.confidence0_s3, self.confidence1_s3, self.confidence2_s3,
+                                                         self.confidence3_s3, self.confidence_classif1_s3, samples_s3, softmax)
+        cur = pred1_s3.detach()                                                                 # cfnet.py:568
+        var3 = torch.sum(prob3 * (cur - samples_s3) ** 2, 1, keepdim=True).sqrt()               # disparity_variance_confidence
+        mn = cur - (self.gamma_s2 + 1) * var3 - self.beta_s2
+        mx = cur + (self.gamma_s2 + 1) * var3 + self.beta_s2
         mn, mx = self.generate_search_range(self.sample_count_s2 + 1, up(mn, 2), up(mx, 2), scale=1)
-        samples = self.generate_disparity_samples(mn, mx, self.sample_count_s2).float()
-        vol2 = self._sampled_volume(fl, fr, "gw2", "concat_feature2", samples, self.num_groups // 2)
-        _, pred1_s2 = self._stage(be, vol2, self.confidence0_s2, self.confidence1_s2, self.confidence2_s2,
-                                  self.confidence3_s2, self.confidence_classif1_s2, samples)
+        samples_s2 = self.generate_disparity_samples(mn, mx, self.sample_count_s2).float()
+        vol2 = self._sampled_volume(fl, fr, "gw2", "concat_feature2", samples_s2, self.num_groups // 2)
+        _, pred1_s2, cost0_s2, out1_s2 = self._stage(be, vol2, self.confidence0_s2, self.confidence1_s2, self.confidence2_s2,
+                                                     self.confidence3_s2, self.confidence_classif1_s2, samples_s2, softmax)
         self._last = dict(pred2_s4=pred2_s4, pred1_s3=pred1_s3)
-        return F.interpolate(pred1_s2 * 2, [H, W], mode="bilinear", align_corners=True).squeeze(1)
+        full = lambda t, k: F.interpolate(t * k, [H, W], mode="bilinear", align_corners=True).squeeze(1)
+        if not tr:
+            return full(pred1_s2, 2)
+        # ---- training: the nine predictions of cfnet.py:651
+        head = lambda cls, t: be.head(be.conv(cls[2], be.conv(cls[0], t, "mish")), self.maxdisp, H, W, align_corners=True)
+        sampled = lambda cls, t, smp: torch.sum(softmax(be.cost_ncdhw(be.conv(cls[2], be.conv(cls[0], t, "mish")))[:, 0]) * smp,
+                                                dim=1, keepdim=True)
+        return [head(self.classif0, costs[0]), head(self.classif1, out1_4), full(pred2_s4, 8),
+                full(sampled(self.confidence_classif0_s3, cost0_s3, samples_s3), 4),
+                full(sampled(self.confidence_classifmid_s3, out1_s3, samples_s3), 4), full(pred1_s3, 4),
+                full(sampled(self.confidence_classif0_s2, cost0_s2, samples_s2), 2),
+                full(sampled(self.confidence_classifmid_s2, out1_s2, samples_s2), 2), full(pred1_s2, 2)]
 
 
 def CFNet(d=192, **kw):

@@ -531,6 +531,36 @@ def pcwnet_train():
     save("pcwnet_train.npz", **out)
 
 
+def cfnet_train():
+    """One CFNet training step of the reference on CPU (train mode, batch 2, maxdisp 64; ``Tensor.get_device`` patch as in
+    cfnet()): the nine predictions (cfnet.py:651), a smooth-L1 loss over them, gradients of one weight per sub-network."""
+    import torch.nn.functional as F
+    from stereo_toolbox_b200.synth import synth_gt
+    orig = torch.Tensor.get_device
+    torch.Tensor.get_device = lambda self: self.device
+    try:
+        net = ref("CFNet.cfnet").CFNet(64)
+        z = np.load(os.path.join(HERE, "bn_calib_cfnet.npz"))
+        net.load_state_dict(synth_state_dict(net.state_dict(), 0, {k: z[k] for k in z.files}), strict=True)
+        net.train()
+        left, right = synth_pair(2, 64, 128, seed=6, shift=5)
+        gt = synth_gt(2, 64, 128)
+        preds = net(left, right)
+        mask = (gt > 0) & (gt < 64)
+        loss = sum(F.smooth_l1_loss(p[mask], gt[mask], reduction="mean") for p in preds)
+        loss.backward()
+    finally:
+        torch.Tensor.get_device = orig
+    out = {"loss": loss.detach()}
+    for i, p in enumerate(preds):
+        out[f"pred{i}"] = p.detach()[:, ::2, ::2]
+    out.update(_grad_sample(dict(net.named_parameters()),
+                            ["dres0.0.0.", "dres0_6.", "combine1.conv1.", "dres3.conv5.", "classif0.", "classif2.",
+                             "confidence0_s3.", "confidence2_s3.conv6.", "confidence_classifmid_s3.", "confidence0_s2.",
+                             "confidence3_s2.", "confidence_classif0_s2.", "feature_extraction.firstconv."]))
+    save("cfnet_train.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]

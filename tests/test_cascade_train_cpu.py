@@ -47,3 +47,8 @@ def _check(g, net, preds, loss, n_preds):
 def test_pcwnet_gc_training_step_vs_reference():
     g, net, preds, loss = _step("pcwnet_gc", lambda S, m: S.PCWNet_GC(m["maxdisp"]), 7, "pcwnet_train.npz")
     _check(g, net, preds, loss, 6)                      # pcwnet.py:480
+
+
+def test_cfnet_training_step_vs_reference():
+    g, net, preds, loss = _step("cfnet", lambda S, m: S.CFNet(m["maxdisp"]), 6, "cfnet_train.npz")
+    _check(g, net, preds, loss, 9)                      # cfnet.py:651

@@ -1,0 +1,41 @@
+"""PCWNet_GC / CFNet training paths on the GPU (3-D path on aggregation.TrainBackend: forward + backward kernels of
+libstb200.so, Mish, align_corners=True heads at x4 / x8) vs one training step of the reference."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, golden_state
+
+UNCONFIRMED = ("written after the round-1 GPU budget was spent: every kernel on this path is green in tests/test_gpu_train.py, "
+               "the model wiring is pinned on CPU (tests/test_cascade_train_cpu.py); not yet run on hardware")
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), pytest.mark.xfail(strict=False, reason=UNCONFIRMED)]
+
+
+@pytest.mark.parametrize("key,ctor,seed,fixture,n", [("pcwnet_gc", "PCWNet_GC", 7, "pcwnet_train.npz", 6),
+                                                     ("cfnet", "CFNet", 6, "cfnet_train.npz", 9)])
+def test_training_step_vs_reference(key, ctor, seed, fixture, n):
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair, synth_gt
+    g = load_golden(fixture)
+    sd, meta = golden_state(key)
+    net = getattr(S, ctor)(meta["maxdisp"])
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    left, right = synth_pair(2, 64, 128, seed=seed, shift=5)
+    gt = synth_gt(2, 64, 128).cuda()
+    preds = net(left.cuda(), right.cuda())
+    assert len(preds) == n
+    mask = (gt > 0) & (gt < meta["maxdisp"])
+    loss = sum(F.smooth_l1_loss(p[mask], gt[mask], reduction="mean") for p in preds)
+    loss.backward()
+    # CFNet's integer disparity samplers turn 1e-6 of upstream difference into whole-sample jumps at isolated pixels:
+    # compare the median error of each prediction, and the loss
+    for i, p in enumerate(preds):
+        assert (p.detach().cpu()[:, ::2, ::2] - g[f"pred{i}"]).abs().median().item() < 1e-3, i
+    assert abs(loss.item() - g["loss"].item()) < 2e-2 * abs(g["loss"].item())
+    params = dict(net.named_parameters())
+    for name in [k[5:] for k in g if k.startswith("grad:")]:
+        got, want = params[name].grad.flatten().cpu(), g["grad:" + name]
+        got = got[::max(1, got.numel() // 20000)]
+        cos = F.cosine_similarity(got, want, dim=0).item()
+        assert cos > 0.99, (name, cos)
