@@ -13,9 +13,39 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .aggregation import convbn_3d, deconvbn_3d, make_backend
+from .aggregation import TrainBackend, convbn_3d, deconvbn_3d, make_backend
 from .features2d import GwcFeatures, convbn
 from .gwcnet import GwcNet, _classif
+
+
+def block_attention_train(qkv, qkv_bias, num_heads, block):
+    """Training-path form of the windowed attention core (ACVNet/submodule.py:392-428) as torch ops, so that autograd
+    provides the adjoint (the inference path runs csrc/acv.cu; an adjoint kernel is not built).  qkv [B,3C,D,H,W] with
+    channel order (3, heads, head_dim) -> [B,C,D,H,W].  Padding semantics of the reference: H and W are padded up to a
+    multiple of the window with tokens whose q,k,v equal the bias; padded and real tokens are masked from each other only
+    when BOTH pads are non-zero -- with exactly one pad the reference's ``mask[:, -0:, :] = 1`` marks every token."""
+    B, C3, D, H0, W0 = qkv.shape
+    C, (b0, b1, b2) = C3 // 3, block
+    ph, pw = (-H0) % b1, (-W0) % b2
+    if ph or pw:
+        canvas = qkv_bias.to(qkv.dtype).view(1, C3, 1, 1, 1).expand(B, C3, D, H0 + ph, W0 + pw).clone()
+        canvas[:, :, :, :H0, :W0] = qkv
+        qkv = canvas
+    H, W = H0 + ph, W0 + pw
+    nd, nh, nw, hd, T = D // b0, H // b1, W // b2, C // num_heads, b0 * b1 * b2
+    win = qkv.view(B, 3, num_heads, hd, nd, b0, nh, b1, nw, b2).permute(1, 0, 4, 6, 8, 2, 5, 7, 9, 3)
+    q, k, v = win.reshape(3, B, nd * nh * nw, num_heads, T, hd).unbind(0)
+    logits = torch.matmul(q, k.transpose(-1, -2)) * hd ** -0.5                       # [B,windows,heads,T,T]
+    if ph and pw:
+        m = torch.zeros(H, W, device=qkv.device)
+        m[H - ph:, :] = 1
+        m[:, W - pw:] = 1
+        m = m.view(nh, b1, nw, b2).permute(0, 2, 1, 3).reshape(nh * nw, 1, b1 * b2).expand(-1, b0, -1).reshape(nh * nw, T)
+        sep = (m[:, :, None] != m[:, None, :]).to(logits.dtype) * -1000.0            # [nh*nw, T, T]
+        logits = logits + sep.repeat(nd, 1, 1)[None, :, None]
+    out = torch.matmul(torch.softmax(logits, dim=-1), v)                             # [B,windows,heads,T,hd]
+    out = out.view(B, nd, nh, nw, num_heads, b0, b1, b2, hd).permute(0, 4, 8, 1, 5, 2, 6, 3, 7).reshape(B, C, D, H, W)
+    return out[:, :, :, :H0, :W0]
 
 
 class attention_block(nn.Module):
@@ -44,6 +74,10 @@ class attention_block(nn.Module):
         return hit[1]
 
     def run(self, be, x):
+        if getattr(be, "training_path", False):           # training: qkv Linear as a differentiable 1x1x1 conv, torch attention core
+            w = self.qkv_3d.weight
+            qkv = torch.nn.functional.conv3d(x, w.view(w.shape[0], w.shape[1], 1, 1, 1), self.qkv_3d.bias)
+            return be.conv(self.final1x1, block_attention_train(qkv, self.qkv_3d.bias, self.num_heads, self.block))
         qkv = be.conv(self._qkv_conv(), x)
         o = be.block_attention(qkv, self.qkv_3d.bias, self.num_heads, self.block)
         return be.conv(self.final1x1, o)
@@ -169,8 +203,44 @@ class ACVNet(nn.Module):
 
     def forward(self, left, right):
         if self.training:
-            raise NotImplementedError(
-                "stereo_toolbox_b200: the training (autograd / batch-stat BatchNorm3d) path is not built yet; "
-                "call model.eval() -- see DESIGN.md 'out of scope this round'")
+            return self._forward_train(left, right)
         fl, fr = self._features(left, right)
         return self.aggregate(fl, fr, left.shape[2], left.shape[3])
+
+    def _forward_train(self, left, right):
+        """Training step forward (exact fp32; acv.py:162-235).  3-D convolutions, volumes and heads on TrainBackend (forward
+        and backward kernels of libstb200.so, batch-statistic BatchNorm3d); the pieces without an adjoint kernel -- the
+        depthwise patch convs, the windowed attention core, softmax over D times the concat volume -- as torch ops.
+        Returns [pred_attention, pred0, pred1, pred2] / [pred0, pred1, pred2] (freeze_attn_weights) / [pred_attention]
+        (attn_weights_only)."""
+        import contextlib
+        be = TrainBackend()
+        H, W = left.shape[2:]
+        D4 = self.maxdisp // 4
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            with (torch.no_grad() if self.freeze_attn_weights else contextlib.nullcontext()):        # acv.py:164-178
+                fl, fr = self.feature_extraction(left), self.feature_extraction(right)
+                vol = be.volume_gwc_concat(fl["gwc_feature"], fr["gwc_feature"], None, None, D4, self.num_groups)
+                v1 = self.patch(vol)
+                pv = torch.cat((self.patch_l1(v1[:, :8]), self.patch_l2(v1[:, 8:24]), self.patch_l3(v1[:, 24:40])), dim=1)
+                c = be.conv(self.dres1_att_[2], be.conv(self.dres1_att_[0], pv, "relu"))
+                c = self.dres2_att_.run(be, c)
+                att = be.conv(self.classif_att_[2], be.conv(self.classif_att_[0], c, "relu"))    # [B,1,D/4,H/4,W/4]
+            preds = []
+            if not self.freeze_attn_weights:
+                preds.append(be.head(att, self.maxdisp, H, W, align_corners=False))
+            if self.attn_weights_only:
+                return preds
+            cl, cr = self.concatconv(fl["gwc_feature"]), self.concatconv(fr["gwc_feature"])
+            ac = torch.softmax(att, dim=2) * be.volume_concat(cl, cr, D4, mask_left=False)       # acv.py:196
+            cost0 = be.conv(self.dres0[2], be.conv(self.dres0[0], ac, "relu"), "relu")
+            cost0 = be.conv(self.dres1[2], be.conv(self.dres1[0], cost0, "relu"), "none", residual=cost0)
+            out1 = self.dres2.run(be, cost0)
+            out2 = self.dres3.run(be, out1)
+            for cls, t in ((self.classif0, cost0), (self.classif1, out1), (self.classif2, out2)):
+                preds.append(be.head(be.conv(cls[2], be.conv(cls[0], t, "relu")), self.maxdisp, H, W, align_corners=False))
+            return preds
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev

@@ -169,6 +169,7 @@ class TrainBackend:
     like the reference -- it is the layer's own torch module applied to the raw convolution output -- and the residual
     add / activation are torch elementwise ops, so their autograd is torch's.  fp32, reference layouts (NCDHW)."""
     name = "fp32-train"
+    training_path = True          # every call differentiable; model code picks its torch-autograd forms where no adjoint kernel exists
 
     def __init__(self):
         self.prof = _NoProf()

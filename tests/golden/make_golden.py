@@ -561,6 +561,34 @@ def cfnet_train():
     save("cfnet_train.npz", **out)
 
 
+def acvnet_train():
+    """One ACVNet training step of the reference on CPU (train mode, batch 2, maxdisp 64, 64x144 pair: the 1/16-scale
+    attention runs in the one-sided padding case): the four predictions (acv.py:235), a smooth-L1 loss, gradients of one
+    weight per sub-network incl. the patch convs and the attention block."""
+    import torch.nn.functional as F
+    from stereo_toolbox_b200.synth import synth_gt
+    net = ref("ACVNet.acv").ACVNet(64)
+    z = np.load(os.path.join(HERE, "bn_calib_acvnet.npz"))
+    net.load_state_dict(synth_state_dict(net.state_dict(), 0, {k: z[k] for k in z.files}), strict=True)
+    net.train()
+    left, right = synth_pair(2, 64, 144, seed=3, shift=5)
+    gt = synth_gt(2, 64, 144)
+    preds = net(left, right)
+    mask = (gt > 0) & (gt < 64)
+    loss = sum(F.smooth_l1_loss(p[mask], gt[mask], reduction="mean") for p in preds)
+    loss.backward()
+    out = {"loss": loss.detach()}
+    for i, p in enumerate(preds):
+        out[f"pred{i}"] = p.detach()[:, ::2, ::2]
+    params = dict(net.named_parameters())
+    out.update(_grad_sample(params, ["patch.", "patch_l2.", "dres1_att_.0.0.", "dres2_att_.conv2.", "dres2_att_.attention_block.final1x1.",
+                                     "classif_att_.2.", "concatconv.0.0.", "dres0.0.0.", "dres2.conv5.", "dres3.attention_block.final1x1.",
+                                     "classif2.2.", "feature_extraction.firstconv."]))
+    for n in ("dres2_att_.attention_block.qkv_3d.weight", "dres3.attention_block.qkv_3d.bias"):
+        out["grad:" + n] = params[n].grad.detach().flatten()
+    save("acvnet_train.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]

@@ -95,6 +95,7 @@ class OracleTrainBackend(OracleBackend):
     """aggregation.TrainBackend's semantics (raw conv -> the layer's own BatchNorm3d module, i.e. batch statistics in
     train mode -> residual -> activation) with torch's convolution instead of the CUDA kernels."""
     name = "oracle-train"
+    training_path = True
 
     def conv(self, layer, x, act="none", residual=None):
         conv, bn = _split(layer)

@@ -78,15 +78,17 @@ def test_conv_plan_tap_lists():
 
 
 def test_training_mode_fails_loudly():
-    """PSMNet / GwcNet train on the CUDA path only (no CPU fallback: CPU tensors are refused); models whose training path
-    is not built raise NotImplementedError instead of silently running something else."""
+    """Every model trains on the CUDA path only: there is no CPU fallback in train mode either (CPU tensors are refused
+    by the first hot-path op), and nothing silently runs something else."""
     import stereo_toolbox_b200 as S
     from stereo_toolbox_b200._lib import StbError
-    net = S.GwcNet_GC(32).train()
-    with pytest.raises(StbError):
-        net(torch.zeros(2, 3, 64, 128), torch.zeros(2, 3, 64, 128))
-    with pytest.raises(NotImplementedError):
-        S.ACVNet(32).train()(torch.zeros(1, 3, 64, 128), torch.zeros(1, 3, 64, 128))
+    for net, hw in ((S.GwcNet_GC(32), (64, 128)), (S.PSMNet(32), (256, 256)), (S.ACVNet(32), (64, 128)), (S.CFNet(64), (64, 128)),
+                    (S.PCWNet_GC(64), (64, 128))):
+        net.train()
+        with pytest.raises(StbError):
+            net(torch.zeros(2, 3, *hw), torch.zeros(2, 3, *hw))
+    with pytest.raises(NotImplementedError):           # the reference's own PCWNet_G cannot run either (pcwnet.py:127-131 vs :493)
+        S.PCWNet_G(64).train()(torch.zeros(2, 3, 64, 128), torch.zeros(2, 3, 64, 128))
 
 
 def test_load_checkpoint_flexible(tmp_path):

@@ -1,4 +1,4 @@
-"""PCWNet_GC / CFNet training paths on the GPU (3-D path on aggregation.TrainBackend: forward + backward kernels of
+"""PCWNet_GC / CFNet / ACVNet training paths on the GPU (3-D path on aggregation.TrainBackend: forward + backward kernels of
 libstb200.so, Mish, align_corners=True heads at x4 / x8) vs one training step of the reference."""
 import pytest
 import torch
@@ -11,9 +11,10 @@ UNCONFIRMED = ("written after the round-1 GPU budget was spent: every kernel on 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), pytest.mark.xfail(strict=False, reason=UNCONFIRMED)]
 
 
-@pytest.mark.parametrize("key,ctor,seed,fixture,n", [("pcwnet_gc", "PCWNet_GC", 7, "pcwnet_train.npz", 6),
-                                                     ("cfnet", "CFNet", 6, "cfnet_train.npz", 9)])
-def test_training_step_vs_reference(key, ctor, seed, fixture, n):
+@pytest.mark.parametrize("key,ctor,seed,fixture,n,width", [("pcwnet_gc", "PCWNet_GC", 7, "pcwnet_train.npz", 6, 128),
+                                                           ("cfnet", "CFNet", 6, "cfnet_train.npz", 9, 128),
+                                                           ("acvnet", "ACVNet", 3, "acvnet_train.npz", 4, 144)])
+def test_training_step_vs_reference(key, ctor, seed, fixture, n, width):
     import stereo_toolbox_b200 as S
     from stereo_toolbox_b200.synth import synth_pair, synth_gt
     g = load_golden(fixture)
@@ -21,8 +22,8 @@ def test_training_step_vs_reference(key, ctor, seed, fixture, n):
     net = getattr(S, ctor)(meta["maxdisp"])
     net.load_state_dict(sd, strict=True)
     net = net.cuda().train()
-    left, right = synth_pair(2, 64, 128, seed=seed, shift=5)
-    gt = synth_gt(2, 64, 128).cuda()
+    left, right = synth_pair(2, 64, width, seed=seed, shift=5)
+    gt = synth_gt(2, 64, width).cuda()
     preds = net(left.cuda(), right.cuda())
     assert len(preds) == n
     mask = (gt > 0) & (gt < meta["maxdisp"])
@@ -36,6 +37,6 @@ def test_training_step_vs_reference(key, ctor, seed, fixture, n):
     params = dict(net.named_parameters())
     for name in [k[5:] for k in g if k.startswith("grad:")]:
         got, want = params[name].grad.flatten().cpu(), g["grad:" + name]
-        got = got[::max(1, got.numel() // 20000)]
+        got = got[::max(1, got.numel() // 20000)] if want.numel() != got.numel() else got
         cos = F.cosine_similarity(got, want, dim=0).item()
         assert cos > 0.99, (name, cos)
