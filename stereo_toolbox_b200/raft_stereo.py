@@ -344,8 +344,11 @@ class RAFTStereo(nn.Module):
         inp_list = [torch.relu(x[1]) for x in cnet_list]
         inp_list = [list(conv(i).split(conv.out_channels // 3, dim=1)) for i, conv in zip(inp_list, self.context_zqr_convs)]
 
-        if a.corr_implementation not in ("reg", "reg_cuda"):
-            raise NotImplementedError("only the regular all-pairs CorrBlock1D ('reg') is built on the CUDA path")
+        # raft_stereo.py:138-149: "reg" / "reg_cuda" / "alt" / "alt_cuda" are four implementations of ONE function (the
+        # alternates trade memory for recomputation: correlation of pooled features == pooled correlation, both linear);
+        # here all of them are the all-pairs kernels of csrc/corr1d.cu (33.5 MB of pyramid at 512x1024 does not need "alt")
+        if a.corr_implementation not in ("reg", "reg_cuda", "alt", "alt_cuda"):
+            raise ValueError(f"unknown corr_implementation {a.corr_implementation!r}")
         # ---- hot path: all-pairs correlation + pyramid (once), lookup (every iteration)
         corr_fn = CorrBlock1D(fmap1.float(), fmap2.float(), radius=a.corr_radius, num_levels=a.corr_levels)
 
