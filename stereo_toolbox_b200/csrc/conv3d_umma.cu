@@ -754,6 +754,15 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         if (Cn <= 16) return STB_E_SMEM;
         Cn = (Cn / 2 + 15) / 16 * 16;
     }
+    {   // tuning overrides for sweeps with tools/layer_bench.py (host-side only; ignored when they do not fit)
+        static const int force_th = getenv("STB_UMMA_TH") ? atoi(getenv("STB_UMMA_TH")) : 0;
+        static const int force_ring = getenv("STB_UMMA_RING") ? atoi(getenv("STB_UMMA_RING")) : 0;
+        if (force_th >= 4 && force_th <= 16 && force_th % 4 == 0) {
+            const int r = ring_for(Cn, force_th);
+            if (r) { TH = force_th; R = r; }
+        }
+        if (force_ring >= window + 1 && force_ring < R) R = force_ring;
+    }
     while (TH > 4 && TH - 4 >= nclass_h) TH -= 4;      // do not stage rows that do not exist
     a.R = R;
     a.tab_bytes = 0;

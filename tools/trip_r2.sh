@@ -37,6 +37,8 @@ cut -c1-300 gpurun_out/r2_train_sceneflow_bf16.json
 # the reference's published Table 3 protocol (RTX 4090 numbers in BASELINE.md) on the drop-in models
 timeout 1500 python tools/table3.py --iters 10 > gpurun_out/r2_table3.md 2> gpurun_out/r2_table3.err; echo "table3 rc=$?"
 cat gpurun_out/r2_table3.md | cut -c1-260
+# tiling sweep of the slow conv flavours (TH=0 / RING=0 = the built-in choice)
+timeout 1800 bash tools/sweep_tiling.sh > gpurun_out/r2_sweep_tiling.log 2>&1; tail -90 gpurun_out/r2_sweep_tiling.log
 # per-layer ncu captures of the slow conv flavours (reports come back in gpurun_out/)
 timeout 2400 bash tools/ncu_layers.sh > gpurun_out/r2_ncu_layers.log 2>&1; tail -60 gpurun_out/r2_ncu_layers.log
 # sanitizers last (slow)
