@@ -126,6 +126,34 @@ tmabw_kernel(const __grid_constant__ CUtensorMap tm, int R, int nbox, uint32_t b
     }
 }
 
+// Same streaming loop with explicit tile origins (tmabw2: unit-stride vs element-strided vs parity-folded tensor maps).
+__global__ void __launch_bounds__(64)
+tmabw2_kernel(const __grid_constant__ CUtensorMap tm, int R, int nbox, uint32_t box_bytes, int D, int tiles_w, int tiles_h,
+              int step_w, int step_h) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+    __shared__ uint64_t full[16];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < R; ++i) mbar_init(&full[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = blockIdx.x;
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th = t % tiles_h; t /= tiles_h;
+        const int b = t;
+        for (int n = 0; n < nbox + R; ++n) {
+            const int slot = n % R;
+            if (n >= R) mbar_wait(&full[slot], ((n / R) - 1) & 1);
+            if (n < nbox) {
+                mbar_arrive_expect_tx(&full[slot], box_bytes);
+                tma_load_5d(smem + (size_t)slot * box_bytes, &tm, &full[slot], 0, tw * step_w, th * step_h, (n % D), b);
+            }
+        }
+    }
+}
+
 // Raw tcgen05.mma issue/execute rate: `nissue` warps each issue `iters` x `per_iter` MMAs (M=128, N, K=16) on
 // garbage smem operands (no TMA, no epilogue), operands K-major with the given swizzle / row shift.
 __global__ void __launch_bounds__(128)
@@ -463,6 +491,59 @@ int main(int argc, char** argv) {
         double gb = (double)grid * nbox * box_bytes / 1e9;
         printf("tmabw C=%d rows=%d (box %u B) ring=%d smem=%zu KB: %.3f ms, %.1f GB/s (%d CTAs x %d boxes)\n", C, rows, box_bytes, R,
                smem / 1024, ms, gb / (ms * 1e-3), grid, nbox);
+        return 0;
+    }
+    if (argc >= 2 && !strcmp(argv[1], "tmabw2")) {
+        // usage: tmabw2 <C:32|64> <rows> <R> <mode>   every box delivers rows x 32 voxels x C channels to shared memory
+        //   mode 0: unit stride (the stride-1 conv's plane load)
+        //   mode 1: every second voxel in h and w through TMA elementStrides (1,2,2,1,1) -- what the stride-2 conv does today
+        //   mode 2: the same voxels through a parity-folded tensor map: dims (C, W/2, H/2, D, B) with DOUBLED w / h byte
+        //           strides and unit element strides (one map per (h,w) parity, base pointer offset by the parity)
+        const int C = atoi(argv[2]), rows = atoi(argv[3]), R = atoi(argv[4]), mode = argc > 5 ? atoi(argv[5]) : 0;
+        const int B = 8, D = 48, H = 96, W = 312;
+        size_t n = (size_t)B * D * H * W * C;
+        __nv_bfloat16* d;
+        CK(cudaMalloc(&d, n * 2));
+        CK(cudaMemset(d, 0, n * 2));
+        CUtensorMap tm;
+        const CUtensorMapSwizzle sw = C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+        bool ok;
+        int step_w, step_h;
+        if (mode == 2) {
+            uint64_t dims[5] = {(uint64_t)C, W / 2, H / 2, D, B};
+            uint64_t str[4] = {(uint64_t)2 * C * 2, (uint64_t)2 * W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)D * H * W * C * 2};
+            uint32_t box[5] = {(uint32_t)C, 32, (uint32_t)rows, 1, 1};
+            ok = umma_host::make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d, dims, str, box, sw);
+            step_w = 30; step_h = rows - 2;
+        } else {
+            uint64_t dims[5] = {(uint64_t)C, W, H, D, B};
+            uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)D * H * W * C * 2};
+            const uint32_t m = mode == 1 ? 2u : 1u;
+            uint32_t box[5] = {(uint32_t)C, 32 * m, (uint32_t)rows * m, 1, 1};
+            uint32_t es[5] = {1, m, m, 1, 1};
+            ok = umma_host::make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d, dims, str, box, sw, es);
+            step_w = 30 * (int)m; step_h = (rows - 2) * (int)m;
+        }
+        if (!ok) { printf("tmap fail\n"); return 1; }
+        const uint32_t box_bytes = (uint32_t)C * 2 * 32 * rows;
+        const int tiles_w = 5, tiles_h = mode == 0 ? 96 / (rows - 2) / 2 : 48 / (rows - 2), nbox = 96;   // same CTA count in all modes
+        size_t smem = (size_t)R * box_bytes + 2048;
+        CK(cudaFuncSetAttribute(tmabw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        const int grid = B * tiles_w * tiles_h;
+        tmabw2_kernel<<<grid, 64, smem>>>(tm, R, nbox, box_bytes, D, tiles_w, tiles_h, step_w, step_h);
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        tmabw2_kernel<<<grid, 64, smem>>>(tm, R, nbox, box_bytes, D, tiles_w, tiles_h, step_w, step_h);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double gb = (double)grid * nbox * box_bytes / 1e9;
+        printf("tmabw2 mode=%d (%s) C=%d rows=%d (box %u B delivered) ring=%d: %.3f ms, %.1f GB/s delivered (%d CTAs x %d boxes)\n", mode,
+               mode == 0 ? "unit stride" : mode == 1 ? "elementStrides 2,2" : "parity-folded map", C, rows, box_bytes, R, ms,
+               gb / (ms * 1e-3), grid, nbox);
         return 0;
     }
     if (argc >= 2 && !strcmp(argv[1], "halo2")) {

@@ -37,6 +37,8 @@ cut -c1-300 gpurun_out/r2_train_sceneflow_bf16.json
 # the reference's published Table 3 protocol (RTX 4090 numbers in BASELINE.md) on the drop-in models
 timeout 1500 python tools/table3.py --iters 10 > gpurun_out/r2_table3.md 2> gpurun_out/r2_table3.err; echo "table3 rc=$?"
 cat gpurun_out/r2_table3.md | cut -c1-260
+# does TMA elementStrides throttle the stride-2 convs' plane loads? (unit stride vs elementStrides vs parity-folded map)
+timeout 300 bash stereo_toolbox_b200/csrc/probe/run_tmabw2.sh > gpurun_out/r2_tmabw2.txt 2>&1; cat gpurun_out/r2_tmabw2.txt
 # tiling sweep of the slow conv flavours (TH=0 / RING=0 = the built-in choice)
 timeout 1800 bash tools/sweep_tiling.sh > gpurun_out/r2_sweep_tiling.log 2>&1; tail -90 gpurun_out/r2_sweep_tiling.log
 # per-layer ncu captures of the slow conv flavours (reports come back in gpurun_out/)
