@@ -1,8 +1,6 @@
 """PCWNet_GC / CFNet training paths on CPU: the drop-in models in train mode with the 3-D path on the oracle's
 TrainBackend stand-in (tests/oracle_backend.py), against one training step of the REFERENCE (tests/golden/*_train.npz:
 the full prediction lists, loss, and one weight gradient per sub-network)."""
-import pytest
-import torch
 import torch.nn.functional as F
 
 from conftest import load_golden, golden_state

@@ -1,7 +1,6 @@
 """PCWNet_GC / CFNet / ACVNet training paths on the GPU (3-D path on aggregation.TrainBackend: forward + backward kernels of
 libstb200.so, Mish, align_corners=True heads at x4 / x8) vs one training step of the reference."""
 import pytest
-import torch
 import torch.nn.functional as F
 
 from conftest import load_golden, golden_state
