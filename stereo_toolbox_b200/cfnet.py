@@ -237,6 +237,9 @@ class cfnet(nn.Module):
         return prob, torch.sum(prob * samples, dim=1, keepdim=True), c, out1
 
     def forward(self, left, right):
+        if getattr(self, "channels_last", False):     # opt-in NHWC torch glue (raft_stereo.glue_channels_last)
+            from .raft_stereo import glue_channels_last
+            left, right = glue_channels_last(self, left, right)
         tr = self.training
         # train(): exact fp32 -- TrainBackend (forward + backward of the 3-D path in libstb200.so, batch-statistic BatchNorm);
         # the explicit-probability ops on [B,S,H,W] tensors are torch there (their autograd)

@@ -143,6 +143,9 @@ class PCWNet(nn.Module):
         return self
 
     def forward(self, left, right):
+        if getattr(self, "channels_last", False):     # opt-in NHWC torch glue (raft_stereo.glue_channels_last)
+            from .raft_stereo import glue_channels_last
+            left, right = glue_channels_last(self, left, right)
         if not self.use_concat_volume:
             raise NotImplementedError("PCWNet_G: the reference's refinement reads features_left['finetune_feature'], which its "
                                       "feature_extraction only returns with concat_feature=True (pcwnet.py:127-131, 493)")

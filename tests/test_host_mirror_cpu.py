@@ -172,3 +172,21 @@ def test_channels_last_glue_is_numerically_equivalent(family):
                    for m in net.modules() if isinstance(m, torch.nn.Conv2d) and m.weight.shape[1] > 1 and m.weight.shape[2] > 1)
         assert all(m.weight.is_contiguous() for m in net.modules() if isinstance(m, torch.nn.Conv3d))
     assert (out - g["disp"]).abs().mean().item() < 1e-3
+
+
+@pytest.mark.parametrize("key,ctor,seed", [("cfnet", "CFNet", 6), ("pcwnet_gc", "PCWNet_GC", 7)])
+def test_channels_last_glue_cascade_models(key, ctor, seed):
+    """The same opt-in for the two models with the largest 2-D networks (their gather warps / sampled volumes / refinement
+    must not depend on the memory format)."""
+    g = load_golden(f"{key}.npz")
+    sd, meta = golden_state(key)
+    with oracle_hot_path():
+        import stereo_toolbox_b200 as S
+        net = getattr(S, ctor)(meta["maxdisp"])
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        net.channels_last = True
+        left, right = _pair(meta, seed)
+        with torch.no_grad():
+            disp = net(left, right)
+    assert (disp - g["disp"]).abs().mean().item() < 1e-3

@@ -55,7 +55,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cuda-graph", action="store_true", help="raft: replay one captured GRU iteration")
-    ap.add_argument("--channels-last", action="store_true", help="raft / igev: NHWC torch glue (model.channels_last)")
+    ap.add_argument("--channels-last", action="store_true", help="raft / igev / cfnet / pcwnet_gc: NHWC torch glue (model.channels_last)")
     args = ap.parse_args()
 
     import stereo_toolbox_b200 as S

@@ -16,6 +16,10 @@ cut -c1-400 gpurun_out/r2_bench.json
   timeout 300 python tools/model_bench.py --model raft   --height 512  --width 1024 --iters 32 --cuda-graph
   timeout 300 python tools/model_bench.py --model raft   --height 512  --width 1024 --iters 32 --cuda-graph --channels-last
   timeout 300 python tools/model_bench.py --model igev   --height 1152 --width 1920 --maxdisp 256 --iters 32 --precision fp16 --channels-last
+  for cl in "" "--channels-last"; do
+    timeout 300 python tools/model_bench.py --model pcwnet_gc --height 384 --width 1248 --precision fp16 $cl
+    timeout 300 python tools/model_bench.py --model cfnet     --height 384 --width 1248 --precision fp16 $cl
+  done
   timeout 300 python tools/model_bench.py --model psmnet --height 576  --width 960  --batch 4 --precision fp16
   timeout 300 python tools/model_bench.py --model gwcnet_gc --height 576 --width 960 --batch 4 --precision fp16
 } > gpurun_out/r2_models.jsonl 2> gpurun_out/r2_models.err
