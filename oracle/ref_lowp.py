@@ -26,8 +26,20 @@ import torch.nn.functional as F
 from . import ref_ops as R
 
 
-def _conv_16bit(dtype: torch.dtype, round_weights: bool = True, round_activations: bool = True):
-    r = lambda t: t.to(dtype).float()
+def _round(dtype: torch.dtype, split: bool):
+    """Storage rounding: one 16-bit value, or (``split``) a hi + lo pair of 16-bit values -- x ~= hi + lo with
+    hi = rn16(x), lo = rn16(x - hi): ~22 mantissa bits for fp16 (profiles/next_round_plan.md section 6)."""
+    if not split:
+        return lambda t: t.to(dtype).float()
+
+    def r(t):
+        hi = t.to(dtype).float()
+        return hi + (t - hi).to(dtype).float()
+    return r
+
+
+def _conv_16bit(dtype: torch.dtype, round_weights: bool = True, round_activations: bool = True, split: bool = False):
+    r = _round(dtype, split)
 
     def conv3d_bn_act(x, weight, bn=None, stride=1, padding=1, act="none", residual=None, transposed=False,
                       output_padding=0):
@@ -52,11 +64,12 @@ def _conv_16bit(dtype: torch.dtype, round_weights: bool = True, round_activation
 
 
 @contextlib.contextmanager
-def storage_16bit(dtype: torch.dtype = torch.float16, round_weights: bool = True, round_activations: bool = True):
+def storage_16bit(dtype: torch.dtype = torch.float16, round_weights: bool = True, round_activations: bool = True,
+                  split: bool = False):
     """Inside the block, every ``ref_ops.conv3d_bn_act`` call (hence every 3-D layer of oracle/ref_models.py) rounds its
     operands / result to ``dtype`` as described in the module docstring."""
     orig = R.conv3d_bn_act
-    R.conv3d_bn_act = _conv_16bit(dtype, round_weights, round_activations)
+    R.conv3d_bn_act = _conv_16bit(dtype, round_weights, round_activations, split)
     try:
         yield
     finally:

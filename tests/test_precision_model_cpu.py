@@ -48,3 +48,12 @@ def test_weights_and_activations_contribute_comparably():
     w_only = (_gwc(torch.bfloat16, round_activations=False)[0] - ref).abs().mean().item()
     a_only = (_gwc(torch.bfloat16, round_weights=False)[0] - ref).abs().mean().item()
     assert 0.3 * both < w_only < both * 1.1 and 0.3 * both < a_only < both * 1.1, (w_only, a_only, both)
+
+
+def test_split_fp16_storage_would_meet_the_fp32_bar():
+    """Design check for an exact path on the tensor cores (profiles/next_round_plan.md section 6): operands stored as
+    fp16 hi + lo pairs (three MMAs per K-step: hi*hi, hi*lo, lo*hi) bring the storage error from 5.7e-3 px down to the
+    fp32 bar of 1e-3 px -- measured with the bench weights: 1.9e-4 px at 192x624, where single fp16 gives 0.097 px."""
+    ref, _ = _gwc()
+    split, _ = _gwc(torch.float16, split=True)
+    assert (split - ref).abs().mean().item() < 1e-4
