@@ -1,7 +1,12 @@
 #!/bin/bash
-# First GPU trip of the next round (run under gpurun from the repo root): confirm what was written after the
-# round-1 GPU budget ran out (IGEVStereo whole model), then measure the configs bench.py does not carry.
+# GPU trips prepared at the end of round 1 (run under gpurun from the repo root; everything lands in gpurun_out/):
+#   bash tools/trip_r2.sh a    confirm what was written without hardware + the headline bench            (~10 min)
+#   bash tools/trip_r2.sh b    whole-model numbers for the other BASELINE configs, Table 3, training      (~15 min)
+#   bash tools/trip_r2.sh c    probes / sweeps / ncu captures / sanitizers for the kernel work            (~40 min)
+# e.g.  gpurun --timeout 1500 -- 'bash tools/trip_r2.sh a'     (no argument = a, b and c in that order)
+PARTS=${1:-abc}
 mkdir -p gpurun_out
+if [[ $PARTS == *a* ]]; then
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?"
 tail -5 gpurun_out/r2_pytest.log
 export STB200_RUN_UNCONFIRMED=1      # from here on also run the tests that launch not-yet-confirmed kernels (skipped by default)
@@ -9,6 +14,9 @@ timeout 600 python -m pytest tests/test_igev_stereo_gpu.py tests/test_lowp_model
 grep -i "EPE\|passed\|failed\|storage model" gpurun_out/r2_igev.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; echo "bench rc=$?"
 cut -c1-400 gpurun_out/r2_bench.json
+fi
+if [[ $PARTS == *b* ]]; then
+export STB200_RUN_UNCONFIRMED=1
 {
   timeout 300 python tools/model_bench.py --model igev   --height 1152 --width 1920 --maxdisp 256 --iters 32 --precision fp16
   timeout 300 python tools/model_bench.py --model igev   --height 1152 --width 1920 --maxdisp 256 --iters 32 --precision fp32
@@ -41,6 +49,8 @@ cut -c1-300 gpurun_out/r2_train_sceneflow_bf16.json
 # the reference's published Table 3 protocol (RTX 4090 numbers in BASELINE.md) on the drop-in models
 timeout 1500 python tools/table3.py --iters 10 > gpurun_out/r2_table3.md 2> gpurun_out/r2_table3.err; echo "table3 rc=$?"
 cat gpurun_out/r2_table3.md | cut -c1-260
+fi
+if [[ $PARTS == *c* ]]; then
 # does TMA elementStrides throttle the stride-2 convs' plane loads? (unit stride vs elementStrides vs parity-folded map)
 timeout 300 bash stereo_toolbox_b200/csrc/probe/run_tmabw2.sh > gpurun_out/r2_tmabw2.txt 2>&1; cat gpurun_out/r2_tmabw2.txt
 # tiling sweep of the slow conv flavours (TH=0 / RING=0 = the built-in choice)
@@ -49,3 +59,4 @@ timeout 1800 bash tools/sweep_tiling.sh > gpurun_out/r2_sweep_tiling.log 2>&1; t
 timeout 2400 bash tools/ncu_layers.sh > gpurun_out/r2_ncu_layers.log 2>&1; tail -60 gpurun_out/r2_ncu_layers.log
 # sanitizers last (slow)
 timeout 2400 bash tools/sanitize.sh > gpurun_out/r2_sanitize.log 2>&1; tail -12 gpurun_out/r2_sanitize.log
+fi
