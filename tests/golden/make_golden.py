@@ -591,6 +591,8 @@ def acvnet_train():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade"]
+    # order matters: models() starts models.json afresh, the later generators add their entries to it
+    which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade", "train", "cfnet", "pcwnet", "igev_model",
+                             "variants", "raft_train", "igev_train", "pcwnet_train", "cfnet_train", "acvnet_train"]
     for w in which:
         globals()[w]()
