@@ -242,6 +242,56 @@ class IGEVStereo(IGEVCostVolume):
         spx_pred = F.softmax(self.spx_gru(self.spx_2_gru(mask_feat_4, stem_2x)), 1)
         return context_upsample(disp * 4.0, spx_pred).unsqueeze(1)
 
+    def _iteration(self, net_list, inp_list, geo_fn, coords, disp):
+        """One GRU iteration of igev_stereo.py:237-242: geometry lookup (one CUDA kernel) + update block (torch)."""
+        a = self.args
+        disp = disp.detach()
+        geo_feat = geo_fn(disp, coords)
+        net_list, mask_feat_4, delta_disp = self.update_block(net_list, inp_list, geo_feat, disp,
+                                                              iter16=a.n_gru_layers == 3, iter08=a.n_gru_layers >= 2)
+        return net_list, mask_feat_4, disp + delta_disp
+
+    def _iterate_graphed(self, net_list, inp_list, geo_fn, coords, disp, iters):
+        """Opt-in (``model.cuda_graph = True``, inference): ONE iteration -- lookup kernel + update block + the write-back of
+        its outputs into its own inputs -- is captured into a CUDA graph once per input shape and replayed ``iters`` times
+        (same scheme as RAFTStereo._iterate_graphed; at small resolutions the loop is launch-bound).  Per call only the
+        graph's static inputs (hidden states, context features, the two pyramids, disparity) are refreshed."""
+        key = (tuple(disp.shape), tuple(tuple(t.shape) for t in net_list), str(disp.device))
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            st = dict(net=[t.clone() for t in net_list], inp=[[t.clone() for t in lvl] for lvl in inp_list],
+                      disp=disp.clone(), coords=coords.clone(),
+                      geos=[t.clone() for t in geo_fn._geos], corrs=[t.clone() for t in geo_fn._corrs])
+            geo_fn._geos, geo_fn._corrs = st["geos"], st["corrs"]      # the captured lookup reads the static pyramid buffers
+            st["geo_fn"] = geo_fn
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                             # warm-up outside capture (cuDNN plans, lazy loading)
+                self._iteration(list(st["net"]), st["inp"], geo_fn, st["coords"], st["disp"])
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                n2, m2, d2 = self._iteration(list(st["net"]), st["inp"], geo_fn, st["coords"], st["disp"])
+                for dst, src in zip(st["net"], n2):
+                    dst.copy_(src)
+                st["disp"].copy_(d2)
+            st["graph"], st["mask"] = graph, m2
+            cache[key] = hit = st
+        else:
+            for dst, src in zip(hit["net"], net_list):
+                dst.copy_(src)
+            for dl, sl in zip(hit["inp"], inp_list):
+                for dst, src in zip(dl, sl):
+                    dst.copy_(src)
+            for dst, src in zip(hit["geos"] + hit["corrs"], list(geo_fn._geos) + list(geo_fn._corrs)):
+                dst.copy_(src)
+            hit["disp"].copy_(disp)
+            hit["coords"].copy_(coords)
+        for _ in range(iters):
+            hit["graph"].replay()
+        return hit["disp"].clone(), hit["mask"]
+
     def forward(self, image1, image2, iters=None, flow_init=None, test_mode=None):
         a = self.args
         if iters is None:
@@ -284,12 +334,12 @@ class IGEVStereo(IGEVCostVolume):
         coords = torch.arange(w, device=match_left.device).float().reshape(1, 1, w, 1).repeat(b, h, 1, 1)
         disp = init_disp
         disp_preds = []
+        if (getattr(self, "cuda_graph", False) and test_mode and not self.training and iters > 1 and disp.is_cuda
+                and not torch.is_grad_enabled()):
+            disp, mask_feat_4 = self._iterate_graphed(net_list, inp_list, geo_fn, coords, disp, iters)
+            return self.upsample_disp(disp, mask_feat_4, stem_2x)
         for itr in range(iters):
-            disp = disp.detach()
-            geo_feat = geo_fn(disp, coords)                          # hot path: one lookup kernel per iteration
-            net_list, mask_feat_4, delta_disp = self.update_block(net_list, inp_list, geo_feat, disp,
-                                                                  iter16=a.n_gru_layers == 3, iter08=a.n_gru_layers >= 2)
-            disp = disp + delta_disp
+            net_list, mask_feat_4, disp = self._iteration(net_list, inp_list, geo_fn, coords, disp)   # hot path: one lookup kernel
             if test_mode and itr < iters - 1:
                 continue                                             # only the last iterate is upsampled
             disp_preds.append(self.upsample_disp(disp, mask_feat_4, stem_2x))

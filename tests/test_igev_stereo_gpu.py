@@ -59,3 +59,30 @@ def test_igev_stereo_fp16_runs():
     assert out.shape == g["disp"].shape
     assert torch.isfinite(out).all()
     print(f"IGEVStereo fp16 stage, whole-model EPE vs reference: {(out - g['disp']).abs().mean().item():.4f} px")
+
+
+def test_igev_stereo_cuda_graph_iteration_is_bit_identical():
+    """model.cuda_graph = True replays one captured GRU iteration (geometry-lookup kernel + update block): same kernels in
+    the same order as the eager loop, so the output must be bit-identical -- also on the second call, which only refreshes
+    the graph's static inputs."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    sd, meta = golden_state("igev_stereo")
+    net = S.IGEVStereo({"max_disp": meta["max_disp"]})
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    left, right = synth_pair(1, 64, 128, seed=8, shift=meta["shift"])
+    left2, right2 = synth_pair(1, 64, 128, seed=9, shift=3)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            eager = net(left.cuda(), right.cuda(), iters=4)
+            eager2 = net(left2.cuda(), right2.cuda(), iters=4)
+            net.cuda_graph = True
+            graphed = net(left.cuda(), right.cuda(), iters=4)
+            graphed2 = net(left2.cuda(), right2.cuda(), iters=4)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert torch.equal(eager, graphed)
+    assert torch.equal(eager2, graphed2)

@@ -54,7 +54,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--cuda-graph", action="store_true", help="raft: replay one captured GRU iteration")
+    ap.add_argument("--cuda-graph", action="store_true", help="raft / igev: replay one captured GRU iteration")
     ap.add_argument("--channels-last", action="store_true", help="raft / igev / cfnet / pcwnet_gc: NHWC torch glue (model.channels_last)")
     args = ap.parse_args()
 

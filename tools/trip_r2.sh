@@ -24,6 +24,8 @@ export STB200_RUN_UNCONFIRMED=1
   timeout 300 python tools/model_bench.py --model raft   --height 512  --width 1024 --iters 32 --cuda-graph
   timeout 300 python tools/model_bench.py --model raft   --height 512  --width 1024 --iters 32 --cuda-graph --channels-last
   timeout 300 python tools/model_bench.py --model igev   --height 1152 --width 1920 --maxdisp 256 --iters 32 --precision fp16 --channels-last
+  timeout 300 python tools/model_bench.py --model igev   --height 480 --width 640 --iters 32 --precision fp16
+  timeout 300 python tools/model_bench.py --model igev   --height 480 --width 640 --iters 32 --precision fp16 --cuda-graph
   for cl in "" "--channels-last"; do
     timeout 300 python tools/model_bench.py --model pcwnet_gc --height 384 --width 1248 --precision fp16 $cl
     timeout 300 python tools/model_bench.py --model cfnet     --height 384 --width 1248 --precision fp16 $cl
