@@ -34,13 +34,17 @@ def main():
     ap.add_argument("--models", nargs="+", default=list(PUBLISHED))
     ap.add_argument("--precisions", nargs="+", default=["fp16", "fp32"])
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--cuda-graph", action="store_true", help="raft / igev: model.cuda_graph = True")
+    ap.add_argument("--channels-last", action="store_true", help="raft / igev / cfnet / pcwnet_gc: model.channels_last = True")
     args = ap.parse_args()
     from stereo_toolbox_b200.evaluation import speed_and_memory_test
     rows, out = [], {}
     for name in args.models:
         for prec in (["fp32"] if name == "raft" else args.precisions):
             try:
-                _, secs, mbs = speed_and_memory_test(build(name, prec), num_iterations=args.iters, verbose=False)
+                net = build(name, prec)
+                net.cuda_graph, net.channels_last = args.cuda_graph, args.channels_last
+                _, secs, mbs = speed_and_memory_test(net, num_iterations=args.iters, verbose=False)
             except Exception as e:          # keep the table going: one model failing at one size is a finding, not a crash
                 rows.append(f"| {name} | {prec} | failed: {type(e).__name__}: {str(e)[:80]} |")
                 continue
