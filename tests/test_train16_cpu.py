@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from conftest import GOLDEN, load_golden, load_meta
+from conftest import GOLDEN, golden_state, load_golden, load_meta
 from oracle import ref_ops as R
 
 
@@ -55,6 +55,12 @@ def _make_backend(dtype_name):
         # the fp32 boundary ops of autograd.py need the CUDA library: differentiable oracle forms here
         def volume_concat(self, l, r, maxdisp4, mask_left=True, att_prob=None):
             return self._to_cl(R.build_concat_volume(l, r, maxdisp4, mask_left))
+
+        def volume_gwc_concat(self, gwc_l, gwc_r, cat_l, cat_r, maxdisp4, groups):
+            vol = R.build_gwc_volume(gwc_l, gwc_r, maxdisp4, groups)
+            if cat_l is not None:
+                vol = torch.cat((vol, R.build_concat_volume(cat_l, cat_r, maxdisp4, True)), 1)
+            return self._to_cl(vol)
 
         def head(self, cost, maxdisp, H, W, align_corners=False):
             B, D, h, w, _ = cost.shape
@@ -161,3 +167,48 @@ def test_psmnet_16bit_training_step_vs_reference(prec, pred_tol, cos_min):
         cos = F.cosine_similarity(got, want, dim=0).item()
         assert cos > cos_min, (name, cos)
         assert 0.9 < (got.norm() / want.norm()).item() < 1.1, name
+
+
+def test_gwcnet_g_16bit_training_matches_the_fp32_training_path():
+    """GwcNet_G (40-group volume zero-padded to 64 channels, 1x1x1 redir convs, four heads) on the 16-bit training backend
+    (torch primitives, fp16 storage) vs the same drop-in on the exact-path stand-in (tests/oracle_backend.py
+    OracleTrainBackend): four predictions within the storage error, gradients aligned."""
+    import stereo_toolbox_b200 as S
+    from oracle_backend import oracle_hot_path
+    from stereo_toolbox_b200.synth import synth_pair, synth_gt
+    sd, meta = golden_state("gwcnet_g")
+    left, right = synth_pair(2, 64, 128, seed=0, shift=5)
+    gt = synth_gt(2, 64, 128)
+    mask = (gt > 0) & (gt < meta["maxdisp"])
+
+    def step(prec):
+        net = S.GwcNet_G(meta["maxdisp"])
+        net.load_state_dict(sd, strict=True)
+        net.train()
+        if prec != "fp32":
+            net.train_precision = prec
+            net.__dict__["_train16"] = _make_backend(prec)
+        preds = net(left, right)
+        loss = sum(F.smooth_l1_loss(p[mask], gt[mask], reduction="mean") for p in preds)
+        loss.backward()
+        return net, preds, loss
+
+    with oracle_hot_path():
+        import stereo_toolbox_b200.aggregation as agg
+        from oracle_backend import OracleTrainBackend
+        old, agg.TrainBackend = agg.TrainBackend, OracleTrainBackend          # train_backend_for() builds agg.TrainBackend
+        try:
+            ref_net, ref_preds, ref_loss = step("fp32")
+        finally:
+            agg.TrainBackend = old
+    net, preds, loss = step("fp16")
+    assert len(preds) == len(ref_preds) == 4                                   # gwcnet.py:216
+    for p, q in zip(preds, ref_preds):
+        assert (p.detach() - q.detach()).abs().mean().item() < 0.02
+    assert abs(loss.item() - ref_loss.item()) < 0.01 * abs(ref_loss.item())
+    ref_params = dict(ref_net.named_parameters())
+    for name, p in net.named_parameters():
+        if p.grad is None or p.dim() < 4 or not name.startswith(("dres", "classif")):
+            continue
+        cos = F.cosine_similarity(p.grad.flatten(), ref_params[name].grad.flatten(), dim=0).item()
+        assert cos > 0.98, (name, cos)
