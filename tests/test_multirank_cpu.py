@@ -87,3 +87,59 @@ def test_two_rank_gradient_allreduce():
         want = (torch.tensor(a) + torch.tensor(b)) / 2
         torch.testing.assert_close(torch.tensor(m0), want)
         torch.testing.assert_close(torch.tensor(m1), want)
+
+
+def _ddp_worker(rank, world, port, q):
+    """A drop-in model under torch's DistributedDataParallel ('DDP(...) must keep working around the
+    patched model', trainer/trainer_torchrun.py:116-121).  CPU: the 3-D path is answered by the oracle's TrainBackend
+    stand-in; what is exercised is the model's train-mode host code under the DDP wrapper and its gradient hooks."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import torch.nn.functional as F
+    import stereo_toolbox_b200 as S
+    import stereo_toolbox_b200.aggregation as agg
+    from oracle_backend import OracleTrainBackend, oracle_hot_path
+    from stereo_toolbox_b200.synth import synth_gt, synth_pair, synth_state_dict
+    net = S.GwcNet_G(32)
+    net.load_state_dict(synth_state_dict(net.state_dict(), 0))             # identical replicas
+    keys = list(net.state_dict())
+    sync_keys = list(torch.nn.SyncBatchNorm.convert_sync_batchnorm(S.GwcNet_G(32)).state_dict())   # trainer_torchrun.py:112-113
+    ddp = torch.nn.parallel.DistributedDataParallel(net.train())
+    left, right = synth_pair(1, 64, 128, seed=10 + rank, shift=4)          # each rank its own shard
+    gt = synth_gt(1, 64, 128)
+    mask = (gt > 0) & (gt < 32)
+    with oracle_hot_path():
+        old, agg.TrainBackend = agg.TrainBackend, OracleTrainBackend
+        try:
+            preds = ddp(left, right)
+            loss = sum(F.smooth_l1_loss(p[mask], gt[mask]) for p in preds)
+            loss.backward()
+        finally:
+            agg.TrainBackend = old
+    g = net.dres0[0][0].weight.grad
+    q.put((rank, len(preds), loss.item(), g.abs().sum().item(), g.flatten()[:64].tolist(), keys == sync_keys))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dropin_model_under_ddp_two_ranks():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (_, n0, loss0, s0, g0, k0), (_, n1, loss1, s1, g1, k1) = res
+    assert n0 == n1 == 4 and k0 and k1                  # four training predictions; SyncBatchNorm conversion keeps the state-dict layout
+    assert loss0 != loss1                               # different shards ...
+    assert s0 > 0 and g0 == g1                          # ... identical (averaged) gradients after DDP's all-reduce
