@@ -212,3 +212,29 @@ def test_gwcnet_g_16bit_training_matches_the_fp32_training_path():
             continue
         cos = F.cosine_similarity(p.grad.flatten(), ref_params[name].grad.flatten(), dim=0).item()
         assert cos > 0.98, (name, cos)
+
+
+def test_kernel_plans_build_for_every_forward_and_adjoint_conv():
+    """Host-side half of the GPU path: for every conv flavour of PSMNet / GwcNet the tcgen05 plan (weight tiles, tap / class
+    tables: aggregation_umma.UmmaPlan, pure host code) builds for the forward conv AND for the adjoint module that
+    ``Umma16TrainBackend._adjoint`` derives from it -- none falls back to the CUDA-core companion."""
+    from stereo_toolbox_b200.aggregation_umma import UmmaPlan
+    from stereo_toolbox_b200.train16 import Umma16TrainBackend
+    be = Umma16TrainBackend("bf16")
+    cases = [(nn.Conv3d(64, 32, 3, 1, 1, bias=False), (1, 8, 16, 16, 64), (1, 8, 16, 16, 32), nn.Conv3d),
+             (nn.Conv3d(32, 64, 3, 2, 1, bias=False), (1, 8, 16, 16, 32), (1, 4, 8, 8, 64), nn.ConvTranspose3d),
+             (nn.ConvTranspose3d(64, 32, 3, 2, 1, output_padding=1, bias=False), (1, 4, 8, 8, 64), (1, 8, 16, 16, 32), nn.Conv3d),
+             (nn.Conv3d(32, 32, 1, 1, 0, bias=False), (1, 8, 16, 16, 32), (1, 8, 16, 16, 32), nn.Conv3d),
+             (nn.Conv3d(32, 1, 3, 1, 1, bias=False), (1, 8, 16, 16, 32), (1, 8, 16, 16, 1), nn.Conv3d),
+             (nn.Conv3d(128, 128, 3, 1, 1, bias=False), (1, 2, 4, 4, 128), (1, 2, 4, 4, 128), nn.Conv3d),
+             (nn.Conv3d(64, 128, 3, 2, 1, bias=False), (1, 4, 8, 8, 64), (1, 2, 4, 4, 128), nn.ConvTranspose3d),
+             (nn.ConvTranspose3d(128, 64, 3, 2, 1, output_padding=1, bias=False), (1, 2, 4, 4, 128), (1, 4, 8, 8, 64), nn.Conv3d)]
+    for conv, xs, ys in [(c, x, y) for c, x, y, _ in cases]:
+        assert UmmaPlan(conv, None, xs[-1], torch.bfloat16).umma_ok
+    for conv, xs, ys, kind in cases:
+        adj = be._adjoint(conv, xs, ys)
+        assert type(adj) is kind
+        if kind is nn.ConvTranspose3d:
+            assert adj.output_padding[0] == 1
+        g_channels = be._as_operand(torch.zeros(ys, dtype=torch.bfloat16)).shape[-1]      # the classifier's 1 -> 16
+        assert UmmaPlan(adj, None, g_channels, torch.bfloat16).umma_ok
