@@ -335,3 +335,34 @@ class CorrBlock1D:
 
     def __call__(self, coords):
         return corr_lookup(self.pyramid, coords[:, 0], self.radius, self.num_levels)
+
+
+# --------------------------------------------------------------------------- "next" rows of SURVEY 8f: learned upsampling
+def convex_upsample(flow: torch.Tensor, mask: torch.Tensor, factor: int) -> torch.Tensor:
+    """RAFTStereo.upsample_flow (RAFTStereo/raft_stereo.py:81-93): every fine pixel (fy, fx) of coarse pixel (h, w) is a convex
+    combination -- softmax over the 9 mask logits of that fine pixel -- of the 3x3 coarse neighbourhood of ``factor * flow``
+    (zero outside the image).  flow [N,D,H,W], mask [N, 9*factor^2, H, W] (channel = tap*factor^2 + fy*factor + fx)
+    -> [N, D, factor*H, factor*W].  Written as explicit loops over the 9 taps."""
+    N, D, H, W = flow.shape
+    f = factor
+    w = torch.softmax(mask.view(N, 9, f, f, H, W), dim=1)
+    padded = F.pad(f * flow, (1, 1, 1, 1))
+    out = torch.zeros(N, D, f, f, H, W, dtype=flow.dtype)
+    for tap in range(9):
+        dy, dx = tap // 3, tap % 3
+        out = out + w[:, tap][:, None] * padded[:, :, dy:dy + H, dx:dx + W][:, :, None, None]
+    return out.permute(0, 1, 4, 2, 5, 3).reshape(N, D, f * H, f * W)
+
+
+def context_upsample(disp_low: torch.Tensor, up_weights: torch.Tensor) -> torch.Tensor:
+    """IGEVStereo/submodule.py:243-255: fine pixel (Y, X) takes the 3x3 neighbourhood of its coarse parent (Y//4, X//4)
+    (zero outside), weighted by its own 9 weights (already soft-maxed by the caller).  disp_low [B,1,h,w],
+    up_weights [B,9,4h,4w] -> [B,4h,4w]."""
+    B, _, h, w = disp_low.shape
+    padded = F.pad(disp_low[:, 0], (1, 1, 1, 1))
+    out = torch.zeros(B, 4 * h, 4 * w, dtype=disp_low.dtype)
+    for tap in range(9):
+        dy, dx = tap // 3, tap % 3
+        nb = padded[:, dy:dy + h, dx:dx + w]
+        out = out + up_weights[:, tap] * nb.repeat_interleave(4, dim=1).repeat_interleave(4, dim=2)
+    return out

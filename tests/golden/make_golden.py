@@ -589,10 +589,25 @@ def acvnet_train():
     save("acvnet_train.npz", **out)
 
 
+@torch.no_grad()
+def upsampling():
+    """the two learned convex upsamplers, op level (RAFTStereo.upsample_flow at factor 4 and 8,
+    IGEVStereo context_upsample)."""
+    import argparse
+    out = {}
+    for f in (4, 8):
+        net = ref("RAFTStereo.raft_stereo").RAFTStereo(argparse.Namespace(n_downsample={4: 2, 8: 3}[f]))
+        flow, mask = rnd(60 + f, 2, 2, 5, 7), rnd(61 + f, 2, 9 * f * f, 5, 7)
+        out.update({f"raft_flow{f}": flow, f"raft_mask{f}": mask, f"raft_up{f}": net.upsample_flow(flow, mask)})
+    disp, wts = rnd(70, 2, 1, 5, 7), torch.softmax(rnd(71, 2, 9, 20, 28), dim=1)
+    out.update(igev_disp=disp, igev_w=wts, igev_up=ref("IGEVStereo.submodule").context_upsample(disp, wts))
+    save("ops_upsampling.npz", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     # order matters: models() starts models.json afresh, the later generators add their entries to it
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade", "train", "cfnet", "pcwnet", "igev_model",
-                             "variants", "raft_train", "igev_train", "pcwnet_train", "cfnet_train", "acvnet_train"]
+                             "variants", "upsampling", "raft_train", "igev_train", "pcwnet_train", "cfnet_train", "acvnet_train"]
     for w in which:
         globals()[w]()
