@@ -59,6 +59,16 @@ int stb_concat_volume_f32(const float* left, const float* right, const float* at
                           int B, int C, int H, int W, int D, int mask_left, int c_total, int c_off,
                           void* stream);
 
+/* CFNet sampled cost volume (cascade stages): cost_volume_generator 'gwc' + 'concat' + the sample channel, concatenated
+ * (CFNet/cfnet.py:472-496, 545-550; SpatialTransformer CFNet/submodule.py:302-349; groupwise_correlation_4D :162-168).
+ *   gw_*  [B,Cg,H,W], cat_* [B,Cc,H,W] (nullable when Cc == 0), samples [B,S,H,W] fp32 holding integer disparities
+ *   vol   [B, G + 2*Cc + 1, S, H, W]: G group-wise correlations at x = w - sample, Cc left channels (broadcast over S),
+ *         Cc right channels gathered at x, the samples themselves; x clamped to [0, W-1], gathered values zeroed where
+ *         w - sample falls outside the row.  Opt-in on the host side (STB_CFNET_SAMPLED), not yet run on hardware. */
+int stb_sampled_volume_f32(const float* gw_left, const float* gw_right, const float* cat_left, const float* cat_right,
+                           const float* samples, float* vol, int B, int Cg, int G, int Cc, int S, int H, int W,
+                           void* stream);
+
 /* F.softmax(x, dim=D axis) of a [B,D,plane] tensor (ACVNet/acv.py:196, plane = H*W). */
 int stb_softmax_d_f32(const float* x, float* y, int B, int D, long long plane, void* stream);
 

@@ -366,3 +366,31 @@ def context_upsample(disp_low: torch.Tensor, up_weights: torch.Tensor) -> torch.
         nb = padded[:, dy:dy + h, dx:dx + w]
         out = out + up_weights[:, tap] * nb.repeat_interleave(4, dim=1).repeat_interleave(4, dim=2)
     return out
+
+
+# --------------------------------------------------------------------------- CFNet sampled volume
+def sampled_volume(gw_left, gw_right, cat_left, cat_right, samples, num_groups: int) -> torch.Tensor:
+    """CFNet cascade-stage volume (CFNet/cfnet.py:545-550): cat of cost_volume_generator(..., 'gwc') (:472-496 with
+    groupwise_correlation_4D, submodule.py:162-168), cost_volume_generator(..., 'concat') and the sample channel.
+    SpatialTransformer (submodule.py:302-349): the right feature at x = w - sample, x clamped to [0, W-1] for the gather,
+    the gathered value zeroed where w - sample is outside [0, W-1]; the left feature broadcast over the samples.
+    gw_* [B,Cg,H,W], cat_* [B,Cc,H,W], samples [B,S,H,W] (integer valued) -> [B, G + 2*Cc + 1, S, H, W]."""
+    B, Cg, H, W = gw_left.shape
+    S = samples.shape[1]
+    coord = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W) - samples.float()            # [B,S,H,W]
+    valid = ~((coord < 0) | (coord > W - 1))
+    x = coord.clamp(0, W - 1).long()
+
+    def warp(right):                                   # [B,C,H,W] -> [B,C,S,H,W]
+        C = right.shape[1]
+        out = torch.zeros(B, C, S, H, W, dtype=right.dtype)
+        for s in range(S):
+            idx = x[:, s][:, None].expand(B, C, H, W)
+            out[:, :, s] = torch.gather(right, 3, idx) * valid[:, s][:, None]
+        return out
+
+    k = Cg // num_groups
+    prod = gw_left[:, :, None] * warp(gw_right)                                               # [B,Cg,S,H,W]
+    gwc = prod.view(B, num_groups, k, S, H, W).mean(dim=2)
+    left = cat_left[:, :, None].expand(B, cat_left.shape[1], S, H, W)
+    return torch.cat((gwc, left, warp(cat_right), samples.float()[:, None]), dim=1)

@@ -28,6 +28,7 @@ _PP = POINTER(c_void_p)
 SIGNATURES = {
     "stb_gwc_volume_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "stb_concat_volume_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "stb_sampled_volume_f32": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "stb_softmax_d_f32": [_P, _P, _I, _I, _LL, _P],
     "stb_upsample_softargmin_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "stb_disparity_regression_f32": [_P, _P, _I, _I, _LL, _P],

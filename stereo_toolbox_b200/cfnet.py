@@ -10,6 +10,8 @@ volumes are host-side torch glue around them.
 from __future__ import annotations
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -154,6 +156,11 @@ def _classif(c):
     return nn.Sequential(convbn_3d(c, c, 3, 1, 1), nn.Identity(), nn.Conv3d(c, 1, kernel_size=3, padding=1, stride=1, bias=False))
 
 
+# STB_CFNET_SAMPLED=1: build the cascade stages' sampled volumes with stb_sampled_volume_f32 instead of the torch
+# expand / gather / multiply / mean / cat chain.  Opt-in until the kernel has been confirmed on hardware.
+_SAMPLED_KERNEL = os.environ.get("STB_CFNET_SAMPLED", "0") == "1"
+
+
 class cfnet(nn.Module):
     def __init__(self, maxdisp, use_concat_volume=False, precision="fp32"):
         super().__init__()
@@ -217,6 +224,8 @@ class cfnet(nn.Module):
 
     def _sampled_volume(self, fl, fr, key_gw, key_cat, samples, groups):
         """cost_volume_generator x2 + cat (cfnet.py:545-550): [gwc(groups) | left | warped right | samples]."""
+        if _SAMPLED_KERNEL and samples.is_cuda and not torch.is_grad_enabled():    # opt-in: one fused launch (csrc/sampled.cu)
+            return ops.sampled_volume(fl[key_gw], fr[key_gw], fl[key_cat], fr[key_cat], samples, groups)
         wr, lf = self._warp(fl[key_cat], fr[key_cat], samples)
         concat = torch.cat((lf, wr), dim=1)
         wr, lf = self._warp(fl[key_gw], fr[key_gw], samples)

@@ -76,6 +76,22 @@ def concat_volume(left: torch.Tensor, right: torch.Tensor, maxdisp: int, mask_le
     return out
 
 
+def sampled_volume(gw_left, gw_right, cat_left, cat_right, samples, num_groups: int) -> torch.Tensor:
+    """CFNet cascade-stage volume [gwc(groups) | left | warped right | samples] in one launch (CFNet/cfnet.py:472-496,
+    545-550; SpatialTransformer CFNet/submodule.py:302-349).  gw_* [B,Cg,H,W], cat_* [B,Cc,H,W], samples [B,S,H,W] (integer
+    valued) -> [B, groups + 2*Cc + 1, S, H, W] fp32."""
+    _need_cuda(gw_left, gw_right, cat_left, cat_right, samples)
+    gw_left, gw_right, cat_left, cat_right, samples = (_f32c(t) for t in (gw_left, gw_right, cat_left, cat_right, samples))
+    B, Cg, H, W = gw_left.shape
+    Cc, S = cat_left.shape[1], samples.shape[1]
+    assert Cg % num_groups == 0                              # CFNet/submodule.py:164
+    assert tuple(samples.shape) == (B, S, H, W) and tuple(cat_left.shape) == (B, Cc, H, W)
+    vol = torch.empty(B, num_groups + 2 * Cc + 1, S, H, W, device=gw_left.device, dtype=torch.float32)
+    _lib.call("stb_sampled_volume_f32", _p(gw_left), _p(gw_right), _p(cat_left), _p(cat_right), _p(samples), _p(vol),
+              B, Cg, num_groups, Cc, S, H, W, _stream())
+    return vol
+
+
 def softmax_d(x: torch.Tensor) -> torch.Tensor:
     """F.softmax(x, dim=2) of [B,1,D,H,W] (or dim=1 of [B,D,H,W])."""
     _need_cuda(x)

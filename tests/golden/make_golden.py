@@ -604,10 +604,31 @@ def upsampling():
     save("ops_upsampling.npz", **out)
 
 
+@torch.no_grad()
+def sampled():
+    """CFNet's sampled cascade volume, op level -- the reference's cost_volume_generator ('gwc' and
+    'concat') + sample channel exactly as cfnet.py:545-550 concatenates them (``Tensor.get_device`` patch as in cfnet()).
+    Samples include values that push w - sample outside the row on both sides."""
+    orig = torch.Tensor.get_device
+    torch.Tensor.get_device = lambda self: self.device
+    try:
+        net = ref("CFNet.cfnet").CFNet(64)
+        gl, gr = rnd(80, 2, 16, 5, 23), rnd(81, 2, 16, 5, 23)
+        cl, cr = rnd(82, 2, 3, 5, 23), rnd(83, 2, 3, 5, 23)
+        g = torch.Generator().manual_seed(84)
+        samples = torch.randint(-3, 26, (2, 6, 5, 23), generator=g)
+        cat_v, _ = net.cost_volume_generator(cl, cr, samples, "concat")
+        gwc_v, smp = net.cost_volume_generator(gl, gr, samples, "gwc", 4)
+        vol = torch.cat((gwc_v, cat_v, smp), dim=1)
+    finally:
+        torch.Tensor.get_device = orig
+    save("ops_sampled.npz", gl=gl, gr=gr, cl=cl, cr=cr, samples=samples.float(), vol=vol)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     # order matters: models() starts models.json afresh, the later generators add their entries to it
     which = sys.argv[1:] or ["ops", "blocks", "models", "raft", "acv", "igev", "cascade", "train", "cfnet", "pcwnet", "igev_model",
-                             "variants", "upsampling", "raft_train", "igev_train", "pcwnet_train", "cfnet_train", "acvnet_train"]
+                             "variants", "upsampling", "sampled", "raft_train", "igev_train", "pcwnet_train", "cfnet_train", "acvnet_train"]
     for w in which:
         globals()[w]()
