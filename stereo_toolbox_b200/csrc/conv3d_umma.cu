@@ -178,6 +178,7 @@ __device__ __forceinline__ void issue_dispatch(const UArgs& a, int tq, uint32_t 
 // kernel that does not carry code they never execute.
 // LEAN: 0 = generic, 1 = lean / plain taps (one column block), 2 = lean / kw-merged (3 column blocks + lane realignment),
 // 4 = kw-merged single-channel classifier with fp32 output (opt-in, STB_UMMA_CLS1),
+// 5 = merged transposed conv with the two w-parity classes stored as one contiguous pair (opt-in, STB_UMMA_T2PAIR),
 // 3 = lean / merged transposed conv (8 parity-class blocks).
 template <int ACT, bool F16, int LEAN>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
@@ -345,7 +346,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // ================================ epilogue warps ================================
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
         const int egroup = (warp - 3) >> 2;         // epilogue group 0/1 drains M-tiles m = egroup, egroup+2, ...
-        const int nblk_e = LEAN == 3 ? 8 : (LEAN ? 1 : (a.cblocks == 8 ? 8 : 1));     // merged transposed conv: all 8 parity classes in one round
+        const int nblk_e = LEAN == 3 ? 8 : LEAN == 5 ? 4 : (LEAN ? 1 : (a.cblocks == 8 ? 8 : 1));     // merged transposed conv: all 8 parity classes in one round (LEAN 5: as 4 w-pairs)
         const int items = a.nM * nblk_e;               // (M-tile, class block) work items per round, dealt to 2 groups
         const bool active = egroup < (items >= 2 ? 2 : 1);
         const size_t ostride_w = (size_t)a.Cout_total;
@@ -372,6 +373,67 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const bool trace = !LEAN && (int)ground < trace_rounds && warp == 3 && lane == 0;
             if (trace) trace_buf[ground * 8 + 4] = clock64();
             for (int item = egroup; item < items && !(dbg & 2); item += 2) {
+              if (LEAN == 5) {
+                // Merged transposed conv, the two w-parity classes of one (d,h) parity handled together: a thread's two output
+                // voxels (ow, ow + 1) are adjacent in memory, so it writes 2 x Cout_total contiguous channels (128 B at 32
+                // channels) and a warp a fully contiguous span, instead of 64-byte pieces at a 128-byte stride; the address /
+                // validity arithmetic is done once per pair.  Cn == 32 (one column block per class).
+                const int m = item >> 2, pb = item & 3;
+                const int od = s * a.out_stride + (pb >> 1);
+                const int q = 128 * m + q4 * 32 + lane;
+                const int jh_l = q / TWP, jw_l = q % TWP;
+                const int jh = jh0 + jh_l, jw = jw0 + jw_l;
+                const bool valid = (jh_l < a.TH) && (jw_l < a.TW) && (jh < a.nclass_h) && (jw < a.nclass_w) && (od < a.Do);
+                const int oh = jh * 2 + (pb & 1), ow = jw * 2;
+                const bool in0 = valid && oh < a.Ho && ow < a.Wo, in1 = in0 && ow + 1 < a.Wo;
+                const size_t eoff = ((((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow) * ostride_w + a.cout_off;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * nM + m) * Cn * 8 + pb * 2 * Cn);
+                uint32_t v0[32], v1[32];
+                __syncwarp();
+                tmem_ld_32x32(taddr, v0);
+                tmem_ld_32x32(taddr + (uint32_t)Cn, v1);
+                tmem_ld_wait();
+                if (item + 2 >= items) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                }
+                auto finish = [&](const uint32_t (&v)[32], size_t off, bool ok) {
+                    if (!ok) return;
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + sh0[i];
+                    if (a.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.residual) + off);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 rv = __ldg(rp + i);
+                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 h2 = unpack16(rw[j], f16);
+                                f[i * 8 + j * 2] += h2.x;
+                                f[i * 8 + j * 2 + 1] += h2.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], ACT);
+                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + off);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 o;
+                        o.x = pack16(f[i * 8 + 0], f[i * 8 + 1], f16);
+                        o.y = pack16(f[i * 8 + 2], f[i * 8 + 3], f16);
+                        o.z = pack16(f[i * 8 + 4], f[i * 8 + 5], f16);
+                        o.w = pack16(f[i * 8 + 6], f[i * 8 + 7], f16);
+                        op[i] = o;
+                    }
+                };
+                finish(v0, eoff, in0);
+                finish(v1, eoff + ostride_w, in1);
+                continue;
+              }
               {
                 const int m = nblk_e == 8 ? (item >> 3) : item, blk = nblk_e == 8 ? (item & 7) : 0;
                 const int cd = nblk_e == 8 ? (blk >> 2) : cl.od0, chh = nblk_e == 8 ? ((blk >> 1) & 1) : cl.oh0,
@@ -583,6 +645,12 @@ int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& t
             return launch_one_impl<ACT, F16, 4>(grid, smem, st, tx, tw, a);
     }
     const bool lean = !a.debug && !g_trace_armed && !a.partial && !a.out_fp32 && (a.Cn_valid & 31) == 0;
+    // opt-in (STB_UMMA_T2PAIR=1) until confirmed on hardware: merged transposed conv with w-paired stores (LEAN 5)
+    static const bool t2pair = getenv("STB_UMMA_T2PAIR") != nullptr && atoi(getenv("STB_UMMA_T2PAIR")) != 0;
+    if constexpr (ACT == STB_ACT_RELU) {
+        if (t2pair && lean && a.cblocks == 8 && a.merge == 1 && a.Cn == 32 && a.shift)
+            return launch_one_impl<ACT, F16, 5>(grid, smem, st, tx, tw, a);
+    }
     if (lean && a.cblocks == 8 && a.merge == 1) return launch_one_impl<ACT, F16, 3>(grid, smem, st, tx, tw, a);
     if (lean && a.cblocks == 3 && a.merge == 3) return launch_one_impl<ACT, F16, 2>(grid, smem, st, tx, tw, a);
     if (lean && a.cblocks == 1 && a.merge == 1) return launch_one_impl<ACT, F16, 1>(grid, smem, st, tx, tw, a);

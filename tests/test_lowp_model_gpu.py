@@ -62,11 +62,13 @@ def test_head_x4_fast_path_matches_generic(tmp_path):
 
 
 @unconfirmed_kernels
-def test_classifier_instantiation_is_bit_identical(tmp_path):
+@pytest.mark.parametrize("switch", ["STB_UMMA_CLS1", "STB_UMMA_T2PAIR"])
+def test_optin_instantiations_are_bit_identical(tmp_path, switch):
     """STB_UMMA_CLS1=1 routes the 32->1 classifiers (kw-merged, fp32 out, no residual) to their own instantiation of
-    the tcgen05 conv kernel (three single-column TMEM reads + 2 shuffles instead of three 32-column reads + 64): same
-    accumulators, same additions in the same order, so the pre-softmax cost must be bit-identical.  The switch is read
-    once per process, hence the subprocess."""
+    the tcgen05 conv kernel (three single-column TMEM reads + 2 shuffles instead of three 32-column reads + 64);
+    STB_UMMA_T2PAIR=1 routes the 64->32 merged transposed convs to the instantiation that stores the two w-parity classes
+    as one contiguous pair.  Same accumulators, same additions in the same order, so the pre-softmax cost must be
+    bit-identical.  The switches are read once per process, hence the subprocess."""
     import os
     import subprocess
     import sys
@@ -82,7 +84,7 @@ def test_classifier_instantiation_is_bit_identical(tmp_path):
             "d = net(l.cuda(), r.cuda()); torch.save((net._last_cost.cpu(), d.cpu()), %r)"
             % (root, os.path.join(root, "tests"), str(tmp_path / "cls1.pt")))
     subprocess.run([sys.executable, "-c", "import torch\nwith torch.no_grad():\n    exec(%r)" % code], check=True,
-                   env=dict(os.environ, STB_UMMA_CLS1="1"), timeout=300)
+                   env=dict(os.environ, **{switch: "1"}), timeout=300)
     cost1, disp1 = torch.load(tmp_path / "cls1.pt")
     sd, meta = golden_state("gwcnet_gc")
     net = S.GwcNet_GC(meta["maxdisp"], precision="fp16")
