@@ -44,6 +44,7 @@ STB_HEAD_X4=1 STB_UMMA_CLS1=1 timeout 600 python bench.py --steps 10 --warmup 3 
 cut -c1-300 gpurun_out/r2_bench_headx4_cls1.json
 STB_HEAD_X4=1 STB_UMMA_CLS1=1 STB_UMMA_T2PAIR=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_all_optins.json 2> gpurun_out/r2_bench_all_optins.err; echo "bench all opt-ins rc=$?"
 cut -c1-300 gpurun_out/r2_bench_all_optins.json
+STB_UMMA_CLS1=1 timeout 200 python tools/layer_bench.py --only "32->1 k3" > gpurun_out/r2_layer_cls1.log 2>&1; python tools/layer_bench.py --only "32->1 k3" >> gpurun_out/r2_layer_cls1.log 2>&1; cat gpurun_out/r2_layer_cls1.log
 STB_UMMA_T2PAIR=1 timeout 200 python tools/layer_bench.py --only "64->32 k3 s2T" > gpurun_out/r2_layer_t2pair.log 2>&1; python tools/layer_bench.py --only "64->32 k3 s2T" >> gpurun_out/r2_layer_t2pair.log 2>&1; cat gpurun_out/r2_layer_t2pair.log
 # BASELINE config 3 shape: exact fp32 training path, then the mixed-precision backend (train16.py, unconfirmed)
 timeout 600 python tools/train_step.py --height 576 --width 960 --batch 1 --steps 3 --warmup 1 > gpurun_out/r2_train_sceneflow.json 2> gpurun_out/r2_train_sceneflow.err; echo "train rc=$?"
