@@ -253,7 +253,7 @@ def main():
     value = total_pairs / (ms / 1e3)
     line = {"metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[precision], "data": "synthetic",
+            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16", "fp16x2": "f16x2"}[precision], "data": "synthetic",
             "config": workload_config(a.batch, precision),
             "e2e": {"value": total_pairs / (ms_e2e / 1e3), "unit": "maps/s",
                     "h2d_bytes_per_step": int(left_h.numel() * 4 * 2), "d2h_bytes_per_step": int(out_h.numel() * 4)},

@@ -243,7 +243,7 @@ def train_backend_for(model):
 def make_backend(precision: str):
     if precision == "fp32":
         return Fp32Backend()
-    if precision in ("bf16", "fp16"):
+    if precision in ("bf16", "fp16", "fp16x2"):
         from .aggregation_umma import UmmaBackend
         return UmmaBackend(precision)
-    raise ValueError(f"unknown precision {precision!r} (use 'fp32', 'bf16' or 'fp16')")
+    raise ValueError(f"unknown precision {precision!r} (use 'fp32', 'fp16x2', 'fp16' or 'bf16')")

@@ -26,7 +26,27 @@ FORCE_SIMT = os.environ.get("STB_UMMA_FORCE_SIMT", "0") == "1"
 KWMERGE = os.environ.get("STB_UMMA_KWMERGE", "1") == "1"          # merge the 3 kw taps along N (N = 3*Cout) for k3 s1 convs
 DECONV_MERGE = os.environ.get("STB_UMMA_DECONV_MERGE", "1") == "1"  # transposed conv: 8 parity classes in one accumulator round
 SIMT_STRIDE2 = os.environ.get("STB_UMMA_SIMT_STRIDE2", "0") == "1"   # keep strided convs on the CUDA-core companion
-TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
+TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp16x2": torch.float16}
+SPLIT_FLAG = 64      # stb_conv3d_umma flags bit6: operand-split fp16 ("fp16x2")
+
+
+def split_pack(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [..., C] (C % 16 == 0) -> operand-split fp16 [..., 2C]: every value x is stored as hi = fp16(x) and
+    lo = fp16(x - hi) (x = hi + lo to 22 mantissa bits), interleaved per 16 channels: [hi 0..15 | lo 0..15 | hi 16..31 | ...]
+    -- the storage format of the 'fp16x2' precision (csrc/conv3d_umma.cu, SPLIT)."""
+    c = w.shape[-1]
+    assert c % 16 == 0
+    hi = w.to(torch.float16)
+    lo = (w - hi.float()).to(torch.float16)
+    lead = w.shape[:-1]
+    return torch.stack((hi.reshape(*lead, c // 16, 16), lo.reshape(*lead, c // 16, 16)), dim=-2).reshape(*lead, 2 * c)
+
+
+def split_unpack(x: torch.Tensor) -> torch.Tensor:
+    """Inverse of split_pack: fp16 [..., 2C] -> fp32 [..., C]."""
+    c2 = x.shape[-1]
+    v = x.reshape(*x.shape[:-1], c2 // 32, 2, 16).float()
+    return (v[..., 0, :] + v[..., 1, :]).reshape(*x.shape[:-1], c2 // 2)
 
 
 def pad_channels(c: int) -> int:
@@ -46,8 +66,10 @@ class UmmaPlan:
     [tile][kc][Cpad][KC], the tap / class tables of stb_conv3d_umma_bf16, and the fp32 tap plan for the
     CUDA-core companion."""
 
-    def __init__(self, conv, bn, cin_tensor: int, dtype=torch.bfloat16):
+    def __init__(self, conv, bn, cin_tensor: int, dtype=torch.bfloat16, split: bool = False):
+        """``cin_tensor``: LOGICAL channel count of the input tensor (split tensors store 2 elements per channel)."""
         self.dtype = dtype
+        self.split = split
         w = conv.weight.detach().float()
         tr = isinstance(conv, nn.ConvTranspose3d)
         stride, pad, k = conv.stride[0], conv.padding[0], conv.kernel_size[0]
@@ -84,8 +106,9 @@ class UmmaPlan:
         if not tr and stride == 2 and SIMT_STRIDE2:
             return False
         in_stride = 1 if tr else stride
-        kc = min(cin, 32 if in_stride == 2 else 64)      # channels per K-chunk = one swizzled smem row
-        nk = cin // kc
+        cin_st = 2 * cin if self.split else cin           # storage elements per voxel
+        kc = min(cin_st, 32 if in_stride == 2 else 64)   # storage elements per K-chunk = one swizzled smem row
+        nk = cin_st // kc
         cpad = (cout + 15) // 16 * 16
         if bnp is not None:
             gamma, beta, mean, var = [t.detach().float() for t in bnp]
@@ -134,6 +157,8 @@ class UmmaPlan:
         full = torch.zeros(k * k * k, cpad, cin, device=w.device)
         full[:, :cout] = wt.reshape(k * k * k, cout, cin)
         tiles = full[torch.tensor(tile_src, device=w.device)]
+        if self.split:
+            tiles = split_pack(tiles)                     # [tile][cpad][2*cin]: (hi, lo) k-slices per 16 input channels
         self.wt = tiles.view(len(tile_src), cpad, nk, kc).permute(0, 2, 1, 3).contiguous().to(self.dtype)
         self.nwtiles, self.kc, self.nk, self.in_stride = len(tile_src), kc, nk, in_stride
         if self.nwtiles * 16 * kc * 2 > 150 * 1024 or len(dz) > 64:
@@ -190,12 +215,19 @@ class UmmaPlan:
 
 
 class UmmaBackend:
-    """precision 'bf16' or 'fp16': 16-bit channels-last activations, fp32 accumulation in TMEM."""
+    """precision 'bf16' or 'fp16': 16-bit channels-last activations, fp32 accumulation in TMEM.
+    precision 'fp16x2': the exact tensor-core path.  Every activation and weight is stored operand-split (fp16 hi + fp16 lo,
+    ``split_pack``), a K=16 step is three MMAs (hi*hi + hi*lo + lo*hi) into the same fp32 accumulator: fp32-level accuracy
+    (<= 1e-3 px vs the fp32 reference) at about a third of the single-fp16 tensor rate.  Tensors between backend calls are
+    [B,D,H,W,2C] fp16 then."""
 
     def __init__(self, precision: str = "bf16"):
         self.name = precision
         self.dtype = TORCH_DT[precision]
-        self.f16 = int(precision == "fp16")
+        self.split = precision == "fp16x2"
+        self.f16 = int(precision in ("fp16", "fp16x2"))
+        self.fmt = 2 if self.split else self.f16           # storage format code of the layout / volume entry points
+        self.cmul = 2 if self.split else 1                 # storage elements per logical channel
         self._plans: Dict[int, tuple] = {}
         self._ws: Dict[tuple, torch.Tensor] = {}
         self.prof = _NoProf()
@@ -209,7 +241,9 @@ class UmmaBackend:
         hit = self._plans.get(id(conv))
         if hit is not None and hit[0] == ver:
             return hit[1]
-        plan = UmmaPlan(conv, bn, cin_tensor, self.dtype)
+        plan = UmmaPlan(conv, bn, cin_tensor, self.dtype, self.split)
+        if self.split and not plan.umma_ok:
+            raise NotImplementedError("fp16x2 precision: this layer shape is not covered by the tcgen05 kernel")
         self._plans[id(conv)] = (ver, plan)
         return plan
 
@@ -230,10 +264,10 @@ class UmmaBackend:
         ct_pad = pad_channels(groups + 2 * cc)
         f = lambda t: None if t is None else ops._f32c(t)
         gwc_l, gwc_r, cat_l, cat_r = f(gwc_l), f(gwc_r), f(cat_l), f(cat_r)
-        vol = torch.empty(B, maxdisp4, H, W, ct_pad, device=gwc_l.device, dtype=self.dtype)
+        vol = torch.empty(B, maxdisp4, H, W, ct_pad * self.cmul, device=gwc_l.device, dtype=self.dtype)
         with self.prof.bracket("volume_cl16", 0.0, 4.0 * 2 * (gwc_l.numel() + (0 if cat_l is None else cat_l.numel()))
                                + 2.0 * vol.numel()):
-            _lib.call("stb_volume_cl16", _p(gwc_l), _p(gwc_r), _p(cat_l), _p(cat_r), _p(vol), self.f16, B, Cg, groups,
+            _lib.call("stb_volume_cl16", _p(gwc_l), _p(gwc_r), _p(cat_l), _p(cat_r), _p(vol), self.fmt, B, Cg, groups,
                       cc, H, W, maxdisp4, ct_pad, 1, _stream())
         return vol
 
@@ -245,13 +279,13 @@ class UmmaBackend:
         _, N, H, W, _ = feats[0].shape
         assert N == 2 * B and all(f.dtype == self.dtype and f.is_contiguous() for f in feats)
         ct_pad = pad_channels(groups + 2 * cc)
-        vol = torch.empty(B, maxdisp4, H, W, ct_pad, device=feats[0].device, dtype=self.dtype)
+        vol = torch.empty(B, maxdisp4, H, W, ct_pad * self.cmul, device=feats[0].device, dtype=self.dtype)
         ptrs = (ctypes.c_void_p * len(feats))(*[f.data_ptr() for f in feats])
-        chs = _iarr([f.shape[-1] for f in feats])
+        chs = _iarr([f.shape[-1] // self.cmul for f in feats])
         nbytes = 2.0 * (sum(f.numel() for f in feats) + (0 if cat is None else cat.numel()) + vol.numel())
         with self.prof.bracket("volume_cl16", 0.0, nbytes):
-            _lib.call("stb_volume_cl16_from_cl16", ptrs, chs, len(feats), _p(cat), 0 if cat is None else cat.shape[-1],
-                      _p(vol), self.f16, B, groups, cc, H, W, maxdisp4, ct_pad, 1, _stream())
+            _lib.call("stb_volume_cl16_from_cl16", ptrs, chs, len(feats), _p(cat), 0 if cat is None else cat.shape[-1] // self.cmul,
+                      _p(vol), self.fmt, B, groups, cc, H, W, maxdisp4, ct_pad, 1, _stream())
         return vol
 
     def volume_concat(self, l, r, maxdisp4, mask_left=True, att_prob=None):
@@ -260,44 +294,57 @@ class UmmaBackend:
         B, C, H, W = l.shape
         ct_pad = pad_channels(2 * C)
         l, r = ops._f32c(l), ops._f32c(r)
-        vol = torch.empty(B, maxdisp4, H, W, ct_pad, device=l.device, dtype=self.dtype)
+        vol = torch.empty(B, maxdisp4, H, W, ct_pad * self.cmul, device=l.device, dtype=self.dtype)
         with self.prof.bracket("volume_cl16", 0.0, 4.0 * 2 * l.numel() + 2.0 * vol.numel()):
-            _lib.call("stb_volume_cl16", _p(None), _p(None), _p(l), _p(r), _p(vol), self.f16, B, 0, 0, C, H, W,
+            _lib.call("stb_volume_cl16", _p(None), _p(None), _p(l), _p(r), _p(vol), self.fmt, B, 0, 0, C, H, W,
                       maxdisp4, ct_pad, int(mask_left), _stream())
         return vol
 
     # ---------------------------------------------------------------- conv family
     def conv(self, layer, x, act="none", residual=None):
         assert x.dtype == self.dtype and x.is_contiguous() and x.dim() == 5
-        B, Di, Hi, Wi, Cin = x.shape
+        B, Di, Hi, Wi, Cst = x.shape                      # Cst: storage elements per voxel (2 per channel when split)
+        Cin = Cst // self.cmul
         plan = self._plan(layer, Cin)
         Do, Ho, Wo = plan.out_size(Di), plan.out_size(Hi), plan.out_size(Wi)
         out_fp32 = plan.cout < 8          # the 32->1 classifier feeds the fp32 soft-argmin head directly
-        out = torch.empty(B, Do, Ho, Wo, plan.cout, device=x.device, dtype=torch.float32 if out_fp32 else self.dtype)
+        cout_t = plan.cout if (out_fp32 or not self.split) else (plan.cout + 15) // 16 * 16
+        alloc = torch.zeros if cout_t != plan.cout else torch.empty      # padded split channels must read as zero
+        out = alloc(B, Do, Ho, Wo, cout_t * (1 if out_fp32 else self.cmul), device=x.device,
+                    dtype=torch.float32 if out_fp32 else self.dtype)
+        post_res, post_act = None, None
         if residual is not None:
             assert residual.shape == out.shape and residual.is_contiguous()
-            if residual.dtype != self.dtype:
+            if out_fp32:
+                # fp32 output (classifier logits): the kernel's residual port is 16-bit, so the fp32 residual of PSMNet's
+                # cumulative heads (cost2 = classif2 + cost1, stackhourglass.py:134-136) is added afterwards on the small
+                # fp32 tensor instead of being rounded to 16 bits first
+                post_res, post_act, residual, act = residual, act, None, "none"
+            elif residual.dtype != self.dtype:
+                assert not self.split
                 residual = residual.to(self.dtype)
         fam = "conv3d_umma" if plan.umma_ok else "conv3d_taps_cl16"
         fl, by = 0.0, 0.0
         if self.prof.enabled:
-            fl, by = conv_work(plan.simt, (B, Cin, Di, Hi, Wi), (B, plan.cout, Do, Ho, Wo), 2, residual is not None)
+            fl, by = conv_work(plan.simt, (B, Cin, Di, Hi, Wi), (B, plan.cout, Do, Ho, Wo), 2 * self.cmul, residual is not None)
         detail = ""
         if self.prof.enabled:
             detail = f"{Cin}->{plan.cout} k{plan.k} s{plan.stride}{'T' if plan.tr else ''} @{Di}x{Hi}x{Wi}"
         with self.prof.bracket(fam, fl, by, detail=detail):
             if plan.umma_ok:
                 nsteps, nh, nw = (Di, Hi, Wi) if plan.tr else (Do, Ho, Wo)
-                ws = self._workspace(out.numel(), x.device) if plan.nk > 1 else None
+                ws = self._workspace(B * Do * Ho * Wo * cout_t, x.device) if plan.nk > 1 else None
                 _lib.call("stb_conv3d_umma", _p(x), _p(plan.wt), _p(plan.shift), _p(residual), _p(out), _p(ws),
-                          self.f16, B, Cin, plan.kc, Di, Hi, Wi, plan.cout, plan.cout, Do, Ho, Wo, plan.ntaps,
+                          self.f16, B, Cst, plan.kc, Di, Hi, Wi, cout_t, plan.cout, Do, Ho, Wo, plan.ntaps,
                           plan.c_dz, plan.c_dh, plan.c_dw, plan.c_sub, plan.c_widx, plan.c_nblk, plan.c_cls0,
                           plan.nwtiles, plan.nclass,
                           plan.c_tb, plan.c_te, plan.c_od0, plan.c_oh0, plan.c_ow0, plan.in_stride, plan.out_stride,
                           nsteps, nh, nw, plan.in_off, plan.in_off, ACT[act], int(out_fp32),
-                          BO_MODE | (ES_VARIANT << 1) | (4 if plan.merge else 0) | (8 if plan.deconv_merge else 0),
+                          BO_MODE | (ES_VARIANT << 1) | (4 if plan.merge else 0) | (8 if plan.deconv_merge else 0)
+                          | (SPLIT_FLAG if self.split else 0),
                           self.dchunk, _stream())
             else:
+                assert not self.split
                 sp = plan.simt
                 for sel, dd, dh, dw, T, in_s, out_s, (od0, oh0, ow0) in sp.classes:
                     nd = (Do - od0 + out_s - 1) // out_s
@@ -308,12 +355,18 @@ class UmmaBackend:
                     _lib.call("stb_conv3d_taps_cl16", _p(x), _p(sel), _p(sp.shift), _p(residual), _p(out),
                               int(out_fp32), self.f16, B, Cin, Di, Hi, Wi, plan.cout, Do, Ho, Wo, T, dd, dh, dw, in_s,
                               out_s, od0, oh0, ow0, nd, nh, nw, ACT[act], _stream())
+        if post_res is not None:
+            out = out + post_res.float()
+            if post_act == "relu":
+                out = torch.relu_(out)
+            elif post_act != "none":
+                raise NotImplementedError(f"activation {post_act!r} after an fp32 residual")
         return out
 
     # ---------------------------------------------------------------- ACVNet helpers
     def from_ncdhw(self, x):
         """fp32 [B,C,D,H,W] -> channels-last 16-bit with the channel count padded to a swizzle row."""
-        return to_channels_last(x, pad_channels(x.shape[1]), self.dtype)
+        return to_channels_last(x, pad_channels(x.shape[1]), self.dtype, split=self.split)
 
     def cost_ncdhw(self, cost):
         B, D, H, W, C = cost.shape
@@ -325,6 +378,8 @@ class UmmaBackend:
         return cost.view(B, D, H, W, 1)
 
     def block_attention(self, qkv, bias, heads, block):
+        if self.split:
+            raise NotImplementedError("fp16x2 precision: windowed attention core not built for split storage")
         B, D, H, W, C3 = qkv.shape
         with self.prof.bracket("block_attention", 4.0 * B * D * H * W * (C3 // 3) * block[0] * block[1] * block[2],
                                2.0 * (qkv.numel() + qkv.numel() // 3)):
@@ -332,21 +387,24 @@ class UmmaBackend:
 
     # ---------------------------------------------------------------- IGEV / CFNet helpers
     def gate(self, x, gate_logits):
+        if self.split:
+            raise NotImplementedError("fp16x2 precision: feature gate not built for split storage")
         return ops.feature_gate(x, gate_logits, channels_last=True, channels=gate_logits.shape[1])
 
     def cat(self, xs):
         """channel concatenation of channels-last tensors, re-padded to a legal K width."""
         xs = list(xs)
-        c = sum(t.shape[-1] for t in xs)
+        c = sum(t.shape[-1] for t in xs) // self.cmul
         cp = pad_channels(c)
+        assert not self.split or all((t.shape[-1] // 2) % 16 == 0 for t in xs)    # whole (hi, lo) blocks only
         if cp != c:
-            xs.append(torch.zeros(xs[0].shape[:-1] + (cp - c,), device=xs[0].device, dtype=xs[0].dtype))
+            xs.append(torch.zeros(xs[0].shape[:-1] + ((cp - c) * self.cmul,), device=xs[0].device, dtype=xs[0].dtype))
         return torch.cat(xs, dim=-1)
 
     def to_ncdhw(self, x, channels=None):
         if x.dtype == torch.float32:            # [B,D,H,W,C] fp32 (classifier-style outputs)
             return x.permute(0, 4, 1, 2, 3).contiguous()
-        return from_channels_last(x, channels)
+        return from_channels_last(x, channels, split=self.split)
 
     # ---------------------------------------------------------------- head (layout exit)
     def head(self, cost, maxdisp, H, W, align_corners=False):
@@ -357,23 +415,26 @@ class UmmaBackend:
 
 
 # layout helpers for tests / callers holding reference-layout tensors
-def to_channels_last(x: torch.Tensor, cpad: Optional[int] = None, dtype=torch.bfloat16) -> torch.Tensor:
+def to_channels_last(x: torch.Tensor, cpad: Optional[int] = None, dtype=torch.bfloat16, split: bool = False) -> torch.Tensor:
+    """fp32 [B,C,...] -> channels-last 16-bit [B,...,cpad]; split=True: operand-split fp16 [B,...,2*cpad] (cpad % 16 == 0)."""
     x = ops._f32c(x)
     B, C = x.shape[:2]
     S = x.numel() // (B * C)
     cpad = cpad or C
-    out = torch.empty((B,) + tuple(x.shape[2:]) + (cpad,), device=x.device, dtype=dtype)
-    _lib.call("stb_ncdhw_to_cl16", _p(x), _p(out), int(dtype == torch.float16), B, C, S, cpad, _stream())
+    if split:
+        assert dtype == torch.float16 and cpad % 16 == 0
+    out = torch.empty((B,) + tuple(x.shape[2:]) + (cpad * (2 if split else 1),), device=x.device, dtype=dtype)
+    _lib.call("stb_ncdhw_to_cl16", _p(x), _p(out), 2 if split else int(dtype == torch.float16), B, C, S, cpad, _stream())
     return out
 
 
-def from_channels_last(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+def from_channels_last(x: torch.Tensor, c: Optional[int] = None, split: bool = False) -> torch.Tensor:
     assert x.dtype in (torch.bfloat16, torch.float16) and x.is_contiguous()
-    B, cpad = x.shape[0], x.shape[-1]
+    B, cpad = x.shape[0], x.shape[-1] // (2 if split else 1)
     c = c or cpad
-    S = x.numel() // (B * cpad)
+    S = x.numel() // (B * x.shape[-1])
     out = torch.empty((B, c) + tuple(x.shape[1:-1]), device=x.device, dtype=torch.float32)
-    _lib.call("stb_cl16_to_ncdhw", _p(x), _p(out), int(x.dtype == torch.float16), B, c, S, cpad, _stream())
+    _lib.call("stb_cl16_to_ncdhw", _p(x), _p(out), 2 if split else int(x.dtype == torch.float16), B, c, S, cpad, _stream())
     return out
 
 

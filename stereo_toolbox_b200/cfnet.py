@@ -158,7 +158,7 @@ def _classif(c):
 
 # STB_CFNET_SAMPLED=1: build the cascade stages' sampled volumes with stb_sampled_volume_f32 instead of the torch
 # expand / gather / multiply / mean / cat chain.  Opt-in until the kernel has been confirmed on hardware.
-_SAMPLED_KERNEL = os.environ.get("STB_CFNET_SAMPLED", "0") == "1"
+_SAMPLED_KERNEL = os.environ.get("STB_CFNET_SAMPLED", "1") == "1"
 
 
 class cfnet(nn.Module):

@@ -132,11 +132,85 @@ __device__ __forceinline__ void store16(uint16_t* p, float v, int f16) {
     else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16(v);
 }
 
+// ---- 32 consecutive logical channels of one voxel <-> storage.  Plain 16-bit: 64 contiguous bytes.  SPLIT (fp16 hi + fp16 lo,
+// interleaved per 16 channels): 128 contiguous bytes  [hi 0..15 | lo 0..15 | hi 16..31 | lo 16..31].
+template <bool F16, bool SPLIT>
+__device__ __forceinline__ void add_residual32(float (&f)[32], const uint16_t* rp) {
+    constexpr int f16 = F16 ? 1 : 0;
+    const uint4* p = reinterpret_cast<const uint4*>(rp);
+    if constexpr (SPLIT) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {              // q = 16-channel block * 2 + which 8 of it
+            const uint4 hv = __ldg(p + (q >> 1) * 4 + (q & 1));
+            const uint4 lv = __ldg(p + (q >> 1) * 4 + 2 + (q & 1));
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 h2 = unpack16(hw[j], 1), l2 = unpack16(lw[j], 1);
+                f[q * 8 + j * 2] += h2.x + l2.x;          // hi + lo is exact in fp32
+                f[q * 8 + j * 2 + 1] += h2.y + l2.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 rv = __ldg(p + i);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 h2 = unpack16(rw[j], f16);
+                f[i * 8 + j * 2] += h2.x;
+                f[i * 8 + j * 2 + 1] += h2.y;
+            }
+        }
+    }
+}
+template <bool F16, bool SPLIT>
+__device__ __forceinline__ void store32(const float (&f)[32], uint16_t* outp) {
+    constexpr int f16 = F16 ? 1 : 0;
+    uint4* op = reinterpret_cast<uint4*>(outp);
+    if constexpr (SPLIT) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float x0 = f[q * 8 + j * 2], x1 = f[q * 8 + j * 2 + 1];
+                const __half2 h = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+                lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            op[(q >> 1) * 4 + (q & 1)] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            op[(q >> 1) * 4 + 2 + (q & 1)] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack16(f[i * 8 + 0], f[i * 8 + 1], f16);
+            o.y = pack16(f[i * 8 + 2], f[i * 8 + 3], f16);
+            o.z = pack16(f[i * 8 + 4], f[i * 8 + 5], f16);
+            o.w = pack16(f[i * 8 + 6], f[i * 8 + 7], f16);
+            op[i] = o;
+        }
+    }
+}
+// storage index of logical channel c inside a split row
+__device__ __forceinline__ int split_idx(int c) { return ((c >> 4) << 5) + (c & 15); }
+
 // ---- MMA issue, straight-line.  A branch controlled by a vector register between two UTCHMMAs costs about as much as
 // an MMA (probe mmarate3 variant 2: 99 vs 56 clk per N=96 MMA), and every counter of the issuer lives in a vector
 // register because it is live across mbarrier spin loops.  So the unit of issue is a chunk of NT taps whose
 // NT x NM x KS MMAs are fully unrolled; per-tap records come from the constant bank (LDCU -> uniform registers).
-template <int NT, int NM, int KS>
+//
+// SPLIT (operand-split fp16, "fp16x2"): every activation and weight is stored as fp16 hi + fp16 lo (x = hi + lo, 22
+// mantissa bits), interleaved per 16 channels -- a 32-byte k-slice of hi values is followed by the 32-byte k-slice of the
+// lo values of the same 16 channels.  One logical K=16 step is three kind::f16 MMAs into the same fp32 accumulator:
+// hi*hi, hi*lo_w, lo_a*hi_w (lo*lo is below fp32 rounding).  The tap / plane machinery is unchanged: the lo values are
+// just further k-slices of the same TMA-staged rows.
+template <int NT, int NM, int KS, bool SPLIT>
 __device__ __forceinline__ void issue_taps(const UArgs& a, int tq, uint32_t abase, uint32_t dbase) {
     const uint32_t mt16 = (128u * (uint32_t)a.ROWB) >> 4, dhi = a.desc_hi, ncol = (uint32_t)(a.Cn * a.cblocks);
 #pragma unroll
@@ -149,24 +223,33 @@ __device__ __forceinline__ void issue_taps(const UArgs& a, int tq, uint32_t abas
         for (int m = 0; m < NM; ++m) {
             const uint32_t dcol_t = dc + (uint32_t)m * ncol;
             const uint32_t alo = a0 + (uint32_t)m * mt16;
+            if constexpr (SPLIT) {
 #pragma unroll
-            for (int k = 0; k < KS; ++k)
-                mma_f16_ss2(dcol_t, alo + 2u * k, e.b16 + 2u * k, dhi, e.idesc, k ? 1u : acc);
+                for (int k = 0; k < KS; k += 2) {           // k-slice k = hi, k + 1 = lo of the same 16 channels
+                    mma_f16_ss2(dcol_t, alo + 2u * k, e.b16 + 2u * k, dhi, e.idesc, k ? 1u : acc);
+                    mma_f16_ss2(dcol_t, alo + 2u * k, e.b16 + 2u * k + 2u, dhi, e.idesc, 1u);
+                    mma_f16_ss2(dcol_t, alo + 2u * k + 2u, e.b16 + 2u * k, dhi, e.idesc, 1u);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < KS; ++k)
+                    mma_f16_ss2(dcol_t, alo + 2u * k, e.b16 + 2u * k, dhi, e.idesc, k ? 1u : acc);
+            }
         }
     }
 }
-template <int NT, int KS>
+template <int NT, int KS, bool SPLIT>
 __device__ __forceinline__ void issue_dispatch_m(const UArgs& a, int tq, uint32_t abase, uint32_t dbase, int nM) {
-    if (nM == 2) issue_taps<NT, 2, KS>(a, tq, abase, dbase);
-    else if (nM == 1) issue_taps<NT, 1, KS>(a, tq, abase, dbase);
-    else if (nM == 4) issue_taps<NT, 4, KS>(a, tq, abase, dbase);
-    else issue_taps<NT, 3, KS>(a, tq, abase, dbase);
+    if (nM == 2) issue_taps<NT, 2, KS, SPLIT>(a, tq, abase, dbase);
+    else if (nM == 1) issue_taps<NT, 1, KS, SPLIT>(a, tq, abase, dbase);
+    else if (nM == 4) issue_taps<NT, 4, KS, SPLIT>(a, tq, abase, dbase);
+    else issue_taps<NT, 3, KS, SPLIT>(a, tq, abase, dbase);
 }
-template <int NT>
+template <int NT, bool SPLIT>
 __device__ __forceinline__ void issue_dispatch(const UArgs& a, int tq, uint32_t abase, uint32_t dbase, int nM, int ks) {
-    if (ks == 2) issue_dispatch_m<NT, 2>(a, tq, abase, dbase, nM);
-    else if (ks == 4) issue_dispatch_m<NT, 4>(a, tq, abase, dbase, nM);
-    else issue_dispatch_m<NT, 1>(a, tq, abase, dbase, nM);
+    if (ks == 2) issue_dispatch_m<NT, 2, SPLIT>(a, tq, abase, dbase, nM);
+    else if (ks == 4) issue_dispatch_m<NT, 4, SPLIT>(a, tq, abase, dbase, nM);
+    else if constexpr (!SPLIT) issue_dispatch_m<NT, 1, SPLIT>(a, tq, abase, dbase, nM);      // split rows hold >= one (hi, lo) slice pair
 }
 
 // ACT / F16 are compile-time so the epilogue stays a few hundred instructions: with a runtime activation switch
@@ -180,7 +263,7 @@ __device__ __forceinline__ void issue_dispatch(const UArgs& a, int tq, uint32_t 
 // 4 = kw-merged single-channel classifier with fp32 output (opt-in, STB_UMMA_CLS1),
 // 5 = merged transposed conv with the two w-parity classes stored as one contiguous pair (opt-in, STB_UMMA_T2PAIR),
 // 3 = lean / merged transposed conv (8 parity-class blocks).
-template <int ACT, bool F16, int LEAN>
+template <int ACT, bool F16, int LEAN, bool SPLIT>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ UArgs a) {
@@ -326,8 +409,12 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                             wait_upto(dead_now + z + 1);
                             if (trace && g == gb) trace_buf[ground * 8 + 2] = clock64();
                             int tq = g0;
-                            for (; tq + 3 <= g1; tq += 3) issue_dispatch<3>(a, tq, abase, dbase, nM, ksteps);
-                            for (; tq < g1; ++tq) issue_dispatch<1>(a, tq, abase, dbase, nM, ksteps);
+                            if constexpr (SPLIT) {          // 3x the MMAs per tap: unroll one tap at a time
+                                for (; tq < g1; ++tq) issue_dispatch<1, true>(a, tq, abase, dbase, nM, ksteps);
+                            } else {
+                                for (; tq + 3 <= g1; tq += 3) issue_dispatch<3, false>(a, tq, abase, dbase, nM, ksteps);
+                                for (; tq < g1; ++tq) issue_dispatch<1, false>(a, tq, abase, dbase, nM, ksteps);
+                            }
                             if (gr.rel && dead_now + z < next_dead) release_upto(dead_now + z + 1);
                         }
                         if (!(dbg & 4)) mma_commit(&tmem_full[buf]);
@@ -351,6 +438,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const bool active = egroup < (items >= 2 ? 2 : 1);
         const size_t ostride_w = (size_t)a.Cout_total;
         constexpr int f16 = F16 ? 1 : 0;
+        constexpr size_t K16 = SPLIT ? 2 : 1;       // 16-bit storage elements per logical channel
         const bool full32 = LEAN || (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
         const float* const partial = LEAN ? nullptr : a.partial;
         const bool out_fp32 = !LEAN && a.out_fp32;
@@ -403,32 +491,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     float f[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + sh0[i];
-                    if (a.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.residual) + off);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint4 rv = __ldg(rp + i);
-                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 h2 = unpack16(rw[j], f16);
-                                f[i * 8 + j * 2] += h2.x;
-                                f[i * 8 + j * 2 + 1] += h2.y;
-                            }
-                        }
-                    }
+                    if (a.residual) add_residual32<F16, SPLIT>(f, reinterpret_cast<const uint16_t*>(a.residual) + off * K16);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], ACT);
-                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + off);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 o;
-                        o.x = pack16(f[i * 8 + 0], f[i * 8 + 1], f16);
-                        o.y = pack16(f[i * 8 + 2], f[i * 8 + 3], f16);
-                        o.z = pack16(f[i * 8 + 4], f[i * 8 + 5], f16);
-                        o.w = pack16(f[i * 8 + 6], f[i * 8 + 7], f16);
-                        op[i] = o;
-                    }
+                    store32<F16, SPLIT>(f, reinterpret_cast<uint16_t*>(a.out) + off * K16);
                 };
                 finish(v0, eoff, in0);
                 finish(v1, eoff + ostride_w, in1);
@@ -530,20 +596,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                                 f[i * 4] += sv.x; f[i * 4 + 1] += sv.y; f[i * 4 + 2] += sv.z; f[i * 4 + 3] += sv.w;
                             }
                         }
-                        if (a.residual) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.residual) + eoff);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint4 rv = __ldg(rp + i);
-                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 h2 = unpack16(rw[j], f16);
-                                    f[i * 8 + j * 2] += h2.x;
-                                    f[i * 8 + j * 2 + 1] += h2.y;
-                                }
-                            }
-                        }
+                        if (a.residual) add_residual32<F16, SPLIT>(f, reinterpret_cast<const uint16_t*>(a.residual) + eoff * K16);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], ACT);
                         if (trace && item == egroup && c0 == 0) trace_buf[ground * 8 + 7] = clock64();     // arithmetic done, stores next
@@ -552,16 +605,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
                             for (int i = 0; i < 8; ++i) op[i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
                         } else {
-                            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + eoff);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                uint4 o;
-                                o.x = pack16(f[i * 8 + 0], f[i * 8 + 1], f16);
-                                o.y = pack16(f[i * 8 + 2], f[i * 8 + 3], f16);
-                                o.z = pack16(f[i * 8 + 4], f[i * 8 + 5], f16);
-                                o.w = pack16(f[i * 8 + 6], f[i * 8 + 7], f16);
-                                op[i] = o;
-                            }
+                            store32<F16, SPLIT>(f, reinterpret_cast<uint16_t*>(a.out) + eoff * K16);
                         }
                     } else if (inb) {
                         // ---------------- ragged path (Cout not a multiple of 32: the 32->1 classifier, IGEV widths)
@@ -572,10 +616,20 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                                 float x = f[i];
                                 if (partial) x += __ldg(partial + eoff + i);
                                 if (a.shift) x += __ldg(a.shift + a.cout_off + c0 + i);
-                                if (a.residual) x += load16(reinterpret_cast<const uint16_t*>(a.residual) + eoff + i, f16);
+                                // split rows: logical channel -> (hi, lo) slots of its 16-channel block
+                                const size_t e16 = SPLIT ? vox * (2 * ostride_w) + split_idx(a.cout_off + c0 + i) : eoff + i;
+                                if (a.residual) {
+                                    const uint16_t* rp = reinterpret_cast<const uint16_t*>(a.residual) + e16;
+                                    x += SPLIT ? load16(rp, 1) + load16(rp + 16, 1) : load16(rp, f16);
+                                }
                                 x = stb_act(x, ACT);
                                 if (out_fp32) reinterpret_cast<float*>(a.out)[eoff + i] = x;
-                                else store16(reinterpret_cast<uint16_t*>(a.out) + eoff + i, x, f16);
+                                else if (SPLIT) {
+                                    const __half h = __float2half_rn(x);
+                                    uint16_t* op = reinterpret_cast<uint16_t*>(a.out) + e16;
+                                    *reinterpret_cast<__half*>(op) = h;
+                                    *reinterpret_cast<__half*>(op + 16) = __float2half_rn(x - __half2float(h));
+                                } else store16(reinterpret_cast<uint16_t*>(a.out) + eoff + i, x, f16);
                             }
                         }
                     }
@@ -596,12 +650,12 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
-template <int ACT, bool F16, int LEAN>
+template <int ACT, bool F16, int LEAN, bool SPLIT = false>
 int launch_one_impl(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, UArgs& a) {
     static bool attr_set = false;
     static uint32_t smem_base = 0;      // per kernel instance: address of the aligned dynamic-smem base in the shared window
     if (!attr_set) {
-        cudaFuncSetAttribute(conv3d_umma_kernel<ACT, F16, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
+        cudaFuncSetAttribute(conv3d_umma_kernel<ACT, F16, LEAN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP);
         // one-off query launch (same kernel, same dynamic-smem attribute; the base does not depend on the size)
         uint32_t* dev = nullptr;
         if (cudaMalloc(&dev, sizeof(uint32_t)) != cudaSuccess) return STB_E_DRIVER;
@@ -609,7 +663,7 @@ int launch_one_impl(unsigned grid, size_t smem, cudaStream_t st, const CUtensorM
         memset(&q, 0, sizeof(q));
         q.ntiles = -1;
         q.out = dev;
-        conv3d_umma_kernel<ACT, F16, LEAN><<<1, UMMA_THREADS, 4096, st>>>(tx, tw, q);
+        conv3d_umma_kernel<ACT, F16, LEAN, SPLIT><<<1, UMMA_THREADS, 4096, st>>>(tx, tw, q);
         cudaError_t e = cudaMemcpyAsync(&smem_base, dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         cudaFree(dev);
@@ -628,39 +682,41 @@ int launch_one_impl(unsigned grid, size_t smem, cudaStream_t st, const CUtensorM
     }
     for (int c = 0; c < a.nclass; ++c) a.iss[a.cls[c].tap_begin].dcol |= 1u << 31;      // overwrite instead of accumulate
     a.desc_hi = (((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29);
-    conv3d_umma_kernel<ACT, F16, LEAN><<<grid, UMMA_THREADS, smem, st>>>(tx, tw, a);
+    conv3d_umma_kernel<ACT, F16, LEAN, SPLIT><<<grid, UMMA_THREADS, smem, st>>>(tx, tw, a);
     STB_CHECK_LAUNCH();
     return STB_OK;
 }
 
 bool g_trace_armed = false;      // host mirror of g_umma_trace != nullptr (stb_conv3d_umma_set_trace)
 
-template <int ACT, bool F16>
+template <int ACT, bool F16, bool SPLIT>
 int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& tw, UArgs& a) {
-    // opt-in (STB_UMMA_CLS1=1) until confirmed on hardware: own instantiation for the single-channel classifiers
-    static const bool cls1 = getenv("STB_UMMA_CLS1") != nullptr && atoi(getenv("STB_UMMA_CLS1")) != 0;
+    // own instantiation for the single-channel classifiers (STB_UMMA_CLS1=0 falls back to the generic epilogue)
+    static const bool cls1 = getenv("STB_UMMA_CLS1") == nullptr || atoi(getenv("STB_UMMA_CLS1")) != 0;
     if constexpr (ACT == STB_ACT_NONE) {
         if (cls1 && !a.debug && !g_trace_armed && !a.partial && a.out_fp32 && a.Cn_valid == 1 && !a.residual &&
             a.cblocks == 3 && a.merge == 3 && a.Cn <= 32)
-            return launch_one_impl<ACT, F16, 4>(grid, smem, st, tx, tw, a);
+            return launch_one_impl<ACT, F16, 4, SPLIT>(grid, smem, st, tx, tw, a);
     }
     const bool lean = !a.debug && !g_trace_armed && !a.partial && !a.out_fp32 && (a.Cn_valid & 31) == 0;
-    // opt-in (STB_UMMA_T2PAIR=1) until confirmed on hardware: merged transposed conv with w-paired stores (LEAN 5)
-    static const bool t2pair = getenv("STB_UMMA_T2PAIR") != nullptr && atoi(getenv("STB_UMMA_T2PAIR")) != 0;
+    // merged transposed conv with w-paired stores (LEAN 5; STB_UMMA_T2PAIR=0 falls back to LEAN 3)
+    static const bool t2pair = getenv("STB_UMMA_T2PAIR") == nullptr || atoi(getenv("STB_UMMA_T2PAIR")) != 0;
     if constexpr (ACT == STB_ACT_RELU) {
         if (t2pair && lean && a.cblocks == 8 && a.merge == 1 && a.Cn == 32 && a.shift)
-            return launch_one_impl<ACT, F16, 5>(grid, smem, st, tx, tw, a);
+            return launch_one_impl<ACT, F16, 5, SPLIT>(grid, smem, st, tx, tw, a);
     }
-    if (lean && a.cblocks == 8 && a.merge == 1) return launch_one_impl<ACT, F16, 3>(grid, smem, st, tx, tw, a);
-    if (lean && a.cblocks == 3 && a.merge == 3) return launch_one_impl<ACT, F16, 2>(grid, smem, st, tx, tw, a);
-    if (lean && a.cblocks == 1 && a.merge == 1) return launch_one_impl<ACT, F16, 1>(grid, smem, st, tx, tw, a);
-    return launch_one_impl<ACT, F16, 0>(grid, smem, st, tx, tw, a);
+    if (lean && a.cblocks == 8 && a.merge == 1) return launch_one_impl<ACT, F16, 3, SPLIT>(grid, smem, st, tx, tw, a);
+    if (lean && a.cblocks == 3 && a.merge == 3) return launch_one_impl<ACT, F16, 2, SPLIT>(grid, smem, st, tx, tw, a);
+    if (lean && a.cblocks == 1 && a.merge == 1) return launch_one_impl<ACT, F16, 1, SPLIT>(grid, smem, st, tx, tw, a);
+    return launch_one_impl<ACT, F16, 0, SPLIT>(grid, smem, st, tx, tw, a);
 }
 
-int launch_umma(int act, int f16, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx,
+int launch_umma(int act, int f16, int split, unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& tx,
                 const CUtensorMap& tw, UArgs& a) {
-#define STB_LAUNCH_ACT(A)                                                         \
-    case A: return f16 ? launch_one<A, true>(grid, smem, st, tx, tw, a) : launch_one<A, false>(grid, smem, st, tx, tw, a);
+#define STB_LAUNCH_ACT(A)                                                                          \
+    case A:                                                                                        \
+        if (split) return launch_one<A, true, true>(grid, smem, st, tx, tw, a);                    \
+        return f16 ? launch_one<A, true, false>(grid, smem, st, tx, tw, a) : launch_one<A, false, false>(grid, smem, st, tx, tw, a);
     switch (act) {
         STB_LAUNCH_ACT(STB_ACT_NONE)
         STB_LAUNCH_ACT(STB_ACT_RELU)
@@ -697,6 +753,10 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     if (Cin % KC) return STB_E_UNSUPPORTED;
     if (in_stride < 1 || in_stride > 2 || out_stride < 1 || out_stride > 2) return STB_E_UNSUPPORTED;
     if (in_stride == 2 && out_stride != 1) return STB_E_UNSUPPORTED;
+    // flags bit6: operand-split fp16 ("fp16x2").  x, wt, residual and a 16-bit out hold fp16 (hi, lo) pairs interleaved per
+    // 16 channels; Cin / KC count STORAGE elements (2 per logical channel), Cout_total / Cout_valid logical channels.
+    const int split = (flags >> 6) & 1;
+    if (split && (!f16 || (KC != 32 && KC != 64) || (Cout_total % 16 && !out_fp32))) return STB_E_UNSUPPORTED;
     const int kdepth = (flags & 32) ? Cin / KC : 0; // flags bit5: K-chunks along a pseudo-depth axis, accumulated in TMEM (2-D convs)
     if (kdepth && (!(flags & 16) || in_stride != 1 || out_stride != 1)) return STB_E_UNSUPPORTED;
     const int nk = kdepth ? 1 : Cin / KC;          // K-split passes
@@ -921,7 +981,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
                         "TH=%d TW=%d nM=%d R=%d window=%d plane=%uB weights=%uB smem=%zuB dchunk=%d items=%d grid=%u\n",
                         Cin, KC, kp, nk, cn, Cpad, ntaps, a.ngroups, a.cblocks, in_stride, out_stride, a.TH, a.TW, a.nM, a.R,
                         window, a.plane_bytes, a.w_bytes_total, smem, a.dchunk, a.ntiles, grid);
-            const int rc = launch_umma(a.act, f16, grid, smem, (cudaStream_t)stream, tm_x, tm_w, a);
+            const int rc = launch_umma(a.act, f16, split, grid, smem, (cudaStream_t)stream, tm_x, tm_w, a);
             if (rc != STB_OK) return rc;
         }
     }

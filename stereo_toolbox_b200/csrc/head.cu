@@ -149,7 +149,7 @@ extern "C" int stb_upsample_softargmin_f32(const float* cost, float* disp, int B
         cudaFuncSetAttribute(upsample_softargmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(stb_ceil_div(outW, HEAD_THREADS), outH, B);
     // opt-in until it has been confirmed bit-identical on hardware (tests/test_lowp_model_gpu.py::test_head_x4_*)
-    static const bool use_x4 = getenv("STB_HEAD_X4") != nullptr && atoi(getenv("STB_HEAD_X4")) != 0;
+    static const bool use_x4 = getenv("STB_HEAD_X4") == nullptr || atoi(getenv("STB_HEAD_X4")) != 0;     // 0 = generic kernel
     if (use_x4 && !align_corners && outD == 4 * D && D >= 2) {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(upsample_softargmin_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -25,6 +25,8 @@ __device__ __forceinline__ float ld16(uint16_t w, int f16) {
     return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&w));
 }
 
+__device__ __forceinline__ int vsplit_idx(int c) { return ((c >> 4) << 5) + (c & 15); }   // storage index of channel c in a split row
+
 constexpr int VT = 256;      // threads
 constexpr int VW = 32;       // w positions per CTA
 
@@ -177,7 +179,9 @@ __device__ __forceinline__ void unpack8(const uint4& q, int f16, float (&v)[8]) 
     }
 }
 
-template <int CPG, bool CACHE_L, bool CLSRC>
+// SPLIT: the volume (and, with CLSRC, the sources) is operand-split fp16 -- fp16 hi + fp16 lo per value, interleaved per 16
+// channels (conv3d_umma.cu) -- so a 16-channel pass writes 64 contiguous bytes per voxel [hi 0..15 | lo 0..15].
+template <int CPG, bool CACHE_L, bool CLSRC, bool SPLIT>
 __global__ void __launch_bounds__(256, 2)
 volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, const float* __restrict__ cl,
                   const float* __restrict__ cr, uint16_t* __restrict__ vol, int Cg, int G, int Cc, int H, int W,
@@ -187,7 +191,8 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
     constexpr int NR = 16 * CPG;
     float* Ls = sm;                                   // [NR][32]
     float* Rs = sm + NR * V2_TW;                      // [NR][RP]   x <-> ww = w0 - D4 + x
-    uint32_t* Os = reinterpret_cast<uint32_t*>(Rs + (size_t)NR * RP);   // [V2_DP][32][9] packed channel pairs
+    constexpr int OP = SPLIT ? 17 : 9;                // words per voxel in the output tile (+1 pad)
+    uint32_t* Os = reinterpret_cast<uint32_t*>(Rs + (size_t)NR * RP);   // [V2_DP][32][OP] packed channel pairs (SPLIT: 8 hi words, 8 lo words)
     const int w0 = blockIdx.x * V2_TW, h = blockIdx.y, b = blockIdx.z;
     const size_t plane = (size_t)H * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -208,12 +213,13 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
             static_assert(!CLSRC || CPG == 8, "channels-last sources: 8 channels per group");
             const int span = V2_TW + RP, total = 16 * span;
             for (int i0 = threadIdx.x; i0 < total; i0 += 256 * 4) {
-                uint4 q[4];
+                uint4 q[4], ql[SPLIT ? 4 : 1];
                 int kind_[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int i = i0 + u * 256;
                     q[u] = make_uint4(0, 0, 0, 0);
+                    if (SPLIT) ql[SPLIT ? u : 0] = make_uint4(0, 0, 0, 0);
                     kind_[u] = -1;
                     if (i >= total) continue;
                     const int ol = i / span, x = i - ol * span, o = oc0 + ol;
@@ -228,11 +234,21 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
                             int t = 0;
 #pragma unroll
                             for (int k = 1; k < 4; ++k) t = (k < cs.n && ch0 >= cs.c0[k]) ? k : t;
+                            if (SPLIT) {
+                                const uint16_t* src = cs.f[t] + vox * (2 * cs.c[t]) + vsplit_idx(ch0 - cs.c0[t]);
+                                q[u] = __ldg(reinterpret_cast<const uint4*>(src));
+                                ql[SPLIT ? u : 0] = __ldg(reinterpret_cast<const uint4*>(src + 16));
+                            } else
                             q[u] = __ldg(reinterpret_cast<const uint4*>(cs.f[t] + vox * cs.c[t] + (ch0 - cs.c0[t])));
                         }
                     } else if (o < G + Cc ? isL : (o < G + 2 * Cc && !isL)) {
                         kind_[u] = 1;
-                        if (ok) q[u].x = __ldg(cs.cat + vox * cs.cat_c + (o < G + Cc ? o - G : o - G - Cc));
+                        const int jc = o < G + Cc ? o - G : o - G - Cc;
+                        if (ok && SPLIT) {
+                            const uint16_t* src = cs.cat + vox * cs.cat_c + vsplit_idx(jc);
+                            q[u].x = __ldg(src);
+                            q[u].y = __ldg(src + 16);
+                        } else if (ok) q[u].x = __ldg(cs.cat + vox * cs.cat_c + jc);
                     }
                 }
 #pragma unroll
@@ -246,10 +262,16 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
                     if (kind_[u] == 0) {
                         float v[8];
                         unpack8(q[u], f16, v);
+                        if (SPLIT) {
+                            float vl[8];
+                            unpack8(ql[SPLIT ? u : 0], 1, vl);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) v[c] += vl[c];
+                        }
 #pragma unroll
                         for (int c = 0; c < 8; ++c) dst[c * pitch] = v[c];
                     } else {
-                        dst[0] = ld16((uint16_t)q[u].x, f16);
+                        dst[0] = ld16((uint16_t)q[u].x, f16) + (SPLIT ? ld16((uint16_t)q[u].y, 1) : 0.f);
                     }
                 }
             }
@@ -306,7 +328,7 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
         }
         for (int d0 = 0; d0 < D; d0 += V2_DP) {
             const int e = (d0 >> 2) + el;
-            uint32_t pk[4][4];
+            uint32_t pk[4][4], pl[SPLIT ? 4 : 1][4];
             if (e < E) {
                 float acc[2][4][4];
                 const int x0 = D4 + 4 * (j - e) - 4;
@@ -358,27 +380,48 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
 #pragma unroll
                 for (int dd = 0; dd < 4; ++dd)
 #pragma unroll
-                    for (int ww = 0; ww < 4; ++ww) pk[dd][ww] = pk16(acc[0][dd][ww], acc[1][dd][ww], f16);
+                    for (int ww = 0; ww < 4; ++ww) {
+                        pk[dd][ww] = pk16(acc[0][dd][ww], acc[1][dd][ww], f16);
+                        if (SPLIT) {
+                            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&pk[dd][ww]));
+                            pl[SPLIT ? dd : 0][ww] = pk16(acc[0][dd][ww] - hf.x, acc[1][dd][ww] - hf.y, 1);
+                        }
+                    }
             }
             __syncthreads();          // previous pass's write-out has finished reading Os
             if (e < E) {
 #pragma unroll
                 for (int dd = 0; dd < 4; ++dd)
 #pragma unroll
-                    for (int ww = 0; ww < 4; ++ww) Os[((4 * el + dd) * V2_TW + 4 * j + ww) * 9 + gp] = pk[dd][ww];
+                    for (int ww = 0; ww < 4; ++ww) {
+                        Os[((4 * el + dd) * V2_TW + 4 * j + ww) * OP + gp] = pk[dd][ww];
+                        if (SPLIT) Os[((4 * el + dd) * V2_TW + 4 * j + ww) * OP + 8 + gp] = pl[SPLIT ? dd : 0][ww];
+                    }
             }
             __syncthreads();
             // ---- write-out: 8 words (32 B) per voxel, consecutive lanes -> consecutive words; a thread keeps its
             // (w, word) and walks the 16 depths of the pass with pointer increments
-            {
+            if (SPLIT) {
+                // 16 words (64 B: [hi 0..15 | lo 0..15]) per voxel
+                const int k = threadIdx.x & 15;
+                const size_t dstride = (size_t)H * W * Ct_pad;           // words per depth plane (2 halves per channel)
+                const int nd = min(V2_DP, D - d0);
+                for (int wl = threadIdx.x >> 4; wl < V2_TW; wl += 16) {
+                    if (w0 + wl >= W) continue;
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(vol + ((((size_t)b * D + d0) * H + h) * W + w0 + wl) * (2 * (size_t)Ct_pad) + 2 * oc0) + k;
+                    const uint32_t* src = Os + wl * OP + k;
+#pragma unroll 4
+                    for (int dl = 0; dl < nd; ++dl) dst[dl * dstride] = src[dl * V2_TW * OP];
+                }
+            } else {
                 const int k = threadIdx.x & 7, wl = threadIdx.x >> 3;
                 if (w0 + wl < W) {
                     const size_t dstride = (size_t)H * W * Ct_pad / 2;       // words per depth plane
                     uint32_t* dst = reinterpret_cast<uint32_t*>(vol + ((((size_t)b * D + d0) * H + h) * W + w0 + wl) * Ct_pad + oc0) + k;
-                    const uint32_t* src = Os + wl * 9 + k;
+                    const uint32_t* src = Os + wl * OP + k;
                     const int nd = min(V2_DP, D - d0);
 #pragma unroll 4
-                    for (int dl = 0; dl < nd; ++dl) dst[dl * dstride] = src[dl * V2_TW * 9];
+                    for (int dl = 0; dl < nd; ++dl) dst[dl * dstride] = src[dl * V2_TW * OP];
                 }
             }
         }
@@ -402,7 +445,16 @@ __global__ void ncdhw_to_cl_kernel(const float* __restrict__ src, uint16_t* __re
     for (int i = threadIdx.y; i < 32; i += 8) {
         const size_t sidx = s0 + i;
         const int c = c0 + threadIdx.x;
-        if (sidx < S && c < Cpad) dst[((size_t)b * S + sidx) * Cpad + c] = cv16(tile[threadIdx.x][i], f16);
+        if (sidx < S && c < Cpad) {
+            if (f16 == 2) {                 // operand-split fp16: hi at vsplit_idx(c), lo 16 elements later
+                const float x = tile[threadIdx.x][i];
+                const __half hv = __float2half_rn(x);
+                uint16_t* d = dst + ((size_t)b * S + sidx) * (2 * (size_t)Cpad) + vsplit_idx(c);
+                *reinterpret_cast<__half*>(d) = hv;
+                *reinterpret_cast<__half*>(d + 16) = __float2half_rn(x - __half2float(hv));
+            } else
+            dst[((size_t)b * S + sidx) * Cpad + c] = cv16(tile[threadIdx.x][i], f16);
+        }
     }
 }
 
@@ -415,6 +467,20 @@ __global__ void ncdhw_to_cl_small_kernel(const float* __restrict__ src, uint16_t
         float v[CPAD];
 #pragma unroll
         for (int c = 0; c < CPAD; ++c) v[c] = c < C ? __ldg(src + ((size_t)b * C + c) * S + s) : 0.f;
+        if (f16 == 2) {                     // operand-split fp16 (CPAD == 16): [hi 0..15 | lo 0..15]
+            uint4* o = reinterpret_cast<uint4*>(dst + ((size_t)b * S + s) * (2 * CPAD));
+            float r[CPAD];
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c) { const __half hv = __float2half_rn(v[c]); r[c] = v[c] - __half2float(hv); }
+#pragma unroll
+            for (int i = 0; i < CPAD / 8; ++i) {
+                o[i] = make_uint4(pk16(v[8 * i], v[8 * i + 1], 1), pk16(v[8 * i + 2], v[8 * i + 3], 1),
+                                  pk16(v[8 * i + 4], v[8 * i + 5], 1), pk16(v[8 * i + 6], v[8 * i + 7], 1));
+                o[CPAD / 8 + i] = make_uint4(pk16(r[8 * i], r[8 * i + 1], 1), pk16(r[8 * i + 2], r[8 * i + 3], 1),
+                                             pk16(r[8 * i + 4], r[8 * i + 5], 1), pk16(r[8 * i + 6], r[8 * i + 7], 1));
+            }
+            continue;
+        }
         uint4* o = reinterpret_cast<uint4*>(dst + ((size_t)b * S + s) * CPAD);
 #pragma unroll
         for (int i = 0; i < CPAD / 8; ++i)
@@ -432,7 +498,14 @@ __global__ void cl_to_ncdhw_kernel(const uint16_t* __restrict__ src, float* __re
     for (int i = threadIdx.y; i < 32; i += 8) {
         const size_t sidx = s0 + i;
         const int c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (sidx < S && c < C) ? ld16(src[((size_t)b * S + sidx) * Cpad + c], f16) : 0.f;
+        float v = 0.f;
+        if (sidx < S && c < C) {
+            if (f16 == 2) {
+                const uint16_t* p = src + ((size_t)b * S + sidx) * (2 * (size_t)Cpad) + vsplit_idx(c);
+                v = ld16(p[0], 1) + ld16(p[16], 1);
+            } else v = ld16(src[((size_t)b * S + sidx) * Cpad + c], f16);
+        }
+        tile[i][threadIdx.x] = v;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += 8) {
@@ -469,19 +542,25 @@ extern "C" int stb_volume_cl16(const float* gwc_l, const float* gwc_r, const flo
     // (register-blocked CPG variants measured SLOWER on B200 -- 2.43 vs 1.86 ms at B=8 K-shape: occupancy drops
     //  to 2 CTAs/SM and the kernel is bound by staging latency + 16-byte strided stores, not by LDS)
     (void)cpg;
-    if (Ct_pad % 16 == 0 && W <= 0x7fffffff - 64 && !getenv("STB_VOLUME_V1")) {
+    const bool split = f16 == 2;             // operand-split fp16 volume (f16 = 2): v2 kernel only
+    if (Ct_pad % 16 == 0 && W <= 0x7fffffff - 64 && (split || !getenv("STB_VOLUME_V1"))) {
         const int E = (D + 3) / 4, RP = 4 * E + V2_TW;
         const int cpg2 = G > 0 ? Cg / G : 1;
-        size_t smem2 = (size_t)16 * cpg2 * (V2_TW + RP) * sizeof(float) + (size_t)V2_DP * V2_TW * 9 * sizeof(uint32_t);
+        size_t smem2 = (size_t)16 * cpg2 * (V2_TW + RP) * sizeof(float) + (size_t)V2_DP * V2_TW * (split ? 17 : 9) * sizeof(uint32_t);
         dim3 grid2(stb_ceil_div(W, V2_TW), H, B);
-#define STB_VOL2_LAUNCH(K, CL)                                                                                      \
+#define STB_VOL2_LAUNCH_S(K, CL, S)                                                                                 \
     do {                                                                                                           \
-        cudaFuncSetAttribute(volume_cl2_kernel<K, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
-        volume_cl2_kernel<K, CL, false><<<grid2, 256, smem2, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r,    \
+        cudaFuncSetAttribute(volume_cl2_kernel<K, CL, false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+        volume_cl2_kernel<K, CL, false, S><<<grid2, 256, smem2, (cudaStream_t)stream>>>(gwc_l, gwc_r, cat_l, cat_r, \
                                                                             (uint16_t*)vol, Cg, G, Cc, H, W, D,   \
-                                                                            Ct_pad, mask_left, f16, ClSrc());     \
+                                                                            Ct_pad, mask_left, split ? 1 : f16, ClSrc()); \
         STB_CHECK_LAUNCH();                                                                                        \
         return STB_OK;                                                                                             \
+    } while (0)
+#define STB_VOL2_LAUNCH(K, CL)                                                                                      \
+    do {                                                                                                           \
+        if (split) STB_VOL2_LAUNCH_S(K, CL, true);                                                                 \
+        STB_VOL2_LAUNCH_S(K, CL, false);                                                                           \
     } while (0)
         if (smem2 <= 200 * 1024) {
             if (cpg2 == 1) STB_VOL2_LAUNCH(1, true);
@@ -490,7 +569,9 @@ extern "C" int stb_volume_cl16(const float* gwc_l, const float* gwc_r, const flo
             if (cpg2 == 12) STB_VOL2_LAUNCH(12, false);
         }
 #undef STB_VOL2_LAUNCH
+#undef STB_VOL2_LAUNCH_S
     }
+    if (split) return STB_E_UNSUPPORTED;
     STB_VOL_LAUNCH(0);
 #undef STB_VOL_LAUNCH
     STB_CHECK_LAUNCH();
@@ -522,11 +603,23 @@ extern "C" int stb_volume_cl16_from_cl16(const void* const* feats, const int* fe
     if (Ct_pad < Ct || Ct_pad % 16 || G % 8) return STB_E_UNSUPPORTED;
     if (H > 65535 || B > 65535) return STB_E_BADARG;
     const int E = (D + 3) / 4, RP = 4 * E + V2_TW;
-    const size_t smem2 = (size_t)16 * 8 * (V2_TW + RP) * sizeof(float) + (size_t)V2_DP * V2_TW * 9 * sizeof(uint32_t);
+    const bool split = f16 == 2;             // sources and volume operand-split fp16; feat_ch / cat_c / Ct_pad stay LOGICAL channel counts
+    const size_t smem2 = (size_t)16 * 8 * (V2_TW + RP) * sizeof(float) + (size_t)V2_DP * V2_TW * (split ? 17 : 9) * sizeof(uint32_t);
     if (smem2 > 200 * 1024) return STB_E_SMEM;
-    cudaFuncSetAttribute(volume_cl2_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     dim3 grid2(stb_ceil_div(W, V2_TW), H, B);
-    volume_cl2_kernel<8, true, true><<<grid2, 256, smem2, (cudaStream_t)stream>>>(nullptr, nullptr, nullptr, nullptr, (uint16_t*)vol,
+    if (split) {
+        for (int i = 0; i < nfeat; ++i)
+            if (feat_ch[i] % 16) return STB_E_UNSUPPORTED;
+        if (Cc > 0 && cat_c % 16) return STB_E_UNSUPPORTED;
+        cs.cat_c = 2 * cat_c;                // storage elements per voxel
+        cudaFuncSetAttribute(volume_cl2_kernel<8, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        volume_cl2_kernel<8, true, true, true><<<grid2, 256, smem2, (cudaStream_t)stream>>>(nullptr, nullptr, nullptr, nullptr, (uint16_t*)vol,
+                                                                                          8 * G, G, Cc, H, W, D, Ct_pad, mask_left, 1, cs);
+        STB_CHECK_LAUNCH();
+        return STB_OK;
+    }
+    cudaFuncSetAttribute(volume_cl2_kernel<8, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    volume_cl2_kernel<8, true, true, false><<<grid2, 256, smem2, (cudaStream_t)stream>>>(nullptr, nullptr, nullptr, nullptr, (uint16_t*)vol,
                                                                                 8 * G, G, Cc, H, W, D, Ct_pad, mask_left, f16, cs);
     STB_CHECK_LAUNCH();
     return STB_OK;
@@ -534,6 +627,7 @@ extern "C" int stb_volume_cl16_from_cl16(const void* const* feats, const int* fe
 
 extern "C" int stb_ncdhw_to_cl16(const float* src, void* dst, int f16, int B, int C, long long S, int Cpad, void* stream) {
     if (!src || !dst || B <= 0 || C <= 0 || S <= 0 || Cpad < C) return STB_E_BADARG;
+    if (f16 == 2 && Cpad % 16) return STB_E_UNSUPPORTED;
     if (C <= 8 && Cpad == 16 && B <= 65535) {
         long long gx = (S + 255) / 256;
         if (gx > 148 * 8) gx = 148 * 8;

@@ -17,8 +17,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .aggregation_umma import (BO_MODE, ES_VARIANT, KWMERGE, TORCH_DT, _iarr, from_channels_last, pad_channels,
-                               to_channels_last)
+from .aggregation_umma import (BO_MODE, ES_VARIANT, KWMERGE, SPLIT_FLAG, TORCH_DT, _iarr, from_channels_last, pad_channels,
+                               split_pack, to_channels_last)
 from .ops import ACT, _p, _stream
 
 KWMERGE_2D = os.environ.get("STB_UMMA_KWMERGE2D", "0")
@@ -28,7 +28,8 @@ KDEPTH = os.environ.get("STB_UMMA_KDEPTH", "1") == "1"     # K-chunks accumulate
 class Conv2dPlan:
     """Tap tables + weight tiles of one Conv2d(+BN) for stb_conv3d_umma (dz = 0 everywhere)."""
 
-    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], cin_tensor: int, dtype):
+    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], cin_tensor: int, dtype, split: bool = False):
+        """``cin_tensor``: logical channels of the input tensor.  split: operand-split fp16 storage (aggregation_umma.split_pack)."""
         w = conv.weight.detach().float()
         cout, cin, kh_, kw_ = w.shape
         assert kh_ == kw_ and conv.groups == 1 and conv.bias is None
@@ -45,13 +46,16 @@ class Conv2dPlan:
             scale, self.shift = torch.ones(cout, device=w.device), None
         self.cin, self.cout, self.k, self.stride, self.pad, self.dil = cin, cout, k, stride, pad, dil
         self.in_stride = stride
-        kc = min(cin, 32 if stride == 2 else 64)
-        assert cin % kc == 0 and kc in (16, 32, 64)
-        self.kc, self.nk = kc, cin // kc
+        cin_st = 2 * cin if split else cin                                   # storage elements per pixel
+        kc = min(cin_st, 32 if stride == 2 else 64)
+        assert cin_st % kc == 0 and kc in (16, 32, 64) and not (split and kc == 16)
+        self.kc, self.nk = kc, cin_st // kc
         cpad = (cout + 15) // 16 * 16
         wt = w.permute(2, 3, 0, 1) * scale.view(1, 1, -1, 1)                # [kh,kw,co,ci]
         tiles = torch.zeros(k * k, cpad, cin, device=w.device)
         tiles[:, :cout] = wt.reshape(k * k, cout, cin)
+        if split:
+            tiles = split_pack(tiles)
         self.wt = tiles.view(k * k, cpad, self.nk, kc).permute(0, 2, 1, 3).contiguous().to(dtype)
         self.nwtiles = k * k
         e = [kk * dil - pad for kk in range(k)]
@@ -84,7 +88,8 @@ class Conv2dPlan:
         self.ntaps = len(dz)
         self.c = [_iarr(v) for v in (dz, dh, dw, sub, widx)]
         self.c_tb, self.c_te, self.c_z = _iarr([0]), _iarr([self.ntaps]), _iarr([0])
-        self.flags = BO_MODE | (ES_VARIANT << 1) | (4 if self.merge else 0) | 16 | ((dil & 7) << 8) | (32 if self.kdepth else 0)
+        self.flags = BO_MODE | (ES_VARIANT << 1) | (4 if self.merge else 0) | 16 | ((dil & 7) << 8) | (32 if self.kdepth else 0) \
+            | (SPLIT_FLAG if split else 0)
 
     def out_size(self, n):
         return (n + 2 * self.pad - self.dil * (self.k - 1) - 1) // self.stride + 1
@@ -94,8 +99,11 @@ class UmmaGwcFeatures:
     """Runs features2d.GwcFeatures (GwcNet/gwcnet.py:12-65) on the tensor-core conv kernel."""
 
     def __init__(self, precision: str = "fp16"):
+        self.precision = precision
         self.dtype = TORCH_DT[precision]
-        self.f16 = int(precision == "fp16")
+        self.split = precision == "fp16x2"
+        self.cmul = 2 if self.split else 1
+        self.f16 = int(precision in ("fp16", "fp16x2"))
         self._plans: Dict[int, tuple] = {}
         self._ws = None
 
@@ -105,25 +113,29 @@ class UmmaGwcFeatures:
                                       bn.running_var._version, bn.running_mean.data_ptr()))
         hit = self._plans.get(id(conv))
         if hit is None or hit[0] != ver:
-            hit = (ver, Conv2dPlan(conv, bn, cin_tensor, self.dtype))
+            hit = (ver, Conv2dPlan(conv, bn, cin_tensor, self.dtype, self.split))
             self._plans[id(conv)] = hit
         return hit[1]
 
     def conv(self, conv, bn, x, act="none", residual=None):
         """x [1, N, H, W, C] channels-last 16-bit (N images as depth) -> [1, N, Ho, Wo, Cout]."""
-        _, N, H, W, C = x.shape
+        _, N, H, W, Cst = x.shape
+        C = Cst // self.cmul
         p = self._plan(conv, bn, C)
         Ho, Wo = p.out_size(H), p.out_size(W)
-        out = torch.empty(1, N, Ho, Wo, p.cout, device=x.device, dtype=self.dtype)
+        cout_t = (p.cout + 15) // 16 * 16 if self.split else p.cout          # split rows are whole 16-channel (hi, lo) blocks
+        alloc = torch.zeros if cout_t != p.cout else torch.empty
+        out = alloc(1, N, Ho, Wo, cout_t * self.cmul, device=x.device, dtype=self.dtype)
         ws = None
         if p.nk > 1 and not p.kdepth:
-            if self._ws is None or self._ws.numel() < out.numel():
-                self._ws = torch.empty(out.numel(), device=x.device, dtype=torch.float32)
+            need = N * Ho * Wo * cout_t
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, device=x.device, dtype=torch.float32)
             ws = self._ws
         if residual is not None:
             assert residual.shape == out.shape and residual.dtype == self.dtype and residual.is_contiguous()
         _lib.call("stb_conv3d_umma", _p(x), _p(p.wt), _p(p.shift), _p(residual), _p(out), _p(ws), self.f16,
-                  1, C, p.kc, N, H, W, p.cout, p.cout, N, Ho, Wo, p.ntaps, p.c[0], p.c[1], p.c[2], p.c[3], p.c[4],
+                  1, Cst, p.kc, N, H, W, cout_t, p.cout, N, Ho, Wo, p.ntaps, p.c[0], p.c[1], p.c[2], p.c[3], p.c[4],
                   None, None, p.nwtiles, 1, p.c_tb, p.c_te, p.c_z, p.c_z, p.c_z, p.in_stride, 1, N, Ho, Wo,
                   p.in_off, p.in_off, ACT[act], 0, p.flags, 0, _stream())
         return out
@@ -151,7 +163,7 @@ class UmmaGwcFeatures:
         B = left.shape[0]
         x = torch.cat((left, right), 0)                                   # [2B,3,H,W]
         H, W = x.shape[2:]
-        x = to_channels_last(x.view(2 * B, 3, H, W), 16, self.dtype).view(1, 2 * B, H, W, 16)
+        x = to_channels_last(x.view(2 * B, 3, H, W), 16, self.dtype, split=self.split).view(1, 2 * B, H, W, 16 * self.cmul)
         fc = fe.firstconv
         x = self._convbn(fc[0], x, "relu")
         x = self._convbn(fc[2], x, "relu")
@@ -176,21 +188,21 @@ class UmmaGwcFeatures:
             if concat_head is not None:
                 y = self._convbn_multi(concat_head[0], (l2, l3, l4), "relu")
                 cat = self.conv(concat_head[1], None, y)
-                cc = cat.shape[-1]
-                if cc % 8:                                                     # the builder reads whole 16-bit elements
+                cc = concat_head[1].out_channels
+                if cc % 8 and not self.split:                                  # the builder reads whole 16-bit elements
                     pad = torch.zeros(cat.shape[:-1] + (8 - cc % 8,), device=cat.device, dtype=cat.dtype)
                     cat = torch.cat((cat, pad), dim=-1)
             cl = {"feats": [l2, l3, l4], "cat": cat, "B": B, "cc": cc}
             return {"_cl": cl}, {"_cl": cl}
         gwc = torch.cat((l2, l3, l4), dim=-1)                             # [1,2B,h,w,320]
         _, N, h, w, _ = gwc.shape
-        gwc_f = from_channels_last(gwc.view(N, h, w, 320))                # [2B,320,h,w] fp32
+        gwc_f = from_channels_last(gwc.view(N, h, w, 320 * self.cmul), split=self.split)                # [2B,320,h,w] fp32
         outs = ({"gwc_feature": gwc_f[:B]}, {"gwc_feature": gwc_f[B:]})
         if concat_head is None and fe.concat_feature:
             concat_head = (fe.lastconv[0], fe.lastconv[2])
         if concat_head is not None:
             y = self._convbn(concat_head[0], gwc, "relu")
             y = self.conv(concat_head[1], None, y)
-            cat_f = from_channels_last(y.view(N, h, w, y.shape[-1]))
+            cat_f = from_channels_last(y.view(N, h, w, y.shape[-1]), concat_head[1].out_channels, split=self.split)
             outs[0]["concat_feature"], outs[1]["concat_feature"] = cat_f[:B], cat_f[B:]
         return outs

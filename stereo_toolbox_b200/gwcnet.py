@@ -116,7 +116,7 @@ class GwcNet(nn.Module):
         try:
             if mode == "umma":
                 from .features_umma import UmmaGwcFeatures
-                if getattr(self, "_fe_umma", None) is None or self._fe_umma.dtype != self._be.dtype:
+                if getattr(self, "_fe_umma", None) is None or self._fe_umma.precision != self._be.name:
                     self._fe_umma = UmmaGwcFeatures(self._be.name)
                 with self._be.prof.bracket("features2d_umma", 0.0, 0.0):
                     head = (self.concatconv[0], self.concatconv[2]) if hasattr(self, "concatconv") else None

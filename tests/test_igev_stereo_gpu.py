@@ -9,8 +9,7 @@ import torch
 
 from conftest import load_golden, golden_state
 
-UNCONFIRMED = ("written after the round-1 GPU budget was spent: composes kernels that are green at these shapes, host code pinned on CPU, but not yet run on hardware -- remove this mark after the first GPU trip of the next round (tools/trip_r2.sh)")
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), pytest.mark.xfail(strict=False, reason=UNCONFIRMED)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 def _run(precision, **fwd):
@@ -61,10 +60,11 @@ def test_igev_stereo_fp16_runs():
     print(f"IGEVStereo fp16 stage, whole-model EPE vs reference: {(out - g['disp']).abs().mean().item():.4f} px")
 
 
-def test_igev_stereo_cuda_graph_iteration_is_bit_identical():
-    """model.cuda_graph = True replays one captured GRU iteration (geometry-lookup kernel + update block): same kernels in
-    the same order as the eager loop, so the output must be bit-identical -- also on the second call, which only refreshes
-    the graph's static inputs."""
+def test_igev_stereo_cuda_graph_iteration_matches_eager():
+    """model.cuda_graph = True replays one captured GRU iteration (geometry-lookup kernel + update block) -- also on the
+    second call, which only refreshes the graph's static inputs.  Our lookup kernel is deterministic, but cuDNN may pick a
+    different algorithm for the update block's small convolutions under stream capture (it did on the round-2 hardware run:
+    not bit-identical), so the bar is the parity bar, 1e-3 px max, not bit identity."""
     import stereo_toolbox_b200 as S
     from stereo_toolbox_b200.synth import synth_pair
     sd, meta = golden_state("igev_stereo")
@@ -84,5 +84,6 @@ def test_igev_stereo_cuda_graph_iteration_is_bit_identical():
             graphed2 = net(left2.cuda(), right2.cuda(), iters=4)
     finally:
         torch.backends.cudnn.allow_tf32 = prev
-    assert torch.equal(eager, graphed)
-    assert torch.equal(eager2, graphed2)
+    d1, d2 = (eager - graphed).abs().max().item(), (eager2 - graphed2).abs().max().item()
+    print(f"IGEV eager vs graph replay: max |diff| {d1:.3e} / {d2:.3e} px")
+    assert d1 < 1e-3 and d2 < 1e-3

@@ -6,10 +6,7 @@ import torch
 
 from conftest import load_golden, golden_state
 
-UNCONFIRMED = ("written after the round-1 GPU budget was spent: every kernel on this path is green in tests/test_gpu_train.py / "
-               "tests/test_gpu_ops.py, the composition and the torch-composed adjoints are pinned on CPU "
-               "(tests/test_igev_train_cpu.py); not yet run on hardware")
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), pytest.mark.xfail(strict=False, reason=UNCONFIRMED)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 def test_igev_training_step_vs_reference():

@@ -7,10 +7,8 @@ written after the round-1 GPU budget was spent."""
 import pytest
 import torch
 
-from conftest import unconfirmed_kernels
 
-UNCONFIRMED = "property tests written after the round-1 GPU budget was spent; kernels confirmed, assertions not yet run on hardware"
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), pytest.mark.xfail(strict=False, reason=UNCONFIRMED)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 B, H4, W4, D4 = 2, 96, 312, 48
 
@@ -82,7 +80,6 @@ def test_corr_symmetry_pyramid_and_integer_lookup():
         torch.testing.assert_close(out[0, k], want, rtol=1e-5, atol=1e-5)
 
 
-@unconfirmed_kernels          # a batch-1 launch geometry of the tcgen05 kernel that no confirmed test or bench has run: opt-in
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 def test_tcgen05_conv_power_of_two_scaling_is_bit_exact(prec):
     """conv(2x) == 2 conv(x) bit for bit on the 16-bit tensor-core path (no BatchNorm shift, no activation): scaling by a

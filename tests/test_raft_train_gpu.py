@@ -6,9 +6,7 @@ import torch
 from conftest import load_golden, golden_state
 from oracle import ref_ops as R
 
-UNCONFIRMED = ("written after the round-1 GPU budget was spent: forward = kernels that are green in tests/test_gpu_ops.py, "
-               "adjoints = torch library calls pinned on CPU (tests/test_raft_train_cpu.py); not yet run on hardware")
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), pytest.mark.xfail(strict=False, reason=UNCONFIRMED)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 def test_corrblock_adjoints_match_autograd_of_the_oracle():

@@ -7,11 +7,10 @@ import sys
 import pytest
 import torch
 
-from conftest import load_golden, golden_state, unconfirmed_kernels
+from conftest import load_golden, golden_state
 from oracle import ref_ops as R
 
-UNCONFIRMED = "kernel written after the round-1 GPU budget was spent; pinned on CPU through its oracle only"
-pytestmark = [pytest.mark.gpu, unconfirmed_kernels, pytest.mark.timeout(600), pytest.mark.xfail(strict=False, reason=UNCONFIRMED)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 def test_sampled_volume_golden_and_oracle():

@@ -7,12 +7,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from conftest import GOLDEN, load_golden, load_meta, unconfirmed_kernels
+from conftest import GOLDEN, load_golden, load_meta
 
-UNCONFIRMED = ("written after the round-1 GPU budget was spent: the host logic is pinned on CPU (tests/test_train16_cpu.py) "
-               "and both primitives are kernels the inference / fp32 training paths already exercise, but this composition "
-               "has not run on hardware yet -- remove this mark after the first GPU trip of the next round")
-pytestmark = [pytest.mark.gpu, unconfirmed_kernels, pytest.mark.timeout(900), pytest.mark.xfail(strict=False, reason=UNCONFIRMED)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 @pytest.mark.parametrize("k,s,p,tr,op,dims", [(3, 1, 1, False, 0, (8, 16, 32)), (1, 1, 0, False, 0, (8, 16, 32)),

@@ -7,10 +7,10 @@
 PARTS=${1:-abc}
 mkdir -p gpurun_out
 if [[ $PARTS == *a* ]]; then
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?"
+timeout 1500 python -m pytest tests -m gpu -x -q -rxXs > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?"
 tail -5 gpurun_out/r2_pytest.log
 export STB200_RUN_UNCONFIRMED=1      # from here on also run the tests that launch not-yet-confirmed kernels (skipped by default)
-timeout 600 python -m pytest tests/test_igev_stereo_gpu.py tests/test_lowp_model_gpu.py tests/test_raft_train_gpu.py tests/test_igev_train_gpu.py tests/test_cascade_train_gpu.py tests/test_sampled_volume_gpu.py tests/test_properties_fullsize_gpu.py -m gpu -q -s --runxfail > gpurun_out/r2_igev.log 2>&1; echo "igev rc=$?"
+timeout 600 python -m pytest tests/test_igev_stereo_gpu.py tests/test_lowp_model_gpu.py tests/test_raft_train_gpu.py tests/test_igev_train_gpu.py tests/test_cascade_train_gpu.py tests/test_sampled_volume_gpu.py tests/test_properties_fullsize_gpu.py -m gpu -q -s --runxfail -rA > gpurun_out/r2_igev.log 2>&1; echo "igev rc=$?"
 grep -i "EPE\|passed\|failed\|storage model" gpurun_out/r2_igev.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; echo "bench rc=$?"
 cut -c1-400 gpurun_out/r2_bench.json
