@@ -67,11 +67,11 @@ def attention_weighted_volume(att: torch.Tensor, concat_volume: torch.Tensor) ->
 
 
 # --------------------------------------------------------------------------- head
-def _linear_taps(out_size: int, in_size: int, align_corners: bool):
+def _linear_taps(out_size: int, in_size: int, align_corners: bool, device=None):
     """Source index pair and weight of 1-D linear resampling as ATen's upsample_*linear does it
     (the op behind F.upsample(mode='trilinear'), GwcNet/gwcnet.py:220, PSMNet/stackhourglass.py:150;
     align_corners=True at CFNet/cfnet.py:605-613, PCWNet/pcwnet.py:486)."""
-    dst = torch.arange(out_size, dtype=torch.float64)
+    dst = torch.arange(out_size, dtype=torch.float64, device=device)
     if align_corners:
         scale = (in_size - 1) / (out_size - 1) if out_size > 1 else 0.0
         src = dst * scale
@@ -87,12 +87,12 @@ def _linear_taps(out_size: int, in_size: int, align_corners: bool):
 def trilinear_upsample(cost: torch.Tensor, out_d: int, out_h: int, out_w: int, align_corners: bool = False) -> torch.Tensor:
     """[B,D,H,W] -> [B,out_d,out_h,out_w], separable linear interpolation in W, then H, then D."""
     B, D, H, W = cost.shape
-    i0, i1, t = _linear_taps(out_w, W, align_corners)
+    i0, i1, t = _linear_taps(out_w, W, align_corners, cost.device)
     x = cost[..., i0] * (1 - t) + cost[..., i1] * t
-    i0, i1, t = _linear_taps(out_h, H, align_corners)
+    i0, i1, t = _linear_taps(out_h, H, align_corners, cost.device)
     t = t.view(-1, 1)
     x = x[:, :, i0] * (1 - t) + x[:, :, i1] * t
-    i0, i1, t = _linear_taps(out_d, D, align_corners)
+    i0, i1, t = _linear_taps(out_d, D, align_corners, cost.device)
     t = t.view(-1, 1, 1)
     x = x[:, i0] * (1 - t) + x[:, i1] * t
     return x
@@ -102,7 +102,7 @@ def disparity_regression(prob: torch.Tensor, maxdisp: int, keepdim: bool = False
     """GwcNet/submodule.py:23-27 (keepdim=False); PSMNet/submodule.py:46-54 and
     IGEVStereo/submodule.py:221-225 (keepdim=True)."""
     assert prob.dim() == 4
-    values = torch.arange(maxdisp, dtype=prob.dtype).view(1, maxdisp, 1, 1)
+    values = torch.arange(maxdisp, dtype=prob.dtype, device=prob.device).view(1, maxdisp, 1, 1)
     return (prob * values).sum(1, keepdim=keepdim)
 
 
@@ -144,10 +144,10 @@ def activation(x: torch.Tensor, act: str) -> torch.Tensor:
     raise ValueError(act)
 
 
-def fold_bn(bn: Optional[dict], c_out: int, eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
+def fold_bn(bn: Optional[dict], c_out: int, eps: float = 1e-5, device=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Eval-mode BatchNorm3d as y = x*scale + shift (PSMNet/submodule.py:16-19)."""
     if bn is None:
-        return torch.ones(c_out), torch.zeros(c_out)
+        return torch.ones(c_out, device=device), torch.zeros(c_out, device=device)
     scale = bn["weight"] / torch.sqrt(bn["running_var"] + eps)
     shift = bn["bias"] - bn["running_mean"] * scale
     return scale, shift
@@ -164,7 +164,7 @@ def conv3d_bn_act(x, weight, bn=None, stride=1, padding=1, act="none", residual=
     else:
         y = F.conv3d(x, weight, stride=stride, padding=padding)
         c_out = weight.shape[0]
-    scale, shift = fold_bn(bn, c_out)
+    scale, shift = fold_bn(bn, c_out, device=y.device)
     y = y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
     if residual is not None:
         y = y + residual

@@ -42,6 +42,18 @@ def split_pack(w: torch.Tensor) -> torch.Tensor:
     return torch.stack((hi.reshape(*lead, c // 16, 16), lo.reshape(*lead, c // 16, 16)), dim=-2).reshape(*lead, 2 * c)
 
 
+def split_weight_exponent(w: torch.Tensor) -> int:
+    """Power of two s the (BN-folded) weights of a layer are multiplied by before split_pack: brings max|w| to [2^13, 2^14),
+    so that the lo halves (|lo| <= 2^-12 |w|) of all but the smallest weights are NORMAL fp16 numbers (an fp16 subnormal lo
+    carries an absolute error of 2^-25, i.e. only ~2^-20 relative to a typical 0.05-sized weight).  The kernel multiplies its
+    fp32 accumulators by 2^-s (flags bits 16..22 of stb_conv3d_umma)."""
+    m = float(w.abs().max())
+    if not (m > 0.0) or m != m or m == float("inf"):
+        return 0
+    import math
+    return max(0, min(100, 13 - math.floor(math.log2(m))))
+
+
 def split_unpack(x: torch.Tensor) -> torch.Tensor:
     """Inverse of split_pack: fp16 [..., 2C] -> fp32 [..., C]."""
     c2 = x.shape[-1]
@@ -157,8 +169,10 @@ class UmmaPlan:
         full = torch.zeros(k * k * k, cpad, cin, device=w.device)
         full[:, :cout] = wt.reshape(k * k * k, cout, cin)
         tiles = full[torch.tensor(tile_src, device=w.device)]
+        self.wexp = 0
         if self.split:
-            tiles = split_pack(tiles)                     # [tile][cpad][2*cin]: (hi, lo) k-slices per 16 input channels
+            self.wexp = split_weight_exponent(tiles)
+            tiles = split_pack(tiles * float(2.0 ** self.wexp))   # [tile][cpad][2*cin]: (hi, lo) k-slices per 16 input channels
         self.wt = tiles.view(len(tile_src), cpad, nk, kc).permute(0, 2, 1, 3).contiguous().to(self.dtype)
         self.nwtiles, self.kc, self.nk, self.in_stride = len(tile_src), kc, nk, in_stride
         if self.nwtiles * 16 * kc * 2 > 150 * 1024 or len(dz) > 64:
@@ -341,7 +355,7 @@ class UmmaBackend:
                           plan.c_tb, plan.c_te, plan.c_od0, plan.c_oh0, plan.c_ow0, plan.in_stride, plan.out_stride,
                           nsteps, nh, nw, plan.in_off, plan.in_off, ACT[act], int(out_fp32),
                           BO_MODE | (ES_VARIANT << 1) | (4 if plan.merge else 0) | (8 if plan.deconv_merge else 0)
-                          | (SPLIT_FLAG if self.split else 0),
+                          | ((SPLIT_FLAG | (plan.wexp << 16)) if self.split else 0),
                           self.dchunk, _stream())
             else:
                 assert not self.split

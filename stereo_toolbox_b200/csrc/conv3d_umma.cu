@@ -81,6 +81,9 @@ struct UArgs {
     int debug;                       // timing experiments only (STB_UMMA_DEBUG): 1 = no TMA plane traffic, 2 = epilogue skips its work
     int ntiles;                      // work items (b, depth chunk, h tile, w tile); CTAs are persistent and stride over them
     int ngroups;
+    int nslices;                     // output-channel slices (of Cn) handled inside ONE launch: CTA c takes slice c % nslices
+    float oscale;                    // SPLIT: the packed weights carry a factor 2^s (keeps their lo halves out of the fp16
+                                     // subnormals); accumulators are multiplied by oscale = 2^-s before shift / residual
     UClass cls[MAX_UCLASS];
     UTap taps[MAX_UTAPS];
     UGroup grp[MAX_UTAPS];
@@ -280,6 +283,13 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     uint8_t* sP = sW + ((a.w_bytes_total + 1023) & ~1023u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Output-channel slices inside one launch (weights of Cpad / nslices channels fit in shared memory, not all of them):
+    // CTA c owns slice c % nslices and walks every work item with stride gridDim.x / nslices, so the CTAs of all slices work
+    // on the same tile at about the same time and the input planes are read from HBM once (L2 serves the others).  Before:
+    // one launch per slice (profiles/op_bench_r01.md: 87 launches for 30 layers).
+    const int nsl = a.nslices, slice = (int)blockIdx.x % nsl;
+    const int tile0 = (int)blockIdx.x / nsl, tstride = (int)gridDim.x / nsl;
+    const int cout_off = a.cout_off + slice * a.Cn;
     if (a.ntiles < 0) {                            // base-address query launch (host: smem_base_of)
         if (threadIdx.x == 0) *reinterpret_cast<uint32_t*>(a.out) = smem_u32(smem);
         return;
@@ -313,10 +323,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             mbar_arrive_expect_tx(bar_w, a.w_bytes_total);
             for (int i = 0; i < a.nwtiles; ++i)
                 tma_load_2d(sW + (size_t)i * a.wtile_bytes, &tm_w, bar_w, 0,
-                            (i * a.w_tile_stride + a.w_kc_off) * a.w_rows + a.cout_off);
+                            (i * a.w_tile_stride + a.w_kc_off) * a.w_rows + cout_off);
             int slot = 0;
             uint32_t eph = 1;                      // parity to wait for on plane_empty[slot] (fresh barrier: passes)
-            for (int tile = blockIdx.x; tile < a.ntiles && !(dbg & 1); tile += gridDim.x) {
+            for (int tile = tile0; tile < a.ntiles && !(dbg & 1); tile += tstride) {
                 const UTile u = decode_tile(a, tile);
                 const int ih0 = (u.jh0 + a.in_h_off) * a.in_stride, iw0 = (u.jw0 + a.in_w_off) * a.in_stride;
                 for (int n = 0; n < u.nplanes; ++n) {
@@ -378,7 +388,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     if (++rslot == R) rslot = 0;
                 }
             };
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < a.ntiles; tile += tstride) {
                 const UTile u = decode_tile(a, tile);
                 int step_slot = base_slot;        // ring slot of plane (s*sd + dzmin) for the current step
                 for (int si = 0; si < u.nst; ++si) {
@@ -444,10 +454,11 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const bool out_fp32 = !LEAN && a.out_fp32;
         float sh0[32];                              // folded-BN shift of the first 32 channels stays in registers
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + a.cout_off + i) : 0.f;
+        for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + cout_off + i) : 0.f;
+        const float oscale = SPLIT ? a.oscale : 1.f;
         const int merge = (LEAN == 2 || LEAN == 4) ? 3 : (LEAN ? 1 : a.merge), Cn = a.Cn, nM = a.nM;
         uint32_t ground = 0;                        // accumulator round counter over all items (same order as the issuer)
-        for (int tile = blockIdx.x; active && tile < a.ntiles && !(dbg & 4); tile += gridDim.x) {
+        for (int tile = tile0; active && tile < a.ntiles && !(dbg & 4); tile += tstride) {
           const UTile u = decode_tile(a, tile);
           const int b = u.b, jh0 = u.jh0, jw0 = u.jw0;
           int e_si = 0, e_c = 0;                      // (step, class) of the round, kept incrementally (no division)
@@ -474,7 +485,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const bool valid = (jh_l < a.TH) && (jw_l < a.TW) && (jh < a.nclass_h) && (jw < a.nclass_w) && (od < a.Do);
                 const int oh = jh * 2 + (pb & 1), ow = jw * 2;
                 const bool in0 = valid && oh < a.Ho && ow < a.Wo, in1 = in0 && ow + 1 < a.Wo;
-                const size_t eoff = ((((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow) * ostride_w + a.cout_off;
+                const size_t eoff = ((((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow) * ostride_w + cout_off;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * nM + m) * Cn * 8 + pb * 2 * Cn);
                 uint32_t v0[32], v1[32];
                 __syncwarp();
@@ -490,7 +501,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     if (!ok) return;
                     float f[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + sh0[i];
+                    for (int i = 0; i < 32; ++i) f[i] = SPLIT ? fmaf(__uint_as_float(v[i]), oscale, sh0[i]) : __uint_as_float(v[i]) + sh0[i];
                     if (a.residual) add_residual32<F16, SPLIT>(f, reinterpret_cast<const uint16_t*>(a.residual) + off * K16);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], ACT);
@@ -537,7 +548,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         const int ms1 = a.merge_step;
                         const float r = __uint_as_float(v0) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1), ms1) +
                                         __shfl_down_sync(0xffffffffu, __uint_as_float(v2), 2 * ms1);
-                        if (inb) reinterpret_cast<float*>(a.out)[vox * ostride_w + a.cout_off] = stb_act(r + sh0[0], ACT);
+                        if (inb) reinterpret_cast<float*>(a.out)[vox * ostride_w + cout_off] = stb_act(SPLIT ? fmaf(r, oscale, sh0[0]) : r + sh0[0], ACT);
                         break;                         // Cn = 16: a single column block per item
                     }
                     float f[32];
@@ -574,7 +585,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                     }
-                    const size_t eoff = vox * ostride_w + a.cout_off + c0;
+                    const size_t eoff = vox * ostride_w + cout_off + c0;
                     if (inb && full32) {
                         // ---------------- vector path: 32 complete channels
                         if (partial) {
@@ -585,11 +596,15 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                                 f[i * 4] += pv.x; f[i * 4 + 1] += pv.y; f[i * 4 + 2] += pv.z; f[i * 4 + 3] += pv.w;
                             }
                         }
+                        if constexpr (SPLIT) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) f[i] *= oscale;
+                        }
                         if (c0 == 0) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) f[i] += sh0[i];
                         } else if (a.shift) {
-                            const float4* sp = reinterpret_cast<const float4*>(a.shift + a.cout_off + c0);
+                            const float4* sp = reinterpret_cast<const float4*>(a.shift + cout_off + c0);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float4 sv = __ldg(sp + i);
@@ -615,9 +630,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                             if (i < nch) {
                                 float x = f[i];
                                 if (partial) x += __ldg(partial + eoff + i);
-                                if (a.shift) x += __ldg(a.shift + a.cout_off + c0 + i);
+                                if (SPLIT) x *= oscale;
+                                if (a.shift) x += __ldg(a.shift + cout_off + c0 + i);
                                 // split rows: logical channel -> (hi, lo) slots of its 16-channel block
-                                const size_t e16 = SPLIT ? vox * (2 * ostride_w) + split_idx(a.cout_off + c0 + i) : eoff + i;
+                                const size_t e16 = SPLIT ? vox * (2 * ostride_w) + split_idx(cout_off + c0 + i) : eoff + i;
                                 if (a.residual) {
                                     const uint16_t* rp = reinterpret_cast<const uint16_t*>(a.residual) + e16;
                                     x += SPLIT ? load16(rp, 1) + load16(rp + 16, 1) : load16(rp, f16);
@@ -662,6 +678,7 @@ int launch_one_impl(unsigned grid, size_t smem, cudaStream_t st, const CUtensorM
         UArgs q;
         memset(&q, 0, sizeof(q));
         q.ntiles = -1;
+        q.nslices = 1;
         q.out = dev;
         conv3d_umma_kernel<ACT, F16, LEAN, SPLIT><<<1, UMMA_THREADS, 4096, st>>>(tx, tw, q);
         cudaError_t e = cudaMemcpyAsync(&smem_base, dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
@@ -756,6 +773,9 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     // flags bit6: operand-split fp16 ("fp16x2").  x, wt, residual and a 16-bit out hold fp16 (hi, lo) pairs interleaved per
     // 16 channels; Cin / KC count STORAGE elements (2 per logical channel), Cout_total / Cout_valid logical channels.
     const int split = (flags >> 6) & 1;
+    // flags bits 16..22 (split only): the packed weights were multiplied by 2^s so that their lo halves stay normal fp16
+    // numbers; the epilogue multiplies the accumulators by 2^-s.
+    const float wscale_inv = ldexpf(1.f, -((flags >> 16) & 127));
     if (split && (!f16 || (KC != 32 && KC != 64) || (Cout_total % 16 && !out_fp32))) return STB_E_UNSUPPORTED;
     const int kdepth = (flags & 32) ? Cin / KC : 0; // flags bit5: K-chunks along a pseudo-depth axis, accumulated in TMEM (2-D convs)
     if (kdepth && (!(flags & 16) || in_stride != 1 || out_stride != 1)) return STB_E_UNSUPPORTED;
@@ -900,6 +920,9 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.plane_bytes = (uint32_t)a.nsub * a.chunk_bytes;
     a.tiles_h = stb_ceil_div(nclass_h, a.TH);
     a.tiles_w = stb_ceil_div(nclass_w, a.TW);
+    // all output-channel slices in one launch when they are equal and complete (see the kernel); else one launch per slice
+    static const bool slice_mode = getenv("STB_UMMA_NSLICE") == nullptr || atoi(getenv("STB_UMMA_NSLICE")) != 0;
+    const int ns = (slice_mode && Cpad % Cn == 0 && Cout_valid == Cpad && Cpad / Cn > 1 && Cpad / Cn <= 16) ? Cpad / Cn : 1;
     if (dchunk <= 0) {
         // Depth chunking: CTAs = columns x chunks, one CTA per SM at a time.  Pick the chunk count that best
         // fills whole waves of SMs while keeping the redundant halo planes (window-1 per chunk) small.
@@ -915,8 +938,9 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             const int dch = stb_ceil_div(nsteps, nch);
             if (dch < 4 && nch > 1) break;
             const long long ctas = cols * stb_ceil_div(nsteps, dch);
-            const long long waves = (ctas + num_sms - 1) / num_sms;
-            const double eff = (double)ctas / (double)(waves * num_sms) * (double)dch / (double)(dch + window - 1);
+            const int sms = num_sms / ns;                      // SMs that work on one output-channel slice
+            const long long waves = (ctas + sms - 1) / sms;
+            const double eff = (double)ctas / (double)(waves * sms) * (double)dch / (double)(dch + window - 1);
             if (eff > best + 1e-3) { best = eff; dchunk = dch; }
         }
     }
@@ -948,7 +972,6 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
     }
-    const unsigned grid = (unsigned)(ncta < sm_count ? ncta : sm_count);     // persistent: one CTA per SM
     static const bool verbose = getenv("STB_UMMA_VERBOSE") != nullptr;
     static const int debug = getenv("STB_UMMA_DEBUG") ? atoi(getenv("STB_UMMA_DEBUG")) : 0;
     a.debug = debug;
@@ -962,10 +985,12 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         a.shift = last ? shift : nullptr;
         a.residual = last ? residual : nullptr;
         a.act = last ? act : STB_ACT_NONE;
-        for (int co = 0; co < Cpad; co += Cn) {
+        a.oscale = (split && last) ? wscale_inv : 1.f;
+        for (int co = 0; co < Cpad; co += Cn * ns) {
             const int cn = (Cpad - co) < Cn ? (Cpad - co) : Cn;
             a.Cn = cn;
             a.cout_off = co;
+            a.nslices = ns;
             a.Cn_valid = (Cout_valid - co) < cn ? (Cout_valid - co) : cn;
             if (a.Cn_valid <= 0) break;
             a.wtile_bytes = (uint32_t)(cn * a.ROWB);
@@ -976,10 +1001,12 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             if (!umma_host::make_tmap(&tm_w, cudt, 2, const_cast<void*>(wt), dims, str, box, cusw)) return STB_E_DRIVER;
             size_t smem = 3072 + a.tab_bytes + (((size_t)a.w_bytes_total + 1023) & ~(size_t)1023) + (size_t)a.R * a.plane_bytes + 1024;
             if (smem > SMEM_CAP) return STB_E_SMEM;
+            const long long want = ncta * ns;
+            const unsigned grid = (unsigned)(want < sm_count ? want : (sm_count / ns) * ns);     // persistent: one CTA per SM
             if (verbose)
-                fprintf(stderr, "[stb_conv3d_umma] Cin=%d KC=%d kpass=%d/%d Cn=%d/%d taps=%d groups=%d cblocks=%d in_stride=%d out_stride=%d "
+                fprintf(stderr, "[stb_conv3d_umma] Cin=%d KC=%d kpass=%d/%d Cn=%d/%d x%d taps=%d groups=%d cblocks=%d in_stride=%d out_stride=%d "
                         "TH=%d TW=%d nM=%d R=%d window=%d plane=%uB weights=%uB smem=%zuB dchunk=%d items=%d grid=%u\n",
-                        Cin, KC, kp, nk, cn, Cpad, ntaps, a.ngroups, a.cblocks, in_stride, out_stride, a.TH, a.TW, a.nM, a.R,
+                        Cin, KC, kp, nk, cn, Cpad, ns, ntaps, a.ngroups, a.cblocks, in_stride, out_stride, a.TH, a.TW, a.nM, a.R,
                         window, a.plane_bytes, a.w_bytes_total, smem, a.dchunk, a.ntiles, grid);
             const int rc = launch_umma(a.act, f16, split, grid, smem, (cudaStream_t)stream, tm_x, tm_w, a);
             if (rc != STB_OK) return rc;

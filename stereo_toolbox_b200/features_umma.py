@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from .aggregation_umma import (BO_MODE, ES_VARIANT, KWMERGE, SPLIT_FLAG, TORCH_DT, _iarr, from_channels_last, pad_channels,
-                               split_pack, to_channels_last)
+                               split_pack, split_weight_exponent, to_channels_last)
 from .ops import ACT, _p, _stream
 
 KWMERGE_2D = os.environ.get("STB_UMMA_KWMERGE2D", "0")
@@ -54,8 +54,10 @@ class Conv2dPlan:
         wt = w.permute(2, 3, 0, 1) * scale.view(1, 1, -1, 1)                # [kh,kw,co,ci]
         tiles = torch.zeros(k * k, cpad, cin, device=w.device)
         tiles[:, :cout] = wt.reshape(k * k, cout, cin)
+        wexp = 0
         if split:
-            tiles = split_pack(tiles)
+            wexp = split_weight_exponent(tiles)
+            tiles = split_pack(tiles * float(2.0 ** wexp))
         self.wt = tiles.view(k * k, cpad, self.nk, kc).permute(0, 2, 1, 3).contiguous().to(dtype)
         self.nwtiles = k * k
         e = [kk * dil - pad for kk in range(k)]
@@ -89,7 +91,7 @@ class Conv2dPlan:
         self.c = [_iarr(v) for v in (dz, dh, dw, sub, widx)]
         self.c_tb, self.c_te, self.c_z = _iarr([0]), _iarr([self.ntaps]), _iarr([0])
         self.flags = BO_MODE | (ES_VARIANT << 1) | (4 if self.merge else 0) | 16 | ((dil & 7) << 8) | (32 if self.kdepth else 0) \
-            | (SPLIT_FLAG if split else 0)
+            | ((SPLIT_FLAG | (wexp << 16)) if split else 0)
 
     def out_size(self, n):
         return (n + 2 * self.pad - self.dil * (self.k - 1) - 1) // self.stride + 1
@@ -106,6 +108,7 @@ class UmmaGwcFeatures:
         self.f16 = int(precision in ("fp16", "fp16x2"))
         self._plans: Dict[int, tuple] = {}
         self._ws = None
+        self.prof = None              # bench.py's KernelProfiler: one bracket per layer ("conv2d_umma" family)
 
     def _plan(self, conv, bn, cin_tensor):
         ver = (conv.weight.data_ptr(), conv.weight._version, cin_tensor) + \
@@ -134,10 +137,18 @@ class UmmaGwcFeatures:
             ws = self._ws
         if residual is not None:
             assert residual.shape == out.shape and residual.dtype == self.dtype and residual.is_contiguous()
-        _lib.call("stb_conv3d_umma", _p(x), _p(p.wt), _p(p.shift), _p(residual), _p(out), _p(ws), self.f16,
-                  1, Cst, p.kc, N, H, W, cout_t, p.cout, N, Ho, Wo, p.ntaps, p.c[0], p.c[1], p.c[2], p.c[3], p.c[4],
-                  None, None, p.nwtiles, 1, p.c_tb, p.c_te, p.c_z, p.c_z, p.c_z, p.in_stride, 1, N, Ho, Wo,
-                  p.in_off, p.in_off, ACT[act], 0, p.flags, 0, _stream())
+        call = lambda: _lib.call("stb_conv3d_umma", _p(x), _p(p.wt), _p(p.shift), _p(residual), _p(out), _p(ws), self.f16,
+                                 1, Cst, p.kc, N, H, W, cout_t, p.cout, N, Ho, Wo, p.ntaps, p.c[0], p.c[1], p.c[2], p.c[3], p.c[4],
+                                 None, None, p.nwtiles, 1, p.c_tb, p.c_te, p.c_z, p.c_z, p.c_z, p.in_stride, 1, N, Ho, Wo,
+                                 p.in_off, p.in_off, ACT[act], 0, p.flags, 0, _stream())
+        if self.prof is not None and self.prof.enabled:
+            flops = 2.0 * p.k * p.k * conv.in_channels * p.cout * N * Ho * Wo
+            nbytes = 2.0 * self.cmul * (x.numel() / self.cmul + out.numel() / self.cmul * (2 if residual is not None else 1))
+            with self.prof.bracket("conv2d_umma", flops, nbytes,
+                                   detail=f"2d {conv.in_channels}->{p.cout} k{p.k} s{p.stride} d{p.dil} @{H}x{W}"):
+                call()
+        else:
+            call()
         return out
 
     def _convbn(self, seq, x, act="none", residual=None):

