@@ -12,6 +12,9 @@ from .pcwnet import PCWNet_G, PCWNet_GC
 from .igev_stereo import IGEVStereo
 from .checkpoint import load_checkpoint_flexible
 from .evaluation import speed_and_memory_test
+from . import ops as _ops
+
+_ops.register_torch_ops()      # torch.ops.stb200.* (dispatcher entries + Meta kernels + autograd formulas); no CUDA needed to register
 
 __all__ = ["build_gwc_volume", "build_concat_volume", "build_concat_volume_unmasked", "groupwise_correlation",
            "disparity_regression", "disparityregression", "upsample_softargmin", "CorrBlock1D",

@@ -94,9 +94,45 @@ def check(code: int, what: str):
 
 LAUNCH_COUNT = 0   # number of kernel launches issued through this binding (bench.py reports it)
 
+# Device of the tensors of the call being assembled.  The C ABI launches on the CURRENT device; the wrappers build a call's
+# arguments with ops._p(tensor) / ops._stream() and then invoke call(): _p notes the device of every tensor it sees (and
+# refuses a mix), _stream() returns that device's current stream, and call() makes that device current for the launch --
+# so ``model.to('cuda:1')`` works without torch.cuda.set_device, like the device-guarded torch ops of the reference.
+_call_device = None
+
+
+def note_device(index):
+    """Called by ops._p for every CUDA tensor argument of the call being assembled."""
+    global _call_device
+    if _call_device is None:
+        _call_device = index
+    elif _call_device != index:
+        bad, _reset = (_call_device, index), _reset_device()
+        raise StbError(f"tensor arguments of one stereo_toolbox_b200 call live on different CUDA devices {bad}")
+
+
+def _reset_device():
+    global _call_device
+    _call_device = None
+
+
+def call_device():
+    return _call_device
+
 
 def call(name: str, *args):
     global LAUNCH_COUNT
-    code = getattr(lib(), name)(*args)
+    dev = _call_device
+    _reset_device()
+    fn = getattr(lib(), name)
+    if dev is None:
+        code = fn(*args)
+    else:
+        import torch
+        if torch.cuda.current_device() == dev:
+            code = fn(*args)
+        else:
+            with torch.cuda.device(dev):
+                code = fn(*args)
     check(code, name)
     LAUNCH_COUNT += 1

@@ -393,7 +393,12 @@ class UmmaBackend:
 
     def block_attention(self, qkv, bias, heads, block):
         if self.split:
-            raise NotImplementedError("fp16x2 precision: windowed attention core not built for split storage")
+            # split storage: the windowed attention core runs on its fp32 NCDHW instantiation (the tensors at the bottom of
+            # the hourglass are 1/16-resolution and small); layout kernels on both sides
+            q32 = from_channels_last(qkv, split=True)
+            with self.prof.bracket("block_attention", 0.0, 4.0 * (q32.numel() + q32.numel() // 3)):
+                o32 = ops.block_attention(q32, bias, heads, block, channels_last=False)
+            return to_channels_last(o32, pad_channels(o32.shape[1]), self.dtype, split=True)
         B, D, H, W, C3 = qkv.shape
         with self.prof.bracket("block_attention", 4.0 * B * D * H * W * (C3 // 3) * block[0] * block[1] * block[2],
                                2.0 * (qkv.numel() + qkv.numel() // 3)):

@@ -42,7 +42,15 @@ upsample_softargmin_kernel(const float* __restrict__ cost, float* __restrict__ d
         float v = a00 * __ldg(p + h0 * W + w0) + a01 * __ldg(p + h0 * W + w1) + a10 * __ldg(p + h1 * W + w0) +
                   a11 * __ldg(p + h1 * W + w1);
         col[d * HEAD_THREADS + threadIdx.x] = v;
-        m = fmaxf(m, v);
+    }
+    // softmax shift = maximum over the INTERPOLATED bins (what F.softmax subtracts), not over the knots: interior knots are
+    // never sampled exactly (td >= 0.125), so for an isolated peak > ~700 above its neighbours every exp(v - max_knot) would
+    // flush to zero and the result would be 0/0
+    for (int od = 0; od < outD; ++od) {
+        int d0, d1;
+        float td;
+        src_index(od, D, sd, align, d0, d1, td);
+        m = fmaxf(m, (1.f - td) * col[d0 * HEAD_THREADS + threadIdx.x] + td * col[d1 * HEAD_THREADS + threadIdx.x]);
     }
     float s = 0.f, acc = 0.f;
     for (int od = 0; od < outD; ++od) {
@@ -83,7 +91,17 @@ upsample_softargmin_x4_kernel(const float* __restrict__ cost, float* __restrict_
         float v = a00 * __ldg(p + h0 * W + w0) + a01 * __ldg(p + h0 * W + w1) + a10 * __ldg(p + h1 * W + w0) +
                   a11 * __ldg(p + h1 * W + w1);
         col[d * HEAD_THREADS + threadIdx.x] = v;
-        m = fmaxf(m, v);
+    }
+    {   // maximum over the interpolated bins: between two knots the bins are linear in td, so only the outermost two
+        // (td = 0.125, 0.875) can be the largest; bins 0, 1 sit on knot 0 and the last two on knot D-1
+        float p0 = col[threadIdx.x];
+        m = p0;
+        for (int k = 0; k + 1 < D; ++k) {
+            const float p1 = col[(k + 1) * HEAD_THREADS + threadIdx.x];
+            m = fmaxf(m, fmaxf(fmaf(0.125f, p1, __fmul_rn(0.875f, p0)), fmaf(0.875f, p1, __fmul_rn(0.125f, p0))));
+            p0 = p1;
+        }
+        m = fmaxf(m, p0);
     }
     float c0 = col[threadIdx.x];
     // bins 0 and 1: td = 0, the generic kernel computes 1*c0 + 0*c1 = c0

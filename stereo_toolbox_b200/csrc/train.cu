@@ -184,7 +184,12 @@ upsample_softargmin_bwd_kernel(const float* __restrict__ cost, const float* __re
                         a11 * __ldg(p + h1 * W + w1);
         col[d * HB_THREADS + threadIdx.x] = v;
         gcol[d * HB_THREADS + threadIdx.x] = 0.f;
-        m = fmaxf(m, v);
+    }
+    for (int od = 0; od < outD; ++od) {          // softmax shift = maximum over the interpolated bins (see head.cu)
+        int d0, d1;
+        float td;
+        src_index_b(od, D, sd, align, d0, d1, td);
+        m = fmaxf(m, (1.f - td) * col[d0 * HB_THREADS + threadIdx.x] + td * col[d1 * HB_THREADS + threadIdx.x]);
     }
     float s = 0.f, acc = 0.f;
     for (int od = 0; od < outD; ++od) {

@@ -46,22 +46,52 @@ class FlatGradAllReduce:
         total = sum(p.numel() for p in self.params)
         device = device or self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self._views = []
         off = 0
         for p in self.params:
             assert p.dtype == torch.float32
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self._views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self._attach()
+
+    def _attach(self):
+        for p, v in zip(self.params, self._views):
+            p.grad = v
 
     @property
     def nbytes(self) -> int:
         return self.flat.numel() * 4
 
     def zero_(self):
+        """Zero the gradients IN PLACE and keep every ``p.grad`` a view of the flat buffer (use this, or
+        ``optimizer.zero_grad(set_to_none=False)``, instead of the default ``optimizer.zero_grad()``)."""
         self.flat.zero_()
+        self._attach()
+
+    def repack_(self) -> int:
+        """Make the flat buffer hold the current gradients again and re-attach the views.  The reference trainer's
+        ``optimizer.zero_grad()`` (trainer/trainer_torchrun.py:286-301) defaults to ``set_to_none=True``, which drops the
+        views; autograd then allocates fresh ``.grad`` tensors and the flat buffer would be reduced as all zeros while the
+        ranks silently diverge.  A parameter whose ``.grad`` no longer aliases its slice is copied in (``None``: the slice is
+        zeroed -- DDP would also contribute zeros for a parameter that received no gradient).  Returns how many were stale."""
+        stale = 0
+        for p, v in zip(self.params, self._views):
+            g = p.grad
+            if g is not None and g.data_ptr() == v.data_ptr() and g.shape == v.shape:
+                continue
+            stale += 1
+            if g is None:
+                v.zero_()
+            else:
+                v.copy_(g)
+            p.grad = v
+        return stale
 
     def allreduce_(self):
-        """sum over ranks, then / world (what DDP does); no-op for a single process."""
+        """sum over ranks, then / world (what DDP does); no-op for a single process.  Gradients that were detached from
+        the flat buffer since the last step (``zero_grad(set_to_none=True)``) are packed back first."""
         import torch.distributed as dist
+        self.repack_()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(dist.get_world_size())

@@ -31,11 +31,19 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 def _p(t: Optional[torch.Tensor]):
-    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+    """Raw device pointer of a tensor argument; notes the tensor's device for the launch (see _lib.note_device)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if t.is_cuda:
+        _lib.note_device(t.device.index)
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Current stream of the device the call's tensors live on (every wrapper passes it as the LAST argument, after the
+    tensors), not of the process-wide current device."""
+    dev = _lib.call_device()
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 # ------------------------------------------------------------------------------------ volumes
@@ -302,7 +310,34 @@ def conv3d_plan_apply(plan: ConvPlan, x: torch.Tensor, act: str = "none",
             continue
         _lib.call("stb_conv3d_taps_f32", _p(x), _p(sel), _p(plan.shift), _p(residual), _p(out), B, Cin, Di, Hi, Wi,
                   plan.cout, Do, Ho, Wo, T, dd, dh, dw, in_s, out_s, od0, oh0, ow0, nd, nh, nw, ACT[act], _stream())
+    if plan.transposed and len(plan.classes) < plan.stride ** 3:
+        # k < stride (e.g. ConvTranspose3d(k=1, s=2)): some output-parity classes receive no tap at all; those positions
+        # hold act(shift + residual), not whatever torch.empty left there
+        have = {c[-1] for c in plan.classes}
+        s_ = plan.stride
+        for cd in range(s_):
+            for ch in range(s_):
+                for cw in range(s_):
+                    if (cd, ch, cw) in have:
+                        continue
+                    sl = (slice(None), slice(None), slice(cd, None, s_), slice(ch, None, s_), slice(cw, None, s_))
+                    v = torch.zeros_like(out[sl])
+                    if plan.shift is not None:
+                        v = v + plan.shift.view(1, -1, 1, 1, 1)
+                    if residual is not None:
+                        v = v + residual[sl]
+                    out[sl] = _act_torch(v, act)
     return out
+
+
+def _act_torch(x, act):
+    if act == "relu":
+        return torch.relu(x)
+    if act == "leaky":
+        return torch.nn.functional.leaky_relu(x, 0.01)
+    if act == "mish":
+        return x * torch.tanh(torch.nn.functional.softplus(x))
+    return x
 
 
 def conv3d_bn_act(x, weight, bn=None, stride=1, padding=1, act="none", residual=None, transposed=False,
@@ -339,6 +374,9 @@ def avgpool_last(x: torch.Tensor) -> torch.Tensor:
 
 
 def _ptr_array(ts: Sequence[torch.Tensor]):
+    for t in ts:
+        if t.is_cuda:
+            _lib.note_device(t.device.index)
     return (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
 
 

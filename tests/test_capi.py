@@ -154,3 +154,17 @@ def test_torch_ops_fake_kernels_give_reference_shapes():
     assert T.disparity_variance(m(2, 12, 8, 16), 12, m(2, 1, 8, 16)).shape == (2, 1, 8, 16)
     assert T.patch_dw(m(1, 40, 12, 8, 16), m(40, 1, 1, 3, 3), 2).shape == (1, 40, 12, 8, 16)
     assert T.block_attention(m(1, 96, 4, 8, 8), m(96), 4, [4, 4, 4]).shape == (1, 32, 4, 8, 8)
+
+
+def test_call_device_tracking():
+    """ops._p notes the device of every tensor argument; a call may not mix devices, and _lib.call() clears the note
+    (the launch itself then runs under torch.cuda.device(<that device>) -- exercised on a 2-GPU box by
+    tests/test_gpu_ops.py::test_ops_follow_the_tensor_device)."""
+    from stereo_toolbox_b200 import _lib
+    _lib._reset_device()
+    _lib.note_device(1)
+    _lib.note_device(1)
+    assert _lib.call_device() == 1
+    with pytest.raises(_lib.StbError):
+        _lib.note_device(0)
+    assert _lib.call_device() is None                       # a refused call leaves no stale note behind

@@ -72,6 +72,21 @@ def test_head_oracle_x4(align):
     assert (got.cpu() - want).abs().max().item() < 1e-3      # values up to 191; fp32 index math vs fp64 oracle
 
 
+@pytest.mark.parametrize("align,outd", [(False, 48), (True, 48), (False, 40)])
+def test_head_extreme_isolated_peak(align, outd):
+    """An isolated logit far (> 700) above its neighbours: the interpolated bins never hit the knot itself, so a softmax
+    shifted by the KNOT maximum would flush every exp to zero (0/0).  F.softmax -- and the kernels -- shift by the maximum of
+    the interpolated bins.  outd=40: the generic kernel (not a x4 upsampling)."""
+    import stereo_toolbox_b200 as S
+    cost = rnd(6, 1, 1, 12, 5, 9)
+    cost[:, :, 7] += 2500.0
+    cost[0, 0, 3, 2, 4] = 9000.0
+    got = S.upsample_softargmin(cu(cost), outd, 20, 36, align).cpu()
+    want = R.upsample_softargmin(cost, outd, 20, 36, align)
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() < 2e-3
+
+
 CONVS = [
     # cin, cout, k, stride, pad, transposed, outpad, act, residual
     (8, 16, 3, 1, 1, False, 0, "relu", False),
@@ -189,3 +204,30 @@ def test_patch_dw_golden_and_slices():
     ops.patch_dw(x, cu(g["patch_w3"][4:]), 3, out=out, c_off=4)
     want = torch.cat((g["patch_y1"][:, :2], g["patch_y2"][:, 2:4], g["patch_y3"][:, 4:]), 1)
     close(out, want)
+
+
+def test_ops_follow_the_tensor_device():
+    """model.to('cuda:1') without torch.cuda.set_device (the reference's speed_and_memory_test(model, device='cuda:1')
+    pattern): kernels must launch on the tensors' device and stream, not on the current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import stereo_toolbox_b200 as S
+    assert torch.cuda.current_device() == 0
+    L, Rr = rnd(1, 1, 80, 6, 24), rnd(2, 1, 80, 6, 24)
+    vol = S.build_gwc_volume(L.to("cuda:1"), Rr.to("cuda:1"), 8, 40)
+    assert vol.device.index == 1 and torch.cuda.current_device() == 0
+    close(vol, R.build_gwc_volume(L, Rr, 8, 40), 1e-5, 2e-5)
+    with pytest.raises(Exception):
+        S.build_gwc_volume(L.to("cuda:0"), Rr.to("cuda:1"), 8, 40)
+
+
+def test_transposed_conv_with_kernel_smaller_than_stride():
+    """ConvTranspose3d(k=1, s=2): seven of the eight output-parity classes receive no tap; they hold act(shift + residual)."""
+    from stereo_toolbox_b200 import ops
+    x, w = rnd(1, 1, 4, 3, 4, 5), rnd(2, 4, 6, 1, 1, 1)
+    res = rnd(3, 1, 6, 5, 7, 9)
+    bn = dict(weight=torch.rand(6) + 0.5, bias=rnd(4, 6), running_mean=rnd(5, 6) * 0.1, running_var=torch.rand(6) + 0.5)
+    got = ops.conv3d_bn_act(cu(x), cu(w), tuple(cu(bn[k]) for k in ("weight", "bias", "running_mean", "running_var")),
+                            stride=2, padding=0, act="relu", residual=cu(res), transposed=True)
+    want = R.conv3d_bn_act(x, w, bn, 2, 0, "relu", res, True, 0)
+    close(got, want, 1e-5, 1e-5)

@@ -136,11 +136,15 @@ def _pair(meta):
     return synth_pair(b, h, w, seed=1 if h == 256 else 0, shift=meta["shift"])
 
 
-# px, hot path only (identical fp32 features: feature_tf32=False); measured values are printed
-EPE_TOL = {"bf16": 0.1, "fp16": 1e-2}
+# px, hot path only (identical fp32 features: feature_tf32=False); measured values are printed.  Model-level bars are the
+# north_star's: 1e-2 px for 16-bit storage.  bf16 storage is NOT a parity precision -- it measures 4.5e-2 px on GwcNet_GC and
+# 9.2e-2 px on ACVNet at fixture size (8-bit mantissa through ~25 layers; oracle/ref_lowp.py predicts 4.8e-2) -- so it is
+# tested per operator (<= 1 ulp of the stored output, above) and against its storage model (test_lowp_model_gpu.py), not
+# against a loosened model-level bar.  The precision that carries the headline is 'fp16x2' (tests/test_split_gpu.py, 1e-3 px).
+EPE_TOL = {"fp16": 1e-2}
 
 
-@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("prec", ["fp16"])
 @pytest.mark.parametrize("key", ["gwcnet_gc", "gwcnet_g"])
 def test_gwcnet_golden_16bit(key, prec):
     import stereo_toolbox_b200 as S
@@ -162,7 +166,7 @@ def test_gwcnet_golden_16bit(key, prec):
     assert epe < EPE_TOL[prec], f"EPE vs reference {epe}"
 
 
-@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("prec", ["fp16"])
 def test_psmnet_golden_16bit(prec):
     import stereo_toolbox_b200 as S
     g = load_golden("psmnet.npz")
@@ -210,10 +214,12 @@ def test_gwc_features_on_umma(prec):
             assert rel < (2e-3 if prec == "fp16" else 1.6e-2)
 
 
-@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("prec", ["fp16x2", "fp16"])
 def test_acvnet_golden_16bit(prec):
     """ACVNet on the tensor-core backend: 1x1x1 qkv / final convs with bias on tcgen05 (Cout 384 -> N-split),
-    the block attention kernel on channels-last 16-bit tensors."""
+    the block attention kernel on channels-last 16-bit tensors.  fp16x2: the exact path, 1e-3 px.  Single fp16 storage
+    measures 1.2e-2 px on this model (two chained aggregation networks + attention): it is the fast secondary path and
+    does not meet the 1e-2 bar here -- asserted only to stay at its storage-format level (< 2e-2)."""
     import stereo_toolbox_b200 as S
     from stereo_toolbox_b200.synth import synth_pair
     g = load_golden("acvnet.npz")
@@ -228,7 +234,7 @@ def test_acvnet_golden_16bit(prec):
     epe = (disp - g["disp"]).abs().mean().item()
     e = (net._last_cost.cpu().permute(0, 4, 1, 2, 3) - g["cost2"]).abs()
     print(f"acvnet {prec} EPE vs reference: {epe:.4e} px; cost2 err mean {e.mean().item():.3e} max {e.max().item():.3e}")
-    assert epe < {"bf16": 0.2, "fp16": 2e-2}[prec], f"EPE vs reference {epe}"
+    assert epe < {"fp16x2": 1e-3, "fp16": 2e-2}[prec], f"EPE vs reference {epe}"
     net.feature_tf32, net.feature_mode = None, "umma"
     with torch.no_grad():
         disp2 = net(left.cuda(), right.cuda()).cpu()

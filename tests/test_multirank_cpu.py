@@ -89,6 +89,59 @@ def test_two_rank_gradient_allreduce():
         torch.testing.assert_close(torch.tensor(m1), want)
 
 
+def _grad_worker_zero_grad(rank, world, port, q):
+    """The reference trainer's loop (trainer/trainer_torchrun.py:272-301): optimizer.zero_grad() with its default
+    set_to_none=True drops the flat views; allreduce_() must notice and still exchange the real gradients."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    for p in net[3].parameters():
+        p.requires_grad_(True)
+    opt = torch.optim.SGD(net.parameters(), lr=0.0)
+    bucket = FlatGradAllReduce(net.parameters())
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(4, 6, generator=g)
+    for _ in range(2):
+        opt.zero_grad()                                    # set_to_none=True: p.grad = None, views dropped
+        net[:3](x).square().mean().backward()              # net[3] receives no gradient this step (stays None)
+        local = [None if p.grad is None else p.grad.clone() for p in net.parameters()]
+        stale = sum(1 for p in net.parameters() if p.grad is None or p.grad.data_ptr() < bucket.flat.data_ptr()
+                    or p.grad.data_ptr() >= bucket.flat.data_ptr() + bucket.nbytes)
+        bucket.allreduce_()
+    views_ok = all(p.grad is not None and bucket.flat.data_ptr() <= p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.nbytes
+                   for p in net.parameters())
+    q.put((rank, [None if t is None else t.tolist() for t in local], [p.grad.tolist() for p in net.parameters()], views_ok, stale))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_survives_zero_grad_set_to_none():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker_zero_grad, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, r0, v0, s0), (_, l1, r1, v1, s1) = res
+    assert v0 and v1 and s0 == 6 and s1 == 6               # every gradient had left the flat buffer before the exchange
+    for a, b, m0, m1 in zip(l0, l1, r0, r1):
+        if a is None:                                      # no gradient this step: contributes zeros, like DDP
+            assert torch.tensor(m0).abs().max() == 0 and torch.tensor(m1).abs().max() == 0
+            continue
+        want = (torch.tensor(a) + torch.tensor(b)) / 2
+        assert want.abs().max() > 0
+        torch.testing.assert_close(torch.tensor(m0), want)
+        torch.testing.assert_close(torch.tensor(m1), want)
+
+
 def _ddp_worker(rank, world, port, q):
     """A drop-in model under torch's DistributedDataParallel ('DDP(...) must keep working around the
     patched model', trainer/trainer_torchrun.py:116-121).  CPU: the 3-D path is answered by the oracle's TrainBackend
