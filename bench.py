@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS),
                     help="kitti = BASELINE.json's metric (default); sceneflow = the north_star's second shape")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train_step leg (BASELINE config 3, run at every N)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the secondary legs (fast_fp16, sceneflow, reference_gpu_eager, train_step); N=1 only anyway")
     ap.add_argument("--cpu-sample", type=int, default=1, help="pairs in the cpu_baseline sample")
@@ -248,10 +249,8 @@ def main():
 
     from stereo_toolbox_b200.distrib import reduce_stats
     (ms, ms_e2e), (total_pairs, launches) = reduce_stats([ms, ms_e2e], [a.batch * a.steps, launches], device="cuda")
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    del bufs
+    torch.cuda.empty_cache()
 
     value = total_pairs / (ms / 1e3)
     line = {"metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -262,6 +261,22 @@ def main():
                     "h2d_bytes_per_step": int(left_h.numel() * 4 * 2), "d2h_bytes_per_step": int(out_h.numel() * 4)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": prof.roofline(precision),
             "kernels": prof.summary(), "layers": prof.layer_table()}
+    # ---- BASELINE config 3 beside the headline, at EVERY N (all ranks take part: it contains the path's one collective):
+    # PSMNet training step, bf16, SceneFlow shape 960x540 -> 960x576, D=192, batch 1 per GPU, gradient all-reduce over NCCL
+    train = None
+    if not a.no_train:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import train_step
+            train = train_step.run(576, 960, 1, steps=3, warmup=1, precision="bf16")
+        except Exception as e:
+            train = {"error": repr(e)[:300]}
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    if train is not None:
+        line["train_step"] = train
     # ---- everything below is reported next to the headline, at N=1 only (rank 0 would hold the other ranks up)
     if world == 1 and not a.no_cpu_baseline:
         r = cpu_reference_run(sd, a.cpu_sample, 1, 0, pair=(left_h[: a.cpu_sample].clone(), right_h[: a.cpu_sample].clone()))

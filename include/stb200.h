@@ -228,6 +228,19 @@ int stb_feature_gate_cl16(const void* x, const float* gate, void* out, int f16, 
 int stb_disparity_variance_f32(const float* prob, const float* disp, float* var, int B, int D, long long plane,
                                void* stream);
 
+/* ---- learned convex 9-tap upsampling of the iterative models -----------------------------
+ * stb_convex_upsample_f32 replaces RAFTStereo.upsample_flow (RAFTStereo/raft_stereo.py:81-93): softmax over the 9 mask
+ * logits of every fine pixel + convex combination of the 3x3 coarse neighbourhood of factor*flow (zero outside).
+ * flow [N,D,H,W], mask [N, 9*factor^2, H, W] (channel = tap*factor^2 + fy*factor + fx) -> out [N,D,factor*H,factor*W].
+ * factor 2, 4 or 8.
+ * stb_context_upsample_f32 replaces context_upsample (IGEVStereo/submodule.py:243-255): out[b,Y,X] = sum_t w[b,t,Y,X] *
+ * scale * disp_low[b, Y/factor + t/3 - 1, X/factor + t%3 - 1]; apply_softmax != 0 soft-maxes the 9 weights first (the
+ * F.softmax(..., 1) the caller applies at igev_stereo.py:164). disp_low [B,1,h,w], weights [B,9,factor*h,factor*w]. */
+int stb_convex_upsample_f32(const float* flow, const float* mask, float* out, int N, int D, int H, int W, int factor,
+                            void* stream);
+int stb_context_upsample_f32(const float* disp_low, const float* weights, float* out, int B, int h, int w, int factor,
+                             float scale, int apply_softmax, void* stream);
+
 /* ---- backward kernels (training path, exact fp32, reference layouts) --------------------------------------
  * The DATA gradient of the conv family needs no entry point of its own: the adjoint of Conv3d(k,s,p) is
  * ConvTranspose3d(k,s,p,op) with the same weight tensor and vice versa, i.e. another stb_conv3d_taps_f32 call.

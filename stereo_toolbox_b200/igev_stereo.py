@@ -239,7 +239,11 @@ class IGEVStereo(IGEVCostVolume):
     def upsample_disp(self, disp, mask_feat_4, stem_2x):
         """igev_stereo.py:157-166: 9 convex weights per full-resolution pixel from the GRU's 32-channel feature and the
         1/2-resolution stem; disparity scaled by 4 with the resolution."""
-        spx_pred = F.softmax(self.spx_gru(self.spx_2_gru(mask_feat_4, stem_2x)), 1)
+        logits = self.spx_gru(self.spx_2_gru(mask_feat_4, stem_2x))
+        if disp.is_cuda and not (torch.is_grad_enabled() and (disp.requires_grad or logits.requires_grad)):
+            from . import ops
+            return ops.context_upsample(disp, logits, scale=4.0, softmax=True).unsqueeze(1)   # softmax + x4 + 9 taps in one kernel
+        spx_pred = F.softmax(logits, 1)
         return context_upsample(disp * 4.0, spx_pred).unsqueeze(1)
 
     def _iteration(self, net_list, inp_list, geo_fn, coords, disp):

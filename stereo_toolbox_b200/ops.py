@@ -415,6 +415,35 @@ def geo_lookup(geos, corrs, disp: torch.Tensor, coords: torch.Tensor, radius: in
     return out
 
 
+# ------------------------------------------------------------------------------------ learned convex upsampling
+def convex_upsample(flow: torch.Tensor, mask: torch.Tensor, factor: int) -> torch.Tensor:
+    """RAFTStereo.upsample_flow (RAFTStereo/raft_stereo.py:81-93) in one launch: flow [N,D,H,W], mask [N,9*factor^2,H,W]
+    (raw logits) -> [N,D,factor*H,factor*W]."""
+    _need_cuda(flow, mask)
+    flow, mask = _f32c(flow), _f32c(mask)
+    N, D, H, W = flow.shape
+    assert tuple(mask.shape) == (N, 9 * factor * factor, H, W)
+    out = torch.empty(N, D, factor * H, factor * W, device=flow.device, dtype=torch.float32)
+    _lib.call("stb_convex_upsample_f32", _p(flow), _p(mask), _p(out), N, D, H, W, factor, _stream())
+    return out
+
+
+def context_upsample(disp_low: torch.Tensor, up_weights: torch.Tensor, scale: float = 1.0, softmax: bool = False) -> torch.Tensor:
+    """context_upsample (IGEVStereo/submodule.py:243-255): disp_low [B,1,h,w], up_weights [B,9,f*h,f*w] -> [B,f*h,f*w].
+    ``scale`` multiplies the coarse disparity (the caller's ``disp * 4.``), ``softmax=True`` applies the F.softmax(.., 1)
+    of igev_stereo.py:164 to the 9 weights inside the kernel."""
+    _need_cuda(disp_low, up_weights)
+    disp_low, up_weights = _f32c(disp_low), _f32c(up_weights)
+    B, c, h, w = disp_low.shape
+    assert c == 1 and up_weights.shape[0] == B and up_weights.shape[1] == 9
+    f = up_weights.shape[2] // h
+    assert tuple(up_weights.shape[2:]) == (f * h, f * w)
+    out = torch.empty(B, f * h, f * w, device=disp_low.device, dtype=torch.float32)
+    _lib.call("stb_context_upsample_f32", _p(disp_low), _p(up_weights), _p(out), B, h, w, f, ctypes.c_float(scale),
+              int(softmax), _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------ torch.ops registration
 # torch.ops.stb200.<op>: same kernels behind the dispatcher, with fake (meta) kernels so that
 # tracing / DDP / autocast wrappers around a patched model keep working (SURVEY.md section 8b).

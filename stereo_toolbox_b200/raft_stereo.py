@@ -261,6 +261,9 @@ class RAFTStereo(nn.Module):
         """Convex 9-tap upsampling (raft_stereo.py:81-93)."""
         N, D, H, W = flow.shape
         f = 2 ** self.args.n_downsample
+        if flow.is_cuda and not (torch.is_grad_enabled() and (flow.requires_grad or mask.requires_grad)) and f in (2, 4, 8):
+            from . import ops
+            return ops.convex_upsample(flow, mask, f)          # one kernel: softmax + 9-tap combination + pixel shuffle (csrc/upsample2d.cu)
         mask = torch.softmax(mask.contiguous().view(N, 1, 9, f, f, H, W), dim=2)      # (channels-last glue: NCHW order first)
         up = F.unfold(f * flow, [3, 3], padding=1).view(N, D, 9, 1, 1, H, W)
         up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)

@@ -231,3 +231,23 @@ def test_transposed_conv_with_kernel_smaller_than_stride():
                             stride=2, padding=0, act="relu", residual=cu(res), transposed=True)
     want = R.conv3d_bn_act(x, w, bn, 2, 0, "relu", res, True, 0)
     close(got, want, 1e-5, 1e-5)
+
+
+def test_convex_upsampling_kernels_golden_and_oracle():
+    """RAFTStereo.upsample_flow (x4 and x8) and IGEV context_upsample against the reference's outputs
+    (fixture made by tests/golden/make_golden.py from the reference's own functions) and the oracle at a RAFT-sized shape."""
+    from stereo_toolbox_b200 import ops
+    g = load_golden("ops_upsampling.npz")
+    for f in (4, 8):
+        got = ops.convex_upsample(cu(g[f"raft_flow{f}"]), cu(g[f"raft_mask{f}"]), f)
+        assert got.shape == g[f"raft_up{f}"].shape
+        close(got, g[f"raft_up{f}"], 1e-5, 1e-5)
+    close(ops.context_upsample(cu(g["igev_disp"]), cu(g["igev_w"])), g["igev_up"], 1e-5, 1e-5)
+    # fused softmax + scale (what IGEVStereo.upsample_disp asks for)
+    logits = rnd(3, 2, 9, 20, 28) * 2
+    want = R.context_upsample(g["igev_disp"] * 4.0, torch.softmax(logits, 1))
+    close(ops.context_upsample(cu(g["igev_disp"]), cu(logits), scale=4.0, softmax=True), want, 1e-5, 2e-5)
+    flow, mask = rnd(4, 1, 2, 33, 70) * 5, rnd(5, 1, 144, 33, 70) * 3          # odd sizes: tails of the 128-wide blocks
+    close(ops.convex_upsample(cu(flow), cu(mask), 4), R.convex_upsample(flow, mask, 4), 1e-5, 2e-5)
+    flow, mask = rnd(6, 1, 1, 9, 11), rnd(7, 1, 36, 9, 11)
+    close(ops.convex_upsample(cu(flow), cu(mask), 2), R.convex_upsample(flow, mask, 2), 1e-5, 1e-5)

@@ -51,7 +51,7 @@ def main():
     ap.add_argument("--maxdisp", type=int, default=192)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--iters", type=int, default=32, help="GRU iterations (raft / igev)")
-    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16x2", "fp16", "bf16"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cuda-graph", action="store_true", help="raft / igev: replay one captured GRU iteration")

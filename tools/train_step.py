@@ -25,42 +25,32 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--batch", type=int, default=2, help="pairs per GPU per step")
-    ap.add_argument("--height", type=int, default=384)
-    ap.add_argument("--width", type=int, default=512)
-    ap.add_argument("--maxdisp", type=int, default=192)
-    ap.add_argument("--lr", type=float, default=1e-4)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp16"],
-                    help="fp32 = exact training path; bf16 / fp16 = train16.Umma16TrainBackend (tcgen05 forward + dgrad)")
-    args = ap.parse_args()
+def run(height=384, width=512, batch=2, steps=5, warmup=2, maxdisp=192, lr=1e-4, precision="fp32"):
+    """Times `steps` complete training steps on every rank of the (already initialised, if world > 1) process group and
+    returns the JSON-able result on rank 0 (None elsewhere).  Called by main() below and by bench.py's ``train_step`` leg."""
     import torch.distributed as dist
     import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200 import _lib
     from stereo_toolbox_b200.distrib import env_rank, FlatGradAllReduce, reduce_stats
     from stereo_toolbox_b200.synth import synth_state_dict, synth_pair, synth_gt
     rank, world, local = env_rank()
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     meta = json.load(open(os.path.join(ROOT, "tests", "golden", "models.json")))["psmnet"]
     tmpl = {k: torch.zeros(s, dtype=torch.int64 if k.endswith("num_batches_tracked") else torch.float32)
             for k, s in meta["keys"].items()}
     z = np.load(os.path.join(ROOT, "tests", "golden", "bn_calib_psmnet.npz"))
-    net = S.PSMNet(args.maxdisp)
+    net = S.PSMNet(maxdisp)
     net.load_state_dict(synth_state_dict(tmpl, 0, {k: z[k] for k in z.files}))
     net = net.cuda().train()
-    net.train_precision = args.precision
+    net.train_precision = precision
     bucket = FlatGradAllReduce(net.parameters())
-    left, right = synth_pair(args.batch, args.height, args.width, seed=1000 + rank, shift=11)
+    left, right = synth_pair(batch, height, width, seed=1000 + rank, shift=11)
     left, right = left.cuda(), right.cuda()
-    gt = synth_gt(args.batch, args.height, args.width).cuda() * (args.maxdisp / 32.0)
-    mask = (gt > 0) & (gt < args.maxdisp)
+    gt = synth_gt(batch, height, width).cuda() * (maxdisp / 32.0)
+    mask = (gt > 0) & (gt < maxdisp)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    t_step, t_ar = [], []
-    for it in range(args.warmup + args.steps):
+    t_step, t_ar, t_fb = [], [], []
+    launches0 = _lib.LAUNCH_COUNT
+    for it in range(warmup + steps):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -75,12 +65,13 @@ def main():
         e2.record()
         with torch.no_grad():
             for p in bucket.params:
-                p.add_(p.grad, alpha=-args.lr)
+                p.add_(p.grad, alpha=-lr)
         e3.record()
         torch.cuda.synchronize()
-        if it >= args.warmup:
+        if it >= warmup:
             t_step.append(e0.elapsed_time(e3))
             t_ar.append(e1.elapsed_time(e2))
+            t_fb.append(e0.elapsed_time(e1))
     # every rank must hold identical gradients after the exchange
     disagree = 0.0
     if world > 1:
@@ -88,17 +79,50 @@ def main():
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         disagree = (hi - lo).abs().max().item()
-    (step_ms, ar_ms), (pairs,) = reduce_stats([sum(t_step) / len(t_step), sum(t_ar) / len(t_ar)], [float(args.batch)], device="cuda")
+    avg = lambda v: sum(v) / len(v)
+    (step_ms, ar_ms, fb_ms), (pairs,) = reduce_stats([avg(t_step), avg(t_ar), avg(t_fb)], [float(batch)], device="cuda")
+    out = None
     if rank == 0:
         bus = 2.0 * (world - 1) / world * bucket.nbytes / (ar_ms * 1e-3) / 1e9 if world > 1 else 0.0
-        print(json.dumps({
-            "metric": "PSMNet training pairs/sec (fp32 exact path, forward+backward in libstb200.so, flat NCCL grad all-reduce)",
-            "value": pairs / (step_ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "allreduce_ms": ar_ms, "allreduce_bytes": bucket.nbytes, "allreduce_busbw_gbs": bus,
-            "grad_disagreement_after_allreduce": disagree, "loss": loss.item(), "scaling": "weak", "dtype": "f32",
-            "config": {"workload": f"PSMNet train step {args.height}x{args.width} D={args.maxdisp}", "batch_per_gpu": args.batch,
-                       "precision": args.precision},
-            "gpu_launches": __import__("stereo_toolbox_b200._lib", fromlist=["x"]).LAUNCH_COUNT}))
+        kind = "fp32 exact path" if precision == "fp32" else \
+            f"{precision}: tcgen05 forward + dgrad on 16-bit channels-last activations, fp32 wgrad / BatchNorm statistics / volumes / head"
+        out = {
+            "metric": f"PSMNet training pairs/sec ({kind}; forward+backward in libstb200.so, one flat NCCL gradient all-reduce)",
+            "value": pairs / (step_ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": step_ms, "forward_backward_ms": fb_ms, "allreduce_ms": ar_ms, "allreduce_bytes": bucket.nbytes,
+            "allreduce_busbw_gbs": bus, "allreduce_share_of_step": ar_ms / step_ms,
+            "overlap": "off: one all-reduce of the flat fp32 gradient buffer after backward (no bucketing, no overlap with backward)",
+            "grad_disagreement_after_allreduce": disagree, "loss": loss.item(), "scaling": "weak",
+            "dtype": {"fp32": "f32"}.get(precision, precision),
+            "config": {"workload": f"PSMNet train step {height}x{width} D={maxdisp}", "batch_per_gpu": batch,
+                       "precision": precision, "loss": "smooth-L1 on the 3 outputs, weights 0.5/0.7/1.0, mask 0 < gt < maxdisp"},
+            "gpu_launches": _lib.LAUNCH_COUNT - launches0}
+    del net, bucket
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=2, help="pairs per GPU per step")
+    ap.add_argument("--height", type=int, default=384)
+    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--maxdisp", type=int, default=192)
+    ap.add_argument("--lr", type=float, default=1e-4)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp16"],
+                    help="fp32 = exact training path; bf16 / fp16 = train16.Umma16TrainBackend (tcgen05 forward + dgrad)")
+    args = ap.parse_args()
+    import torch.distributed as dist
+    from stereo_toolbox_b200.distrib import env_rank
+    rank, world, local = env_rank()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = run(args.height, args.width, args.batch, args.steps, args.warmup, args.maxdisp, args.lr, args.precision)
+    if rank == 0:
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
