@@ -414,7 +414,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                             const UGroup gr = a.grp[g];
                             const int z = (int)gr.z, g0 = (int)gr.tap_begin, g1 = (int)gr.tap_end;
                             int sl = step_slot + z;
-                            sl -= sl >= R ? R : 0;
+                            while (sl >= R) sl -= R;          // (kdepth rings may be shorter than a round's chunk count)
                             const uint32_t abase = (uint32_t)sl * plane16;
                             wait_upto(dead_now + z + 1);
                             if (trace && g == gb) trace_buf[ground * 8 + 2] = clock64();
@@ -431,7 +431,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         if (trace) trace_buf[ground * 8 + 3] = clock64();
                     }
                     step_slot += sd;
-                    if (step_slot >= R) step_slot -= R;
+                    while (step_slot >= R) step_slot -= R;
                 }
                 release_upto(u.nplanes);          // everything of this item (also planes only the other issuer read)
                 base_slot = (base_slot + u.nplanes) % R;
@@ -865,6 +865,10 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.TW = TWP - (a.merge == 3 ? 2 * a.merge_step : maxdw);
     a.dzmin = dzmin; a.dzmax = dzmax;
     const int window = dzmax - dzmin + 1;
+    // Planes an accumulator round needs RESIDENT AT ONCE.  3-D convs: the whole dz window.  K-chunks along the pseudo-depth
+    // axis (kdepth): the chunk planes of a round are consumed strictly one after the other and handed back right after
+    // their group, so one resident plane suffices and the ring may be shorter than the round (kdepth up to 10 chunks).
+    const int need = kdepth ? 1 : window;
     a.B = B; a.Do = Do; a.Ho = Ho; a.Wo = Wo;
     a.Cout_total = Cout_total;
     a.out_stride = out_stride; a.nsteps = nsteps; a.nclass_h = nclass_h; a.nclass_w = nclass_w;
@@ -884,16 +888,16 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         if (3072 + wbytes + 2048 >= SMEM_CAP) return 0;
         int r = (int)((SMEM_CAP - 3072 - wbytes - 1024) / plane);
         if (r > MAX_RING) r = MAX_RING;
-        return r >= window + 1 ? r : 0;
+        return r >= need + 1 ? r : 0;
     };
-    if (window > 6) return STB_E_UNSUPPORTED;
+    if (need > 6 || window > 16) return STB_E_UNSUPPORTED;
     for (;;) {
         size_t best_score = 0;
         for (int th = 16; th >= 4; th -= 4) {
             const int r = ring_for(Cn, th);
             if (!r) continue;
             const size_t plane = (size_t)a.nsub * (th + maxdh) * TWP * a.ROWB;
-            size_t inflight = (size_t)(r - window) * plane;
+            size_t inflight = (size_t)(r - need) * plane;
             if (inflight > 64 * 1024) inflight = 64 * 1024;   // enough to cover TMA latency; beyond that prefer tall tiles
                                                               // (>= 2 M-tiles per round keep both issuers / epilogue groups busy)
             if (inflight > best_score) { best_score = inflight; TH = th; R = r; }
@@ -909,7 +913,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             const int r = ring_for(Cn, force_th);
             if (r) { TH = force_th; R = r; }
         }
-        if (force_ring >= window + 1 && force_ring < R) R = force_ring;
+        if (force_ring >= need + 1 && force_ring < R) R = force_ring;
     }
     while (TH > 4 && TH - 4 >= nclass_h) TH -= 4;      // do not stage rows that do not exist
     a.R = R;
@@ -940,7 +944,8 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             const long long ctas = cols * stb_ceil_div(nsteps, dch);
             const int sms = num_sms / ns;                      // SMs that work on one output-channel slice
             const long long waves = (ctas + sms - 1) / sms;
-            const double eff = (double)ctas / (double)(waves * sms) * (double)dch / (double)(dch + window - 1);
+            const int halo = kdepth ? 0 : window - 1;         // redundant planes per depth chunk (none between images)
+            const double eff = (double)ctas / (double)(waves * sms) * (double)dch / (double)(dch + halo);
             if (eff > best + 1e-3) { best = eff; dchunk = dch; }
         }
     }

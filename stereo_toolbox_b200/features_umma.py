@@ -28,9 +28,15 @@ KDEPTH = os.environ.get("STB_UMMA_KDEPTH", "1") == "1"     # K-chunks accumulate
 class Conv2dPlan:
     """Tap tables + weight tiles of one Conv2d(+BN) for stb_conv3d_umma (dz = 0 everywhere)."""
 
-    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], cin_tensor: int, dtype, split: bool = False):
-        """``cin_tensor``: logical channels of the input tensor.  split: operand-split fp16 storage (aggregation_umma.split_pack)."""
+    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], cin_tensor: int, dtype, split: bool = False,
+                 cin_range=None, with_shift: bool = True):
+        """``cin_tensor``: logical channels of the input tensor.  split: operand-split fp16 storage (aggregation_umma.split_pack).
+        ``cin_range`` = (c0, c1): the plan covers input channels [c0, c1) of ``conv`` only (one addend of a convolution over a
+        channel concatenation, see UmmaGwcFeatures._convbn_multi); ``with_shift=False`` drops the BatchNorm shift (the scale
+        stays folded into the weights) for all but the last addend."""
         w = conv.weight.detach().float()
+        if cin_range is not None:
+            w = w[:, cin_range[0]:cin_range[1]]
         cout, cin, kh_, kw_ = w.shape
         assert kh_ == kw_ and conv.groups == 1 and conv.bias is None
         k, stride, pad, dil = kh_, conv.stride[0], conv.padding[0], conv.dilation[0]
@@ -44,6 +50,9 @@ class Conv2dPlan:
             self.shift = (bn.bias.detach().float() - bn.running_mean.float() * scale).contiguous()
         else:
             scale, self.shift = torch.ones(cout, device=w.device), None
+        if not with_shift:
+            self.shift = None
+        self.conv_cin = cin                                                  # real input channels (FLOP accounting)
         self.cin, self.cout, self.k, self.stride, self.pad, self.dil = cin, cout, k, stride, pad, dil
         self.in_stride = stride
         cin_st = 2 * cin if split else cin                                   # storage elements per pixel
@@ -58,7 +67,6 @@ class Conv2dPlan:
         if split:
             wexp = split_weight_exponent(tiles)
             tiles = split_pack(tiles * float(2.0 ** wexp))
-        self.wt = tiles.view(k * k, cpad, self.nk, kc).permute(0, 2, 1, 3).contiguous().to(dtype)
         self.nwtiles = k * k
         e = [kk * dil - pad for kk in range(k)]
         par = [x % stride for x in e]
@@ -66,27 +74,43 @@ class Conv2dPlan:
         mn = min(off)
         self.in_off = mn
         # kw-merge trades MMA work (3x fewer A-operand reads) for epilogue work (3 TMEM loads + 64 shuffles per 32 channels).
-        # A 2-D conv has 3x fewer taps per output than a 3-D one, so its epilogue already bounds it: merging is off for
-        # 2-D convs by default (extractor 9.0 -> 8.0 ms at the benchmark shape); STB_UMMA_KWMERGE2D = 1 | 32 | 64 re-enables
-        # it for all / only Cout = 32 / only Cout = 64 layers.
+        # A 2-D conv has 3x fewer taps per output than a 3-D one, so with single-fp16 storage its epilogue already bounds it:
+        # merging is off there by default (extractor 9.0 -> 8.0 ms at the benchmark shape); STB_UMMA_KWMERGE2D = 1 | 32 | 64
+        # re-enables it for all / only Cout = 32 / only Cout = 64 layers.  Split storage issues 3x the MMAs per tap against the
+        # same epilogue, so there the MMA side bounds the layer and merging (N = 3*Cn: 86-100 % instead of 40-67 % of the
+        # tensor rate) is on.
         m2d = KWMERGE_2D == "1" or KWMERGE_2D == str(cout)
-        self.merge = bool(KWMERGE and m2d and stride == 1 and k == 3 and cout <= 64)   # N >= 128 is math-bound without merging
+        if split:
+            self.merge = bool(KWMERGE and KWMERGE_2D != "off" and stride == 1 and k == 3)
+        else:
+            self.merge = bool(KWMERGE and m2d and stride == 1 and k == 3 and cout <= 64)   # N >= 128 is math-bound without merging
         # Cin beyond one K-chunk: instead of K-split passes chained through an fp32 workspace, lay the K-chunks along a
         # pseudo-depth axis (plane = image*nk + chunk, taps of chunk c carry dz = c) so they accumulate in TMEM inside
-        # one launch (conv3d_umma flags bit5).  Needs all nk*k*k weight tiles resident: taken for the 128-channel layers.
-        self.kdepth = bool(KDEPTH and self.nk > 1 and stride == 1 and not self.merge and self.nk * k * k <= 64 and self.nk <= 2)
+        # one launch (conv3d_umma flags bit5).  Needs all nk*k*k weight tiles of an output-channel slice resident.
+        taps_per_chunk = k if self.merge else k * k
+        if split:
+            # (weights of a 32-channel output slice must fit next to a short plane ring: 128->128 yes, the 320->128 lastconv no)
+            self.kdepth = bool(KDEPTH and self.nk > 1 and stride == 1 and self.nk * taps_per_chunk <= 64 and self.nk <= 10
+                               and self.nk * k * k * 32 * kc * 2 <= 150 * 1024)
+        else:
+            self.kdepth = bool(KDEPTH and self.nk > 1 and stride == 1 and not self.merge and self.nk * k * k <= 64 and self.nk <= 2)
+        tiles = tiles.view(k * k, cpad, self.nk, kc)
+        if self.kdepth:
+            # tiles ordered [chunk][tap]: the three kw tiles of a merged tap stay contiguous
+            self.wt = tiles.permute(2, 0, 1, 3).contiguous().to(dtype)
+            self.nwtiles = k * k * self.nk
+        else:
+            self.wt = tiles.permute(0, 2, 1, 3).contiguous().to(dtype)
         dz, dh, dw, sub, widx = [], [], [], [], []
         for c in range(self.nk if self.kdepth else 1):
             for a in range(k):
                 if self.merge:
-                    dz.append(0); dh.append(off[a] - mn); dw.append(0); sub.append(0); widx.append(a * k)
+                    dz.append(c); dh.append(off[a] - mn); dw.append(0); sub.append(0); widx.append(c * k * k + a * k)
                     continue
                 for b in range(k):
                     dz.append(c); dh.append(off[a] - mn); dw.append(off[b] - mn)
                     sub.append(par[a] * 2 + par[b] if stride == 2 else 0)
-                    widx.append((a * k + b) * self.nk + c if self.kdepth else a * k + b)
-        if self.kdepth:
-            self.nwtiles = k * k * self.nk           # weight tiles are [tap][chunk][Cpad][KC]: tile index = tap*nk + chunk
+                    widx.append(c * k * k + a * k + b)
         self.ntaps = len(dz)
         self.c = [_iarr(v) for v in (dz, dh, dw, sub, widx)]
         self.c_tb, self.c_te, self.c_z = _iarr([0]), _iarr([self.ntaps]), _iarr([0])
@@ -110,21 +134,22 @@ class UmmaGwcFeatures:
         self._ws = None
         self.prof = None              # bench.py's KernelProfiler: one bracket per layer ("conv2d_umma" family)
 
-    def _plan(self, conv, bn, cin_tensor):
+    def _plan(self, conv, bn, cin_tensor, cin_range=None, with_shift=True):
         ver = (conv.weight.data_ptr(), conv.weight._version, cin_tensor) + \
               (() if bn is None else (bn.weight._version, bn.bias._version, bn.running_mean._version,
                                       bn.running_var._version, bn.running_mean.data_ptr()))
-        hit = self._plans.get(id(conv))
+        key = (id(conv), cin_range, with_shift)
+        hit = self._plans.get(key)
         if hit is None or hit[0] != ver:
-            hit = (ver, Conv2dPlan(conv, bn, cin_tensor, self.dtype, self.split))
-            self._plans[id(conv)] = hit
+            hit = (ver, Conv2dPlan(conv, bn, cin_tensor, self.dtype, self.split, cin_range, with_shift))
+            self._plans[key] = hit
         return hit[1]
 
-    def conv(self, conv, bn, x, act="none", residual=None):
+    def conv(self, conv, bn, x, act="none", residual=None, cin_range=None, with_shift=True):
         """x [1, N, H, W, C] channels-last 16-bit (N images as depth) -> [1, N, Ho, Wo, Cout]."""
         _, N, H, W, Cst = x.shape
         C = Cst // self.cmul
-        p = self._plan(conv, bn, C)
+        p = self._plan(conv, bn, C, cin_range, with_shift)
         Ho, Wo = p.out_size(H), p.out_size(W)
         cout_t = (p.cout + 15) // 16 * 16 if self.split else p.cout          # split rows are whole 16-channel (hi, lo) blocks
         alloc = torch.zeros if cout_t != p.cout else torch.empty
@@ -142,10 +167,10 @@ class UmmaGwcFeatures:
                                  None, None, p.nwtiles, 1, p.c_tb, p.c_te, p.c_z, p.c_z, p.c_z, p.in_stride, 1, N, Ho, Wo,
                                  p.in_off, p.in_off, ACT[act], 0, p.flags, 0, _stream())
         if self.prof is not None and self.prof.enabled:
-            flops = 2.0 * p.k * p.k * conv.in_channels * p.cout * N * Ho * Wo
+            flops = 2.0 * p.k * p.k * p.conv_cin * p.cout * N * Ho * Wo
             nbytes = 2.0 * self.cmul * (x.numel() / self.cmul + out.numel() / self.cmul * (2 if residual is not None else 1))
             with self.prof.bracket("conv2d_umma", flops, nbytes,
-                                   detail=f"2d {conv.in_channels}->{p.cout} k{p.k} s{p.stride} d{p.dil} @{H}x{W}"):
+                                   detail=f"2d {p.conv_cin}->{p.cout} k{p.k} s{p.stride} d{p.dil} @{H}x{W}"):
                 call()
         else:
             call()
@@ -155,9 +180,22 @@ class UmmaGwcFeatures:
         return self.conv(seq[0], seq[1], x, act, residual)
 
     def _convbn_multi(self, seq, xs, act="none"):
-        """convbn on the channel concatenation of ``xs`` (the 320-channel lastconv input).  The conv kernel takes one
-        input tensor, so the pieces are concatenated here (a 16-bit copy; the fp32 NCHW copy is what is saved)."""
-        return self.conv(seq[0], seq[1], torch.cat(xs, dim=-1), act)
+        """convbn on the channel concatenation of ``xs`` (the 320-channel lastconv input).
+        Split storage: a convolution over a concatenation is the sum of the convolutions of its pieces, so it runs as one
+        launch per piece chained through the residual port (y1 = conv_a(l2); y2 = conv_b(l3) + y1; y = act(conv_c(l4) + shift
+        + y2)): every piece has few enough K-chunks to accumulate in TMEM (the 10-chunk whole does not fit and took ten
+        K-split passes through an fp32 workspace: 2.7 ms -> see profiles/), and the 320-channel concatenation is never built.
+        Single-fp16 storage: the pieces are concatenated (a 16-bit copy) and convolved in one call as before."""
+        if not self.split:
+            return self.conv(seq[0], seq[1], torch.cat(xs, dim=-1), act)
+        y, c0 = None, 0
+        for i, x in enumerate(xs):
+            c = x.shape[-1] // self.cmul
+            last = i == len(xs) - 1
+            y = self.conv(seq[0], seq[1], x, act if last else "none", residual=y, cin_range=(c0, c0 + c), with_shift=last)
+            c0 += c
+        assert c0 == seq[0].in_channels
+        return y
 
     def _block(self, blk, x):
         """BasicBlock (GwcNet/submodule.py:66-91): conv1+BN+ReLU, conv2+BN, + shortcut (no ReLU after the add)."""
@@ -212,7 +250,7 @@ class UmmaGwcFeatures:
         if concat_head is None and fe.concat_feature:
             concat_head = (fe.lastconv[0], fe.lastconv[2])
         if concat_head is not None:
-            y = self._convbn(concat_head[0], gwc, "relu")
+            y = self._convbn_multi(concat_head[0], (l2, l3, l4), "relu")
             y = self.conv(concat_head[1], None, y)
             cat_f = from_channels_last(y.view(N, h, w, y.shape[-1]), concat_head[1].out_channels, split=self.split)
             outs[0]["concat_feature"], outs[1]["concat_feature"] = cat_f[:B], cat_f[B:]
