@@ -135,35 +135,50 @@ __device__ __forceinline__ void store16(uint16_t* p, float v, int f16) {
     else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16(v);
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256).  An epilogue thread owns a whole output row (one voxel x 32 channels), so
+// the 32 lanes of a warp access 32 different rows: with 128-bit accesses every instruction touched HALF of 32 sectors (ncu on
+// the transposed convs: 2.0 store sectors per sector of data, l1tex LSU data pipe at 69-84 % -- the limiter of the memory-heavy
+// flavours); with 256-bit accesses an instruction moves whole 32-byte sectors and half as many wavefronts.
+__device__ __forceinline__ void stg256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                       uint32_t a6, uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4),
+                 "r"(a5), "r"(a6), "r"(a7)
+                 : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+
 // ---- 32 consecutive logical channels of one voxel <-> storage.  Plain 16-bit: 64 contiguous bytes.  SPLIT (fp16 hi + fp16 lo,
 // interleaved per 16 channels): 128 contiguous bytes  [hi 0..15 | lo 0..15 | hi 16..31 | lo 16..31].
 template <bool F16, bool SPLIT>
 __device__ __forceinline__ void add_residual32(float (&f)[32], const uint16_t* rp) {
     constexpr int f16 = F16 ? 1 : 0;
-    const uint4* p = reinterpret_cast<const uint4*>(rp);
     if constexpr (SPLIT) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {              // q = 16-channel block * 2 + which 8 of it
-            const uint4 hv = __ldg(p + (q >> 1) * 4 + (q & 1));
-            const uint4 lv = __ldg(p + (q >> 1) * 4 + 2 + (q & 1));
-            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+        for (int blk = 0; blk < 2; ++blk) {        // 16-channel block: 32 B of hi halves, then 32 B of lo halves
+            uint32_t hw[8], lw[8];
+            ldg256(rp + blk * 32, hw);
+            ldg256(rp + blk * 32 + 16, lw);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 const float2 h2 = unpack16(hw[j], 1), l2 = unpack16(lw[j], 1);
-                f[q * 8 + j * 2] += h2.x + l2.x;          // hi + lo is exact in fp32
-                f[q * 8 + j * 2 + 1] += h2.y + l2.y;
+                f[blk * 16 + j * 2] += h2.x + l2.x;          // hi + lo is exact in fp32
+                f[blk * 16 + j * 2 + 1] += h2.y + l2.y;
             }
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint4 rv = __ldg(p + i);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+        for (int i = 0; i < 2; ++i) {
+            uint32_t rw[8];
+            ldg256(rp + i * 16, rw);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 const float2 h2 = unpack16(rw[j], f16);
-                f[i * 8 + j * 2] += h2.x;
-                f[i * 8 + j * 2 + 1] += h2.y;
+                f[i * 16 + j * 2] += h2.x;
+                f[i * 16 + j * 2 + 1] += h2.y;
             }
         }
     }
@@ -171,33 +186,29 @@ __device__ __forceinline__ void add_residual32(float (&f)[32], const uint16_t* r
 template <bool F16, bool SPLIT>
 __device__ __forceinline__ void store32(const float (&f)[32], uint16_t* outp) {
     constexpr int f16 = F16 ? 1 : 0;
-    uint4* op = reinterpret_cast<uint4*>(outp);
     if constexpr (SPLIT) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t hw[4], lw[4];
+        for (int blk = 0; blk < 2; ++blk) {
+            uint32_t hw[8], lw[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float x0 = f[q * 8 + j * 2], x1 = f[q * 8 + j * 2 + 1];
+            for (int j = 0; j < 8; ++j) {
+                const float x0 = f[blk * 16 + j * 2], x1 = f[blk * 16 + j * 2 + 1];
                 const __half2 h = __floats2half2_rn(x0, x1);
                 const float2 hf = __half22float2(h);
                 const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
                 hw[j] = *reinterpret_cast<const uint32_t*>(&h);
                 lw[j] = *reinterpret_cast<const uint32_t*>(&l);
             }
-            op[(q >> 1) * 4 + (q & 1)] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            op[(q >> 1) * 4 + 2 + (q & 1)] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            stg256(outp + blk * 32, hw[0], hw[1], hw[2], hw[3], hw[4], hw[5], hw[6], hw[7]);
+            stg256(outp + blk * 32 + 16, lw[0], lw[1], lw[2], lw[3], lw[4], lw[5], lw[6], lw[7]);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            o.x = pack16(f[i * 8 + 0], f[i * 8 + 1], f16);
-            o.y = pack16(f[i * 8 + 2], f[i * 8 + 3], f16);
-            o.z = pack16(f[i * 8 + 4], f[i * 8 + 5], f16);
-            o.w = pack16(f[i * 8 + 6], f[i * 8 + 7], f16);
-            op[i] = o;
-        }
+        for (int i = 0; i < 2; ++i)
+            stg256(outp + i * 16, pack16(f[i * 16 + 0], f[i * 16 + 1], f16), pack16(f[i * 16 + 2], f[i * 16 + 3], f16),
+                   pack16(f[i * 16 + 4], f[i * 16 + 5], f16), pack16(f[i * 16 + 6], f[i * 16 + 7], f16),
+                   pack16(f[i * 16 + 8], f[i * 16 + 9], f16), pack16(f[i * 16 + 10], f[i * 16 + 11], f16),
+                   pack16(f[i * 16 + 12], f[i * 16 + 13], f16), pack16(f[i * 16 + 14], f[i * 16 + 15], f16));
     }
 }
 // storage index of logical channel c inside a split row
@@ -458,15 +469,56 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const float oscale = SPLIT ? a.oscale : 1.f;
         const int merge = (LEAN == 2 || LEAN == 4) ? 3 : (LEAN ? 1 : a.merge), Cn = a.Cn, nM = a.nM;
         uint32_t ground = 0;                        // accumulator round counter over all items (same order as the issuer)
+        // The memory-heavy flavours (transposed convs: 8 output blocks per M-tile, each with a residual row to read; K-split
+        // passes reading their fp32 partial sums) were bound by the LATENCY of those loads: a block loads, waits, computes,
+        // stores, and only then the next block's loads are issued (fp16 64->32 s2T: 0.66 ms for an MMA time of 0.14 ms and a
+        // HBM floor of 0.26 ms).  Registers for a software pipeline do not exist (168-register cap), so the rows a round will
+        // read are pulled into L2 one round ahead with prefetch.global.L2 -- no registers, no completion to wait for.
+        constexpr bool PREFETCH = LEAN == 0 || LEAN == 1 || LEAN == 3 || LEAN == 5;
+        const bool want_pf = PREFETCH && (a.residual != nullptr || partial != nullptr);
+        auto prefetch_round = [&](const UTile& u, int s, const UClass& cl) {
+            for (int item = egroup; item < items; item += 2) {
+                int m, od, oh, ow, jh_l, jw_l;
+                bool ok;
+                if (LEAN == 5) {
+                    m = item >> 2;
+                    const int pb = item & 3, q = 128 * m + q4 * 32 + lane;
+                    jh_l = q / TWP; jw_l = q % TWP;
+                    od = s * a.out_stride + (pb >> 1); oh = (u.jh0 + jh_l) * 2 + (pb & 1); ow = (u.jw0 + jw_l) * 2;
+                } else {
+                    m = nblk_e == 8 ? (item >> 3) : item;
+                    const int blk = nblk_e == 8 ? (item & 7) : 0, q = 128 * m + q4 * 32 + lane;
+                    jh_l = q / TWP; jw_l = q % TWP;
+                    od = s * a.out_stride + (nblk_e == 8 ? (blk >> 2) : cl.od0);
+                    oh = (u.jh0 + jh_l) * a.out_stride + (nblk_e == 8 ? ((blk >> 1) & 1) : cl.oh0);
+                    ow = (u.jw0 + jw_l) * a.out_stride + (nblk_e == 8 ? (blk & 1) : cl.ow0);
+                }
+                ok = jh_l < a.TH && jw_l < a.TW && (u.jh0 + jh_l) < a.nclass_h && (u.jw0 + jw_l) < a.nclass_w && od < a.Do &&
+                     oh < a.Ho && ow < a.Wo;
+                if (!ok) continue;
+                const size_t vox = (((size_t)u.b * a.Do + od) * a.Ho + oh) * a.Wo + ow;
+                for (int c0 = 0; c0 < Cn; c0 += 32) {
+                    const size_t eoff = vox * ostride_w + cout_off + c0;
+                    if (a.residual) {
+                        const uint16_t* rp = reinterpret_cast<const uint16_t*>(a.residual) + eoff * K16;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+                        if (LEAN == 5 && SPLIT) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 64));   // the pair's second voxel
+                    }
+                    if (partial) asm volatile("prefetch.global.L2 [%0];" ::"l"(partial + eoff));
+                }
+            }
+        };
         for (int tile = tile0; active && tile < a.ntiles && !(dbg & 4); tile += tstride) {
           const UTile u = decode_tile(a, tile);
           const int b = u.b, jh0 = u.jh0, jw0 = u.jw0;
+          if (want_pf) prefetch_round(u, u.s_lo, a.cls[0]);
           int e_si = 0, e_c = 0;                      // (step, class) of the round, kept incrementally (no division)
           for (int round = 0; round < u.nouts; ++round, ++ground) {
             const int buf = ground & 1;
             const int s = u.s_lo + e_si;
             const UClass cl = a.cls[e_c];
             if (++e_c == a.nclass) { e_c = 0; ++e_si; }
+            if (want_pf && round + 1 < u.nouts) prefetch_round(u, u.s_lo + e_si, a.cls[e_c]);   // (e_si, e_c) already name the NEXT round
             mbar_wait_warp(&tmem_full[buf], (ground >> 1) & 1);
             tc_fence_after();
             const bool trace = !LEAN && (int)ground < trace_rounds && warp == 3 && lane == 0;
@@ -589,11 +641,12 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     if (inb && full32) {
                         // ---------------- vector path: 32 complete channels
                         if (partial) {
-                            const float4* pp = reinterpret_cast<const float4*>(partial + eoff);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 pv = __ldg(pp + i);
-                                f[i * 4] += pv.x; f[i * 4 + 1] += pv.y; f[i * 4 + 2] += pv.z; f[i * 4 + 3] += pv.w;
+                            for (int i = 0; i < 4; ++i) {
+                                uint32_t pv[8];
+                                ldg256(partial + eoff + i * 8, pv);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[i * 8 + j] += __uint_as_float(pv[j]);
                             }
                         }
                         if constexpr (SPLIT) {
@@ -616,9 +669,12 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         for (int i = 0; i < 32; ++i) f[i] = stb_act(f[i], ACT);
                         if (trace && item == egroup && c0 == 0) trace_buf[ground * 8 + 7] = clock64();     // arithmetic done, stores next
                         if (out_fp32) {
-                            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + eoff);
+                            float* op = reinterpret_cast<float*>(a.out) + eoff;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) op[i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+                            for (int i = 0; i < 4; ++i)
+                                stg256(op + i * 8, __float_as_uint(f[i * 8]), __float_as_uint(f[i * 8 + 1]), __float_as_uint(f[i * 8 + 2]),
+                                       __float_as_uint(f[i * 8 + 3]), __float_as_uint(f[i * 8 + 4]), __float_as_uint(f[i * 8 + 5]),
+                                       __float_as_uint(f[i * 8 + 6]), __float_as_uint(f[i * 8 + 7]));
                         } else {
                             store32<F16, SPLIT>(f, reinterpret_cast<uint16_t*>(a.out) + eoff * K16);
                         }
