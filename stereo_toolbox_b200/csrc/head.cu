@@ -85,24 +85,19 @@ upsample_softargmin_x4_kernel(const float* __restrict__ cost, float* __restrict_
     const size_t plane = (size_t)H * W;
     const float* base = cost + (size_t)b * D * plane;
     const float a00 = (1.f - th) * (1.f - tw), a01 = (1.f - th) * tw, a10 = th * (1.f - tw), a11 = th * tw;
-    float m = -INFINITY;
+    float m = -INFINITY, pv = 0.f;
     for (int d = 0; d < D; ++d) {
         const float* p = base + (size_t)d * plane;
         float v = a00 * __ldg(p + h0 * W + w0) + a01 * __ldg(p + h0 * W + w1) + a10 * __ldg(p + h1 * W + w0) +
                   a11 * __ldg(p + h1 * W + w1);
         col[d * HEAD_THREADS + threadIdx.x] = v;
+        // softmax shift = maximum over the INTERPOLATED bins (see the generic kernel): between two knots the bins are linear
+        // in td, so only the outermost two (td = 0.125, 0.875) can be the largest; bins 0, 1 sit on knot 0 and the last two
+        // on knot D-1.  Tracked here, while the knots pass through registers (no second pass over the column).
+        m = d == 0 ? v : fmaxf(m, fmaxf(fmaf(0.125f, v, __fmul_rn(0.875f, pv)), fmaf(0.875f, v, __fmul_rn(0.125f, pv))));
+        pv = v;
     }
-    {   // maximum over the interpolated bins: between two knots the bins are linear in td, so only the outermost two
-        // (td = 0.125, 0.875) can be the largest; bins 0, 1 sit on knot 0 and the last two on knot D-1
-        float p0 = col[threadIdx.x];
-        m = p0;
-        for (int k = 0; k + 1 < D; ++k) {
-            const float p1 = col[(k + 1) * HEAD_THREADS + threadIdx.x];
-            m = fmaxf(m, fmaxf(fmaf(0.125f, p1, __fmul_rn(0.875f, p0)), fmaf(0.875f, p1, __fmul_rn(0.125f, p0))));
-            p0 = p1;
-        }
-        m = fmaxf(m, p0);
-    }
+    m = fmaxf(m, pv);
     float c0 = col[threadIdx.x];
     // bins 0 and 1: td = 0, the generic kernel computes 1*c0 + 0*c1 = c0
     float e = __expf(c0 - m);
