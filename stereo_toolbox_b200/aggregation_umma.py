@@ -25,6 +25,7 @@ ES_VARIANT = int(os.environ.get("STB_TMA_ES_VARIANT", "0"))      # box extent co
 FORCE_SIMT = os.environ.get("STB_UMMA_FORCE_SIMT", "0") == "1"
 KWMERGE = os.environ.get("STB_UMMA_KWMERGE", "1") == "1"          # merge the 3 kw taps along N (N = 3*Cout) for k3 s1 convs
 DECONV_MERGE = os.environ.get("STB_UMMA_DECONV_MERGE", "1") == "1"  # transposed conv: 8 parity classes in one accumulator round
+KDEPTH3D = os.environ.get("STB_UMMA_KDEPTH3D", "1") == "1"          # 3-D layers: K-chunks accumulated in TMEM when the weights fit
 SIMT_STRIDE2 = os.environ.get("STB_UMMA_SIMT_STRIDE2", "0") == "1"   # keep strided convs on the CUDA-core companion
 TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp16x2": torch.float16}
 SPLIT_FLAG = 64      # stb_conv3d_umma flags bit6: operand-split fp16 ("fp16x2")
@@ -219,6 +220,38 @@ class UmmaPlan:
             self.out_stride = stride
         if max(dh) > 3 or max(dw) > 3 or len(dz) > 64:
             return False
+        # ---- all K-chunks of the layer in ONE launch (conv3d_umma flags bit5, 3-D form): pseudo-plane = depth*nk + chunk, the
+        # taps of chunk c carry dz*nk + c, so the chunks accumulate in TMEM instead of chaining K-split passes through an fp32
+        # partial (64->32 s2T on fp16x2: two passes, 1.47 GB of partial written and read back per call).  Needs the weight tiles
+        # of ALL chunks of an output-channel slice resident next to a ring of (window*nk + 1) chunk slots; the merged
+        # transposed conv may narrow the slice to 16 channels (own epilogue instantiation, LEAN 6).
+        self.kdepth = False
+        if KDEPTH3D and self.split and nk > 1 and in_stride == 1 and len(tb) == 1 and len(dz) * nk <= 64:
+            window = max(dz) - min(dz) + 1
+            slot = (4 + max(dh)) * 32 * kc * 2
+            ring = (window * nk + 1) * slot
+            fits = lambda cn: 3072 + ((self.nwtiles * nk * cn * kc * 2 + 1023) & ~1023) + 1024 + ring <= 227 * 1024
+            cblocks = 8 if self.deconv_merge else (3 if self.merge else 1)
+            ok_full = cpad * cblocks <= 256 and fits(cpad)
+            ok_16 = self.deconv_merge and cpad % 16 == 0 and cout == cpad and fits(16)
+            if window * nk <= 6 and (ok_full or ok_16):
+                n0 = len(dz)
+                base = (list(dz), list(dh), list(dw), list(sub), list(widx), None if nblk is None else list(nblk),
+                        None if cls0 is None else list(cls0))
+                dz, dh, dw, sub, widx = [], [], [], [], []
+                nblk = None if base[5] is None else []
+                cls0 = None if base[6] is None else []
+                for c in range(nk):
+                    for t in range(n0):
+                        dz.append(base[0][t] * nk + c); dh.append(base[1][t]); dw.append(base[2][t]); sub.append(base[3][t])
+                        widx.append(c * self.nwtiles + base[4][t])
+                        if nblk is not None:
+                            nblk.append(base[5][t]); cls0.append(base[6][t])
+                te = [len(dz)]
+                # tiles ordered [chunk][tile]: runs of consecutive tiles (merged taps) stay contiguous
+                self.wt = tiles.view(self.nwtiles, cpad, nk, kc).permute(2, 0, 1, 3).contiguous().to(self.dtype)
+                self.nwtiles *= nk
+                self.kdepth = True
         self.ntaps, self.nclass = len(dz), len(tb)
         self.c_dz, self.c_dh, self.c_dw, self.c_sub, self.c_widx = _iarr(dz), _iarr(dh), _iarr(dw), _iarr(sub), _iarr(widx)
         self.c_nblk = _iarr(nblk) if nblk is not None else None
@@ -347,7 +380,7 @@ class UmmaBackend:
         with self.prof.bracket(fam, fl, by, detail=detail):
             if plan.umma_ok:
                 nsteps, nh, nw = (Di, Hi, Wi) if plan.tr else (Do, Ho, Wo)
-                ws = self._workspace(B * Do * Ho * Wo * cout_t, x.device) if plan.nk > 1 else None
+                ws = self._workspace(B * Do * Ho * Wo * cout_t, x.device) if (plan.nk > 1 and not plan.kdepth) else None
                 _lib.call("stb_conv3d_umma", _p(x), _p(plan.wt), _p(plan.shift), _p(residual), _p(out), _p(ws),
                           self.f16, B, Cst, plan.kc, Di, Hi, Wi, cout_t, plan.cout, Do, Ho, Wo, plan.ntaps,
                           plan.c_dz, plan.c_dh, plan.c_dw, plan.c_sub, plan.c_widx, plan.c_nblk, plan.c_cls0,
@@ -355,7 +388,7 @@ class UmmaBackend:
                           plan.c_tb, plan.c_te, plan.c_od0, plan.c_oh0, plan.c_ow0, plan.in_stride, plan.out_stride,
                           nsteps, nh, nw, plan.in_off, plan.in_off, ACT[act], int(out_fp32),
                           BO_MODE | (ES_VARIANT << 1) | (4 if plan.merge else 0) | (8 if plan.deconv_merge else 0)
-                          | ((SPLIT_FLAG | (plan.wexp << 16)) if self.split else 0),
+                          | (32 if plan.kdepth else 0) | ((SPLIT_FLAG | (plan.wexp << 16)) if self.split else 0),
                           self.dchunk, _stream())
             else:
                 assert not self.split

@@ -211,6 +211,53 @@ __device__ __forceinline__ void store32(const float (&f)[32], uint16_t* outp) {
                    pack16(f[i * 16 + 12], f[i * 16 + 13], f16), pack16(f[i * 16 + 14], f[i * 16 + 15], f16));
     }
 }
+// ---- 16 consecutive logical channels (one storage block): 32 bytes plain, 64 bytes split [hi 0..15 | lo 0..15]
+template <bool F16, bool SPLIT>
+__device__ __forceinline__ void add_residual16(float (&f)[16], const uint16_t* rp) {
+    constexpr int f16 = F16 ? 1 : 0;
+    uint32_t hw[8];
+    ldg256(rp, hw);
+    if constexpr (SPLIT) {
+        uint32_t lw[8];
+        ldg256(rp + 16, lw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 h2 = unpack16(hw[j], 1), l2 = unpack16(lw[j], 1);
+            f[j * 2] += h2.x + l2.x;
+            f[j * 2 + 1] += h2.y + l2.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 h2 = unpack16(hw[j], f16);
+            f[j * 2] += h2.x;
+            f[j * 2 + 1] += h2.y;
+        }
+    }
+}
+template <bool F16, bool SPLIT>
+__device__ __forceinline__ void store16v(const float (&f)[16], uint16_t* outp) {
+    constexpr int f16 = F16 ? 1 : 0;
+    uint32_t hw[8];
+    if constexpr (SPLIT) {
+        uint32_t lw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float x0 = f[j * 2], x1 = f[j * 2 + 1];
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+            lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        stg256(outp, hw[0], hw[1], hw[2], hw[3], hw[4], hw[5], hw[6], hw[7]);
+        stg256(outp + 16, lw[0], lw[1], lw[2], lw[3], lw[4], lw[5], lw[6], lw[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hw[j] = pack16(f[j * 2], f[j * 2 + 1], f16);
+        stg256(outp, hw[0], hw[1], hw[2], hw[3], hw[4], hw[5], hw[6], hw[7]);
+    }
+}
 // storage index of logical channel c inside a split row
 __device__ __forceinline__ int split_idx(int c) { return ((c >> 4) << 5) + (c & 15); }
 
@@ -347,7 +394,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     if (a.kdepth > 0) {
                         // 2-D conv with Cin = kdepth K-chunks: pseudo-plane P = image*kdepth + chunk; the taps of chunk c
                         // carry dz = c, so all chunks accumulate in TMEM inside one launch (no fp32 workspace round trip)
-                        const int P = u.p_first + n, img = P / a.kdepth, chunk = P - img * a.kdepth;
+                        const int P = u.p_first + n, img = (P + 64 * a.kdepth) / a.kdepth - 64, chunk = P - img * a.kdepth;   // floor division: 3-D planes may be negative (padding)
                         tma_load_5d(dst, &tm_x, &plane_full[slot], chunk * (a.ROWB >> 1), iw0, ih0, img, u.b);
                     } else {
                         for (int sb = 0; sb < a.nsub; ++sb)       // sub-tile sb = (h parity, w parity) for stride 2
@@ -454,7 +501,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // ================================ epilogue warps ================================
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
         const int egroup = (warp - 3) >> 2;         // epilogue group 0/1 drains M-tiles m = egroup, egroup+2, ...
-        const int nblk_e = LEAN == 3 ? 8 : LEAN == 5 ? 4 : (LEAN ? 1 : (a.cblocks == 8 ? 8 : 1));     // merged transposed conv: all 8 parity classes in one round (LEAN 5: as 4 w-pairs)
+        const int nblk_e = LEAN == 3 ? 8 : (LEAN == 5 || LEAN == 6) ? 4 : (LEAN ? 1 : (a.cblocks == 8 ? 8 : 1));     // merged transposed conv: all 8 parity classes in one round (LEAN 5: as 4 w-pairs)
         const int items = a.nM * nblk_e;               // (M-tile, class block) work items per round, dealt to 2 groups
         const bool active = egroup < (items >= 2 ? 2 : 1);
         const size_t ostride_w = (size_t)a.Cout_total;
@@ -474,13 +521,13 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // stores, and only then the next block's loads are issued (fp16 64->32 s2T: 0.66 ms for an MMA time of 0.14 ms and a
         // HBM floor of 0.26 ms).  Registers for a software pipeline do not exist (168-register cap), so the rows a round will
         // read are pulled into L2 one round ahead with prefetch.global.L2 -- no registers, no completion to wait for.
-        constexpr bool PREFETCH = LEAN == 0 || LEAN == 1 || LEAN == 3 || LEAN == 5;
+        constexpr bool PREFETCH = LEAN == 0 || LEAN == 1 || LEAN == 3 || LEAN == 5 || LEAN == 6;
         const bool want_pf = PREFETCH && (a.residual != nullptr || partial != nullptr);
         auto prefetch_round = [&](const UTile& u, int s, const UClass& cl) {
             for (int item = egroup; item < items; item += 2) {
                 int m, od, oh, ow, jh_l, jw_l;
                 bool ok;
-                if (LEAN == 5) {
+                if (LEAN == 5 || LEAN == 6) {
                     m = item >> 2;
                     const int pb = item & 3, q = 128 * m + q4 * 32 + lane;
                     jh_l = q / TWP; jw_l = q % TWP;
@@ -503,6 +550,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         const uint16_t* rp = reinterpret_cast<const uint16_t*>(a.residual) + eoff * K16;
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
                         if (LEAN == 5 && SPLIT) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 64));   // the pair's second voxel
+                        if (LEAN == 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + ostride_w * K16));
                     }
                     if (partial) asm volatile("prefetch.global.L2 [%0];" ::"l"(partial + eoff));
                 }
@@ -524,6 +572,44 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const bool trace = !LEAN && (int)ground < trace_rounds && warp == 3 && lane == 0;
             if (trace) trace_buf[ground * 8 + 4] = clock64();
             for (int item = egroup; item < items && !(dbg & 2); item += 2) {
+              if (LEAN == 6) {
+                // Merged transposed conv on a 16-channel output slice (Cn == 16: all K-chunks of the layer accumulate in TMEM because
+                // the weights of a 16-channel slice fit next to the chunk ring, no K-split pass through an fp32 partial).  The two
+                // w-parity classes of one (d,h) parity are ADJACENT 16-column blocks, so one 32-column TMEM read holds the thread's
+                // two output voxels (ow, ow + 1) x 16 channels; each is one whole 16-channel storage block of its voxel row.
+                const int m = item >> 2, pb = item & 3;
+                const int od = s * a.out_stride + (pb >> 1);
+                const int q = 128 * m + q4 * 32 + lane;
+                const int jh_l = q / TWP, jw_l = q % TWP;
+                const int jh = jh0 + jh_l, jw = jw0 + jw_l;
+                const bool valid = (jh_l < a.TH) && (jw_l < a.TW) && (jh < a.nclass_h) && (jw < a.nclass_w) && (od < a.Do);
+                const int oh = jh * 2 + (pb & 1), ow = jw * 2;
+                const bool in0 = valid && oh < a.Ho && ow < a.Wo, in1 = in0 && ow + 1 < a.Wo;
+                const size_t eoff = ((((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow) * ostride_w + cout_off;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * nM + m) * Cn * 8 + pb * 2 * Cn);
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld_32x32(taddr, v);
+                tmem_ld_wait();
+                if (item + 2 >= items) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!(h ? in1 : in0)) continue;
+                    const size_t off = eoff + (size_t)h * ostride_w;
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = SPLIT ? fmaf(__uint_as_float(v[h * 16 + i]), oscale, sh0[i]) : __uint_as_float(v[h * 16 + i]) + sh0[i];
+                    if (a.residual) add_residual16<F16, SPLIT>(f, reinterpret_cast<const uint16_t*>(a.residual) + off * K16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = stb_act(f[i], ACT);
+                    store16v<F16, SPLIT>(f, reinterpret_cast<uint16_t*>(a.out) + off * K16);
+                }
+                continue;
+              }
               if (LEAN == 5) {
                 // Merged transposed conv, the two w-parity classes of one (d,h) parity handled together: a thread's two output
                 // voxels (ow, ow + 1) are adjacent in memory, so it writes 2 x Cout_total contiguous channels (128 B at 32
@@ -778,6 +864,12 @@ int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& t
         if (t2pair && lean && a.cblocks == 8 && a.merge == 1 && a.Cn == 32 && a.shift)
             return launch_one_impl<ACT, F16, 5, SPLIT>(grid, smem, st, tx, tw, a);
     }
+    // merged transposed conv on 16-channel output slices (all K-chunks in TMEM, see LEAN 6 in the epilogue)
+    if constexpr (ACT == STB_ACT_RELU && SPLIT) {
+        if (!a.debug && !g_trace_armed && !a.partial && !a.out_fp32 && a.cblocks == 8 && a.merge == 1 && a.Cn == 16 &&
+            a.Cn_valid == 16 && a.shift)
+            return launch_one_impl<ACT, F16, 6, SPLIT>(grid, smem, st, tx, tw, a);
+    }
     if (lean && a.cblocks == 8 && a.merge == 1) return launch_one_impl<ACT, F16, 3, SPLIT>(grid, smem, st, tx, tw, a);
     if (lean && a.cblocks == 3 && a.merge == 3) return launch_one_impl<ACT, F16, 2, SPLIT>(grid, smem, st, tx, tw, a);
     if (lean && a.cblocks == 1 && a.merge == 1) return launch_one_impl<ACT, F16, 1, SPLIT>(grid, smem, st, tx, tw, a);
@@ -834,7 +926,9 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     const float wscale_inv = ldexpf(1.f, -((flags >> 16) & 127));
     if (split && (!f16 || (KC != 32 && KC != 64) || (Cout_total % 16 && !out_fp32))) return STB_E_UNSUPPORTED;
     const int kdepth = (flags & 32) ? Cin / KC : 0; // flags bit5: K-chunks along a pseudo-depth axis, accumulated in TMEM (2-D convs)
-    if (kdepth && (!(flags & 16) || in_stride != 1 || out_stride != 1)) return STB_E_UNSUPPORTED;
+    // (3-D layers too: pseudo-plane = depth*kdepth + chunk, taps carry dz*kdepth + chunk; unit input stride only)
+    if (kdepth && in_stride != 1) return STB_E_UNSUPPORTED;
+    const bool kdepth2d = kdepth && (flags & 16);
     const int nk = kdepth ? 1 : Cin / KC;          // K-split passes
     if (nk > 1 && !ws) return STB_E_BADARG;        // needs the fp32 partial workspace [B,Do,Ho,Wo,Cout_total]
     UArgs a;
@@ -924,7 +1018,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     // Planes an accumulator round needs RESIDENT AT ONCE.  3-D convs: the whole dz window.  K-chunks along the pseudo-depth
     // axis (kdepth): the chunk planes of a round are consumed strictly one after the other and handed back right after
     // their group, so one resident plane suffices and the ring may be shorter than the round (kdepth up to 10 chunks).
-    const int need = kdepth ? 1 : window;
+    const int need = kdepth2d ? 1 : window;
     a.B = B; a.Do = Do; a.Ho = Ho; a.Wo = Wo;
     a.Cout_total = Cout_total;
     a.out_stride = out_stride; a.nsteps = nsteps; a.nclass_h = nclass_h; a.nclass_w = nclass_w;
@@ -1000,7 +1094,8 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             const long long ctas = cols * stb_ceil_div(nsteps, dch);
             const int sms = num_sms / ns;                      // SMs that work on one output-channel slice
             const long long waves = (ctas + sms - 1) / sms;
-            const int halo = kdepth ? 0 : window - 1;         // redundant planes per depth chunk (none between images)
+            // redundant depth steps per depth chunk (none between the images of a 2-D conv)
+            const int halo = kdepth ? (kdepth2d ? 0 : (window - kdepth) / kdepth) : window - 1;
             const double eff = (double)ctas / (double)(waves * sms) * (double)dch / (double)(dch + halo);
             if (eff > best + 1e-3) { best = eff; dchunk = dch; }
         }

@@ -80,6 +80,9 @@ SCONVS = [
     (32, 64, 3, 2, 1, False, "relu", False, (6, 10, 22)),       # strided conv: parity sub-tiles
     (64, 128, 3, 2, 1, False, "relu", False, (4, 8, 70)),
     (32, 32, 3, 1, 1, False, "mish", True, (3, 20, 64)),
+    (64, 64, 1, 1, 0, False, "none", True, (4, 10, 33)),        # k1, both K-chunks accumulated in TMEM (3-D pseudo-depth chunks)
+    (64, 32, 3, 2, 1, True, "relu", True, (9, 13, 70)),         # merged transposed conv on 16-channel slices, several tiles / depth chunks
+    (64, 32, 3, 2, 1, True, "none", False, (3, 5, 17)),         # same plan through the generic epilogue
 ]
 
 

@@ -1,0 +1,132 @@
+"""Host-side tap tables of the tcgen05 convolution (aggregation_umma.UmmaPlan) checked WITHOUT a GPU: a few lines of
+numpy-style torch re-state what csrc/conv3d_umma.cu does with a plan (plane / chunk / sub-tile addressing, merged taps,
+parity-class blocks, K-chunks along the pseudo-depth axis) and the result is compared with torch's own convolution in
+fp64.  This is test infrastructure (it never runs on the product path): it pins the PLAN, the -m gpu tests pin the kernel.
+"""
+import pytest
+import torch
+import torch.nn as nn
+
+from stereo_toolbox_b200.aggregation_umma import UmmaPlan, split_pack, split_unpack
+
+
+def emulate(plan: UmmaPlan, x: torch.Tensor) -> torch.Tensor:
+    """x [B,Cin,D,H,W] fp64 -> conv output [B,Cout,Do,Ho,Wo] fp64 following the plan's tables the way the kernel does."""
+    B, Cin, Di, Hi, Wi = x.shape
+    split = plan.split
+    cst = 2 if split else 1
+    # storage view of the input: channels-last, (hi, lo) interleaved per 16 channels when split
+    xcl = x.permute(0, 2, 3, 4, 1).float()
+    xs = (split_pack(xcl) if split else xcl.half()).double()                     # [B,D,H,W,Cst]
+    Do, Ho, Wo = plan.out_size(Di), plan.out_size(Hi), plan.out_size(Wi)
+    nk, kc = plan.nk, plan.kc
+    kdepth = getattr(plan, "kdepth", False)
+    wt = plan.wt.double()                  # [tile][nk][cpad][kc]  or (kdepth)  [nk*tile][1..][cpad][kc] flattened below
+    if kdepth:
+        wt = wt.reshape(plan.nwtiles, 1, plan.cpad, kc)
+    ntaps = plan.ntaps
+    dz, dh, dw, sub, widx = (list(plan.c_dz), list(plan.c_dh), list(plan.c_dw), list(plan.c_sub), list(plan.c_widx))
+    merge = 3 if plan.merge else 1
+    nblk = list(plan.c_nblk) if plan.c_nblk is not None else [merge] * ntaps
+    cls0 = list(plan.c_cls0) if plan.c_cls0 is not None else [0] * ntaps
+    tb, te = list(plan.c_tb), list(plan.c_te)
+    od0, oh0, ow0 = list(plan.c_od0), list(plan.c_oh0), list(plan.c_ow0)
+    in_s, out_s = plan.in_stride, plan.out_stride
+    nsteps, nh, nw = (Di, Hi, Wi) if plan.tr else (Do, Ho, Wo)
+    sd_in = nk if kdepth else in_s
+    out = torch.zeros(B, Do, Ho, Wo, plan.cpad, dtype=torch.float64)
+    cb = 8 if plan.deconv_merge else merge
+
+    def gather(P, chunk_k, hh, ww):
+        """rows of the A operand: input storage elements [B, nh, nw, kc] at plane P, positions (hh[jh], ww[jw])."""
+        if kdepth:
+            depth, chunk = P // nk, P % nk        # floor division
+        else:
+            depth, chunk = P, chunk_k
+        a = torch.zeros(B, nh, nw, kc, dtype=torch.float64)
+        if depth < 0 or depth >= Di:
+            return a
+        hv = (hh >= 0) & (hh < Hi)
+        wv = (ww >= 0) & (ww < Wi)
+        src = xs[:, depth][:, hh.clamp(0, Hi - 1)][:, :, ww.clamp(0, Wi - 1)][..., chunk * kc:(chunk + 1) * kc]
+        return src * (hv.view(1, -1, 1, 1) & wv.view(1, 1, -1, 1))
+
+    jh, jw = torch.arange(nh), torch.arange(nw)
+    for s in range(nsteps):
+        for c in range(len(tb)):
+            acc = torch.zeros(B, nh, nw, cb, plan.cpad, dtype=torch.float64)
+            for kp in range(1 if kdepth else nk):
+                for t in range(tb[c], te[c]):
+                    P = s * sd_in + dz[t]
+                    for j in range(nblk[t]):
+                        shift_w = j if (merge == 3) else 0            # kw-merged tiles: column block j is realigned by j lanes
+                        hh = (jh + plan.in_off) * in_s + (sub[t] >> 1) + in_s * dh[t]
+                        ww = (jw + plan.in_off) * in_s + (sub[t] & 1) + in_s * (dw[t] + shift_w)
+                        a = gather(P, kp, hh, ww)
+                        w = wt[widx[t] + j, 0 if kdepth else kp]                      # [cpad][kc]
+                        # (split: hi*hi + hi*lo + lo*hi = the product of the joined values minus lo*lo, below fp32 rounding)
+                        blk = cls0[t] + (0 if merge == 3 else j)
+                        contrib = torch.einsum("bhwk,ok->bhwo", _join(a, split), _join(w, split))
+                        acc[:, :, :, blk if merge != 3 else 0] += contrib
+            for blk in range(cb if plan.deconv_merge else 1):
+                cd, ch, cw = ((blk >> 2, (blk >> 1) & 1, blk & 1) if plan.deconv_merge else (od0[c], oh0[c], ow0[c]))
+                od = s * out_s + cd
+                if od >= Do:
+                    continue
+                oh, ow = jh * out_s + ch, jw * out_s + cw
+                okh, okw = oh < Ho, ow < Wo
+                out[:, od][:, oh[okh][:, None], ow[okw][None, :]] = acc[:, :, :, blk][:, okh][:, :, okw]
+    out = out * (2.0 ** -plan.wexp)
+    if plan.shift is not None:
+        out[..., :plan.cout] += plan.shift.double()
+    return out[..., :plan.cout].permute(0, 4, 1, 2, 3)
+
+
+def _join(t, split):
+    """storage elements along the last axis -> logical values (hi + lo) when split."""
+    if not split:
+        return t
+    c2 = t.shape[-1]
+    v = t.reshape(*t.shape[:-1], c2 // 32, 2, 16)
+    return (v[..., 0, :] + v[..., 1, :]).reshape(*t.shape[:-1], c2 // 2)
+
+
+CASES = [
+    # cin, cout, k, stride, pad, transposed, split, (D,H,W), expect_kdepth
+    (32, 32, 3, 1, 1, False, True, (3, 5, 6), False),
+    (64, 32, 3, 1, 1, False, True, (3, 4, 5), False),        # K-split passes
+    (64, 64, 1, 1, 0, False, True, (2, 4, 5), True),         # k1: both K-chunks in TMEM
+    (64, 32, 3, 2, 1, True, True, (2, 3, 4), True),          # merged transposed conv, chunks along the pseudo-depth axis
+    (128, 64, 3, 2, 1, True, True, (2, 2, 3), False),
+    (32, 64, 3, 2, 1, False, True, (4, 6, 6), False),        # strided conv: parity sub-tiles
+    (64, 32, 3, 2, 1, True, False, (2, 3, 4), False),        # single fp16
+    (32, 32, 3, 1, 1, False, False, (3, 4, 5), False),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,tr,split,dims,want_kdepth", CASES)
+def test_plan_tables_reproduce_the_convolution(cin, cout, k, stride, pad, tr, split, dims, want_kdepth):
+    g = torch.Generator().manual_seed(cin * 7 + cout + k + stride)
+    D, H, W = dims
+    opad = 1 if (tr and k == 3) else 0
+    conv = (nn.ConvTranspose3d(cin, cout, k, stride=stride, padding=pad, output_padding=opad, bias=False) if tr
+            else nn.Conv3d(cin, cout, k, stride, pad, bias=False))
+    bn = nn.BatchNorm3d(cout)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (cin * k ** 3)) ** 0.5)
+        bn.weight.copy_(0.75 + 0.5 * torch.rand(cout, generator=g)); bn.bias.copy_(0.1 * torch.randn(cout, generator=g))
+        bn.running_mean.copy_(0.1 * torch.randn(cout, generator=g)); bn.running_var.copy_(0.5 + torch.rand(cout, generator=g))
+    bn.eval()
+    plan = UmmaPlan(conv, bn, cin, torch.float16, split)
+    assert plan.umma_ok
+    assert bool(getattr(plan, "kdepth", False)) == want_kdepth
+    x = torch.randn(1, cin, D, H, W, generator=g)
+    if not split:
+        x = x.half().float()
+    got = emulate(plan, x.double())
+    with torch.no_grad():
+        want = bn.double()(conv.double()(x.double()))
+    scale = max(1.0, want.abs().max().item())
+    tol = 4e-6 if split else 2e-3            # single fp16: the weights are rounded to 11 bits
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < tol * scale
