@@ -253,6 +253,14 @@ int stb_context_upsample_f32(const float* disp_low, const float* weights, float*
 int stb_conv3d_wgrad_f32(const float* P, const float* Q, float* dW, int B, int Cp, int Dp, int Hp, int Wp, int Cq,
                          int Dq, int Hq, int Wq, int K, int pad, int stride, void* stream);
 
+/* The same weight gradient on the tensor cores, straight from the channels-last 16-bit tensors of the 16-bit training path
+ * (train16.py; BASELINE config 3, reference: trainer/trainer_torchrun.py:105-123 runs the step under autocast):
+ *   P [B,Dp,Hp,Wp,Cp], Q [B,Dq,Hq,Wq,Cq] bf16 (f16 = 0) or fp16 (f16 = 1), Cp and Cq multiples of 32 (zero-padded channels
+ *   give zero rows / columns); dW [K^3][Cp][Cq] fp32, zeroed by the caller (fp32 accumulation, atomics across CTAs).
+ * K in 1..3, stride in {1, 2}; max_ctas <= 0: one persistent CTA per SM (and per tap / channel group). */
+int stb_conv3d_wgrad_cl16(const void* P, const void* Q, float* dW, int f16, int B, int Dp, int Hp, int Wp, int Cp, int Dq,
+                          int Hq, int Wq, int Cq, int K, int pad, int stride, int max_ctas, void* stream);
+
 /* Adjoint of build_concat_volume (variant A mask_left=1 / B mask_left=0): dvol [B,c_total,D,H,W] channels
  * [c_off, c_off+2C) -> dleft, dright [B,C,H,W]. */
 int stb_concat_volume_bwd_f32(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W, int D,

@@ -54,6 +54,7 @@ SIGNATURES = {
     "stb_convex_upsample_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "stb_context_upsample_f32": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
     "stb_conv3d_wgrad_f32": [_P, _P, _P] + [_I] * 12 + [_P],
+    "stb_conv3d_wgrad_cl16": [_P, _P, _P] + [_I] * 14 + [_P],
     "stb_concat_volume_bwd_f32": [_P, _P, _P] + [_I] * 8 + [_P],
     "stb_gwc_volume_bwd_f32": [_P, _P, _P, _P, _P] + [_I] * 8 + [_P],
     "stb_upsample_softargmin_bwd_f32": [_P, _P, _P] + [_I] * 8 + [_P],

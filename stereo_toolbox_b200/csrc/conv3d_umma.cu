@@ -1114,7 +1114,10 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         const uint32_t bm = (in_stride == 2 && !es_variant) ? 2u : 1u;     // box extent convention under element strides
         uint32_t box[5] = {(uint32_t)KC, (uint32_t)TWP * bm, (uint32_t)box_h * bm, 1, 1};
         uint32_t es[5] = {1, (uint32_t)in_stride, (uint32_t)in_stride, 1, 1};
-        if (!umma_host::make_tmap(&tm_x, cudt, 5, const_cast<void*>(x), dims, str, box, cusw, es)) return STB_E_DRIVER;
+        // K-split passes read ONE K-chunk of every row per launch: promote no wider than the chunk (STB_TMA_PROMO overrides)
+        static const int promo_env = getenv("STB_TMA_PROMO") ? atoi(getenv("STB_TMA_PROMO")) : 0;
+        const int promo = promo_env > 0 ? promo_env : (nk > 1 ? KC * 2 : 256);
+        if (!umma_host::make_tmap(&tm_x, cudt, 5, const_cast<void*>(x), dims, str, box, cusw, es, promo)) return STB_E_DRIVER;
     }
     a.w_rows = Cpad;
     a.w_tile_stride = nk;

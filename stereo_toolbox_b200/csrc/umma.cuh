@@ -244,7 +244,7 @@ inline EncodeTiledFn encode_fn() {
 // dims/strides innermost first; strides in bytes for dims 1..rank-1.
 inline bool make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int rank, void* base, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw,
-                      const uint32_t* elem_strides = nullptr) {
+                      const uint32_t* elem_strides = nullptr, int promo_bytes = 256) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t gd[5], gs[4];
@@ -255,8 +255,13 @@ inline bool make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int rank, void* ba
         es[i] = elem_strides ? elem_strides[i] : 1;
         if (i > 0) gs[i - 1] = strides_bytes[i - 1];
     }
+    // L2 promotion widens every TMA request to 64 / 128 / 256 B sectors-groups: a box whose inner extent covers only PART of a
+    // row (one K-chunk of a K-split pass) must not promote beyond its own bytes, or every pass fetches the whole tensor
+    const CUtensorMapL2promotion promo = promo_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                         : promo_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                         : promo_bytes >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
     CUresult r = fn(m, dt, (cuuint32_t)rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 }  // namespace umma_host

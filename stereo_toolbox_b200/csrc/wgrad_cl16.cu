@@ -7,11 +7,12 @@
 // (the transposed conv is the adjoint of the strided conv, so the same index relation holds with the roles swapped).
 //
 // The contraction runs over POSITIONS, which are the slow axis of NDHWC tensors, so both operands are "MN-major";
-// this first version uses the warp-level tensor path (mma.sync m16n8k16, ldmatrix.trans from padded smem rows) --
+// this version uses the warp-level tensor path (mma.sync m16n8k16, ldmatrix.trans from padded smem rows) --
 // SASS: HMMA + LDSM.  A persistent CTA keeps up to 32 output blocks of 32x32 (tap, cp-block, cq-block) in registers
 // (4 per warp), streams (P halo tile, Q tile) pairs through a cp.async double buffer and adds its partial sums to the
-// fp32 result with atomics once at the end.  The tcgen05 formulation (MN-major smem descriptors) is the next step,
-// see DESIGN.md.
+// fp32 result with atomics once at the end.  Why not tcgen05 here: with K = positions both operands are MN-major, the
+// 32-channel layers (most of PSMNet's FLOPs) give M = 32 < the UMMA minimum of 64, and the junk columns of the padded
+// position tiles would have to be zeroed in shared memory before every MMA.
 #include <cuda_fp16.h>
 #include "common.cuh"
 
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradArgs a)
     const int tap1 = min(ntaps, tap0 + a.taps_per_cta);
     const int pbn = a.cps / 32, qbn = a.cqs / 32;
     const int nunits = (tap1 - tap0) * pbn * qbn;
-    int u_tap[WG_UPW], u_pb[WG_UPW], u_qb[WG_UPW];
+    int u_tap[WG_UPW], u_pb[WG_UPW], u_qb[WG_UPW], u_poff[WG_UPW];
     bool u_ok[WG_UPW];
 #pragma unroll
     for (int i = 0; i < WG_UPW; ++i) {
@@ -94,6 +95,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradArgs a)
         u_tap[i] = tap0 + uu / (pbn * qbn);
         u_pb[i] = (uu / qbn) % pbn;
         u_qb[i] = uu % qbn;
+        const int t = u_tap[i];
+        const int kd = t / (a.K * a.K), kh = (t / a.K) % a.K, kw = t % a.K;
+        u_poff[i] = (kd * a.PH + kh) * a.PW + kw;            // halo-tile row of the tap's (0, 0) position
     }
     float acc[WG_UPW][2][4][4];
 #pragma unroll
@@ -165,8 +169,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradArgs a)
 #pragma unroll
             for (int i = 0; i < WG_UPW; ++i) {
                 if (!u_ok[i]) continue;                       // warp-uniform
-                const int t = u_tap[i];
-                const int kd = t / (a.K * a.K), kh = (t / a.K) % a.K, kw = t % a.K;
                 // B fragments: Q rows r*32 + c0 + k, channels qb*32 + n
                 uint32_t bfr[4][2];
                 {
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradArgs a)
                     ldsm_x4_t(base + 32, bfr[2][0], bfr[2][1], bfr[3][0], bfr[3][1]);
                 }
                 // A fragments: P halo rows (kd, s*r + kh, s*(c0 + k) + kw), channels pb*32 + m
-                const int prow_i = (kd * a.PH + a.s * r + kh) * a.PW + a.s * (c0 + a_krow) + kw;
+                const int prow_i = u_poff[i] + a.s * r * a.PW + a.s * (c0 + a_krow);
                 const uint32_t abase = sp + (uint32_t)(prow_i * ppitch + (u_pb[i] * 32 + a_mcol) * 2);
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
@@ -233,8 +235,8 @@ extern "C" int stb_conv3d_wgrad_cl16(const void* P, const void* Q, float* dW, in
     a.taps_per_cta = (ntaps + a.ntapgrp - 1) / a.ntapgrp;           // balance the groups
     const size_t limit = 220 * 1024;
     int best_th = 0, best_stage = 0;
-    for (int th = 4; th >= 1 && !best_th; th >>= 1)
-        for (int st = 2; st >= 1; --st) {
+    for (int st = 2; st >= 1 && !best_th; --st)          // a double buffer first (loads overlap the MMAs), then the tallest tile
+        for (int th = 4; th >= 1; th >>= 1) {
             const int ph = stride * (th - 1) + K, pw = stride * (WG_TW - 1) + K;
             size_t pb = (size_t)K * ph * pw * (a.cps * 2 + WG_PADB), qb = (size_t)th * WG_TW * (a.cqs * 2 + WG_PADB);
             size_t sb = (pb + qb + 127) / 128 * 128;

@@ -9,7 +9,8 @@ FLOPs run on the tcgen05 kernel:
                    Conv3d(k, s=1, p)          -> Conv3d(k, 1, k-1-p) with flipped taps and swapped channel roles
                    Conv3d(k3, s=2, p1)        -> ConvTranspose3d(k3, 2, p1, output_padding from the shapes), same weight
                    ConvTranspose3d(k3,2,p1,1) -> Conv3d(k3, 2, p1), same weight ................. ``stb_conv3d_umma``
-  weight gradient fp32 CUDA-core kernel on fp32 copies of the two 16-bit operands ............ ``stb_conv3d_wgrad_f32``
+  weight gradient tensor cores (mma.sync, fp32 accumulation) on the two channels-last 16-bit operands
+                   (the single-channel classifier: fp32 CUDA-core kernel) ..................... ``stb_conv3d_wgrad_cl16``
 
 BatchNorm3d (train mode: batch statistics, running-stat update), residual adds and activations are torch elementwise /
 reduction ops on the 16-bit channels-last tensors, so their autograd is torch's.  The volume builders and the fused
@@ -30,7 +31,11 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import os
+
 from .aggregation import _NoProf, _split
+
+WGRAD_TC = os.environ.get("STB_WGRAD_TC", "1") == "1"      # weight gradient on the tensor cores (csrc/wgrad_cl16.cu); 0: fp32 CUDA cores
 
 
 def _pad_channels(c: int) -> int:
@@ -96,12 +101,23 @@ class Umma16TrainBackend:
         from .ops import _p, _stream
         tr = isinstance(conv, nn.ConvTranspose3d)
         cin, cout = (conv.weight.shape[0], conv.weight.shape[1]) if tr else (conv.weight.shape[1], conv.weight.shape[0])
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        if (WGRAD_TC and gy.dtype == self.dtype and x16.shape[-1] % 32 == 0 and gy.shape[-1] % 32 == 0 and k <= 3
+                and s in (1, 2)):
+            # tensor-core weight gradient straight from the channels-last 16-bit operands (csrc/wgrad_cl16.cu): no fp32 NCDHW
+            # copies, fp32 accumulation.  Zero-padded channels come back as zero rows / columns and are sliced off.
+            x16, g16 = x16.contiguous(), gy.contiguous()
+            P, Q = (g16, x16) if tr else (x16, g16)
+            dw = torch.zeros(k, k, k, P.shape[-1], Q.shape[-1], device=x16.device, dtype=torch.float32)
+            _lib.call("stb_conv3d_wgrad_cl16", _p(P), _p(Q), _p(dw), int(self.dtype == torch.float16), P.shape[0], P.shape[1],
+                      P.shape[2], P.shape[3], P.shape[4], Q.shape[1], Q.shape[2], Q.shape[3], Q.shape[4], k, p, s, 0, _stream())
+            cp, cq = (cout, cin) if tr else (cin, cout)
+            return dw[..., :cp, :cq].permute(4, 3, 0, 1, 2).contiguous()
         xf = from_channels_last(x16.contiguous(), cin)                       # fp32 [B,Cin,D,H,W], padding dropped
         if gy.dtype == torch.float32:                                        # classifier: [B,D,H,W,1] fp32
             gf = gy.permute(0, 4, 1, 2, 3).contiguous()
         else:
             gf = from_channels_last(gy.contiguous(), cout)
-        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         P, Q = (gf, xf) if tr else (xf, gf)
         dw = torch.zeros(k, k, k, P.shape[1], Q.shape[1], device=xf.device, dtype=torch.float32)
         _lib.call("stb_conv3d_wgrad_f32", _p(P), _p(Q), _p(dw), P.shape[0], P.shape[1], P.shape[2], P.shape[3],

@@ -40,6 +40,43 @@ def test_raw_conv_gradients_match_torch(k, s, p, tr, op, dims):
     torch.testing.assert_close(conv.weight.grad, w2.grad, rtol=1e-3, atol=1e-2)
 
 
+@pytest.mark.parametrize("cin,cout,k,s,p,tr,op,dims", [
+    (32, 32, 3, 1, 1, False, 0, (5, 9, 37)),
+    (64, 32, 3, 1, 1, False, 0, (4, 6, 40)),
+    (64, 64, 3, 1, 1, False, 0, (3, 7, 33)),
+    (32, 64, 3, 2, 1, False, 0, (6, 10, 36)),
+    (64, 64, 3, 2, 1, False, 0, (5, 9, 35)),          # odd sizes: the adjoint carries output_padding 0
+    (64, 32, 3, 2, 1, True, 1, (3, 5, 18)),
+    (32, 32, 1, 1, 0, False, 0, (4, 6, 34)),
+])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_tensor_core_wgrad_matches_torch(cin, cout, k, s, p, tr, op, dims, dtype):
+    """stb_conv3d_wgrad_cl16 (mma.sync, fp32 accumulation) on 16-bit operands vs torch's fp32 weight gradient of the SAME
+    rounded operands: the products are exact in fp32, so only the summation order differs."""
+    from stereo_toolbox_b200.train16 import Umma16TrainBackend
+    be = Umma16TrainBackend("bf16" if dtype == torch.bfloat16 else "fp16")
+    g = torch.Generator().manual_seed(cin + cout + k + s)
+    conv = (nn.ConvTranspose3d(cin, cout, k, s, p, output_padding=op, bias=False) if tr
+            else nn.Conv3d(cin, cout, k, s, p, bias=False)).cuda()
+    x = torch.randn(2, *dims, cin, generator=g).to(dtype).cuda()
+    x2 = x.float().permute(0, 4, 1, 2, 3)
+    w2 = conv.weight.detach().clone().requires_grad_(True)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y2 = (F.conv_transpose3d(x2, w2, stride=s, padding=p, output_padding=op) if tr else F.conv3d(x2, w2, stride=s, padding=p))
+        gy = torch.randn(y2.shape, generator=g).to(dtype).cuda()
+        y2.backward(gy.float())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    got = be._wgrad(conv, x, gy.permute(0, 2, 3, 4, 1).contiguous())
+    assert got.shape == conv.weight.shape
+    scale = w2.grad.abs().max().item()
+    err = (got - w2.grad).abs().max().item()
+    print(f"wgrad {cin}->{cout} k{k} s{s} tr={tr} {dtype}: max err {err:.3e} of scale {scale:.3e}")
+    assert err < 2e-4 * scale
+
+
 def test_psmnet_bf16_training_step_vs_reference():
     import stereo_toolbox_b200 as S
     from stereo_toolbox_b200.synth import synth_state_dict, synth_pair, synth_gt
