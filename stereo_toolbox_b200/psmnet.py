@@ -128,6 +128,19 @@ class PSMNet(nn.Module):
         the cost-volume path runs on TrainBackend -- forward and backward in libstb200.so.  Returns the reference's
         list [pred1, pred2, pred3] (stackhourglass.py:159)."""
         from .aggregation import train_backend_for
+        prec = getattr(self, "train_precision", "fp32")
+        if getattr(self, "train_features", "fp32") == "amp" and prec in ("bf16", "fp16"):
+            # the reference's own mixed-precision recipe for the torch part (trainer/trainer_torchrun.py:219,274: the whole step
+            # runs under torch.amp.autocast): the 2-D extractor's cuDNN convs in the training dtype on channels-last
+            # tensors, BatchNorm2d statistics in fp32 (autocast policy); opt-in, ``model.train_features = "amp"``
+            if not getattr(self, "_fe_channels_last", False):
+                self.feature_extraction.to(memory_format=torch.channels_last)
+                self._fe_channels_last = True
+            with torch.autocast("cuda", dtype=torch.bfloat16 if prec == "bf16" else torch.float16):
+                fl = self.feature_extraction(left.contiguous(memory_format=torch.channels_last))
+                fr = self.feature_extraction(right.contiguous(memory_format=torch.channels_last))
+            fl, fr = fl.float(), fr.float()
+            return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=train_backend_for(self), all_heads=True)
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = prev and self.feature_mode not in (None, "fp32") and self.feature_tf32 is not False
         try:

@@ -77,7 +77,9 @@ def test_tensor_core_wgrad_matches_torch(cin, cout, k, s, p, tr, op, dims, dtype
     assert err < 2e-4 * scale
 
 
-def test_psmnet_bf16_training_step_vs_reference():
+@pytest.mark.parametrize("features", ["fp32", "amp"])
+def test_psmnet_bf16_training_step_vs_reference(features):
+    """features = 'amp': the torch 2-D extractor under bf16 autocast as well (the reference trainer's amp recipe)."""
     import stereo_toolbox_b200 as S
     from stereo_toolbox_b200.synth import synth_state_dict, synth_pair, synth_gt
     g = load_golden("psmnet_train.npz")
@@ -89,6 +91,7 @@ def test_psmnet_bf16_training_step_vs_reference():
     net.load_state_dict(synth_state_dict(tmpl, 0, {k: z[k] for k in z.files}), strict=True)
     net = net.cuda().train()
     net.train_precision = "bf16"
+    net.train_features = features
     left, right = synth_pair(2, 256, 256, seed=1, shift=7)
     gt = synth_gt(2, 256, 256).cuda()
     preds = net(left.cuda(), right.cuda())
@@ -97,7 +100,8 @@ def test_psmnet_bf16_training_step_vs_reference():
     loss = sum(w * F.smooth_l1_loss(p.squeeze(1)[mask], gt[mask], reduction="mean") for w, p in zip((0.5, 0.7, 1.0), preds))
     loss.backward()
     for i, p in enumerate(preds):
-        assert (p.detach().cpu()[:, :, ::2, ::2] - g[f"pred{i + 1}"]).abs().mean().item() < 0.15
+        # bf16 storage of the cost-volume path alone: 0.10-0.14 px here; with the 2-D extractor in bf16 too: 0.17 px
+        assert (p.detach().cpu()[:, :, ::2, ::2] - g[f"pred{i + 1}"]).abs().mean().item() < {"fp32": 0.15, "amp": 0.25}[features]
     assert abs(loss.item() - g["loss"].item()) < 0.01 * abs(g["loss"].item())
     params = dict(net.named_parameters())
     for name in [k[5:] for k in g if k.startswith("grad:")]:

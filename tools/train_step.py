@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(height=384, width=512, batch=2, steps=5, warmup=2, maxdisp=192, lr=1e-4, precision="fp32"):
+def run(height=384, width=512, batch=2, steps=5, warmup=2, maxdisp=192, lr=1e-4, precision="fp32", features="fp32"):
     """Times `steps` complete training steps on every rank of the (already initialised, if world > 1) process group and
     returns the JSON-able result on rank 0 (None elsewhere).  Called by main() below and by bench.py's ``train_step`` leg."""
     import torch.distributed as dist
@@ -42,6 +42,7 @@ def run(height=384, width=512, batch=2, steps=5, warmup=2, maxdisp=192, lr=1e-4,
     net.load_state_dict(synth_state_dict(tmpl, 0, {k: z[k] for k in z.files}))
     net = net.cuda().train()
     net.train_precision = precision
+    net.train_features = features          # "amp": the torch 2-D extractor under autocast in the training dtype (the reference's amp recipe)
     bucket = FlatGradAllReduce(net.parameters())
     left, right = synth_pair(batch, height, width, seed=1000 + rank, shift=11)
     left, right = left.cuda(), right.cuda()
@@ -97,7 +98,7 @@ def run(height=384, width=512, batch=2, steps=5, warmup=2, maxdisp=192, lr=1e-4,
     if rank == 0:
         bus = 2.0 * (world - 1) / world * bucket.nbytes / (ar_pure * 1e-3) / 1e9 if world > 1 else 0.0
         kind = "fp32 exact path" if precision == "fp32" else \
-            f"{precision}: tcgen05 forward + dgrad on 16-bit channels-last activations, fp32 wgrad / BatchNorm statistics / volumes / head"
+            f"{precision}: tcgen05 forward + dgrad and tensor-core (mma.sync) wgrad on 16-bit channels-last activations, fp32 BatchNorm statistics / volumes / head; 2-D extractor (torch): {'autocast ' + precision if features == 'amp' else 'fp32'}"
         out = {
             "metric": f"PSMNet training pairs/sec ({kind}; forward+backward in libstb200.so, one flat NCCL gradient all-reduce)",
             "value": pairs / (step_ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -108,7 +109,7 @@ def run(height=384, width=512, batch=2, steps=5, warmup=2, maxdisp=192, lr=1e-4,
             "grad_disagreement_after_allreduce": disagree, "loss": loss.item(), "scaling": "weak",
             "dtype": {"fp32": "f32"}.get(precision, precision),
             "config": {"workload": f"PSMNet train step {height}x{width} D={maxdisp}", "batch_per_gpu": batch,
-                       "precision": precision, "loss": "smooth-L1 on the 3 outputs, weights 0.5/0.7/1.0, mask 0 < gt < maxdisp"},
+                       "precision": precision, "features": features, "loss": "smooth-L1 on the 3 outputs, weights 0.5/0.7/1.0, mask 0 < gt < maxdisp"},
             "gpu_launches": _lib.LAUNCH_COUNT - launches0}
     del net, bucket
     torch.cuda.empty_cache()
@@ -126,6 +127,8 @@ def main():
     ap.add_argument("--lr", type=float, default=1e-4)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp16"],
                     help="fp32 = exact training path; bf16 / fp16 = train16.Umma16TrainBackend (tcgen05 forward + dgrad)")
+    ap.add_argument("--features", default="fp32", choices=["fp32", "amp"],
+                    help="torch 2-D extractor: exact fp32, or autocast in the training dtype (the reference's amp recipe)")
     args = ap.parse_args()
     import torch.distributed as dist
     from stereo_toolbox_b200.distrib import env_rank
@@ -133,7 +136,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    out = run(args.height, args.width, args.batch, args.steps, args.warmup, args.maxdisp, args.lr, args.precision)
+    out = run(args.height, args.width, args.batch, args.steps, args.warmup, args.maxdisp, args.lr, args.precision, args.features)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
