@@ -36,6 +36,8 @@ extern "C" {
 #define STB_ACT_RELU 1
 #define STB_ACT_LEAKY 2   /* LeakyReLU(0.01), IGEVStereo/submodule.py:36 */
 #define STB_ACT_MISH 3    /* x*tanh(softplus(x)), CFNet/submodule.py:99-106 */
+#define STB_ACT_SIGMOID 4 /* ConvGRU gates z, r (RAFTStereo/update.py:40-41); stb_conv3d_umma: split storage only */
+#define STB_ACT_TANH 5    /* ConvGRU candidate q (RAFTStereo/update.py:42); stb_conv3d_umma: split storage only */
 
 const char* stb_error_string(int code);
 int stb_version(void);
@@ -260,6 +262,17 @@ int stb_conv3d_wgrad_f32(const float* P, const float* Q, float* dW, int B, int C
  * K in 1..3, stride in {1, 2}; max_ctas <= 0: one persistent CTA per SM (and per tap / channel group). */
 int stb_conv3d_wgrad_cl16(const void* P, const void* Q, float* dW, int f16, int B, int Dp, int Hp, int Wp, int Cp, int Dq,
                           int Hq, int Wq, int Cq, int K, int pad, int stride, int max_ctas, void* stream);
+
+/* Between the convolutions of the iterative models' update block (RAFTStereo/update.py:29-44 ConvGRU, :91-95 pool2x /
+ * interp, :115-138 BasicMultiUpdateBlock.forward), on channels-last operand-split fp16 rows ([.., 2*C] halves, C % 16 == 0):
+ *   stb_gru_rh_split     out[p][c] = r * h, r = logical channels [C, 2C) of zr ([npix][2C] logical: sigmoid(convz | convr))
+ *   stb_gru_blend_split  out = (1 - z) * h + z * q, z = logical channels [0, C) of zr
+ *   stb_pool2x_split     F.avg_pool2d(x, 3, stride=2, padding=1): x [N,H,W,C] -> out [N,(H-1)/2+1,(W-1)/2+1,C]
+ *   stb_interp_split     F.interpolate(x, (Ho,Wo), mode="bilinear", align_corners=True): x [N,H,W,C] -> out [N,Ho,Wo,C] */
+int stb_gru_rh_split(const void* zr, const void* h, void* out, long long npix, int C, void* stream);
+int stb_gru_blend_split(const void* zr, const void* h, const void* q, void* out, long long npix, int C, void* stream);
+int stb_pool2x_split(const void* x, void* out, int N, int H, int W, int C, void* stream);
+int stb_interp_split(const void* x, void* out, int N, int H, int W, int Ho, int Wo, int C, void* stream);
 
 /* Adjoint of build_concat_volume (variant A mask_left=1 / B mask_left=0): dvol [B,c_total,D,H,W] channels
  * [c_off, c_off+2C) -> dleft, dright [B,C,H,W]. */

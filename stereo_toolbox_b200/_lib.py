@@ -55,6 +55,10 @@ SIGNATURES = {
     "stb_context_upsample_f32": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
     "stb_conv3d_wgrad_f32": [_P, _P, _P] + [_I] * 12 + [_P],
     "stb_conv3d_wgrad_cl16": [_P, _P, _P] + [_I] * 14 + [_P],
+    "stb_gru_rh_split": [_P, _P, _P, _LL, _I, _P],
+    "stb_gru_blend_split": [_P, _P, _P, _P, _LL, _I, _P],
+    "stb_pool2x_split": [_P, _P, _I, _I, _I, _I, _P],
+    "stb_interp_split": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "stb_concat_volume_bwd_f32": [_P, _P, _P] + [_I] * 8 + [_P],
     "stb_gwc_volume_bwd_f32": [_P, _P, _P, _P, _P] + [_I] * 8 + [_P],
     "stb_upsample_softargmin_bwd_f32": [_P, _P, _P] + [_I] * 8 + [_P],

@@ -22,6 +22,8 @@ __device__ __forceinline__ float stb_act(float v, int act) {
             float sp = v > 20.f ? v : log1pf(expf(v));
             return v * tanhf(sp);
         }
+        case STB_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        case STB_ACT_TANH: return tanhf(v);
         default: return v;
     }
 }

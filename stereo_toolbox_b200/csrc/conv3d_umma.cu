@@ -887,6 +887,9 @@ int launch_umma(int act, int f16, int split, unsigned grid, size_t smem, cudaStr
         STB_LAUNCH_ACT(STB_ACT_RELU)
         STB_LAUNCH_ACT(STB_ACT_LEAKY)
         STB_LAUNCH_ACT(STB_ACT_MISH)
+        // gate activations of the ConvGRU (update block of the iterative models): split storage only
+        case STB_ACT_SIGMOID: return split ? launch_one<STB_ACT_SIGMOID, true, true>(grid, smem, st, tx, tw, a) : STB_E_UNSUPPORTED;
+        case STB_ACT_TANH: return split ? launch_one<STB_ACT_TANH, true, true>(grid, smem, st, tx, tw, a) : STB_E_UNSUPPORTED;
         default: return STB_E_BADARG;
     }
 #undef STB_LAUNCH_ACT

@@ -38,7 +38,8 @@ class Conv2dPlan:
         if cin_range is not None:
             w = w[:, cin_range[0]:cin_range[1]]
         cout, cin, kh_, kw_ = w.shape
-        assert kh_ == kw_ and conv.groups == 1 and conv.bias is None
+        assert kh_ == kw_ and conv.groups == 1
+        bias = None if conv.bias is None else conv.bias.detach().float()
         k, stride, pad, dil = kh_, conv.stride[0], conv.padding[0], conv.dilation[0]
         assert stride in (1, 2) and (stride == 1 or dil == 1)
         if cin_tensor != cin:
@@ -48,8 +49,10 @@ class Conv2dPlan:
         if bn is not None:
             scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
             self.shift = (bn.bias.detach().float() - bn.running_mean.float() * scale).contiguous()
+            if bias is not None:
+                self.shift = (self.shift + bias * scale).contiguous()
         else:
-            scale, self.shift = torch.ones(cout, device=w.device), None
+            scale, self.shift = torch.ones(cout, device=w.device), (None if bias is None else bias.contiguous())
         if not with_shift:
             self.shift = None
         self.conv_cin = cin                                                  # real input channels (FLOP accounting)
@@ -136,6 +139,7 @@ class UmmaGwcFeatures:
 
     def _plan(self, conv, bn, cin_tensor, cin_range=None, with_shift=True):
         ver = (conv.weight.data_ptr(), conv.weight._version, cin_tensor) + \
+              (() if getattr(conv, "bias", None) is None else (conv.bias.data_ptr(), conv.bias._version)) + \
               (() if bn is None else (bn.weight._version, bn.bias._version, bn.running_mean._version,
                                       bn.running_var._version, bn.running_mean.data_ptr()))
         key = (id(conv), cin_range, with_shift)

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 
-ACT = {"none": 0, "relu": 1, "leaky": 2, "mish": 3}
+ACT = {"none": 0, "relu": 1, "leaky": 2, "mish": 3, "sigmoid": 4, "tanh": 5}
 
 
 def _need_cuda(*ts):

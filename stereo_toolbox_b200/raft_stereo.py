@@ -326,6 +326,62 @@ class RAFTStereo(nn.Module):
             hit["graph"].replay()
         return hit["coords"].clone(), hit["mask"]
 
+    def _iterate_umma(self, net_list, inp_list, corr_fn, coords0, coords1, iters):
+        """The GRU loop with the update block on the tensor-core 2-D conv path (update_umma.UmmaRaftUpdate: every conv of
+        the block on tcgen05 in the exact 'fp16x2' format, hidden states resident in that layout).
+        Opt-in: ``model.update_mode = "umma"`` (inference, no slow_fast_gru).  With ``model.cuda_graph`` one iteration is
+        captured once per shape and replayed.  Returns (coords1, up_mask of the last iterate)."""
+        from .update_umma import UmmaRaftUpdate
+        upd = self.__dict__.get("_umma_update")
+        if upd is None:
+            upd = self.__dict__["_umma_update"] = UmmaRaftUpdate(self.update_block, self.args)
+        upd._prepare()
+        net = [upd.to_cl(t) for t in net_list]
+        ctx = upd.context(inp_list)
+
+        def one(net, ctx, fn, c0, c1):
+            net, delta = upd.step(net, ctx, fn(c1), c1 - c0)
+            delta[:, 1] = 0.0                     # stereo: project the update onto the epipolar line (raft_stereo.py:172)
+            return net, c1 + delta
+
+        if not getattr(self, "cuda_graph", False) or iters < 2:
+            for _ in range(iters):
+                net, coords1 = one(net, ctx, corr_fn, coords0, coords1)
+            return coords1, upd.mask(net[0])
+        key = ("umma", tuple(coords1.shape), tuple(tuple(t.shape) for t in net), str(coords1.device))
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            st = dict(net=[t.clone() for t in net], ctx=[(a.clone(), b.clone()) for a, b in ctx], coords=coords1.clone(),
+                      coords0=coords0.clone(), levels=[t.clone() for t in corr_fn._levels])
+            corr_fn._levels = st["levels"]                # the captured lookup reads the static pyramid buffers
+            st["corr_fn"] = corr_fn
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                 # warm-up outside capture (kernel plans, lazy module loading)
+                one(st["net"], st["ctx"], corr_fn, st["coords0"], st["coords"])
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                n2, c2 = one(st["net"], st["ctx"], corr_fn, st["coords0"], st["coords"])
+                for dst, src in zip(st["net"], n2):
+                    dst.copy_(src)
+                st["coords"].copy_(c2)
+            st["graph"] = graph
+            cache[key] = hit = st
+        else:
+            for dst, src in zip(hit["net"], net):
+                dst.copy_(src)
+            for (da, db), (sa, sb) in zip(hit["ctx"], ctx):
+                da.copy_(sa); db.copy_(sb)
+            for dst, src in zip(hit["levels"], corr_fn._levels):
+                dst.copy_(src)
+            hit["coords"].copy_(coords1)
+            hit["coords0"].copy_(coords0)
+        for _ in range(iters):
+            hit["graph"].replay()
+        return hit["coords"].clone(), upd.mask(hit["net"][0])
+
     def forward(self, image1, image2, iters=None, flow_init=None, test_mode=False):
         a = self.args
         if iters is None:
@@ -370,6 +426,9 @@ class RAFTStereo(nn.Module):
                 net_list, up_mask, coords1 = self._iteration(net_list, inp_list, corr_fn, coords0, coords1)
                 preds.append(-self.upsample_flow(coords1 - coords0, up_mask)[:, :1])
             return preds
+        if getattr(self, "update_mode", "torch") == "umma" and not a.slow_fast_gru and image1.is_cuda:
+            coords1, up_mask = self._iterate_umma(net_list, inp_list, corr_fn, coords0, coords1, iters)
+            return -self.upsample_flow(coords1 - coords0, up_mask)[:, :1]
         if getattr(self, "cuda_graph", False) and flow_init is None and iters > 1:
             coords1, up_mask = self._iterate_graphed(net_list, inp_list, corr_fn, coords0, coords1, iters)
             flow_up = self.upsample_flow(coords1 - coords0, up_mask)[:, :1]
