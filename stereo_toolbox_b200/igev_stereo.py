@@ -255,6 +255,60 @@ class IGEVStereo(IGEVCostVolume):
                                                               iter16=a.n_gru_layers == 3, iter08=a.n_gru_layers >= 2)
         return net_list, mask_feat_4, disp + delta_disp
 
+    def _iterate_umma(self, net_list, inp_list, geo_fn, coords, disp, iters):
+        """The GRU loop with the update block on the tensor-core 2-D conv path (update_umma.UmmaIgevUpdate, exact 'fp16x2'
+        format, hidden states resident in kernel layout).  Opt-in: ``model.update_mode = "umma"`` (inference); with
+        ``model.cuda_graph`` one iteration is captured per shape and replayed.  Returns (disp, mask_feat_4 of the last iterate)."""
+        from .update_umma import UmmaIgevUpdate
+        upd = self.__dict__.get("_umma_update")
+        if upd is None:
+            upd = self.__dict__["_umma_update"] = UmmaIgevUpdate(self.update_block, self.args)
+        upd._prepare()
+        net = [upd.to_cl(t) for t in net_list]
+        ctx = upd.context(inp_list)
+
+        def one(net, ctx, fn, co, d):
+            net, delta = upd.step(net, ctx, fn(d, co), d)
+            return net, d + delta
+
+        if not getattr(self, "cuda_graph", False) or iters < 2:
+            for _ in range(iters):
+                net, disp = one(net, ctx, geo_fn, coords, disp)
+            return disp, upd.mask(net[0])
+        key = ("umma", tuple(disp.shape), tuple(tuple(t.shape) for t in net), str(disp.device))
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            st = dict(net=[t.clone() for t in net], ctx=[(a.clone(), b.clone()) for a, b in ctx], disp=disp.clone(),
+                      coords=coords.clone(), geos=[t.clone() for t in geo_fn._geos], corrs=[t.clone() for t in geo_fn._corrs])
+            geo_fn._geos, geo_fn._corrs = st["geos"], st["corrs"]      # the captured lookup reads the static pyramid buffers
+            st["geo_fn"] = geo_fn
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                one(st["net"], st["ctx"], geo_fn, st["coords"], st["disp"])
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                n2, d2 = one(st["net"], st["ctx"], geo_fn, st["coords"], st["disp"])
+                for dst, src in zip(st["net"], n2):
+                    dst.copy_(src)
+                st["disp"].copy_(d2)
+            st["graph"] = graph
+            cache[key] = hit = st
+        else:
+            for dst, src in zip(hit["net"], net):
+                dst.copy_(src)
+            for (da, db), (sa, sb) in zip(hit["ctx"], ctx):
+                da.copy_(sa); db.copy_(sb)
+            for dst, src in zip(hit["geos"] + hit["corrs"], list(geo_fn._geos) + list(geo_fn._corrs)):
+                dst.copy_(src)
+            hit["disp"].copy_(disp)
+            hit["coords"].copy_(coords)
+        for _ in range(iters):
+            hit["graph"].replay()
+        return hit["disp"].clone(), upd.mask(hit["net"][0])
+
     def _iterate_graphed(self, net_list, inp_list, geo_fn, coords, disp, iters):
         """Opt-in (``model.cuda_graph = True``, inference): ONE iteration -- lookup kernel + update block + the write-back of
         its outputs into its own inputs -- is captured into a CUDA graph once per input shape and replayed ``iters`` times
@@ -338,6 +392,10 @@ class IGEVStereo(IGEVCostVolume):
         coords = torch.arange(w, device=match_left.device).float().reshape(1, 1, w, 1).repeat(b, h, 1, 1)
         disp = init_disp
         disp_preds = []
+        if (getattr(self, "update_mode", "torch") == "umma" and test_mode and not self.training and disp.is_cuda
+                and not torch.is_grad_enabled() and iters >= 1):
+            disp, mask_feat_4 = self._iterate_umma(net_list, inp_list, geo_fn, coords, disp.detach(), iters)
+            return self.upsample_disp(disp, mask_feat_4, stem_2x)
         if (getattr(self, "cuda_graph", False) and test_mode and not self.training and iters > 1 and disp.is_cuda
                 and not torch.is_grad_enabled()):
             disp, mask_feat_4 = self._iterate_graphed(net_list, inp_list, geo_fn, coords, disp, iters)

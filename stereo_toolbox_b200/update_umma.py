@@ -47,6 +47,11 @@ def _pad16(c: int) -> int:
 
 
 class UmmaRaftUpdate:
+    # reference module names: ConvGRUs finest -> coarsest, the motion encoder's two flow convs, the regression head
+    GRUS = ("gru08", "gru16", "gru32")
+    ENC_F = ("convf1", "convf2")
+    HEAD = "flow_head"
+
     def __init__(self, update_block: nn.Module, args):
         self.ub, self.args = update_block, args
         self.fx = UmmaGwcFeatures("fp16x2")
@@ -60,7 +65,7 @@ class UmmaRaftUpdate:
             return
         ub, v = self.ub, {}
         with torch.no_grad():
-            for name in ("gru08", "gru16", "gru32"):
+            for name in self.GRUS:
                 g = getattr(ub, name)
                 v[name + ".zr"] = _VConv(torch.cat((g.convz.weight, g.convr.weight), 0).detach().float(),
                                          torch.cat((g.convz.bias, g.convr.bias), 0).detach().float(), g.convz.padding[0])
@@ -71,7 +76,7 @@ class UmmaRaftUpdate:
             b = torch.zeros(cp, device=w.device)
             w[:co], b[:co] = e.conv.weight.detach().float(), e.conv.bias.detach().float()
             v["enc.conv"] = _VConv(w, b, 1)
-            fh = ub.flow_head
+            fh = getattr(ub, self.HEAD)
             half = fh.conv1.out_channels // 2
             v["fh.conv1a"] = _VConv(fh.conv1.weight[:half].detach().float(), fh.conv1.bias[:half].detach().float(), 1)
             v["fh.conv1b"] = _VConv(fh.conv1.weight[half:].detach().float(), fh.conv1.bias[half:].detach().float(), 1)
@@ -141,17 +146,19 @@ class UmmaRaftUpdate:
         """BasicMotionEncoder.forward (update.py:71-79) -> (conv output, 126 channels in a 128-channel tensor; flow in a
         16-channel tensor): the concatenation [out, flow] is consumed piecewise by the finest GRU."""
         e = self.ub.encoder
-        cor = self.fx.conv(e.convc1, None, self.to_cl(corr, 64 if corr.shape[1] <= 64 else _pad16(corr.shape[1])), "relu")
+        cc = corr.shape[1]                        # (RAFT: 36 lookup channels, IGEV: 162 -> whole 64-element K-chunks)
+        cor = self.fx.conv(e.convc1, None, self.to_cl(corr, 64 if cc <= 64 else (cc + 31) // 32 * 32), "relu")
         cor = self.fx.conv(e.convc2, None, cor, "relu")
+        f1, f2 = getattr(e, self.ENC_F[0]), getattr(e, self.ENC_F[1])
         fl = self.to_cl(flow, 16)
-        flo = self.fx.conv(e.convf1, None, fl, "relu")
-        flo = self.fx.conv(e.convf2, None, flo, "relu")
+        flo = self.fx.conv(f1, None, fl, "relu")
+        flo = self.fx.conv(f2, None, flo, "relu")
         c1 = e.convc2.out_channels
-        out = self._conv_cat(self._v["enc.conv"], [(cor, (0, c1)), (flo, (c1, c1 + e.convf2.out_channels))], "relu")
+        out = self._conv_cat(self._v["enc.conv"], [(cor, (0, c1)), (flo, (c1, c1 + f2.out_channels))], "relu")
         return out, fl
 
     def flow_head(self, h):
-        fh = self.ub.flow_head
+        fh = getattr(self.ub, self.HEAD)
         half = fh.conv1.out_channels // 2
         ya = self.fx.conv(self._v["fh.conv1a"], None, h, "relu")
         yb = self.fx.conv(self._v["fh.conv1b"], None, h, "relu")
@@ -171,20 +178,33 @@ class UmmaRaftUpdate:
         net = list(net)
         hid = lambda t: t.shape[-1] // 2
         if n == 3:
-            net[2] = self.gru("gru32", net[2], ctx[2][0], ctx[2][1], [(self.pool2x(net[1]), hid(net[1]))])
+            net[2] = self.gru(self.GRUS[2], net[2], ctx[2][0], ctx[2][1], [(self.pool2x(net[1]), hid(net[1]))])
         if n >= 2:
             xs = [(self.pool2x(net[0]), hid(net[0]))]
             if n > 2:
                 xs.append((self.interp(net[2], net[1]), hid(net[2])))
-            net[1] = self.gru("gru16", net[1], ctx[1][0], ctx[1][1], xs)
+            net[1] = self.gru(self.GRUS[1], net[1], ctx[1][0], ctx[1][1], xs)
         mo, fl = self.motion(flow, corr)
         e = self.ub.encoder
         xs = [(mo, e.conv.out_channels), (fl, flow.shape[1])]
         if n > 1:
             xs.append((self.interp(net[1], net[0]), hid(net[1])))
-        net[0] = self.gru("gru08", net[0], ctx[0][0], ctx[0][1], xs)
+        net[0] = self.gru(self.GRUS[0], net[0], ctx[0][0], ctx[0][1], xs)
         return net, self.flow_head(net[0])
 
     def mask(self, h08):
         """0.25 * mask head on the final hidden state (update.py:112-113,136): once per forward, torch."""
         return 0.25 * self.ub.mask(self.from_cl(h08))
+
+
+class UmmaIgevUpdate(UmmaRaftUpdate):
+    """IGEV-Stereo's update block (models/IGEVStereo/update.py:72-92 BasicMotionEncoder on the 162-channel geometry lookup
+    and the 1-channel disparity, :115-153 BasicMultiUpdateBlock: gru16 -> gru08 -> gru04, DispHead, mask_feat_4): the same
+    structure under other names; ``step`` returns (net, delta_disp [N,1,h,w])."""
+    GRUS = ("gru04", "gru08", "gru16")
+    ENC_F = ("convd1", "convd2")
+    HEAD = "disp_head"
+
+    def mask(self, h04):
+        """mask_feat_4 of the final hidden state (update.py:152): once per forward, torch."""
+        return self.ub.mask_feat_4(self.from_cl(h04))

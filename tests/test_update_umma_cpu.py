@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 
 import stereo_toolbox_b200.raft_stereo as rs
-from stereo_toolbox_b200.update_umma import UmmaRaftUpdate
+from stereo_toolbox_b200.update_umma import UmmaIgevUpdate, UmmaRaftUpdate
 
 
 class _TorchFx:
@@ -37,7 +37,7 @@ class _TorchFx:
         return {"none": lambda t: t, "relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}[act](y)
 
 
-class _CpuUpdate(UmmaRaftUpdate):
+class _CpuMixin:
     def __init__(self, ub, args):
         self.ub, self.args = ub, args
         self.fx = _TorchFx()
@@ -65,6 +65,41 @@ class _CpuUpdate(UmmaRaftUpdate):
     def interp(self, x, dest):
         y = F.interpolate(x[0].permute(0, 3, 1, 2), dest.shape[2:4], mode="bilinear", align_corners=True)
         return y.permute(0, 2, 3, 1)[None]
+
+
+class _CpuUpdate(_CpuMixin, UmmaRaftUpdate):
+    pass
+
+
+class _CpuIgevUpdate(_CpuMixin, UmmaIgevUpdate):
+    pass
+
+
+def test_igev_update_step_matches_torch_update_block():
+    import stereo_toolbox_b200.igev_stereo as ig
+    torch.manual_seed(0)
+    net = ig.IGEVStereo().eval()
+    ub, a = net.update_block, net.args
+    N, h, w = 1, 12, 20
+    sizes = [(h, w), (6, 10), (3, 5)]
+    g = torch.Generator().manual_seed(1)
+    net_list = [torch.tanh(torch.randn(N, 128, *sizes[i], generator=g)) for i in range(3)]
+    inp_list = [[0.5 * torch.randn(N, 128, *sizes[i], generator=g) for _ in range(3)] for i in range(3)]
+    corr = torch.randn(N, a.corr_levels * (2 * a.corr_radius + 1) * 9, h, w, generator=g)
+    disp = 5.0 * torch.rand(N, 1, h, w, generator=g)
+    with torch.no_grad():
+        want_net, want_mask, want_delta = ub([t.clone() for t in net_list], inp_list, corr, disp)
+    upd = _CpuIgevUpdate(ub, a)
+    with torch.no_grad():
+        upd._prepare()
+        got_net, got_delta = _run_with_doubling(upd, [upd.to_cl(t) for t in net_list],
+                                                [(upd.to_cl(torch.cat((cz, cr), 1)), upd.to_cl(cq)) for cz, cr, cq in inp_list],
+                                                corr, disp)
+    for gt, wt in zip(got_net, want_net):
+        assert (upd.from_cl(gt) - wt).abs().max().item() < 1e-5
+    assert got_delta.shape == want_delta.shape == (N, 1, h, w)
+    assert (got_delta - want_delta).abs().max().item() < 1e-5
+    assert (upd.mask(got_net[0]) - want_mask).abs().max().item() < 1e-4
 
 
 @pytest.mark.parametrize("n_gru_layers", [3, 2, 1])

@@ -56,7 +56,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cuda-graph", action="store_true", help="raft / igev: replay one captured GRU iteration")
     ap.add_argument("--update", default="", choices=["", "torch", "umma"],
-                    help="raft: update block in torch/cuDNN or on the tcgen05 2-D conv path (update_umma.py, exact fp16x2 format)")
+                    help="raft / igev: update block in torch/cuDNN or on the tcgen05 2-D conv path (update_umma.py, exact fp16x2 format)")
     ap.add_argument("--exact-glue", action="store_true", help="torch glue in true fp32 (no TF32): the arithmetic the parity tests pin")
     ap.add_argument("--channels-last", action="store_true", help="raft / igev / cfnet / pcwnet_gc: NHWC torch glue (model.channels_last)")
     args = ap.parse_args()
