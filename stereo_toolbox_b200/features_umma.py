@@ -15,6 +15,7 @@ from typing import Dict, Optional
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib, ops
 from .aggregation_umma import (BO_MODE, ES_VARIANT, KWMERGE, SPLIT_FLAG, TORCH_DT, _iarr, from_channels_last, pad_channels,
@@ -207,12 +208,8 @@ class UmmaGwcFeatures:
         short = x if blk.downsample is None else self.conv(blk.downsample[0], blk.downsample[1], x)
         return self._convbn(blk.conv2, y, "none", residual=short)
 
-    @torch.no_grad()
-    def __call__(self, fe, left, right, concat_head=None, channels_last_out=False):
-        """fe: features2d.GwcFeatures; left/right [B,3,H,W] fp32.  Returns (feat_left, feat_right) dicts of NCHW fp32
-        tensors like the reference feature_extraction (the layout the volume builder reads).  ``concat_head``:
-        (convbn Sequential, 1x1 Conv2d) applied to the gwc feature -- GwcNet's own lastconv by default, ACVNet's
-        model-level concatconv (ACVNet/acv.py:104-107) when given."""
+    def _trunk(self, fe, left, right):
+        """firstconv + layer1..4 shared by both extractors (features2d._Backbone) -> (l2, l3, l4), [1,2B,h,w,C] each."""
         B = left.shape[0]
         x = torch.cat((left, right), 0)                                   # [2B,3,H,W]
         H, W = x.shape[2:]
@@ -232,6 +229,42 @@ class UmmaGwcFeatures:
         l4 = l3
         for blk in fe.layer4:
             l4 = self._block(blk, l4)
+        return l2, l3, l4
+
+    @torch.no_grad()
+    def psm(self, fe, left, right):
+        """features2d.PsmFeatures (PSMNet/submodule.py:57-132) on the tensor-core conv kernel: trunk and lastconv
+        (320 -> 128 k3 over the concatenation [l2, l4, branch4..1] as three chained addends, 128 -> 32 k1) run on tcgen05; the
+        four SPP branches -- 64/32/16/8-pixel average pools of l4, a 1x1 conv on a handful of pixels, bilinear upsampling --
+        are fp32 torch ops on tiny tensors.  Returns (feat_left, feat_right) [B,32,h,w] fp32 like the reference."""
+        B = left.shape[0]
+        l2, _, l4 = self._trunk(fe, left, right)
+        _, N, h, w, _ = l4.shape
+        l4f = from_channels_last(l4.view(N, h, w, l4.shape[-1]), split=self.split)                   # [2B,128,h,w] fp32
+        prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            br = [F.interpolate(getattr(fe, f"branch{i}")(l4f), (h, w), mode="bilinear", align_corners=False) for i in (4, 3, 2, 1)]
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        brc = torch.cat(br, 1)                                                                       # [2B,128,h,w]
+        brc = to_channels_last(brc, brc.shape[1], self.dtype, split=self.split).view(1, N, h, w, brc.shape[1] * self.cmul)
+        if self.split:
+            y = self._convbn_multi(fe.lastconv[0], (l2, l4, brc), "relu")
+        else:
+            y = self.conv(fe.lastconv[0][0], fe.lastconv[0][1], torch.cat((l2, l4, brc), dim=-1), "relu")
+        y = self.conv(fe.lastconv[2], None, y)
+        f = from_channels_last(y.view(N, h, w, y.shape[-1]), fe.lastconv[2].out_channels, split=self.split)
+        return f[:B], f[B:]
+
+    @torch.no_grad()
+    def __call__(self, fe, left, right, concat_head=None, channels_last_out=False):
+        """fe: features2d.GwcFeatures; left/right [B,3,H,W] fp32.  Returns (feat_left, feat_right) dicts of NCHW fp32
+        tensors like the reference feature_extraction (the layout the volume builder reads).  ``concat_head``:
+        (convbn Sequential, 1x1 Conv2d) applied to the gwc feature -- GwcNet's own lastconv by default, ACVNet's
+        model-level concatconv (ACVNet/acv.py:104-107) when given."""
+        B = left.shape[0]
+        l2, l3, l4 = self._trunk(fe, left, right)
         if channels_last_out:
             # hand the layer2/3/4 outputs (and the concat head's output) to the volume builder as they are
             # (aggregation_umma.UmmaBackend.volume_from_cl): no torch.cat, no NCHW fp32 copy

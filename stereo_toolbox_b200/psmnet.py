@@ -86,13 +86,22 @@ class PSMNet(nn.Module):
                  <=1e-3 px), 'tf32' torch's default for convs (what the reference itself does on a GPU),
           'tf32_cl' same arithmetic as 'tf32' but channels-last activations: cuDNN's TF32 kernels are NHWC, and with
                  NCHW tensors ~46% of the extractor's GPU time is nchwToNhwc/nhwcToNchw transposes (profiles/ncu_launches_r01.txt),
-          'fp16' channels-last fp16 autocast.  None = 'fp32' for precision fp32, else 'tf32_cl'.
+          'fp16' channels-last fp16 autocast,
+          'umma' trunk + lastconv on the tcgen05 conv kernel in the storage format of the precision, the SPP branches
+                 (pooled to a handful of pixels) in fp32 torch (features_umma.UmmaGwcFeatures.psm).
+        None = 'fp32' for precision fp32, 'umma' for 'fp16x2' (exact: the whole model stays inside the fp32 bar), else 'tf32_cl'.
         feature_tf32 (legacy knob): False forces 'fp32'."""
         mode = self.feature_mode
         if self.feature_tf32 is False:
             mode = "fp32"
         if mode is None:
-            mode = "fp32" if self.precision == "fp32" else "tf32_cl"
+            mode = "fp32" if self.precision == "fp32" else ("umma" if self.precision == "fp16x2" else "tf32_cl")
+        if mode == "umma":
+            from .features_umma import UmmaGwcFeatures
+            if getattr(self, "_fe_umma", None) is None or self._fe_umma.precision != self._be.name:
+                self._fe_umma = UmmaGwcFeatures(self._be.name)
+            self._fe_umma.prof = self._be.prof
+            return self._fe_umma.psm(self.feature_extraction, left, right)
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = prev and mode != "fp32"
         try:
@@ -140,6 +149,20 @@ class PSMNet(nn.Module):
                 fl = self.feature_extraction(left.contiguous(memory_format=torch.channels_last))
                 fr = self.feature_extraction(right.contiguous(memory_format=torch.channels_last))
             fl, fr = fl.float(), fr.float()
+            return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=train_backend_for(self), all_heads=True)
+        if getattr(self, "train_features", "fp32") == "tf32":
+            # torch's own default for convolutions on a GPU (cudnn.allow_tf32), i.e. what the reference trainer computes
+            # without amp; channels-last so that cuDNN's NHWC tensor-core kernels run without layout transposes
+            if not getattr(self, "_fe_channels_last", False):
+                self.feature_extraction.to(memory_format=torch.channels_last)
+                self._fe_channels_last = True
+            prev = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = True
+            try:
+                fl = self.feature_extraction(left.contiguous(memory_format=torch.channels_last))
+                fr = self.feature_extraction(right.contiguous(memory_format=torch.channels_last))
+            finally:
+                torch.backends.cudnn.allow_tf32 = prev
             return self.aggregate(fl, fr, left.shape[2], left.shape[3], be=train_backend_for(self), all_heads=True)
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = prev and self.feature_mode not in (None, "fp32") and self.feature_tf32 is not False

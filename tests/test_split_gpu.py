@@ -153,7 +153,10 @@ def test_gwcnet_gc_golden_fp16x2(feature_mode):
     assert epe < 1e-3
 
 
-def test_psmnet_golden_fp16x2():
+@pytest.mark.parametrize("feature_mode", ["fp32", "umma"])
+def test_psmnet_golden_fp16x2(feature_mode):
+    """'umma': the SPP extractor's trunk and lastconv on the split tcgen05 kernel too (features_umma.UmmaGwcFeatures.psm), the
+    model's default on this precision."""
     import stereo_toolbox_b200 as S
     g = load_golden("psmnet.npz")
     sd, meta = golden_state("psmnet")
@@ -161,9 +164,12 @@ def test_psmnet_golden_fp16x2():
     net = S.PSMNet(meta["maxdisp"], precision="fp16x2")
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
-    net.feature_mode = "fp32"
+    if feature_mode == "fp32":
+        net.feature_mode = "fp32"
+    else:
+        assert net.feature_mode is None                   # default -> 'umma' on fp16x2
     with torch.no_grad():
         disp = net(left.cuda(), right.cuda()).cpu()
     epe = (disp - g["disp"]).abs().mean().item()
-    print(f"PSMNet fp16x2: EPE vs reference {epe:.3e} px")
+    print(f"PSMNet fp16x2 features={feature_mode}: EPE vs reference {epe:.3e} px")
     assert epe < 1e-3

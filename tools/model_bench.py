@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--cuda-graph", action="store_true", help="raft / igev: replay one captured GRU iteration")
     ap.add_argument("--update", default="", choices=["", "torch", "umma"],
                     help="raft / igev: update block in torch/cuDNN or on the tcgen05 2-D conv path (update_umma.py, exact fp16x2 format)")
+    ap.add_argument("--features", default="", help="2-D extractor mode of the 3-D-conv models (fp32 | tf32 | tf32_cl | fp16 | umma); default: the model's")
     ap.add_argument("--exact-glue", action="store_true", help="torch glue in true fp32 (no TF32): the arithmetic the parity tests pin")
     ap.add_argument("--channels-last", action="store_true", help="raft / igev / cfnet / pcwnet_gc: NHWC torch glue (model.channels_last)")
     args = ap.parse_args()
@@ -72,6 +73,8 @@ def main():
         net.channels_last = True
     if args.update:
         net.update_mode = args.update
+    if args.features:
+        net.feature_mode = args.features
     if args.exact_glue:
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -95,7 +98,7 @@ def main():
     ms = ts[len(ts) // 2]
     res = dict(model=args.model, precision=args.precision if args.model != "raft" else "fp32",
                shape=[args.batch, args.height, args.width], maxdisp=args.maxdisp,
-               iters=fwd.get("iters"), cuda_graph=args.cuda_graph, channels_last=args.channels_last, update=args.update or "torch", exact_glue=args.exact_glue, ms_per_forward=ms, maps_per_s=args.batch / (ms * 1e-3),
+               iters=fwd.get("iters"), cuda_graph=args.cuda_graph, channels_last=args.channels_last, update=args.update or "torch", features=args.features or "default", exact_glue=args.exact_glue, ms_per_forward=ms, maps_per_s=args.batch / (ms * 1e-3),
                peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, out_shape=list(out.shape),
                finite=bool(torch.isfinite(out.float()).all().item()))
     print(json.dumps(res))

@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--maxdisp", type=int, default=192)
     ap.add_argument("--top", type=int, default=25)
-    ap.add_argument("--features", default="amp")
+    ap.add_argument("--features", default="tf32")
     args = ap.parse_args()
     import stereo_toolbox_b200 as S
     from stereo_toolbox_b200.synth import synth_state_dict, synth_pair, synth_gt

@@ -98,7 +98,7 @@ def run(height=384, width=512, batch=2, steps=5, warmup=2, maxdisp=192, lr=1e-4,
     if rank == 0:
         bus = 2.0 * (world - 1) / world * bucket.nbytes / (ar_pure * 1e-3) / 1e9 if world > 1 else 0.0
         kind = "fp32 exact path" if precision == "fp32" else \
-            f"{precision}: tcgen05 forward + dgrad and tensor-core (mma.sync) wgrad on 16-bit channels-last activations, fp32 BatchNorm statistics / volumes / head; 2-D extractor (torch): {'autocast ' + precision if features == 'amp' else 'fp32'}"
+            f"{precision}: tcgen05 forward + dgrad and tensor-core (mma.sync) wgrad on 16-bit channels-last activations, fp32 BatchNorm statistics / volumes / head; 2-D extractor (torch): {'autocast ' + precision if features == 'amp' else features}"
         out = {
             "metric": f"PSMNet training pairs/sec ({kind}; forward+backward in libstb200.so, one flat NCCL gradient all-reduce)",
             "value": pairs / (step_ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -127,7 +127,7 @@ def main():
     ap.add_argument("--lr", type=float, default=1e-4)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp16"],
                     help="fp32 = exact training path; bf16 / fp16 = train16.Umma16TrainBackend (tcgen05 forward + dgrad)")
-    ap.add_argument("--features", default="fp32", choices=["fp32", "amp"],
+    ap.add_argument("--features", default="fp32", choices=["fp32", "tf32", "amp"],
                     help="torch 2-D extractor: exact fp32, or autocast in the training dtype (the reference's amp recipe)")
     args = ap.parse_args()
     import torch.distributed as dist
