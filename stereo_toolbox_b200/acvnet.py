@@ -115,7 +115,7 @@ def _patch(c, dil):
 
 
 class ACVNet(nn.Module):
-    def __init__(self, maxdisp=192, attn_weights_only=False, freeze_attn_weights=False, precision="fp32"):
+    def __init__(self, maxdisp=192, attn_weights_only=False, freeze_attn_weights=False, precision="auto"):
         super().__init__()
         self.maxdisp = maxdisp
         self.attn_weights_only = attn_weights_only
@@ -143,6 +143,7 @@ class ACVNet(nn.Module):
         self.set_precision(precision)
 
     set_precision = GwcNet.set_precision
+    _resolve_auto_precision = GwcNet._resolve_auto_precision
     _features = GwcNet._features
 
     def _concat_features(self, fl, fr):
@@ -204,6 +205,7 @@ class ACVNet(nn.Module):
     def forward(self, left, right):
         if self.training:
             return self._forward_train(left, right)
+        self._resolve_auto_precision(left)
         fl, fr = self._features(left, right)
         return self.aggregate(fl, fr, left.shape[2], left.shape[3])
 

@@ -42,7 +42,7 @@ def _classif():
 
 
 class PSMNet(nn.Module):
-    def __init__(self, maxdisp=192, precision="fp32"):
+    def __init__(self, maxdisp=192, precision="auto"):
         super().__init__()
         self.maxdisp = maxdisp
         self.feature_extraction = PsmFeatures()
@@ -58,6 +58,11 @@ class PSMNet(nn.Module):
         self.set_precision(precision)
 
     def set_precision(self, precision: str):
+        """'fp32' | 'fp16x2' | 'fp16' | 'bf16'; 'auto' (constructor default): 'fp16x2', the exact tensor-core path, from the
+        first CUDA inference forward on, 'fp32' until then (see GwcNet.set_precision)."""
+        self._auto_precision = precision == "auto"
+        if self._auto_precision:
+            precision = "fp32"
         self.precision = precision
         self._be = make_backend(precision)
         return self
@@ -129,6 +134,8 @@ class PSMNet(nn.Module):
     def forward(self, left, right):
         if self.training:
             return self._forward_train(left, right)
+        if getattr(self, "_auto_precision", False) and left.is_cuda:
+            self.set_precision("fp16x2")
         fl, fr = self._features(left, right)
         return self.aggregate(fl, fr, left.shape[2], left.shape[3])
 

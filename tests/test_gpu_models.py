@@ -20,7 +20,7 @@ def test_gwcnet_golden_fp32(key):
     import stereo_toolbox_b200 as S
     g = load_golden(f"{key}.npz")
     sd, meta = golden_state(key)
-    net = (S.GwcNet_GC if key == "gwcnet_gc" else S.GwcNet_G)(meta["maxdisp"])
+    net = (S.GwcNet_GC if key == "gwcnet_gc" else S.GwcNet_G)(meta["maxdisp"], precision="fp32")
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
     left, right = _pair(meta)
@@ -38,7 +38,7 @@ def test_psmnet_golden_fp32():
     import stereo_toolbox_b200 as S
     g = load_golden("psmnet.npz")
     sd, meta = golden_state("psmnet")
-    net = S.PSMNet(meta["maxdisp"])
+    net = S.PSMNet(meta["maxdisp"], precision="fp32")
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
     left, right = _pair(meta)
@@ -56,7 +56,7 @@ def test_gwcnet_oracle_fp32_wider():
     sd, _ = golden_state("gwcnet_gc")
     left, right = synth_pair(1, 96, 176, seed=5, shift=9)
     want, aux = M.gwcnet_forward(sd, left, right, 48, True, return_aux=True)
-    net = S.GwcNet_GC(48)
+    net = S.GwcNet_GC(48, precision="fp32")
     net.load_state_dict(sd)
     net = net.cuda().eval()
     with torch.no_grad():
@@ -149,7 +149,7 @@ def test_acvnet_golden_fp32():
     from stereo_toolbox_b200.synth import synth_pair
     g = load_golden("acvnet.npz")
     sd, meta = golden_state("acvnet")
-    net = S.ACVNet(meta["maxdisp"])
+    net = S.ACVNet(meta["maxdisp"], precision="fp32")
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
     left, right = synth_pair(1, 64, 144, seed=3, shift=meta["shift"])
@@ -174,7 +174,7 @@ def test_acvnet_oracle_fp32_padded_shape():
     sd, _ = golden_state("acvnet")
     left, right = synth_pair(1, 96, 112, seed=6, shift=4)          # 1/16 scale: 6 x 7
     want = M.acvnet_forward(sd, left, right, 64)
-    net = S.ACVNet(64)
+    net = S.ACVNet(64, precision="fp32")
     net.load_state_dict(sd)
     net = net.cuda().eval()
     with torch.no_grad():
@@ -246,3 +246,27 @@ def test_pcwnet_gc_golden():
             assert epe < 1e-3, f"EPE vs reference {epe}"
     d = (stage["fp16"] - stage["fp32"]).abs().mean().item()
     assert d < 1e-2, f"cost-volume stage disparity fp16 vs fp32 path: {d} px"
+
+
+@pytest.mark.parametrize("key", ["gwcnet_gc", "psmnet", "acvnet"])
+def test_default_constructor_runs_the_exact_tensor_core_path(key):
+    """precision='auto' (the constructor default of GwcNet / PSMNet / ACVNet): the first CUDA inference forward switches the
+    model to 'fp16x2' -- a drop-in user who never calls set_precision gets the tensor-core path, inside the fp32 bar."""
+    import stereo_toolbox_b200 as S
+    g = load_golden(f"{key}.npz")
+    sd, meta = golden_state(key)
+    net = {"gwcnet_gc": S.GwcNet_GC, "psmnet": S.PSMNet, "acvnet": S.ACVNet}[key](meta["maxdisp"])
+    assert net.precision == "fp32" and net._auto_precision            # nothing resolved before a CUDA forward
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    if key == "acvnet":
+        from stereo_toolbox_b200.synth import synth_pair
+        left, right = synth_pair(1, 64, 144, seed=3, shift=meta["shift"])
+    else:
+        left, right = _pair(meta)
+    with torch.no_grad():
+        disp = net(left.cuda(), right.cuda()).cpu()
+    assert net.precision == "fp16x2" and not net._auto_precision
+    epe = (disp - g["disp"]).abs().mean().item()
+    print(f"{key} default constructor -> {net.precision}: EPE vs reference {epe:.3e} px")
+    assert epe < 1e-3
