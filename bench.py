@@ -348,6 +348,39 @@ def extras(line, a, sd, net, left, right, ref, precision):
         except Exception as e:      # never lose the headline to a secondary leg
             line["reference_gpu_eager"] = {"error": repr(e)[:200]}
         torch.cuda.empty_cache()
+        # BASELINE config 4: RAFT-Stereo, 32 GRU iterations at 512x1024, batch 1 -- all-pairs correlation, pyramid, lookup
+        # and the update block (every conv on tcgen05, exact fp16x2 format; update_umma.py) in libstb200.so, one captured
+        # iteration replayed; beside it the torch / cuDNN update block in true fp32 (the arithmetic the goldens pin) and
+        # its distance to ours on the same inputs
+        try:
+            from stereo_toolbox_b200.synth import synth_pair, synth_state_dict
+            raft = S.RAFTStereo()
+            raft.load_state_dict(synth_state_dict(raft.state_dict(), 0), strict=True)
+            raft = raft.cuda().eval()
+            l4, r4 = (t.cuda() for t in synth_pair(1, 512, 1024, seed=4, shift=9))
+            prev = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False               # exact torch encoders on both sides: isolates the update block
+            try:
+                raft.update_mode, raft.cuda_graph = "torch", False
+                ms_t = timed_steps(lambda: raft(l4, r4, iters=32), 2, 1)
+                want = raft(l4, r4, iters=32)
+                raft.update_mode, raft.cuda_graph = "auto", True
+                got = raft(l4, r4, iters=32)
+                ms_x = timed_steps(lambda: raft(l4, r4, iters=32), 3, 2)
+            finally:
+                torch.backends.cudnn.allow_tf32 = prev
+            ms_u = timed_steps(lambda: raft(l4, r4, iters=32), 3, 2)  # torch encoders at torch's default (TF32)
+            line["raft_stereo"] = {"config": "BASELINE config 4: RAFT-Stereo 32 iterations, 512x1024, batch 1", "unit": "maps/s",
+                                   "value": 1e3 / ms_u, "ms_per_forward": ms_u,
+                                   "ms_per_forward_exact_encoders": ms_x, "update_block": "tcgen05 fp16x2 (update_umma.py), CUDA-graph replay",
+                                   "torch_fp32_ms_per_forward": ms_t,
+                                   "epe_vs_torch_fp32_px": float((got - want).abs().mean()),
+                                   "note": "synthetic (untrained) weights: the recurrence is not contractive, so the distance after 32 "
+                                           "iterations amplifies last-bit differences; the golden-fixture test is tests/test_update_umma_gpu.py"}
+            del raft, l4, r4
+        except Exception as e:
+            line["raft_stereo"] = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
         if a.workload == "kitti":
             try:
                 select_workload("sceneflow")

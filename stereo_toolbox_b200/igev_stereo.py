@@ -392,8 +392,9 @@ class IGEVStereo(IGEVCostVolume):
         coords = torch.arange(w, device=match_left.device).float().reshape(1, 1, w, 1).repeat(b, h, 1, 1)
         disp = init_disp
         disp_preds = []
-        if (getattr(self, "update_mode", "torch") == "umma" and test_mode and not self.training and disp.is_cuda
-                and not torch.is_grad_enabled() and iters >= 1):
+        # update_mode: "auto" (default) = the tensor-core update block whenever it applies (CUDA inference), "torch" = torch/cuDNN
+        if (getattr(self, "update_mode", "auto") in ("umma", "auto") and test_mode and not self.training and disp.is_cuda
+                and not torch.is_grad_enabled() and iters >= 1 and all(d % 16 == 0 for d in a.hidden_dims)):
             disp, mask_feat_4 = self._iterate_umma(net_list, inp_list, geo_fn, coords, disp.detach(), iters)
             return self.upsample_disp(disp, mask_feat_4, stem_2x)
         if (getattr(self, "cuda_graph", False) and test_mode and not self.training and iters > 1 and disp.is_cuda

@@ -3,8 +3,9 @@
 Same constructor (``RAFTStereo(args=None, imagenet_norm=False)``, ``args`` a Namespace merged via ``vars()``),
 same ``forward(image1, image2, iters=None, flow_init=None, test_mode=False)`` and state-dict names.  The hot
 path of the iterative model -- all-pairs 1-D correlation, its 1x2 average pyramid and the 4-level x 9-tap
-lookup executed every GRU iteration (``CorrBlock1D``, RAFTStereo/corr.py:110-156) -- runs in libstb200.so;
-encoders, ConvGRUs and convex upsampling stay in torch ("next").
+lookup executed every GRU iteration (``CorrBlock1D``, RAFTStereo/corr.py:110-156) -- runs in libstb200.so, and so do, for
+CUDA inference, the update block (every conv on the tcgen05 2-D conv path, ``update_umma.py``; ``update_mode``) and the
+learned convex upsampling; the encoders stay in torch (rank 2).
 """
 from __future__ import annotations
 
@@ -329,7 +330,7 @@ class RAFTStereo(nn.Module):
     def _iterate_umma(self, net_list, inp_list, corr_fn, coords0, coords1, iters):
         """The GRU loop with the update block on the tensor-core 2-D conv path (update_umma.UmmaRaftUpdate: every conv of
         the block on tcgen05 in the exact 'fp16x2' format, hidden states resident in that layout).
-        Opt-in: ``model.update_mode = "umma"`` (inference, no slow_fast_gru).  With ``model.cuda_graph`` one iteration is
+        The default for CUDA inference (``model.update_mode = "auto"``; ``"torch"`` selects the torch block).  With ``model.cuda_graph`` one iteration is
         captured once per shape and replayed.  Returns (coords1, up_mask of the last iterate)."""
         from .update_umma import UmmaRaftUpdate
         upd = self.__dict__.get("_umma_update")
@@ -426,7 +427,13 @@ class RAFTStereo(nn.Module):
                 net_list, up_mask, coords1 = self._iteration(net_list, inp_list, corr_fn, coords0, coords1)
                 preds.append(-self.upsample_flow(coords1 - coords0, up_mask)[:, :1])
             return preds
-        if getattr(self, "update_mode", "torch") == "umma" and not a.slow_fast_gru and image1.is_cuda:
+        # update_mode: "auto" (default) = "umma" whenever it applies (CUDA inference, no slow_fast_gru, hidden widths that are
+        # whole 16-channel blocks), "torch" = the reference-style torch/cuDNN update block, "umma" = insist
+        mode = getattr(self, "update_mode", "auto")
+        umma_ok = image1.is_cuda and not a.slow_fast_gru and all(d % 16 == 0 for d in a.hidden_dims) and not torch.is_grad_enabled()
+        if mode == "umma" and not umma_ok:
+            raise RuntimeError("update_mode='umma' needs CUDA tensors, torch.no_grad(), slow_fast_gru=False and hidden_dims % 16 == 0")
+        if mode in ("umma", "auto") and umma_ok:
             coords1, up_mask = self._iterate_umma(net_list, inp_list, corr_fn, coords0, coords1, iters)
             return -self.upsample_flow(coords1 - coords0, up_mask)[:, :1]
         if getattr(self, "cuda_graph", False) and flow_init is None and iters > 1:

@@ -75,6 +75,7 @@ def test_raft_stereo_golden():
     net = S.RAFTStereo()
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
+    net.update_mode = "torch"              # this test pins the torch / cuDNN update block (the default is the tensor-core one)
     left, right = synth_pair(1, 64, 128, seed=2, shift=meta["shift"])
     prev = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False       # the 2-D encoders/GRUs are torch; keep them fp32 for the comparison
@@ -98,6 +99,7 @@ def test_raft_stereo_cuda_graph_iteration_is_bit_identical():
     net = S.RAFTStereo()
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
+    net.update_mode = "torch"              # this test pins the torch / cuDNN update block (the default is the tensor-core one)
     left, right = synth_pair(1, 64, 128, seed=2, shift=meta["shift"])
     prev = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
@@ -134,6 +136,7 @@ def test_raft_stereo_oracle_512x1024_shape_slice():
     net = S.RAFTStereo()
     net.load_state_dict(sd)
     net = net.cuda().eval()
+    net.update_mode = "torch"              # this test pins the torch / cuDNN update block (the default is the tensor-core one)
     prev = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:

@@ -19,6 +19,7 @@ def _run(precision, **fwd):
     net = S.IGEVStereo({"max_disp": meta["max_disp"]}, precision=precision)
     net.load_state_dict(sd, strict=True)          # the reference's own parameter names (timm-named MobileNetV2 trunk)
     net = net.cuda().eval()
+    net.update_mode = "torch"                     # these tests pin the torch / cuDNN update block (the default is the tensor-core one)
     left, right = synth_pair(1, 64, 128, seed=8, shift=meta["shift"])
     prev = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False       # the 2-D networks are torch glue; keep them fp32 for the comparison
@@ -71,6 +72,7 @@ def test_igev_stereo_cuda_graph_iteration_matches_eager():
     net = S.IGEVStereo({"max_disp": meta["max_disp"]})
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
+    net.update_mode = "torch"
     left, right = synth_pair(1, 64, 128, seed=8, shift=meta["shift"])
     left2, right2 = synth_pair(1, 64, 128, seed=9, shift=3)
     prev = torch.backends.cudnn.allow_tf32
@@ -100,7 +102,7 @@ def test_igev_stereo_golden_update_on_tensor_cores(graph):
     net = S.IGEVStereo({"max_disp": meta["max_disp"]})
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
-    net.update_mode = "umma"
+    assert getattr(net, "update_mode", "auto") == "auto"          # the default: tensor-core update block for CUDA inference
     net.cuda_graph = graph
     left, right = synth_pair(1, 64, 128, seed=8, shift=meta["shift"])
     prev = torch.backends.cudnn.allow_tf32

@@ -98,7 +98,7 @@ def test_raft_stereo_golden_update_on_tensor_cores(graph):
     net = S.RAFTStereo()
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
-    net.update_mode = "umma"
+    assert getattr(net, "update_mode", "auto") == "auto"          # the default: tensor-core update block for CUDA inference
     net.cuda_graph = graph
     left, right = synth_pair(1, 64, 128, seed=2, shift=meta["shift"])
     prev = torch.backends.cudnn.allow_tf32
