@@ -268,7 +268,7 @@ def main():
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import train_step
-            train = train_step.run(576, 960, 1, steps=3, warmup=1, precision="bf16", features="tf32")
+            train = train_step.run(576, 960, 1, steps=3, warmup=2, precision="bf16", features="tf32")
         except Exception as e:
             train = {"error": repr(e)[:300]}
     if rank != 0:

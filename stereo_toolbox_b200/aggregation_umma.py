@@ -70,6 +70,9 @@ def pad_channels(c: int) -> int:
     return (c + 63) // 64 * 64
 
 
+_TILE_IDX_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
 def _iarr(vals):
     return (ctypes.c_int * len(vals))(*vals)
 
@@ -101,12 +104,33 @@ class UmmaPlan:
             else:
                 wpad[:, :cin] = w
             w = wpad
-        self.simt = ops.ConvPlan(w, bnp, stride, pad, tr, opad, eps, bias=conv.bias)   # fp32 taps (+ shift) for the companion
-        self.shift = self.simt.shift
+        # fp32 tap plan of the CUDA-core companion: built lazily (its ~30 small tensor ops per layer are pure overhead on the
+        # tensor-core path, and the 16-bit training backend rebuilds every plan after every optimizer step)
+        self._simt_args = (w, bnp, stride, pad, tr, opad, eps, conv.bias)
+        self._simt = None
+        self.opad = opad
+        if bnp is not None:
+            gamma, beta, mean, var = [t.detach().float() for t in bnp]
+            scale = gamma / torch.sqrt(var + eps)
+            self.shift = (beta - mean * scale).contiguous()
+        else:
+            scale, self.shift = None, None
+        if conv.bias is not None:       # BN(y + b) = scale*y + (shift + scale*b)
+            sb = conv.bias.detach().float() if scale is None else scale * conv.bias.detach().float()
+            self.shift = sb.contiguous() if self.shift is None else (self.shift + sb).contiguous()
         self.umma_ok = (not FORCE_SIMT) and self._build_umma(w, bnp, eps)
 
+    @property
+    def simt(self):
+        if self._simt is None:
+            w, bnp, stride, pad, tr, opad, eps, bias = self._simt_args
+            self._simt = ops.ConvPlan(w, bnp, stride, pad, tr, opad, eps, bias=bias)
+        return self._simt
+
     def out_size(self, n):
-        return self.simt.out_size(n)
+        if self.tr:
+            return (n - 1) * self.stride - 2 * self.pad + self.k + self.opad
+        return (n + 2 * self.pad - self.k) // self.stride + 1
 
     def _build_umma(self, w, bnp, eps) -> bool:
         cin, cout, k, stride, pad, tr = self.cin_tensor, self.cout, self.k, self.stride, self.pad, self.tr
@@ -169,7 +193,16 @@ class UmmaPlan:
                 self.in_off, self.out_stride, self.merge, self.deconv_merge = mn, stride, False, True
         full = torch.zeros(k * k * k, cpad, cin, device=w.device)
         full[:, :cout] = wt.reshape(k * k * k, cout, cin)
-        tiles = full[torch.tensor(tile_src, device=w.device)]
+        # (identity order: no gather; otherwise the index tensor is cached per device -- building it from a Python list is a
+        #  pageable host-to-device copy, i.e. a stream synchronisation per plan, and training rebuilds every plan every step)
+        if tile_src == list(range(k ** 3)):
+            tiles = full
+        else:
+            key = (tuple(tile_src), str(w.device))
+            idx = _TILE_IDX_CACHE.get(key)
+            if idx is None:
+                idx = _TILE_IDX_CACHE[key] = torch.tensor(tile_src, device=w.device)
+            tiles = full.index_select(0, idx)
         self.wexp = 0
         if self.split:
             self.wexp = split_weight_exponent(tiles)

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--maxdisp", type=int, default=192)
     ap.add_argument("--top", type=int, default=25)
     ap.add_argument("--features", default="tf32")
+    ap.add_argument("--cpu", action="store_true", help="also: host issue time of a step and the host-side top list")
     args = ap.parse_args()
     import stereo_toolbox_b200 as S
     from stereo_toolbox_b200.synth import synth_state_dict, synth_pair, synth_gt
@@ -46,12 +47,14 @@ def main():
     left, right = left.cuda(), right.cuda()
     gt = synth_gt(1, args.height, args.width).cuda() * (args.maxdisp / 32.0)
     mask = (gt > 0) & (gt < args.maxdisp)
+    maskf, nvalid = mask.float(), mask.float().sum().clamp_min(1.0)
 
     def step():
         for p in net.parameters():
             p.grad = None
         preds = net(left, right)
-        loss = sum(w * F.smooth_l1_loss(p.squeeze(1)[mask], gt[mask], reduction="mean") for w, p in zip((0.5, 0.7, 1.0), preds))
+        loss = sum(w * (F.smooth_l1_loss(p.squeeze(1), gt, reduction="none") * maskf).sum() / nvalid
+                   for w, p in zip((0.5, 0.7, 1.0), preds))       # masked mean without boolean indexing (no device sync)
         loss.backward()
 
     for _ in range(2):
@@ -80,6 +83,19 @@ def main():
     print(f"GPU time of one step: {total / 1e3:.1f} ms over {sum(v[1] for v in fam.values())} kernels")
     for k, (us, n) in sorted(fam.items(), key=lambda kv: -kv[1][0]):
         print(f"  {k:38s} {us / 1e3:8.2f} ms  {100 * us / total:5.1f} %  {n:5d} launches")
+    if args.cpu:
+        import time
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step()
+        t_host = time.perf_counter() - t0          # host time to ISSUE a step (no sync inside unless the step syncs itself)
+        torch.cuda.synchronize()
+        t_all = time.perf_counter() - t0
+        print(f"host issue time of one step: {t_host * 1e3:.1f} ms, until the GPU is done: {t_all * 1e3:.1f} ms")
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof2:
+            step()
+            torch.cuda.synchronize()
+        print(prof2.key_averages().table(sort_by="self_cpu_time_total", row_limit=30, max_name_column_width=60))
     print("top kernels:")
     for k, (us, n) in sorted(names.items(), key=lambda kv: -kv[1][0])[:args.top]:
         print(f"  {us / 1e3:8.2f} ms {n:5d}x  {k}")

@@ -48,6 +48,7 @@ def run(height=384, width=512, batch=2, steps=5, warmup=2, maxdisp=192, lr=1e-4,
     left, right = left.cuda(), right.cuda()
     gt = synth_gt(batch, height, width).cuda() * (maxdisp / 32.0)
     mask = (gt > 0) & (gt < maxdisp)
+    maskf, nvalid = mask.float(), mask.float().sum().clamp_min(1.0)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     t_step, t_ar, t_fb = [], [], []
     launches0 = _lib.LAUNCH_COUNT
@@ -59,14 +60,16 @@ def run(height=384, width=512, batch=2, steps=5, warmup=2, maxdisp=192, lr=1e-4,
         e0.record()
         bucket.zero_()
         preds = net(left, right)
-        loss = sum(w * F.smooth_l1_loss(p.squeeze(1)[mask], gt[mask], reduction="mean") for w, p in zip((0.5, 0.7, 1.0), preds))
+        # mean smooth-L1 over the masked pixels (trainer_torchrun.py:272-278) written as a masked reduction: the same value as
+        # F.smooth_l1_loss(p[mask], gt[mask]) without boolean indexing, whose nonzero() forces a device sync per prediction
+        loss = sum(w * (F.smooth_l1_loss(p.squeeze(1), gt, reduction="none") * maskf).sum() / nvalid
+                   for w, p in zip((0.5, 0.7, 1.0), preds))
         loss.backward()
         e1.record()
         bucket.allreduce_()
         e2.record()
-        with torch.no_grad():
-            for p in bucket.params:
-                p.add_(p.grad, alpha=-lr)
+        with torch.no_grad():       # SGD update as one multi-tensor launch sequence instead of one launch per parameter
+            torch._foreach_add_(list(bucket.params), [p.grad for p in bucket.params], alpha=-lr)
         e3.record()
         torch.cuda.synchronize()
         if it >= warmup:
