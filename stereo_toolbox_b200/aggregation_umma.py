@@ -25,6 +25,7 @@ ES_VARIANT = int(os.environ.get("STB_TMA_ES_VARIANT", "0"))      # box extent co
 FORCE_SIMT = os.environ.get("STB_UMMA_FORCE_SIMT", "0") == "1"
 KWMERGE = os.environ.get("STB_UMMA_KWMERGE", "1") == "1"          # merge the 3 kw taps along N (N = 3*Cout) for k3 s1 convs
 DECONV_MERGE = os.environ.get("STB_UMMA_DECONV_MERGE", "1") == "1"  # transposed conv: 8 parity classes in one accumulator round
+PAIRMERGE = os.environ.get("STB_UMMA_PAIRMERGE", "1") == "1"        # stride-2 convs: kw = 0 / 2 taps as one N = 2*Cn MMA
 KDEPTH3D = os.environ.get("STB_UMMA_KDEPTH3D", "1") == "1"          # 3-D layers: K-chunks accumulated in TMEM when the weights fit
 SIMT_STRIDE2 = os.environ.get("STB_UMMA_SIMT_STRIDE2", "0") == "1"   # keep strided convs on the CUDA-core companion
 TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp16x2": torch.float16}
@@ -191,6 +192,25 @@ class UmmaPlan:
                         i = j + 1
                 te.append(len(dz)); od0.append(0); oh0.append(0); ow0.append(0)
                 self.in_off, self.out_stride, self.merge, self.deconv_merge = mn, stride, False, True
+        # ---- stride-2 pair merge: the kw = 0 and kw = 2 taps read the SAME w-parity sub-tile one position apart, so they run as
+        # one MMA against the two contiguous weight tiles (N = 2*Cn instead of two N = Cn MMAs: the N = 32 MMAs of these layers
+        # are operand-bandwidth bound, 40 clk for 16 clk of math) and the epilogue realigns block 1 by one lane (flags bit7)
+        self.pair_merge = bool(PAIRMERGE and not tr and in_stride == 2 and k == 3 and pad == 1)
+        if self.pair_merge:
+            e = [kk - pad for kk in range(k)]
+            par = [x % in_stride for x in e]
+            off = [(x - p_) // in_stride for x, p_ in zip(e, par)]
+            mn = min(off)
+            assert par[0] == par[2] == 1 and off[2] - off[0] == 1 and par[1] == 0
+            tile_src, nblk, cls0 = [], [], []
+            for a in range(k):
+                for b in range(k):
+                    dz.append(e[a]); dh.append(off[b] - mn); dw.append(off[0] - mn); sub.append(par[b] * 2 + 1)
+                    widx.append(len(tile_src)); nblk.append(2); cls0.append(0)
+                    tile_src += [flat(a, b, 0), flat(a, b, 2)]
+                    dz.append(e[a]); dh.append(off[b] - mn); dw.append(off[1] - mn); sub.append(par[b] * 2 + 0)
+                    widx.append(len(tile_src)); nblk.append(1); cls0.append(0)
+                    tile_src.append(flat(a, b, 1))
         full = torch.zeros(k * k * k, cpad, cin, device=w.device)
         full[:, :cout] = wt.reshape(k * k * k, cout, cin)
         # (identity order: no gather; otherwise the index tensor is cached per device -- building it from a Python list is a
@@ -221,7 +241,7 @@ class UmmaPlan:
             mn = min(off)
             tb.append(0)
             self.merge = KWMERGE and in_stride == 1 and k == 3 and pad == 1
-            for a in range(k):
+            for a in range(0 if self.pair_merge else k):
                 for b in range(k):
                     if self.merge:
                         # one MMA per (kd,kh) against the 3 contiguous weight tiles (kd,kh,0..2): N = 3*Cout;
@@ -421,7 +441,7 @@ class UmmaBackend:
                           plan.c_tb, plan.c_te, plan.c_od0, plan.c_oh0, plan.c_ow0, plan.in_stride, plan.out_stride,
                           nsteps, nh, nw, plan.in_off, plan.in_off, ACT[act], int(out_fp32),
                           BO_MODE | (ES_VARIANT << 1) | (4 if plan.merge else 0) | (8 if plan.deconv_merge else 0)
-                          | (32 if plan.kdepth else 0) | ((SPLIT_FLAG | (plan.wexp << 16)) if self.split else 0),
+                          | (32 if plan.kdepth else 0) | (128 if plan.pair_merge else 0) | ((SPLIT_FLAG | (plan.wexp << 16)) if self.split else 0),
                           self.dchunk, _stream())
             else:
                 assert not self.split

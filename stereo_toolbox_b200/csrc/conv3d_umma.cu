@@ -82,6 +82,7 @@ struct UArgs {
     int ntiles;                      // work items (b, depth chunk, h tile, w tile); CTAs are persistent and stride over them
     int ngroups;
     int nslices;                     // output-channel slices (of Cn) handled inside ONE launch: CTA c takes slice c % nslices
+    int cluster;                     // > 1: the nslices CTAs of a tile form a thread-block cluster and share every plane load (TMA multicast)
     float oscale;                    // SPLIT: the packed weights carry a factor 2^s (keeps their lo halves out of the fp16
                                      // subnormals); accumulators are multiplied by oscale = 2^-s before shift / residual
     UClass cls[MAX_UCLASS];
@@ -360,16 +361,23 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int trace_rounds = (!LEAN && trace_buf && blockIdx.x == 0) ? g_umma_trace_rounds : 0;
     const int dbg = LEAN ? 0 : a.debug;
 
+    // Cluster mode: the CTAs of a cluster (= the output-channel slices of one tile sequence) walk identical plane sequences; every
+    // plane box is issued by ONE of them, round robin, and multicast into the ring slot of all of them.  A slot may be refilled
+    // once the issuers of ALL CTAs have released it: plane_empty counts 2 * ncl arrivals, delivered by multicast commits.
+    const int ncl = a.cluster > 1 ? a.cluster : 1;
+    const uint32_t crank = ncl > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << ncl) - 1u);
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
         const int n_grp = a.nM * (a.cblocks == 8 ? 8 : 1) >= 2 ? 2 : 1;           // active epilogue groups
-        for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 2); }
+        for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 2 * ncl); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * n_grp); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_holder, a.tmem_cols);
     tc_fence_before();
-    __syncthreads();
+    if (ncl > 1) cluster_sync_all();          // no CTA may multicast into a peer whose barriers are not initialised yet
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
@@ -384,6 +392,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                             (i * a.w_tile_stride + a.w_kc_off) * a.w_rows + cout_off);
             int slot = 0;
             uint32_t eph = 1;                      // parity to wait for on plane_empty[slot] (fresh barrier: passes)
+            uint32_t gbox = 0;                     // running box counter, identical in every CTA of a cluster: box j is issued by CTA j % ncl
             for (int tile = tile0; tile < a.ntiles && !(dbg & 1); tile += tstride) {
                 const UTile u = decode_tile(a, tile);
                 const int ih0 = (u.jh0 + a.in_h_off) * a.in_stride, iw0 = (u.jw0 + a.in_w_off) * a.in_stride;
@@ -395,11 +404,19 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         // 2-D conv with Cin = kdepth K-chunks: pseudo-plane P = image*kdepth + chunk; the taps of chunk c
                         // carry dz = c, so all chunks accumulate in TMEM inside one launch (no fp32 workspace round trip)
                         const int P = u.p_first + n, img = (P + 64 * a.kdepth) / a.kdepth - 64, chunk = P - img * a.kdepth;   // floor division: 3-D planes may be negative (padding)
-                        tma_load_5d(dst, &tm_x, &plane_full[slot], chunk * (a.ROWB >> 1), iw0, ih0, img, u.b);
+                        if (ncl == 1) tma_load_5d(dst, &tm_x, &plane_full[slot], chunk * (a.ROWB >> 1), iw0, ih0, img, u.b);
+                        else if (gbox % (uint32_t)ncl == crank)
+                            tma_load_5d_mc(dst, &tm_x, &plane_full[slot], chunk * (a.ROWB >> 1), iw0, ih0, img, u.b, cmask);
+                        ++gbox;
                     } else {
-                        for (int sb = 0; sb < a.nsub; ++sb)       // sub-tile sb = (h parity, w parity) for stride 2
-                            tma_load_5d(dst + (size_t)sb * a.chunk_bytes, &tm_x, &plane_full[slot], a.cin_off,
-                                        iw0 + (sb & 1), ih0 + (sb >> 1), u.p_first + n, u.b);
+                        for (int sb = 0; sb < a.nsub; ++sb, ++gbox) {     // sub-tile sb = (h parity, w parity) for stride 2
+                            if (ncl == 1)
+                                tma_load_5d(dst + (size_t)sb * a.chunk_bytes, &tm_x, &plane_full[slot], a.cin_off,
+                                            iw0 + (sb & 1), ih0 + (sb >> 1), u.p_first + n, u.b);
+                            else if (gbox % (uint32_t)ncl == crank)
+                                tma_load_5d_mc(dst + (size_t)sb * a.chunk_bytes, &tm_x, &plane_full[slot], a.cin_off,
+                                               iw0 + (sb & 1), ih0 + (sb >> 1), u.p_first + n, u.b, cmask);
+                        }
                     }
                     if (++slot == a.R) { slot = 0; eph ^= 1; }
                 }
@@ -421,7 +438,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const int ksteps = a.ROWB / 32;
             // The per-tap records hold ABSOLUTE encoded addresses (the host knows this kernel's dynamic-smem base, see
             // launch_one): everything the issue blocks need is an LDCU away, never an R2UR.
-            if (smem_u32(smem) != a.smem_base) asm volatile("trap;");
+            if ((smem_u32(smem) & 0xFFFFFFu) != a.smem_base) asm volatile("trap;");      // low 24 bits: CTA-local offset (cluster rank above)
             const int nM = a.nM, R = a.R, sd = a.sd_in, nclass = a.nclass;
             const uint32_t ncol = (uint32_t)(a.Cn * a.cblocks);
             mbar_wait(bar_w, 0);
@@ -441,7 +458,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             auto release_upto = [&](int n) {      // each arrival fires when every MMA this thread issued so far has completed
                 while (released < n) {
                     wait_upto(released + 1);      // never hand back a plane that has not landed (phase safety)
-                    mma_commit(&plane_empty[rslot]);
+                    if (ncl > 1) mma_commit_mc(&plane_empty[rslot], cmask);
+                    else mma_commit(&plane_empty[rslot]);
                     ++released;
                     if (++rslot == R) rslot = 0;
                 }
@@ -711,6 +729,21 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         for (int i = 0; i < 32; ++i)
                             f[i] = __uint_as_float(v0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), ms) +
                                    __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2 * ms);
+                    } else if (!LEAN && merge == 2) {
+                        // stride-2 pair merge: block 0 = kw 0 (+ the un-merged kw 1 taps), block 1 = kw 2 evaluated one padded
+                        // position early: out[q] = P_0[q] + P_1[q+1]
+                        uint32_t v0[32], v1[32];
+                        tmem_ld_32x32(taddr, v0);
+                        tmem_ld_32x32(taddr + (uint32_t)Cn, v1);
+                        tmem_ld_wait();
+                        if (item + 2 >= items && c0 + 32 >= Cn) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            f[i] = __uint_as_float(v0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), 1);
                     } else {
                         uint32_t v[32];
                         tmem_ld_32x32(taddr, v);
@@ -804,7 +837,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (ncl > 1) cluster_sync_all();          // peers may still multicast plane data / slot releases into this CTA until they are done
+    else __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
@@ -829,10 +863,13 @@ int launch_one_impl(unsigned grid, size_t smem, cudaStream_t st, const CUtensorM
         if (e != cudaSuccess || smem_base == 0) return STB_E_DRIVER;
         attr_set = true;
     }
+    // (in a cluster launch cvta-to-shared returns shared::cluster window addresses: CTA rank in bits 24+, the same CTA-local
+    //  offset below -- the kernel compares the low 24 bits)
+    const uint32_t base_used = smem_base;
     // absolute encoded operand addresses: weights at base + 2048, plane ring after the (1 KB-rounded) weight block
-    const uint32_t w0 = smem_base + 2048;
+    const uint32_t w0 = base_used + 2048;
     const uint32_t p0 = w0 + ((a.w_bytes_total + 1023) & ~1023u);
-    a.smem_base = smem_base;
+    a.smem_base = base_used;
     for (int t = 0; t < a.ntaps_total; ++t) {
         a.iss[t].a16 = ((p0 + (uint32_t)a.taps[t].sub * a.chunk_bytes + (uint32_t)a.taps[t].rowoff * a.ROWB) >> 4) | (1u << 16);
         a.iss[t].b16 = ((w0 + (uint32_t)a.taps[t].widx * a.wtile_bytes) >> 4) | (1u << 16);
@@ -841,6 +878,41 @@ int launch_one_impl(unsigned grid, size_t smem, cudaStream_t st, const CUtensorM
     }
     for (int c = 0; c < a.nclass; ++c) a.iss[a.cls[c].tap_begin].dcol |= 1u << 31;      // overwrite instead of accumulate
     a.desc_hi = (((8u * a.ROWB) >> 4) & 0x3FFFu) | (1u << 14) | ((uint32_t)a.layout << 29);
+    if (a.cluster > 1) {
+        // the nslices CTAs of a tile as one thread-block cluster (consecutive blockIdx.x): plane loads are multicast
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid, 1, 1);
+        cfg.blockDim = dim3(UMMA_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)a.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        // persistent CTAs: no more clusters than can be resident at once (a cluster must fit into one GPC)
+        static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int& mc = max_clusters[a.cluster];
+        if (mc == 0) {
+            int n = 0;
+            cudaLaunchConfig_t probe = cfg;
+            probe.dynamicSmemBytes = SMEM_CAP;
+            if (cudaOccupancyMaxActiveClusters(&n, conv3d_umma_kernel<ACT, F16, LEAN, SPLIT>, &probe) != cudaSuccess || n <= 0) {
+                cudaGetLastError();
+                n = -1;
+            }
+            mc = n;
+        }
+        if (mc > 0 && grid > (unsigned)(mc * a.cluster)) cfg.gridDim.x = (unsigned)(mc * a.cluster);
+        if (cudaLaunchKernelEx(&cfg, conv3d_umma_kernel<ACT, F16, LEAN, SPLIT>, tx, tw, a) != cudaSuccess) {
+            STB_CHECK_LAUNCH();
+            return STB_E_DRIVER;
+        }
+        STB_CHECK_LAUNCH();
+        return STB_OK;
+    }
     conv3d_umma_kernel<ACT, F16, LEAN, SPLIT><<<grid, UMMA_THREADS, smem, st>>>(tx, tw, a);
     STB_CHECK_LAUNCH();
     return STB_OK;
@@ -944,9 +1016,12 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     const CUtensorMapDataType cudt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     a.bo_mode = flags & 1;
     const int es_variant = (flags >> 1) & 1;
-    a.merge = (flags & 4) ? 3 : 1;            // kw-merged taps: N = 3*Cn, weight tiles (kd,kh,0..2) are contiguous
+    a.merge = (flags & 4) ? 3 : ((flags & 128) ? 2 : 1);   // kw-merged taps: N = 3*Cn, weight tiles (kd,kh,0..2) are contiguous;
+                                              // flags bit7: stride-2 pair merge, N = 2*Cn: the kw = 0 / 2 taps read the same parity
+                                              // sub-tile one row apart, block 1 is realigned by one lane in the epilogue
     a.merge_step = ((flags >> 8) & 7) ? ((flags >> 8) & 7) : 1;   // flags bits 8..10: dilation along w of the merged taps
     if (a.merge == 3 && (in_stride != 1 || out_stride != 1 || nclass != 1)) return STB_E_UNSUPPORTED;
+    if (a.merge == 2 && (in_stride != 2 || out_stride != 1 || nclass != 1 || (flags & 8))) return STB_E_UNSUPPORTED;
     a.in_stride = in_stride;
     a.nsub = in_stride == 2 ? 4 : 1;
     a.sd_in = kdepth ? kdepth : ((flags & 16) ? 1 : in_stride);     // flags bit4: 2-D convolution, the depth axis (image index) is never strided
@@ -980,7 +1055,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         a.taps[i].sub = (uint8_t)sub[t];
         a.taps[i].rowoff = (int16_t)(dh[t] * TWP + dw[t]);
         a.taps[i].widx = (uint16_t)widx[t];
-        a.taps[i].nblk = (uint8_t)(nblk ? nblk[t] : a.merge);
+        a.taps[i].nblk = (uint8_t)(nblk ? nblk[t] : (a.merge == 2 ? 1 : a.merge));
         a.taps[i].cls0 = (uint8_t)(cls0 ? cls0[t] : 0);
         if (a.taps[i].nblk < 1 || a.taps[i].nblk + a.taps[i].cls0 > 8) return STB_E_BADARG;
     }
@@ -1015,7 +1090,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         a.cls[c].od0 = od0[c]; a.cls[c].oh0 = oh0[c]; a.cls[c].ow0 = ow0[c];
     }
     a.nclass = nclass;
-    a.TW = TWP - (a.merge == 3 ? 2 * a.merge_step : maxdw);
+    a.TW = TWP - (a.merge == 3 ? 2 * a.merge_step : (a.merge == 2 && maxdw < 1 ? 1 : maxdw));
     a.dzmin = dzmin; a.dzmax = dzmax;
     const int window = dzmax - dzmin + 1;
     // Planes an accumulator round needs RESIDENT AT ONCE.  3-D convs: the whole dz window.  K-chunks along the pseudo-depth
@@ -1153,6 +1228,11 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
             a.Cn = cn;
             a.cout_off = co;
             a.nslices = ns;
+            // STB_UMMA_CLUSTER: 0 (default) = off, 1 = clusters of 2 / 4 slices, 2 = also 8.  Measured (profiles/bench_r02_progress.md,
+            // trip 36): bit-identical results, no gain for 2-CTA clusters and +20 % time for 4-CTA clusters (lockstep rings, 8-14 %
+            // of the SMs idle because a cluster must fit into a GPC) -- the sliced layers are not bound by L2 -> smem traffic
+            static const int cluster_mode = getenv("STB_UMMA_CLUSTER") ? atoi(getenv("STB_UMMA_CLUSTER")) : 0;
+            a.cluster = (cluster_mode > 0 && !debug && ns >= 2 && ns <= (cluster_mode > 1 ? 8 : 4) && ncta * ns >= 2 * ns) ? ns : 0;
             a.Cn_valid = (Cout_valid - co) < cn ? (Cout_valid - co) : cn;
             if (a.Cn_valid <= 0) break;
             a.wtile_bytes = (uint32_t)(cn * a.ROWB);

@@ -92,6 +92,27 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// ---- thread-block clusters: the CTAs that hold the output-channel slices of one tile read the SAME input planes, so a plane
+// box is fetched from L2 once and written into the shared memory of every CTA of the cluster (and its byte count signalled
+// on the mbarrier at the same offset in each of them).
+__device__ __forceinline__ void tma_load_5d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                               int c4, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, "
+        "%6, %7}], [%2], %8;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// every thread of every CTA of the cluster
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // One lane of a converged warp: the compiler treats an elect.sync predicate as single-thread, so uniform-
 // datapath instructions (UTCHMMA, UTMALDG) issue without the ELECT/BRA.U.ANY serialisation loop that a plain
 // `if (lane == 0)` produces.
@@ -173,6 +194,15 @@ __device__ __forceinline__ uint32_t uni(uint32_t self_mask, uint32_t v) { return
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// the same arrival on the mbarrier at this offset in EVERY CTA of cta_mask (ring slots are refilled by multicast, so a slot
+// is free only when the consumers of all CTAs of the cluster have released it)
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
                  : "memory");
 }
 

@@ -27,6 +27,7 @@ def emulate(plan: UmmaPlan, x: torch.Tensor) -> torch.Tensor:
     ntaps = plan.ntaps
     dz, dh, dw, sub, widx = (list(plan.c_dz), list(plan.c_dh), list(plan.c_dw), list(plan.c_sub), list(plan.c_widx))
     merge = 3 if plan.merge else 1
+    lane_merged = bool(plan.merge) or bool(getattr(plan, "pair_merge", False))   # column block j is realigned by j lanes -> block 0
     nblk = list(plan.c_nblk) if plan.c_nblk is not None else [merge] * ntaps
     cls0 = list(plan.c_cls0) if plan.c_cls0 is not None else [0] * ntaps
     tb, te = list(plan.c_tb), list(plan.c_te)
@@ -35,7 +36,7 @@ def emulate(plan: UmmaPlan, x: torch.Tensor) -> torch.Tensor:
     nsteps, nh, nw = (Di, Hi, Wi) if plan.tr else (Do, Ho, Wo)
     sd_in = nk if kdepth else in_s
     out = torch.zeros(B, Do, Ho, Wo, plan.cpad, dtype=torch.float64)
-    cb = 8 if plan.deconv_merge else merge
+    cb = 8 if plan.deconv_merge else (2 if getattr(plan, "pair_merge", False) else merge)
 
     def gather(P, chunk_k, hh, ww):
         """rows of the A operand: input storage elements [B, nh, nw, kc] at plane P, positions (hh[jh], ww[jw])."""
@@ -59,15 +60,15 @@ def emulate(plan: UmmaPlan, x: torch.Tensor) -> torch.Tensor:
                 for t in range(tb[c], te[c]):
                     P = s * sd_in + dz[t]
                     for j in range(nblk[t]):
-                        shift_w = j if (merge == 3) else 0            # kw-merged tiles: column block j is realigned by j lanes
+                        shift_w = j if lane_merged else 0             # merged tiles: column block j is realigned by j lanes
                         hh = (jh + plan.in_off) * in_s + (sub[t] >> 1) + in_s * dh[t]
                         ww = (jw + plan.in_off) * in_s + (sub[t] & 1) + in_s * (dw[t] + shift_w)
                         a = gather(P, kp, hh, ww)
                         w = wt[widx[t] + j, 0 if kdepth else kp]                      # [cpad][kc]
                         # (split: hi*hi + hi*lo + lo*hi = the product of the joined values minus lo*lo, below fp32 rounding)
-                        blk = cls0[t] + (0 if merge == 3 else j)
+                        blk = 0 if lane_merged else cls0[t] + j
                         contrib = torch.einsum("bhwk,ok->bhwo", _join(a, split), _join(w, split))
-                        acc[:, :, :, blk if merge != 3 else 0] += contrib
+                        acc[:, :, :, blk] += contrib
             for blk in range(cb if plan.deconv_merge else 1):
                 cd, ch, cw = ((blk >> 2, (blk >> 1) & 1, blk & 1) if plan.deconv_merge else (od0[c], oh0[c], ow0[c]))
                 od = s * out_s + cd
@@ -98,7 +99,9 @@ CASES = [
     (64, 64, 1, 1, 0, False, True, (2, 4, 5), True),         # k1: both K-chunks in TMEM
     (64, 32, 3, 2, 1, True, True, (2, 3, 4), True),          # merged transposed conv, chunks along the pseudo-depth axis
     (128, 64, 3, 2, 1, True, True, (2, 2, 3), False),
-    (32, 64, 3, 2, 1, False, True, (4, 6, 6), False),        # strided conv: parity sub-tiles
+    (32, 64, 3, 2, 1, False, True, (4, 6, 6), False),        # strided conv: parity sub-tiles, kw 0 / 2 pair-merged
+    (64, 128, 3, 2, 1, False, True, (5, 7, 9), False),
+    (32, 64, 3, 2, 1, False, False, (4, 6, 8), False),
     (64, 32, 3, 2, 1, True, False, (2, 3, 4), False),        # single fp16
     (32, 32, 3, 1, 1, False, False, (3, 4, 5), False),
 ]
