@@ -274,6 +274,15 @@ int stb_gru_blend_split(const void* zr, const void* h, const void* q, void* out,
 int stb_pool2x_split(const void* x, void* out, int N, int H, int W, int C, void* stream);
 int stb_interp_split(const void* x, void* out, int N, int H, int W, int Ho, int Wo, int C, void* stream);
 
+/* PCWNet's full-resolution refinement inputs (PCWNet/submodule.py:122-152 `warp`, :104-120 `build_corrleation_volume` with
+ * num_groups = 1; PCWNet/pcwnet.py:491-506):
+ *   stb_warp_disp_f32: x [B,C,H,W], disp [B,1,H,W] -> out [B,C,H,W] = grid_sample(x, grid(x - disp)) * (grid_sample(1) >= 0.999)
+ *     with the reference's grid arithmetic (normalised with W-1 / H-1, sampled with align_corners=False, zero padding);
+ *   stb_corr_volume_1d_f32: left, right [B,C,H,W] -> vol [B,2*maxdisp+1,H,W] (every element written); maxdisp in {4, 8, 24}. */
+int stb_warp_disp_f32(const float* x, const float* disp, float* out, int B, int C, int H, int W, void* stream);
+int stb_corr_volume_1d_f32(const float* left, const float* right, float* vol, int B, int C, int H, int W, int maxdisp,
+                           void* stream);
+
 /* Adjoint of build_concat_volume (variant A mask_left=1 / B mask_left=0): dvol [B,c_total,D,H,W] channels
  * [c_off, c_off+2C) -> dleft, dright [B,C,H,W]. */
 int stb_concat_volume_bwd_f32(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W, int D,

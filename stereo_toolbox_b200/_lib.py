@@ -11,7 +11,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstb200.so")
+LIB_PATH = os.environ.get("STB200_LIB") or os.path.join(_HERE, "libstb200.so")     # STB200_LIB: A/B builds of the same source (kernel work)
 
 _lib = None
 
@@ -55,6 +55,8 @@ SIGNATURES = {
     "stb_context_upsample_f32": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
     "stb_conv3d_wgrad_f32": [_P, _P, _P] + [_I] * 12 + [_P],
     "stb_conv3d_wgrad_cl16": [_P, _P, _P] + [_I] * 14 + [_P],
+    "stb_warp_disp_f32": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "stb_corr_volume_1d_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "stb_gru_rh_split": [_P, _P, _P, _LL, _I, _P],
     "stb_gru_blend_split": [_P, _P, _P, _P, _LL, _I, _P],
     "stb_pool2x_split": [_P, _P, _I, _I, _I, _I, _P],

@@ -329,6 +329,9 @@ template <int ACT, bool F16, int LEAN, bool SPLIT>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ UArgs a) {
+    // LV: the epilogue flavour; LEAN 7 = the generic flavour (0) plus the stride-2 pair merge, kept out of LEAN 0 so that the generic
+    // instantiation (K-split passes of the big layers) does not carry it
+    constexpr int LV = LEAN == 7 ? 0 : LEAN;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
     // [0,2048): barriers + tmem holder + issue tables ; then weights ; then plane ring
@@ -357,26 +360,31 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // ---- persistent CTA: work items blockIdx.x, blockIdx.x + gridDim.x, ... ; every role walks the same list and
     // carries its pipeline state (ring slot / phase, accumulator round) across items, so the producer is already
     // filling the ring for the next item while the tensor pipe and the epilogue finish the current one.
-    long long* const trace_buf = LEAN ? nullptr : g_umma_trace;   // read ONCE: a global load per round sat on the issuer's critical path
-    const int trace_rounds = (!LEAN && trace_buf && blockIdx.x == 0) ? g_umma_trace_rounds : 0;
-    const int dbg = LEAN ? 0 : a.debug;
+    long long* const trace_buf = LV ? nullptr : g_umma_trace;   // read ONCE: a global load per round sat on the issuer's critical path
+    const int trace_rounds = (!LV && trace_buf && blockIdx.x == 0) ? g_umma_trace_rounds : 0;
+    const int dbg = LV ? 0 : a.debug;
 
     // Cluster mode: the CTAs of a cluster (= the output-channel slices of one tile sequence) walk identical plane sequences; every
     // plane box is issued by ONE of them, round robin, and multicast into the ring slot of all of them.  A slot may be refilled
     // once the issuers of ALL CTAs have released it: plane_empty counts 2 * ncl arrivals, delivered by multicast commits.
-    const int ncl = a.cluster > 1 ? a.cluster : 1;
-    const uint32_t crank = ncl > 1 ? cluster_ctarank() : 0u;
-    const uint16_t cmask = (uint16_t)((1u << ncl) - 1u);
     if (threadIdx.x == 0) {
+        const int ncl = a.cluster > 1 ? a.cluster : 1;
         mbar_init(bar_w, 1);
-        const int n_grp = a.nM * (a.cblocks == 8 ? 8 : 1) >= 2 ? 2 : 1;           // active epilogue groups
+        // active epilogue groups: two when a round holds >= 2 (M-tile, class block) items, or (column split) when its single
+        // item is >= 64 channels wide -- the groups then take alternate 32-column blocks
+#ifdef STB_NO_CSPLIT
+        const bool csplit_i = false;
+#else
+        const bool csplit_i = (LV == 1 || LV == 2) && a.nM == 1 && a.cblocks != 8 && a.Cn >= 64;
+#endif
+        const int n_grp = (a.nM * (a.cblocks == 8 ? 8 : 1) >= 2 || csplit_i) ? 2 : 1;
         for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 2 * ncl); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * n_grp); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_holder, a.tmem_cols);
     tc_fence_before();
-    if (ncl > 1) cluster_sync_all();          // no CTA may multicast into a peer whose barriers are not initialised yet
+    if (a.cluster > 1) cluster_sync_all();    // no CTA may multicast into a peer whose barriers are not initialised yet
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
@@ -393,6 +401,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             int slot = 0;
             uint32_t eph = 1;                      // parity to wait for on plane_empty[slot] (fresh barrier: passes)
             uint32_t gbox = 0;                     // running box counter, identical in every CTA of a cluster: box j is issued by CTA j % ncl
+            const int ncl = a.cluster > 1 ? a.cluster : 1;
+            const uint32_t crank = ncl > 1 ? cluster_ctarank() : 0u;
+            const uint16_t cmask = (uint16_t)((1u << ncl) - 1u);
             for (int tile = tile0; tile < a.ntiles && !(dbg & 1); tile += tstride) {
                 const UTile u = decode_tile(a, tile);
                 const int ih0 = (u.jh0 + a.in_h_off) * a.in_stride, iw0 = (u.jw0 + a.in_w_off) * a.in_stride;
@@ -440,6 +451,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             // launch_one): everything the issue blocks need is an LDCU away, never an R2UR.
             if ((smem_u32(smem) & 0xFFFFFFu) != a.smem_base) asm volatile("trap;");      // low 24 bits: CTA-local offset (cluster rank above)
             const int nM = a.nM, R = a.R, sd = a.sd_in, nclass = a.nclass;
+            const int ncl = a.cluster > 1 ? a.cluster : 1;
+            const uint16_t cmask = (uint16_t)((1u << ncl) - 1u);
             const uint32_t ncol = (uint32_t)(a.Cn * a.cblocks);
             mbar_wait(bar_w, 0);
             int waited = 0, released = 0;         // planes of the CURRENT item known resident / handed back (this issuer)
@@ -471,7 +484,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     const int dead_now = si * sd;                 // item-relative index of the step's first plane
                     for (int c = 0; c < nclass; ++c, ++ground) {
                         if ((int)(ground & 1u) != issuer) continue;
-                        const bool trace = !LEAN && (int)ground < trace_rounds;
+                        const bool trace = !LV && (int)ground < trace_rounds;
                         if (trace) trace_buf[ground * 8 + 0] = clock64();
                         // first plane this issuer still needs in ITS next round (ground + 2)
                         int nsi = si, nc = c + 2;
@@ -519,33 +532,45 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // ================================ epilogue warps ================================
         const int q4 = warp & 3;                    // TMEM lane quarter this warp may touch
         const int egroup = (warp - 3) >> 2;         // epilogue group 0/1 drains M-tiles m = egroup, egroup+2, ...
-        const int nblk_e = LEAN == 3 ? 8 : (LEAN == 5 || LEAN == 6) ? 4 : (LEAN ? 1 : (a.cblocks == 8 ? 8 : 1));     // merged transposed conv: all 8 parity classes in one round (LEAN 5: as 4 w-pairs)
+        const int nblk_e = LV == 3 ? 8 : (LV == 5 || LV == 6) ? 4 : (LV ? 1 : (a.cblocks == 8 ? 8 : 1));     // merged transposed conv: all 8 parity classes in one round (LV 5: as 4 w-pairs)
         const int items = a.nM * nblk_e;               // (M-tile, class block) work items per round, dealt to 2 groups
-        const bool active = egroup < (items >= 2 ? 2 : 1);
+        // Column split: with one M-tile per round (the split-storage tiling) the second epilogue group used to idle; for items
+        // >= 64 channels wide the two groups take alternate 32-column blocks (2-D 64-channel layers: the epilogue, not the MMAs,
+        // bounded them -- 8.1 k clk per item for 3.5 k clk of MMAs)
+#ifdef STB_NO_CSPLIT
+        constexpr bool csplit = false;
+        const int item0 = egroup;
+        constexpr int item_step = 2, cblk0 = 0, cblk_step = 32;
+#else
+        const bool csplit = (LV == 1 || LV == 2) && items == 1 && a.Cn >= 64;
+        const int item0 = csplit ? 0 : egroup, item_step = csplit ? 1 : 2;
+        const int cblk0 = csplit ? 32 * egroup : 0, cblk_step = csplit ? 64 : 32;
+#endif
+        const bool active = egroup < ((items >= 2 || csplit) ? 2 : 1);
         const size_t ostride_w = (size_t)a.Cout_total;
         constexpr int f16 = F16 ? 1 : 0;
         constexpr size_t K16 = SPLIT ? 2 : 1;       // 16-bit storage elements per logical channel
-        const bool full32 = LEAN || (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
-        const float* const partial = LEAN ? nullptr : a.partial;
-        const bool out_fp32 = !LEAN && a.out_fp32;
+        const bool full32 = LV || (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
+        const float* const partial = LV ? nullptr : a.partial;
+        const bool out_fp32 = !LV && a.out_fp32;
         float sh0[32];                              // folded-BN shift of the first 32 channels stays in registers
 #pragma unroll
         for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + cout_off + i) : 0.f;
         const float oscale = SPLIT ? a.oscale : 1.f;
-        const int merge = (LEAN == 2 || LEAN == 4) ? 3 : (LEAN ? 1 : a.merge), Cn = a.Cn, nM = a.nM;
+        const int merge = (LV == 2 || LV == 4) ? 3 : (LV ? 1 : a.merge), Cn = a.Cn, nM = a.nM;
         uint32_t ground = 0;                        // accumulator round counter over all items (same order as the issuer)
         // The memory-heavy flavours (transposed convs: 8 output blocks per M-tile, each with a residual row to read; K-split
         // passes reading their fp32 partial sums) were bound by the LATENCY of those loads: a block loads, waits, computes,
         // stores, and only then the next block's loads are issued (fp16 64->32 s2T: 0.66 ms for an MMA time of 0.14 ms and a
         // HBM floor of 0.26 ms).  Registers for a software pipeline do not exist (168-register cap), so the rows a round will
         // read are pulled into L2 one round ahead with prefetch.global.L2 -- no registers, no completion to wait for.
-        constexpr bool PREFETCH = LEAN == 0 || LEAN == 1 || LEAN == 3 || LEAN == 5 || LEAN == 6;
+        constexpr bool PREFETCH = LV == 0 || LV == 1 || LV == 3 || LV == 5 || LV == 6;
         const bool want_pf = PREFETCH && (a.residual != nullptr || partial != nullptr);
         auto prefetch_round = [&](const UTile& u, int s, const UClass& cl) {
             for (int item = egroup; item < items; item += 2) {
                 int m, od, oh, ow, jh_l, jw_l;
                 bool ok;
-                if (LEAN == 5 || LEAN == 6) {
+                if (LV == 5 || LV == 6) {
                     m = item >> 2;
                     const int pb = item & 3, q = 128 * m + q4 * 32 + lane;
                     jh_l = q / TWP; jw_l = q % TWP;
@@ -567,8 +592,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     if (a.residual) {
                         const uint16_t* rp = reinterpret_cast<const uint16_t*>(a.residual) + eoff * K16;
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
-                        if (LEAN == 5 && SPLIT) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 64));   // the pair's second voxel
-                        if (LEAN == 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + ostride_w * K16));
+                        if (LV == 5 && SPLIT) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 64));   // the pair's second voxel
+                        if (LV == 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + ostride_w * K16));
                     }
                     if (partial) asm volatile("prefetch.global.L2 [%0];" ::"l"(partial + eoff));
                 }
@@ -587,10 +612,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             if (want_pf && round + 1 < u.nouts) prefetch_round(u, u.s_lo + e_si, a.cls[e_c]);   // (e_si, e_c) already name the NEXT round
             mbar_wait_warp(&tmem_full[buf], (ground >> 1) & 1);
             tc_fence_after();
-            const bool trace = !LEAN && (int)ground < trace_rounds && warp == 3 && lane == 0;
+            const bool trace = !LV && (int)ground < trace_rounds && warp == 3 && lane == 0;
             if (trace) trace_buf[ground * 8 + 4] = clock64();
-            for (int item = egroup; item < items && !(dbg & 2); item += 2) {
-              if (LEAN == 6) {
+            for (int item = item0; item < items && !(dbg & 2); item += item_step) {
+              if (LV == 6) {
                 // Merged transposed conv on a 16-channel output slice (Cn == 16: all K-chunks of the layer accumulate in TMEM because
                 // the weights of a 16-channel slice fit next to the chunk ring, no K-split pass through an fp32 partial).  The two
                 // w-parity classes of one (d,h) parity are ADJACENT 16-column blocks, so one 32-column TMEM read holds the thread's
@@ -628,7 +653,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 }
                 continue;
               }
-              if (LEAN == 5) {
+              if (LV == 5) {
                 // Merged transposed conv, the two w-parity classes of one (d,h) parity handled together: a thread's two output
                 // voxels (ow, ow + 1) are adjacent in memory, so it writes 2 x Cout_total contiguous channels (128 B at 32
                 // channels) and a warp a fully contiguous span, instead of 64-byte pieces at a 128-byte stride; the address /
@@ -679,14 +704,14 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const int oh = jh * a.out_stride + chh, ow = jw * a.out_stride + cww;
                 const bool inb = valid && oh < a.Ho && ow < a.Wo;
                 const size_t vox = (((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow;
-                for (int c0 = 0; c0 < Cn; c0 += 32) {
+                for (int c0 = cblk0; c0 < Cn; c0 += cblk_step) {
                     const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) +
                                            (uint32_t)((buf * nM + m) * Cn * a.cblocks + (nblk_e == 8 ? blk * Cn : 0) + c0);
                     // All TMEM reads of the block are issued back to back and waited for once; after the LAST block of
                     // the round the accumulator buffer is handed back to its issuer BEFORE the arithmetic and the
                     // stores (the data is in registers): the buffer is busy ~0.3K instead of ~2.5K clocks per round,
                     // which was what the issuers were waiting for (profiles/umma_issue_r01.md).
-                    if (LEAN == 4) {
+                    if (LV == 4) {
                         // 32->1 classifier (kw-merged, fp32 out, no residual): ONE accumulator column per kw block is
                         // live, so read three single columns instead of three 32-column blocks and realign with two
                         // shuffles instead of 64.  Same additions in the same order as the generic path below.
@@ -719,7 +744,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         tmem_ld_32x32(taddr + (uint32_t)(2 * Cn), v2);
                         tmem_ld_wait();
                         if (trace && item == egroup && c0 == 0) trace_buf[ground * 8 + 6] = clock64();     // TMEM data in registers
-                        if (item + 2 >= items && c0 + 32 >= Cn) {
+                        if (item + item_step >= items && c0 + cblk_step >= Cn) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -729,14 +754,14 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         for (int i = 0; i < 32; ++i)
                             f[i] = __uint_as_float(v0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), ms) +
                                    __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2 * ms);
-                    } else if (!LEAN && merge == 2) {
+                    } else if (LEAN == 7 && merge == 2) {
                         // stride-2 pair merge: block 0 = kw 0 (+ the un-merged kw 1 taps), block 1 = kw 2 evaluated one padded
                         // position early: out[q] = P_0[q] + P_1[q+1]
                         uint32_t v0[32], v1[32];
                         tmem_ld_32x32(taddr, v0);
                         tmem_ld_32x32(taddr + (uint32_t)Cn, v1);
                         tmem_ld_wait();
-                        if (item + 2 >= items && c0 + 32 >= Cn) {
+                        if (item + item_step >= items && c0 + cblk_step >= Cn) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -748,7 +773,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         uint32_t v[32];
                         tmem_ld_32x32(taddr, v);
                         tmem_ld_wait();
-                        if (item + 2 >= items && c0 + 32 >= Cn) {
+                        if (item + item_step >= items && c0 + cblk_step >= Cn) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -837,7 +862,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         }
     }
     tc_fence_before();
-    if (ncl > 1) cluster_sync_all();          // peers may still multicast plane data / slot releases into this CTA until they are done
+    if (a.cluster > 1) cluster_sync_all();    // peers may still multicast plane data / slot releases into this CTA until they are done
     else __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
@@ -942,6 +967,7 @@ int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& t
             a.Cn_valid == 16 && a.shift)
             return launch_one_impl<ACT, F16, 6, SPLIT>(grid, smem, st, tx, tw, a);
     }
+    if (a.merge == 2) return launch_one_impl<ACT, F16, 7, SPLIT>(grid, smem, st, tx, tw, a);      // stride-2 pair merge (generic + 2-block realignment)
     if (lean && a.cblocks == 8 && a.merge == 1) return launch_one_impl<ACT, F16, 3, SPLIT>(grid, smem, st, tx, tw, a);
     if (lean && a.cblocks == 3 && a.merge == 3) return launch_one_impl<ACT, F16, 2, SPLIT>(grid, smem, st, tx, tw, a);
     if (lean && a.cblocks == 1 && a.merge == 1) return launch_one_impl<ACT, F16, 1, SPLIT>(grid, smem, st, tx, tw, a);

@@ -86,10 +86,22 @@ class refinenet_version3(nn.Module):
         return disp + self.conv8(self.conv7(self.conv6(self.conv5(x))))
 
 
+def _kernel_path(*ts):
+    return all(t.is_cuda for t in ts) and not (torch.is_grad_enabled() and any(t.requires_grad for t in ts))
+
+
 def warp(x, disp):
     """PCWNet/submodule.py:122-152: bilinear resampling of the right features at x - disp (grid normalised with W-1 but
-    sampled with grid_sample's default align_corners=False, exactly like the reference) and a validity mask."""
+    sampled with grid_sample's default align_corners=False, exactly like the reference) and a validity mask.
+    CUDA inference: one kernel (csrc/refine2d.cu); the torch form below is the differentiable / CPU-test form."""
     B, C, H, W = x.shape
+    if _kernel_path(x, disp):
+        from . import _lib
+        from .ops import _f32c, _p, _stream
+        x, disp = _f32c(x), _f32c(disp)
+        out = torch.empty_like(x)
+        _lib.call("stb_warp_disp_f32", _p(x), _p(disp), _p(out), B, C, H, W, _stream())
+        return out
     xx = torch.arange(0, W, device=x.device).view(1, 1, 1, W).expand(B, 1, H, W).float()
     yy = torch.arange(0, H, device=x.device).view(1, 1, H, 1).expand(B, 1, H, W).float()
     gx = 2.0 * (xx - disp) / max(W - 1, 1) - 1.0
@@ -107,6 +119,14 @@ def build_correlation_volume(left, right, maxdisp):
     ``[..., i:]``, i.e. with k = -i the FIRST k columns of the left times the LAST k columns of the right, written to
     columns [0, k) -- reproduced as is."""
     B, C, H, W = left.shape
+    if _kernel_path(left, right) and maxdisp in (4, 8, 24) and maxdisp < W:
+        # all 2*maxdisp+1 planes in one pass over the staged row tiles instead of 49 slice-multiply-mean-assign sequences
+        from . import _lib
+        from .ops import _f32c, _p, _stream
+        left, right = _f32c(left), _f32c(right)
+        vol = torch.empty(B, 2 * maxdisp + 1, H, W, device=left.device, dtype=torch.float32)
+        _lib.call("stb_corr_volume_1d_f32", _p(left), _p(right), _p(vol), B, C, H, W, maxdisp, _stream())
+        return vol
     vol = left.new_zeros(B, 2 * maxdisp + 1, H, W)
     for i in range(-maxdisp, maxdisp + 1):
         if i > 0:
