@@ -18,6 +18,9 @@
 
 namespace {
 
+// 8 warps x 4 output blocks.  (16 warps x 2 blocks at 128 registers was measured too, on the hypothesis that two warps per
+// scheduler cannot hide the fixed HMMA / LDSM latencies -- ncu: issue slots 36 % busy, "wait" 2.4 per issue, HMMA pipe 30 % --:
+// 11.3 ms instead of 10.9 ms for the 28 launches of a PSMNet step, so occupancy is not what limits it.)
 constexpr int WG_THREADS = 256;
 constexpr int WG_TW = 32;        // q positions per tile row
 constexpr int WG_UPW = 4;        // 32x32 output blocks per warp
