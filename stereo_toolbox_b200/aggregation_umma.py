@@ -135,8 +135,8 @@ class UmmaPlan:
 
     def _build_umma(self, w, bnp, eps) -> bool:
         cin, cout, k, stride, pad, tr = self.cin_tensor, self.cout, self.k, self.stride, self.pad, self.tr
-        if cin not in (16, 32, 64) and cin % 64:
-            return False
+        if cin % 16 or (not self.split and cin not in (16, 32, 64) and cin % 64):
+            return False            # (single 16-bit storage keeps its round-1 rule: other widths go to the CUDA-core companion)
         if tr and stride != 2:
             return False
         if not tr and stride not in (1, 2):
@@ -145,7 +145,16 @@ class UmmaPlan:
             return False
         in_stride = 1 if tr else stride
         cin_st = 2 * cin if self.split else cin           # storage elements per voxel
-        kc = min(cin_st, 32 if in_stride == 2 else 64)   # storage elements per K-chunk = one swizzled smem row
+        # storage elements per K-chunk = one swizzled smem row: the largest of 64 / 32 / 16 that divides the row (48 channels,
+        # IGEV's third level: 3 chunks of 16 resp. 32) -- split rows need whole (hi, lo) slice pairs, i.e. >= 32
+        # ... and for which the weight tiles of the narrowest (16-channel) output slice fit next to a minimal plane ring
+        # (k4 transposed convs stage 64 tiles: 131 KB at a 64-element chunk -- they take 32)
+        def _fits(d):
+            ring = 4 * (4 + 2) * 32 * d * 2 * (4 if in_stride == 2 else 1)
+            return k ** 3 * 16 * d * 2 + ring + 4096 <= 227 * 1024
+        kc = next((d for d in ((32, 16) if in_stride == 2 else (64, 32, 16)) if cin_st % d == 0 and (_fits(d) or d == 16)), 0)
+        if kc == 0 or (self.split and kc < 32):
+            return False
         nk = cin_st // kc
         cpad = (cout + 15) // 16 * 16
         if bnp is not None:
@@ -492,9 +501,7 @@ class UmmaBackend:
 
     # ---------------------------------------------------------------- IGEV / CFNet helpers
     def gate(self, x, gate_logits):
-        if self.split:
-            raise NotImplementedError("fp16x2 precision: feature gate not built for split storage")
-        return ops.feature_gate(x, gate_logits, channels_last=True, channels=gate_logits.shape[1])
+        return ops.feature_gate(x, gate_logits, channels_last=True, channels=gate_logits.shape[1], split=self.split)
 
     def cat(self, xs):
         """channel concatenation of channels-last tensors, re-padded to a legal K width."""

@@ -60,6 +60,41 @@ __global__ void gate_cl16_kernel(const uint16_t* __restrict__ x, const float* __
     }
 }
 
+// Operand-split storage ("fp16x2": [B,D,H,W,2*Cpad] halves, (hi, lo) interleaved per 16 channels): a thread owns 8 logical
+// channels of a voxel -- the hi and the lo 16-byte pieces of its 16-channel block -- joins them, gates in fp32, splits again.
+__global__ void gate_split_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gate, uint16_t* __restrict__ out,
+                                  int C, int Cpad, int D, int H, int W, long long nvox) {
+    const int chunks = Cpad >> 3;
+    const long long total = nvox * chunks;
+    const long long hw = (long long)H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long vox = i / chunks;
+        const int c8 = (int)(i - vox * chunks), c0 = c8 * 8;
+        const long long p = vox % hw;
+        const long long b = vox / (hw * D);
+        const size_t off = (size_t)vox * (2 * (size_t)Cpad) + (c8 >> 1) * 32 + (c8 & 1) * 8;
+        const uint4 hq = *reinterpret_cast<const uint4*>(x + off), lq = *reinterpret_cast<const uint4*>(x + off + 16);
+        const uint32_t hw_[4] = {hq.x, hq.y, hq.z, hq.w}, lw_[4] = {lq.x, lq.y, lq.z, lq.w};
+        uint32_t ho[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw_[j]));
+            const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lw_[j]));
+            float2 f = make_float2(a.x + l.x, a.y + l.y);
+            const int c = c0 + 2 * j;
+            if (c < C) f.x *= sigmoidf_(__ldg(gate + (b * C + c) * hw + p));
+            if (c + 1 < C) f.y *= sigmoidf_(__ldg(gate + (b * C + c + 1) * hw + p));
+            const __half2 h = __floats2half2_rn(f.x, f.y);
+            const float2 hf = __half22float2(h);
+            const __half2 r = __floats2half2_rn(f.x - hf.x, f.y - hf.y);
+            ho[j] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+        *reinterpret_cast<uint4*>(out + off + 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
 // prob [B,D,plane], disp [B,plane] -> var [B,plane]
 __global__ void variance_kernel(const float* __restrict__ prob, const float* __restrict__ disp, float* __restrict__ var,
                                 int D, long long plane, long long total) {
@@ -100,6 +135,13 @@ extern "C" int stb_feature_gate_cl16(const void* x, const float* gate, void* out
                                      int H, int W, void* stream) {
     if (!x || !gate || !out || B <= 0 || C <= 0 || Cpad < C || (Cpad & 7) || D <= 0 || H <= 0 || W <= 0) return STB_E_BADARG;
     const long long nvox = (long long)B * D * H * W;
+    if (f16 == 2) {       // operand-split fp16 storage
+        if (Cpad & 15) return STB_E_BADARG;
+        gate_split_kernel<<<grid_for(nvox * (Cpad >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+            (const uint16_t*)x, gate, (uint16_t*)out, C, Cpad, D, H, W, nvox);
+        STB_CHECK_LAUNCH();
+        return STB_OK;
+    }
     gate_cl16_kernel<<<grid_for(nvox * (Cpad >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint16_t*)x, gate, (uint16_t*)out, C, Cpad, D, H, W, nvox, f16);
     STB_CHECK_LAUNCH();

@@ -156,7 +156,8 @@ def disparity_variance(prob: torch.Tensor, maxdisp: int, disparity: torch.Tensor
     return var
 
 
-def feature_gate(x: torch.Tensor, gate_logits: torch.Tensor, channels_last: bool = False, channels: Optional[int] = None):
+def feature_gate(x: torch.Tensor, gate_logits: torch.Tensor, channels_last: bool = False, channels: Optional[int] = None,
+                 split: bool = False):
     """FeatureAtt gate (IGEVStereo/submodule.py:236-241): x * sigmoid(gate_logits)[:, :, None].
     x [B,C,D,H,W] fp32, or channels-last 16-bit [B,D,H,W,Cpad] with ``channels`` real channels; gate_logits [B,C,H,W]."""
     _need_cuda(x, gate_logits)
@@ -170,10 +171,14 @@ def feature_gate(x: torch.Tensor, gate_logits: torch.Tensor, channels_last: bool
         return out
     assert x.is_contiguous() and x.dtype in (torch.float16, torch.bfloat16)
     B, D, H, W, cpad = x.shape
+    if split:                      # operand-split fp16 storage: two halves per logical channel
+        assert x.dtype == torch.float16 and cpad % 32 == 0
+        cpad //= 2
     C = channels or cpad
     assert tuple(g.shape) == (B, C, H, W)
     out = torch.empty_like(x)
-    _lib.call("stb_feature_gate_cl16", _p(x), _p(g), _p(out), int(x.dtype == torch.float16), B, C, cpad, D, H, W, _stream())
+    _lib.call("stb_feature_gate_cl16", _p(x), _p(g), _p(out), 2 if split else int(x.dtype == torch.float16), B, C, cpad, D, H, W,
+              _stream())
     return out
 
 

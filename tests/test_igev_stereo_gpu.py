@@ -40,6 +40,29 @@ def test_igev_stereo_golden_fp32():
     assert epe < 1e-3, f"EPE vs reference {epe}"          # px, north_star fp32 bar
 
 
+def test_igev_stereo_golden_fp16x2():
+    """The whole model with the cost-volume stage on the exact tensor-core path as well (precision='fp16x2': 48-channel level
+    as three K-chunks, k4-s2 transposed convs, split-storage feature gates) and the update block on tcgen05 (default)."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair
+    g = load_golden("igev_stereo.npz")
+    sd, meta = golden_state("igev_stereo")
+    net = S.IGEVStereo({"max_disp": meta["max_disp"]}, precision="fp16x2")
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    left, right = synth_pair(1, 64, 128, seed=8, shift=meta["shift"])
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            out = net(left.cuda(), right.cuda(), iters=meta["iters"]).cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    epe = (out - g["disp"]).abs().mean().item()
+    print(f"IGEVStereo fp16x2 stage + tcgen05 update block: EPE vs reference {epe:.3e} px")
+    assert epe < 1e-3, f"EPE vs reference {epe}"
+
+
 def test_igev_stereo_train_style_return_fp32():
     """test_mode=False in eval: (upsampled initial disparity, one prediction per iteration) -- igev_stereo.py:254-255."""
     g = load_golden("igev_stereo.npz")

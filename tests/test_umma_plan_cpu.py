@@ -102,6 +102,9 @@ CASES = [
     (32, 64, 3, 2, 1, False, True, (4, 6, 6), False),        # strided conv: parity sub-tiles, kw 0 / 2 pair-merged
     (64, 128, 3, 2, 1, False, True, (5, 7, 9), False),
     (32, 64, 3, 2, 1, False, False, (4, 6, 8), False),
+    (48, 32, 4, 2, 1, True, True, (2, 3, 3), False),         # IGEV: k4 s2 p1 transposed conv from the 48-channel level (3 K-chunks of 32)
+    (48, 48, 3, 1, 1, False, True, (2, 3, 4), False),
+    (16, 8, 4, 2, 1, True, True, (2, 2, 3), False),
     (64, 32, 3, 2, 1, True, False, (2, 3, 4), False),        # single fp16
     (32, 32, 3, 1, 1, False, False, (3, 4, 5), False),
 ]

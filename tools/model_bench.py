@@ -98,7 +98,7 @@ def main():
     ms = ts[len(ts) // 2]
     res = dict(model=args.model, precision=args.precision if args.model != "raft" else "fp32",
                shape=[args.batch, args.height, args.width], maxdisp=args.maxdisp,
-               iters=fwd.get("iters"), cuda_graph=args.cuda_graph, channels_last=args.channels_last, update=args.update or "torch", features=args.features or "default", exact_glue=args.exact_glue, ms_per_forward=ms, maps_per_s=args.batch / (ms * 1e-3),
+               iters=fwd.get("iters"), cuda_graph=args.cuda_graph, channels_last=args.channels_last, update=args.update or "auto", features=args.features or "default", exact_glue=args.exact_glue, ms_per_forward=ms, maps_per_s=args.batch / (ms * 1e-3),
                peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, out_shape=list(out.shape),
                finite=bool(torch.isfinite(out.float()).all().item()))
     print(json.dumps(res))
