@@ -383,7 +383,23 @@ class RAFTStereo(nn.Module):
             hit["graph"].replay()
         return hit["coords"].clone(), upd.mask(hit["net"][0])
 
+    def _folded(self, image1):
+        """CUDA inference runs on a shadow copy with every eval BatchNorm2d folded into its convolution (glue.py): the context
+        encoder's BatchNorm passes are pure memory traffic.  ``model.fold_bn = False`` turns it off."""
+        if not getattr(self, "fold_bn", True) or self.training or not image1.is_cuda or torch.is_grad_enabled():
+            return None
+        from .glue import inference_shadow
+        ex = torch.zeros(1, 3, 64, 128, device=image1.device)
+        sh = inference_shadow(self, lambda m: m(ex, ex, iters=1))
+        for k in ("update_mode", "cuda_graph", "channels_last"):
+            if k in self.__dict__:
+                sh.__dict__[k] = self.__dict__[k]
+        return sh
+
     def forward(self, image1, image2, iters=None, flow_init=None, test_mode=False):
+        sh = self._folded(image1)
+        if sh is not None:
+            return sh(image1, image2, iters=iters, flow_init=flow_init, test_mode=test_mode)
         a = self.args
         if iters is None:
             iters = a.train_iters if self.training else a.valid_iters       # raft_stereo.py:99-103
