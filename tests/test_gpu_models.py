@@ -230,7 +230,7 @@ def test_pcwnet_gc_golden():
     sd, meta = golden_state("pcwnet_gc")
     left, right = synth_pair(1, 64, 128, seed=7, shift=meta["shift"])
     stage = {}
-    for precision in ("fp32", "fp16"):
+    for precision in ("fp32", "fp16x2", "fp16"):
         net = S.PCWNet_GC(meta["maxdisp"], precision=precision)
         net.load_state_dict(sd, strict=True)
         net = net.cuda().eval()
@@ -245,8 +245,10 @@ def test_pcwnet_gc_golden():
         stage[precision] = net._last["pred3"].cpu()
         if precision == "fp32":
             torch.testing.assert_close(net._last_cost.cpu(), g["cost3"], rtol=2e-3, atol=2e-3)
+        if precision in ("fp32", "fp16x2"):      # fp16x2: the whole 3-D path (Mish epilogues, 3-level hourglassup) on the exact tensor-core format
             epe = (disp - g["disp"]).abs().mean().item()
-            assert epe < 1e-3, f"EPE vs reference {epe}"
+            print(f"PCWNet_GC {precision}: EPE vs reference {epe:.3e} px")
+            assert epe < 1e-3, f"{precision}: EPE vs reference {epe}"
     d = (stage["fp16"] - stage["fp32"]).abs().mean().item()
     assert d < 1e-2, f"cost-volume stage disparity fp16 vs fp32 path: {d} px"
 
