@@ -69,19 +69,42 @@ def test_psmnet_sceneflow_shape():
     pad = lambda t: torch.nn.functional.pad(t, (0, 0, 576 - 540, 0))
     left, right = pad(left), pad(right)
     want = M.psmnet_forward(sd, left, right, 192)
-    for precision in ("fp16x2", "fp32"):
+    for precision, features in (("fp16x2", "fp32"), ("fp16x2", "umma"), ("fp32", "fp32")):
         net = S.PSMNet(192, precision=precision)
         net.load_state_dict(sd, strict=True)
         net = net.cuda().eval()
-        net.feature_mode = "fp32"
+        net.feature_mode = features          # 'umma': the SPP extractor on the split tcgen05 kernel too (the model's default on fp16x2)
         with torch.no_grad():
             disp = net(left.cuda(), right.cuda()).cpu()
         assert disp.shape == (1, 1, 576, 960)
         epe = (disp - want).abs().mean().item()
-        print(f"PSMNet 576x960 D=192 {precision}: EPE vs oracle {epe:.3e} px")
-        assert epe < 1e-3
+        print(f"PSMNet 576x960 D=192 {precision} (features {features}): EPE vs oracle {epe:.3e} px")
+        # hot path alone (identical features): the fp32 bar.  With the 2-D extractor on tcgen05 as well the whole model measures
+        # 8.1e-3 px here (8.0e-4 px at the 256x256 fixture): every stage of the extractor is at 2-5e-6 of its output scale
+        # (tools/debug_psm_features.py), but the SPP branches -- BatchNorm after a 64x64 average pool, whose input sits at the
+        # running mean -- amplify that to 7e-5 of the feature scale.  Reported, and bounded by the 16-bit bar.
+        assert epe < (1e-3 if features == "fp32" else 1e-2)
         del net
         torch.cuda.empty_cache()
+
+
+def test_raft_stereo_update_block_full_shape():
+    """BASELINE config 4 (512x1024, 32 iterations): the update block on tcgen05 (exact fp16x2 format, CUDA-graph replay) against
+    the torch / cuDNN update block in true fp32 on the same inputs and the same (exact torch) encoders."""
+    import stereo_toolbox_b200 as S
+    from stereo_toolbox_b200.synth import synth_pair, synth_state_dict
+    net = S.RAFTStereo()
+    net.load_state_dict(synth_state_dict(net.state_dict(), 0), strict=True)
+    net = net.cuda().eval()
+    left, right = (t.cuda() for t in synth_pair(1, 512, 1024, seed=4, shift=9))
+    with torch.no_grad():
+        net.update_mode = "torch"
+        want = net(left, right, iters=32)
+        net.update_mode, net.cuda_graph = "auto", True
+        got = net(left, right, iters=32)
+    epe = (got - want).abs().mean().item()
+    print(f"RAFT-Stereo 512x1024 x32: update block on tcgen05 vs torch fp32: {epe:.3e} px (|disp| mean {want.abs().mean().item():.1f})")
+    assert got.shape == (1, 1, 512, 1024) and epe < 2e-3      # the untrained recurrence amplifies last-bit differences over 32 iterations
 
 
 def test_raft_corr_and_lookup_full_shape():
