@@ -189,10 +189,17 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
     extern __shared__ __align__(16) float sm[];
     const int E = (D + 3) >> 2, D4 = E * 4, RP = D4 + V2_TW;
     constexpr int NR = 16 * CPG;
-    float* Ls = sm;                                   // [NR][32]
-    float* Rs = sm + NR * V2_TW;                      // [NR][RP]   x <-> ww = w0 - D4 + x
+    // Channels-last sources: the 16 groups of a pass are contiguous in a voxel's row, so consecutive lanes of the staging loop
+    // take consecutive GROUPS of one voxel (8 lines per warp load instead of 32: ncu counted as many LSU wavefronts for these
+    // scattered 16-byte loads as for all shared-memory traffic).  The staged rows are then channel-major (row = c*16 + group)
+    // with a pitch of +4 floats, so that the 16 lanes of a voxel scatter to 8 different banks.
+    constexpr int LPIT = CLSRC ? V2_TW + 4 : V2_TW;   // pitch of the left rows
+    const int RPIT = CLSRC ? RP + 4 : RP;             // pitch of the right rows
+#define VROW(ol, c) (CLSRC ? (c) * 16 + (ol) : (ol) * CPG + (c))
+    float* Ls = sm;                                   // [NR][LPIT]
+    float* Rs = sm + NR * LPIT;                       // [NR][RPIT]   x <-> ww = w0 - D4 + x
     constexpr int OP = SPLIT ? 17 : 9;                // words per voxel in the output tile (+1 pad)
-    uint32_t* Os = reinterpret_cast<uint32_t*>(Rs + (size_t)NR * RP);   // [V2_DP][32][OP] packed channel pairs (SPLIT: 8 hi words, 8 lo words)
+    uint32_t* Os = reinterpret_cast<uint32_t*>(Rs + (size_t)NR * RPIT);   // [V2_DP][32][OP] packed channel pairs (SPLIT: 8 hi words, 8 lo words)
     const int w0 = blockIdx.x * V2_TW, h = blockIdx.y, b = blockIdx.z;
     const size_t plane = (size_t)H * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -211,18 +218,19 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
             // one 16-byte load = the 8 channels of one correlation group at one voxel; scattered (as fp32) to the 8 source
             // rows of that group.  Loads of a batch are issued before the first store.
             static_assert(!CLSRC || CPG == 8, "channels-last sources: 8 channels per group");
+            constexpr int VB = SPLIT ? 2 : 4;       // loads in flight per thread (split rows need two 16-byte loads each: 4 spilled)
             const int span = V2_TW + RP, total = 16 * span;
-            for (int i0 = threadIdx.x; i0 < total; i0 += 256 * 4) {
-                uint4 q[4], ql[SPLIT ? 4 : 1];
-                int kind_[4];
+            for (int i0 = threadIdx.x; i0 < total; i0 += 256 * VB) {
+                uint4 q[VB], ql[SPLIT ? VB : 1];
+                int kind_[VB];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < VB; ++u) {
                     const int i = i0 + u * 256;
                     q[u] = make_uint4(0, 0, 0, 0);
                     if (SPLIT) ql[SPLIT ? u : 0] = make_uint4(0, 0, 0, 0);
                     kind_[u] = -1;
                     if (i >= total) continue;
-                    const int ol = i / span, x = i - ol * span, o = oc0 + ol;
+                    const int x = i >> 4, ol = i & 15, o = oc0 + ol;          // group fastest: a voxel's 16 groups are contiguous
                     const bool isL = x < V2_TW;
                     const int ww = isL ? w0 + x : w0 - D4 + (x - V2_TW);
                     const bool ok = ww >= 0 && ww < W;
@@ -252,13 +260,13 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < VB; ++u) {
                     const int i = i0 + u * 256;
                     if (kind_[u] < 0) continue;
-                    const int ol = i / span, x = i - ol * span;
+                    const int x = i >> 4, ol = i & 15;
                     const bool isL = x < V2_TW;
-                    float* dst = isL ? Ls + (size_t)(ol * CPG) * V2_TW + x : Rs + (size_t)(ol * CPG) * RP + (x - V2_TW);
-                    const int pitch = isL ? V2_TW : RP;
+                    float* dst = isL ? Ls + (size_t)VROW(ol, 0) * LPIT + x : Rs + (size_t)VROW(ol, 0) * RPIT + (x - V2_TW);
+                    const int pitch = (isL ? LPIT : RPIT) * (CLSRC ? 16 : 1);          // distance between the rows of channel c and c + 1
                     if (kind_[u] == 0) {
                         float v[8];
                         unpack8(q[u], f16, v);
@@ -291,20 +299,20 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
             if (vec) {
                 if (lsrc && lane < 8) {
                     const int ww = w0 + 4 * lane;
-                    vcl_cp16(Ls + r * V2_TW + 4 * lane, lsrc + (ww < W ? ww : 0), ww < W);
+                    vcl_cp16(Ls + r * LPIT + 4 * lane, lsrc + (ww < W ? ww : 0), ww < W);
                 }
                 if (rsrc)
                     for (int x4 = lane; x4 < (RP >> 2); x4 += 32) {
                         const int ww = w0 - D4 + 4 * x4;
                         const bool ok = ww >= 0 && ww < W;
-                        vcl_cp16(Rs + (size_t)r * RP + 4 * x4, rsrc + (ok ? ww : 0), ok);
+                        vcl_cp16(Rs + (size_t)r * RPIT + 4 * x4, rsrc + (ok ? ww : 0), ok);
                     }
             } else {
-                if (lsrc) Ls[r * V2_TW + lane] = (w0 + lane < W) ? __ldg(lsrc + w0 + lane) : 0.f;
+                if (lsrc) Ls[r * LPIT + lane] = (w0 + lane < W) ? __ldg(lsrc + w0 + lane) : 0.f;
                 if (rsrc)
                     for (int x = lane; x < RP; x += 32) {
                         const int ww = w0 - D4 + x;
-                        Rs[(size_t)r * RP + x] = (ww >= 0 && ww < W) ? __ldg(rsrc + ww) : 0.f;
+                        Rs[(size_t)r * RPIT + x] = (ww >= 0 && ww < W) ? __ldg(rsrc + ww) : 0.f;
                     }
             }
         }
@@ -324,7 +332,7 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
 #pragma unroll
                 for (int c = 0; c < CPG; ++c)
                     if (kind[q] == 0)
-                        Lc[q][CACHE_L ? c : 0] = *reinterpret_cast<const float4*>(Ls + ((2 * gp + q) * CPG + c) * V2_TW + 4 * j);
+                        Lc[q][CACHE_L ? c : 0] = *reinterpret_cast<const float4*>(Ls + VROW(2 * gp + q, c) * LPIT + 4 * j);
         }
         for (int d0 = 0; d0 < D; d0 += V2_DP) {
             const int e = (d0 >> 2) + el;
@@ -338,13 +346,13 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
                     for (int dd = 0; dd < 4; ++dd)
 #pragma unroll
                         for (int ww = 0; ww < 4; ++ww) acc[q][dd][ww] = 0.f;
-                    const int rbase = (2 * gp + q) * CPG;
+                    const int og = 2 * gp + q;               // output channel (group) inside the pass
                     if (kind[q] == 0) {
 #pragma unroll
                         for (int c = 0; c < CPG; ++c) {
                             const float4 l4 = CACHE_L ? Lc[q][CACHE_L ? c : 0]
-                                                      : *reinterpret_cast<const float4*>(Ls + (rbase + c) * V2_TW + 4 * j);
-                            const float* rr = Rs + (size_t)(rbase + c) * RP + x0;
+                                                      : *reinterpret_cast<const float4*>(Ls + VROW(og, c) * LPIT + 4 * j);
+                            const float* rr = Rs + (size_t)VROW(og, c) * RPIT + x0;
                             const float4 ra = *reinterpret_cast<const float4*>(rr);
                             const float4 rb = *reinterpret_cast<const float4*>(rr + 4);
                             const float v[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
@@ -359,7 +367,7 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
 #pragma unroll
                             for (int ww = 0; ww < 4; ++ww) acc[q][dd][ww] *= inv;
                     } else if (kind[q] == 1) {
-                        const float4 l4 = *reinterpret_cast<const float4*>(Ls + rbase * V2_TW + 4 * j);
+                        const float4 l4 = *reinterpret_cast<const float4*>(Ls + VROW(og, 0) * LPIT + 4 * j);
                         const float l[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
                         for (int dd = 0; dd < 4; ++dd)
@@ -367,7 +375,7 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
                             for (int ww = 0; ww < 4; ++ww)
                                 acc[q][dd][ww] = (mask_left && (w0 + 4 * j + ww) < (4 * e + dd)) ? 0.f : l[ww];
                     } else if (kind[q] == 2) {
-                        const float* rr = Rs + (size_t)rbase * RP + x0;
+                        const float* rr = Rs + (size_t)VROW(og, 0) * RPIT + x0;
                         const float4 ra = *reinterpret_cast<const float4*>(rr);
                         const float4 rb = *reinterpret_cast<const float4*>(rr + 4);
                         const float v[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
@@ -427,6 +435,7 @@ volume_cl2_kernel(const float* __restrict__ gl, const float* __restrict__ gr, co
         }
     }
 }
+#undef VROW
 
 // NCDHW fp32 -> NDHWC bf16 and back (layout boundary of the tensor-core path; used by tests and by
 // models that enter / leave the path with reference-layout tensors)
@@ -604,7 +613,7 @@ extern "C" int stb_volume_cl16_from_cl16(const void* const* feats, const int* fe
     if (H > 65535 || B > 65535) return STB_E_BADARG;
     const int E = (D + 3) / 4, RP = 4 * E + V2_TW;
     const bool split = f16 == 2;             // sources and volume operand-split fp16; feat_ch / cat_c / Ct_pad stay LOGICAL channel counts
-    const size_t smem2 = (size_t)16 * 8 * (V2_TW + RP) * sizeof(float) + (size_t)V2_DP * V2_TW * (split ? 17 : 9) * sizeof(uint32_t);
+    const size_t smem2 = (size_t)16 * 8 * (V2_TW + 4 + RP + 4) * sizeof(float) + (size_t)V2_DP * V2_TW * (split ? 17 : 9) * sizeof(uint32_t);
     if (smem2 > 200 * 1024) return STB_E_SMEM;
     dim3 grid2(stb_ceil_div(W, V2_TW), H, B);
     if (split) {
@@ -612,9 +621,19 @@ extern "C" int stb_volume_cl16_from_cl16(const void* const* feats, const int* fe
             if (feat_ch[i] % 16) return STB_E_UNSUPPORTED;
         if (Cc > 0 && cat_c % 16) return STB_E_UNSUPPORTED;
         cs.cat_c = 2 * cat_c;                // storage elements per voxel
-        cudaFuncSetAttribute(volume_cl2_kernel<8, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        volume_cl2_kernel<8, true, true, true><<<grid2, 256, smem2, (cudaStream_t)stream>>>(nullptr, nullptr, nullptr, nullptr, (uint16_t*)vol,
-                                                                                          8 * G, G, Cc, H, W, D, Ct_pad, mask_left, 1, cs);
+        // CACHE_L keeps the left values of a thread's two channels in 64 registers over the depth passes: with the split epilogue's
+        // extra live values the kernel then spills 160 bytes per thread at its 128-register cap; STB_VOLUME_CACHEL selects
+        // the register-resident variant (measured: 1.73 -> 1.48 ms per batch-8 step without it, profiles/bench_r02_progress.md)
+        static const bool cache_l = getenv("STB_VOLUME_CACHEL") ? atoi(getenv("STB_VOLUME_CACHEL")) != 0 : false;
+        if (cache_l) {
+            cudaFuncSetAttribute(volume_cl2_kernel<8, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            volume_cl2_kernel<8, true, true, true><<<grid2, 256, smem2, (cudaStream_t)stream>>>(nullptr, nullptr, nullptr, nullptr, (uint16_t*)vol,
+                                                                                              8 * G, G, Cc, H, W, D, Ct_pad, mask_left, 1, cs);
+        } else {
+            cudaFuncSetAttribute(volume_cl2_kernel<8, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            volume_cl2_kernel<8, false, true, true><<<grid2, 256, smem2, (cudaStream_t)stream>>>(nullptr, nullptr, nullptr, nullptr, (uint16_t*)vol,
+                                                                                               8 * G, G, Cc, H, W, D, Ct_pad, mask_left, 1, cs);
+        }
         STB_CHECK_LAUNCH();
         return STB_OK;
     }
