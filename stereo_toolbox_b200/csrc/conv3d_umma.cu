@@ -375,7 +375,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #ifdef STB_NO_CSPLIT
         const bool csplit_i = false;
 #else
-        const bool csplit_i = (LV == 1 || LV == 2) && a.nM == 1 && a.cblocks != 8 && a.Cn >= 64;
+        const bool csplit_i = ((LV == 1 || LV == 2) && a.nM == 1 && a.cblocks != 8 && a.Cn >= 64) || LV == 8;
 #endif
         const int n_grp = (a.nM * (a.cblocks == 8 ? 8 : 1) >= 2 || csplit_i) ? 2 : 1;
         for (int i = 0; i < a.R; ++i) { mbar_init(&plane_full[i], 1); mbar_init(&plane_empty[i], 2 * ncl); }
@@ -543,10 +543,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         constexpr int item_step = 2, cblk0 = 0, cblk_step = 32;
 #else
         const bool csplit = (LV == 1 || LV == 2) && items == 1 && a.Cn >= 64;
-        const int item0 = csplit ? 0 : egroup, item_step = csplit ? 1 : 2;
+        const int item0 = (csplit || LV == 8) ? 0 : egroup, item_step = csplit ? 1 : 2;
         const int cblk0 = csplit ? 32 * egroup : 0, cblk_step = csplit ? 64 : 32;
 #endif
-        const bool active = egroup < ((items >= 2 || csplit) ? 2 : 1);
+        const bool active = egroup < ((items >= 2 || csplit || LV == 8) ? 2 : 1);
         const size_t ostride_w = (size_t)a.Cout_total;
         constexpr int f16 = F16 ? 1 : 0;
         constexpr size_t K16 = SPLIT ? 2 : 1;       // 16-bit storage elements per logical channel
@@ -556,8 +556,11 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         float sh0[32];                              // folded-BN shift of the first 32 channels stays in registers
 #pragma unroll
         for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + cout_off + i) : 0.f;
+        float sh16[16];                             // LEAN 8: this group's 16 channels
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sh16[i] = (LV == 8 && a.shift) ? __ldg(a.shift + cout_off + 16 * egroup + i) : 0.f;
         const float oscale = SPLIT ? a.oscale : 1.f;
-        const int merge = (LV == 2 || LV == 4) ? 3 : (LV ? 1 : a.merge), Cn = a.Cn, nM = a.nM;
+        const int merge = (LV == 2 || LV == 4 || LV == 8) ? 3 : (LV ? 1 : a.merge), Cn = a.Cn, nM = a.nM;
         uint32_t ground = 0;                        // accumulator round counter over all items (same order as the issuer)
         // The memory-heavy flavours (transposed convs: 8 output blocks per M-tile, each with a residual row to read; K-split
         // passes reading their fp32 partial sums) were bound by the LATENCY of those loads: a block loads, waits, computes,
@@ -652,6 +655,43 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     store16v<F16, SPLIT>(f, reinterpret_cast<uint16_t*>(a.out) + off * K16);
                 }
                 continue;
+              }
+              if (LV == 8) {
+                // kw-merged conv, ONE 32-channel M-tile per round (the 2-D layers on split storage: extractor 128-channel layers in
+                // 32-channel slices, the update block's convs): the round's single item is split by COLUMNS -- group g takes
+                // channels [16g, 16g + 16), one whole (hi, lo) storage block -- instead of leaving the second group idle; these
+                // layers have a third of the taps per output of a 3-D conv, so the epilogue bounds them.
+                const int q = q4 * 32 + lane;
+                const int jh_l = q / TWP, jw_l = q % TWP;
+                const int jh = jh0 + jh_l, jw = jw0 + jw_l;
+                const int od = s + cl.od0;
+                const bool inb = (jh_l < a.TH) && (jw_l < a.TW) && (jh < a.nclass_h) && (jw < a.nclass_w) && (od < a.Do) && jh < a.Ho && jw < a.Wo;
+                const size_t eoff = ((((size_t)b * a.Do + od) * a.Ho + jh) * a.Wo + jw) * ostride_w + cout_off + 16 * egroup;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * Cn * 3 + 16 * egroup);
+                uint32_t v0[16], v1[16], v2[16];
+                __syncwarp();
+                tmem_ld_32x32_x16(taddr, v0);
+                tmem_ld_32x32_x16(taddr + (uint32_t)Cn, v1);
+                tmem_ld_32x32_x16(taddr + (uint32_t)(2 * Cn), v2);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                const int ms = a.merge_step;
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float r = __uint_as_float(v0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), ms) +
+                                    __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2 * ms);
+                    f[i] = SPLIT ? fmaf(r, oscale, sh16[i]) : r + sh16[i];
+                }
+                if (inb) {
+                    if (a.residual) add_residual16<F16, SPLIT>(f, reinterpret_cast<const uint16_t*>(a.residual) + eoff * K16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = stb_act(f[i], ACT);
+                    store16v<F16, SPLIT>(f, reinterpret_cast<uint16_t*>(a.out) + eoff * K16);
+                }
+                break;                                  // the round's only item
               }
               if (LV == 5) {
                 // Merged transposed conv, the two w-parity classes of one (d,h) parity handled together: a thread's two output
@@ -969,6 +1009,12 @@ int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& t
     }
     if (a.merge == 2) return launch_one_impl<ACT, F16, 7, SPLIT>(grid, smem, st, tx, tw, a);      // stride-2 pair merge (generic + 2-block realignment)
     if (lean && a.cblocks == 8 && a.merge == 1) return launch_one_impl<ACT, F16, 3, SPLIT>(grid, smem, st, tx, tw, a);
+    // one 32-channel M-tile per round: epilogue split by columns across the two groups (LEAN 8; STB_UMMA_CSPLIT16=0 -> LEAN 2)
+    static const bool csplit16 = getenv("STB_UMMA_CSPLIT16") == nullptr || atoi(getenv("STB_UMMA_CSPLIT16")) != 0;
+    if constexpr (SPLIT) {
+        if (csplit16 && lean && a.cblocks == 3 && a.merge == 3 && a.nM == 1 && a.Cn == 32 && a.nclass == 1 && a.out_stride == 1 && (a.kdepth > 0 || a.sd_in == 1 && a.dzmin == 0 && a.dzmax == 0))
+            return launch_one_impl<ACT, F16, 8, SPLIT>(grid, smem, st, tx, tw, a);
+    }
     if (lean && a.cblocks == 3 && a.merge == 3) return launch_one_impl<ACT, F16, 2, SPLIT>(grid, smem, st, tx, tw, a);
     if (lean && a.cblocks == 1 && a.merge == 1) return launch_one_impl<ACT, F16, 1, SPLIT>(grid, smem, st, tx, tw, a);
     return launch_one_impl<ACT, F16, 0, SPLIT>(grid, smem, st, tx, tw, a);
