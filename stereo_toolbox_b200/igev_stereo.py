@@ -380,7 +380,10 @@ class IGEVStereo(IGEVCostVolume):
             image1 = 2 * (image1 * std + mean) - 1.0
             image2 = 2 * (image2 * std + mean) - 1.0
 
-        if getattr(self, "channels_last", False):                   # opt-in: NHWC torch glue (raft_stereo.glue_channels_last)
+        # NHWC torch glue (raft_stereo.glue_channels_last): cuDNN's tensor-core kernels are NHWC, with NCHW tensors torch brackets
+        # the 2-D convs with layout transposes (measured at 1152x1920: 152 -> 140 ms).  Default for CUDA inference (where the
+        # forward runs on the folded shadow copy, so the model's own parameters keep their layout); ``channels_last = False`` opts out
+        if getattr(self, "channels_last", image1.is_cuda and not self.training and not torch.is_grad_enabled()):
             image1, image2 = glue_channels_last(self, image1, image2)
 
         # ---- torch glue: 2-D features (igev_stereo.py:195-204)
