@@ -38,6 +38,49 @@ patch_dw_kernel(const float* __restrict__ x, const float* __restrict__ wgt, floa
     out[base + (size_t)h * W + w] = acc;
 }
 
+// Four consecutive outputs per thread (W % 4 == 0, dilation <= 4): per filter row one aligned 16-byte load left, centre and
+// right of the thread's quad covers every tap -- 9 loads for 4 outputs instead of 36 (the scalar kernel was LSU-bound at
+// 1.55 TB/s: ACVNet 1152x1920 D=256 spent 7.2 ms in its four launches).  Same products, same summation order per output.
+template <int DIL>
+__global__ void __launch_bounds__(256)
+patch_dw_v4_kernel(const float* __restrict__ x, const float* __restrict__ wgt, float* __restrict__ out,
+                   int Ctot, int c0, int C, int D, int H, int W, size_t total4) {
+    constexpr int dil = DIL;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int W4 = W >> 2;
+    const int w = (int)(i % W4) << 2;
+    size_t r = i / W4;
+    const int h = (int)(r % H); r /= H;
+    const int d = (int)(r % D); r /= D;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    const size_t base = (((size_t)b * Ctot + c0 + c) * D + d) * H * (size_t)W;
+    const float* wc = wgt + c * 9;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int hh = h + (a - 1) * dil;
+        if (hh < 0 || hh >= H) continue;
+        const float* row = x + base + (size_t)hh * W + w;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 lf = w >= 4 ? __ldg(reinterpret_cast<const float4*>(row - 4)) : z;
+        const float4 ce = __ldg(reinterpret_cast<const float4*>(row));
+        const float4 rt = w + 4 < W ? __ldg(reinterpret_cast<const float4*>(row + 4)) : z;
+        const float v[12] = {lf.x, lf.y, lf.z, lf.w, ce.x, ce.y, ce.z, ce.w, rt.x, rt.y, rt.z, rt.w};
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) {
+            const float wv = __ldg(wc + a * 3 + bb);
+            const int off = 4 + (bb - 1) * dil;            // compile time; dil <= 4: 0 <= off + j <= 11
+            // (columns outside the image are zero in v: the left / right quads are zero-filled, and an out-of-range column can
+            //  only occur there)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fmaf(wv, v[off + j], acc[j]);
+        }
+    }
+    *reinterpret_cast<float4*>(out + base + (size_t)h * W + w) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
 // ---------------------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float ld_f(const T* p);
 template <> __device__ __forceinline__ float ld_f<float>(const float* p) { return __ldg(p); }
@@ -155,6 +198,19 @@ extern "C" int stb_patch_dw_f32(const float* x, const float* weight, float* out,
         return STB_E_BADARG;
     if (x == out) return STB_E_BADARG;          // taps read neighbours: not an in-place operation
     const size_t total = (size_t)B * C * D * H * W;
+    if ((W & 3) == 0 && dilation <= 4 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+        const size_t total4 = total >> 2;
+        const unsigned g = (unsigned)((total4 + 255) / 256);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (dilation) {
+            case 1: patch_dw_v4_kernel<1><<<g, 256, 0, st>>>(x, weight, out, c_total, c_off, C, D, H, W, total4); break;
+            case 2: patch_dw_v4_kernel<2><<<g, 256, 0, st>>>(x, weight, out, c_total, c_off, C, D, H, W, total4); break;
+            case 3: patch_dw_v4_kernel<3><<<g, 256, 0, st>>>(x, weight, out, c_total, c_off, C, D, H, W, total4); break;
+            default: patch_dw_v4_kernel<4><<<g, 256, 0, st>>>(x, weight, out, c_total, c_off, C, D, H, W, total4); break;
+        }
+        STB_CHECK_LAUNCH();
+        return STB_OK;
+    }
     patch_dw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, weight, out, c_total, c_off, C,
                                                                                       D, H, W, dilation, total);
     STB_CHECK_LAUNCH();

@@ -251,3 +251,17 @@ def test_convex_upsampling_kernels_golden_and_oracle():
     close(ops.convex_upsample(cu(flow), cu(mask), 4), R.convex_upsample(flow, mask, 4), 1e-5, 2e-5)
     flow, mask = rnd(6, 1, 1, 9, 11), rnd(7, 1, 36, 9, 11)
     close(ops.convex_upsample(cu(flow), cu(mask), 2), R.convex_upsample(flow, mask, 2), 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("W", [16, 20, 18])
+def test_patch_dw_vectorised_and_scalar_kernels_agree_with_torch(W):
+    """W % 4 == 0 takes the four-outputs-per-thread kernel (one aligned 16-byte load left / centre / right of the quad per
+    filter row), anything else the scalar one: both against torch's depthwise dilated Conv3d, incl. images narrower than a
+    dilated tap reach."""
+    from stereo_toolbox_b200 import ops
+    g = torch.Generator().manual_seed(W)
+    x = torch.randn(2, 6, 3, 7, W, generator=g)
+    for dil in (1, 2, 3):
+        wt = torch.randn(6, 1, 1, 3, 3, generator=g)
+        want = torch.nn.functional.conv3d(x, wt, padding=(0, dil, dil), dilation=(1, dil, dil), groups=6)
+        close(ops.patch_dw(cu(x), cu(wt), dil), want, 1e-5, 1e-6)
