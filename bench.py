@@ -381,6 +381,29 @@ def extras(line, a, sd, net, left, right, ref, precision):
         except Exception as e:
             line["raft_stereo"] = {"error": repr(e)[:200]}
         torch.cuda.empty_cache()
+        # BASELINE config 5: ACVNet and IGEV-Stereo at 1152x1920 (1920x1080 padded), D=256, batch 1, whole models through the
+        # drop-in API on the exact tensor-core format (ACVNet: default precision; IGEV: stage on fp16x2, update block on tcgen05)
+        try:
+            from stereo_toolbox_b200.synth import synth_pair, synth_state_dict
+            l5, r5 = (t.cuda() for t in synth_pair(1, 1152, 1920, seed=4, shift=9))
+            cfg5 = {}
+            for name, ctor, fwd in (("acvnet", lambda: S.ACVNet(256), {}),
+                                    ("igev_stereo", lambda: S.IGEVStereo({"max_disp": 256}, precision="fp16x2"), {"iters": 32})):
+                m5 = ctor()
+                m5.load_state_dict(synth_state_dict(m5.state_dict(), 0), strict=True)
+                m5 = m5.cuda().eval()
+                ms = timed_steps(lambda: m5(l5, r5, **fwd), 3, 2)
+                out5 = m5(l5, r5, **fwd)
+                cfg5[name] = {"ms_per_forward": ms, "maps_per_s": 1e3 / ms, "precision": getattr(m5, "precision", None),
+                              "finite": bool(torch.isfinite(out5.float()).all().item()), **fwd}
+                del m5, out5
+                torch.cuda.empty_cache()
+            cfg5["config"] = "BASELINE config 5: 1920x1080 zero-padded to 1920x1152, D=256, batch 1, synthetic weights"
+            line["config5"] = cfg5
+            del l5, r5
+        except Exception as e:
+            line["config5"] = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
         if a.workload == "kitti":
             try:
                 select_workload("sceneflow")

@@ -1,7 +1,8 @@
 """PCWNet_GC / CFNet: the exact tensor-core path ('fp16x2') against the fp32 CUDA-core path of the same drop-in model at the
 KITTI shape (the fp32 path is pinned to the reference by the golden fixtures)."""
-import sys, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import golden_state
 import stereo_toolbox_b200 as S
 from stereo_toolbox_b200.synth import synth_pair
