@@ -136,3 +136,78 @@ def test_plan_tables_reproduce_the_convolution(cin, cout, k, stride, pad, tr, sp
     tol = 4e-6 if split else 2e-3            # single fp16: the weights are rounded to 11 bits
     assert got.shape == want.shape
     assert (got - want).abs().max().item() < tol * scale
+
+
+# ----------------------------------------------------------------------------------------------- 2-D plans (features_umma.Conv2dPlan)
+def emulate2d(plan, x: torch.Tensor) -> torch.Tensor:
+    """x [N,Cin,H,W] fp64 -> [N,Cout,Ho,Wo] fp64 following a Conv2dPlan's tables the way csrc/conv3d_umma.cu reads them: dz = 0
+    everywhere, or (K-chunks along the pseudo-depth axis) dz = the chunk a tap reads; kw-merged taps carry three column
+    blocks realigned by ``dil`` lanes each; stride-2 taps read (h, w)-parity sub-tiles."""
+    N, Cin, H, W = x.shape
+    split = plan.flags & 64
+    xcl = x.permute(0, 2, 3, 1).float()
+    ct = plan.cin
+    xcl = torch.nn.functional.pad(xcl, (0, ct - Cin))
+    xs = (split_pack(xcl) if split else xcl.half()).double()                 # [N,H,W,Cst]
+    Ho, Wo = plan.out_size(H), plan.out_size(W)
+    kc, nk, kdepth = plan.kc, plan.nk, plan.kdepth
+    cpad = plan.wt.shape[-2]
+    wt = plan.wt.double()                                                    # kdepth: [nk][k*k][cpad][kc] (chunk-major tiles); else [k*k][nk][cpad][kc]
+    if kdepth:
+        wt = wt.reshape(-1, cpad, kc)
+    dz, dh, dw, sub, widx = (list(a) for a in plan.c)
+    s, dil = plan.in_stride, plan.dil
+    jh, jw = torch.arange(Ho), torch.arange(Wo)
+    out = torch.zeros(N, Ho, Wo, cpad, dtype=torch.float64)
+    for kp in range(1 if kdepth else nk):
+        for t in range(plan.ntaps):
+            chunk = dz[t] if kdepth else kp
+            for j in range(3 if plan.merge else 1):
+                hh = (jh + plan.in_off) * s + (sub[t] >> 1) + s * dh[t]
+                ww = (jw + plan.in_off) * s + (sub[t] & 1) + s * (dw[t] + j * dil)
+                hv, wv = (hh >= 0) & (hh < H), (ww >= 0) & (ww < W)
+                a = xs[:, hh.clamp(0, H - 1)][:, :, ww.clamp(0, W - 1)][..., chunk * kc:(chunk + 1) * kc]
+                a = a * (hv.view(1, -1, 1, 1) & wv.view(1, 1, -1, 1))
+                w = wt[widx[t] + j] if kdepth else wt[widx[t] + j, kp]
+                out += torch.einsum("bhwk,ok->bhwo", _join(a, split), _join(w, split))
+    wexp = (plan.flags >> 16) & 127
+    out = out * (2.0 ** -wexp)
+    if plan.shift is not None:
+        out[..., :plan.cout] += plan.shift.double()
+    return out[..., :plan.cout].permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dil,split,bias,hw", [
+    (32, 32, 3, 1, 1, True, False, (9, 11)),         # kw-merged
+    (128, 128, 3, 1, 2, True, False, (10, 9)),       # dilated, four K-chunks in TMEM, merged taps 2 lanes apart
+    (32, 64, 3, 2, 1, True, False, (10, 12)),        # stride 2: parity sub-tiles
+    (32, 64, 1, 2, 1, True, False, (9, 11)),         # 1x1 stride-2 shortcut
+    (16, 64, 7, 1, 1, True, True, (8, 9)),           # 7x7 with bias (the update block's flow conv)
+    (64, 64, 3, 1, 1, False, False, (7, 8)),         # single fp16
+])
+def test_conv2d_plan_tables_reproduce_the_convolution(cin, cout, k, stride, dil, split, bias, hw):
+    from stereo_toolbox_b200.features_umma import Conv2dPlan
+    g = torch.Generator().manual_seed(cin + cout + k + stride + dil)
+    pad = dil if k == 3 else (k // 2 if k > 1 else 0)
+    conv = nn.Conv2d(cin, cout, k, stride, pad, dil, bias=bias)
+    bn = None if bias else nn.BatchNorm2d(cout)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (cin * k * k)) ** 0.5)
+        if bias:
+            conv.bias.copy_(0.1 * torch.randn(cout, generator=g))
+        else:
+            bn.weight.copy_(0.75 + 0.5 * torch.rand(cout, generator=g)); bn.bias.copy_(0.1 * torch.randn(cout, generator=g))
+            bn.running_mean.copy_(0.1 * torch.randn(cout, generator=g)); bn.running_var.copy_(0.5 + torch.rand(cout, generator=g))
+            bn.eval()
+    plan = Conv2dPlan(conv, bn, cin, torch.float16, split)
+    x = torch.randn(2, cin, *hw, generator=g)
+    if not split:
+        x = x.half().float()
+    got = emulate2d(plan, x.double())
+    with torch.no_grad():
+        want = conv.double()(x.double())
+        if bn is not None:
+            want = bn.double()(want)
+    scale = max(1.0, want.abs().max().item())
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < (4e-6 if split else 2e-3) * scale
