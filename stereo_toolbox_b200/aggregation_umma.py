@@ -27,6 +27,7 @@ KWMERGE = os.environ.get("STB_UMMA_KWMERGE", "1") == "1"          # merge the 3 
 DECONV_MERGE = os.environ.get("STB_UMMA_DECONV_MERGE", "1") == "1"  # transposed conv: 8 parity classes in one accumulator round
 PAIRMERGE = os.environ.get("STB_UMMA_PAIRMERGE", "1") == "1"        # stride-2 convs: kw = 0 / 2 taps as one N = 2*Cn MMA
 KDEPTH3D = os.environ.get("STB_UMMA_KDEPTH3D", "1") == "1"          # 3-D layers: K-chunks accumulated in TMEM when the weights fit
+KGROUP = os.environ.get("STB_UMMA_KGROUP", "1") == "1"              # ... and G < nk chunks per K-split pass when all of them do not
 SIMT_STRIDE2 = os.environ.get("STB_UMMA_SIMT_STRIDE2", "0") == "1"   # keep strided convs on the CUDA-core companion
 TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp16x2": torch.float16}
 SPLIT_FLAG = 64      # stb_conv3d_umma flags bit6: operand-split fp16 ("fp16x2")
@@ -287,32 +288,42 @@ class UmmaPlan:
         # partial (64->32 s2T on fp16x2: two passes, 1.47 GB of partial written and read back per call).  Needs the weight tiles
         # of ALL chunks of an output-channel slice resident next to a ring of (window*nk + 1) chunk slots; the merged
         # transposed conv may narrow the slice to 16 channels (own epilogue instantiation, LEAN 6).
-        self.kdepth = False
-        if KDEPTH3D and self.split and nk > 1 and in_stride == 1 and len(tb) == 1 and len(dz) * nk <= 64:
+        # When all nk chunks do not fit (128->64 s2T: 4 chunks = 221 KB of weight tiles per 16-channel slice), G < nk chunks per
+        # pass do: nk / G K-split passes instead of nk (flags bits 11..13; the merged transposed conv's 16-channel-slice epilogue
+        # reads / writes the fp32 partial, LEAN 9).
+        self.kdepth, self.kgroup = False, 0
+        if KDEPTH3D and self.split and nk > 1 and in_stride == 1 and len(tb) == 1:
             window = max(dz) - min(dz) + 1
             slot = (4 + max(dh)) * 32 * kc * 2
-            ring = (window * nk + 1) * slot
-            fits = lambda cn: 3072 + ((self.nwtiles * nk * cn * kc * 2 + 1023) & ~1023) + 1024 + ring <= 227 * 1024
+            fits = lambda cn, g: (3072 + ((self.nwtiles * g * cn * kc * 2 + 1023) & ~1023) + 1024 + (window * g + 1) * slot
+                                  <= 227 * 1024)
             cblocks = 8 if self.deconv_merge else (3 if self.merge else 1)
-            ok_full = cpad * cblocks <= 256 and fits(cpad)
-            ok_16 = self.deconv_merge and cpad % 16 == 0 and cout == cpad and fits(16)
-            if window * nk <= 6 and (ok_full or ok_16):
+            def group_ok(g):
+                if window * g > 6 or len(dz) * g > 64:
+                    return False
+                ok_full = cpad * cblocks <= 256 and fits(cpad, g)
+                ok_16 = self.deconv_merge and cpad % 16 == 0 and cout == cpad and fits(16, g)
+                # fewer passes than chunks: only where the sliced transposed-conv epilogue takes the partial (ok_16 alone)
+                return (ok_full or ok_16) if g == nk else (KGROUP and ok_16 and not ok_full and g <= 7)
+            G = next((g for g in range(nk, 1, -1) if nk % g == 0 and group_ok(g)), 0)
+            if G:
                 n0 = len(dz)
+                self.kgroup = G if G < nk else 0
                 base = (list(dz), list(dh), list(dw), list(sub), list(widx), None if nblk is None else list(nblk),
                         None if cls0 is None else list(cls0))
                 dz, dh, dw, sub, widx = [], [], [], [], []
                 nblk = None if base[5] is None else []
                 cls0 = None if base[6] is None else []
-                for c in range(nk):
+                for c in range(G):
                     for t in range(n0):
-                        dz.append(base[0][t] * nk + c); dh.append(base[1][t]); dw.append(base[2][t]); sub.append(base[3][t])
+                        dz.append(base[0][t] * G + c); dh.append(base[1][t]); dw.append(base[2][t]); sub.append(base[3][t])
                         widx.append(c * self.nwtiles + base[4][t])
                         if nblk is not None:
                             nblk.append(base[5][t]); cls0.append(base[6][t])
                 te = [len(dz)]
-                # tiles ordered [chunk][tile]: runs of consecutive tiles (merged taps) stay contiguous
+                # tiles ordered [chunk][tile] (= [pass][chunk in pass][tile]): runs of consecutive tiles (merged taps) stay contiguous
                 self.wt = tiles.view(self.nwtiles, cpad, nk, kc).permute(2, 0, 1, 3).contiguous().to(self.dtype)
-                self.nwtiles *= nk
+                self.nwtiles *= G               # tiles of ONE pass
                 self.kdepth = True
         self.ntaps, self.nclass = len(dz), len(tb)
         self.c_dz, self.c_dh, self.c_dw, self.c_sub, self.c_widx = _iarr(dz), _iarr(dh), _iarr(dw), _iarr(sub), _iarr(widx)
@@ -442,7 +453,7 @@ class UmmaBackend:
         with self.prof.bracket(fam, fl, by, detail=detail):
             if plan.umma_ok:
                 nsteps, nh, nw = (Di, Hi, Wi) if plan.tr else (Do, Ho, Wo)
-                ws = self._workspace(B * Do * Ho * Wo * cout_t, x.device) if (plan.nk > 1 and not plan.kdepth) else None
+                ws = self._workspace(B * Do * Ho * Wo * cout_t, x.device) if (plan.nk > 1 and (not plan.kdepth or plan.kgroup)) else None
                 _lib.call("stb_conv3d_umma", _p(x), _p(plan.wt), _p(plan.shift), _p(residual), _p(out), _p(ws),
                           self.f16, B, Cst, plan.kc, Di, Hi, Wi, cout_t, plan.cout, Do, Ho, Wo, plan.ntaps,
                           plan.c_dz, plan.c_dh, plan.c_dw, plan.c_sub, plan.c_widx, plan.c_nblk, plan.c_cls0,
@@ -450,7 +461,7 @@ class UmmaBackend:
                           plan.c_tb, plan.c_te, plan.c_od0, plan.c_oh0, plan.c_ow0, plan.in_stride, plan.out_stride,
                           nsteps, nh, nw, plan.in_off, plan.in_off, ACT[act], int(out_fp32),
                           BO_MODE | (ES_VARIANT << 1) | (4 if plan.merge else 0) | (8 if plan.deconv_merge else 0)
-                          | (32 if plan.kdepth else 0) | (128 if plan.pair_merge else 0) | ((SPLIT_FLAG | (plan.wexp << 16)) if self.split else 0),
+                          | (32 if plan.kdepth else 0) | (plan.kgroup << 11) | (128 if plan.pair_merge else 0) | ((SPLIT_FLAG | (plan.wexp << 16)) if self.split else 0),
                           self.dchunk, _stream())
             else:
                 assert not self.split

@@ -331,7 +331,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                    const __grid_constant__ UArgs a) {
     // LV: the epilogue flavour; LEAN 7 = the generic flavour (0) plus the stride-2 pair merge, kept out of LEAN 0 so that the generic
     // instantiation (K-split passes of the big layers) does not carry it
-    constexpr int LV = LEAN == 7 ? 0 : LEAN;
+    // LEAN 9 = flavour 6 (merged transposed conv on 16-channel slices) as a K-split pass: adds the fp32 partial of the earlier
+    // passes and / or writes its own (grouped pseudo-depth chunks, flags bits 11..13 of the host entry)
+    constexpr int LV = LEAN == 7 ? 0 : (LEAN == 9 ? 6 : LEAN);
+    constexpr bool PIO = LEAN == 9;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
     // [0,2048): barriers + tmem holder + issue tables ; then weights ; then plane ring
@@ -415,9 +418,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         // 2-D conv with Cin = kdepth K-chunks: pseudo-plane P = image*kdepth + chunk; the taps of chunk c
                         // carry dz = c, so all chunks accumulate in TMEM inside one launch (no fp32 workspace round trip)
                         const int P = u.p_first + n, img = (P + 64 * a.kdepth) / a.kdepth - 64, chunk = P - img * a.kdepth;   // floor division: 3-D planes may be negative (padding)
-                        if (ncl == 1) tma_load_5d(dst, &tm_x, &plane_full[slot], chunk * (a.ROWB >> 1), iw0, ih0, img, u.b);
+                        if (ncl == 1) tma_load_5d(dst, &tm_x, &plane_full[slot], a.cin_off + chunk * (a.ROWB >> 1), iw0, ih0, img, u.b);
                         else if (gbox % (uint32_t)ncl == crank)
-                            tma_load_5d_mc(dst, &tm_x, &plane_full[slot], chunk * (a.ROWB >> 1), iw0, ih0, img, u.b, cmask);
+                            tma_load_5d_mc(dst, &tm_x, &plane_full[slot], a.cin_off + chunk * (a.ROWB >> 1), iw0, ih0, img, u.b, cmask);
                         ++gbox;
                     } else {
                         for (int sb = 0; sb < a.nsub; ++sb, ++gbox) {     // sub-tile sb = (h parity, w parity) for stride 2
@@ -551,8 +554,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         constexpr int f16 = F16 ? 1 : 0;
         constexpr size_t K16 = SPLIT ? 2 : 1;       // 16-bit storage elements per logical channel
         const bool full32 = LV || (a.Cn_valid & 31) == 0;  // every 32-column block is complete: vector path
-        const float* const partial = LV ? nullptr : a.partial;
-        const bool out_fp32 = !LV && a.out_fp32;
+        const float* const partial = (LV && !PIO) ? nullptr : a.partial;
+        const bool out_fp32 = (!LV || PIO) && a.out_fp32;
         float sh0[32];                              // folded-BN shift of the first 32 channels stays in registers
 #pragma unroll
         for (int i = 0; i < 32; ++i) sh0[i] = (a.shift && i < a.Cn_valid) ? __ldg(a.shift + cout_off + i) : 0.f;
@@ -599,6 +602,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         if (LV == 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + ostride_w * K16));
                     }
                     if (partial) asm volatile("prefetch.global.L2 [%0];" ::"l"(partial + eoff));
+                    if (PIO && partial) asm volatile("prefetch.global.L2 [%0];" ::"l"(partial + eoff + ostride_w));   // the pair's second voxel
                 }
             }
         };
@@ -647,8 +651,35 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     if (!(h ? in1 : in0)) continue;
                     const size_t off = eoff + (size_t)h * ostride_w;
                     float f[16];
+                    if constexpr (PIO) {
+                        // K-split pass: (+ the fp32 partial of the earlier passes) and, unless it is the last pass, the raw sums back
+                        // out as the next pass's partial -- 16 floats = two whole sectors per voxel
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = SPLIT ? fmaf(__uint_as_float(v[h * 16 + i]), oscale, sh0[i]) : __uint_as_float(v[h * 16 + i]) + sh0[i];
+                        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[h * 16 + i]);
+                        if (partial) {
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                uint32_t pv[8];
+                                ldg256(partial + off + i * 8, pv);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[i * 8 + j] += __uint_as_float(pv[j]);
+                            }
+                        }
+                        if (out_fp32) {
+                            float* op = reinterpret_cast<float*>(a.out) + off;
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                stg256(op + i * 8, __float_as_uint(f[i * 8]), __float_as_uint(f[i * 8 + 1]), __float_as_uint(f[i * 8 + 2]),
+                                       __float_as_uint(f[i * 8 + 3]), __float_as_uint(f[i * 8 + 4]), __float_as_uint(f[i * 8 + 5]),
+                                       __float_as_uint(f[i * 8 + 6]), __float_as_uint(f[i * 8 + 7]));
+                            continue;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] = SPLIT ? fmaf(f[i], oscale, sh0[i]) : f[i] + sh0[i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] = SPLIT ? fmaf(__uint_as_float(v[h * 16 + i]), oscale, sh0[i]) : __uint_as_float(v[h * 16 + i]) + sh0[i];
+                    }
                     if (a.residual) add_residual16<F16, SPLIT>(f, reinterpret_cast<const uint16_t*>(a.residual) + off * K16);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = stb_act(f[i], ACT);
@@ -1007,6 +1038,12 @@ int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& t
             a.Cn_valid == 16 && a.shift)
             return launch_one_impl<ACT, F16, 6, SPLIT>(grid, smem, st, tx, tw, a);
     }
+    // ... and the same flavour as a K-split pass (grouped pseudo-depth chunks: fp32 partial in and / or out, LEAN 9)
+    if constexpr ((ACT == STB_ACT_RELU || ACT == STB_ACT_NONE) && SPLIT) {
+        if (!a.debug && !g_trace_armed && (a.partial || a.out_fp32) && a.kdepth > 0 && a.cblocks == 8 && a.merge == 1 && a.Cn == 16 &&
+            a.Cn_valid == 16 && (a.Cout_total & 7) == 0)
+            return launch_one_impl<ACT, F16, 9, SPLIT>(grid, smem, st, tx, tw, a);
+    }
     if (a.merge == 2) return launch_one_impl<ACT, F16, 7, SPLIT>(grid, smem, st, tx, tw, a);      // stride-2 pair merge (generic + 2-block realignment)
     if (lean && a.cblocks == 8 && a.merge == 1) return launch_one_impl<ACT, F16, 3, SPLIT>(grid, smem, st, tx, tw, a);
     // one 32-channel M-tile per round: epilogue split by columns across the two groups (LEAN 8; STB_UMMA_CSPLIT16=0 -> LEAN 2)
@@ -1072,11 +1109,16 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     // numbers; the epilogue multiplies the accumulators by 2^-s.
     const float wscale_inv = ldexpf(1.f, -((flags >> 16) & 127));
     if (split && (!f16 || (KC != 32 && KC != 64) || (Cout_total % 16 && !out_fp32))) return STB_E_UNSUPPORTED;
-    const int kdepth = (flags & 32) ? Cin / KC : 0; // flags bit5: K-chunks along a pseudo-depth axis, accumulated in TMEM (2-D convs)
+    // flags bits 11..13: chunks per pass G of the pseudo-depth form (0 = all of them, one pass).  With 0 < G < Cin/KC the layer
+    // runs as (Cin/KC)/G K-split passes of G chunks each: pass p reads the chunks [p*G, p*G + G) (taps carry dz*G + chunk-in-pass,
+    // weight tiles ordered [pass][chunk in pass][tile], nwtiles = tiles of ONE pass) and chains through the fp32 partial.
+    const int kgroup = (flags >> 11) & 7;
+    const int kdepth = (flags & 32) ? (kgroup ? kgroup : Cin / KC) : 0; // flags bit5: K-chunks along a pseudo-depth axis, accumulated in TMEM (2-D convs)
     // (3-D layers too: pseudo-plane = depth*kdepth + chunk, taps carry dz*kdepth + chunk; unit input stride only)
     if (kdepth && in_stride != 1) return STB_E_UNSUPPORTED;
+    if (kgroup && (!(flags & 32) || (Cin / KC) % kgroup)) return STB_E_BADARG;
     const bool kdepth2d = kdepth && (flags & 16);
-    const int nk = kdepth ? 1 : Cin / KC;          // K-split passes
+    const int nk = kdepth ? (Cin / KC) / kdepth : Cin / KC;          // K-split passes
     if (nk > 1 && !ws) return STB_E_BADARG;        // needs the fp32 partial workspace [B,Do,Ho,Wo,Cout_total]
     UArgs a;
     memset(&a, 0, sizeof(a));
@@ -1270,7 +1312,7 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
         if (!umma_host::make_tmap(&tm_x, cudt, 5, const_cast<void*>(x), dims, str, box, cusw, es, promo)) return STB_E_DRIVER;
     }
     a.w_rows = Cpad;
-    a.w_tile_stride = nk;
+    a.w_tile_stride = kdepth ? 1 : nk;       // pseudo-depth form: the tiles of a pass are contiguous ([pass][chunk][tile])
     a.nwtiles = nwtiles;
     const long long ncta = (long long)B * a.nchunks * a.tiles_h * a.tiles_w;
     if (ncta > 2147483647LL) return STB_E_BADARG;
@@ -1286,8 +1328,8 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.debug = debug;
     for (int kp = 0; kp < nk; ++kp) {
         const bool last = kp == nk - 1;
-        a.cin_off = kp * KC;
-        a.w_kc_off = kp;
+        a.cin_off = kp * KC * (kdepth ? kdepth : 1);
+        a.w_kc_off = kdepth ? kp * nwtiles : kp;
         a.partial = kp > 0 ? ws : nullptr;
         a.out = last ? out : (void*)ws;
         a.out_fp32 = last ? out_fp32 : 1;

@@ -83,6 +83,9 @@ SCONVS = [
     (64, 64, 1, 1, 0, False, "none", True, (4, 10, 33)),        # k1, both K-chunks accumulated in TMEM (3-D pseudo-depth chunks)
     (64, 32, 3, 2, 1, True, "relu", True, (9, 13, 70)),         # merged transposed conv on 16-channel slices, several tiles / depth chunks
     (64, 32, 3, 2, 1, True, "none", False, (3, 5, 17)),         # same plan through the generic epilogue
+    (128, 64, 3, 2, 1, True, "relu", True, (7, 11, 40)),        # 4 K-chunks as two passes of two chunks (fp32 partial between them), 4 slices
+    (192, 32, 3, 2, 1, True, "relu", True, (3, 5, 17)),         # three passes: the middle one reads AND writes the partial
+    (128, 64, 3, 2, 1, True, "mish", False, (3, 5, 17)),        # last pass through the generic epilogue (PCWNet's Mish)
 ]
 
 

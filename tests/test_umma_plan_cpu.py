@@ -21,9 +21,11 @@ def emulate(plan: UmmaPlan, x: torch.Tensor) -> torch.Tensor:
     Do, Ho, Wo = plan.out_size(Di), plan.out_size(Hi), plan.out_size(Wi)
     nk, kc = plan.nk, plan.kc
     kdepth = getattr(plan, "kdepth", False)
-    wt = plan.wt.double()                  # [tile][nk][cpad][kc]  or (kdepth)  [nk*tile][1..][cpad][kc] flattened below
+    G = (getattr(plan, "kgroup", 0) or nk) if kdepth else 1     # chunks per pass of the pseudo-depth form (kgroup: fewer than nk)
+    npass = nk // G if kdepth else nk
+    wt = plan.wt.double()                  # [tile][nk][cpad][kc]  or (kdepth)  [pass][chunk in pass][tile][cpad][kc] flattened below
     if kdepth:
-        wt = wt.reshape(plan.nwtiles, 1, plan.cpad, kc)
+        wt = wt.reshape(npass * plan.nwtiles, 1, plan.cpad, kc)
     ntaps = plan.ntaps
     dz, dh, dw, sub, widx = (list(plan.c_dz), list(plan.c_dh), list(plan.c_dw), list(plan.c_sub), list(plan.c_widx))
     merge = 3 if plan.merge else 1
@@ -34,14 +36,14 @@ def emulate(plan: UmmaPlan, x: torch.Tensor) -> torch.Tensor:
     od0, oh0, ow0 = list(plan.c_od0), list(plan.c_oh0), list(plan.c_ow0)
     in_s, out_s = plan.in_stride, plan.out_stride
     nsteps, nh, nw = (Di, Hi, Wi) if plan.tr else (Do, Ho, Wo)
-    sd_in = nk if kdepth else in_s
+    sd_in = G if kdepth else in_s
     out = torch.zeros(B, Do, Ho, Wo, plan.cpad, dtype=torch.float64)
     cb = 8 if plan.deconv_merge else (2 if getattr(plan, "pair_merge", False) else merge)
 
     def gather(P, chunk_k, hh, ww):
         """rows of the A operand: input storage elements [B, nh, nw, kc] at plane P, positions (hh[jh], ww[jw])."""
         if kdepth:
-            depth, chunk = P // nk, P % nk        # floor division
+            depth, chunk = P // G, chunk_k * G + P % G        # floor division; chunk_k = the pass
         else:
             depth, chunk = P, chunk_k
         a = torch.zeros(B, nh, nw, kc, dtype=torch.float64)
@@ -56,7 +58,7 @@ def emulate(plan: UmmaPlan, x: torch.Tensor) -> torch.Tensor:
     for s in range(nsteps):
         for c in range(len(tb)):
             acc = torch.zeros(B, nh, nw, cb, plan.cpad, dtype=torch.float64)
-            for kp in range(1 if kdepth else nk):
+            for kp in range(npass):
                 for t in range(tb[c], te[c]):
                     P = s * sd_in + dz[t]
                     for j in range(nblk[t]):
@@ -64,7 +66,7 @@ def emulate(plan: UmmaPlan, x: torch.Tensor) -> torch.Tensor:
                         hh = (jh + plan.in_off) * in_s + (sub[t] >> 1) + in_s * dh[t]
                         ww = (jw + plan.in_off) * in_s + (sub[t] & 1) + in_s * (dw[t] + shift_w)
                         a = gather(P, kp, hh, ww)
-                        w = wt[widx[t] + j, 0 if kdepth else kp]                      # [cpad][kc]
+                        w = wt[kp * plan.nwtiles + widx[t] + j, 0] if kdepth else wt[widx[t] + j, kp]       # [cpad][kc]
                         # (split: hi*hi + hi*lo + lo*hi = the product of the joined values minus lo*lo, below fp32 rounding)
                         blk = 0 if lane_merged else cls0[t] + j
                         contrib = torch.einsum("bhwk,ok->bhwo", _join(a, split), _join(w, split))
@@ -98,7 +100,7 @@ CASES = [
     (64, 32, 3, 1, 1, False, True, (3, 4, 5), False),        # K-split passes
     (64, 64, 1, 1, 0, False, True, (2, 4, 5), True),         # k1: both K-chunks in TMEM
     (64, 32, 3, 2, 1, True, True, (2, 3, 4), True),          # merged transposed conv, chunks along the pseudo-depth axis
-    (128, 64, 3, 2, 1, True, True, (2, 2, 3), False),
+    (128, 64, 3, 2, 1, True, True, (2, 2, 3), True),         # ... 4 chunks as two passes of two (kgroup)
     (32, 64, 3, 2, 1, False, True, (4, 6, 6), False),        # strided conv: parity sub-tiles, kw 0 / 2 pair-merged
     (64, 128, 3, 2, 1, False, True, (5, 7, 9), False),
     (32, 64, 3, 2, 1, False, False, (4, 6, 8), False),
@@ -126,6 +128,8 @@ def test_plan_tables_reproduce_the_convolution(cin, cout, k, stride, pad, tr, sp
     plan = UmmaPlan(conv, bn, cin, torch.float16, split)
     assert plan.umma_ok
     assert bool(getattr(plan, "kdepth", False)) == want_kdepth
+    if (cin, cout, tr, split) == (128, 64, True, True):
+        assert plan.kgroup == 2 and plan.nk == 4
     x = torch.randn(1, cin, D, H, W, generator=g)
     if not split:
         x = x.half().float()
