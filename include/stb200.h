@@ -143,7 +143,11 @@ int stb_cl16_to_ncdhw(const void* src, float* dst, int f16, int B, int C, long l
  * (flags bit3) 8 parity-class blocks drained in one round.  All index arrays are HOST arrays.
  * flags: bit0 UMMA base-offset convention, bit1 TMA element-stride box convention (both settled by
  * csrc/probe/umma_probe.cu), bit2 kw-merge, bit3 merged transposed conv, bit4 2-D convolution (dz = 0,
- * the image index is the depth axis and is never strided), bits 8-10 dilation of the kw-merged taps (0 = 1);
+ * the image index is the depth axis and is never strided), bits 8-10 dilation of the kw-merged taps (0 = 1),
+ * bit5 K-chunks along a pseudo-depth axis (plane P = depth*G + chunk, taps carry dz*G + chunk: the chunks
+ * accumulate in TMEM; weight tiles ordered [pass][chunk][tile], nwtiles = tiles of one pass) with bits 11-13 = G
+ * chunks per pass (0 = all Cin/KC chunks in one pass; else (Cin/KC)/G passes chained through ws), bit6 operand-split
+ * fp16 storage ("fp16x2"; bits 16-22: exponent of the weight pre-scale), bit7 stride-2 kw = 0 / 2 pair merge;
  * dchunk: depth steps per CTA
  * (0 = auto).  Cout_valid = real (unpadded) channels. */
 int stb_conv3d_umma(const void* x, const void* wt, const float* shift, const void* residual, void* out,
