@@ -147,7 +147,8 @@ int stb_cl16_to_ncdhw(const void* src, float* dst, int f16, int B, int C, long l
  * bit5 K-chunks along a pseudo-depth axis (plane P = depth*G + chunk, taps carry dz*G + chunk: the chunks
  * accumulate in TMEM; weight tiles ordered [pass][chunk][tile], nwtiles = tiles of one pass) with bits 11-13 = G
  * chunks per pass (0 = all Cin/KC chunks in one pass; else (Cin/KC)/G passes chained through ws), bit6 operand-split
- * fp16 storage ("fp16x2"; bits 16-22: exponent of the weight pre-scale), bit7 stride-2 kw = 0 / 2 pair merge;
+ * fp16 storage ("fp16x2"; bits 16-22: exponent of the weight pre-scale), bit7 stride-2 kw = 0 / 2 pair merge,
+ * bit14 (with bit3) the 8 parity-class column blocks hold the classes 0,1,3,2,6,7,5,4 (Gray order) instead of 0..7;
  * dchunk: depth steps per CTA
  * (0 = auto).  Cout_valid = real (unpadded) channels. */
 int stb_conv3d_umma(const void* x, const void* wt, const float* shift, const void* residual, void* out,

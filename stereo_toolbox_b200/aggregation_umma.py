@@ -27,6 +27,7 @@ KWMERGE = os.environ.get("STB_UMMA_KWMERGE", "1") == "1"          # merge the 3 
 DECONV_MERGE = os.environ.get("STB_UMMA_DECONV_MERGE", "1") == "1"  # transposed conv: 8 parity classes in one accumulator round
 PAIRMERGE = os.environ.get("STB_UMMA_PAIRMERGE", "1") == "1"        # stride-2 convs: kw = 0 / 2 taps as one N = 2*Cn MMA
 KDEPTH3D = os.environ.get("STB_UMMA_KDEPTH3D", "1") == "1"          # 3-D layers: K-chunks accumulated in TMEM when the weights fit
+GRAYCLS = os.environ.get("STB_UMMA_GRAYCLS", "1") == "1"            # merged transposed convs on 16-channel slices: Gray order of the class blocks
 KGROUP = os.environ.get("STB_UMMA_KGROUP", "1") == "1"              # ... and G < nk chunks per K-split pass when all of them do not
 SIMT_STRIDE2 = os.environ.get("STB_UMMA_SIMT_STRIDE2", "0") == "1"   # keep strided convs on the CUDA-core companion
 TORCH_DT = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp16x2": torch.float16}
@@ -158,6 +159,24 @@ class UmmaPlan:
             return False
         nk = cin_st // kc
         cpad = (cout + 15) // 16 * 16
+
+        def kdepth_group(ntaps_, ntiles_, window_, maxdh_, cblocks_, deconv_):
+            """(G, full): G K-chunks per pass accumulate in TMEM along the pseudo-depth axis (0: classic K-split passes), on the
+            whole padded channel count (full) or on 16-channel output slices."""
+            if not (KDEPTH3D and self.split and nk > 1 and in_stride == 1):
+                return 0, False
+            slot = (4 + maxdh_) * 32 * kc * 2
+            fits = lambda cn, g: (3072 + ((ntiles_ * g * cn * kc * 2 + 1023) & ~1023) + 1024 + (window_ * g + 1) * slot
+                                  <= 227 * 1024)
+            for g in range(nk, 1, -1):
+                if nk % g or window_ * g > 6 or ntaps_ * g > 64:
+                    continue
+                ok_full = cpad * cblocks_ <= 256 and fits(cpad, g)
+                ok_16 = deconv_ and cpad % 16 == 0 and cout == cpad and fits(16, g)
+                # fewer passes than chunks: only where the sliced transposed-conv epilogue takes the partial (ok_16 alone)
+                if (ok_full or ok_16) if g == nk else (KGROUP and ok_16 and not ok_full and g <= 7):
+                    return g, ok_full
+            return 0, False
         if bnp is not None:
             gamma, beta, mean, var = [t.detach().float() for t in bnp]
             scale = gamma / torch.sqrt(var + eps)
@@ -170,6 +189,7 @@ class UmmaPlan:
         nblk, cls0 = None, None
         tile_src = list(range(k ** 3))          # which (kd,kh,kw) weight matrix each staged tile holds
         self.deconv_merge = False
+        self.class_order = list(range(8))       # merged transposed conv: class (cd*4 + ch*2 + cw) held by column block p
         if tr and DECONV_MERGE and stride == 2:
             # ---- merged transposed conv: one accumulator round holds all 8 output-parity classes (column block
             # c = cd*4+ch*2+cw).  A shift (a,b,c) of the input tile feeds every class whose per-dim tap set contains it;
@@ -185,23 +205,39 @@ class UmmaPlan:
                         if sh[0] in kof[cd] and sh[1] in kof[ch] and sh[2] in kof[cw]]
             shifts.sort(key=lambda sh: -len(classes_of(sh)))                      # the all-classes shift first
             if len(classes_of(shifts[0])) == 8:
-                tile_src, nblk, cls0 = [], [], []
+                def build_merged(order):
+                    # column block p holds class order[p]; a run of consecutive POSITIONS is one MMA
+                    nonlocal tile_src, nblk, cls0
+                    pos = {c: p_ for p_, c in enumerate(order)}
+                    tile_src, nblk, cls0 = [], [], []
+                    del dz[:], dh[:], dw[:], sub[:], widx[:]
+                    for sh in shifts:
+                        ps = sorted(pos[c] for c in classes_of(sh))
+                        i = 0
+                        while i < len(ps):
+                            j = i
+                            while j + 1 < len(ps) and ps[j + 1] == ps[j] + 1:
+                                j += 1
+                            dz.append(sh[0]); dh.append(sh[1] - mn); dw.append(sh[2] - mn); sub.append(0)
+                            widx.append(len(tile_src)); nblk.append(j - i + 1); cls0.append(ps[i])
+                            for p_ in ps[i:j + 1]:
+                                c = order[p_]
+                                cd, ch, cw = c >> 2, (c >> 1) & 1, c & 1
+                                tile_src.append(flat(kof[cd][sh[0]], kof[ch][sh[1]], kof[cw][sh[2]]))
+                            i = j + 1
+                    self.class_order = list(order)
                 tb.append(0)
-                for sh in shifts:
-                    cl = classes_of(sh)
-                    i = 0
-                    while i < len(cl):
-                        j = i
-                        while j + 1 < len(cl) and cl[j + 1] == cl[j] + 1:
-                            j += 1
-                        dz.append(sh[0]); dh.append(sh[1] - mn); dw.append(sh[2] - mn); sub.append(0)
-                        widx.append(len(tile_src)); nblk.append(j - i + 1); cls0.append(cl[i])
-                        for c in cl[i:j + 1]:
-                            cd, ch, cw = c >> 2, (c >> 1) & 1, c & 1
-                            tile_src.append(flat(kof[cd][sh[0]], kof[ch][sh[1]], kof[cw][sh[2]]))
-                        i = j + 1
+                build_merged(list(range(8)))
                 te.append(len(dz)); od0.append(0); oh0.append(0); ow0.append(0)
                 self.in_off, self.out_stride, self.merge, self.deconv_merge = mn, stride, False, True
+                # Gray order of the class blocks (flags bit14; w-pairs stay adjacent, every other pair reversed): the class sets of
+                # the 8 input shifts fall into 10 runs instead of 14, i.e. 10 MMAs per K-step instead of 14.  Taken where the MMAs
+                # are narrow (16-channel slices of the pseudo-depth form: ncu shows the tensor pipe's operand fetch 70 % busy at
+                # 22 % math) and the epilogue flavours read the order (generic, LEAN 6 / 9)
+                g_, full_ = kdepth_group(len(dz), len(tile_src), max(dz) - min(dz) + 1, max(dh), 8, True)
+                if GRAYCLS and g_ and not full_:
+                    build_merged([0, 1, 3, 2, 6, 7, 5, 4])
+                    te[-1] = len(dz)
         # ---- stride-2 pair merge: the kw = 0 and kw = 2 taps read the SAME w-parity sub-tile one position apart, so they run as
         # one MMA against the two contiguous weight tiles (N = 2*Cn instead of two N = Cn MMAs: the N = 32 MMAs of these layers
         # are operand-bandwidth bound, 40 clk for 16 clk of math) and the epilogue realigns block 1 by one lane (flags bit7)
@@ -292,20 +328,9 @@ class UmmaPlan:
         # pass do: nk / G K-split passes instead of nk (flags bits 11..13; the merged transposed conv's 16-channel-slice epilogue
         # reads / writes the fp32 partial, LEAN 9).
         self.kdepth, self.kgroup = False, 0
-        if KDEPTH3D and self.split and nk > 1 and in_stride == 1 and len(tb) == 1:
-            window = max(dz) - min(dz) + 1
-            slot = (4 + max(dh)) * 32 * kc * 2
-            fits = lambda cn, g: (3072 + ((self.nwtiles * g * cn * kc * 2 + 1023) & ~1023) + 1024 + (window * g + 1) * slot
-                                  <= 227 * 1024)
-            cblocks = 8 if self.deconv_merge else (3 if self.merge else 1)
-            def group_ok(g):
-                if window * g > 6 or len(dz) * g > 64:
-                    return False
-                ok_full = cpad * cblocks <= 256 and fits(cpad, g)
-                ok_16 = self.deconv_merge and cpad % 16 == 0 and cout == cpad and fits(16, g)
-                # fewer passes than chunks: only where the sliced transposed-conv epilogue takes the partial (ok_16 alone)
-                return (ok_full or ok_16) if g == nk else (KGROUP and ok_16 and not ok_full and g <= 7)
-            G = next((g for g in range(nk, 1, -1) if nk % g == 0 and group_ok(g)), 0)
+        if len(tb) == 1:
+            G, _ = kdepth_group(len(dz), self.nwtiles, max(dz) - min(dz) + 1, max(dh),
+                                8 if self.deconv_merge else (3 if self.merge else 1), self.deconv_merge)
             if G:
                 n0 = len(dz)
                 self.kgroup = G if G < nk else 0
@@ -461,7 +486,7 @@ class UmmaBackend:
                           plan.c_tb, plan.c_te, plan.c_od0, plan.c_oh0, plan.c_ow0, plan.in_stride, plan.out_stride,
                           nsteps, nh, nw, plan.in_off, plan.in_off, ACT[act], int(out_fp32),
                           BO_MODE | (ES_VARIANT << 1) | (4 if plan.merge else 0) | (8 if plan.deconv_merge else 0)
-                          | (32 if plan.kdepth else 0) | (plan.kgroup << 11) | (128 if plan.pair_merge else 0) | ((SPLIT_FLAG | (plan.wexp << 16)) if self.split else 0),
+                          | (32 if plan.kdepth else 0) | (plan.kgroup << 11) | ((1 << 14) if plan.class_order != list(range(8)) else 0) | (128 if plan.pair_merge else 0) | ((SPLIT_FLAG | (plan.wexp << 16)) if self.split else 0),
                           self.dchunk, _stream())
             else:
                 assert not self.split

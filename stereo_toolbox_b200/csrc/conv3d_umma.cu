@@ -75,6 +75,7 @@ struct UArgs {
     int cblocks;                     // accumulator column blocks (of Cn) per M-tile: 1, 3 (kw-merge) or 8 (merged transposed conv)
     int nclass_h, nclass_w;          // class output extents per step in h/w (positions)
     uint32_t plane_bytes, chunk_bytes, wtile_bytes, w_bytes_total, tmem_cols;
+    uint32_t cperm;                  // merged transposed conv: output-parity class (cd*4 + ch*2 + cw) held by column block p = (cperm >> 4p) & 7
     int kdepth;                      // > 0: the K-chunks of the input lie along a PSEUDO-depth axis (plane P = image*kdepth + chunk), 2-D convs
     uint32_t desc_hi;                // high word of every smem descriptor (SBO = 8 rows, version, swizzle mode)
     uint32_t smem_base;              // shared-window address of the 1024-aligned dynamic smem base (queried once per kernel instance)
@@ -580,10 +581,11 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     m = item >> 2;
                     const int pb = item & 3, q = 128 * m + q4 * 32 + lane;
                     jh_l = q / TWP; jw_l = q % TWP;
-                    od = s * a.out_stride + (pb >> 1); oh = (u.jh0 + jh_l) * 2 + (pb & 1); ow = (u.jw0 + jw_l) * 2;
+                    const int pc = (int)((a.cperm >> (8 * pb)) & 7u);          // class of the pair's first column block
+                    od = s * a.out_stride + (pc >> 2); oh = (u.jh0 + jh_l) * 2 + ((pc >> 1) & 1); ow = (u.jw0 + jw_l) * 2;
                 } else {
                     m = nblk_e == 8 ? (item >> 3) : item;
-                    const int blk = nblk_e == 8 ? (item & 7) : 0, q = 128 * m + q4 * 32 + lane;
+                    const int blk = nblk_e == 8 ? (int)((a.cperm >> (4 * (item & 7))) & 7u) : 0, q = 128 * m + q4 * 32 + lane;
                     jh_l = q / TWP; jw_l = q % TWP;
                     od = s * a.out_stride + (nblk_e == 8 ? (blk >> 2) : cl.od0);
                     oh = (u.jh0 + jh_l) * a.out_stride + (nblk_e == 8 ? ((blk >> 1) & 1) : cl.oh0);
@@ -627,13 +629,17 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 // the weights of a 16-channel slice fit next to the chunk ring, no K-split pass through an fp32 partial).  The two
                 // w-parity classes of one (d,h) parity are ADJACENT 16-column blocks, so one 32-column TMEM read holds the thread's
                 // two output voxels (ow, ow + 1) x 16 channels; each is one whole 16-channel storage block of its voxel row.
+                // (class order of the column blocks = a.cperm: the two blocks of a pair always share (cd, ch); with the Gray order
+                //  -- fewer, wider MMAs, see the host plan -- every other pair holds cw = 1 FIRST: `rev`)
                 const int m = item >> 2, pb = item & 3;
-                const int od = s * a.out_stride + (pb >> 1);
+                const int pc = (int)((a.cperm >> (8 * pb)) & 7u);
+                const bool rev = pc & 1;
+                const int od = s * a.out_stride + (pc >> 2);
                 const int q = 128 * m + q4 * 32 + lane;
                 const int jh_l = q / TWP, jw_l = q % TWP;
                 const int jh = jh0 + jh_l, jw = jw0 + jw_l;
                 const bool valid = (jh_l < a.TH) && (jw_l < a.TW) && (jh < a.nclass_h) && (jw < a.nclass_w) && (od < a.Do);
-                const int oh = jh * 2 + (pb & 1), ow = jw * 2;
+                const int oh = jh * 2 + ((pc >> 1) & 1), ow = jw * 2;
                 const bool in0 = valid && oh < a.Ho && ow < a.Wo, in1 = in0 && ow + 1 < a.Wo;
                 const size_t eoff = ((((size_t)b * a.Do + od) * a.Ho + oh) * a.Wo + ow) * ostride_w + cout_off;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)((buf * nM + m) * Cn * 8 + pb * 2 * Cn);
@@ -645,6 +651,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                }
+                if (rev) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { const uint32_t t = v[i]; v[i] = v[16 + i]; v[16 + i] = t; }
                 }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -764,9 +774,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 continue;
               }
               {
-                const int m = nblk_e == 8 ? (item >> 3) : item, blk = nblk_e == 8 ? (item & 7) : 0;
-                const int cd = nblk_e == 8 ? (blk >> 2) : cl.od0, chh = nblk_e == 8 ? ((blk >> 1) & 1) : cl.oh0,
-                          cww = nblk_e == 8 ? (blk & 1) : cl.ow0;
+                const int m = nblk_e == 8 ? (item >> 3) : item, blk = nblk_e == 8 ? (item & 7) : 0;      // blk: column-block position
+                const int pcls = (int)((a.cperm >> (4 * blk)) & 7u);                                       // ... and the class it holds
+                const int cd = nblk_e == 8 ? (pcls >> 2) : cl.od0, chh = nblk_e == 8 ? ((pcls >> 1) & 1) : cl.oh0,
+                          cww = nblk_e == 8 ? (pcls & 1) : cl.ow0;
                 const int od = s * a.out_stride + cd;
                 const int q = 128 * m + q4 * 32 + lane;
                 const int jh_l = q / TWP, jw_l = q % TWP;
@@ -1029,7 +1040,7 @@ int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& t
     // merged transposed conv with w-paired stores (LEAN 5; STB_UMMA_T2PAIR=0 falls back to LEAN 3)
     static const bool t2pair = getenv("STB_UMMA_T2PAIR") == nullptr || atoi(getenv("STB_UMMA_T2PAIR")) != 0;
     if constexpr (ACT == STB_ACT_RELU) {
-        if (t2pair && lean && a.cblocks == 8 && a.merge == 1 && a.Cn == 32 && a.shift)
+        if (t2pair && lean && a.cblocks == 8 && a.merge == 1 && a.Cn == 32 && a.shift && a.cperm == 0x76543210u)
             return launch_one_impl<ACT, F16, 5, SPLIT>(grid, smem, st, tx, tw, a);
     }
     // merged transposed conv on 16-channel output slices (all K-chunks in TMEM, see LEAN 6 in the epilogue)
@@ -1045,7 +1056,7 @@ int launch_one(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& t
             return launch_one_impl<ACT, F16, 9, SPLIT>(grid, smem, st, tx, tw, a);
     }
     if (a.merge == 2) return launch_one_impl<ACT, F16, 7, SPLIT>(grid, smem, st, tx, tw, a);      // stride-2 pair merge (generic + 2-block realignment)
-    if (lean && a.cblocks == 8 && a.merge == 1) return launch_one_impl<ACT, F16, 3, SPLIT>(grid, smem, st, tx, tw, a);
+    if (lean && a.cblocks == 8 && a.merge == 1 && a.cperm == 0x76543210u) return launch_one_impl<ACT, F16, 3, SPLIT>(grid, smem, st, tx, tw, a);
     // one 32-channel M-tile per round: epilogue split by columns across the two groups (LEAN 8; STB_UMMA_CSPLIT16=0 -> LEAN 2)
     static const bool csplit16 = getenv("STB_UMMA_CSPLIT16") == nullptr || atoi(getenv("STB_UMMA_CSPLIT16")) != 0;
     if constexpr (SPLIT) {
@@ -1140,6 +1151,9 @@ extern "C" int stb_conv3d_umma(const void* x, const void* wt, const float* shift
     a.nsub = in_stride == 2 ? 4 : 1;
     a.sd_in = kdepth ? kdepth : ((flags & 16) ? 1 : in_stride);     // flags bit4: 2-D convolution, the depth axis (image index) is never strided
     a.kdepth = kdepth;
+    // flags bit14 (merged transposed conv): the 8 parity-class column blocks are in Gray order 0,1,3,2,6,7,5,4 instead of 0..7
+    // (w-pairs stay adjacent; the class sets of the input shifts become 10 runs instead of 14 = 10 MMAs per K-step instead of 14)
+    a.cperm = (flags & (1 << 14)) ? 0x45762310u : 0x76543210u;
     int maxdh = 0, maxdw = 0, dzmin = 127, dzmax = -127;
     // Taps of a class are issued in the order of the plane they read (stable sort by dz): the issuer then consumes
     // planes monotonically and can wait for / hand back each plane individually.

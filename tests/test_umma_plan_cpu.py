@@ -71,8 +71,10 @@ def emulate(plan: UmmaPlan, x: torch.Tensor) -> torch.Tensor:
                         blk = 0 if lane_merged else cls0[t] + j
                         contrib = torch.einsum("bhwk,ok->bhwo", _join(a, split), _join(w, split))
                         acc[:, :, :, blk] += contrib
+            order = getattr(plan, "class_order", list(range(8)))      # column block -> output-parity class (Gray order: flags bit14)
             for blk in range(cb if plan.deconv_merge else 1):
-                cd, ch, cw = ((blk >> 2, (blk >> 1) & 1, blk & 1) if plan.deconv_merge else (od0[c], oh0[c], ow0[c]))
+                pc = order[blk]
+                cd, ch, cw = ((pc >> 2, (pc >> 1) & 1, pc & 1) if plan.deconv_merge else (od0[c], oh0[c], ow0[c]))
                 od = s * out_s + cd
                 if od >= Do:
                     continue
@@ -130,6 +132,10 @@ def test_plan_tables_reproduce_the_convolution(cin, cout, k, stride, pad, tr, sp
     assert bool(getattr(plan, "kdepth", False)) == want_kdepth
     if (cin, cout, tr, split) == (128, 64, True, True):
         assert plan.kgroup == 2 and plan.nk == 4
+    if tr and split and k == 3 and cin >= 64:
+        # 16-channel slices: Gray order of the class blocks, 10 runs per chunk instead of 14; w-pairs stay adjacent
+        assert plan.class_order == [0, 1, 3, 2, 6, 7, 5, 4] and plan.ntaps == 10 * (plan.kgroup or plan.nk)
+        assert all((plan.class_order[2 * p] ^ plan.class_order[2 * p + 1]) == 1 for p in range(4))
     x = torch.randn(1, cin, D, H, W, generator=g)
     if not split:
         x = x.half().float()
